@@ -1,0 +1,68 @@
+#!/usr/bin/env bash
+# Headless build of the UNMODIFIED reference DiffRedMax (externals/DiffHand/core/projects/redmax)
+# as the python module `redmax_py`, from the sources where they lie under /root/reference.
+# Outputs go ONLY into oracle/_ref/ (git-ignored; travels to the GPU box with gpurun).
+# The reference's own CMake build is not used (it requires OpenGL/X11 dev packages that this
+# image lacks); the viewer is replaced by a 6-line stub so Simulation::replay() is a no-op.
+# Test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+# --impl reference legs may load what this script builds.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${REF_ROOT:-/root/reference}"
+C="$REF/externals/DiffHand/core"
+OUT="$HERE/_ref"
+PY="${PYTHON:-python3}"
+EXT="$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')"
+if [ ! -d "$C/projects/redmax" ]; then
+  echo "build_ref: $C not present (GPU box?) - using prebuilt files in $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj" "$OUT/assets"
+cat > "$OUT/defs.h" <<X
+#define GRAPHICS_CODEBASE_SOURCE_DIR "$C"
+#define PROJECT_DIR "$C"
+X
+cat > "$OUT/SimViewerStub.cpp" <<'X'
+#include "SimViewer.h"
+#include "Simulation.h"
+namespace redmax {
+SimViewer::SimViewer(Simulation* sim) : _sim(sim), _timer(nullptr), _keyboard_handler(nullptr) {}
+SimViewer::~SimViewer() {}
+void SimViewer::initialize() {}
+void SimViewer::run() {}
+}
+X
+SRCS="$(find "$C/projects/redmax" -name '*.cpp' ! -name main.cpp ! -name SimViewer.cpp ! -name Test.cpp | sort) \
+ $C/projects/opengl_viewer/src/geometry.cpp $C/projects/opengl_viewer/src/image.cpp $C/projects/opengl_viewer/src/bounding_box.cpp \
+ $C/externals/pugixml/src/pugixml.cpp $C/externals/tiny_obj_loader/tiny_obj_loader.cpp $OUT/SimViewerStub.cpp"
+FLAGS="-O2 -std=c++14 -fPIC -w -DGLEW_STATIC -DGLEW_NO_GLU -DGLFW_INCLUDE_NONE -include $OUT/defs.h \
+ -I$C/projects/redmax -I$C/projects/opengl_viewer/include -I$C/externals/eigen -I$C/externals/glew/include \
+ -I$C/externals/glfw/include/GLFW -I$C/externals/imgui -I$C/externals/stb -I$C/externals/pugixml/src -I$C/externals/tiny_obj_loader \
+ -I$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])') -I$($PY -c 'import pybind11;print(pybind11.get_include())')"
+TARGET="$OUT/redmax_py$EXT"
+PROBE="$OUT/redmax_probe$EXT"
+if [ -f "$TARGET" ] && [ -f "$PROBE" ] && [ "$PROBE" -nt "$HERE/ref_probe.cpp" ] && [ -z "${FORCE:-}" ]; then
+  echo "build_ref: $TARGET and $PROBE already built"
+else
+  if [ ! -f "$OUT/obj/.done" ] || [ -n "${FORCE:-}" ]; then
+    i=0
+    for s in $SRCS; do i=$((i+1)); b="$(basename "$s" .cpp)"; echo "g++ $FLAGS -c $s -o $OUT/obj/${i}_$b.o"; done | xargs -P "$(nproc)" -I{} sh -c "{}"
+    touch "$OUT/obj/.done"
+  fi
+  g++ -shared -o "$TARGET" "$OUT"/obj/*.o -ldl
+  # the probe: our own read-only pybind module, linked with the same reference objects
+  # (minus the reference's python_interface.o, which defines the other module)
+  g++ $FLAGS -c "$HERE/ref_probe.cpp" -o "$OUT/obj/probe.o.tmp"
+  g++ -shared -o "$PROBE" $(ls "$OUT"/obj/*.o | grep -v python_interface) "$OUT/obj/probe.o.tmp" -ldl
+  rm -f "$OUT/obj/probe.o.tmp"
+  echo "build_ref: built $TARGET and $PROBE"
+fi
+# Scene assets the reference binary needs at run time (XML + meshes are data, not source;
+# they live only in the git-ignored _ref directory so the reference arm can run on the GPU box).
+for scene in pusher; do
+  mkdir -p "$OUT/assets/$scene"
+  cp -f "$REF/envs/assets/$scene"/* "$OUT/assets/$scene/"
+done
+# synthetic 32x13 variant named by BASELINE.json (same scene, denser marker grid)
+sed 's/resolution="13 10"/resolution="32 13"/' "$OUT/assets/pusher/pusher.xml" > "$OUT/assets/pusher/pusher_32x13.xml"
+echo "build_ref: assets in $OUT/assets"

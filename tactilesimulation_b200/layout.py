@@ -1,0 +1,155 @@
+"""Packs a :class:`Scene` into the (int32, float64) buffers described by
+``csrc/scene_layout.h``; ``unpack_sizes`` reads the header back."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import scene as S
+
+TS_MAGIC = 0x54533230
+TS_VERSION = 3
+MAXJ, MAXN, MAXCAND = 8, 8, 4
+I_HEADER, D_HEADER = 32, 16
+JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 8
+JD, CD, AD, ED, SD = 48, 4, 12, 4, 16
+
+
+def pack_scene(sc: "S.Scene"):
+    if sc.integrator != "BDF1":
+        raise S.SceneError(f"integrator {sc.integrator} is not supported by the B200 path yet (BDF1 only)")
+    if sc.nj > MAXJ or sc.ndof_r > MAXN:
+        raise S.SceneError(f"scene too large for this build: nj={sc.nj} (max {MAXJ}), ndof_r={sc.ndof_r} (max {MAXN})")
+    if len(sc.sensors) > 1:
+        raise S.SceneError("more than one tactile sensor is not supported by the B200 path yet")
+    for a in sc.actuators:
+        if a["mode"] != S.ACT_FORCE:
+            raise S.SceneError("position-controlled motors are not supported by the B200 path yet")
+    ints = [np.zeros(I_HEADER, dtype=np.int64)]
+    dbls = [np.zeros(D_HEADER, dtype=np.float64)]
+    hdr, dh = ints[0], dbls[0]
+
+    def ioff():
+        return sum(len(a) for a in ints)
+
+    def doff():
+        return sum(len(a) for a in dbls)
+
+    # points pool: only bodies that actually use their sample points
+    pts, pt_off = [], {}
+
+    def points_of(b):
+        if b not in pt_off:
+            pt_off[b] = sum(len(p) for p in pts)
+            pts.append(sc.contact_points[b])
+        return pt_off[b], len(sc.contact_points[b])
+
+    hdr[0:16] = [TS_MAGIC, TS_VERSION, sc.nj, sc.ndof_r, sc.ndof_u, len(sc.end_effectors), sc.n_markers,
+                 len(sc.ground_contacts), len(sc.gp_contacts), len(sc.actuators), len(sc.sensors),
+                 sc.max_iter, sc.max_ls, 0, 0, 0]
+    dh[0] = sc.h
+    dh[1:4] = sc.gravity
+    dh[4] = sc.tol
+    dh[5:8] = sc.E_g[:3, 2]
+    dh[8:11] = sc.E_g[:3, 3]
+
+    hdr[16], hdr[24] = ioff(), doff()
+    ji = np.zeros((sc.nj, JI), dtype=np.int64)
+    jd = np.zeros((sc.nj, JD))
+    for j in range(sc.nj):
+        ji[j, :5] = [sc.jtype[j], sc.parent[j], sc.qoff[j], sc.ndof[j], sc.shape[j]]
+        jd[j, 0:9] = sc.E_pj0[j][:3, :3].reshape(-1)
+        jd[j, 9:12] = sc.E_pj0[j][:3, 3]
+        jd[j, 12:15] = sc.axis0[j]
+        jd[j, 15:18] = sc.axis1[j]
+        jd[j, 18:22] = [sc.damping[j], sc.lim_lo[j], sc.lim_hi[j], sc.lim_k[j]]
+        jd[j, 22:31] = sc.E_ji[j][:3, :3].reshape(-1)
+        jd[j, 31:34] = sc.E_ji[j][:3, 3]
+        jd[j, 34:40] = sc.inertia[j]
+        if sc.shape[j] == S.SH_CUBOID:
+            jd[j, 40:43] = sc.size[j] / 2.0
+        else:
+            jd[j, 40:43] = sc.size[j]
+    ints.append(ji.reshape(-1))
+    dbls.append(jd.reshape(-1))
+
+    hdr[17], hdr[25] = ioff(), doff()
+    gi = np.zeros((len(sc.ground_contacts), GI), dtype=np.int64)
+    gd = np.zeros((len(sc.ground_contacts), CD))
+    for i, g in enumerate(sc.ground_contacts):
+        o, c = points_of(g["body"])
+        gi[i, :3] = [g["body"], o, c]
+        gd[i] = [g["kn"], g["kt"], g["mu"], g["damping"]]
+    ints.append(gi.reshape(-1))
+    dbls.append(gd.reshape(-1))
+
+    hdr[18], hdr[26] = ioff(), doff()
+    pi = np.zeros((len(sc.gp_contacts), PI), dtype=np.int64)
+    pd = np.zeros((len(sc.gp_contacts), CD))
+    for i, f in enumerate(sc.gp_contacts):
+        o, c = points_of(f["body1"])
+        pi[i] = [f["body1"], f["body2"], o, c]
+        pd[i] = [f["kn"], f["kt"], f["mu"], f["damping"]]
+    ints.append(pi.reshape(-1))
+    dbls.append(pd.reshape(-1))
+
+    hdr[19], hdr[27] = ioff(), doff()
+    ai = np.zeros((len(sc.actuators), AI), dtype=np.int64)
+    ad = np.zeros((len(sc.actuators), AD))
+    for i, a in enumerate(sc.actuators):
+        ai[i] = [a["joint"], a["mode"], a["uoff"], a["ndof"]]
+        nd = a["ndof"]
+        ad[i, 0:nd] = a["cmin"]
+        ad[i, 3:3 + nd] = a["cmax"]
+        ad[i, 6:6 + nd] = a["P"]
+        ad[i, 9:9 + nd] = a["D"]
+    ints.append(ai.reshape(-1))
+    dbls.append(ad.reshape(-1))
+
+    hdr[20], hdr[28] = ioff(), doff()
+    ei = np.zeros((len(sc.end_effectors), EI), dtype=np.int64)
+    ed = np.zeros((len(sc.end_effectors), ED))
+    for i, e in enumerate(sc.end_effectors):
+        ei[i, 0] = e["joint"]
+        ed[i, :3] = e["pos"]
+    ints.append(ei.reshape(-1))
+    dbls.append(ed.reshape(-1))
+
+    hdr[21], hdr[29] = ioff(), doff()
+    si = np.zeros((len(sc.sensors), SI), dtype=np.int64)
+    sd = np.zeros((len(sc.sensors), SD))
+    moff = 0
+    markers = []
+    for i, s in enumerate(sc.sensors):
+        if len(s.candidates) > MAXCAND:
+            raise S.SceneError(f"more than {MAXCAND} tactile candidate bodies are not supported yet")
+        for arr in (s.axis0, s.axis1, s.normal):
+            if np.abs(arr - arr[0]).max() > 0:
+                raise S.SceneError("per-marker tactile axes are not supported by the B200 path yet")
+        si[i, :4] = [s.body, moff, len(s.pos), len(s.candidates)]
+        si[i, 4:4 + len(s.candidates)] = s.candidates
+        sd[i, :4] = [s.kn, s.kt, s.mu, s.damping]
+        sd[i, 4:7] = s.axis0[0]
+        sd[i, 7:10] = s.axis1[0]
+        sd[i, 10:13] = s.normal[0]
+        markers.append(s.pos)
+        moff += len(s.pos)
+    ints.append(si.reshape(-1))
+    dbls.append(sd.reshape(-1))
+
+    hdr[30] = doff()
+    P = np.concatenate(pts, axis=0) if pts else np.zeros((0, 3))
+    hdr[13] = len(P)
+    dbls.append(P.reshape(-1))
+    hdr[31] = doff()
+    Mk = np.concatenate(markers, axis=0) if markers else np.zeros((0, 3))
+    dbls.append(Mk.reshape(-1))
+    ibuf = np.concatenate(ints).astype(np.int32)
+    dbuf = np.concatenate(dbls).astype(np.float64)
+    return ibuf, dbuf
+
+
+def unpack_sizes(ibuf):
+    if int(ibuf[0]) != TS_MAGIC or int(ibuf[1]) != TS_VERSION:
+        raise S.SceneError("not a tactilesimulation_b200 scene blob (magic/version mismatch)")
+    nj, n, nu, nee, nm = (int(ibuf[i]) for i in (2, 3, 4, 5, 6))
+    return dict(nj=nj, ndof_r=n, ndof_m=6 * nj, ndof_u=nu, ndof_var=3 * nee, n_markers=nm, ndof_tactile=3 * nm)

@@ -1,0 +1,630 @@
+"""Scene compiler: redmax XML -> flat, batch-invariant topology tables.
+
+This is the host-side loader of the B200 simulator.  It reads the same
+``<redmax>`` XML scene files the reference reads
+(``DH/Simulation_Constructor.cpp:70-705``; DH = externals/DiffHand/core/projects/redmax)
+and produces a :class:`Scene` of plain numpy tables which ``Scene.pack()`` flattens into
+the two buffers (int32 / float64) that the CUDA kernels index directly.
+
+Semantics reproduced from the reference loader (behaviour, not code):
+
+* attributes parsed with pugixml ``as_float()`` are rounded through fp32
+  (timestep, damping, density, radius, length, kn/kt/mu/damping, P, D, ...),
+  ``Simulation_Constructor.cpp:108,230-251,510,559,578-579``; vectors go through
+  ``str_to_eigen`` in double (``Utils.h:388-402``).
+* joints are numbered in DFS order over ``<link>`` nesting, reduced dofs are assigned
+  in that order, every link carries one body (``Robot.cpp:38-100``).
+* ``<default>`` fallbacks for joint damping / lim_stiffness, contact and tactile
+  coefficients, motor ctrl_range/P/D.
+* body mass properties: cuboid ``BodyCuboid.cpp:20-26``, cylinder
+  ``BodyCylinder.cpp:21-27``, sphere ``BodySphere.cpp:17-21``, mesh (volume integral +
+  principal axes) ``BodyMeshObj.cpp:69-173``.
+* contact sample points: cuboid surface grid ``BodyCuboid.cpp:28-41``, cylinder faces
+  ``BodyCylinder.cpp:30-45``.
+* rect_array marker grid, row-major with the axis0 index outermost
+  ``TactileSensorRectArray.cpp:43-68``.
+* tactile candidate bodies = every primitive-shape body except the pad, in body order
+  (``TactileSensor.cpp:44-46``).
+
+Unsupported scene features raise :class:`SceneError` loudly (no silent fallback).
+"""
+from __future__ import annotations
+
+import math
+import os
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+# joint types (values are shared with csrc/scene_layout.h)
+JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL = 0, 1, 2, 3, 4
+JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3}
+JOINT_TYPES = {"fixed": JT_FIXED, "revolute": JT_REVOLUTE, "prismatic": JT_PRISMATIC,
+               "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL}
+# body shapes
+SH_NONE, SH_CUBOID, SH_CYLINDER, SH_SPHERE = 0, 1, 2, 3
+# actuator modes
+ACT_FORCE, ACT_POS = 0, 1
+
+INT_MIN, INT_MAX = -2147483648, 2147483647
+
+
+class SceneError(RuntimeError):
+    pass
+
+
+def _f32(s) -> float:
+    """pugixml as_float(): strtod then cast to float, widened back to double."""
+    return float(np.float32(float(s)))
+
+
+def _vec(s: str) -> np.ndarray:
+    return np.array([float(t) for t in s.split()], dtype=np.float64)
+
+
+def _ivec(s: str) -> np.ndarray:
+    return np.array([int(t) for t in s.split()], dtype=np.int64)
+
+
+def quat2mat(quat) -> np.ndarray:
+    """w x y z quaternion -> rotation (normalised first), ``Utils.h:142-150``."""
+    q = np.asarray(quat, dtype=np.float64)
+    q = q / np.linalg.norm(q)
+    w, x, y, z = q
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    return np.array([[1 - (tyy + tzz), txy - twz, txz + twy],
+                     [txy + twz, 1 - (txx + tzz), tyz - twx],
+                     [txz - twy, tyz + twx, 1 - (txx + tyy)]])
+
+
+def SE(R, p) -> np.ndarray:
+    E = np.eye(4)
+    E[:3, :3] = R
+    E[:3, 3] = p
+    return E
+
+
+def Einv(E) -> np.ndarray:
+    Rt = E[:3, :3].T
+    return SE(Rt, -Rt @ E[:3, 3])
+
+
+def _attr(node, root_default, tag, name):
+    """attribute with <default><tag name=.../> fallback; None if absent in both."""
+    if node.get(name) is not None:
+        return node.get(name)
+    if root_default is not None:
+        d = root_default.find(tag)
+        if d is not None and d.get(name) is not None:
+            return d.get(name)
+    return None
+
+
+def _load_obj(path: str):
+    """Vertices (through fp32, as tinyobj's real_t) and triangulated faces of the first
+    shape of a Wavefront OBJ (``BodyMeshObj.cpp:45-67``)."""
+    V, F = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            if line.startswith("v "):
+                t = line.split()
+                V.append([float(np.float32(float(t[1]))), float(np.float32(float(t[2]))),
+                          float(np.float32(float(t[3])))])
+            elif line.startswith("f "):
+                idx = []
+                for tok in line.split()[1:]:
+                    i = int(tok.split("/")[0])
+                    idx.append(i - 1 if i > 0 else len(V) + i)
+                for k in range(1, len(idx) - 1):
+                    F.append([idx[0], idx[k], idx[k + 1]])
+    if not V or not F:
+        raise SceneError(f"mesh {path} has no geometry")
+    return np.array(V, dtype=np.float64), np.array(F, dtype=np.int64)
+
+
+def mesh_mass_properties(V: np.ndarray, F: np.ndarray):
+    """volume, centre of mass and unit-mass inertia tensor of a closed triangle mesh
+    (signed tetrahedra against the origin), following ``BodyMeshObj.cpp:118-173``."""
+    A = V[F]                                    # (nf, 3 verts, 3 coords)
+    vol_f = np.linalg.det(np.transpose(A, (0, 2, 1)))
+    volume = vol_f.sum()
+    COM = (vol_f[:, None] * A.sum(axis=1)).sum(axis=0) / (volume * 4.0)
+    volume = volume / 6.0
+    B = A - COM                                 # rows = vertices, cols = coords
+    d = np.linalg.det(B)
+    diag = np.zeros(3)
+    offd = np.zeros(3)
+    for j in range(3):
+        j1, j2 = (j + 1) % 3, (j + 2) % 3
+        a = B[:, :, j]
+        diag[j] = ((a[:, 0] * a[:, 1] + a[:, 1] * a[:, 2] + a[:, 2] * a[:, 0]
+                    + a[:, 0] ** 2 + a[:, 1] ** 2 + a[:, 2] ** 2) * d).sum()
+        b, c = B[:, :, j1], B[:, :, j2]
+        offd[j] = ((b[:, 0] * c[:, 1] + b[:, 1] * c[:, 2] + b[:, 2] * c[:, 0]
+                    + b[:, 0] * c[:, 2] + b[:, 1] * c[:, 0] + b[:, 2] * c[:, 1]
+                    + 2 * b[:, 0] * c[:, 0] + 2 * b[:, 1] * c[:, 1] + 2 * b[:, 2] * c[:, 2]) * d).sum()
+    diag /= volume * 60.0
+    offd /= volume * 120.0
+    I = np.array([[diag[1] + diag[2], -offd[2], -offd[1]],
+                  [-offd[2], diag[0] + diag[2], -offd[0]],
+                  [-offd[1], -offd[0], diag[0] + diag[1]]])
+    return volume, COM, I
+
+
+@dataclass
+class TactileSensor:
+    name: str
+    body: int
+    kn: float
+    kt: float
+    mu: float
+    damping: float
+    pos: np.ndarray          # (M,3) marker positions in the pad body frame
+    axis0: np.ndarray        # (M,3)
+    axis1: np.ndarray        # (M,3)
+    normal: np.ndarray       # (M,3)
+    image_pos: np.ndarray    # (M,2) int
+    candidates: List[int] = field(default_factory=list)
+
+
+@dataclass
+class Scene:
+    name: str = ""
+    h: float = 0.01
+    gravity: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, -980.0]))
+    integrator: str = "BDF2"
+    tol: float = 1e-9
+    max_iter: int = 10
+    max_ls: int = 20
+    # joints / bodies, DFS order (one body per joint)
+    joint_names: List[str] = field(default_factory=list)
+    body_names: List[str] = field(default_factory=list)
+    jtype: List[int] = field(default_factory=list)
+    parent: List[int] = field(default_factory=list)
+    qoff: List[int] = field(default_factory=list)
+    ndof: List[int] = field(default_factory=list)
+    E_pj0: List[np.ndarray] = field(default_factory=list)
+    E_j0_0: List[np.ndarray] = field(default_factory=list)
+    axis0: List[np.ndarray] = field(default_factory=list)
+    axis1: List[np.ndarray] = field(default_factory=list)
+    damping: List[float] = field(default_factory=list)
+    lim_lo: List[float] = field(default_factory=list)
+    lim_hi: List[float] = field(default_factory=list)
+    lim_k: List[float] = field(default_factory=list)
+    E_ji: List[np.ndarray] = field(default_factory=list)
+    inertia: List[np.ndarray] = field(default_factory=list)   # (6,) Ixx Iyy Izz m m m
+    shape: List[int] = field(default_factory=list)
+    size: List[np.ndarray] = field(default_factory=list)      # cuboid: lengths; cylinder: (r, l, 0)
+    contact_points: List[np.ndarray] = field(default_factory=list)
+    E_g: np.ndarray = field(default_factory=lambda: np.eye(4))
+    has_ground: bool = False
+    ground_contacts: List[dict] = field(default_factory=list)  # body,kn,kt,mu,damping
+    gp_contacts: List[dict] = field(default_factory=list)      # body1,body2,kn,kt,mu,damping
+    actuators: List[dict] = field(default_factory=list)        # joint,mode,cmin,cmax,P,D,uoff
+    end_effectors: List[dict] = field(default_factory=list)    # joint,pos
+    sensors: List[TactileSensor] = field(default_factory=list)
+    virtual_names: List[str] = field(default_factory=list)
+    ndof_r: int = 0
+    ndof_u: int = 0
+
+    # ------------------------------------------------------------------ sizes
+    @property
+    def nj(self) -> int:
+        return len(self.jtype)
+
+    @property
+    def ndof_m(self) -> int:
+        return 6 * self.nj
+
+    @property
+    def ndof_var(self) -> int:
+        return 3 * len(self.end_effectors)
+
+    @property
+    def ndof_tactile(self) -> int:
+        return 3 * sum(len(s.pos) for s in self.sensors)
+
+    @property
+    def n_markers(self) -> int:
+        return sum(len(s.pos) for s in self.sensors)
+
+    # ------------------------------------------------------------ serialisation
+    def to_npz_dict(self) -> Dict[str, np.ndarray]:
+        ib, db = self.pack()
+        return {"ibuf": ib, "dbuf": db,
+                "names": np.array([self.name] + self.joint_names + self.body_names
+                                  + [s.name for s in self.sensors])}
+
+    # ------------------------------------------------------------------ pack
+    def pack(self):
+        """Flatten to (int32 ibuf, float64 dbuf) in the layout of csrc/scene_layout.h."""
+        from .layout import pack_scene
+        return pack_scene(self)
+
+
+def _cuboid_points(length, res):
+    pts = []
+    for i in range(res[0]):
+        for j in range(res[1]):
+            for k in range(res[2]):
+                if i in (0, res[0] - 1) or j in (0, res[1] - 1) or k in (0, res[2] - 1):
+                    pts.append([i / (res[0] - 1) * length[0] - length[0] / 2.0,
+                                j / (res[1] - 1) * length[1] - length[1] / 2.0,
+                                k / (res[2] - 1) * length[2] - length[2] / 2.0])
+    return np.array(pts, dtype=np.float64)
+
+
+def _cylinder_points(radius, length, ares, rres):
+    pts = []
+    for dz in (-1, 1):
+        pts.append([0.0, 0.0, dz * length / 2.0])
+        for a in range(ares):
+            angle = math.pi * 2.0 / ares * a
+            for r in range(rres):
+                pts.append([0.0 + math.cos(angle) * (r + 1) / rres * radius,
+                            0.0 + math.sin(angle) * (r + 1) / rres * radius,
+                            dz * length / 2.0 + 0.0])
+    return np.array(pts, dtype=np.float64)
+
+
+def compile_scene(xml_path: str) -> Scene:
+    """Parse a redmax XML scene file into a :class:`Scene`."""
+    if not os.path.isfile(xml_path):
+        raise SceneError("Input Model File (.xml) is incorrect.")
+    try:
+        root = ET.parse(xml_path).getroot()
+    except ET.ParseError as e:
+        raise SceneError("Input Model File (.xml) is incorrect.") from e
+    if root.tag != "redmax":
+        raise SceneError("Input Model File (.xml) is incorrect.")
+    asset_dir = os.path.dirname(os.path.abspath(xml_path))
+    sc = Scene(name=root.get("model", ""))
+    default = root.find("default")
+
+    opt = root.find("option")
+    if opt is not None:
+        if opt.get("gravity") is not None:
+            sc.gravity = _vec(opt.get("gravity"))
+        if opt.get("timestep") is not None:
+            sc.h = _f32(opt.get("timestep"))
+        if opt.get("integrator") is not None:
+            sc.integrator = opt.get("integrator")
+        unit = opt.get("unit", "cm-g")
+    else:
+        unit = "cm-g"
+    so = root.find("solver_option")
+    if so is not None:
+        if so.get("tol") is not None:
+            sc.tol = float(so.get("tol"))
+        if so.get("max_iter") is not None:
+            sc.max_iter = int(so.get("max_iter"))
+        if so.get("max_ls") is not None:
+            sc.max_ls = int(so.get("max_ls"))
+
+    g = root.find("ground")
+    if g is not None:
+        sc.has_ground = True
+        pos = _vec(g.get("pos"))
+        nz = _vec(g.get("normal"))
+        nz = nz / np.linalg.norm(nz)
+        # rotation taking +z to nz (Eigen setFromTwoVectors); only the normal and the
+        # origin enter the dynamics (ForceGroundContact.cpp:106-107)
+        z = np.array([0.0, 0.0, 1.0])
+        c = float(z @ nz)
+        if c > 1.0 - 1e-12:
+            Rg = np.eye(3)
+        elif c < -1.0 + 1e-12:
+            Rg = np.diag([1.0, -1.0, -1.0])
+        else:
+            ax = np.cross(z, nz)
+            s = np.linalg.norm(ax)
+            ax = ax / s
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            Rg = np.eye(3) + s * K + (1 - c) * (K @ K)
+        Rg[:, 2] = nz
+        # the reference scales the origin by 10 for the viewer and back (cm-g: /10 then *10)
+        p = (pos / 10.0) * 10.0 if unit == "cm-g" else (pos * 10.0) / 10.0
+        sc.E_g = SE(Rg, p)
+
+    joint_map: Dict[str, int] = {}
+    body_map: Dict[str, int] = {}
+
+    def parse_link(node, parent_idx):
+        jn = node.find("joint")
+        bn = node.find("body")
+        if jn is None or bn is None:
+            raise SceneError("every <link> needs a <joint> and a <body>")
+        tname = jn.get("type")
+        if tname not in JOINT_TYPES:
+            raise SceneError(f"Joint type not supported by the B200 path yet: {tname}")
+        jt = JOINT_TYPES[tname]
+        pos = _vec(jn.get("pos"))
+        R = quat2mat(_vec(jn.get("quat")))
+        frame = jn.get("frame", "LOCAL")
+        if frame not in ("LOCAL", "WORLD"):
+            raise SceneError("Frame type error: " + frame)
+        idx = sc.nj
+        if frame == "WORLD" and parent_idx >= 0:
+            E_pj0 = sc.E_j0_0[parent_idx] @ SE(R, pos)
+        else:
+            E_pj0 = SE(R, pos)
+        E_jp0 = Einv(E_pj0)
+        E_j00 = E_jp0 if parent_idx < 0 else E_jp0 @ sc.E_j0_0[parent_idx]
+        a0 = np.zeros(3)
+        a1 = np.zeros(3)
+        if jt in (JT_REVOLUTE, JT_PRISMATIC):
+            a0 = _vec(jn.get("axis"))
+            a0 = a0 / np.linalg.norm(a0)
+            if frame == "WORLD":
+                a0 = E_j00[:3, :3] @ a0
+        elif jt == JT_PLANAR:
+            a0 = _vec(jn.get("axis0"))
+            a1 = _vec(jn.get("axis1"))
+            a0 = a0 / np.linalg.norm(a0)
+            a1 = a1 / np.linalg.norm(a1)
+            if frame == "WORLD":
+                a0 = E_j00[:3, :3] @ a0
+                a1 = E_j00[:3, :3] @ a1
+        sc.jtype.append(jt)
+        sc.parent.append(parent_idx)
+        sc.ndof.append(JOINT_NDOF[jt])
+        sc.qoff.append(-1)
+        sc.E_pj0.append(E_pj0)
+        sc.E_j0_0.append(E_j00)
+        sc.axis0.append(a0)
+        sc.axis1.append(a1)
+        name = jn.get("name", f"joint{idx}")
+        sc.joint_names.append(name)
+        if jn.get("name") is not None:
+            joint_map[name] = idx
+        d = _attr(jn, default, "joint", "damping")
+        sc.damping.append(_f32(d) if d is not None else 0.0)
+        if jn.get("lim") is not None:
+            lim = _vec(jn.get("lim"))
+            lk = _attr(jn, default, "joint", "lim_stiffness")
+            sc.lim_lo.append(float(lim[0]))
+            sc.lim_hi.append(float(lim[1]))
+            sc.lim_k.append(_f32(lk) if lk is not None else 0.0)
+        else:
+            sc.lim_lo.append(float(INT_MIN))
+            sc.lim_hi.append(float(INT_MAX))
+            sc.lim_k.append(0.0)
+
+        # ---------------------------------------------------------------- body
+        btype = bn.get("type")
+        bpos = _vec(bn.get("pos"))
+        bR = quat2mat(_vec(bn.get("quat")))
+        dens = _attr(bn, default, "body", "density")
+        density = _f32(dens) if dens is not None else 1.0
+        sc_attr = _attr(bn, default, "body", "scale")
+        scale = _vec(sc_attr) if sc_attr is not None else np.ones(3)
+        inertia = np.zeros(6)
+        size = np.zeros(3)
+        pts = np.zeros((0, 3))
+        shape = SH_NONE
+        E_ji = SE(bR, bpos)
+        if btype == "cuboid":
+            length = _vec(bn.get("size"))
+            res = _ivec(bn.get("general_contact_resolution")) if bn.get("general_contact_resolution") else np.array([6, 6, 6])
+            if (res <= 1).any():
+                raise SceneError("General contact resolution of cuboid should be at least 2.")
+            mass = float(np.prod(length)) * density
+            inertia[0] = mass / 12.0 * (length[1] * length[1] + length[2] * length[2])
+            inertia[1] = mass / 12.0 * (length[0] * length[0] + length[2] * length[2])
+            inertia[2] = mass / 12.0 * (length[0] * length[0] + length[1] * length[1])
+            inertia[3:] = mass
+            shape, size, pts = SH_CUBOID, length, _cuboid_points(length, res)
+        elif btype == "cylinder":
+            length = _f32(bn.get("length"))
+            radius = _f32(bn.get("radius"))
+            ares = int(bn.get("general_contact_angle_resolution", 8))
+            rres = int(bn.get("general_contact_radius_resolution", 3))
+            mass = math.pi * radius * radius * length * density
+            inertia[0] = mass * length * length / 12.0 + mass * radius * radius / 4.0
+            inertia[1] = mass * length * length / 12.0 + mass * radius * radius / 4.0
+            inertia[2] = mass * radius * radius / 2.0
+            inertia[3:] = mass
+            shape, size = SH_CYLINDER, np.array([radius, length, 0.0])
+            pts = _cylinder_points(radius, length, ares, rres)
+        elif btype == "mesh":
+            V, F = _load_obj(os.path.join(asset_dir, bn.get("filename")))
+            V = V * scale[None, :]
+            volume, COM, I = mesh_mass_properties(V, F)
+            mass = volume * density
+            I = I * mass
+            w, vecs = np.linalg.eigh(I)
+            if np.dot(np.cross(vecs[:, 0], vecs[:, 1]), vecs[:, 2]) < 0.0:
+                vecs[:, 2] *= -1.0
+            inertia[:3] = w
+            inertia[3:] = mass
+            E_oi = SE(vecs, COM)
+            tt = bn.get("transform_type", "BODY_TO_JOINT")
+            if tt == "BODY_TO_JOINT":
+                E_ji = SE(bR, bpos)
+            elif tt == "OBJ_TO_WORLD":
+                E_ji = E_j00 @ SE(bR, bpos) @ E_oi
+            elif tt == "OBJ_TO_JOINT":
+                E_ji = SE(bR @ E_oi[:3, :3], bR @ E_oi[:3, 3] + bpos)
+            else:
+                raise SceneError("Transform type error: " + tt)
+            # mesh vertices sampled as contact points are never used by the supported
+            # force types (general_primitive_contact needs them only on the general body)
+        else:
+            raise SceneError(f"Body type not supported by the B200 path yet: {btype}")
+        sc.E_ji.append(E_ji)
+        sc.inertia.append(inertia)
+        sc.shape.append(shape)
+        sc.size.append(np.asarray(size, dtype=np.float64))
+        sc.contact_points.append(pts)
+        bname = bn.get("name", f"body{idx}")
+        sc.body_names.append(bname)
+        if bn.get("name") is not None:
+            body_map[bname] = idx
+        for child in node:
+            if child.tag == "link":
+                parse_link(child, idx)
+        return idx
+
+    for robot in root:
+        if robot.tag == "robot":
+            for rn in robot:
+                if rn.tag == "link":
+                    parse_link(rn, -1)
+
+    # reduced dof offsets in DFS order
+    off = 0
+    for j in range(sc.nj):
+        sc.qoff[j] = off
+        off += sc.ndof[j]
+    sc.ndof_r = off
+
+    # actuators
+    uoff = 0
+    for an in root:
+        if an.tag != "actuator":
+            continue
+        for m in an:
+            if m.tag != "motor":
+                continue
+            jname = m.get("joint")
+            if jname not in joint_map:
+                raise SceneError("Actuator joint name error: " + str(jname))
+            j = joint_map[jname]
+            cr = _attr(m, default, "motor", "ctrl_range")
+            rng = _vec(cr) if cr is not None else np.array([float(INT_MIN), float(INT_MAX)])
+            mode = m.get("ctrl")
+            nd = sc.ndof[j]
+            act = {"joint": j, "uoff": uoff, "ndof": nd,
+                   "cmin": np.full(nd, rng[0]), "cmax": np.full(nd, rng[1]),
+                   "P": np.zeros(nd), "D": np.zeros(nd)}
+            if mode == "force":
+                act["mode"] = ACT_FORCE
+            elif mode == "position":
+                act["mode"] = ACT_POS
+                P = _attr(m, default, "motor", "P")
+                D = _attr(m, default, "motor", "D")
+                act["P"] = np.full(nd, _f32(P) if P is not None else 0.0)
+                act["D"] = np.full(nd, _f32(D) if D is not None else 0.0)
+            else:
+                continue  # the reference silently ignores unknown ctrl types
+            sc.actuators.append(act)
+            uoff += nd
+    sc.ndof_u = uoff
+
+    # tactile sensors
+    for sn in root:
+        if sn.tag != "sensor":
+            continue
+        for t in sn:
+            if t.tag != "tactile":
+                continue
+            bname = t.get("body")
+            if bname not in body_map:
+                raise SceneError("Tactile body name error: " + str(bname))
+            b = body_map[bname]
+            coef = {}
+            for key in ("kn", "kt", "mu", "damping"):
+                v = _attr(t, default, "tactile", key)
+                coef[key] = _f32(v) if v is not None else 0.0
+            ttype = t.get("type")
+            if ttype != "rect_array":
+                raise SceneError(f"Tactile type {ttype} is not supported by the B200 path yet")
+            if sc.shape[b] == SH_NONE:
+                raise SceneError("rect_array tactile sensors need a primitive pad body")
+            p0 = _vec(t.get("rect_pos0"))
+            p1 = _vec(t.get("rect_pos1"))
+            ax0 = _vec(t.get("axis0"))
+            ax1 = _vec(t.get("axis1"))
+            res = _ivec(t.get("resolution"))
+            l0 = float((p1 - p0) @ ax0)
+            l1 = float((p1 - p0) @ ax1)
+            if np.linalg.norm(p0 + l0 * ax0 + l1 * ax1 - p1) > 1e-5:
+                raise SceneError("Tactile info for " + bname + " is incompatible")
+            s0 = l0 / (res[0] - 1) * ax0
+            s1 = l1 / (res[1] - 1) * ax1
+            normal = np.cross(ax0, ax1)
+            pos, ipos = [], []
+            for i in range(res[0]):
+                for j in range(res[1]):
+                    pos.append(p0 + s0 * i + s1 * j)
+                    ipos.append([i, j])
+            M = len(pos)
+            cands = [k for k in range(sc.nj) if sc.shape[k] != SH_NONE and k != b]
+            sc.sensors.append(TactileSensor(
+                name=t.get("name", ""), body=b, pos=np.array(pos), axis0=np.tile(ax0, (M, 1)),
+                axis1=np.tile(ax1, (M, 1)), normal=np.tile(normal, (M, 1)),
+                image_pos=np.array(ipos, dtype=np.int64), candidates=cands, **coef))
+
+    # contacts
+    for cn in root:
+        if cn.tag != "contact":
+            continue
+        for c in cn:
+            coef = {}
+            for key in ("kn", "kt", "mu", "damping"):
+                v = _attr(c, default, c.tag, key)
+                coef[key] = _f32(v) if v is not None else 0.0
+            if c.tag == "ground_contact":
+                bname = c.get("body")
+                if bname not in body_map:
+                    raise SceneError("Ground contact body name error: " + str(bname))
+                if sc.shape[body_map[bname]] == SH_SPHERE:
+                    raise SceneError("sphere ground contact is not supported by the B200 path yet")
+                sc.ground_contacts.append(dict(body=body_map[bname], **coef))
+            elif c.tag == "general_primitive_contact":
+                b1, b2 = c.get("general_body"), c.get("primitive_body")
+                if b1 not in body_map:
+                    raise SceneError("General contact body name error: " + str(b1))
+                if b2 not in body_map:
+                    raise SceneError("Primitive contact body name error: " + str(b2))
+                if sc.shape[body_map[b2]] == SH_NONE:
+                    raise SceneError("The second body in Contact should be primitive body.")
+                sc.gp_contacts.append(dict(body1=body_map[b1], body2=body_map[b2], **coef))
+            else:
+                raise SceneError(f"contact type {c.tag} is not supported by the B200 path yet")
+
+    # variables
+    for vn in root:
+        if vn.tag != "variable":
+            continue
+        for e in vn:
+            if e.tag != "endeffector":
+                continue
+            jname = e.get("joint")
+            if jname not in joint_map:
+                raise SceneError("Endeffector joint name error: " + str(jname))
+            sc.end_effectors.append({"joint": joint_map[jname], "pos": _vec(e.get("pos")),
+                                     "name": e.get("name", "")})
+    for vn in root:
+        if vn.tag == "virtual":
+            for e in vn:
+                sc.virtual_names.append(e.get("name", ""))
+    for s in sc.sensors:
+        for k in s.candidates:
+            if sc.shape[k] != SH_CUBOID:
+                raise SceneError("tactile candidates other than cuboids are not supported by the B200 path yet")
+    for gp in sc.gp_contacts:
+        if sc.shape[gp["body2"]] != SH_CUBOID:
+            raise SceneError("primitive contact bodies other than cuboids are not supported by the B200 path yet")
+    return sc
+
+
+def joint_Q(jt: int, a0, a1, q):
+    """Joint transform Q(q) (``Joint*.cpp update``)."""
+    Q = np.eye(4)
+    if jt == JT_REVOLUTE:
+        c, s = math.cos(q[0]), math.sin(q[0])
+        K = np.array([[0, -a0[2], a0[1]], [a0[2], 0, -a0[0]], [-a0[1], a0[0], 0]])
+        Q[:3, :3] = np.eye(3) * c + s * K + (1 - c) * np.outer(a0, a0)
+    elif jt == JT_PRISMATIC:
+        Q[:3, 3] = a0 * q[0]
+    elif jt == JT_PLANAR:
+        Q[:3, 3] = a0 * q[0] + a1 * q[1]
+    elif jt == JT_TRANSLATIONAL:
+        Q[:3, 3] = q
+    return Q

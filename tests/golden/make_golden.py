@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory by RUNNING THE UNMODIFIED REFERENCE
+(oracle/_ref/redmax_py + redmax_probe, built by oracle/build_ref.sh from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Fixtures (npz): compiled scene blobs + seeded inputs + reference outputs
+    q, qdot, var, tactile per step; active contact-point index sets per Force and
+    marker->body ids per step; df_dq0 / df_dqdot0 / df_du of Simulation::backward();
+    df_du of a StepSimFunction-style chain of backward_steps(5).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+import redmax_py  # noqa: E402
+import redmax_probe  # noqa: E402
+from tactilesimulation_b200.scene import compile_scene  # noqa: E402
+
+ASSETS = os.path.join(ROOT, "oracle", "_ref", "assets", "pusher")
+
+
+def make_inputs(sim, T, seed, push=True):
+    """SURVEY.md §8(d) config 2/3 inputs: q0[1]=-0.001, q0[4]~U(-.02,.02); u=tanh(N(0,1)) on
+    dims 0-2, dims 3-4 resampled every 10 steps (p=.5 zero else U(-1,1)), dim 5 = 0."""
+    rng = np.random.default_rng(seed)
+    q0 = np.array(sim.get_q_init())
+    q0[1] = -0.001
+    q0[4] = rng.uniform(-0.02, 0.02)
+    u = np.zeros((T, sim.ndof_u))
+    ext = np.zeros(2)
+    for t in range(T):
+        u[t, :3] = np.tanh(rng.normal(size=3))
+        if push:
+            u[t, 0] = abs(u[t, 0])          # keep pushing so that contact happens
+        if t % 10 == 0:
+            ext = rng.uniform(-1, 1, 2) if rng.uniform() >= 0.5 else np.zeros(2)
+        u[t, 3:5] = ext
+    return q0, u
+
+
+def pad_ids(lists, width):
+    out = -np.ones((len(lists), width), dtype=np.int32)
+    for i, l in enumerate(lists):
+        out[i, :len(l)] = l
+    return out
+
+
+def episodic_case(xml, T, seed, push=True):
+    sim = redmax_py.Simulation(xml)
+    probe = redmax_probe.ProbeSimulation(xml)
+    sc = compile_scene(xml)
+    q0, u = make_inputs(sim, T, seed, push)
+    n, nv, nt = sim.ndof_r, sim.ndof_var, sim.ndof_tactile
+    for s in (sim, probe):
+        s.set_state_init(q0, np.zeros(n))
+        s.reset(True)
+    q, qd, var, tac = [], [], [], []
+    ground, gp, mb = [], [], []
+    for t in range(T):
+        for s in (sim, probe):
+            s.set_u(u[t])
+            s.forward(1)
+        assert np.array_equal(sim.get_q(), probe.get_q())
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        var.append(sim.get_variables().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+        cs = probe.contact_sets()
+        ground.append(cs["ground"][0])
+        gp.append(cs["gp"][0])
+        mb.append(cs["marker_body"][0])
+    rng = np.random.default_rng(1000 + seed)
+    df_dq = rng.normal(size=(T, n))
+    df_dvar = rng.normal(size=(T, nv))
+    df_dtac = 1e-3 * rng.normal(size=(T, nt))
+    bi = sim.backward_info
+    bi.set_flags(True, True, False, True)
+    bi.df_dq = df_dq.reshape(-1)
+    bi.df_dvar = df_dvar.reshape(-1)
+    bi.df_dtactile = df_dtac.reshape(-1)
+    bi.df_dq0 = np.zeros(n)
+    bi.df_dqdot0 = np.zeros(n)
+    bi.df_du = np.zeros(sim.ndof_u * T)
+    sim.backward()
+    br = sim.backward_results
+    ib, db = sc.pack()
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(n), u=u, q=np.array(q), qd=np.array(qd), var=np.array(var),
+                tactile=np.array(tac), ground_ids=pad_ids(ground, len(sc.contact_points[sc.ground_contacts[0]["body"]])),
+                gp_ids=pad_ids(gp, len(sc.contact_points[sc.gp_contacts[0]["body1"]])),
+                marker_body=np.array(mb, dtype=np.int32), df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac,
+                df_dq0=np.array(br.df_dq0), df_dqdot0=np.array(br.df_dqdot0),
+                df_du=np.array(br.df_du).reshape(T, sim.ndof_u))
+
+
+def stepsim_case(xml, nsteps, frame_skip, seed):
+    """The StepSimFunction call pattern (R/envs/redmax_torch_functions.py:112-174):
+    forward(frame_skip, save_last_frame_var_only=True) per gym step, then a reverse chain of
+    backward_steps(frame_skip) with cotangents on the last sub-step only."""
+    sim = redmax_py.Simulation(xml)
+    sc = compile_scene(xml)
+    q0, u = make_inputs(sim, nsteps, seed)
+    n, nv, nt, nu = sim.ndof_r, sim.ndof_var, sim.ndof_tactile, sim.ndof_u
+    sim.set_state_init(q0, np.zeros(n))
+    sim.reset(True)
+    q, var, tac = [], [], []
+    for t in range(nsteps):
+        sim.set_u(u[t])
+        sim.forward(frame_skip, False, False, True)
+        q.append(sim.get_q().copy())
+        var.append(sim.get_variables().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+    rng = np.random.default_rng(2000 + seed)
+    df_dq = rng.normal(size=(nsteps, n))
+    df_dvar = rng.normal(size=(nsteps, nv))
+    df_dtac = 1e-3 * rng.normal(size=(nsteps, nt))
+    df_du = np.zeros((nsteps, frame_skip, nu))
+    for t in range(nsteps - 1, -1, -1):
+        bi = sim.backward_info
+        bi.set_flags(False, False, False, True)
+        a = np.zeros(n * frame_skip); a[-n:] = df_dq[t]
+        b = np.zeros(nv * frame_skip); b[-nv:] = df_dvar[t]
+        c = np.zeros(nt * frame_skip); c[-nt:] = df_dtac[t]
+        bi.df_dq, bi.df_dvar, bi.df_dtactile = a, b, c
+        bi.df_du = np.zeros(nu * frame_skip)
+        sim.backward_steps(frame_skip)
+        df_du[t] = np.array(sim.backward_results.df_du).reshape(frame_skip, nu)
+    ib, db = sc.pack()
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(n), u=u, frame_skip=frame_skip, q=np.array(q), var=np.array(var),
+                tactile=np.array(tac), df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac, df_du=df_du)
+
+
+def main():
+    x13 = os.path.join(ASSETS, "pusher.xml")
+    x32 = os.path.join(ASSETS, "pusher_32x13.xml")
+    cases = {
+        "pusher13x10_episodic_s0": episodic_case(x13, 60, 0),
+        "pusher13x10_episodic_s1": episodic_case(x13, 60, 1, push=False),
+        "pusher32x13_episodic_s0": episodic_case(x32, 30, 0),
+        "pusher13x10_stepsim_s0": stepsim_case(x13, 8, 5, 0),
+    }
+    for name, c in cases.items():
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **c)
+        print(name, os.path.getsize(path) // 1024, "KiB", "contacts/step:",
+              [int((r >= 0).sum()) for r in c.get("gp_ids", np.zeros((0, 0)))][:12])
+
+
+if __name__ == "__main__":
+    main()
