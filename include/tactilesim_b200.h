@@ -1,0 +1,93 @@
+/* C ABI of the B200 tactile simulator (libtactilesim_b200.so).
+ *
+ * Drop-in boundary for ONE path of eanswer/TactileSimulation: the per-timestep differentiable
+ * simulation step + dense tactile force field + reverse-time adjoint that the reference reaches
+ * through pybind11 (R = /root/reference, DH = R/externals/DiffHand/core/projects/redmax):
+ *
+ *   tsim_scene_create    <- Simulation(xml_file_path)            DH/python_interface.cpp:86-88
+ *                           (the XML is compiled on the host by tactilesimulation_b200.scene;
+ *                            the blob replaces the pointer graph of DH/Simulation_Constructor.cpp)
+ *   tsim_scene_sizes     <- ndof_r/ndof_m/ndof_u/ndof_var/ndof_tactile  DH/python_interface.cpp:93-98
+ *   tsim_forward         <- set_u + forward(num_steps, ..., save_last_frame_var_only) + get_q /
+ *                           get_qdot / get_variables / get_tactile_force_vector
+ *                           DH/python_interface.cpp:118-135,159,229-231 ; DH/Simulation.cpp:1057-1148
+ *   tsim_readout         <- get_variables / get_tactile_force_vector at the current state
+ *                           DH/Robot.cpp:359-370
+ *   tsim_backward        <- backward() and backward_steps(n) with backward_info.df_dq/df_dvar/
+ *                           df_dtactile in, backward_results.df_du/df_dq0/df_dqdot0 out
+ *                           DH/python_interface.cpp:64-83,232-236 ; DH/Simulation.cpp:1569-1713,1876-1971
+ *
+ * Conventions: all data pointers are DEVICE pointers (fp64, C-contiguous, env-major inside a
+ * step: [step][env][component]); `stream` is a cudaStream_t passed as void*; every call is
+ * asynchronous on that stream.  Functions return 0 on success, non-zero on error with a message
+ * available from tsim_last_error().  Newton non-convergence is not an error (as in the reference,
+ * DH/Simulation.cpp:1218-1222); it is reported per env-step in `status`.
+ */
+#ifndef TACTILESIM_B200_H
+#define TACTILESIM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tsim_scene tsim_scene;
+
+/* status word of one env-step: bits 0-7 Newton iterations, bits 8-15 line-search evaluations,
+ * bit 16 not converged, bit 17 NaN state */
+#define TSIM_STAT_NOT_CONVERGED (1 << 16)
+#define TSIM_STAT_NAN (1 << 17)
+
+/* indices into the array filled by tsim_scene_sizes */
+enum { TSIM_NJ = 0, TSIM_NDOF_R, TSIM_NDOF_M, TSIM_NDOF_U, TSIM_NDOF_VAR, TSIM_NDOF_TACTILE, TSIM_N_MARKERS,
+       TSIM_TAPE_DOUBLES /* per env-step: 3*ndof_r^2 */, TSIM_N_SIZES };
+
+const char* tsim_last_error(void);
+
+/* Uploads a packed scene (host pointers; layout: tactilesimulation_b200/csrc/scene_layout.h) to
+ * `device` and returns a handle. */
+int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, int64_t n_dbl, int device,
+                      tsim_scene** out);
+void tsim_scene_destroy(tsim_scene* scene);
+int tsim_scene_sizes(const tsim_scene* scene, int32_t* out /* [TSIM_N_SIZES] */);
+/* lanes cooperating on one environment: 8, 16 or 32 (default 8) */
+int tsim_scene_set_lanes(tsim_scene* scene, int lanes_per_env);
+
+/* Advances B environments by T implicit (BDF1/Newton) steps.
+ *   q, qd        [B,n]        state, in/out
+ *   u            u[t*u_step_stride + env*nu + i]; u_step_stride = 0 holds one action for all T steps
+ *   q_traj,qd_traj [T,B,n]    states after each step, or NULL (required later by tsim_backward)
+ *   var_out      [rows,B,nvar]   end-effector variables of step t at row var_row[t] (NULL map: row t;
+ *                                row < 0: skipped), or NULL
+ *   tac_out      [rows,B,ntac]   tactile field (marker-major: shear.axis0, shear.axis1, normal)
+ *   tape         [T,B,3,n,n]  adjoint tape (H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0), or NULL = no-grad mode
+ *   status       [T,B] or NULL
+ *   contact_masks [T,B,4] or NULL: active contact-point bitmasks (word 0: ground force 0;
+ *                                words 1-3: general-primitive force 0)
+ *   marker_body  [rows,B,M] or NULL: contacted body id per marker (-1 none), rows as tac_out */
+int tsim_forward(const tsim_scene* scene, int32_t B, int32_t T, double* q, double* qd, const double* u,
+                 int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
+                 double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
+                 int32_t* marker_body, void* stream);
+
+/* Readouts at a given state (no stepping). Any output may be NULL. */
+int tsim_readout(const tsim_scene* scene, int32_t B, const double* q, const double* qd, double* var_out,
+                 double* tac_out, int32_t* marker_body, uint32_t* contact_masks, void* stream);
+
+/* Reverse sweep over the T steps recorded by tsim_forward (same B, T, u, q_traj, qd_traj, tape).
+ *   df_dq/df_dvar/df_dtac  cotangents [rows,B,*] with optional row maps [T] as above (NULL = no cotangent)
+ *   carry        [B,2,n] in/out: pending adjoint contributions of later steps.  Zero it before the
+ *                reverse sweep of the LAST chunk of a trajectory and pass it unchanged to the
+ *                sweeps of earlier chunks (this is what backward_steps() keeps in BackwardInfo::_z).
+ *   df_du        [T,B,nu] out, or NULL
+ *   df_dq0, df_dqdot0 [B,n] out, or NULL: gradient w.r.t. the state at the start of the chunk
+ *                (meaningful for the first chunk: Simulation::backward's df_dq0 / df_dqdot0) */
+int tsim_backward(const tsim_scene* scene, int32_t B, int32_t T, const double* q_traj, const double* qd_traj,
+                  const double* u, int64_t u_step_stride, const double* tape, const double* df_dq,
+                  const int32_t* dq_row, const double* df_dvar, const int32_t* dvar_row, const double* df_dtac,
+                  const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

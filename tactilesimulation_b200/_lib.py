@@ -1,0 +1,47 @@
+"""ctypes binding of libtactilesim_b200.so (C ABI: include/tactilesim_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is visible, every
+entry point raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtactilesim_b200.so")
+
+SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes",
+           "tsim_forward", "tsim_readout", "tsim_backward"]
+(NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, N_SIZES) = range(9)
+
+_lib = None
+
+
+class TactileSimError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TactileSimError(
+            f"{LIB_PATH} is missing: build the sm_100a library first (python -m tactilesimulation_b200.build "
+            "or __graft_entry__.build()); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.tsim_last_error.restype = ctypes.c_char_p
+    lib.tsim_scene_create.argtypes = [vp, i64, vp, i64, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.tsim_scene_destroy.argtypes = [vp]
+    lib.tsim_scene_destroy.restype = None
+    lib.tsim_scene_sizes.argtypes = [vp, vp]
+    lib.tsim_scene_set_lanes.argtypes = [vp, ctypes.c_int]
+    lib.tsim_forward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsim_readout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsim_backward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, lib):
+    if rc != 0:
+        raise TactileSimError(lib.tsim_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,262 @@
+// sm_100a kernels + C ABI (include/tactilesim_b200.h) of the B200 tactile simulator.
+//
+// Execution model: one environment per TILE of LPE lanes (8/16/32) of a warp, one persistent
+// tile per environment for all T steps of a call (state stays in registers across steps, the
+// scene blob is staged once per CTA in shared memory).  Lane k of a tile owns reduced
+// coordinate k: it carries the Dual tangent along q_k through the matrix-free residual, holds
+// column k of the Newton matrix for the shuffle-based pivoted LU, and strides over tactile
+// markers / contact points in the readout and adjoint passes.  See sim_core.cuh.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/tactilesim_b200.h"
+#include "sim_core.cuh"
+
+template <int LPE_>
+struct DevTile {
+  static const int LPE = LPE_;
+  int lane;
+  unsigned mask;
+  HD double bcast(double v, int src) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(mask, v, src, LPE_);
+#else
+    return v;
+#endif
+  }
+  HD int bcasti(int v, int src) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(mask, v, src, LPE_);
+#else
+    return v;
+#endif
+  }
+  HD double sum(double v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = LPE_ / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, LPE_);
+#endif
+    return v;
+  }
+};
+
+#define TS_BLOCK 128
+
+// stage the scene blob in shared memory (ints first, then doubles, 8-byte aligned)
+__device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni, const double* db, int nd,
+                                            unsigned char* smem) {
+  double* sd = (double*)smem;
+  int* si = (int*)(smem + (size_t)nd * sizeof(double));
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) sd[i] = db[i];
+  for (int i = threadIdx.x; i < ni; i += blockDim.x) si[i] = ib[i];
+  __syncthreads();
+  scene_view_init(S, si, sd);
+}
+
+template <int LPE>
+__device__ __forceinline__ DevTile<LPE> make_tile() {
+  DevTile<LPE> tl;
+  tl.lane = threadIdx.x % LPE;
+  const int wl = threadIdx.x & 31;
+  tl.mask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (wl - tl.lane));
+  return tl;
+}
+
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+  if (env >= a.B) return;
+  DevTile<LPE> tl = make_tile<LPE>();
+  __align__(16) unsigned char wb[sizeof(Work<Dual>)];
+  env_forward(tl, S, a, env, wb);
+}
+
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+  if (env >= a.B) return;
+  DevTile<LPE> tl = make_tile<LPE>();
+  __align__(16) unsigned char wb[sizeof(Work<Dual>)];
+  env_backward(tl, S, a, env, wb);
+}
+
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni, const double* db, int nd, int B,
+                                                          const double* q, const double* qd, double* var_out,
+                                                          double* tac_out, int* marker_body, unsigned* cmask) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+  if (env >= B) return;
+  DevTile<LPE> tl = make_tile<LPE>();
+  __align__(16) unsigned char wb[sizeof(Work<double>)];
+  double ql[TS_MAXN], qdl[TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) {
+    ql[i] = (i < S.n) ? q[(long long)env * S.n + i] : 0.0;
+    qdl[i] = (i < S.n) ? qd[(long long)env * S.n + i] : 0.0;
+  }
+  env_readout(tl, S, ql, qdl, var_out ? var_out + (long long)env * 3 * S.nee : (double*)0,
+              tac_out ? tac_out + (long long)env * 3 * S.nmark : (double*)0,
+              marker_body ? marker_body + (long long)env * S.nmark : (int*)0,
+              cmask ? cmask + (long long)env * 4 : (unsigned*)0, wb);
+}
+
+// ------------------------------------------------------------------ host side of the C ABI
+struct tsim_scene {
+  int device;
+  int* d_ib;
+  double* d_db;
+  int ni, nd;
+  int lanes;
+  int sizes[TSIM_N_SIZES];
+};
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(x)                                                                                          \
+  do {                                                                                                 \
+    cudaError_t e_ = (x);                                                                              \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+static size_t scene_smem(const tsim_scene* s) { return (size_t)s->nd * sizeof(double) + (size_t)s->ni * sizeof(int) + 16; }
+
+template <class K>
+static int prep(K kern, size_t smem) {
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+extern "C" {
+
+const char* tsim_last_error(void) { return g_err.c_str(); }
+
+int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, int64_t n_dbl, int device,
+                      tsim_scene** out) {
+  if (!ibuf || !dbuf || !out) return fail("tsim_scene_create: null argument");
+  if (n_int < TS_I_HEADER || ibuf[TS_I_MAGIC] != TS_MAGIC || ibuf[TS_I_VERSION] != TS_VERSION)
+    return fail("tsim_scene_create: not a scene blob of this version");
+  if (ibuf[TS_I_NJ] > TS_MAXJ || ibuf[TS_I_NDOF_R] > TS_MAXN || ibuf[TS_I_NDOF_U] > TS_MAXU)
+    return fail("tsim_scene_create: scene exceeds the compiled capacities (joints/dofs/controls)");
+  if (ibuf[TS_I_NSENSORS] > 1) return fail("tsim_scene_create: at most one tactile sensor is supported");
+  CK(cudaSetDevice(device));
+  tsim_scene* s = new tsim_scene();
+  s->device = device;
+  s->ni = (int)n_int;
+  s->nd = (int)n_dbl;
+  s->lanes = 8;
+  CK(cudaMalloc(&s->d_ib, sizeof(int) * n_int));
+  CK(cudaMalloc(&s->d_db, sizeof(double) * n_dbl));
+  CK(cudaMemcpy(s->d_ib, ibuf, sizeof(int) * n_int, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_db, dbuf, sizeof(double) * n_dbl, cudaMemcpyHostToDevice));
+  const int n = ibuf[TS_I_NDOF_R];
+  s->sizes[TSIM_NJ] = ibuf[TS_I_NJ];
+  s->sizes[TSIM_NDOF_R] = n;
+  s->sizes[TSIM_NDOF_M] = 6 * ibuf[TS_I_NJ];
+  s->sizes[TSIM_NDOF_U] = ibuf[TS_I_NDOF_U];
+  s->sizes[TSIM_NDOF_VAR] = 3 * ibuf[TS_I_NEE];
+  s->sizes[TSIM_NDOF_TACTILE] = 3 * ibuf[TS_I_NMARKERS];
+  s->sizes[TSIM_N_MARKERS] = ibuf[TS_I_NMARKERS];
+  s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n;
+  *out = s;
+  return 0;
+}
+
+void tsim_scene_destroy(tsim_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_ib);
+  cudaFree(s->d_db);
+  delete s;
+}
+
+int tsim_scene_sizes(const tsim_scene* s, int32_t* out) {
+  if (!s || !out) return fail("tsim_scene_sizes: null argument");
+  for (int i = 0; i < TSIM_N_SIZES; ++i) out[i] = s->sizes[i];
+  return 0;
+}
+
+int tsim_scene_set_lanes(tsim_scene* s, int lanes) {
+  if (!s) return fail("tsim_scene_set_lanes: null scene");
+  if (lanes != 8 && lanes != 16 && lanes != 32) return fail("tsim_scene_set_lanes: lanes must be 8, 16 or 32");
+  s->lanes = lanes;
+  return 0;
+}
+
+
+int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, const double* u,
+                 int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
+                 double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
+                 int32_t* marker_body, void* stream) {
+  if (!s) return fail("tsim_forward: null scene");
+  if (B <= 0 || T < 0) return fail("tsim_forward: bad batch or step count");
+  if (!q || !qd || !u) return fail("tsim_forward: q, qd and u are required");
+  if (T == 0) return 0;
+  CK(cudaSetDevice(s->device));
+  FwdArgs a;
+  a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_step_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
+  a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
+  a.status = status; a.cmask = contact_masks; a.marker_body = marker_body;
+  const size_t smem = scene_smem(s);
+  const long long threads = (long long)B * s->lanes;
+  const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else { if (prep(fwd_kernel<32>, smem)) return 1; fwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* qd, double* var_out, double* tac_out,
+                 int32_t* marker_body, uint32_t* contact_masks, void* stream) {
+  if (!s) return fail("tsim_readout: null scene");
+  if (B <= 0 || !q || !qd) return fail("tsim_readout: bad arguments");
+  CK(cudaSetDevice(s->device));
+  const size_t smem = scene_smem(s);
+  const long long threads = (long long)B * s->lanes;
+  const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->lanes == 8) { if (prep(readout_kernel<8>, smem)) return 1; readout_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
+  else if (s->lanes == 16) { if (prep(readout_kernel<16>, smem)) return 1; readout_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
+  else { if (prep(readout_kernel<32>, smem)) return 1; readout_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_traj, const double* qd_traj,
+                  const double* u, int64_t u_step_stride, const double* tape, const double* df_dq,
+                  const int32_t* dq_row, const double* df_dvar, const int32_t* dvar_row, const double* df_dtac,
+                  const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0,
+                  void* stream) {
+  if (!s) return fail("tsim_backward: null scene");
+  if (B <= 0 || T <= 0) return fail("tsim_backward: bad batch or step count");
+  if (!q_traj || !qd_traj || !u || !tape || !carry)
+    return fail("tsim_backward: q_traj, qd_traj, u, tape and carry are required (run tsim_forward with a tape first)");
+  CK(cudaSetDevice(s->device));
+  BwdArgs a;
+  a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_step_stride; a.tape = tape;
+  a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
+  a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
+  const size_t smem = scene_smem(s);
+  const long long threads = (long long)B * s->lanes;
+  const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->lanes == 8) { if (prep(bwd_kernel<8>, smem)) return 1; bwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1058 @@
+// Per-lane simulation math of the B200 tactile simulator.
+//
+// Everything here is templated on the scalar T (double, or Dual = value + one tangent) and
+// is free of CUDA intrinsics, so the same source is (a) inlined into the sm_100a kernels in
+// kernels.cu and (b) compiled by g++ into the test-only host harness (tests/emu) that lets
+// the parity tests run without a GPU.  Cross-lane work (LU solve, reductions, marker
+// striding) goes through a Tile policy: DevTile<LPE> = warp shuffles over a tile of LPE
+// lanes, HostTile = one lane that owns everything.
+//
+// Formulation (differs from the reference on purpose; reference = DiffRedMax, cited as
+// DH/... = externals/DiffHand/core/projects/redmax/...):
+//   * residual of the implicit BDF1 step, DH/Simulation.cpp:1227-1251,
+//       g(q1) = M(q1) (q1-q0-h qd0) - h^2 f(q1,(q1-q0)/h)
+//     is evaluated matrix-free by one outward sweep over the joint tree (poses, twists
+//     phi = J qd, psi = J (q1-q0-h qd0), bias eta = Jdot qd), per-body wrenches
+//     a_i = I psi_i - h^2 (coriolis + gravity + contacts - I eta_i), and one inward sweep that
+//     accumulates J^T a  -- the reference instead builds J (42x7), Jdot, Mm, Km, Dm, dJ_dq ...
+//     (DH/Simulation.cpp:256-454, DH/Robot.cpp:803-885).
+//   * derivatives: H = dg/dq1 and the adjoint blocks G0 = dg/dq0, G1 = dg/dqdot0 come from the
+//     same code on Dual numbers, one reduced coordinate per lane (see dual.cuh).  With
+//     FORCE actuators G0 = -M + hD and G1 = -hM in the reference's notation
+//     (DH/Simulation.cpp:1652,1657,1670,1692).
+//   * tactile readout: per-marker penalty force in the contacted box's frame
+//     (DH/Sensor/TactileSensor.cpp:29-87); its adjoint is hand-written reverse mode
+//     accumulating cotangents on (R2^T R1, R2^T(p1-p2), phi1, phi2) per candidate body
+//     (replaces the 3M x 12 blocks of TactileSensor.cpp:89-235 and the 3M x n products of
+//     Simulation.cpp:811-838).
+#pragma once
+#include "dual.cuh"
+#include "scene_layout.h"
+
+#define TS_EPS 1e-8  // constants::eps of the reference (DH/Common.h)
+
+struct SceneView {
+  const int* ib;
+  const double* db;
+  int nj, n, nu, nee, nmark, nground, ngp, nact, nsens, max_iter, max_ls;
+  int o_joint, o_ground, o_gp, o_act, o_ee, o_sensor;
+  int d_joint, d_ground, d_gp, d_act, d_ee, d_sensor, d_points, d_markers;
+  double h, tol, grav[3], gn[3], gx[3];
+};
+
+HDN inline void scene_view_init(SceneView& S, const int* ib, const double* db) {
+  S.ib = ib; S.db = db;
+  S.nj = ib[TS_I_NJ]; S.n = ib[TS_I_NDOF_R]; S.nu = ib[TS_I_NDOF_U]; S.nee = ib[TS_I_NEE];
+  S.nmark = ib[TS_I_NMARKERS]; S.nground = ib[TS_I_NGROUND]; S.ngp = ib[TS_I_NGP];
+  S.nact = ib[TS_I_NACT]; S.nsens = ib[TS_I_NSENSORS];
+  S.max_iter = ib[TS_I_MAX_ITER]; S.max_ls = ib[TS_I_MAX_LS];
+  S.o_joint = ib[TS_I_OFF_JOINT]; S.o_ground = ib[TS_I_OFF_GROUND]; S.o_gp = ib[TS_I_OFF_GP];
+  S.o_act = ib[TS_I_OFF_ACT]; S.o_ee = ib[TS_I_OFF_EE]; S.o_sensor = ib[TS_I_OFF_SENSOR];
+  S.d_joint = ib[TS_I_DOFF_JOINT]; S.d_ground = ib[TS_I_DOFF_GROUND]; S.d_gp = ib[TS_I_DOFF_GP];
+  S.d_act = ib[TS_I_DOFF_ACT]; S.d_ee = ib[TS_I_DOFF_EE]; S.d_sensor = ib[TS_I_DOFF_SENSOR];
+  S.d_points = ib[TS_I_DOFF_POINTS]; S.d_markers = ib[TS_I_DOFF_MARKERS];
+  S.h = db[TS_D_H]; S.tol = db[TS_D_TOL];
+  for (int i = 0; i < 3; ++i) { S.grav[i] = db[TS_D_GRAV + i]; S.gn[i] = db[TS_D_GN + i]; S.gx[i] = db[TS_D_GX + i]; }
+}
+
+// ------------------------------------------------------------------ small vector algebra
+template <class A, class B, class C> HD void cross3(const A* a, const B* b, C* o) {
+  C x = a[1] * b[2] - a[2] * b[1];
+  C y = a[2] * b[0] - a[0] * b[2];
+  C z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+template <class A, class B> HD auto dot3(const A* a, const B* b) -> decltype(a[0] * b[0]) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+// o = R v   (R row-major 3x3)
+template <class A, class B, class C> HD void mv3(const A* R, const B* v, C* o) {
+  C x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  C y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  C z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+// o = R^T v
+template <class A, class B, class C> HD void mtv3(const A* R, const B* v, C* o) {
+  C x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  C y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  C z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+// O = A B
+template <class A, class B, class C> HD void mm3(const A* a, const B* b, C* o) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+// twist to a child frame: given E = (R,p) of the child expressed in the parent,
+// out = Ad(E^-1) in :  w' = R^T w,  v' = R^T (v + w x p)
+template <class A, class B, class C> HD void twist_to_child(const A* R, const A* p, const B* in, C* out) {
+  C t[3];
+  cross3(in, p, t);
+  t[0] = t[0] + in[3]; t[1] = t[1] + in[4]; t[2] = t[2] + in[5];
+  mtv3(R, in, out);
+  mtv3(R, t, out + 3);
+}
+// wrench to the parent frame: out = Ad(E^-1)^T in :  f' = R f,  tau' = R tau + p x f'
+template <class A, class B, class C> HD void wrench_to_parent(const A* R, const A* p, const B* in, C* out) {
+  C f[3], t[3], pf[3];
+  mv3(R, in + 3, f);
+  mv3(R, in, t);
+  cross3(p, f, pf);
+  out[0] = t[0] + pf[0]; out[1] = t[1] + pf[1]; out[2] = t[2] + pf[2];
+  out[3] = f[0]; out[4] = f[1]; out[5] = f[2];
+}
+
+// ------------------------------------------------------------------ per-lane work space
+template <class T> struct Work {
+  T Rpj[TS_MAXJ][9], ppj[TS_MAXJ][3];   // joint frame in its parent joint frame
+  T R0j[TS_MAXJ][9], p0j[TS_MAXJ][3];   // joint frame in the world
+  T phj[TS_MAXJ][6], psj[TS_MAXJ][6], etj[TS_MAXJ][6];
+  T R0i[TS_MAXJ][9], p0i[TS_MAXJ][3];   // body frame in the world
+  T phi[TS_MAXJ][6];                    // body twist (angular; linear), body frame
+  T a[TS_MAXJ][6];                      // body wrench  I psi - h^2 (f - I eta)
+  T bj[TS_MAXJ][6];                     // joint-frame wrench accumulated from the subtree
+};
+
+// Outward sweep.  dyn=false computes poses and twists only (readout / adjoint use).
+template <class T>
+HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Work<T>& W, bool dyn) {
+  const double h2 = S.h * S.h;
+  for (int j = 0; j < S.nj; ++j) {
+    const int* ji = S.ib + S.o_joint + j * TS_JI_STRIDE;
+    const double* jd = S.db + S.d_joint + j * TS_JD_STRIDE;
+    const int jt = ji[0], par = ji[1], qo = ji[2];
+    const double* R0 = jd + TS_JD_RPJ;
+    const double* p0 = jd + TS_JD_PPJ;
+    const double* a0 = jd + TS_JD_AX0;
+    const double* a1 = jd + TS_JD_AX1;
+    T sq[6], sd[6], pq[3];
+    for (int i = 0; i < 6; ++i) { sq[i] = 0.0; sd[i] = 0.0; }
+    pq[0] = 0.0; pq[1] = 0.0; pq[2] = 0.0;
+    T* Rpj = W.Rpj[j];
+    T* ppj = W.ppj[j];
+    if (jt == TS_JT_REVOLUTE) {          // Q = exp([axis] q)      (DH/Joint/JointRevolute.cpp:38-69)
+      T s, c;
+      dsincos(q[qo], s, c);
+      T c1 = 1.0 - c;
+      T Rq[9];
+      Rq[0] = c + c1 * (a0[0] * a0[0]); Rq[1] = c1 * (a0[0] * a0[1]) - s * a0[2]; Rq[2] = c1 * (a0[0] * a0[2]) + s * a0[1];
+      Rq[3] = c1 * (a0[1] * a0[0]) + s * a0[2]; Rq[4] = c + c1 * (a0[1] * a0[1]); Rq[5] = c1 * (a0[1] * a0[2]) - s * a0[0];
+      Rq[6] = c1 * (a0[2] * a0[0]) - s * a0[1]; Rq[7] = c1 * (a0[2] * a0[1]) + s * a0[0]; Rq[8] = c + c1 * (a0[2] * a0[2]);
+      mm3(R0, Rq, Rpj);
+      for (int i = 0; i < 3; ++i) { sq[i] = a0[i] * qd[qo]; if (dyn) sd[i] = a0[i] * dl[qo]; }
+    } else {
+      for (int i = 0; i < 9; ++i) Rpj[i] = R0[i];
+      if (jt == TS_JT_PRISMATIC) {       // DH/Joint/JointPrismatic.cpp:22-45
+        for (int i = 0; i < 3; ++i) { pq[i] = a0[i] * q[qo]; sq[3 + i] = a0[i] * qd[qo]; if (dyn) sd[3 + i] = a0[i] * dl[qo]; }
+      } else if (jt == TS_JT_PLANAR) {   // DH/Joint/JointPlanar.cpp:7-33
+        for (int i = 0; i < 3; ++i) {
+          pq[i] = a0[i] * q[qo] + a1[i] * q[qo + 1];
+          sq[3 + i] = a0[i] * qd[qo] + a1[i] * qd[qo + 1];
+          if (dyn) sd[3 + i] = a0[i] * dl[qo] + a1[i] * dl[qo + 1];
+        }
+      } else if (jt == TS_JT_TRANSLATIONAL) {  // DH/Joint/JointTranslational.cpp:9-40
+        for (int i = 0; i < 3; ++i) { pq[i] = q[qo + i]; sq[3 + i] = qd[qo + i]; if (dyn) sd[3 + i] = dl[qo + i]; }
+      }
+    }
+    mv3(R0, pq, ppj);
+    ppj[0] = ppj[0] + p0[0]; ppj[1] = ppj[1] + p0[1]; ppj[2] = ppj[2] + p0[2];
+    T* R0j = W.R0j[j];
+    T* p0j = W.p0j[j];
+    T* phj = W.phj[j];
+    T* psj = W.psj[j];
+    T* etj = W.etj[j];
+    if (par < 0) {
+      for (int i = 0; i < 9; ++i) R0j[i] = Rpj[i];
+      for (int i = 0; i < 3; ++i) p0j[i] = ppj[i];
+      for (int i = 0; i < 6; ++i) { phj[i] = sq[i]; psj[i] = sd[i]; etj[i] = 0.0; }
+    } else {
+      mm3(W.R0j[par], Rpj, R0j);
+      mv3(W.R0j[par], ppj, p0j);
+      for (int i = 0; i < 3; ++i) p0j[i] = p0j[i] + W.p0j[par][i];
+      T b[6];
+      twist_to_child(Rpj, ppj, W.phj[par], b);
+      for (int i = 0; i < 6; ++i) phj[i] = sq[i] + b[i];
+      if (dyn) {
+        T t[6];
+        twist_to_child(Rpj, ppj, W.psj[par], t);
+        for (int i = 0; i < 6; ++i) psj[i] = sd[i] + t[i];
+        // eta_j = Ad(E_jp) eta_p - ad(S qd)(Ad(E_jp) phi_p)    (time derivative of Ad(E_jp))
+        twist_to_child(Rpj, ppj, W.etj[par], t);
+        T c0[3], c1[3], c2[3];
+        cross3(sq, b, c0);           // aw x bw
+        cross3(sq + 3, b, c1);       // av x bw
+        cross3(sq, b + 3, c2);       // aw x bv
+        for (int i = 0; i < 3; ++i) { etj[i] = t[i] - c0[i]; etj[3 + i] = t[3 + i] - (c1[i] + c2[i]); }
+      }
+    }
+    for (int i = 0; i < 6; ++i) W.bj[j][i] = 0.0;
+    // body rigidly attached to the joint frame by E_ji            (DH/Body/Body.cpp:122-141)
+    const double* Rji = jd + TS_JD_RJI;
+    const double* pji = jd + TS_JD_PJI;
+    T* R0i = W.R0i[j];
+    T* p0i = W.p0i[j];
+    mm3(R0j, Rji, R0i);
+    mv3(R0j, pji, p0i);
+    for (int i = 0; i < 3; ++i) p0i[i] = p0i[i] + p0j[i];
+    T* ph = W.phi[j];
+    twist_to_child(Rji, pji, phj, ph);
+    if (dyn) {
+      const double* I6 = jd + TS_JD_INERTIA;
+      T ps[6], et[6];
+      twist_to_child(Rji, pji, psj, ps);
+      twist_to_child(Rji, pji, etj, et);
+      // coriolis ad(phi)^T (I phi) and gravity (0; m R^T g)      (DH/Body/Body.cpp:234-247)
+      T Iw[3], mv[3], fc0[3], fc1[3], fc2[3], gb[3];
+      for (int i = 0; i < 3; ++i) { Iw[i] = I6[i] * ph[i]; mv[i] = I6[3 + i] * ph[3 + i]; }
+      cross3(Iw, ph, fc0);
+      cross3(mv, ph + 3, fc1);
+      cross3(mv, ph, fc2);
+      mtv3(R0i, S.grav, gb);
+      T* a = W.a[j];
+      for (int i = 0; i < 3; ++i) {
+        a[i] = I6[i] * ps[i] - h2 * ((fc0[i] + fc1[i]) - I6[i] * et[i]);
+        a[3 + i] = I6[3 + i] * ps[3 + i] - h2 * ((fc2[i] + I6[3] * gb[i]) - I6[3 + i] * et[3 + i]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ cuboid SDF face pick
+// (DH/Body/BodyCuboid.cpp:162-173: strict '>' scanned +x,-x,+y,-y,+z,-z)
+HD double cuboid_face(const double* x, const double* hs, int& axis, double& sgn) {
+  double d = -9999999.0;
+  axis = 0; sgn = 1.0;
+  for (int i = 0; i < 3; ++i) {
+    if (x[i] - hs[i] > d) { d = x[i] - hs[i]; axis = i; sgn = 1.0; }
+    if (-x[i] - hs[i] > d) { d = -x[i] - hs[i]; axis = i; sgn = -1.0; }
+  }
+  return d;
+}
+HD double cuboid_distance(const double* x, const double* hs) {
+  double d = -99999999.0;
+  for (int i = 0; i < 3; ++i) { d = fmax(d, fmax(x[i] - hs[i], -x[i] - hs[i])); }
+  return d;
+}
+
+// ------------------------------------------------------------------ contact forces
+// ground plane vs sampled body points: DH/Force/ForceGroundContact.cpp:105-147,
+// detection d <= 0: DH/CollisionDetection/CollisionDetection.cpp:13-42
+template <class T>
+HDN void ground_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out) {
+  const double h2 = S.h * S.h;
+  for (int gi = 0; gi < S.nground; ++gi) {
+    const int* r = S.ib + S.o_ground + gi * TS_GI_STRIDE;
+    const double* c = S.db + S.d_ground + gi * TS_CD_STRIDE;
+    const int b = r[0], po = r[1], pc = r[2];
+    const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
+    const T* R = W.R0i[b];
+    const T* p = W.p0i[b];
+    const T* ph = W.phi[b];
+    T wr[6];
+    for (int i = 0; i < 6; ++i) wr[i] = 0.0;
+    for (int k = 0; k < pc; ++k) {
+      const double* xi = S.db + S.d_points + 3 * (po + k);
+      T xw[3];
+      mv3(R, xi, xw);
+      T d = (xw[0] + p[0] - S.gx[0]) * S.gn[0] + (xw[1] + p[1] - S.gx[1]) * S.gn[1] + (xw[2] + p[2] - S.gx[2]) * S.gn[2];
+      if (!(val(d) <= 0.0)) continue;
+      if (mask_out && k < 32) mask_out[gi] |= (1u << k);
+      T w[3], vw[3];
+      cross3(ph, xi, w);
+      w[0] = w[0] + ph[3]; w[1] = w[1] + ph[4]; w[2] = w[2] + ph[5];
+      mv3(R, w, vw);
+      T vn = dot3(vw, S.gn);
+      T F[3], a[3];
+      for (int i = 0; i < 3; ++i) {
+        F[i] = -kn * S.gn[i] * d - damp * S.gn[i] * vn;
+        a[i] = vw[i] - S.gn[i] * vn;
+      }
+      if (!(mu < TS_EPS)) {
+        double an = sqrt(val(a[0]) * val(a[0]) + val(a[1]) * val(a[1]) + val(a[2]) * val(a[2]));
+        if (mu * fabs(kn * val(d)) >= kt * an - TS_EPS) {
+          for (int i = 0; i < 3; ++i) F[i] = F[i] - kt * a[i];
+        } else {
+          T anT = dsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+          T sc = (mu * kn) * d / anT;
+          for (int i = 0; i < 3; ++i) F[i] = F[i] + sc * a[i];
+        }
+      }
+      T Fb[3], tq[3];
+      mtv3(R, F, Fb);
+      cross3(xi, Fb, tq);
+      for (int i = 0; i < 3; ++i) { wr[i] = wr[i] + tq[i]; wr[3 + i] = wr[3 + i] + Fb[i]; }
+    }
+    for (int i = 0; i < 6; ++i) W.a[b][i] = W.a[b][i] - h2 * wr[i];
+  }
+}
+
+// sampled points of a general body vs a cuboid SDF: DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
+// DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83
+template <class T>
+HDN void gp_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out /* 3 words per force */) {
+  const double h2 = S.h * S.h;
+  for (int fi = 0; fi < S.ngp; ++fi) {
+    const int* r = S.ib + S.o_gp + fi * TS_PI_STRIDE;
+    const double* c = S.db + S.d_gp + fi * TS_CD_STRIDE;
+    const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
+    const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
+    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+    const T* R1 = W.R0i[b1]; const T* p1 = W.p0i[b1]; const T* ph1 = W.phi[b1];
+    const T* R2 = W.R0i[b2]; const T* p2 = W.p0i[b2]; const T* ph2 = W.phi[b2];
+    T w1[6], w2[6];
+    for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+    for (int k = 0; k < pc; ++k) {
+      const double* xi1 = S.db + S.d_points + 3 * (po + k);
+      T xw[3], y[3], x[3];
+      mv3(R1, xi1, xw);
+      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
+      mtv3(R2, y, x);
+      double xv[3] = {val(x[0]), val(x[1]), val(x[2])};
+      if (!(cuboid_distance(xv, hs) < 0.0)) continue;
+      if (mask_out && k < 96) mask_out[3 * fi + (k >> 5)] |= (1u << (k & 31));
+      int ax; double sg;
+      cuboid_face(xv, hs, ax, sg);
+      T d = sg * x[ax] - hs[ax];
+      // velocities: point of body 1 (pad frame), relative velocity in the box frame
+      T v1[3], xwd[3], u[3], t3[3];
+      cross3(ph1, xi1, v1);
+      v1[0] = v1[0] + ph1[3]; v1[1] = v1[1] + ph1[4]; v1[2] = v1[2] + ph1[5];
+      mv3(R1, v1, xwd);
+      mtv3(R2, xwd, u);
+      cross3(ph2, x, t3);
+      for (int i = 0; i < 3; ++i) u[i] = u[i] - t3[i] - ph2[3 + i];          // u = R2^T xw_dot - w2 x x - v2
+      T ddot = sg * u[ax];
+      // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
+      T tb[3];
+      double e[3] = {0.0, 0.0, 0.0};
+      e[ax] = sg;
+      cross3(ph2, e, t3);
+      for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
+      tb[ax] = tb[ax] - sg * (sg * tb[ax]);
+      T s = kn * d - damp * ddot * d;
+      // n1 = R1^T R2 e ; normal wrench on body 1 = -s (xi1 x n1; n1)
+      T nw[3], n1[3], m1[3];
+      for (int i = 0; i < 3; ++i) nw[i] = sg * R2[3 * i + ax];
+      mtv3(R1, nw, n1);
+      cross3(xi1, n1, m1);
+      T Fb[3];
+      for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
+      if (mu > TS_EPS) {
+        // the reference uses the norm of the 6-vector wrench on body 1 (:208)
+        double n6 = 0.0;
+        for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
+        double fcn = fabs(val(s)) * sqrt(n6);
+        double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
+        if (mu * fcn >= kt * tn - TS_EPS) {
+          for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
+        } else {
+          T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+          T fcT = dabs(s) * dsqrt(n6T);
+          T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
+          T sc = mu * fcT / tnT;
+          for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+        }
+      }
+      // wrenches: body 2 gets -Gamma(xi2)^T Fb with xi2 = x - d e ; body 1 gets Gamma(xi1)^T R1^T R2 Fb
+      T xi2[3], tq[3], Fw[3], F1[3];
+      for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
+      cross3(xi2, Fb, tq);
+      for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
+      mv3(R2, Fb, Fw);
+      mtv3(R1, Fw, F1);
+      cross3(xi1, F1, tq);
+      for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + F1[i]; }
+    }
+    for (int i = 0; i < 6; ++i) {
+      W.a[b1][i] = W.a[b1][i] - h2 * w1[i];
+      W.a[b2][i] = W.a[b2][i] - h2 * w2[i];
+    }
+  }
+}
+
+// FORCE motor: clamp, affine map to ctrl_range, clamp  (DH/Actuator/ActuatorMotor.cpp:31-36, Utils.h:384-386)
+HD double motor_force(double u, double cmin, double cmax) {
+  double uc = fmax(fmin(u, 1.0), -1.0);
+  double f = (uc - (-1.0)) * (1.0 / (1.0 - (-1.0))) * (cmax - cmin) + cmin;
+  return fmax(fmin(f, cmax), cmin);
+}
+
+// Inward sweep: g = J^T a - h^2 (joint damping + limit springs + motors)
+template <class T>
+HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const double* u, T* g) {
+  const double h2 = S.h * S.h;
+  for (int j = S.nj - 1; j >= 0; --j) {
+    const int* ji = S.ib + S.o_joint + j * TS_JI_STRIDE;
+    const double* jd = S.db + S.d_joint + j * TS_JD_STRIDE;
+    const int jt = ji[0], par = ji[1], qo = ji[2], nd = ji[3];
+    T b[6], t[6];
+    wrench_to_parent(jd + TS_JD_RJI, jd + TS_JD_PJI, W.a[j], t);
+    for (int i = 0; i < 6; ++i) b[i] = W.bj[j][i] + t[i];
+    const double* a0 = jd + TS_JD_AX0;
+    const double* a1 = jd + TS_JD_AX1;
+    if (jt == TS_JT_REVOLUTE) g[qo] = dot3(a0, b);
+    else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, b + 3);
+    else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, b + 3); g[qo + 1] = dot3(a1, b + 3); }
+    else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = b[3]; g[qo + 1] = b[4]; g[qo + 2] = b[5]; }
+    // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
+    const double damp = jd[TS_JD_DAMP], lo = jd[TS_JD_LIMLO], hi = jd[TS_JD_LIMHI], lk = jd[TS_JD_LIMK];
+    for (int i = 0; i < nd; ++i) {
+      T fr = -(damp * qd[qo + i]);
+      if (val(q[qo + i]) < lo) fr = fr + lk * (lo - q[qo + i]);
+      if (val(q[qo + i]) > hi) fr = fr + lk * (hi - q[qo + i]);
+      g[qo + i] = g[qo + i] - h2 * fr;
+    }
+    if (par >= 0) {
+      wrench_to_parent(W.Rpj[j], W.ppj[j], b, t);
+      for (int i = 0; i < 6; ++i) W.bj[par][i] = W.bj[par][i] + t[i];
+    }
+  }
+  for (int ai = 0; ai < S.nact; ++ai) {
+    const int* r = S.ib + S.o_act + ai * TS_AI_STRIDE;
+    const double* c = S.db + S.d_act + ai * TS_AD_STRIDE;
+    const int qo = S.ib[S.o_joint + r[0] * TS_JI_STRIDE + 2];
+    for (int i = 0; i < r[3]; ++i) g[qo + i] = g[qo + i] - h2 * motor_force(u[r[2] + i], c[i], c[3 + i]);
+  }
+}
+
+// residual of the BDF1 step for (q1; q0, qd0)
+template <class T>
+HDN void eval_g(const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W, T* g,
+                unsigned* gmask, unsigned* pmask) {
+  T qd1[TS_MAXN], dl[TS_MAXN];
+  for (int i = 0; i < S.n; ++i) {
+    qd1[i] = (q1[i] - q0[i]) / S.h;
+    dl[i] = q1[i] - q0[i] - S.h * qd0[i];
+  }
+  kinematics<T>(S, q1, qd1, dl, W, true);
+  ground_contacts<T>(S, W, gmask);
+  gp_contacts<T>(S, W, pmask);
+  inward<T>(S, W, q1, qd1, u, g);
+}
+
+// ------------------------------------------------------------------ tile policies
+struct HostTile {
+  static const int LPE = 1;
+  int lane;
+  HostTile() : lane(0) {}
+  HD double bcast(double v, int) const { return v; }
+  HD int bcasti(int v, int) const { return v; }
+  HD double sum(double v) const { return v; }
+  HD int any(int p) const { return p; }
+};
+
+#define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
+
+// Partial-pivot LU solve of the n x n system whose columns are dealt round-robin to the lanes
+// (column k lives in lane k % LPE at slot k / LPE); rhs is replicated and overwritten with the
+// solution.  Pivot = first row of maximal |a| (Eigen partialPivLu, DH/Simulation.cpp:1178).
+template <class Tile>
+HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
+  const int L = Tile::LPE;
+  for (int j = 0; j < n; ++j) {
+    const int own = j % L, sl = j / L;
+    int p = j;
+    if (tl.lane == own) {
+      double best = fabs(col[sl][j]);
+      for (int i = j + 1; i < n; ++i) {
+        double v = fabs(col[sl][i]);
+        if (v > best) { best = v; p = i; }
+      }
+    }
+    p = tl.bcasti(p, own);
+    if (p != j) {
+      for (int c = 0; c < TS_NC(L); ++c) {
+        double t = 0.0, s = 0.0;
+        for (int i = 0; i < TS_MAXN; ++i) { if (i == j) t = col[c][i]; if (i == p) s = col[c][i]; }
+        for (int i = 0; i < TS_MAXN; ++i) { if (i == j) col[c][i] = s; if (i == p) col[c][i] = t; }
+      }
+      double t = 0.0, s = 0.0;
+      for (int i = 0; i < TS_MAXN; ++i) { if (i == j) t = rhs[i]; if (i == p) s = rhs[i]; }
+      for (int i = 0; i < TS_MAXN; ++i) { if (i == j) rhs[i] = s; if (i == p) rhs[i] = t; }
+    }
+    double piv = 0.0, rj = 0.0;
+    for (int i = 0; i < TS_MAXN; ++i) if (i == j) rj = rhs[i];
+    if (tl.lane == own) for (int i = 0; i < TS_MAXN; ++i) if (i == j) piv = col[sl][i];
+    for (int i = 0; i < TS_MAXN; ++i) {
+      if (i <= j || i >= n) continue;
+      double l = 0.0;
+      if (tl.lane == own) l = col[sl][i] / piv;
+      l = tl.bcast(l, own);
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        if (k > j && k < n) {
+          double cj = 0.0;
+          for (int m = 0; m < TS_MAXN; ++m) if (m == j) cj = col[c][m];
+          col[c][i] -= l * cj;
+        }
+      }
+      rhs[i] -= l * rj;
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    const int own = k % L, sl = k / L;
+    double xk = 0.0;
+    if (tl.lane == own) {
+      double rk = 0.0, ukk = 1.0;
+      for (int i = 0; i < TS_MAXN; ++i) if (i == k) { rk = rhs[i]; ukk = col[sl][i]; }
+      xk = rk / ukk;
+    }
+    xk = tl.bcast(xk, own);
+    for (int i = 0; i < TS_MAXN; ++i) {
+      if (i == k) rhs[i] = xk;
+      if (i < k) {
+        double c = 0.0;
+        if (tl.lane == own) c = col[sl][i] * xk;
+        c = tl.bcast(c, own);
+        rhs[i] -= c;
+      }
+    }
+  }
+}
+
+HD double norm_n(const double* v, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += v[i] * v[i];
+  return sqrt(s);
+}
+
+// One Dual evaluation per owned column: returns g (replicated) and the owned columns of
+// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.
+template <class Tile>
+HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0, const double* qd0,
+                      const double* u, int seed, Work<Dual>& W, double* g, double (*col)[TS_MAXN]) {
+  const int L = Tile::LPE;
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    Dual xq[TS_MAXN], xq0[TS_MAXN], xqd0[TS_MAXN], gD[TS_MAXN];
+    for (int i = 0; i < S.n; ++i) {
+      xq[i] = mkdual(x[i], (seed == 0 && i == k) ? 1.0 : 0.0);
+      xq0[i] = mkdual(q0[i], (seed == 1 && i == k) ? 1.0 : 0.0);
+      xqd0[i] = mkdual(qd0[i], (seed == 2 && i == k) ? 1.0 : 0.0);
+    }
+    eval_g<Dual>(S, xq, xq0, xqd0, u, W, gD, (unsigned*)0, (unsigned*)0);
+    for (int i = 0; i < TS_MAXN; ++i) {
+      if (i < S.n) { g[i] = gD[i].v; col[c][i] = (k < S.n) ? gD[i].d : 0.0; }
+      else { g[i] = 0.0; col[c][i] = 0.0; }
+    }
+  }
+}
+
+// status word per env-step: newton iterations | line-search evaluations << 8 | flags << 16
+#define TS_STAT_NOT_CONVERGED (1 << 16)
+#define TS_STAT_NAN (1 << 17)
+
+// One implicit step (DH/Simulation.cpp:1325-1351 with the Newton of :1150-1225).
+// q, qd: in = state at t, out = state at t+h (replicated over the tile).
+// tape (grad mode): H, G0, G1 as [3][n][n] row-major, columns written by their owner lanes.
+template <class Tile>
+HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, const double* u,
+                     double* tape, void* workbuf) {
+  const int L = Tile::LPE;
+  const int n = S.n;
+  Work<Dual>& WD = *(Work<Dual>*)workbuf;
+  Work<double>& WS = *(Work<double>*)workbuf;
+  double x[TS_MAXN], g[TS_MAXN], gn_[TS_MAXN], dx[TS_MAXN], xn[TS_MAXN];
+  double col[TS_NC(L)][TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; gn_[i] = 0.0; }
+  for (int i = 0; i < n; ++i) x[i] = q[i] + S.h * qd[i];
+  int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
+  int fail_strike = 0, iters = 0, ls = 0;
+  bool converged = false;
+  for (int it = 0; it < max_newton; ++it) {
+    ++iters;
+    eval_columns(tl, S, x, q, qd, u, 0, WD, g, col);
+    for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -g[i] : 0.0;
+    lu_solve(tl, col, dx, n);
+    const double gnorm = norm_n(g, n);
+    double alpha = 1.0;
+    bool success = false;
+    for (int trial = 0; trial < S.max_ls; ++trial, alpha *= 0.5) {
+      ++ls;
+      for (int i = 0; i < n; ++i) xn[i] = x[i] + alpha * dx[i];
+      eval_g<double>(S, xn, q, qd, u, WS, gn_, (unsigned*)0, (unsigned*)0);
+      if (norm_n(gn_, n) < gnorm) { success = true; break; }
+    }
+    if (success) fail_strike = 0;
+    else { ++fail_strike; if (fail_strike >= 10) break; }
+    for (int i = 0; i < n; ++i) x[i] = x[i] + alpha * dx[i];
+    if (norm_n(gn_, n) < S.tol) { converged = true; break; }
+  }
+  int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
+  if (tape) {
+    // adjoint tape at the converged state: H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0
+    for (int s = 0; s < 3; ++s) {
+      eval_columns(tl, S, x, q, qd, u, s, WD, g, col);
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        if (k < n) for (int i = 0; i < n; ++i) tape[s * n * n + i * n + k] = col[c][i];
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double q1 = x[i];
+    qd[i] = (q1 - q[i]) / S.h;
+    q[i] = q1;
+    if (!(q1 == q1)) stat |= TS_STAT_NAN;
+  }
+  return stat;
+}
+
+// ------------------------------------------------------------------ readouts at a state
+// end-effector positions (DH/EndEffector/EndEffector.cpp:31-36)
+template <class T>
+HD void variable_of(const SceneView& S, const Work<T>& W, int e, T* out) {
+  const int j = S.ib[S.o_ee + e * TS_EI_STRIDE];
+  const double* pos = S.db + S.d_ee + e * TS_ED_STRIDE;
+  mv3(W.R0j[j], pos, out);
+  for (int i = 0; i < 3; ++i) out[i] = out[i] + W.p0j[j][i];
+}
+
+// per-marker intermediate of the tactile force, shared by the value pass and its adjoint
+struct MarkerHit {
+  int body;           // contacted body (last candidate with d < 0), -1 if none
+  int ax; double sg;  // face of the box
+  double x[3], u[3], d, ddot, tb[3], s, tn;
+  bool dynamic;
+};
+
+// Evaluate marker m of sensor record (sr, sd).  DH/Sensor/TactileSensor.cpp:29-87
+HD void marker_force(const SceneView& S, const Work<double>& W, const int* sr, const double* sd, const double* xi1,
+                     MarkerHit& H, double* F1 /* force in the pad frame */) {
+  const int b1 = sr[0], nc = sr[3];
+  const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
+  const double* R1 = W.R0i[b1]; const double* p1 = W.p0i[b1]; const double* ph1 = W.phi[b1];
+  double xw[3];
+  mv3(R1, xi1, xw);
+  for (int i = 0; i < 3; ++i) xw[i] += p1[i];
+  H.body = -1;
+  for (int c = 0; c < nc; ++c) {
+    const int b2 = sr[4 + c];
+    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+    double y[3], x[3];
+    for (int i = 0; i < 3; ++i) y[i] = xw[i] - W.p0i[b2][i];
+    mtv3(W.R0i[b2], y, x);
+    if (cuboid_distance(x, hs) < 0.0) { H.body = b2; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
+  }
+  F1[0] = F1[1] = F1[2] = 0.0;
+  if (H.body < 0) return;
+  const int b2 = H.body;
+  const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+  const double* R2 = W.R0i[b2]; const double* ph2 = W.phi[b2];
+  H.d = cuboid_face(H.x, hs, H.ax, H.sg);
+  double v1[3], xwd[3], t3[3];
+  cross3(ph1, xi1, v1);
+  for (int i = 0; i < 3; ++i) v1[i] += ph1[3 + i];
+  mv3(R1, v1, xwd);
+  mtv3(R2, xwd, H.u);
+  cross3(ph2, H.x, t3);
+  for (int i = 0; i < 3; ++i) H.u[i] = H.u[i] - t3[i] - ph2[3 + i];
+  H.ddot = H.sg * H.u[H.ax];
+  double e[3] = {0.0, 0.0, 0.0};
+  e[H.ax] = H.sg;
+  cross3(ph2, e, t3);
+  for (int i = 0; i < 3; ++i) H.tb[i] = H.u[i] + H.d * t3[i];
+  H.tb[H.ax] -= H.sg * (H.sg * H.tb[H.ax]);
+  H.s = kn * H.d - damp * H.ddot * H.d;
+  double Fb[3];
+  for (int i = 0; i < 3; ++i) Fb[i] = -(H.s * e[i]);
+  H.dynamic = false;
+  H.tn = sqrt(H.tb[0] * H.tb[0] + H.tb[1] * H.tb[1] + H.tb[2] * H.tb[2]);
+  if (mu > TS_EPS) {
+    const double fcn = fabs(H.s);   // |fc| of the 3-vector -s R1^T n
+    if (mu * fcn >= kt * H.tn - TS_EPS) {
+      for (int i = 0; i < 3; ++i) Fb[i] -= kt * H.tb[i];
+    } else {
+      H.dynamic = true;
+      const double sc = mu * fcn / H.tn;
+      for (int i = 0; i < 3; ++i) Fb[i] -= sc * H.tb[i];
+    }
+  }
+  double Fw[3];
+  mv3(R2, Fb, Fw);
+  mtv3(R1, Fw, F1);
+}
+
+// tactile values of this env, markers strided over the tile's lanes.
+// out: [M][3] = (shear . axis0, shear . axis1, normal)      (TactileSensor.cpp:74-81)
+template <class Tile>
+HDN void tactile_values(const Tile& tl, const SceneView& S, const Work<double>& W, double* out, int* body_out) {
+  for (int si = 0; si < S.nsens; ++si) {
+    const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
+    const double* sd = S.db + S.d_sensor + si * TS_SD_STRIDE;
+    const int mo = sr[1], mc = sr[2];
+    for (int m = tl.lane; m < mc; m += Tile::LPE) {
+      const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
+      MarkerHit H;
+      double F1[3];
+      marker_force(S, W, sr, sd, xi1, H, F1);
+      double* o = out + 3 * (mo + m);
+      o[0] = dot3(F1, sd + 4);
+      o[1] = dot3(F1, sd + 7);
+      o[2] = -dot3(F1, sd + 10);
+      if (body_out) body_out[mo + m] = H.body;
+    }
+  }
+}
+
+// cotangent accumulators of the tactile adjoint for one candidate body:
+// R21 = R2^T R1 (9), r = R2^T (p1 - p2) (3), phi1 (6), phi2 (6)
+struct TacAcc {
+  double v[24];
+};
+
+// Reverse-mode through marker_force for every marker of this lane's stride.
+template <class Tile>
+HDN void tactile_vjp(const Tile& tl, const SceneView& S, const Work<double>& W, const double* wbar, TacAcc* acc) {
+  for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = 0.0;
+  for (int si = 0; si < S.nsens; ++si) {
+    const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
+    const double* sd = S.db + S.d_sensor + si * TS_SD_STRIDE;
+    const int b1 = sr[0], mo = sr[1], mc = sr[2], nc = sr[3];
+    const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
+    const double* R1 = W.R0i[b1]; const double* ph1 = W.phi[b1];
+    for (int m = tl.lane; m < mc; m += Tile::LPE) {
+      const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
+      const double* wb = wbar + 3 * (mo + m);
+      MarkerHit H;
+      double F1[3];
+      marker_force(S, W, sr, sd, xi1, H, F1);
+      if (H.body < 0) continue;
+      int ci = 0;
+      for (int c = 0; c < nc; ++c) if (sr[4 + c] == H.body) ci = c;
+      double* A = acc[ci].v;
+      const double* R2 = W.R0i[H.body]; const double* ph2 = W.phi[H.body];
+      double R21[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R21[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
+      double e[3] = {0.0, 0.0, 0.0};
+      e[H.ax] = H.sg;
+      // F1 = R21^T Fb ; tau = P^T F1 with P = [axis0, axis1, -normal]
+      double F1b[3], Fbb[3], Fb[3];
+      for (int i = 0; i < 3; ++i) F1b[i] = sd[4 + i] * wb[0] + sd[7 + i] * wb[1] - sd[10 + i] * wb[2];
+      mv3(R21, F1b, Fbb);
+      // recompute Fb (box frame) for the R21 cotangent
+      for (int i = 0; i < 3; ++i) Fb[i] = -(H.s * e[i]);
+      double sbar, tbar[3];
+      if (!(mu > TS_EPS)) {
+        sbar = -dot3(e, Fbb);
+        tbar[0] = tbar[1] = tbar[2] = 0.0;
+      } else if (!H.dynamic) {
+        for (int i = 0; i < 3; ++i) Fb[i] -= kt * H.tb[i];
+        sbar = -dot3(e, Fbb);
+        for (int i = 0; i < 3; ++i) tbar[i] = -kt * Fbb[i];
+      } else {
+        const double as = fabs(H.s), sgn = H.s < 0.0 ? -1.0 : 1.0;
+        const double sc = mu * as / H.tn;
+        for (int i = 0; i < 3; ++i) Fb[i] -= sc * H.tb[i];
+        const double tF = dot3(H.tb, Fbb);
+        sbar = -dot3(e, Fbb) - mu * sgn * tF / H.tn;
+        for (int i = 0; i < 3; ++i) tbar[i] = -mu * as * (Fbb[i] / H.tn - H.tb[i] * tF / (H.tn * H.tn * H.tn));
+      }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[3 * i + j] += Fb[i] * F1b[j];
+      double dbar = sbar * (kn - damp * H.ddot);
+      double ddbar = -sbar * damp * H.d;
+      // tb = (I - e e^T) u + d (w2 x e)
+      double ubar[3], w2e[3], t3[3];
+      for (int i = 0; i < 3; ++i) ubar[i] = tbar[i];
+      ubar[H.ax] -= H.sg * (H.sg * tbar[H.ax]);
+      cross3(ph2, e, w2e);
+      dbar += dot3(tbar, w2e);
+      cross3(e, tbar, t3);
+      double w2bar[3], v2bar[3], xbar[3];
+      for (int i = 0; i < 3; ++i) w2bar[i] = H.d * t3[i];
+      for (int i = 0; i < 3; ++i) ubar[i] += ddbar * e[i];
+      for (int i = 0; i < 3; ++i) xbar[i] = dbar * e[i];
+      // u = R21 w - w2 x x - v2 ,  w = w1 x xi1 + v1
+      double w[3], wbar_[3];
+      cross3(ph1, xi1, w);
+      for (int i = 0; i < 3; ++i) w[i] += ph1[3 + i];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[3 * i + j] += ubar[i] * w[j];
+      mtv3(R21, ubar, wbar_);
+      cross3(ubar, H.x, t3);
+      for (int i = 0; i < 3; ++i) w2bar[i] += t3[i];
+      cross3(ph2, ubar, t3);
+      for (int i = 0; i < 3; ++i) { xbar[i] += t3[i]; v2bar[i] = -ubar[i]; }
+      cross3(xi1, wbar_, t3);
+      for (int i = 0; i < 3; ++i) { A[12 + i] += t3[i]; A[15 + i] += wbar_[i]; }
+      for (int i = 0; i < 3; ++i) { A[18 + i] += w2bar[i]; A[21 + i] += v2bar[i]; }
+      // x = R21 xi1 + r
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[3 * i + j] += xbar[i] * xi1[j];
+      for (int i = 0; i < 3; ++i) A[9 + i] += xbar[i];
+    }
+  }
+  for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = tl.sum(acc[c].v[i]);
+}
+
+// body-frame Jacobian column from a Dual pose: w = axial(R^T dR), v = R^T dp
+HD void jac_col(const Dual* R, const Dual* p, double* J) {
+  J[0] = R[2].v * R[1].d + R[5].v * R[4].d + R[8].v * R[7].d;   // (R^T dR)[2][1]
+  J[1] = R[0].v * R[2].d + R[3].v * R[5].d + R[6].v * R[8].d;   // (R^T dR)[0][2]
+  J[2] = R[1].v * R[0].d + R[4].v * R[3].d + R[7].v * R[6].d;   // (R^T dR)[1][0]
+  J[3] = R[0].v * p[0].d + R[3].v * p[1].d + R[6].v * p[2].d;
+  J[4] = R[1].v * p[0].d + R[4].v * p[1].d + R[7].v * p[2].d;
+  J[5] = R[2].v * p[0].d + R[5].v * p[1].d + R[8].v * p[2].d;
+}
+
+// One reverse step of the BDF1 adjoint (DH/Simulation.cpp:1619-1713 / :1921-1971) in
+// "pending contribution" form: pendA = everything later steps add to y_k, pendB = what step
+// k+1 adds to y_{k-1}.  Both are distributed (slot c of lane l holds dof l + c*LPE).
+//   y_k = df_dq_k + dvar_dq^T b + dtac_dq^T w + (1/h) dtac_dqdot^T w - pendA
+//   z_k = H_k^-T y_k ;  df_du_k = h^2 dfr_du^T z_k
+//   pendA' = pendB + (G0 + G1/h)^T z_k + (1/h) dtac_dqdot^T w ;  pendB' = -(G1/h)^T z_k
+// out_g0z / out_g1z / out_c (optional, distributed) expose G0^T z, G1^T z and
+// (1/h) dtac_dqdot^T w for the q0 / qdot0 gradients of the first step.
+template <class Tile>
+HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, const double* qdk, const double* uk,
+                       const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
+                       double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
+                       double* out_c, void* workbuf) {
+  const int L = Tile::LPE;
+  const int n = S.n;
+  double y[TS_NC(L)], cterm[TS_NC(L)];
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    y[c] = (k < n && dq_cot) ? dq_cot[k] : 0.0;
+    if (k < n) y[c] -= pendA[c];
+    cterm[c] = 0.0;
+  }
+  const bool have_var = dvar_cot != 0 && S.nee > 0;
+  const bool have_tac = dtac_cot != 0 && S.nmark > 0;
+  if (have_var || have_tac) {
+    TacAcc acc[TS_MAXCAND];
+    if (have_tac) {
+      Work<double>& WS = *(Work<double>*)workbuf;
+      kinematics<double>(S, qk, qdk, (const double*)0, WS, false);
+      tactile_vjp(tl, S, WS, dtac_cot, acc);
+    }
+    Work<Dual>& WD = *(Work<Dual>*)workbuf;
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      Dual xq[TS_MAXN], xqd[TS_MAXN];
+      for (int i = 0; i < n; ++i) { xq[i] = mkdual(qk[i], (i == k) ? 1.0 : 0.0); xqd[i] = mkdual(qdk[i], 0.0); }
+      kinematics<Dual>(S, xq, xqd, (const Dual*)0, WD, false);
+      double yk = 0.0, ck = 0.0;
+      if (have_var) {
+        for (int e = 0; e < S.nee; ++e) {
+          Dual v[3];
+          variable_of<Dual>(S, WD, e, v);
+          yk += v[0].d * dvar_cot[3 * e] + v[1].d * dvar_cot[3 * e + 1] + v[2].d * dvar_cot[3 * e + 2];
+        }
+      }
+      if (have_tac) {
+        for (int si = 0; si < S.nsens; ++si) {
+          const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
+          const int b1 = sr[0], nc = sr[3];
+          double J1[6];
+          jac_col(WD.R0i[b1], WD.p0i[b1], J1);
+          for (int ci = 0; ci < nc; ++ci) {
+            const double* A = acc[ci].v;
+            double nz = 0.0;
+            for (int i = 0; i < 24; ++i) nz += fabs(A[i]);
+            if (nz == 0.0) continue;
+            const int b2 = sr[4 + ci];
+            const Dual* R1 = WD.R0i[b1]; const Dual* R2 = WD.R0i[b2];
+            // R21 = R2^T R1, r = R2^T (p1 - p2) on Duals; take the tangents
+            for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 3; ++j) {
+                Dual r = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
+                yk += A[3 * i + j] * r.d;
+              }
+            Dual dp[3], rr[3];
+            for (int i = 0; i < 3; ++i) dp[i] = WD.p0i[b1][i] - WD.p0i[b2][i];
+            mtv3(R2, dp, rr);
+            double J2[6];
+            jac_col(WD.R0i[b2], WD.p0i[b2], J2);
+            for (int i = 0; i < 3; ++i) yk += A[9 + i] * rr[i].d;
+            for (int i = 0; i < 6; ++i) {
+              yk += A[12 + i] * WD.phi[b1][i].d + A[18 + i] * WD.phi[b2][i].d;
+              ck += A[12 + i] * J1[i] + A[18 + i] * J2[i];
+            }
+          }
+        }
+      }
+      if (k < n) { cterm[c] = ck / S.h; y[c] += yk + cterm[c]; }
+    }
+  }
+  // gather y, solve H^T z = y (lane owning dof k loads row k of H = column k of H^T)
+  double z[TS_MAXN];
+  double col[TS_NC(L)][TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) z[i] = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double v = 0.0;
+    for (int c = 0; c < TS_NC(L); ++c) if (tl.lane + c * L == k) v = y[c];
+    v = tl.bcast(v, k % L);
+    for (int i = 0; i < TS_MAXN; ++i) if (i == k) z[i] = v;
+  }
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    for (int i = 0; i < TS_MAXN; ++i) col[c][i] = (k < n && i < n) ? tape[k * n + i] : 0.0;
+  }
+  lu_solve(tl, col, z, n);
+  // controls: dg/du = -h^2 dfr/du, FORCE motors (DH/Actuator/ActuatorMotor.cpp:48-55)
+  if (du_out && tl.lane == 0) {
+    for (int ai = 0; ai < S.nact; ++ai) {
+      const int* r = S.ib + S.o_act + ai * TS_AI_STRIDE;
+      const double* cdat = S.db + S.d_act + ai * TS_AD_STRIDE;
+      const int qo = S.ib[S.o_joint + r[0] * TS_JI_STRIDE + 2];
+      for (int i = 0; i < r[3]; ++i) {
+        const double uu = uk[r[2] + i];
+        double gain = (uu >= -1.0 && uu <= 1.0) ? (cdat[3 + i] - cdat[i]) / 2.0 : 0.0;
+        double zz = 0.0;
+        for (int m = 0; m < TS_MAXN; ++m) if (m == qo + i) zz = z[m];
+        du_out[r[2] + i] = S.h * S.h * gain * zz;
+      }
+    }
+  }
+  // pending contributions for the earlier steps
+  const double* G0 = tape + n * n;
+  const double* G1 = tape + 2 * n * n;
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    if (k >= n) continue;
+    double g0z = 0.0, g1z = 0.0;
+    for (int i = 0; i < n; ++i) { g0z += G0[i * n + k] * z[i]; g1z += G1[i * n + k] * z[i]; }
+    const double oldB = pendB[c];
+    pendA[c] = oldB + g0z + g1z / S.h + cterm[c];
+    pendB[c] = -g1z / S.h;
+    if (out_g0z) out_g0z[c] = g0z + oldB + cterm[c];   // what the step adds to dL/dq0 (to be subtracted)
+    if (out_g1z) out_g1z[c] = g1z;
+    if (out_c) out_c[c] = cterm[c];
+  }
+}
+
+// ------------------------------------------------------------------ contact index sets (diagnostic outputs)
+// word 0: ground force 0, points 0..31; words 1..3: general-primitive force 0, points 0..95.
+HDN inline void contact_sets(const SceneView& S, const Work<double>& W, unsigned* m4) {
+  m4[0] = m4[1] = m4[2] = m4[3] = 0u;
+  if (S.nground > 0) {
+    const int* r = S.ib + S.o_ground;
+    const int b = r[0], po = r[1], pc = r[2];
+    for (int k = 0; k < pc && k < 32; ++k) {
+      const double* xi = S.db + S.d_points + 3 * (po + k);
+      double xw[3];
+      mv3(W.R0i[b], xi, xw);
+      double d = (xw[0] + W.p0i[b][0] - S.gx[0]) * S.gn[0] + (xw[1] + W.p0i[b][1] - S.gx[1]) * S.gn[1] +
+                 (xw[2] + W.p0i[b][2] - S.gx[2]) * S.gn[2];
+      if (d <= 0.0) m4[0] |= (1u << k);
+    }
+  }
+  if (S.ngp > 0) {
+    const int* r = S.ib + S.o_gp;
+    const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
+    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+    for (int k = 0; k < pc && k < 96; ++k) {
+      const double* xi = S.db + S.d_points + 3 * (po + k);
+      double xw[3], y[3], x[3];
+      mv3(W.R0i[b1], xi, xw);
+      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + W.p0i[b1][i]) - W.p0i[b2][i];
+      mtv3(W.R0i[b2], y, x);
+      if (cuboid_distance(x, hs) < 0.0) m4[1 + (k >> 5)] |= (1u << (k & 31));
+    }
+  }
+}
+
+#define TS_MAXU 8
+
+struct FwdArgs {
+  int B, T;
+  double* q; double* qd;              // [B,n] state, in/out
+  const double* u; long long u_stride; // u[t*u_stride + env*nu + i]
+  double* q_traj; double* qd_traj;    // [T,B,n] or null
+  double* var_out; const int* var_row; // [rows,B,nvar]; row of step t (null map = t), <0 = skip
+  double* tac_out; const int* tac_row; // [rows,B,3M]
+  double* tape;                       // [T,B,3,n,n] or null
+  int* status;                        // [T,B] or null
+  unsigned* cmask;                    // [T,B,4] or null
+  int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
+};
+
+// readouts of the state (q,qd): variables, tactile field, contact sets
+template <class Tile>
+HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const double* qd, double* var_o,
+                     double* tac_o, int* mb_o, unsigned* cm_o, void* wb) {
+  Work<double>& WS = *(Work<double>*)wb;
+  kinematics<double>(S, q, qd, (const double*)0, WS, false);
+  if (var_o && tl.lane == 0)
+    for (int e = 0; e < S.nee; ++e) variable_of<double>(S, WS, e, var_o + 3 * e);
+  if (tac_o) tactile_values(tl, S, WS, tac_o, mb_o);
+  if (cm_o && tl.lane == 0) contact_sets(S, WS, cm_o);
+}
+
+template <class Tile>
+HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env, void* wb) {
+  const int n = S.n, nu = S.nu, B = a.B;
+  double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
+  for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
+  for (int t = 0; t < a.T; ++t) {
+    for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+    const long long es = (long long)t * B + env;
+    double* tp = a.tape ? a.tape + es * 3 * n * n : (double*)0;
+    int stat = step_forward(tl, S, q, qd, u, tp, wb);
+    if (tl.lane == 0) {
+      if (a.status) a.status[es] = stat;
+      if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = q[i];
+      if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qd[i];
+    }
+    const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
+    const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
+    if (vr >= 0 || tr >= 0 || a.cmask) {
+      env_readout(tl, S, q, qd, vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
+                  tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
+                  (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
+                  a.cmask ? a.cmask + es * 4 : (unsigned*)0, wb);
+    }
+  }
+  if (tl.lane == 0)
+    for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = q[i]; a.qd[(long long)env * n + i] = qd[i]; }
+}
+
+struct BwdArgs {
+  int B, T;
+  const double* q_traj; const double* qd_traj;   // [T,B,n] states AFTER each step
+  const double* u; long long u_stride;
+  const double* tape;                            // [T,B,3,n,n]
+  const double* df_dq; const int* dq_row;        // cotangents [rows,B,*]; row maps as in FwdArgs
+  const double* df_dvar; const int* dvar_row;
+  const double* df_dtac; const int* dtac_row;
+  double* carry;                                 // [B,2,n] pending vectors, in/out
+  double* df_du;                                 // [T,B,nu] or null
+  double* df_dq0; double* df_dqdot0;             // [B,n] or null: MINUS the adjoint terms of step 0
+};
+
+template <class Tile>
+HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int env, void* wb) {
+  const int L = Tile::LPE;
+  const int n = S.n, nu = S.nu, B = a.B;
+  double pA[TS_NC(L)], pB[TS_NC(L)], g0z[TS_NC(L)], g1z[TS_NC(L)];
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    pA[c] = (k < n) ? a.carry[((long long)env * 2 + 0) * n + k] : 0.0;
+    pB[c] = (k < n) ? a.carry[((long long)env * 2 + 1) * n + k] : 0.0;
+    g0z[c] = g1z[c] = 0.0;
+  }
+  for (int t = a.T - 1; t >= 0; --t) {
+    const long long es = (long long)t * B + env;
+    double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
+    for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q_traj[es * n + i] : 0.0; qd[i] = (i < n) ? a.qd_traj[es * n + i] : 0.0; }
+    for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+    const int r0 = a.df_dq ? (a.dq_row ? a.dq_row[t] : t) : -1;
+    const int r1 = a.df_dvar ? (a.dvar_row ? a.dvar_row[t] : t) : -1;
+    const int r2 = a.df_dtac ? (a.dtac_row ? a.dtac_row[t] : t) : -1;
+    step_backward(tl, S, q, qd, u, a.tape + es * 3 * n * n,
+                  r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
+                  r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
+                  r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,
+                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, (double*)0, wb);
+  }
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    if (k >= n) continue;
+    a.carry[((long long)env * 2 + 0) * n + k] = pA[c];
+    a.carry[((long long)env * 2 + 1) * n + k] = pB[c];
+    if (a.df_dq0) a.df_dq0[(long long)env * n + k] = -g0z[c];
+    if (a.df_dqdot0) a.df_dqdot0[(long long)env * n + k] = -g1z[c];
+  }
+}

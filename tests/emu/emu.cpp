@@ -1,0 +1,57 @@
+// TEST-ONLY host harness.  Compiles the very same per-lane math the sm_100a kernels inline
+// (tactilesimulation_b200/csrc/sim_core.cuh) with g++ and runs it with a one-lane tile, so the
+// kernel arithmetic can be checked against the oracle on a machine without a GPU.
+// It is NOT a product path: tactilesimulation_b200/ never loads this library, and the product
+// fails loudly when the CUDA extension is missing.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../tactilesimulation_b200/csrc/sim_core.cuh"
+
+extern "C" {
+
+int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, double* q, double* qd,
+                const double* u, int64_t u_stride, double* q_traj, double* qd_traj, double* var_out,
+                const int32_t* var_row, double* tac_out, const int32_t* tac_row, double* tape, int32_t* status,
+                uint32_t* cmask, int32_t* marker_body) {
+  SceneView S;
+  scene_view_init(S, ibuf, dbuf);
+  FwdArgs a;
+  a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
+  a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
+  a.status = status; a.cmask = cmask; a.marker_body = marker_body;
+  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  HostTile tl;
+  for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb.data());
+  return 0;
+}
+
+int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, const double* q_traj,
+                 const double* qd_traj, const double* u, int64_t u_stride, const double* tape, const double* df_dq,
+                 const int32_t* dq_row, const double* df_dvar, const int32_t* dvar_row, const double* df_dtac,
+                 const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0) {
+  SceneView S;
+  scene_view_init(S, ibuf, dbuf);
+  BwdArgs a;
+  a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_stride; a.tape = tape;
+  a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
+  a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
+  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  HostTile tl;
+  for (int env = 0; env < B; ++env) env_backward(tl, S, a, env, wb.data());
+  return 0;
+}
+
+int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double* q, const double* qd, double* var_out,
+                double* tac_out, int32_t* marker_body, uint32_t* cmask) {
+  SceneView S;
+  scene_view_init(S, ibuf, dbuf);
+  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  HostTile tl;
+  for (int env = 0; env < B; ++env)
+    env_readout(tl, S, q + (long long)env * S.n, qd + (long long)env * S.n,
+                var_out ? var_out + (long long)env * 3 * S.nee : 0, tac_out ? tac_out + (long long)env * 3 * S.nmark : 0,
+                marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * 4 : 0, wb.data());
+  return 0;
+}
+}

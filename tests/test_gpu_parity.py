@@ -1,0 +1,111 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs golden vectors of the reference
+on the same seeded inputs.
+
+Tolerances (print_error norm DH/Utils.h:315-319): q, qdot, var <= 1e-9; tactile <= 1e-8 (north_star
+allows 1e-4); contact-point index sets and marker->body ids identical; gradients <= 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["pusher13x10_episodic_s0", "pusher13x10_episodic_s1", "pusher32x13_episodic_s0"]
+
+
+def _ids(words):
+    out = []
+    for w, word in enumerate(words):
+        for b in range(32):
+            if ((int(word) & 0xffffffff) >> b) & 1:
+                out.append(32 * w + b)
+    return out
+
+
+def _sim(g, lanes=8):
+    from tactilesimulation_b200.sim import BatchedSim
+    return BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0", lanes=lanes)
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_and_adjoint_match_reference(name, lanes):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sim = _sim(g, lanes)
+    dev = sim.device
+    T = g["u"].shape[0]
+    B = 3   # three identical envs: also checks that tiles do not interfere
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.tensor(np.tile(g["qd0"], (B, 1)), device=dev)
+    u = torch.tensor(np.tile(g["u"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    out = sim.forward(q, qd, u, T, grad=True, want_status=True, want_contacts=True)
+    torch.cuda.synchronize()
+    qt, qdt = out["q_traj"].cpu().numpy(), out["qd_traj"].cpu().numpy()
+    var, tac = out["var"].cpu().numpy(), out["tactile"].cpu().numpy()
+    cm, mb = out["contact_masks"].cpu().numpy(), out["marker_body"].cpu().numpy()
+    assert int((out["status"] >> 16).max().item()) == 0
+    for e in range(B):
+        for t in range(T):
+            assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
+            assert rel_err(qdt[t, e], g["qd"][t]) <= 1e-9, (t, e)
+            assert rel_err(var[t, e], g["var"][t]) <= 1e-9, (t, e)
+            assert rel_err(tac[t, e], g["tactile"][t]) <= 1e-8, (t, e)
+            assert _ids(cm[t, e, 0:1]) == [int(x) for x in g["ground_ids"][t] if x >= 0], (t, e)
+            assert _ids(cm[t, e, 1:4]) == [int(x) for x in g["gp_ids"][t] if x >= 0], (t, e)
+            assert np.array_equal(mb[t, e], g["marker_body"][t]), (t, e)
+    assert np.allclose(q.cpu().numpy(), qt[-1])
+    dq = torch.tensor(np.tile(g["df_dq"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    dv = torch.tensor(np.tile(g["df_dvar"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    dt = torch.tensor(np.tile(g["df_dtactile"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    bw = sim.backward(out, u, T, dq, dv, dt, want_q0=True)
+    torch.cuda.synchronize()
+    for e in range(B):
+        assert rel_err(bw["df_du"][:, e].cpu().numpy(), g["df_du"]) <= 1e-6
+        assert rel_err(bw["df_dq0"][e].cpu().numpy(), g["df_dq0"]) <= 1e-6
+        assert rel_err(bw["df_dqdot0"][e].cpu().numpy(), g["df_dqdot0"]) <= 1e-6
+
+
+def test_stepsim_chain_matches_reference():
+    """forward(5, save_last_frame_var_only) per gym step, then chained backward over 5-step chunks
+    with the carry -- the StepSimFunction pattern (R/envs/redmax_torch_functions.py:112-174)."""
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_stepsim_s0.npz"))
+    sim = _sim(g)
+    dev = sim.device
+    fs, ns = int(g["frame_skip"]), g["u"].shape[0]
+    B = 2
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.tensor(np.tile(g["qd0"], (B, 1)), device=dev)
+    rows = [-1] * (fs - 1) + [0]
+    fwds, us = [], []
+    for t in range(ns):
+        u = torch.tensor(np.tile(g["u"][t], (B, 1)), device=dev)
+        o = sim.forward(q, qd, u, fs, grad=True, var_rows=rows, tac_rows=rows)
+        fwds.append(o)
+        us.append(u)
+        assert rel_err(q[0].cpu().numpy(), g["q"][t]) <= 1e-9
+        assert rel_err(o["var"][0, 1].cpu().numpy(), g["var"][t]) <= 1e-9
+        assert rel_err(o["tactile"][0, 0].cpu().numpy(), g["tactile"][t]) <= 1e-8
+    carry = None
+    for t in range(ns - 1, -1, -1):
+        dq = torch.tensor(np.tile(g["df_dq"][t], (1, B, 1)), device=dev).contiguous()
+        dv = torch.tensor(np.tile(g["df_dvar"][t], (1, B, 1)), device=dev).contiguous()
+        dt = torch.tensor(np.tile(g["df_dtactile"][t], (1, B, 1)), device=dev).contiguous()
+        bw = sim.backward(fwds[t], us[t], fs, dq, dv, dt, dq_rows=rows, dvar_rows=rows, dtac_rows=rows, carry=carry)
+        carry = bw["carry"]
+        assert rel_err(bw["df_du"][:, 0].cpu().numpy(), g["df_du"][t]) <= 1e-6, t
+
+
+def test_readout_matches_step_outputs():
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_episodic_s0.npz"))
+    sim = _sim(g)
+    dev = sim.device
+    t = 40
+    q = torch.tensor(g["q"][t][None], device=dev)
+    qd = torch.tensor(g["qd"][t][None], device=dev)
+    r = sim.readout(q, qd, want_contacts=True)
+    assert rel_err(r["tactile"][0].cpu().numpy(), g["tactile"][t]) <= 1e-8
+    assert rel_err(r["var"][0].cpu().numpy(), g["var"][t]) <= 1e-9
+    assert np.array_equal(r["marker_body"][0].cpu().numpy(), g["marker_body"][t])
