@@ -1,0 +1,387 @@
+"""Host-side mirror of the reference's ``redmax_py.Simulation`` for the accelerated path.
+
+Same method names, argument meaning and error behaviour as the pybind11 class
+(``DH/python_interface.cpp:33-249``, DH = externals/DiffHand/core/projects/redmax) so that
+``R/envs/redmax_torch_functions.py`` / ``redmax_torch_env.py`` / ``tactile_push_env.py`` can be
+pointed at it, but every call runs on the GPU through the C ABI and the
+object may hold a whole batch of environments:
+
+* numpy face (batch == 1): ``get_q() -> float64[n]`` etc., exactly the reference shapes;
+* tensor face (any batch): the ``*_t`` methods take/return CUDA tensors with a leading env dim and
+  never leave the device; ``tactilesimulation_b200.torch_functions`` builds the batched
+  ``StepSimFunction`` / ``EpisodicSimFunction`` on them.
+
+State machine as in the reference: ``reset()`` must precede ``forward()``
+(``DH/Simulation.cpp:1061-1064``), ``forward`` precedes ``backward``/``backward_steps``
+(``:1570-1573``, ``:1877-1880``), ``backward_steps`` forbids ``flag_q0``/``flag_qdot0``
+(``:1884-1889``); size mismatches raise (``:1578-1606``).  Newton non-convergence is not an error.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ._lib import TactileSimError
+from .scene import Scene, compile_scene
+from .sim import BatchedSim
+
+
+class Options:
+    """``Simulation::Options`` (read-only view, python_interface.cpp:36-44)."""
+
+    def __init__(self, gravity, h, integrator):
+        self.gravity = np.array(gravity, dtype=np.float64)
+        self.h = float(h)
+        self.integrator = integrator
+
+
+class ViewerOptions:
+    """Accepted and ignored: there is no display on the GPU box (python_interface.cpp:47-61)."""
+
+    def __init__(self):
+        self.fps = 30
+        self.speed = 1.0
+        self.camera_pos = np.zeros(3)
+        self.camera_lookat = np.zeros(3)
+        self.camera_up = np.array([0.0, 0.0, 1.0])
+        self.ground = True
+        self.E_g = np.eye(4)
+        self.record = False
+        self.record_folder = ""
+        self.loop = False
+        self.infinite = False
+
+
+class BackwardInfo:
+    """Cotangent inputs of the adjoint (``DH/BackwardData.h:32-46``, python_interface.cpp:64-76)."""
+
+    def __init__(self):
+        self.df_dq0 = np.zeros(0)
+        self.df_dqdot0 = np.zeros(0)
+        self.df_dp = np.zeros(0)
+        self.df_du = np.zeros(0)
+        self.df_dq = np.zeros(0)
+        self.df_dvar = np.zeros(0)
+        self.df_dtactile = np.zeros(0)
+        self.flag_q0 = self.flag_qdot0 = self.flag_p = self.flag_u = False
+
+    def set_flags(self, flag_q0=False, flag_qdot0=False, flag_p=False, flag_u=False):
+        self.flag_q0, self.flag_qdot0, self.flag_p, self.flag_u = bool(flag_q0), bool(flag_qdot0), bool(flag_p), bool(flag_u)
+
+
+class BackwardResults:
+    def __init__(self):
+        self.df_dq0 = np.zeros(0)
+        self.df_dqdot0 = np.zeros(0)
+        self.df_dp = np.zeros(0)
+        self.df_du = np.zeros(0)
+
+
+class _Chunk:
+    """One forward() call: T steps recorded on the device."""
+    __slots__ = ("T", "u", "fwd", "rows", "start")
+
+    def __init__(self, T, u, fwd, rows, start):
+        self.T, self.u, self.fwd, self.rows, self.start = T, u, fwd, rows, start
+
+
+class Simulation:
+    def __init__(self, xml_file_path, verbose: bool = False, batch: int = 1, device="cuda:0", lanes: int = 8):
+        if isinstance(xml_file_path, Scene):
+            self.scene = xml_file_path
+        else:
+            self.scene = compile_scene(str(xml_file_path))
+        self.core = BatchedSim(self.scene, device=device, lanes=lanes)
+        self.device = self.core.device
+        self.batch = int(batch)
+        c = self.core
+        self.ndof_r, self.ndof_m, self.ndof_u = c.ndof_r, c.ndof_m, c.ndof_u
+        self.ndof_var, self.ndof_tactile, self.ndof_p = c.ndof_var, c.ndof_tactile, 0
+        self.options = Options(self.scene.gravity, self.scene.h, self.scene.integrator)
+        self.viewer_options = ViewerOptions()
+        self.backward_info = BackwardInfo()
+        self.backward_results = BackwardResults()
+        z = lambda: torch.zeros((self.batch, self.ndof_r), dtype=torch.float64, device=self.device)
+        self._q_init, self._qd_init = z(), z()
+        self._q, self._qd = z(), z()
+        self._u = torch.zeros((self.batch, self.ndof_u), dtype=torch.float64, device=self.device)
+        self._reset_done = False
+        self._grad = False
+        self._chunks: List[_Chunk] = []
+        self._nsteps = 0
+        self._current_backward_step = 0
+        self._carry: Optional[torch.Tensor] = None
+        self._cache = []
+
+    # ------------------------------------------------------------------ helpers
+    def _t(self, x, width, name):
+        """numpy/tensor -> [batch,width] fp64 device tensor; size mismatch raises like the reference."""
+        if isinstance(x, torch.Tensor):
+            t = x.detach().to(device=self.device, dtype=torch.float64)
+        else:
+            t = torch.as_tensor(np.asarray(x, dtype=np.float64), device=self.device)
+        if t.dim() == 1:
+            if t.numel() != width:
+                raise TactileSimError(f"[Error] {name}: size {t.numel()} != {width}.")
+            t = t.unsqueeze(0).expand(self.batch, width)
+        if tuple(t.shape) != (self.batch, width):
+            raise TactileSimError(f"[Error] {name}: shape {tuple(t.shape)} != {(self.batch, width)}.")
+        return t.contiguous().clone()
+
+    def _np(self, t):
+        if self.batch != 1:
+            raise TactileSimError("the numpy face needs batch == 1; use the *_t methods for batches")
+        return t[0].detach().cpu().numpy().copy()
+
+    # ------------------------------------------------------------------ state (python_interface.cpp:102-135)
+    def set_state_init(self, q_init, qdot_init):
+        self.set_q_init(q_init)
+        self.set_qdot_init(qdot_init)
+
+    def set_q_init(self, q_init):
+        self._q_init = self._t(q_init, self.ndof_r, "set_q_init")
+
+    def set_qdot_init(self, qdot_init):
+        self._qd_init = self._t(qdot_init, self.ndof_r, "set_qdot_init")
+
+    def get_q_init(self):
+        return self._np(self._q_init)
+
+    def get_qdot_init(self):
+        return self._np(self._qd_init)
+
+    def get_q(self):
+        return self._np(self._q)
+
+    def get_qdot(self):
+        return self._np(self._qd)
+
+    def get_q_t(self):
+        return self._q.clone()
+
+    def get_qdot_t(self):
+        return self._qd.clone()
+
+    def set_u(self, u):
+        self._u = self._t(u, self.ndof_u, "set_u")
+
+    def get_variables(self):
+        return self._np(self.get_variables_t())
+
+    def get_variables_t(self):
+        return self.core.readout(self._q, self._qd)["var"]
+
+    def get_tactile_force_vector(self):
+        return self._np(self.get_tactile_force_vector_t())
+
+    def get_tactile_force_vector_t(self):
+        return self.core.readout(self._q, self._qd)["tactile"]
+
+    def get_tactile_sensor_pos(self, name):
+        for s in self.scene.sensors:
+            if s.name == name:
+                return [p.copy() for p in s.pos]
+        raise TactileSimError(f"tactile sensor {name} not found")
+
+    def get_tactile_image_pos(self, name):
+        for s in self.scene.sensors:
+            if s.name == name:
+                return [p.copy() for p in s.image_pos]
+        raise TactileSimError(f"tactile sensor {name} not found")
+
+    def get_tactile_force(self, name):
+        off = 0
+        vec = self.get_tactile_force_vector()
+        for s in self.scene.sensors:
+            M = len(s.pos)
+            if s.name == name:
+                return [vec[off + 3 * i: off + 3 * i + 3].copy() for i in range(M)]
+            off += 3 * M
+        raise TactileSimError(f"tactile sensor {name} not found")
+
+    def update_virtual_object(self, name, data):
+        """Render-only objects (goal marker) do not enter the dynamics: accepted as a no-op."""
+        return None
+
+    # ------------------------------------------------------------------ reset / caches (Simulation.cpp:999-1055)
+    def reset(self, backward_flag: bool = False, backward_design_params_flag: bool = False):
+        if backward_design_params_flag:
+            raise TactileSimError("design-parameter gradients are out of scope of the B200 path")
+        self._q = self._q_init.clone()
+        self._qd = self._qd_init.clone()
+        self._grad = bool(backward_flag)
+        self._chunks = []
+        self._nsteps = 0
+        self._current_backward_step = 0
+        self._carry = None
+        self._reset_done = True
+
+    def clearBackwardCache(self):
+        self._cache = []
+
+    def saveBackwardCache(self):
+        self._cache.append((list(self._chunks), self._nsteps, self._current_backward_step,
+                            None if self._carry is None else self._carry.clone(), self.backward_info, self.backward_results))
+        self.backward_info = BackwardInfo()
+        self.backward_results = BackwardResults()
+
+    def popBackwardCache(self):
+        self._chunks, self._nsteps, self._current_backward_step, self._carry, self.backward_info, self.backward_results = self._cache.pop()
+
+    def backwardCacheSize(self):
+        return len(self._cache)
+
+    # ------------------------------------------------------------------ forward (Simulation.cpp:1057-1148)
+    def forward(self, num_steps, verbose=False, test_derivatives=False, save_last_frame_var_only=False):
+        self.forward_t(int(num_steps), self._u, save_last_frame_var_only)
+
+    def forward_t(self, num_steps: int, u: torch.Tensor, save_last_frame_var_only: bool = False, tac_rows=None,
+                  want_outputs: bool = False):
+        """u: [batch,nu] held for all steps, or [T,batch,nu].  Returns the kernel outputs when
+        ``want_outputs`` (q_traj, var, tactile ...)."""
+        if not self._reset_done:
+            raise TactileSimError("[Error] Please call simulation.reset() before simulation.forward().")
+        T = int(num_steps)
+        if T <= 0:
+            return None
+        rows = ([-1] * (T - 1) + [0]) if save_last_frame_var_only else None
+        trows = rows if tac_rows is None else tac_rows
+        u = u.contiguous()
+        fwd = self.core.forward(self._q, self._qd, u, T, grad=self._grad, var_rows=rows, tac_rows=trows,
+                                want_var=want_outputs, want_tactile=want_outputs, want_traj=want_outputs or self._grad)
+        if self._grad:
+            self._chunks.append(_Chunk(T, u, fwd, rows, self._nsteps))
+            self._current_backward_step += T
+        self._nsteps += T
+        return fwd if want_outputs else None
+
+    # ------------------------------------------------------------------ adjoint
+    def _sweep(self, lo: int, hi: int, df_dq, df_dvar, df_dtac, want_q0: bool):
+        """Reverse sweep over global steps [lo, hi); cotangent tensors are [hi-lo, batch, *] or None.
+        Returns df_du [hi-lo,batch,nu] and, if want_q0, (df_dq0, df_dqdot0) of step lo."""
+        nu = self.ndof_u
+        df_du = torch.zeros((hi - lo, self.batch, nu), dtype=torch.float64, device=self.device)
+        if self._carry is None:
+            self._carry = torch.zeros((self.batch, 2, self.ndof_r), dtype=torch.float64, device=self.device)
+        dq0 = dqd0 = None
+        for ch in reversed(self._chunks):
+            a, b = max(lo, ch.start), min(hi, ch.start + ch.T)
+            if a >= b:
+                continue
+            s, e = a - ch.start, b - ch.start          # slice inside the chunk
+            f = ch.fwd
+            sub = dict(q_traj=f["q_traj"][s:e], qd_traj=f["qd_traj"][s:e], tape=f["tape"][s:e])
+            u = ch.u if ch.u.dim() == 2 else ch.u[s:e]
+            T = e - s
+            # cotangent rows: the reference zeroes dvar_dq / dtactile on non-final sub-steps of a
+            # save_last_frame_var_only chunk (Simulation.cpp:1135-1139)
+            vrows = None
+            if ch.rows is not None:
+                vrows = [(-1 if ch.rows[s + i] < 0 else i) for i in range(T)]
+            sl = slice(a - lo, b - lo)
+            res = self.core.backward(sub, u, T,
+                                     None if df_dq is None else df_dq[sl].contiguous(),
+                                     None if df_dvar is None else df_dvar[sl].contiguous(),
+                                     None if df_dtac is None else df_dtac[sl].contiguous(),
+                                     dq_rows=None, dvar_rows=vrows, dtac_rows=vrows, carry=self._carry,
+                                     want_q0=want_q0 and a == lo)
+            df_du[sl] = res["df_du"]
+            if want_q0 and a == lo:
+                dq0, dqd0 = res["df_dq0"], res["df_dqdot0"]
+        return df_du, dq0, dqd0
+
+    def backward_t(self, df_dq, df_dvar, df_dtactile, want_q0=True):
+        """Full-trajectory adjoint on device tensors [T,batch,*] (Simulation::backward)."""
+        if self._nsteps < 1 or not self._chunks:
+            raise TactileSimError("[Error] Please call simulation.forward() before simulation.backward().")
+        T = self._nsteps
+        self._carry = None
+        out = self._sweep(0, T, df_dq, df_dvar, df_dtactile, want_q0)
+        self._carry = None
+        return out
+
+    def backward_steps_t(self, num_backward_steps: int, df_dq, df_dvar, df_dtactile):
+        """The last ``num_backward_steps`` not yet swept steps (Simulation::backward_steps)."""
+        if self._current_backward_step <= 0:
+            raise TactileSimError("[Error] Please call simulation.forward() before simulation.backward().")
+        hi = self._current_backward_step
+        lo = hi - int(num_backward_steps)
+        if lo < 0:
+            raise TactileSimError("backward_steps: more steps than recorded")
+        df_du, _, _ = self._sweep(lo, hi, df_dq, df_dvar, df_dtactile, False)
+        self._current_backward_step = lo
+        return df_du
+
+    def _cot(self, flat, T, width, name):
+        a = np.asarray(flat, dtype=np.float64).reshape(-1)
+        if a.size != width * T:
+            raise TactileSimError(f"_backward_info.{name}.size != {width} * T")
+        if width == 0:
+            return None
+        return torch.as_tensor(a.reshape(T, 1, width), device=self.device)
+
+    def backward(self):
+        if self._nsteps < 1 or not self._grad:
+            raise TactileSimError("[Error] Please call simulation.forward() before simulation.backward().")
+        bi, T = self.backward_info, self._nsteps
+        n, nu = self.ndof_r, self.ndof_u
+        if bi.flag_q0 and np.asarray(bi.df_dq0).size != n:
+            raise TactileSimError("_backward_info._df_dq0.size != _ndof_r")
+        if bi.flag_qdot0 and np.asarray(bi.df_dqdot0).size != n:
+            raise TactileSimError("_backward_info._df_dqdot0.size != _ndof_r")
+        if bi.flag_p:
+            raise TactileSimError("design-parameter gradients are out of scope of the B200 path")
+        if bi.flag_u and np.asarray(bi.df_du).size != nu * T:
+            raise TactileSimError("_backward_info._df_du.size != _ndof_u * T")
+        dq = self._cot(bi.df_dq, T, n, "_df_dq")
+        dv = self._cot(bi.df_dvar, T, self.ndof_var, "_df_dvar")
+        dt = self._cot(bi.df_dtactile, T, self.ndof_tactile, "_df_dtactile")
+        df_du, dq0, dqd0 = self.backward_t(dq, dv, dt, want_q0=True)
+        br = self.backward_results
+        if bi.flag_q0:
+            br.df_dq0 = np.asarray(bi.df_dq0, dtype=np.float64) + self._np(dq0)
+        if bi.flag_qdot0:
+            br.df_dqdot0 = np.asarray(bi.df_dqdot0, dtype=np.float64) + self._np(dqd0)
+        if bi.flag_u:
+            br.df_du = np.asarray(bi.df_du, dtype=np.float64).reshape(-1) + df_du[:, 0].reshape(-1).cpu().numpy()
+
+    def backward_steps(self, num_backward_steps):
+        bi, ns = self.backward_info, int(num_backward_steps)
+        if self._current_backward_step <= 0:
+            raise TactileSimError("[Error] Please call simulation.forward() before simulation.backward().")
+        if bi.flag_q0:
+            raise TactileSimError("_backward_info._flag_q0 should be false for backward_steps")
+        if bi.flag_qdot0:
+            raise TactileSimError("_backward_info._flag_qdot0 should be false for backward_steps")
+        if bi.flag_p:
+            raise TactileSimError("design-parameter gradients are out of scope of the B200 path")
+        n, nu = self.ndof_r, self.ndof_u
+        if bi.flag_u and np.asarray(bi.df_du).size != nu * ns:
+            raise TactileSimError("_backward_info._df_du.size != _ndof_u * num_backward_steps")
+        dq = self._cot(bi.df_dq, ns, n, "_df_dq")
+        dv = self._cot(bi.df_dvar, ns, self.ndof_var, "_df_dvar")
+        dt = self._cot(bi.df_dtactile, ns, self.ndof_tactile, "_df_dtactile")
+        df_du = self.backward_steps_t(ns, dq, dv, dt)
+        if bi.flag_u:
+            self.backward_results.df_du = (np.asarray(bi.df_du, dtype=np.float64).reshape(-1)
+                                           + df_du[:, 0].reshape(-1).cpu().numpy())
+
+    # ------------------------------------------------------------------ viewer / reports: no display here
+    def replay(self):
+        return None
+
+    def export_replay(self, path):
+        raise TactileSimError("export_replay is out of scope of the B200 path (no viewer)")
+
+    def print_time_report(self):
+        print("[tactilesimulation_b200] timing lives in CUDA events / ncu; see bench.py")
+
+    def print_ctrl_info(self):
+        for a in self.scene.actuators:
+            print("motor on joint", self.scene.joint_names[a["joint"]], "ctrl_range", a["cmin"], a["cmax"])
+
+
+def make_sim(env_name, integrator="BDF2"):
+    raise TactileSimError("programmatic test scenes (SimEnvGenerator) are out of scope of the B200 path")

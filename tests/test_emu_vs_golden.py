@@ -1,0 +1,96 @@
+"""CPU-side check of the KERNEL ARITHMETIC: the per-lane math that the sm_100a kernels inline
+(tactilesimulation_b200/csrc/sim_core.cuh) is compiled by g++ into a test-only harness
+(tests/emu) and compared with the golden vectors of the reference.  This is development/test
+infrastructure, not a product path (the product has no CPU fallback); the GPU parity tests in
+test_gpu_parity.py are the parity tests proper.
+
+Tolerances as in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import emu_lib
+from tests.conftest import GOLDEN, rel_err
+
+
+@pytest.mark.parametrize("name", ["pusher13x10_episodic_s0", "pusher13x10_episodic_s1", "pusher32x13_episodic_s0"])
+def test_emulated_kernel_math_matches_reference(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    T = g["u"].shape[0]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9
+        assert rel_err(out["var"][t, 0], g["var"][t]) <= 1e-9
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, 0:1]) == [int(x) for x in g["ground_ids"][t] if x >= 0]
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, 1:4]) == [int(x) for x in g["gp_ids"][t] if x >= 0]
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t])
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], g["df_dq"][:, None, :],
+                          g["df_dvar"][:, None, :], g["df_dtactile"][:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_stepsim_chain_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_stepsim_s0.npz"))
+    fs, ns = int(g["frame_skip"]), g["u"].shape[0]
+    rows = [-1] * (fs - 1) + [0]
+    q, qd = g["q0"].copy(), g["qd0"].copy()
+    fwds, us = [], []
+    for t in range(ns):
+        u = np.tile(g["u"][t], (fs, 1, 1))
+        o = emu_lib.forward(g["ibuf"], g["dbuf"], q, qd, u, grad=True, var_row=rows, tac_row=rows)
+        q, qd = o["q_final"][0], o["qd_final"][0]
+        fwds.append(o)
+        us.append(u)
+        assert rel_err(q, g["q"][t]) <= 1e-9
+        assert rel_err(o["var"][0, 0], g["var"][t]) <= 1e-9
+        assert rel_err(o["tactile"][0, 0], g["tactile"][t]) <= 1e-8
+    carry = None
+    for t in range(ns - 1, -1, -1):
+        bw = emu_lib.backward(g["ibuf"], g["dbuf"], fwds[t], us[t], g["df_dq"][t][None, None], g["df_dvar"][t][None, None],
+                              g["df_dtactile"][t][None, None], rows, rows, rows, carry=carry, want_q0=False)
+        carry = bw["carry"]
+        assert rel_err(bw["df_du"][:, 0], g["df_du"][t]) <= 1e-6, t
+
+
+def test_emulated_matches_oracle_on_fresh_seed():
+    """CUDA-path arithmetic vs the numpy oracle on inputs that are NOT in the golden set."""
+    from oracle.redmax_oracle import OracleSim
+    from tests.blob_scene import scene_from_blob
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_episodic_s0.npz"))
+    sc = scene_from_blob(g["ibuf"], g["dbuf"])
+    rng = np.random.default_rng(77)
+    T = 16
+    q0 = g["q0"].copy()
+    q0[4] = 0.013
+    q0[1] = 0.0005          # start in contact
+    u = np.zeros((T, 6))
+    u[:, :3] = np.tanh(rng.normal(size=(T, 3)))
+    u[:, 0] = 0.9
+    u[:, 3:5] = rng.uniform(-1, 1, 2)
+    o = OracleSim(sc)
+    o.set_state_init(q0, np.zeros(7))
+    o.reset(True)
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], q0, np.zeros(7), u[:, None, :], grad=True)
+    for t in range(T):
+        o.set_u(u[t])
+        o.forward(1)
+        assert rel_err(out["q"][t, 0], o.get_q()) <= 1e-9
+        assert rel_err(out["tactile"][t, 0], o.get_tactile_force_vector()) <= 1e-8
+        assert (out["status"][t, 0] & 255) == o.newton_iters[t]
+        # tape: H and the adjoint blocks G0 = -M + hD, G1 = -hM (FORCE motors)
+        H, M, D = o.tape["H"][t], o.tape["M"][t], o.tape["D"][t]
+        assert rel_err(out["tape"][t, 0, 0], H) <= 1e-8
+        assert rel_err(out["tape"][t, 0, 1], -M + o.h * D) <= 1e-8
+        assert rel_err(out["tape"][t, 0, 2], -o.h * M) <= 1e-8
+    dq, dv, dt = rng.normal(size=(T, 7)), rng.normal(size=(T, 6)), 1e-3 * rng.normal(size=(T, 390))
+    ref = o.backward(dq, dv, dt)
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, u[:, None, :], dq[:, None], dv[:, None], dt[:, None])
+    assert rel_err(bw["df_du"][:, 0], ref["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], ref["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], ref["df_dqdot0"]) <= 1e-6
