@@ -1,0 +1,65 @@
+// Kernel tables: what the sm_100a kernels actually index.  Produced on the host by
+// lower_scene() (scene_lower.h) from the portable scene blob (scene_layout.h) at
+// tsim_scene_create time; never leaves the library.
+//
+// Lowering performed (all batch-invariant, done once per scene handle):
+//   * fixed joints are folded away: every body / end-effector hangs off its nearest MOVING
+//     ancestor joint through a precomposed constant transform, and every moving joint carries the
+//     precomposed constant offset from its nearest moving ancestor (the reference walks these
+//     identity-motion joints every evaluation, DH/Joint/Joint.cpp:119-165);
+//   * bounding radii of contact point sets / marker grids / boxes for exact-safe culling;
+//   * ancestor bitmasks per moving joint (mass-matrix columns).
+#pragma once
+
+#define KT_MAXJ 8        // moving joints
+#define KT_MAXN 8        // reduced dofs
+#define KT_MAXB 16       // bodies
+#define KT_MAXU 8        // controls
+#define KT_MAXCAND 4     // tactile candidate bodies per sensor
+
+enum {
+  KI_NMJ = 0, KI_N, KI_NU, KI_NEE, KI_NMARK, KI_NGROUND, KI_NGP, KI_NACT, KI_NSENS, KI_MAX_ITER, KI_MAX_LS,
+  KI_NBODY, KI_NPOINTS,
+  KI_O_JOINT = 16, KI_O_BODY, KI_O_GROUND, KI_O_GP, KI_O_ACT, KI_O_EE, KI_O_SENSOR,
+  KI_D_JOINT = 24, KI_D_BODY, KI_D_GROUND, KI_D_GP, KI_D_ACT, KI_D_EE, KI_D_SENSOR, KI_D_POINTS, KI_D_MARKERS,
+  KI_HEADER = 40
+};
+enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 };
+
+// moving joint: int {type, parent (moving index, -1 = world), qoff, ndof, ancestor-or-self bitmask}
+#define KJ_ISTRIDE 8
+// dbl {Ra(9) pa(3): constant offset from the parent moving frame | axis0(3) axis1(3) | damping lo hi limk}
+#define KJ_DSTRIDE 24
+#define KJ_RA 0
+#define KJ_PA 9
+#define KJ_AX0 12
+#define KJ_AX1 15
+#define KJ_DAMP 18
+#define KJ_LIMLO 19
+#define KJ_LIMHI 20
+#define KJ_LIMK 21
+// body: int {moving joint (-1 = static), shape, dynamic (has mass and a moving joint), unused}
+#define KB_ISTRIDE 4
+// dbl {Rmi(9) pmi(3): body frame in its moving joint frame | inertia(6) | half-size(3) | bounding radius}
+#define KB_DSTRIDE 24
+#define KB_RMI 0
+#define KB_PMI 9
+#define KB_INERTIA 12
+#define KB_HALF 18
+#define KB_RBOUND 21
+// ground contact: int {body, point_off, point_cnt, -}; dbl {kn kt mu damping}
+#define KG_ISTRIDE 4
+#define KG_DSTRIDE 4
+// general-primitive contact: int {body1, body2, point_off, point_cnt}; dbl {kn kt mu damping r_points - - -}
+#define KP_ISTRIDE 4
+#define KP_DSTRIDE 8
+// actuator: int {moving joint, mode, uoff, ndof}; dbl {cmin[3] cmax[3] P[3] D[3]}
+#define KA_ISTRIDE 4
+#define KA_DSTRIDE 12
+// end effector: int {moving joint (-1 = world), -}; dbl {pos(3) in that frame, -}
+#define KE_ISTRIDE 2
+#define KE_DSTRIDE 4
+// sensor: int {body, marker_off, marker_cnt, ncand, cand[4]}; dbl {kn kt mu damping axis0 axis1 normal r_markers}
+#define KS_ISTRIDE 8
+#define KS_DSTRIDE 16
+#define KS_RMARK 13

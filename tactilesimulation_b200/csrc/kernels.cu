@@ -13,6 +13,7 @@
 #include <string>
 
 #include "../../include/tactilesim_b200.h"
+#include "scene_lower.h"
 #include "sim_core.cuh"
 
 template <int LPE_>
@@ -146,19 +147,20 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   if (!ibuf || !dbuf || !out) return fail("tsim_scene_create: null argument");
   if (n_int < TS_I_HEADER || ibuf[TS_I_MAGIC] != TS_MAGIC || ibuf[TS_I_VERSION] != TS_VERSION)
     return fail("tsim_scene_create: not a scene blob of this version");
-  if (ibuf[TS_I_NJ] > TS_MAXJ || ibuf[TS_I_NDOF_R] > TS_MAXN || ibuf[TS_I_NDOF_U] > TS_MAXU)
-    return fail("tsim_scene_create: scene exceeds the compiled capacities (joints/dofs/controls)");
-  if (ibuf[TS_I_NSENSORS] > 1) return fail("tsim_scene_create: at most one tactile sensor is supported");
+  // lower the portable scene description to the kernel tables (fixed joints folded, culling radii, ...)
+  KernelTables kt;
+  const std::string err = lower_scene(ibuf, n_int, dbuf, n_dbl, kt);
+  if (!err.empty()) return fail("tsim_scene_create: " + err);
   CK(cudaSetDevice(device));
   tsim_scene* s = new tsim_scene();
   s->device = device;
-  s->ni = (int)n_int;
-  s->nd = (int)n_dbl;
+  s->ni = (int)kt.ib.size();
+  s->nd = (int)kt.db.size();
   s->lanes = 8;
-  CK(cudaMalloc(&s->d_ib, sizeof(int) * n_int));
-  CK(cudaMalloc(&s->d_db, sizeof(double) * n_dbl));
-  CK(cudaMemcpy(s->d_ib, ibuf, sizeof(int) * n_int, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(s->d_db, dbuf, sizeof(double) * n_dbl, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
+  CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd));
+  CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_db, kt.db.data(), sizeof(double) * s->nd, cudaMemcpyHostToDevice));
   const int n = ibuf[TS_I_NDOF_R];
   s->sizes[TSIM_NJ] = ibuf[TS_I_NJ];
   s->sizes[TSIM_NDOF_R] = n;

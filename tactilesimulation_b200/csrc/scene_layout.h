@@ -19,11 +19,7 @@
 #define TS_ACT_FORCE 0
 #define TS_ACT_POS 1
 
-// ---- compile-time capacities of the kernels
-#define TS_MAXJ 8       // joints (= bodies)
-#define TS_MAXN 8       // reduced dofs (<= lanes per env)
-#define TS_MAXCAND 4    // tactile candidate bodies per sensor
-#define TS_MAXDEPTH 8
+// (compile-time capacities of the kernels live in kernel_layout.h)
 
 // ---- int header
 enum {

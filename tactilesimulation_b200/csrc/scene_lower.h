@@ -1,0 +1,194 @@
+// Host-side lowering of the portable scene blob (scene_layout.h, written by
+// tactilesimulation_b200/layout.py) into the kernel tables of kernel_layout.h.
+// Plain C++ (no CUDA): used by tsim_scene_create and by the test-only host harness.
+#pragma once
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "kernel_layout.h"
+#include "scene_layout.h"
+
+struct KernelTables {
+  std::vector<int> ib;
+  std::vector<double> db;
+  int nj_ref;          // joints (= bodies) of the reference topology
+};
+
+namespace tsim_lower {
+
+struct Xf { double R[9]; double p[3]; };
+
+inline Xf xf_identity() {
+  Xf e;
+  for (int i = 0; i < 9; ++i) e.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  e.p[0] = e.p[1] = e.p[2] = 0.0;
+  return e;
+}
+inline Xf xf_mul(const Xf& a, const Xf& b) {   // a * b
+  Xf o;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) o.R[3 * i + j] = a.R[3 * i] * b.R[j] + a.R[3 * i + 1] * b.R[3 + j] + a.R[3 * i + 2] * b.R[6 + j];
+  for (int i = 0; i < 3; ++i) o.p[i] = a.R[3 * i] * b.p[0] + a.R[3 * i + 1] * b.p[1] + a.R[3 * i + 2] * b.p[2] + a.p[i];
+  return o;
+}
+inline Xf xf_load(const double* R, const double* p) {
+  Xf e;
+  for (int i = 0; i < 9; ++i) e.R[i] = R[i];
+  for (int i = 0; i < 3; ++i) e.p[i] = p[i];
+  return e;
+}
+inline double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+}  // namespace tsim_lower
+
+// Returns "" on success, otherwise an error message.
+inline std::string lower_scene(const int* ib, long long ni, const double* db, long long nd, KernelTables& out) {
+  using namespace tsim_lower;
+  if (ni < TS_I_HEADER || ib[TS_I_MAGIC] != TS_MAGIC || ib[TS_I_VERSION] != TS_VERSION)
+    return "not a scene blob of this version";
+  const int nj = ib[TS_I_NJ], n = ib[TS_I_NDOF_R], nu = ib[TS_I_NDOF_U], nee = ib[TS_I_NEE], nmark = ib[TS_I_NMARKERS];
+  const int nground = ib[TS_I_NGROUND], ngp = ib[TS_I_NGP], nact = ib[TS_I_NACT], nsens = ib[TS_I_NSENSORS];
+  const int npoints = ib[TS_I_NPOINTS];
+  if (nj > KT_MAXB) return "scene exceeds the compiled capacity (bodies)";
+  if (n > KT_MAXN || nu > KT_MAXU) return "scene exceeds the compiled capacities (dofs/controls)";
+  if (nsens > 1) return "at most one tactile sensor is supported";
+  const int* J = ib + ib[TS_I_OFF_JOINT];
+  const double* JD = db + ib[TS_I_DOFF_JOINT];
+  // nearest moving ancestor-or-self and the constant transform from its frame to each joint frame
+  std::vector<int> mov(nj), midx(nj, -1);
+  std::vector<Xf> erel(nj), ea(nj);
+  int nmj = 0;
+  for (int j = 0; j < nj; ++j) {
+    const int jt = J[j * TS_JI_STRIDE], par = J[j * TS_JI_STRIDE + 1];
+    if (par >= j) return "joints are not in parent-first order";
+    const Xf e0 = xf_load(JD + j * TS_JD_STRIDE + TS_JD_RPJ, JD + j * TS_JD_STRIDE + TS_JD_PPJ);
+    const Xf up = (par < 0) ? e0 : xf_mul(erel[par], e0);
+    if (jt == TS_JT_FIXED) {
+      mov[j] = (par < 0) ? -1 : mov[par];
+      erel[j] = up;
+    } else {
+      ea[j] = up;
+      mov[j] = j;
+      erel[j] = xf_identity();
+      midx[j] = nmj++;
+    }
+  }
+  if (nmj > KT_MAXJ) return "scene exceeds the compiled capacity (moving joints)";
+  auto mv_of = [&](int j) { return (j < 0 || mov[j] < 0) ? -1 : midx[mov[j]]; };
+
+  std::vector<int>& oi = out.ib;
+  std::vector<double>& od = out.db;
+  oi.assign(KI_HEADER, 0);
+  od.assign(KD_HEADER, 0.0);
+  out.nj_ref = nj;
+  for (int i = 0; i < TS_D_HEADER && i < KD_HEADER; ++i) od[i] = db[i];   // h, gravity, tol, ground: same slots
+  oi[KI_NMJ] = nmj; oi[KI_N] = n; oi[KI_NU] = nu; oi[KI_NEE] = nee; oi[KI_NMARK] = nmark; oi[KI_NGROUND] = nground;
+  oi[KI_NGP] = ngp; oi[KI_NACT] = nact; oi[KI_NSENS] = nsens; oi[KI_MAX_ITER] = ib[TS_I_MAX_ITER];
+  oi[KI_MAX_LS] = ib[TS_I_MAX_LS]; oi[KI_NBODY] = nj; oi[KI_NPOINTS] = npoints;
+
+  // ---- moving joints
+  oi[KI_O_JOINT] = (int)oi.size(); oi[KI_D_JOINT] = (int)od.size();
+  std::vector<int> anc(nmj, 0);
+  for (int j = 0; j < nj; ++j) {
+    if (midx[j] < 0) continue;
+    const int m = midx[j];
+    const int par = J[j * TS_JI_STRIDE + 1];
+    const int pm = mv_of(par);
+    anc[m] = (1 << m) | (pm >= 0 ? anc[pm] : 0);
+    int rec[KJ_ISTRIDE] = {J[j * TS_JI_STRIDE], pm, J[j * TS_JI_STRIDE + 2], J[j * TS_JI_STRIDE + 3], anc[m], 0, 0, 0};
+    oi.insert(oi.end(), rec, rec + KJ_ISTRIDE);
+    double d[KJ_DSTRIDE] = {0};
+    for (int i = 0; i < 9; ++i) d[KJ_RA + i] = ea[j].R[i];
+    for (int i = 0; i < 3; ++i) d[KJ_PA + i] = ea[j].p[i];
+    const double* s = JD + j * TS_JD_STRIDE;
+    for (int i = 0; i < 3; ++i) { d[KJ_AX0 + i] = s[TS_JD_AX0 + i]; d[KJ_AX1 + i] = s[TS_JD_AX1 + i]; }
+    d[KJ_DAMP] = s[TS_JD_DAMP]; d[KJ_LIMLO] = s[TS_JD_LIMLO]; d[KJ_LIMHI] = s[TS_JD_LIMHI]; d[KJ_LIMK] = s[TS_JD_LIMK];
+    od.insert(od.end(), d, d + KJ_DSTRIDE);
+  }
+  // ---- bodies (same order and ids as the reference: body j hangs off joint j)
+  oi[KI_O_BODY] = (int)oi.size(); oi[KI_D_BODY] = (int)od.size();
+  for (int j = 0; j < nj; ++j) {
+    const double* s = JD + j * TS_JD_STRIDE;
+    const Xf eji = xf_load(s + TS_JD_RJI, s + TS_JD_PJI);
+    const Xf emi = xf_mul(erel[j], eji);
+    const int m = mv_of(j);
+    double mass = 0.0;
+    for (int i = 0; i < 6; ++i) mass += fabs(s[TS_JD_INERTIA + i]);
+    int rec[KB_ISTRIDE] = {m, J[j * TS_JI_STRIDE + 4], (m >= 0 && mass > 0.0) ? 1 : 0, 0};
+    oi.insert(oi.end(), rec, rec + KB_ISTRIDE);
+    double d[KB_DSTRIDE] = {0};
+    for (int i = 0; i < 9; ++i) d[KB_RMI + i] = emi.R[i];
+    for (int i = 0; i < 3; ++i) d[KB_PMI + i] = emi.p[i];
+    for (int i = 0; i < 6; ++i) d[KB_INERTIA + i] = s[TS_JD_INERTIA + i];
+    for (int i = 0; i < 3; ++i) d[KB_HALF + i] = s[TS_JD_HALF + i];
+    d[KB_RBOUND] = norm3(s + TS_JD_HALF);
+    od.insert(od.end(), d, d + KB_DSTRIDE);
+  }
+  const double* P = db + ib[TS_I_DOFF_POINTS];
+  const double* MK = db + ib[TS_I_DOFF_MARKERS];
+  // ---- ground contacts
+  oi[KI_O_GROUND] = (int)oi.size(); oi[KI_D_GROUND] = (int)od.size();
+  for (int g = 0; g < nground; ++g) {
+    const int* r = ib + ib[TS_I_OFF_GROUND] + g * TS_GI_STRIDE;
+    const double* c = db + ib[TS_I_DOFF_GROUND] + g * TS_CD_STRIDE;
+    if (g == 0 && r[2] > 32) return "more than 32 ground contact points per body are not supported";
+    oi.insert(oi.end(), r, r + KG_ISTRIDE);
+    od.insert(od.end(), c, c + KG_DSTRIDE);
+  }
+  // ---- general-primitive contacts
+  oi[KI_O_GP] = (int)oi.size(); oi[KI_D_GP] = (int)od.size();
+  for (int f = 0; f < ngp; ++f) {
+    const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
+    const double* c = db + ib[TS_I_DOFF_GP] + f * TS_CD_STRIDE;
+    if (J[r[1] * TS_JI_STRIDE + 4] != TS_SH_CUBOID) return "general-primitive contact: only cuboid primitives are supported";
+    if (r[3] > 96) return "more than 96 contact points per general body are not supported";
+    oi.insert(oi.end(), r, r + KP_ISTRIDE);
+    double d[KP_DSTRIDE] = {c[0], c[1], c[2], c[3], 0, 0, 0, 0};
+    for (int k = 0; k < r[3]; ++k) d[4] = fmax(d[4], norm3(P + 3 * (r[2] + k)));
+    od.insert(od.end(), d, d + KP_DSTRIDE);
+  }
+  // ---- actuators
+  oi[KI_O_ACT] = (int)oi.size(); oi[KI_D_ACT] = (int)od.size();
+  for (int a = 0; a < nact; ++a) {
+    const int* r = ib + ib[TS_I_OFF_ACT] + a * TS_AI_STRIDE;
+    const double* c = db + ib[TS_I_DOFF_ACT] + a * TS_AD_STRIDE;
+    if (r[1] != TS_ACT_FORCE) return "position-controlled motors are not supported yet";
+    if (midx[r[0]] < 0) return "actuator on a fixed joint";
+    int rec[KA_ISTRIDE] = {midx[r[0]], r[1], r[2], r[3]};
+    oi.insert(oi.end(), rec, rec + KA_ISTRIDE);
+    od.insert(od.end(), c, c + KA_DSTRIDE);
+  }
+  // ---- end effectors
+  oi[KI_O_EE] = (int)oi.size(); oi[KI_D_EE] = (int)od.size();
+  for (int e = 0; e < nee; ++e) {
+    const int j = ib[ib[TS_I_OFF_EE] + e * TS_EI_STRIDE];
+    const double* pos = db + ib[TS_I_DOFF_EE] + e * TS_ED_STRIDE;
+    const Xf& x = erel[j];
+    int rec[KE_ISTRIDE] = {mv_of(j), 0};
+    oi.insert(oi.end(), rec, rec + KE_ISTRIDE);
+    double d[KE_DSTRIDE] = {0};
+    for (int i = 0; i < 3; ++i) d[i] = x.R[3 * i] * pos[0] + x.R[3 * i + 1] * pos[1] + x.R[3 * i + 2] * pos[2] + x.p[i];
+    od.insert(od.end(), d, d + KE_DSTRIDE);
+  }
+  // ---- sensors
+  oi[KI_O_SENSOR] = (int)oi.size(); oi[KI_D_SENSOR] = (int)od.size();
+  for (int s = 0; s < nsens; ++s) {
+    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * TS_SI_STRIDE;
+    const double* c = db + ib[TS_I_DOFF_SENSOR] + s * TS_SD_STRIDE;
+    if (r[3] > KT_MAXCAND) return "too many tactile candidate bodies";
+    for (int k = 0; k < r[3]; ++k)
+      if (J[r[4 + k] * TS_JI_STRIDE + 4] != TS_SH_CUBOID) return "tactile candidates must be cuboids";
+    oi.insert(oi.end(), r, r + KS_ISTRIDE);
+    double d[KS_DSTRIDE] = {0};
+    for (int i = 0; i < 13; ++i) d[i] = c[i];
+    for (int k = 0; k < r[2]; ++k) d[KS_RMARK] = fmax(d[KS_RMARK], norm3(MK + 3 * (r[1] + k)));
+    od.insert(od.end(), d, d + KS_DSTRIDE);
+  }
+  oi[KI_D_POINTS] = (int)od.size();
+  od.insert(od.end(), P, P + 3 * npoints);
+  oi[KI_D_MARKERS] = (int)od.size();
+  od.insert(od.end(), MK, MK + 3 * nmark);
+  (void)nd;
+  return "";
+}

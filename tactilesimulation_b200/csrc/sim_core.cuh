@@ -1,7 +1,7 @@
 // Per-lane simulation math of the B200 tactile simulator.
 //
 // Everything here is templated on the scalar T (double, or Dual = value + one tangent) and
-// is free of CUDA intrinsics, so the same source is (a) inlined into the sm_100a kernels in
+// is free of CUDA intrinsics, so the same source is (a) compiled into the sm_100a kernels in
 // kernels.cu and (b) compiled by g++ into the test-only host harness (tests/emu) that lets
 // the parity tests run without a GPU.  Cross-lane work (LU solve, reductions, marker
 // striding) goes through a Tile policy: DevTile<LPE> = warp shuffles over a tile of LPE
@@ -11,15 +11,21 @@
 // DH/... = externals/DiffHand/core/projects/redmax/...):
 //   * residual of the implicit BDF1 step, DH/Simulation.cpp:1227-1251,
 //       g(q1) = M(q1) (q1-q0-h qd0) - h^2 f(q1,(q1-q0)/h)
-//     is evaluated matrix-free by one outward sweep over the joint tree (poses, twists
-//     phi = J qd, psi = J (q1-q0-h qd0), bias eta = Jdot qd), per-body wrenches
-//     a_i = I psi_i - h^2 (coriolis + gravity + contacts - I eta_i), and one inward sweep that
-//     accumulates J^T a  -- the reference instead builds J (42x7), Jdot, Mm, Km, Dm, dJ_dq ...
+//     is evaluated matrix-free in WORLD-frame spatial algebra over the MOVING joints only
+//     (fixed joints are folded into constant transforms by scene_lower.h):
+//       outward sweep   E_0j, V_j = J qd (twist), X_j = J (q1-q0-h qd0) + h^2 Jdot qd
+//       per body        a_i = I chi_i - h^2 (coriolis + gravity) in the body frame, pushed to the
+//                       world-frame wrench accumulator of its joint; contact wrenches likewise
+//       inward sweep    g_k = S_k . (sum of wrenches in the subtree of joint k) - h^2 (joint forces)
+//     -- the reference instead builds J (42x7), Jdot, Mm, Km, Dm, dJ_dq ...
 //     (DH/Simulation.cpp:256-454, DH/Robot.cpp:803-885).
-//   * derivatives: H = dg/dq1 and the adjoint blocks G0 = dg/dq0, G1 = dg/dqdot0 come from the
-//     same code on Dual numbers, one reduced coordinate per lane (see dual.cuh).  With
-//     FORCE actuators G0 = -M + hD and G1 = -hM in the reference's notation
-//     (DH/Simulation.cpp:1652,1657,1670,1692).
+//   * derivatives: H = dg/dq1 and the adjoint block G0 = dg/dq0 come from the same code on Dual
+//     numbers, one reduced coordinate per lane (see dual.cuh); G1 = dg/dqdot0 = -h M is built
+//     from mass-matrix columns (value arithmetic only).  With FORCE actuators G0 = -M + hD and
+//     G1 = -hM in the reference's notation (DH/Simulation.cpp:1652,1657,1670,1692).
+//   * Newton with backtracking line search (DH/Simulation.cpp:1150-1225): every line-search trial is
+//     evaluated WITH its Jacobian columns, so an accepted trial is at once the next iterate's
+//     (g, H) and -- when converged -- the tape's H; no residual is evaluated twice.
 //   * tactile readout: per-marker penalty force in the contacted box's frame
 //     (DH/Sensor/TactileSensor.cpp:29-87); its adjoint is hand-written reverse mode
 //     accumulating cotangents on (R2^T R1, R2^T(p1-p2), phi1, phi2) per candidate body
@@ -27,32 +33,45 @@
 //     Simulation.cpp:811-838).
 #pragma once
 #include "dual.cuh"
+#include "kernel_layout.h"
 #include "scene_layout.h"
 
-#define TS_EPS 1e-8  // constants::eps of the reference (DH/Common.h)
+#define TS_EPS 1e-8        // constants::eps of the reference (DH/Common.h)
+#define TS_CULL_MARGIN 1e-9  // slack (metres) of the bounding-sphere culls; rounding is ~1e-17
+
+#if defined(__CUDACC__)
+#define TS_NOINLINE __noinline__
+#else
+#define TS_NOINLINE __attribute__((noinline))
+#endif
+
+#define TS_MAXJ KT_MAXJ
+#define TS_MAXN KT_MAXN
+#define TS_MAXU KT_MAXU
+#define TS_MAXCAND KT_MAXCAND
 
 struct SceneView {
   const int* ib;
   const double* db;
-  int nj, n, nu, nee, nmark, nground, ngp, nact, nsens, max_iter, max_ls;
-  int o_joint, o_ground, o_gp, o_act, o_ee, o_sensor;
-  int d_joint, d_ground, d_gp, d_act, d_ee, d_sensor, d_points, d_markers;
+  int nj, n, nu, nee, nmark, nground, ngp, nact, nsens, max_iter, max_ls, nbody;
+  int o_joint, o_body, o_ground, o_gp, o_act, o_ee, o_sensor;
+  int d_joint, d_body, d_ground, d_gp, d_act, d_ee, d_sensor, d_points, d_markers;
   double h, tol, grav[3], gn[3], gx[3];
 };
 
 HDN inline void scene_view_init(SceneView& S, const int* ib, const double* db) {
   S.ib = ib; S.db = db;
-  S.nj = ib[TS_I_NJ]; S.n = ib[TS_I_NDOF_R]; S.nu = ib[TS_I_NDOF_U]; S.nee = ib[TS_I_NEE];
-  S.nmark = ib[TS_I_NMARKERS]; S.nground = ib[TS_I_NGROUND]; S.ngp = ib[TS_I_NGP];
-  S.nact = ib[TS_I_NACT]; S.nsens = ib[TS_I_NSENSORS];
-  S.max_iter = ib[TS_I_MAX_ITER]; S.max_ls = ib[TS_I_MAX_LS];
-  S.o_joint = ib[TS_I_OFF_JOINT]; S.o_ground = ib[TS_I_OFF_GROUND]; S.o_gp = ib[TS_I_OFF_GP];
-  S.o_act = ib[TS_I_OFF_ACT]; S.o_ee = ib[TS_I_OFF_EE]; S.o_sensor = ib[TS_I_OFF_SENSOR];
-  S.d_joint = ib[TS_I_DOFF_JOINT]; S.d_ground = ib[TS_I_DOFF_GROUND]; S.d_gp = ib[TS_I_DOFF_GP];
-  S.d_act = ib[TS_I_DOFF_ACT]; S.d_ee = ib[TS_I_DOFF_EE]; S.d_sensor = ib[TS_I_DOFF_SENSOR];
-  S.d_points = ib[TS_I_DOFF_POINTS]; S.d_markers = ib[TS_I_DOFF_MARKERS];
-  S.h = db[TS_D_H]; S.tol = db[TS_D_TOL];
-  for (int i = 0; i < 3; ++i) { S.grav[i] = db[TS_D_GRAV + i]; S.gn[i] = db[TS_D_GN + i]; S.gx[i] = db[TS_D_GX + i]; }
+  S.nj = ib[KI_NMJ]; S.n = ib[KI_N]; S.nu = ib[KI_NU]; S.nee = ib[KI_NEE];
+  S.nmark = ib[KI_NMARK]; S.nground = ib[KI_NGROUND]; S.ngp = ib[KI_NGP];
+  S.nact = ib[KI_NACT]; S.nsens = ib[KI_NSENS]; S.nbody = ib[KI_NBODY];
+  S.max_iter = ib[KI_MAX_ITER]; S.max_ls = ib[KI_MAX_LS];
+  S.o_joint = ib[KI_O_JOINT]; S.o_body = ib[KI_O_BODY]; S.o_ground = ib[KI_O_GROUND]; S.o_gp = ib[KI_O_GP];
+  S.o_act = ib[KI_O_ACT]; S.o_ee = ib[KI_O_EE]; S.o_sensor = ib[KI_O_SENSOR];
+  S.d_joint = ib[KI_D_JOINT]; S.d_body = ib[KI_D_BODY]; S.d_ground = ib[KI_D_GROUND]; S.d_gp = ib[KI_D_GP];
+  S.d_act = ib[KI_D_ACT]; S.d_ee = ib[KI_D_EE]; S.d_sensor = ib[KI_D_SENSOR];
+  S.d_points = ib[KI_D_POINTS]; S.d_markers = ib[KI_D_MARKERS];
+  S.h = db[KD_H]; S.tol = db[KD_TOL];
+  for (int i = 0; i < 3; ++i) { S.grav[i] = db[KD_GRAV + i]; S.gn[i] = db[KD_GN + i]; S.gx[i] = db[KD_GX + i]; }
 }
 
 // ------------------------------------------------------------------ small vector algebra
@@ -85,54 +104,57 @@ template <class A, class B, class C> HD void mm3(const A* a, const B* b, C* o) {
     for (int j = 0; j < 3; ++j)
       o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
-// twist to a child frame: given E = (R,p) of the child expressed in the parent,
-// out = Ad(E^-1) in :  w' = R^T w,  v' = R^T (v + w x p)
-template <class A, class B, class C> HD void twist_to_child(const A* R, const A* p, const B* in, C* out) {
+// world twist (w, v_O) -> twist of the frame (R,p) in its own coordinates:
+//   w' = R^T w,  v' = R^T (v_O + w x p)
+template <class A, class B, class C> HD void twist_to_frame(const A* R, const A* p, const B* in, C* out) {
   C t[3];
   cross3(in, p, t);
   t[0] = t[0] + in[3]; t[1] = t[1] + in[4]; t[2] = t[2] + in[5];
   mtv3(R, in, out);
   mtv3(R, t, out + 3);
 }
-// wrench to the parent frame: out = Ad(E^-1)^T in :  f' = R f,  tau' = R tau + p x f'
-template <class A, class B, class C> HD void wrench_to_parent(const A* R, const A* p, const B* in, C* out) {
-  C f[3], t[3], pf[3];
-  mv3(R, in + 3, f);
-  mv3(R, in, t);
-  cross3(p, f, pf);
-  out[0] = t[0] + pf[0]; out[1] = t[1] + pf[1]; out[2] = t[2] + pf[2];
-  out[3] = f[0]; out[4] = f[1]; out[5] = f[2];
-}
 
 // ------------------------------------------------------------------ per-lane work space
+// One record per MOVING joint, world frame: pose, twist V = J qd, X = J dl + h^2 Jdot qd and the
+// wrench accumulator of the joint's own bodies (summed over the subtree by the inward sweep).
 template <class T> struct Work {
-  T Rpj[TS_MAXJ][9], ppj[TS_MAXJ][3];   // joint frame in its parent joint frame
-  T R0j[TS_MAXJ][9], p0j[TS_MAXJ][3];   // joint frame in the world
-  T phj[TS_MAXJ][6], psj[TS_MAXJ][6], etj[TS_MAXJ][6];
-  T R0i[TS_MAXJ][9], p0i[TS_MAXJ][3];   // body frame in the world
-  T phi[TS_MAXJ][6];                    // body twist (angular; linear), body frame
-  T a[TS_MAXJ][6];                      // body wrench  I psi - h^2 (f - I eta)
-  T bj[TS_MAXJ][6];                     // joint-frame wrench accumulated from the subtree
+  T R0[TS_MAXJ][9], p0[TS_MAXJ][3];
+  T V[TS_MAXJ][6], X[TS_MAXJ][6];
+  T Wa[TS_MAXJ][6];
 };
 
-// Outward sweep.  dyn=false computes poses and twists only (readout / adjoint use).
+// Outward sweep over the moving joints.  dyn=false computes poses and twists only.
+// Joint models: DH/Joint/JointRevolute.cpp:38-69, JointPrismatic.cpp:22-45, JointPlanar.cpp:7-33,
+// JointTranslational.cpp:9-40; recursion DH/Joint/Joint.cpp:119-165.
 template <class T>
 HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Work<T>& W, bool dyn) {
   const double h2 = S.h * S.h;
   for (int j = 0; j < S.nj; ++j) {
-    const int* ji = S.ib + S.o_joint + j * TS_JI_STRIDE;
-    const double* jd = S.db + S.d_joint + j * TS_JD_STRIDE;
+    const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     const int jt = ji[0], par = ji[1], qo = ji[2];
-    const double* R0 = jd + TS_JD_RPJ;
-    const double* p0 = jd + TS_JD_PPJ;
-    const double* a0 = jd + TS_JD_AX0;
-    const double* a1 = jd + TS_JD_AX1;
-    T sq[6], sd[6], pq[3];
-    for (int i = 0; i < 6; ++i) { sq[i] = 0.0; sd[i] = 0.0; }
-    pq[0] = 0.0; pq[1] = 0.0; pq[2] = 0.0;
-    T* Rpj = W.Rpj[j];
-    T* ppj = W.ppj[j];
-    if (jt == TS_JT_REVOLUTE) {          // Q = exp([axis] q)      (DH/Joint/JointRevolute.cpp:38-69)
+    const double* Rc = jd + KJ_RA;
+    const double* pc = jd + KJ_PA;
+    const double* a0 = jd + KJ_AX0;
+    const double* a1 = jd + KJ_AX1;
+    // pre-motion frame = parent moving frame * constant offset
+    T Ra[9], pa[3], Vp[6], Xp[6];
+    if (par < 0) {
+      for (int i = 0; i < 9; ++i) Ra[i] = Rc[i];
+      for (int i = 0; i < 3; ++i) pa[i] = pc[i];
+      for (int i = 0; i < 6; ++i) { Vp[i] = 0.0; Xp[i] = 0.0; }
+    } else {
+      mm3(W.R0[par], Rc, Ra);
+      mv3(W.R0[par], pc, pa);
+      for (int i = 0; i < 3; ++i) pa[i] = pa[i] + W.p0[par][i];
+      for (int i = 0; i < 6; ++i) { Vp[i] = W.V[par][i]; if (dyn) Xp[i] = W.X[par][i]; else Xp[i] = 0.0; }
+    }
+    // world screw sums  sq = sum_d S_d qd_d,  sl = sum_d S_d dl_d
+    T sq[6], sl[6];
+    for (int i = 0; i < 6; ++i) { sq[i] = 0.0; sl[i] = 0.0; }
+    T* R0 = W.R0[j];
+    T* p0 = W.p0[j];
+    if (jt == TS_JT_REVOLUTE) {          // Q = exp([axis] q)
       T s, c;
       dsincos(q[qo], s, c);
       T c1 = 1.0 - c;
@@ -140,82 +162,127 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
       Rq[0] = c + c1 * (a0[0] * a0[0]); Rq[1] = c1 * (a0[0] * a0[1]) - s * a0[2]; Rq[2] = c1 * (a0[0] * a0[2]) + s * a0[1];
       Rq[3] = c1 * (a0[1] * a0[0]) + s * a0[2]; Rq[4] = c + c1 * (a0[1] * a0[1]); Rq[5] = c1 * (a0[1] * a0[2]) - s * a0[0];
       Rq[6] = c1 * (a0[2] * a0[0]) - s * a0[1]; Rq[7] = c1 * (a0[2] * a0[1]) + s * a0[0]; Rq[8] = c + c1 * (a0[2] * a0[2]);
-      mm3(R0, Rq, Rpj);
-      for (int i = 0; i < 3; ++i) { sq[i] = a0[i] * qd[qo]; if (dyn) sd[i] = a0[i] * dl[qo]; }
+      mm3(Ra, Rq, R0);
+      for (int i = 0; i < 3; ++i) p0[i] = pa[i];
+      T w[3], m[3];
+      mv3(Ra, a0, w);                    // world axis; screw = (w, p x w)
+      cross3(pa, w, m);
+      for (int i = 0; i < 3; ++i) {
+        sq[i] = w[i] * qd[qo]; sq[3 + i] = m[i] * qd[qo];
+        if (dyn) { sl[i] = w[i] * dl[qo]; sl[3 + i] = m[i] * dl[qo]; }
+      }
     } else {
-      for (int i = 0; i < 9; ++i) Rpj[i] = R0[i];
-      if (jt == TS_JT_PRISMATIC) {       // DH/Joint/JointPrismatic.cpp:22-45
-        for (int i = 0; i < 3; ++i) { pq[i] = a0[i] * q[qo]; sq[3 + i] = a0[i] * qd[qo]; if (dyn) sd[3 + i] = a0[i] * dl[qo]; }
-      } else if (jt == TS_JT_PLANAR) {   // DH/Joint/JointPlanar.cpp:7-33
+      for (int i = 0; i < 9; ++i) R0[i] = Ra[i];
+      T pq[3], vq[3], vl[3];
+      for (int i = 0; i < 3; ++i) { pq[i] = 0.0; vq[i] = 0.0; vl[i] = 0.0; }
+      if (jt == TS_JT_PRISMATIC) {
+        for (int i = 0; i < 3; ++i) { pq[i] = a0[i] * q[qo]; vq[i] = a0[i] * qd[qo]; if (dyn) vl[i] = a0[i] * dl[qo]; }
+      } else if (jt == TS_JT_PLANAR) {
         for (int i = 0; i < 3; ++i) {
           pq[i] = a0[i] * q[qo] + a1[i] * q[qo + 1];
-          sq[3 + i] = a0[i] * qd[qo] + a1[i] * qd[qo + 1];
-          if (dyn) sd[3 + i] = a0[i] * dl[qo] + a1[i] * dl[qo + 1];
+          vq[i] = a0[i] * qd[qo] + a1[i] * qd[qo + 1];
+          if (dyn) vl[i] = a0[i] * dl[qo] + a1[i] * dl[qo + 1];
         }
-      } else if (jt == TS_JT_TRANSLATIONAL) {  // DH/Joint/JointTranslational.cpp:9-40
-        for (int i = 0; i < 3; ++i) { pq[i] = q[qo + i]; sq[3 + i] = qd[qo + i]; if (dyn) sd[3 + i] = dl[qo + i]; }
+      } else if (jt == TS_JT_TRANSLATIONAL) {
+        for (int i = 0; i < 3; ++i) { pq[i] = q[qo + i]; vq[i] = qd[qo + i]; if (dyn) vl[i] = dl[qo + i]; }
       }
+      T t[3];
+      mv3(Ra, pq, t);
+      for (int i = 0; i < 3; ++i) p0[i] = pa[i] + t[i];
+      mv3(Ra, vq, sq + 3);               // pure translations: screw = (0, Ra axis)
+      if (dyn) mv3(Ra, vl, sl + 3);
     }
-    mv3(R0, pq, ppj);
-    ppj[0] = ppj[0] + p0[0]; ppj[1] = ppj[1] + p0[1]; ppj[2] = ppj[2] + p0[2];
-    T* R0j = W.R0j[j];
-    T* p0j = W.p0j[j];
-    T* phj = W.phj[j];
-    T* psj = W.psj[j];
-    T* etj = W.etj[j];
-    if (par < 0) {
-      for (int i = 0; i < 9; ++i) R0j[i] = Rpj[i];
-      for (int i = 0; i < 3; ++i) p0j[i] = ppj[i];
-      for (int i = 0; i < 6; ++i) { phj[i] = sq[i]; psj[i] = sd[i]; etj[i] = 0.0; }
-    } else {
-      mm3(W.R0j[par], Rpj, R0j);
-      mv3(W.R0j[par], ppj, p0j);
-      for (int i = 0; i < 3; ++i) p0j[i] = p0j[i] + W.p0j[par][i];
-      T b[6];
-      twist_to_child(Rpj, ppj, W.phj[par], b);
-      for (int i = 0; i < 6; ++i) phj[i] = sq[i] + b[i];
-      if (dyn) {
-        T t[6];
-        twist_to_child(Rpj, ppj, W.psj[par], t);
-        for (int i = 0; i < 6; ++i) psj[i] = sd[i] + t[i];
-        // eta_j = Ad(E_jp) eta_p - ad(S qd)(Ad(E_jp) phi_p)    (time derivative of Ad(E_jp))
-        twist_to_child(Rpj, ppj, W.etj[par], t);
-        T c0[3], c1[3], c2[3];
-        cross3(sq, b, c0);           // aw x bw
-        cross3(sq + 3, b, c1);       // av x bw
-        cross3(sq, b + 3, c2);       // aw x bv
-        for (int i = 0; i < 3; ++i) { etj[i] = t[i] - c0[i]; etj[3 + i] = t[3 + i] - (c1[i] + c2[i]); }
-      }
-    }
-    for (int i = 0; i < 6; ++i) W.bj[j][i] = 0.0;
-    // body rigidly attached to the joint frame by E_ji            (DH/Body/Body.cpp:122-141)
-    const double* Rji = jd + TS_JD_RJI;
-    const double* pji = jd + TS_JD_PJI;
-    T* R0i = W.R0i[j];
-    T* p0i = W.p0i[j];
-    mm3(R0j, Rji, R0i);
-    mv3(R0j, pji, p0i);
-    for (int i = 0; i < 3; ++i) p0i[i] = p0i[i] + p0j[i];
-    T* ph = W.phi[j];
-    twist_to_child(Rji, pji, phj, ph);
+    T* V = W.V[j];
+    for (int i = 0; i < 6; ++i) V[i] = Vp[i] + sq[i];
     if (dyn) {
-      const double* I6 = jd + TS_JD_INERTIA;
-      T ps[6], et[6];
-      twist_to_child(Rji, pji, psj, ps);
-      twist_to_child(Rji, pji, etj, et);
-      // coriolis ad(phi)^T (I phi) and gravity (0; m R^T g)      (DH/Body/Body.cpp:234-247)
-      T Iw[3], mv[3], fc0[3], fc1[3], fc2[3], gb[3];
-      for (int i = 0; i < 3; ++i) { Iw[i] = I6[i] * ph[i]; mv[i] = I6[3 + i] * ph[3 + i]; }
-      cross3(Iw, ph, fc0);
-      cross3(mv, ph + 3, fc1);
-      cross3(mv, ph, fc2);
-      mtv3(R0i, S.grav, gb);
-      T* a = W.a[j];
+      // X_j = X_p + S dl + h^2 ad(V_p)(S qd): the joint axes are fixed in the parent body
+      T c0[3], c1v[3], c2[3];
+      cross3(Vp, sq, c0);                // w_p x s_w
+      cross3(Vp, sq + 3, c1v);           // w_p x s_v
+      cross3(Vp + 3, sq, c2);            // v_p x s_w
+      T* X = W.X[j];
       for (int i = 0; i < 3; ++i) {
-        a[i] = I6[i] * ps[i] - h2 * ((fc0[i] + fc1[i]) - I6[i] * et[i]);
-        a[3 + i] = I6[3 + i] * ps[3 + i] - h2 * ((fc2[i] + I6[3] * gb[i]) - I6[3 + i] * et[3 + i]);
+        X[i] = Xp[i] + sl[i] + h2 * c0[i];
+        X[3 + i] = Xp[3 + i] + sl[3 + i] + h2 * (c1v[i] + c2[i]);
       }
+      for (int i = 0; i < 6; ++i) W.Wa[j][i] = 0.0;
     }
+  }
+}
+
+// pose of body b (and its twist in body coordinates) from the work space
+template <class T>
+HD void body_frame(const SceneView& S, const Work<T>& W, int b, T* R, T* p, T* ph) {
+  const int j = S.ib[S.o_body + b * KB_ISTRIDE];
+  const double* bd = S.db + S.d_body + b * KB_DSTRIDE;
+  if (j < 0) {
+    for (int i = 0; i < 9; ++i) R[i] = bd[KB_RMI + i];
+    for (int i = 0; i < 3; ++i) p[i] = bd[KB_PMI + i];
+    if (ph) for (int i = 0; i < 6; ++i) ph[i] = 0.0;
+    return;
+  }
+  mm3(W.R0[j], bd + KB_RMI, R);
+  mv3(W.R0[j], bd + KB_PMI, p);
+  for (int i = 0; i < 3; ++i) p[i] = p[i] + W.p0[j][i];
+  if (ph) twist_to_frame(R, p, W.V[j], ph);
+}
+// value-only variant (readouts run on the values of whatever scalar the work space holds)
+template <class T>
+HD void body_frame_v(const SceneView& S, const Work<T>& W, int b, double* R, double* p, double* ph) {
+  const int j = S.ib[S.o_body + b * KB_ISTRIDE];
+  const double* bd = S.db + S.d_body + b * KB_DSTRIDE;
+  if (j < 0) {
+    for (int i = 0; i < 9; ++i) R[i] = bd[KB_RMI + i];
+    for (int i = 0; i < 3; ++i) p[i] = bd[KB_PMI + i];
+    for (int i = 0; i < 6; ++i) ph[i] = 0.0;
+    return;
+  }
+  double R0[9], p0[3], V[6];
+  for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
+  for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
+  for (int i = 0; i < 6; ++i) V[i] = val(W.V[j][i]);
+  mm3(R0, bd + KB_RMI, R);
+  mv3(R0, bd + KB_PMI, p);
+  for (int i = 0; i < 3; ++i) p[i] += p0[i];
+  twist_to_frame(R, p, V, ph);
+}
+
+// body-frame wrench (moment; force) of the body at (R,p) -> world wrench about the origin, added
+// (times scale) to the accumulator of moving joint j
+template <class T>
+HD void push_wrench(Work<T>& W, int j, const T* R, const T* p, const T* wr, double scale) {
+  if (j < 0) return;
+  T f[3], t[3], pf[3];
+  mv3(R, wr + 3, f);
+  mv3(R, wr, t);
+  cross3(p, f, pf);
+  T* A = W.Wa[j];
+  for (int i = 0; i < 3; ++i) { A[i] = A[i] + scale * (t[i] + pf[i]); A[3 + i] = A[3 + i] + scale * f[i]; }
+}
+
+// a_i = I chi_i - h^2 (coriolis + gravity) for every dynamic body   (DH/Body/Body.cpp:234-247)
+template <class T>
+HDN void body_dynamics(const SceneView& S, Work<T>& W) {
+  const double h2 = S.h * S.h;
+  for (int b = 0; b < S.nbody; ++b) {
+    const int* bi = S.ib + S.o_body + b * KB_ISTRIDE;
+    if (!bi[2]) continue;
+    const int j = bi[0];
+    const double* I6 = S.db + S.d_body + b * KB_DSTRIDE + KB_INERTIA;
+    T R[9], p[3], ph[6], ch[6];
+    body_frame(S, W, b, R, p, ph);
+    twist_to_frame(R, p, W.X[j], ch);
+    T Iw[3], mv[3], fc0[3], fc1[3], fc2[3], gb[3], a[6];
+    for (int i = 0; i < 3; ++i) { Iw[i] = I6[i] * ph[i]; mv[i] = I6[3 + i] * ph[3 + i]; }
+    cross3(Iw, ph, fc0);
+    cross3(mv, ph + 3, fc1);
+    cross3(mv, ph, fc2);
+    mtv3(R, S.grav, gb);
+    for (int i = 0; i < 3; ++i) {
+      a[i] = I6[i] * ch[i] - h2 * (fc0[i] + fc1[i]);
+      a[3 + i] = I6[3 + i] * ch[3 + i] - h2 * (fc2[i] + I6[3] * gb[i]);
+    }
+    push_wrench(W, j, R, p, a, 1.0);
   }
 }
 
@@ -235,30 +302,40 @@ HD double cuboid_distance(const double* x, const double* hs) {
   for (int i = 0; i < 3; ++i) { d = fmax(d, fmax(x[i] - hs[i], -x[i] - hs[i])); }
   return d;
 }
+template <class T> HD void vals3(const T* a, double* o) { o[0] = val(a[0]); o[1] = val(a[1]); o[2] = val(a[2]); }
+template <class T> HD void vals9(const T* a, double* o) { for (int i = 0; i < 9; ++i) o[i] = val(a[i]); }
 
 // ------------------------------------------------------------------ contact forces
 // ground plane vs sampled body points: DH/Force/ForceGroundContact.cpp:105-147,
 // detection d <= 0: DH/CollisionDetection/CollisionDetection.cpp:13-42
 template <class T>
-HDN void ground_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out) {
+HDN void ground_contacts(const SceneView& S, Work<T>& W) {
   const double h2 = S.h * S.h;
   for (int gi = 0; gi < S.nground; ++gi) {
-    const int* r = S.ib + S.o_ground + gi * TS_GI_STRIDE;
-    const double* c = S.db + S.d_ground + gi * TS_CD_STRIDE;
+    const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
+    const double* c = S.db + S.d_ground + gi * KG_DSTRIDE;
     const int b = r[0], po = r[1], pc = r[2];
+    const int jb = S.ib[S.o_body + b * KB_ISTRIDE];
+    if (jb < 0) continue;
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
-    const T* R = W.R0i[b];
-    const T* p = W.p0i[b];
-    const T* ph = W.phi[b];
+    T R[9], p[3], ph[6];
+    body_frame(S, W, b, R, p, ph);
+    double Rv[9], pv[3];
+    vals9(R, Rv);
+    vals3(p, pv);
     T wr[6];
     for (int i = 0; i < 6; ++i) wr[i] = 0.0;
+    bool any = false;
     for (int k = 0; k < pc; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
+      double xv[3];
+      mv3(Rv, xi, xv);
+      const double dv = (xv[0] + pv[0] - S.gx[0]) * S.gn[0] + (xv[1] + pv[1] - S.gx[1]) * S.gn[1] + (xv[2] + pv[2] - S.gx[2]) * S.gn[2];
+      if (!(dv <= 0.0)) continue;
+      any = true;
       T xw[3];
       mv3(R, xi, xw);
       T d = (xw[0] + p[0] - S.gx[0]) * S.gn[0] + (xw[1] + p[1] - S.gx[1]) * S.gn[1] + (xw[2] + p[2] - S.gx[2]) * S.gn[2];
-      if (!(val(d) <= 0.0)) continue;
-      if (mask_out && k < 32) mask_out[gi] |= (1u << k);
       T w[3], vw[3];
       cross3(ph, xi, w);
       w[0] = w[0] + ph[3]; w[1] = w[1] + ph[4]; w[2] = w[2] + ph[5];
@@ -284,34 +361,52 @@ HDN void ground_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out) {
       cross3(xi, Fb, tq);
       for (int i = 0; i < 3; ++i) { wr[i] = wr[i] + tq[i]; wr[3 + i] = wr[3 + i] + Fb[i]; }
     }
-    for (int i = 0; i < 6; ++i) W.a[b][i] = W.a[b][i] - h2 * wr[i];
+    if (any) push_wrench(W, jb, R, p, wr, -h2);
   }
 }
 
 // sampled points of a general body vs a cuboid SDF: DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
 // DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83
 template <class T>
-HDN void gp_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out /* 3 words per force */) {
+HDN void gp_contacts(const SceneView& S, Work<T>& W) {
   const double h2 = S.h * S.h;
   for (int fi = 0; fi < S.ngp; ++fi) {
-    const int* r = S.ib + S.o_gp + fi * TS_PI_STRIDE;
-    const double* c = S.db + S.d_gp + fi * TS_CD_STRIDE;
+    const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
+    const double* c = S.db + S.d_gp + fi * KP_DSTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
+    const int j1 = S.ib[S.o_body + b1 * KB_ISTRIDE], j2 = S.ib[S.o_body + b2 * KB_ISTRIDE];
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
-    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
-    const T* R1 = W.R0i[b1]; const T* p1 = W.p0i[b1]; const T* ph1 = W.phi[b1];
-    const T* R2 = W.R0i[b2]; const T* p2 = W.p0i[b2]; const T* ph2 = W.phi[b2];
+    const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
+    const double* hs = bd2 + KB_HALF;
+    // exact-safe cull on values: a point of body 1 inside the box needs |p1 - p2| <= r_points + |half|
+    double R1v[9], p1v[3], R2v[9], p2v[3], phv[6];
+    body_frame_v(S, W, b1, R1v, p1v, phv);
+    body_frame_v(S, W, b2, R2v, p2v, phv);
+    {
+      const double rr = c[4] + bd2[KB_RBOUND] + TS_CULL_MARGIN;
+      const double dx = p1v[0] - p2v[0], dy = p1v[1] - p2v[1], dz = p1v[2] - p2v[2];
+      if (dx * dx + dy * dy + dz * dz > rr * rr) continue;
+    }
+    T R1[9], p1[3], ph1[6], R2[9], p2[3], ph2[6];
     T w1[6], w2[6];
-    for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+    bool any = false;
     for (int k = 0; k < pc; ++k) {
       const double* xi1 = S.db + S.d_points + 3 * (po + k);
+      double xwv[3], yv[3], xv[3];
+      mv3(R1v, xi1, xwv);
+      for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
+      mtv3(R2v, yv, xv);
+      if (!(cuboid_distance(xv, hs) < 0.0)) continue;
+      if (!any) {
+        any = true;
+        body_frame(S, W, b1, R1, p1, ph1);
+        body_frame(S, W, b2, R2, p2, ph2);
+        for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+      }
       T xw[3], y[3], x[3];
       mv3(R1, xi1, xw);
       for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
       mtv3(R2, y, x);
-      double xv[3] = {val(x[0]), val(x[1]), val(x[2])};
-      if (!(cuboid_distance(xv, hs) < 0.0)) continue;
-      if (mask_out && k < 96) mask_out[3 * fi + (k >> 5)] |= (1u << (k & 31));
       int ax; double sg;
       cuboid_face(xv, hs, ax, sg);
       T d = sg * x[ax] - hs[ax];
@@ -365,9 +460,9 @@ HDN void gp_contacts(const SceneView& S, Work<T>& W, unsigned* mask_out /* 3 wor
       cross3(xi1, F1, tq);
       for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + F1[i]; }
     }
-    for (int i = 0; i < 6; ++i) {
-      W.a[b1][i] = W.a[b1][i] - h2 * w1[i];
-      W.a[b2][i] = W.a[b2][i] - h2 * w2[i];
+    if (any) {
+      push_wrench(W, j1, R1, p1, w1, -h2);
+      push_wrench(W, j2, R2, p2, w2, -h2);
     }
   }
 }
@@ -379,56 +474,58 @@ HD double motor_force(double u, double cmin, double cmax) {
   return fmax(fmin(f, cmax), cmin);
 }
 
-// Inward sweep: g = J^T a - h^2 (joint damping + limit springs + motors)
+// Inward sweep: g = S^T (subtree wrench) - h^2 (joint damping + limit springs + motors)
 template <class T>
 HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const double* u, T* g) {
   const double h2 = S.h * S.h;
   for (int j = S.nj - 1; j >= 0; --j) {
-    const int* ji = S.ib + S.o_joint + j * TS_JI_STRIDE;
-    const double* jd = S.db + S.d_joint + j * TS_JD_STRIDE;
+    const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     const int jt = ji[0], par = ji[1], qo = ji[2], nd = ji[3];
-    T b[6], t[6];
-    wrench_to_parent(jd + TS_JD_RJI, jd + TS_JD_PJI, W.a[j], t);
-    for (int i = 0; i < 6; ++i) b[i] = W.bj[j][i] + t[i];
-    const double* a0 = jd + TS_JD_AX0;
-    const double* a1 = jd + TS_JD_AX1;
-    if (jt == TS_JT_REVOLUTE) g[qo] = dot3(a0, b);
-    else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, b + 3);
-    else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, b + 3); g[qo + 1] = dot3(a1, b + 3); }
-    else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = b[3]; g[qo + 1] = b[4]; g[qo + 2] = b[5]; }
+    const T* A = W.Wa[j];
+    const double* a0 = jd + KJ_AX0;
+    const double* a1 = jd + KJ_AX1;
+    T fj[3];
+    mtv3(W.R0[j], A + 3, fj);            // force in joint coordinates
+    if (jt == TS_JT_REVOLUTE) {
+      T pf[3], t[3], nj3[3];
+      cross3(W.p0[j], A + 3, pf);        // moment about the joint origin
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      mtv3(W.R0[j], t, nj3);
+      g[qo] = dot3(a0, nj3);
+    } else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, fj);
+    else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, fj); g[qo + 1] = dot3(a1, fj); }
+    else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = fj[0]; g[qo + 1] = fj[1]; g[qo + 2] = fj[2]; }
     // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
-    const double damp = jd[TS_JD_DAMP], lo = jd[TS_JD_LIMLO], hi = jd[TS_JD_LIMHI], lk = jd[TS_JD_LIMK];
+    const double damp = jd[KJ_DAMP], lo = jd[KJ_LIMLO], hi = jd[KJ_LIMHI], lk = jd[KJ_LIMK];
     for (int i = 0; i < nd; ++i) {
       T fr = -(damp * qd[qo + i]);
       if (val(q[qo + i]) < lo) fr = fr + lk * (lo - q[qo + i]);
       if (val(q[qo + i]) > hi) fr = fr + lk * (hi - q[qo + i]);
       g[qo + i] = g[qo + i] - h2 * fr;
     }
-    if (par >= 0) {
-      wrench_to_parent(W.Rpj[j], W.ppj[j], b, t);
-      for (int i = 0; i < 6; ++i) W.bj[par][i] = W.bj[par][i] + t[i];
-    }
+    if (par >= 0) for (int i = 0; i < 6; ++i) W.Wa[par][i] = W.Wa[par][i] + A[i];
   }
   for (int ai = 0; ai < S.nact; ++ai) {
-    const int* r = S.ib + S.o_act + ai * TS_AI_STRIDE;
-    const double* c = S.db + S.d_act + ai * TS_AD_STRIDE;
-    const int qo = S.ib[S.o_joint + r[0] * TS_JI_STRIDE + 2];
+    const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
+    const double* c = S.db + S.d_act + ai * KA_DSTRIDE;
+    const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
     for (int i = 0; i < r[3]; ++i) g[qo + i] = g[qo + i] - h2 * motor_force(u[r[2] + i], c[i], c[3 + i]);
   }
 }
 
 // residual of the BDF1 step for (q1; q0, qd0)
 template <class T>
-HDN void eval_g(const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W, T* g,
-                unsigned* gmask, unsigned* pmask) {
+HDN void eval_g(const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W, T* g) {
   T qd1[TS_MAXN], dl[TS_MAXN];
   for (int i = 0; i < S.n; ++i) {
     qd1[i] = (q1[i] - q0[i]) / S.h;
     dl[i] = q1[i] - q0[i] - S.h * qd0[i];
   }
   kinematics<T>(S, q1, qd1, dl, W, true);
-  ground_contacts<T>(S, W, gmask);
-  gp_contacts<T>(S, W, pmask);
+  body_dynamics<T>(S, W);
+  ground_contacts<T>(S, W);
+  gp_contacts<T>(S, W);
   inward<T>(S, W, q1, qd1, u, g);
 }
 
@@ -440,7 +537,6 @@ struct HostTile {
   HD double bcast(double v, int) const { return v; }
   HD int bcasti(int v, int) const { return v; }
   HD double sum(double v) const { return v; }
-  HD int any(int p) const { return p; }
 };
 
 #define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
@@ -519,10 +615,12 @@ HD double norm_n(const double* v, int n) {
 }
 
 // One Dual evaluation per owned column: returns g (replicated) and the owned columns of
-// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.
+// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  Deliberately NOT inlined: the kernels call it from
+// several places and one copy of the residual code keeps the instruction working set small.
 template <class Tile>
-HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0, const double* qd0,
-                      const double* u, int seed, Work<Dual>& W, double* g, double (*col)[TS_MAXN]) {
+TS_NOINLINE HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
+                                  const double* qd0, const double* u, int seed, Work<Dual>& W, double* g,
+                                  double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;
@@ -532,11 +630,77 @@ HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const
       xq0[i] = mkdual(q0[i], (seed == 1 && i == k) ? 1.0 : 0.0);
       xqd0[i] = mkdual(qd0[i], (seed == 2 && i == k) ? 1.0 : 0.0);
     }
-    eval_g<Dual>(S, xq, xq0, xqd0, u, W, gD, (unsigned*)0, (unsigned*)0);
+    eval_g<Dual>(S, xq, xq0, xqd0, u, W, gD);
     for (int i = 0; i < TS_MAXN; ++i) {
       if (i < S.n) { g[i] = gD[i].v; col[c][i] = (k < S.n) ? gD[i].d : 0.0; }
       else { g[i] = 0.0; col[c][i] = 0.0; }
     }
+  }
+}
+
+// Column k of the mass matrix M = J^T Mm J at the poses held in W (values), value arithmetic only:
+// psi = S_k on every joint of the subtree of dof k's joint, a_i = I psi_i, projected inward.
+template <class T>
+HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) {
+  for (int i = 0; i < TS_MAXN; ++i) Mcol[i] = 0.0;
+  if (k >= S.n) return;
+  // joint and world screw of dof k
+  int jk = -1;
+  double Sk[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < S.nj; ++j) {
+    const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
+    if (k < ji[2] || k >= ji[2] + ji[3]) continue;
+    jk = j;
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
+    double R0[9], p0[3];
+    for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
+    for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
+    const int jt = ji[0], loc = k - ji[2];
+    if (jt == TS_JT_REVOLUTE) {
+      mv3(R0, jd + KJ_AX0, Sk);            // R0 a = Ra a for a rotation about a
+      cross3(p0, Sk, Sk + 3);
+    } else if (jt == TS_JT_PRISMATIC) mv3(R0, jd + KJ_AX0, Sk + 3);
+    else if (jt == TS_JT_PLANAR) mv3(R0, loc == 0 ? jd + KJ_AX0 : jd + KJ_AX1, Sk + 3);
+    else { for (int i = 0; i < 3; ++i) Sk[3 + i] = R0[3 * i + loc]; }
+  }
+  if (jk < 0) return;
+  double Wm[TS_MAXJ][6];
+  for (int j = 0; j < TS_MAXJ; ++j) for (int i = 0; i < 6; ++i) Wm[j][i] = 0.0;
+  for (int b = 0; b < S.nbody; ++b) {
+    const int* bi = S.ib + S.o_body + b * KB_ISTRIDE;
+    if (!bi[2]) continue;
+    const int j = bi[0];
+    if (!((S.ib[S.o_joint + j * KJ_ISTRIDE + 4] >> jk) & 1)) continue;   // body not in the subtree of jk
+    const double* I6 = S.db + S.d_body + b * KB_DSTRIDE + KB_INERTIA;
+    double R[9], p[3], ph[6], ps[6], a[6];
+    body_frame_v(S, W, b, R, p, ph);
+    twist_to_frame(R, p, Sk, ps);
+    for (int i = 0; i < 6; ++i) a[i] = I6[i] * ps[i];
+    double f[3], t[3], pf[3];
+    mv3(R, a + 3, f);
+    mv3(R, a, t);
+    cross3(p, f, pf);
+    for (int i = 0; i < 3; ++i) { Wm[j][i] += t[i] + pf[i]; Wm[j][3 + i] += f[i]; }
+  }
+  for (int j = S.nj - 1; j >= 0; --j) {
+    const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
+    const int jt = ji[0], par = ji[1], qo = ji[2];
+    double R0[9], p0[3], fj[3];
+    for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
+    for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
+    const double* A = Wm[j];
+    mtv3(R0, A + 3, fj);
+    if (jt == TS_JT_REVOLUTE) {
+      double pf[3], t[3], nj3[3];
+      cross3(p0, A + 3, pf);
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      mtv3(R0, t, nj3);
+      Mcol[qo] = dot3(jd + KJ_AX0, nj3);
+    } else if (jt == TS_JT_PRISMATIC) Mcol[qo] = dot3(jd + KJ_AX0, fj);
+    else if (jt == TS_JT_PLANAR) { Mcol[qo] = dot3(jd + KJ_AX0, fj); Mcol[qo + 1] = dot3(jd + KJ_AX1, fj); }
+    else if (jt == TS_JT_TRANSLATIONAL) { Mcol[qo] = fj[0]; Mcol[qo + 1] = fj[1]; Mcol[qo + 2] = fj[2]; }
+    if (par >= 0) for (int i = 0; i < 6; ++i) Wm[par][i] += A[i];
   }
 }
 
@@ -547,49 +711,74 @@ HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const
 // One implicit step (DH/Simulation.cpp:1325-1351 with the Newton of :1150-1225).
 // q, qd: in = state at t, out = state at t+h (replicated over the tile).
 // tape (grad mode): H, G0, G1 as [3][n][n] row-major, columns written by their owner lanes.
+// On return the work space holds the kinematics (values) of the new state.
 template <class Tile>
 HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, const double* u,
                      double* tape, void* workbuf) {
   const int L = Tile::LPE;
   const int n = S.n;
   Work<Dual>& WD = *(Work<Dual>*)workbuf;
-  Work<double>& WS = *(Work<double>*)workbuf;
   double x[TS_MAXN], g[TS_MAXN], gn_[TS_MAXN], dx[TS_MAXN], xn[TS_MAXN];
-  double col[TS_NC(L)][TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; gn_[i] = 0.0; }
+  double col[TS_NC(L)][TS_MAXN], coln[TS_NC(L)][TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; gn_[i] = 0.0; g[i] = 0.0; }
   for (int i = 0; i < n; ++i) x[i] = q[i] + S.h * qd[i];
   int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
   int fail_strike = 0, iters = 0, ls = 0;
   bool converged = false;
+  bool fresh = false;        // (g, col) are the residual and Jacobian columns at the current x
+  bool work_at_x = false;    // the work space holds the kinematics of the current x
   for (int it = 0; it < max_newton; ++it) {
     ++iters;
-    eval_columns(tl, S, x, q, qd, u, 0, WD, g, col);
+    if (!fresh) eval_columns(tl, S, x, q, qd, u, 0, WD, g, col);
     for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -g[i] : 0.0;
     lu_solve(tl, col, dx, n);
+    fresh = false;
     const double gnorm = norm_n(g, n);
     double alpha = 1.0;
     bool success = false;
     for (int trial = 0; trial < S.max_ls; ++trial, alpha *= 0.5) {
       ++ls;
       for (int i = 0; i < n; ++i) xn[i] = x[i] + alpha * dx[i];
-      eval_g<double>(S, xn, q, qd, u, WS, gn_, (unsigned*)0, (unsigned*)0);
+      eval_columns(tl, S, xn, q, qd, u, 0, WD, gn_, coln);
       if (norm_n(gn_, n) < gnorm) { success = true; break; }
     }
     if (success) fail_strike = 0;
     else { ++fail_strike; if (fail_strike >= 10) break; }
     for (int i = 0; i < n; ++i) x[i] = x[i] + alpha * dx[i];
+    if (success) {
+      // the accepted trial is the next iterate: reuse its residual and Jacobian columns
+      for (int i = 0; i < TS_MAXN; ++i) g[i] = gn_[i];
+      for (int c = 0; c < TS_NC(L); ++c) for (int i = 0; i < TS_MAXN; ++i) col[c][i] = coln[c][i];
+      fresh = true;
+    }
+    work_at_x = success;
     if (norm_n(gn_, n) < S.tol) { converged = true; break; }
   }
   int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
   if (tape) {
-    // adjoint tape at the converged state: H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0
-    for (int s = 0; s < 3; ++s) {
-      eval_columns(tl, S, x, q, qd, u, s, WD, g, col);
-      for (int c = 0; c < TS_NC(L); ++c) {
-        const int k = tl.lane + c * L;
-        if (k < n) for (int i = 0; i < n; ++i) tape[s * n * n + i * n + k] = col[c][i];
+    // adjoint tape at the final state: H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0 = -h M
+    if (!fresh) { eval_columns(tl, S, x, q, qd, u, 0, WD, g, col); work_at_x = true; }
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = col[c][i];
+    }
+    eval_columns(tl, S, x, q, qd, u, 1, WD, g, col);
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      if (k < n) {
+        double Mc[TS_MAXN];
+        mass_column(S, WD, k, Mc);
+        for (int i = 0; i < n; ++i) {
+          tape[n * n + i * n + k] = col[c][i];
+          tape[2 * n * n + i * n + k] = -S.h * Mc[i];
+        }
       }
     }
+  } else if (!work_at_x) {
+    // rare: the last line search failed, so the work space is not at the final state
+    Dual xq[TS_MAXN], xqd[TS_MAXN];
+    for (int i = 0; i < n; ++i) { xq[i] = mkdual(x[i], 0.0); xqd[i] = mkdual((x[i] - q[i]) / S.h, 0.0); }
+    kinematics<Dual>(S, xq, xqd, (const Dual*)0, WD, false);
   }
   for (int i = 0; i < n; ++i) {
     double q1 = x[i];
@@ -604,43 +793,62 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
 // end-effector positions (DH/EndEffector/EndEffector.cpp:31-36)
 template <class T>
 HD void variable_of(const SceneView& S, const Work<T>& W, int e, T* out) {
-  const int j = S.ib[S.o_ee + e * TS_EI_STRIDE];
-  const double* pos = S.db + S.d_ee + e * TS_ED_STRIDE;
-  mv3(W.R0j[j], pos, out);
-  for (int i = 0; i < 3; ++i) out[i] = out[i] + W.p0j[j][i];
+  const int j = S.ib[S.o_ee + e * KE_ISTRIDE];
+  const double* pos = S.db + S.d_ee + e * KE_DSTRIDE;
+  if (j < 0) { for (int i = 0; i < 3; ++i) out[i] = pos[i]; return; }
+  mv3(W.R0[j], pos, out);
+  for (int i = 0; i < 3; ++i) out[i] = out[i] + W.p0[j][i];
+}
+
+// world frames of the sensor body (slot 0) and its candidate bodies (slots 1..ncand), values only
+struct Frames {
+  double R[1 + TS_MAXCAND][9], p[1 + TS_MAXCAND][3], ph[1 + TS_MAXCAND][6];
+  bool near[1 + TS_MAXCAND];   // candidate may touch a marker (bounding-sphere test)
+};
+template <class T>
+HDN void sensor_frames(const SceneView& S, const Work<T>& W, const int* sr, const double* sd, Frames& F) {
+  const int nc = sr[3];
+  body_frame_v(S, W, sr[0], F.R[0], F.p[0], F.ph[0]);
+  F.near[0] = true;
+  for (int c = 0; c < nc; ++c) {
+    const int b2 = sr[4 + c];
+    body_frame_v(S, W, b2, F.R[1 + c], F.p[1 + c], F.ph[1 + c]);
+    const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
+    const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
+    F.near[1 + c] = !(dx * dx + dy * dy + dz * dz > rr * rr);
+  }
 }
 
 // per-marker intermediate of the tactile force, shared by the value pass and its adjoint
 struct MarkerHit {
-  int body;           // contacted body (last candidate with d < 0), -1 if none
+  int cand;           // index of the contacted candidate (last candidate with d < 0), -1 if none
   int ax; double sg;  // face of the box
   double x[3], u[3], d, ddot, tb[3], s, tn;
   bool dynamic;
 };
 
-// Evaluate marker m of sensor record (sr, sd).  DH/Sensor/TactileSensor.cpp:29-87
-HD void marker_force(const SceneView& S, const Work<double>& W, const int* sr, const double* sd, const double* xi1,
+// Evaluate one marker of sensor record (sr, sd).  DH/Sensor/TactileSensor.cpp:29-87
+HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const double* sd, const double* xi1,
                      MarkerHit& H, double* F1 /* force in the pad frame */) {
-  const int b1 = sr[0], nc = sr[3];
+  const int nc = sr[3];
   const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
-  const double* R1 = W.R0i[b1]; const double* p1 = W.p0i[b1]; const double* ph1 = W.phi[b1];
+  const double* R1 = F.R[0]; const double* p1 = F.p[0]; const double* ph1 = F.ph[0];
   double xw[3];
   mv3(R1, xi1, xw);
   for (int i = 0; i < 3; ++i) xw[i] += p1[i];
-  H.body = -1;
+  H.cand = -1;
   for (int c = 0; c < nc; ++c) {
-    const int b2 = sr[4 + c];
-    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+    if (!F.near[1 + c]) continue;
+    const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
     double y[3], x[3];
-    for (int i = 0; i < 3; ++i) y[i] = xw[i] - W.p0i[b2][i];
-    mtv3(W.R0i[b2], y, x);
-    if (cuboid_distance(x, hs) < 0.0) { H.body = b2; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
+    for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
+    mtv3(F.R[1 + c], y, x);
+    if (cuboid_distance(x, hs) < 0.0) { H.cand = c; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
   }
   F1[0] = F1[1] = F1[2] = 0.0;
-  if (H.body < 0) return;
-  const int b2 = H.body;
-  const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
-  const double* R2 = W.R0i[b2]; const double* ph2 = W.phi[b2];
+  if (H.cand < 0) return;
+  const double* hs = S.db + S.d_body + sr[4 + H.cand] * KB_DSTRIDE + KB_HALF;
+  const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
   H.d = cuboid_face(H.x, hs, H.ax, H.sg);
   double v1[3], xwd[3], t3[3];
   cross3(ph1, xi1, v1);
@@ -677,22 +885,31 @@ HD void marker_force(const SceneView& S, const Work<double>& W, const int* sr, c
 
 // tactile values of this env, markers strided over the tile's lanes.
 // out: [M][3] = (shear . axis0, shear . axis1, normal)      (TactileSensor.cpp:74-81)
-template <class Tile>
-HDN void tactile_values(const Tile& tl, const SceneView& S, const Work<double>& W, double* out, int* body_out) {
+template <class Tile, class T>
+HDN void tactile_values(const Tile& tl, const SceneView& S, const Work<T>& W, double* out, int* body_out) {
   for (int si = 0; si < S.nsens; ++si) {
-    const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
-    const double* sd = S.db + S.d_sensor + si * TS_SD_STRIDE;
+    const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
+    const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
     const int mo = sr[1], mc = sr[2];
+    Frames F;
+    sensor_frames(S, W, sr, sd, F);
+    bool anynear = false;
+    for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
+      double* o = out + 3 * (mo + m);
+      if (!anynear) {
+        o[0] = 0.0; o[1] = 0.0; o[2] = -0.0;
+        if (body_out) body_out[mo + m] = -1;
+        continue;
+      }
       const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
       MarkerHit H;
       double F1[3];
-      marker_force(S, W, sr, sd, xi1, H, F1);
-      double* o = out + 3 * (mo + m);
+      marker_force(S, F, sr, sd, xi1, H, F1);
       o[0] = dot3(F1, sd + 4);
       o[1] = dot3(F1, sd + 7);
       o[2] = -dot3(F1, sd + 10);
-      if (body_out) body_out[mo + m] = H.body;
+      if (body_out) body_out[mo + m] = H.cand < 0 ? -1 : sr[4 + H.cand];
     }
   }
 }
@@ -703,27 +920,33 @@ struct TacAcc {
   double v[24];
 };
 
-// Reverse-mode through marker_force for every marker of this lane's stride.
-template <class Tile>
-HDN void tactile_vjp(const Tile& tl, const SceneView& S, const Work<double>& W, const double* wbar, TacAcc* acc) {
+// Reverse-mode through marker_force for every marker of this lane's stride.  Returns (tile-wide)
+// whether any marker is in contact; acc is only meaningful then.
+template <class Tile, class T>
+HDN bool tactile_vjp(const Tile& tl, const SceneView& S, const Work<T>& W, const double* wbar, TacAcc* acc) {
   for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = 0.0;
+  double hits = 0.0;
   for (int si = 0; si < S.nsens; ++si) {
-    const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
-    const double* sd = S.db + S.d_sensor + si * TS_SD_STRIDE;
-    const int b1 = sr[0], mo = sr[1], mc = sr[2], nc = sr[3];
+    const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
+    const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
+    const int mo = sr[1], mc = sr[2];
     const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
-    const double* R1 = W.R0i[b1]; const double* ph1 = W.phi[b1];
+    Frames F;
+    sensor_frames(S, W, sr, sd, F);
+    bool anynear = false;
+    for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
+    if (!anynear) continue;
+    const double* R1 = F.R[0]; const double* ph1 = F.ph[0];
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
       const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
       const double* wb = wbar + 3 * (mo + m);
       MarkerHit H;
       double F1[3];
-      marker_force(S, W, sr, sd, xi1, H, F1);
-      if (H.body < 0) continue;
-      int ci = 0;
-      for (int c = 0; c < nc; ++c) if (sr[4 + c] == H.body) ci = c;
-      double* A = acc[ci].v;
-      const double* R2 = W.R0i[H.body]; const double* ph2 = W.phi[H.body];
+      marker_force(S, F, sr, sd, xi1, H, F1);
+      if (H.cand < 0) continue;
+      hits += 1.0;
+      double* A = acc[H.cand].v;
+      const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
       double R21[9];
       for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R21[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
@@ -783,7 +1006,10 @@ HDN void tactile_vjp(const Tile& tl, const SceneView& S, const Work<double>& W, 
       for (int i = 0; i < 3; ++i) A[9 + i] += xbar[i];
     }
   }
+  hits = tl.sum(hits);
+  if (hits == 0.0) return false;
   for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = tl.sum(acc[c].v[i]);
+  return true;
 }
 
 // body-frame Jacobian column from a Dual pose: w = axial(R^T dR), v = R^T dp
@@ -802,13 +1028,13 @@ HD void jac_col(const Dual* R, const Dual* p, double* J) {
 //   y_k = df_dq_k + dvar_dq^T b + dtac_dq^T w + (1/h) dtac_dqdot^T w - pendA
 //   z_k = H_k^-T y_k ;  df_du_k = h^2 dfr_du^T z_k
 //   pendA' = pendB + (G0 + G1/h)^T z_k + (1/h) dtac_dqdot^T w ;  pendB' = -(G1/h)^T z_k
-// out_g0z / out_g1z / out_c (optional, distributed) expose G0^T z, G1^T z and
-// (1/h) dtac_dqdot^T w for the q0 / qdot0 gradients of the first step.
+// out_g0z / out_g1z (optional, distributed) expose G0^T z (+ pending terms) and G1^T z for the
+// q0 / qdot0 gradients of the first step.
 template <class Tile>
 HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, const double* qdk, const double* uk,
                        const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
                        double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
-                       double* out_c, void* workbuf) {
+                       void* workbuf) {
   const int L = Tile::LPE;
   const int n = S.n;
   double y[TS_NC(L)], cterm[TS_NC(L)];
@@ -819,20 +1045,17 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
     cterm[c] = 0.0;
   }
   const bool have_var = dvar_cot != 0 && S.nee > 0;
-  const bool have_tac = dtac_cot != 0 && S.nmark > 0;
+  bool have_tac = dtac_cot != 0 && S.nmark > 0;
   if (have_var || have_tac) {
     TacAcc acc[TS_MAXCAND];
-    if (have_tac) {
-      Work<double>& WS = *(Work<double>*)workbuf;
-      kinematics<double>(S, qk, qdk, (const double*)0, WS, false);
-      tactile_vjp(tl, S, WS, dtac_cot, acc);
-    }
     Work<Dual>& WD = *(Work<Dual>*)workbuf;
     for (int c = 0; c < TS_NC(L); ++c) {
       const int k = tl.lane + c * L;
       Dual xq[TS_MAXN], xqd[TS_MAXN];
       for (int i = 0; i < n; ++i) { xq[i] = mkdual(qk[i], (i == k) ? 1.0 : 0.0); xqd[i] = mkdual(qdk[i], 0.0); }
       kinematics<Dual>(S, xq, xqd, (const Dual*)0, WD, false);
+      // the values of the Dual work space are the kinematics of the state: the marker pass reads them
+      if (c == 0 && have_tac) have_tac = tactile_vjp(tl, S, WD, dtac_cot, acc);
       double yk = 0.0, ck = 0.0;
       if (have_var) {
         for (int e = 0; e < S.nee; ++e) {
@@ -843,17 +1066,20 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
       }
       if (have_tac) {
         for (int si = 0; si < S.nsens; ++si) {
-          const int* sr = S.ib + S.o_sensor + si * TS_SI_STRIDE;
+          const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
           const int b1 = sr[0], nc = sr[3];
+          Dual R1[9], p1[3], ph1[6];
+          body_frame(S, WD, b1, R1, p1, ph1);
           double J1[6];
-          jac_col(WD.R0i[b1], WD.p0i[b1], J1);
+          jac_col(R1, p1, J1);
           for (int ci = 0; ci < nc; ++ci) {
             const double* A = acc[ci].v;
             double nz = 0.0;
             for (int i = 0; i < 24; ++i) nz += fabs(A[i]);
             if (nz == 0.0) continue;
             const int b2 = sr[4 + ci];
-            const Dual* R1 = WD.R0i[b1]; const Dual* R2 = WD.R0i[b2];
+            Dual R2[9], p2[3], ph2[6];
+            body_frame(S, WD, b2, R2, p2, ph2);
             // R21 = R2^T R1, r = R2^T (p1 - p2) on Duals; take the tangents
             for (int i = 0; i < 3; ++i)
               for (int j = 0; j < 3; ++j) {
@@ -861,13 +1087,13 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
                 yk += A[3 * i + j] * r.d;
               }
             Dual dp[3], rr[3];
-            for (int i = 0; i < 3; ++i) dp[i] = WD.p0i[b1][i] - WD.p0i[b2][i];
+            for (int i = 0; i < 3; ++i) dp[i] = p1[i] - p2[i];
             mtv3(R2, dp, rr);
             double J2[6];
-            jac_col(WD.R0i[b2], WD.p0i[b2], J2);
+            jac_col(R2, p2, J2);
             for (int i = 0; i < 3; ++i) yk += A[9 + i] * rr[i].d;
             for (int i = 0; i < 6; ++i) {
-              yk += A[12 + i] * WD.phi[b1][i].d + A[18 + i] * WD.phi[b2][i].d;
+              yk += A[12 + i] * ph1[i].d + A[18 + i] * ph2[i].d;
               ck += A[12 + i] * J1[i] + A[18 + i] * J2[i];
             }
           }
@@ -894,9 +1120,9 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
   // controls: dg/du = -h^2 dfr/du, FORCE motors (DH/Actuator/ActuatorMotor.cpp:48-55)
   if (du_out && tl.lane == 0) {
     for (int ai = 0; ai < S.nact; ++ai) {
-      const int* r = S.ib + S.o_act + ai * TS_AI_STRIDE;
-      const double* cdat = S.db + S.d_act + ai * TS_AD_STRIDE;
-      const int qo = S.ib[S.o_joint + r[0] * TS_JI_STRIDE + 2];
+      const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
+      const double* cdat = S.db + S.d_act + ai * KA_DSTRIDE;
+      const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
       for (int i = 0; i < r[3]; ++i) {
         const double uu = uk[r[2] + i];
         double gain = (uu >= -1.0 && uu <= 1.0) ? (cdat[3 + i] - cdat[i]) / 2.0 : 0.0;
@@ -919,42 +1145,44 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
     pendB[c] = -g1z / S.h;
     if (out_g0z) out_g0z[c] = g0z + oldB + cterm[c];   // what the step adds to dL/dq0 (to be subtracted)
     if (out_g1z) out_g1z[c] = g1z;
-    if (out_c) out_c[c] = cterm[c];
   }
 }
 
 // ------------------------------------------------------------------ contact index sets (diagnostic outputs)
 // word 0: ground force 0, points 0..31; words 1..3: general-primitive force 0, points 0..95.
-HDN inline void contact_sets(const SceneView& S, const Work<double>& W, unsigned* m4) {
+template <class T>
+HDN void contact_sets(const SceneView& S, const Work<T>& W, unsigned* m4) {
   m4[0] = m4[1] = m4[2] = m4[3] = 0u;
+  double R1[9], p1[3], R2[9], p2[3], ph[6];
   if (S.nground > 0) {
     const int* r = S.ib + S.o_ground;
     const int b = r[0], po = r[1], pc = r[2];
+    body_frame_v(S, W, b, R1, p1, ph);
     for (int k = 0; k < pc && k < 32; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
       double xw[3];
-      mv3(W.R0i[b], xi, xw);
-      double d = (xw[0] + W.p0i[b][0] - S.gx[0]) * S.gn[0] + (xw[1] + W.p0i[b][1] - S.gx[1]) * S.gn[1] +
-                 (xw[2] + W.p0i[b][2] - S.gx[2]) * S.gn[2];
+      mv3(R1, xi, xw);
+      double d = (xw[0] + p1[0] - S.gx[0]) * S.gn[0] + (xw[1] + p1[1] - S.gx[1]) * S.gn[1] +
+                 (xw[2] + p1[2] - S.gx[2]) * S.gn[2];
       if (d <= 0.0) m4[0] |= (1u << k);
     }
   }
   if (S.ngp > 0) {
     const int* r = S.ib + S.o_gp;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
-    const double* hs = S.db + S.d_joint + b2 * TS_JD_STRIDE + TS_JD_HALF;
+    const double* hs = S.db + S.d_body + b2 * KB_DSTRIDE + KB_HALF;
+    body_frame_v(S, W, b1, R1, p1, ph);
+    body_frame_v(S, W, b2, R2, p2, ph);
     for (int k = 0; k < pc && k < 96; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
       double xw[3], y[3], x[3];
-      mv3(W.R0i[b1], xi, xw);
-      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + W.p0i[b1][i]) - W.p0i[b2][i];
-      mtv3(W.R0i[b2], y, x);
+      mv3(R1, xi, xw);
+      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
+      mtv3(R2, y, x);
       if (cuboid_distance(x, hs) < 0.0) m4[1 + (k >> 5)] |= (1u << (k & 31));
     }
   }
 }
-
-#define TS_MAXU 8
 
 struct FwdArgs {
   int B, T;
@@ -969,16 +1197,27 @@ struct FwdArgs {
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
 };
 
-// readouts of the state (q,qd): variables, tactile field, contact sets
+// readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
+template <class Tile, class T>
+HDN void readout_from_work(const Tile& tl, const SceneView& S, const Work<T>& W, double* var_o, double* tac_o,
+                           int* mb_o, unsigned* cm_o) {
+  if (var_o && tl.lane == 0)
+    for (int e = 0; e < S.nee; ++e) {
+      T v[3];
+      variable_of<T>(S, W, e, v);
+      for (int i = 0; i < 3; ++i) var_o[3 * e + i] = val(v[i]);
+    }
+  if (tac_o) tactile_values(tl, S, W, tac_o, mb_o);
+  if (cm_o && tl.lane == 0) contact_sets(S, W, cm_o);
+}
+
+// readouts of a given state (q,qd)
 template <class Tile>
 HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const double* qd, double* var_o,
                      double* tac_o, int* mb_o, unsigned* cm_o, void* wb) {
   Work<double>& WS = *(Work<double>*)wb;
   kinematics<double>(S, q, qd, (const double*)0, WS, false);
-  if (var_o && tl.lane == 0)
-    for (int e = 0; e < S.nee; ++e) variable_of<double>(S, WS, e, var_o + 3 * e);
-  if (tac_o) tactile_values(tl, S, WS, tac_o, mb_o);
-  if (cm_o && tl.lane == 0) contact_sets(S, WS, cm_o);
+  readout_from_work(tl, S, WS, var_o, tac_o, mb_o, cm_o);
 }
 
 template <class Tile>
@@ -999,10 +1238,12 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
     const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
     if (vr >= 0 || tr >= 0 || a.cmask) {
-      env_readout(tl, S, q, qd, vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
-                  tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
-                  (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
-                  a.cmask ? a.cmask + es * 4 : (unsigned*)0, wb);
+      // the work space already holds the kinematics of the new state (last residual evaluation)
+      readout_from_work(tl, S, *(const Work<Dual>*)wb,
+                        vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
+                        tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
+                        (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
+                        a.cmask ? a.cmask + es * 4 : (unsigned*)0);
     }
   }
   if (tl.lane == 0)
@@ -1045,7 +1286,7 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
                   r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
                   r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
                   r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,
-                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, (double*)0, wb);
+                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, wb);
   }
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;

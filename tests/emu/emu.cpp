@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include "../../tactilesimulation_b200/csrc/scene_lower.h"
 #include "../../tactilesimulation_b200/csrc/sim_core.cuh"
 
 extern "C" {
@@ -14,8 +15,10 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
                 const double* u, int64_t u_stride, double* q_traj, double* qd_traj, double* var_out,
                 const int32_t* var_row, double* tac_out, const int32_t* tac_row, double* tape, int32_t* status,
                 uint32_t* cmask, int32_t* marker_body) {
+  KernelTables kt;
+  if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return 1;
   SceneView S;
-  scene_view_init(S, ibuf, dbuf);
+  scene_view_init(S, kt.ib.data(), kt.db.data());
   FwdArgs a;
   a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
@@ -30,8 +33,10 @@ int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, 
                  const double* qd_traj, const double* u, int64_t u_stride, const double* tape, const double* df_dq,
                  const int32_t* dq_row, const double* df_dvar, const int32_t* dvar_row, const double* df_dtac,
                  const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0) {
+  KernelTables kt;
+  if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return 1;
   SceneView S;
-  scene_view_init(S, ibuf, dbuf);
+  scene_view_init(S, kt.ib.data(), kt.db.data());
   BwdArgs a;
   a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_stride; a.tape = tape;
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
@@ -44,8 +49,10 @@ int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, 
 
 int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double* q, const double* qd, double* var_out,
                 double* tac_out, int32_t* marker_body, uint32_t* cmask) {
+  KernelTables kt;
+  if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return 1;
   SceneView S;
-  scene_view_init(S, ibuf, dbuf);
+  scene_view_init(S, kt.ib.data(), kt.db.data());
   std::vector<unsigned char> wb(sizeof(Work<Dual>));
   HostTile tl;
   for (int env = 0; env < B; ++env)

@@ -17,7 +17,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [SRC] + [os.path.join(CORE, f) for f in ("sim_core.cuh", "dual.cuh", "scene_layout.h")]
+        deps = [SRC] + [os.path.join(CORE, f) for f in ("sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h")]
         if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", "-o", LIB, SRC])
         _lib = ctypes.CDLL(LIB)

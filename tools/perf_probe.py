@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--case", default="pusher32x13_episodic_s0")
     ap.add_argument("--lanes", type=int, nargs="+", default=[8, 16, 32])
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
     for lanes in a.lanes:
@@ -47,7 +48,8 @@ def main():
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             torch.cuda.synchronize()
             e[0].record()
-            out = sim.forward(q, qd, u, a.T, grad=False, want_status=True)
+            if not a.grad_only:
+                out = sim.forward(q, qd, u, a.T, grad=False, want_status=True)
             e[1].record()
             q, qd = q0.clone(), qd0.clone()
             out = sim.forward(q, qd, u, a.T, grad=True, want_status=True)
