@@ -7,6 +7,9 @@
 //     ancestor joint through a precomposed constant transform, and every moving joint carries the
 //     precomposed constant offset from its nearest moving ancestor (the reference walks these
 //     identity-motion joints every evaluation, DH/Joint/Joint.cpp:119-165);
+//   * the bodies rigidly attached to one moving joint are merged into ONE composite rigid body
+//     (6x6 spatial inertia summed in the joint frame), so the dynamics sweep touches each moving
+//     joint once instead of each reference body once;
 //   * bounding radii of contact point sets / marker grids / boxes for exact-safe culling;
 //   * ancestor bitmasks per moving joint (mass-matrix columns).
 #pragma once
@@ -26,10 +29,12 @@ enum {
 };
 enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 };
 
-// moving joint: int {type, parent (moving index, -1 = world), qoff, ndof, ancestor-or-self bitmask}
+// moving joint: int {type, parent (moving index, -1 = world), qoff, ndof, ancestor-or-self bitmask, has_mass}
 #define KJ_ISTRIDE 8
-// dbl {Ra(9) pa(3): constant offset from the parent moving frame | axis0(3) axis1(3) | damping lo hi limk}
-#define KJ_DSTRIDE 24
+// dbl {Ra(9) pa(3): constant offset from the parent moving frame | axis0(3) axis1(3) | damping lo hi limk |
+//      composite spatial inertia of every body rigidly attached to this joint, in the joint frame:
+//      Ibar(9) rotational inertia about the joint origin, mc(3) = sum m_i c_i, m = sum m_i}
+#define KJ_DSTRIDE 40
 #define KJ_RA 0
 #define KJ_PA 9
 #define KJ_AX0 12
@@ -38,6 +43,9 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 #define KJ_LIMLO 19
 #define KJ_LIMHI 20
 #define KJ_LIMK 21
+#define KJ_IBAR 22
+#define KJ_MC 31
+#define KJ_MASS 34
 // body: int {moving joint (-1 = static), shape, dynamic (has mass and a moving joint), unused}
 #define KB_ISTRIDE 4
 // dbl {Rmi(9) pmi(3): body frame in its moving joint frame | inertia(6) | half-size(3) | bounding radius}

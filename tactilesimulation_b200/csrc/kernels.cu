@@ -42,6 +42,15 @@ struct DevTile {
 #endif
     return v;
   }
+  // predicate of every lane of the tile, bit i = lane i
+  HD unsigned ballot(bool p) const {
+#ifdef __CUDA_ARCH__
+    const unsigned b = __ballot_sync(mask, p);
+    return (LPE_ == 32) ? b : ((b >> ((threadIdx.x & 31) - lane)) & ((1u << LPE_) - 1u));
+#else
+    return p ? 1u : 0u;
+#endif
+  }
 };
 
 #define TS_BLOCK 128

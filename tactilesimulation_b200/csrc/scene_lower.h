@@ -87,6 +87,37 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   oi[KI_NGP] = ngp; oi[KI_NACT] = nact; oi[KI_NSENS] = nsens; oi[KI_MAX_ITER] = ib[TS_I_MAX_ITER];
   oi[KI_MAX_LS] = ib[TS_I_MAX_LS]; oi[KI_NBODY] = nj; oi[KI_NPOINTS] = npoints;
 
+  // ---- composite spatial inertia per moving joint: sum over the attached bodies of X^T diag(I_i) X,
+  //      X = twist transform joint frame -> body frame (DH/Robot.cpp:652-658 gathers diag(I_i) per body)
+  std::vector<std::vector<double> > comp(nmj, std::vector<double>(36, 0.0));
+  std::vector<int> has_mass(nmj, 0);
+  for (int j = 0; j < nj; ++j) {
+    const int m = mv_of(j);
+    if (m < 0) continue;
+    const double* s = JD + j * TS_JD_STRIDE;
+    double mass = 0.0;
+    for (int i = 0; i < 6; ++i) mass += fabs(s[TS_JD_INERTIA + i]);
+    if (!(mass > 0.0)) continue;
+    has_mass[m] = 1;
+    const Xf e = xf_mul(erel[j], xf_load(s + TS_JD_RJI, s + TS_JD_PJI));   // body frame in the joint frame
+    // X = [[R^T, 0], [-R^T [p]x, R^T]]
+    double X[6][6] = {{0}};
+    const double px[9] = {0, -e.p[2], e.p[1], e.p[2], 0, -e.p[0], -e.p[1], e.p[0], 0};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        X[a][b] = e.R[3 * b + a];
+        X[3 + a][3 + b] = e.R[3 * b + a];
+        double t = 0.0;
+        for (int c = 0; c < 3; ++c) t += e.R[3 * c + a] * px[3 * c + b];
+        X[3 + a][b] = -t;
+      }
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        double t = 0.0;
+        for (int c = 0; c < 6; ++c) t += X[c][a] * s[TS_JD_INERTIA + c] * X[c][b];
+        comp[m][6 * a + b] += t;
+      }
+  }
   // ---- moving joints
   oi[KI_O_JOINT] = (int)oi.size(); oi[KI_D_JOINT] = (int)od.size();
   std::vector<int> anc(nmj, 0);
@@ -96,7 +127,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int par = J[j * TS_JI_STRIDE + 1];
     const int pm = mv_of(par);
     anc[m] = (1 << m) | (pm >= 0 ? anc[pm] : 0);
-    int rec[KJ_ISTRIDE] = {J[j * TS_JI_STRIDE], pm, J[j * TS_JI_STRIDE + 2], J[j * TS_JI_STRIDE + 3], anc[m], 0, 0, 0};
+    int rec[KJ_ISTRIDE] = {J[j * TS_JI_STRIDE], pm, J[j * TS_JI_STRIDE + 2], J[j * TS_JI_STRIDE + 3], anc[m], has_mass[m], 0, 0};
     oi.insert(oi.end(), rec, rec + KJ_ISTRIDE);
     double d[KJ_DSTRIDE] = {0};
     for (int i = 0; i < 9; ++i) d[KJ_RA + i] = ea[j].R[i];
@@ -104,6 +135,13 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const double* s = JD + j * TS_JD_STRIDE;
     for (int i = 0; i < 3; ++i) { d[KJ_AX0 + i] = s[TS_JD_AX0 + i]; d[KJ_AX1 + i] = s[TS_JD_AX1 + i]; }
     d[KJ_DAMP] = s[TS_JD_DAMP]; d[KJ_LIMLO] = s[TS_JD_LIMLO]; d[KJ_LIMHI] = s[TS_JD_LIMHI]; d[KJ_LIMK] = s[TS_JD_LIMK];
+    // 6x6 = [[Ibar, [mc]x], [[mc]x^T, m 1]]
+    const std::vector<double>& C = comp[m];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) d[KJ_IBAR + 3 * a + b] = 0.5 * (C[6 * a + b] + C[6 * b + a]);
+    d[KJ_MASS] = (C[6 * 3 + 3] + C[6 * 4 + 4] + C[6 * 5 + 5]) / 3.0;
+    d[KJ_MC + 0] = 0.5 * (C[6 * 2 + 4] - C[6 * 1 + 5]);   // [mc]x = [[0,-z,y],[z,0,-x],[-y,x,0]] in the upper-right block
+    d[KJ_MC + 1] = 0.5 * (C[6 * 0 + 5] - C[6 * 2 + 3]);
+    d[KJ_MC + 2] = 0.5 * (C[6 * 1 + 3] - C[6 * 0 + 4]);
     od.insert(od.end(), d, d + KJ_DSTRIDE);
   }
   // ---- bodies (same order and ids as the reference: body j hangs off joint j)

@@ -260,29 +260,45 @@ HD void push_wrench(Work<T>& W, int j, const T* R, const T* p, const T* wr, doub
   for (int i = 0; i < 3; ++i) { A[i] = A[i] + scale * (t[i] + pf[i]); A[3 + i] = A[3 + i] + scale * f[i]; }
 }
 
-// a_i = I chi_i - h^2 (coriolis + gravity) for every dynamic body   (DH/Body/Body.cpp:234-247)
+// momentum-like product of the composite spatial inertia of joint j with a joint-frame twist:
+//   h_ang = Ibar w + mc x v,  h_lin = m v + w x mc
 template <class T>
-HDN void body_dynamics(const SceneView& S, Work<T>& W) {
+HD void inertia_mul(const double* jd, const T* tw, T* hm) {
+  const double* Ib = jd + KJ_IBAR;
+  const double* mc = jd + KJ_MC;
+  const double m = jd[KJ_MASS];
+  T a[3], b[3];
+  mv3(Ib, tw, hm);
+  cross3(mc, tw + 3, a);
+  cross3(tw, mc, b);
+  for (int i = 0; i < 3; ++i) { hm[i] = hm[i] + a[i]; hm[3 + i] = m * tw[3 + i] + b[i]; }
+}
+
+// a_j = I chi_j - h^2 (coriolis + gravity) for the composite body of every moving joint, in the joint
+// frame (per reference body: DH/Body/Body.cpp:234-247; summed here by linearity of the spatial inertia)
+template <class T>
+HDN void joint_dynamics(const SceneView& S, Work<T>& W) {
   const double h2 = S.h * S.h;
-  for (int b = 0; b < S.nbody; ++b) {
-    const int* bi = S.ib + S.o_body + b * KB_ISTRIDE;
-    if (!bi[2]) continue;
-    const int j = bi[0];
-    const double* I6 = S.db + S.d_body + b * KB_DSTRIDE + KB_INERTIA;
-    T R[9], p[3], ph[6], ch[6];
-    body_frame(S, W, b, R, p, ph);
-    twist_to_frame(R, p, W.X[j], ch);
-    T Iw[3], mv[3], fc0[3], fc1[3], fc2[3], gb[3], a[6];
-    for (int i = 0; i < 3; ++i) { Iw[i] = I6[i] * ph[i]; mv[i] = I6[3 + i] * ph[3 + i]; }
-    cross3(Iw, ph, fc0);
-    cross3(mv, ph + 3, fc1);
-    cross3(mv, ph, fc2);
-    mtv3(R, S.grav, gb);
+  for (int j = 0; j < S.nj; ++j) {
+    if (!S.ib[S.o_joint + j * KJ_ISTRIDE + 5]) continue;
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
+    T ph[6], ch[6], hp[6], a[6];
+    twist_to_frame(W.R0[j], W.p0[j], W.V[j], ph);
+    twist_to_frame(W.R0[j], W.p0[j], W.X[j], ch);
+    inertia_mul(jd, ph, hp);
+    inertia_mul(jd, ch, a);
+    // coriolis ad(phi)^T h = (h_ang x w + h_lin x v ; h_lin x w), gravity (mc x R^T g ; m R^T g)
+    T c0[3], c1[3], c2[3], gb[3], gm[3];
+    cross3(hp, ph, c0);
+    cross3(hp + 3, ph + 3, c1);
+    cross3(hp + 3, ph, c2);
+    mtv3(W.R0[j], S.grav, gb);
+    cross3(jd + KJ_MC, gb, gm);
     for (int i = 0; i < 3; ++i) {
-      a[i] = I6[i] * ch[i] - h2 * (fc0[i] + fc1[i]);
-      a[3 + i] = I6[3 + i] * ch[3 + i] - h2 * (fc2[i] + I6[3] * gb[i]);
+      a[i] = a[i] - h2 * ((c0[i] + c1[i]) + gm[i]);
+      a[3 + i] = a[3 + i] - h2 * (c2[i] + jd[KJ_MASS] * gb[i]);
     }
-    push_wrench(W, j, R, p, a, 1.0);
+    push_wrench(W, j, W.R0[j], W.p0[j], a, 1.0);
   }
 }
 
@@ -301,6 +317,37 @@ HD double cuboid_distance(const double* x, const double* hs) {
   double d = -99999999.0;
   for (int i = 0; i < 3; ++i) { d = fmax(d, fmax(x[i] - hs[i], -x[i] - hs[i])); }
   return d;
+}
+// distance(x) < 0 of DH/Body/BodyCuboid.cpp:135-144, without forming the distance:
+// max_i(|x_i| - h_i) < 0  <=>  |x_i| < h_i for all i  (a - b < 0 <=> a < b in IEEE arithmetic)
+HD bool cuboid_inside(const double* x, const double* hs) {
+  return !(fabs(x[0]) >= hs[0]) && !(fabs(x[1]) >= hs[1]) && !(fabs(x[2]) >= hs[2]);
+}
+// Cheap conservative classification of a point given in the box frame through the PRECOMPOSED relative
+// transform (x = R21 xi + r differs from the reference's evaluation order by rounding, ~1e-17 m):
+// +1 surely inside, -1 surely outside, 0 too close to a face to tell -> caller runs the exact test.
+#define TS_BAND 1e-12
+HD int cuboid_classify(const double* R21, const double* r, const double* xi, const double* hs) {
+  double x[3];
+  mv3(R21, xi, x);
+  const double m0 = hs[0] - fabs(x[0] + r[0]), m1 = hs[1] - fabs(x[1] + r[1]), m2 = hs[2] - fabs(x[2] + r[2]);
+  if (m0 < -TS_BAND || m1 < -TS_BAND || m2 < -TS_BAND) return -1;
+  if (m0 > TS_BAND && m1 > TS_BAND && m2 > TS_BAND) return 1;
+  return 0;
+}
+// relative transform of frame 1 in frame 2: R21 = R2^T R1, r = R2^T (p1 - p2)
+HD void rel_frame(const double* R1, const double* p1, const double* R2, const double* p2, double* R21, double* r) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R21[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
+  double d[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  mtv3(R2, d, r);
+}
+HD int ts_ffs(unsigned m) {   // index of the lowest set bit (m != 0)
+#ifdef __CUDA_ARCH__
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
 }
 template <class T> HD void vals3(const T* a, double* o) { o[0] = val(a[0]); o[1] = val(a[1]); o[2] = val(a[2]); }
 template <class T> HD void vals9(const T* a, double* o) { for (int i = 0; i < 9; ++i) o[i] = val(a[i]); }
@@ -367,8 +414,9 @@ HDN void ground_contacts(const SceneView& S, Work<T>& W) {
 
 // sampled points of a general body vs a cuboid SDF: DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
 // DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83
-template <class T>
-HDN void gp_contacts(const SceneView& S, Work<T>& W) {
+template <class Tile, class T>
+HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
+  const int L = Tile::LPE;
   const double h2 = S.h * S.h;
   for (int fi = 0; fi < S.ngp; ++fi) {
     const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
@@ -387,83 +435,102 @@ HDN void gp_contacts(const SceneView& S, Work<T>& W) {
       const double dx = p1v[0] - p2v[0], dy = p1v[1] - p2v[1], dz = p1v[2] - p2v[2];
       if (dx * dx + dy * dy + dz * dz > rr * rr) continue;
     }
-    T R1[9], p1[3], ph1[6], R2[9], p2[3], ph2[6];
-    T w1[6], w2[6];
-    bool any = false;
-    for (int k = 0; k < pc; ++k) {
-      const double* xi1 = S.db + S.d_points + 3 * (po + k);
-      double xwv[3], yv[3], xv[3];
-      mv3(R1v, xi1, xwv);
-      for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
-      mtv3(R2v, yv, xv);
-      if (!(cuboid_distance(xv, hs) < 0.0)) continue;
-      if (!any) {
-        any = true;
-        body_frame(S, W, b1, R1, p1, ph1);
-        body_frame(S, W, b2, R2, p2, ph2);
-        for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
-      }
-      T xw[3], y[3], x[3];
-      mv3(R1, xi1, xw);
-      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
-      mtv3(R2, y, x);
-      int ax; double sg;
-      cuboid_face(xv, hs, ax, sg);
-      T d = sg * x[ax] - hs[ax];
-      // velocities: point of body 1 (pad frame), relative velocity in the box frame
-      T v1[3], xwd[3], u[3], t3[3];
-      cross3(ph1, xi1, v1);
-      v1[0] = v1[0] + ph1[3]; v1[1] = v1[1] + ph1[4]; v1[2] = v1[2] + ph1[5];
-      mv3(R1, v1, xwd);
-      mtv3(R2, xwd, u);
-      cross3(ph2, x, t3);
-      for (int i = 0; i < 3; ++i) u[i] = u[i] - t3[i] - ph2[3 + i];          // u = R2^T xw_dot - w2 x x - v2
-      T ddot = sg * u[ax];
-      // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
-      T tb[3];
-      double e[3] = {0.0, 0.0, 0.0};
-      e[ax] = sg;
-      cross3(ph2, e, t3);
-      for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
-      tb[ax] = tb[ax] - sg * (sg * tb[ax]);
-      T s = kn * d - damp * ddot * d;
-      // n1 = R1^T R2 e ; normal wrench on body 1 = -s (xi1 x n1; n1)
-      T nw[3], n1[3], m1[3];
-      for (int i = 0; i < 3; ++i) nw[i] = sg * R2[3 * i + ax];
-      mtv3(R1, nw, n1);
-      cross3(xi1, n1, m1);
-      T Fb[3];
-      for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
-      if (mu > TS_EPS) {
-        // the reference uses the norm of the 6-vector wrench on body 1 (:208)
-        double n6 = 0.0;
-        for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
-        double fcn = fabs(val(s)) * sqrt(n6);
-        double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
-        if (mu * fcn >= kt * tn - TS_EPS) {
-          for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
-        } else {
-          T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
-          T fcT = dabs(s) * dsqrt(n6T);
-          T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
-          T sc = mu * fcT / tnT;
-          for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+    // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
+    double R21[9], r21[3];
+    rel_frame(R1v, p1v, R2v, p2v, R21, r21);
+    unsigned act[3] = {0u, 0u, 0u};
+    for (int base = 0; base < pc; base += L) {
+      const int k = base + tl.lane;
+      bool in = false;
+      if (k < pc) {
+        const double* xi1 = S.db + S.d_points + 3 * (po + k);
+        const int cls = cuboid_classify(R21, r21, xi1, hs);
+        if (cls > 0) in = true;
+        else if (cls == 0) {                 // reference evaluation order (CollisionDetection.cpp:73-79)
+          double xwv[3], yv[3], xv[3];
+          mv3(R1v, xi1, xwv);
+          for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
+          mtv3(R2v, yv, xv);
+          in = cuboid_inside(xv, hs);
         }
       }
-      // wrenches: body 2 gets -Gamma(xi2)^T Fb with xi2 = x - d e ; body 1 gets Gamma(xi1)^T R1^T R2 Fb
-      T xi2[3], tq[3], Fw[3], F1[3];
-      for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
-      cross3(xi2, Fb, tq);
-      for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
-      mv3(R2, Fb, Fw);
-      mtv3(R1, Fw, F1);
-      cross3(xi1, F1, tq);
-      for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + F1[i]; }
+      const unsigned bits = tl.ballot(in);
+      act[base >> 5] |= bits << (base & 31);
     }
-    if (any) {
-      push_wrench(W, j1, R1, p1, w1, -h2);
-      push_wrench(W, j2, R2, p2, w2, -h2);
+    if (!(act[0] | act[1] | act[2])) continue;
+    T R1[9], p1[3], ph1[6], R2[9], p2[3], ph2[6];
+    T w1[6], w2[6];
+    body_frame(S, W, b1, R1, p1, ph1);
+    body_frame(S, W, b2, R2, p2, ph2);
+    for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+    for (int wd = 0; wd < 3; ++wd) {
+      unsigned m = act[wd];
+      while (m) {
+        const int k = 32 * wd + ts_ffs(m);
+        m &= m - 1;
+        const double* xi1 = S.db + S.d_points + 3 * (po + k);
+        T xw[3], y[3], x[3];
+        mv3(R1, xi1, xw);
+        for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
+        mtv3(R2, y, x);
+        double xv[3];
+        vals3(x, xv);
+        int ax; double sg;
+        cuboid_face(xv, hs, ax, sg);
+        T d = sg * x[ax] - hs[ax];
+        // velocities: point of body 1 (pad frame), relative velocity in the box frame
+        T v1[3], xwd[3], u[3], t3[3];
+        cross3(ph1, xi1, v1);
+        v1[0] = v1[0] + ph1[3]; v1[1] = v1[1] + ph1[4]; v1[2] = v1[2] + ph1[5];
+        mv3(R1, v1, xwd);
+        mtv3(R2, xwd, u);
+        cross3(ph2, x, t3);
+        for (int i = 0; i < 3; ++i) u[i] = u[i] - t3[i] - ph2[3 + i];          // u = R2^T xw_dot - w2 x x - v2
+        T ddot = sg * u[ax];
+        // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
+        T tb[3];
+        double e[3] = {0.0, 0.0, 0.0};
+        e[ax] = sg;
+        cross3(ph2, e, t3);
+        for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
+        tb[ax] = tb[ax] - sg * (sg * tb[ax]);
+        T s = kn * d - damp * ddot * d;
+        // n1 = R1^T R2 e ; normal wrench on body 1 = -s (xi1 x n1; n1)
+        T nw[3], n1[3], m1[3];
+        for (int i = 0; i < 3; ++i) nw[i] = sg * R2[3 * i + ax];
+        mtv3(R1, nw, n1);
+        cross3(xi1, n1, m1);
+        T Fb[3];
+        for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
+        if (mu > TS_EPS) {
+          // the reference uses the norm of the 6-vector wrench on body 1 (:208)
+          double n6 = 0.0;
+          for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
+          double fcn = fabs(val(s)) * sqrt(n6);
+          double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
+          if (mu * fcn >= kt * tn - TS_EPS) {
+            for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
+          } else {
+            T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+            T fcT = dabs(s) * dsqrt(n6T);
+            T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
+            T sc = mu * fcT / tnT;
+            for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+          }
+        }
+        // wrenches: body 2 gets -Gamma(xi2)^T Fb with xi2 = x - d e ; body 1 gets Gamma(xi1)^T R1^T R2 Fb
+        T xi2[3], tq[3], Fw[3], F1[3];
+        for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
+        cross3(xi2, Fb, tq);
+        for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
+        mv3(R2, Fb, Fw);
+        mtv3(R1, Fw, F1);
+        cross3(xi1, F1, tq);
+        for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + F1[i]; }
+      }
     }
+    push_wrench(W, j1, R1, p1, w1, -h2);
+    push_wrench(W, j2, R2, p2, w2, -h2);
   }
 }
 
@@ -515,17 +582,18 @@ HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const d
 }
 
 // residual of the BDF1 step for (q1; q0, qd0)
-template <class T>
-HDN void eval_g(const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W, T* g) {
+template <class Tile, class T>
+HDN void eval_g(const Tile& tl, const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W,
+                T* g) {
   T qd1[TS_MAXN], dl[TS_MAXN];
   for (int i = 0; i < S.n; ++i) {
     qd1[i] = (q1[i] - q0[i]) / S.h;
     dl[i] = q1[i] - q0[i] - S.h * qd0[i];
   }
   kinematics<T>(S, q1, qd1, dl, W, true);
-  body_dynamics<T>(S, W);
+  joint_dynamics<T>(S, W);
   ground_contacts<T>(S, W);
-  gp_contacts<T>(S, W);
+  gp_contacts(tl, S, W);
   inward<T>(S, W, q1, qd1, u, g);
 }
 
@@ -537,6 +605,7 @@ struct HostTile {
   HD double bcast(double v, int) const { return v; }
   HD int bcasti(int v, int) const { return v; }
   HD double sum(double v) const { return v; }
+  HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
 };
 
 #define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
@@ -615,10 +684,11 @@ HD double norm_n(const double* v, int n) {
 }
 
 // One Dual evaluation per owned column: returns g (replicated) and the owned columns of
-// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  Deliberately NOT inlined: the kernels call it from
-// several places and one copy of the residual code keeps the instruction working set small.
+// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  step_forward calls it from exactly ONE place, so the
+// residual code exists once per kernel and everything it touches keeps its address space
+// (scene tables: shared memory, work space: local memory).
 template <class Tile>
-TS_NOINLINE HDN void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
+HD void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
                                   const double* qd0, const double* u, int seed, Work<Dual>& W, double* g,
                                   double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
@@ -630,7 +700,7 @@ TS_NOINLINE HDN void eval_columns(const Tile& tl, const SceneView& S, const doub
       xq0[i] = mkdual(q0[i], (seed == 1 && i == k) ? 1.0 : 0.0);
       xqd0[i] = mkdual(qd0[i], (seed == 2 && i == k) ? 1.0 : 0.0);
     }
-    eval_g<Dual>(S, xq, xq0, xqd0, u, W, gD);
+    eval_g(tl, S, xq, xq0, xqd0, u, W, gD);
     for (int i = 0; i < TS_MAXN; ++i) {
       if (i < S.n) { g[i] = gD[i].v; col[c][i] = (k < S.n) ? gD[i].d : 0.0; }
       else { g[i] = 0.0; col[c][i] = 0.0; }
@@ -666,16 +736,15 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
   if (jk < 0) return;
   double Wm[TS_MAXJ][6];
   for (int j = 0; j < TS_MAXJ; ++j) for (int i = 0; i < 6; ++i) Wm[j][i] = 0.0;
-  for (int b = 0; b < S.nbody; ++b) {
-    const int* bi = S.ib + S.o_body + b * KB_ISTRIDE;
-    if (!bi[2]) continue;
-    const int j = bi[0];
-    if (!((S.ib[S.o_joint + j * KJ_ISTRIDE + 4] >> jk) & 1)) continue;   // body not in the subtree of jk
-    const double* I6 = S.db + S.d_body + b * KB_DSTRIDE + KB_INERTIA;
-    double R[9], p[3], ph[6], ps[6], a[6];
-    body_frame_v(S, W, b, R, p, ph);
+  for (int j = 0; j < S.nj; ++j) {
+    const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
+    if (!ji[5] || !((ji[4] >> jk) & 1)) continue;      // massless, or not in the subtree of jk
+    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
+    double R[9], p[3], ps[6], a[6];
+    for (int i = 0; i < 9; ++i) R[i] = val(W.R0[j][i]);
+    for (int i = 0; i < 3; ++i) p[i] = val(W.p0[j][i]);
     twist_to_frame(R, p, Sk, ps);
-    for (int i = 0; i < 6; ++i) a[i] = I6[i] * ps[i];
+    inertia_mul(jd, ps, a);
     double f[3], t[3], pf[3];
     mv3(R, a + 3, f);
     mv3(R, a, t);
@@ -718,68 +787,82 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
   const int L = Tile::LPE;
   const int n = S.n;
   Work<Dual>& WD = *(Work<Dual>*)workbuf;
-  double x[TS_MAXN], g[TS_MAXN], gn_[TS_MAXN], dx[TS_MAXN], xn[TS_MAXN];
-  double col[TS_NC(L)][TS_MAXN], coln[TS_NC(L)][TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; gn_[i] = 0.0; g[i] = 0.0; }
+  double x[TS_MAXN], xn[TS_MAXN], xe[TS_MAXN], dx[TS_MAXN], ge[TS_MAXN];
+  double cole[TS_NC(L)][TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; ge[i] = 0.0; }
   for (int i = 0; i < n; ++i) x[i] = q[i] + S.h * qd[i];
-  int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
-  int fail_strike = 0, iters = 0, ls = 0;
+  const int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
+  // phase 0: (g, H) at x, then iterate | 1: line-search trial at xn | 2: (H) at the final x | 3: G0 at the final x
+  int phase = 0, fail_strike = 0, iters = 0, ls = 0, trial = 0;
+  double alpha = 1.0, gnorm = 0.0;
   bool converged = false;
-  bool fresh = false;        // (g, col) are the residual and Jacobian columns at the current x
-  bool work_at_x = false;    // the work space holds the kinematics of the current x
-  for (int it = 0; it < max_newton; ++it) {
-    ++iters;
-    if (!fresh) eval_columns(tl, S, x, q, qd, u, 0, WD, g, col);
-    for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -g[i] : 0.0;
-    lu_solve(tl, col, dx, n);
-    fresh = false;
-    const double gnorm = norm_n(g, n);
-    double alpha = 1.0;
-    bool success = false;
-    for (int trial = 0; trial < S.max_ls; ++trial, alpha *= 0.5) {
-      ++ls;
-      for (int i = 0; i < n; ++i) xn[i] = x[i] + alpha * dx[i];
-      eval_columns(tl, S, xn, q, qd, u, 0, WD, gn_, coln);
-      if (norm_n(gn_, n) < gnorm) { success = true; break; }
-    }
-    if (success) fail_strike = 0;
-    else { ++fail_strike; if (fail_strike >= 10) break; }
-    for (int i = 0; i < n; ++i) x[i] = x[i] + alpha * dx[i];
-    if (success) {
-      // the accepted trial is the next iterate: reuse its residual and Jacobian columns
-      for (int i = 0; i < TS_MAXN; ++i) g[i] = gn_[i];
-      for (int c = 0; c < TS_NC(L); ++c) for (int i = 0; i < TS_MAXN; ++i) col[c][i] = coln[c][i];
-      fresh = true;
-    }
-    work_at_x = success;
-    if (norm_n(gn_, n) < S.tol) { converged = true; break; }
-  }
-  int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
-  if (tape) {
-    // adjoint tape at the final state: H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0 = -h M
-    if (!fresh) { eval_columns(tl, S, x, q, qd, u, 0, WD, g, col); work_at_x = true; }
-    for (int c = 0; c < TS_NC(L); ++c) {
-      const int k = tl.lane + c * L;
-      if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = col[c][i];
-    }
-    eval_columns(tl, S, x, q, qd, u, 1, WD, g, col);
-    for (int c = 0; c < TS_NC(L); ++c) {
-      const int k = tl.lane + c * L;
-      if (k < n) {
-        double Mc[TS_MAXN];
-        mass_column(S, WD, k, Mc);
-        for (int i = 0; i < n; ++i) {
-          tape[n * n + i * n + k] = col[c][i];
-          tape[2 * n * n + i * n + k] = -S.h * Mc[i];
+  for (;;) {
+    for (int i = 0; i < TS_MAXN; ++i) xe[i] = (phase == 1) ? xn[i] : x[i];
+    eval_columns(tl, S, xe, q, qd, u, phase == 3 ? 1 : 0, WD, ge, cole);
+    if (phase == 3) {
+      // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        if (k < n) {
+          double Mc[TS_MAXN];
+          mass_column(S, WD, k, Mc);
+          for (int i = 0; i < n; ++i) {
+            tape[n * n + i * n + k] = cole[c][i];
+            tape[2 * n * n + i * n + k] = -S.h * Mc[i];
+          }
         }
       }
+      break;
     }
-  } else if (!work_at_x) {
-    // rare: the last line search failed, so the work space is not at the final state
-    Dual xq[TS_MAXN], xqd[TS_MAXN];
-    for (int i = 0; i < n; ++i) { xq[i] = mkdual(x[i], 0.0); xqd[i] = mkdual((x[i] - q[i]) / S.h, 0.0); }
-    kinematics<Dual>(S, xq, xqd, (const Dual*)0, WD, false);
+    bool finished = false, fresh = (phase == 2);   // fresh: (ge, cole) belong to the final x
+    if (phase == 1) {
+      ++ls;
+      const double gnn = norm_n(ge, n);
+      if (gnn < gnorm) {                           // trial accepted: it is the next iterate
+        for (int i = 0; i < n; ++i) x[i] = xn[i];
+        fail_strike = 0;
+        fresh = true;
+        if (gnn < S.tol) { converged = true; finished = true; }
+      } else {
+        ++trial;
+        alpha *= 0.5;
+        if (trial < S.max_ls) {
+          for (int i = 0; i < n; ++i) xn[i] = x[i] + alpha * dx[i];
+          continue;
+        }
+        // line search exhausted (DH/Simulation.cpp:1201-1214): strike, else step with the last alpha
+        ++fail_strike;
+        if (fail_strike >= 10) finished = true;
+        else {
+          for (int i = 0; i < n; ++i) x[i] = x[i] + alpha * dx[i];
+          if (gnn < S.tol) { converged = true; finished = true; }
+          else if (iters >= max_newton) finished = true;
+          else { phase = 0; continue; }
+        }
+      }
+      if (!finished && iters >= max_newton) finished = true;
+    }
+    if (finished || phase == 2) {
+      if (!fresh) { phase = 2; continue; }         // (H) and the work space must be at the final x
+      if (!tape) break;
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = cole[c][i];
+      }
+      phase = 3;
+      continue;
+    }
+    // Newton iteration from (x, ge, cole): dx = -H^-1 g, then line search from alpha = 1
+    ++iters;
+    gnorm = norm_n(ge, n);
+    for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -ge[i] : 0.0;
+    lu_solve(tl, cole, dx, n);
+    alpha = 1.0;
+    trial = 0;
+    for (int i = 0; i < n; ++i) xn[i] = x[i] + dx[i];
+    phase = 1;
   }
+  int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
   for (int i = 0; i < n; ++i) {
     double q1 = x[i];
     qd[i] = (q1 - q[i]) / S.h;
@@ -803,6 +886,7 @@ HD void variable_of(const SceneView& S, const Work<T>& W, int e, T* out) {
 // world frames of the sensor body (slot 0) and its candidate bodies (slots 1..ncand), values only
 struct Frames {
   double R[1 + TS_MAXCAND][9], p[1 + TS_MAXCAND][3], ph[1 + TS_MAXCAND][6];
+  double R21[TS_MAXCAND][9], r21[TS_MAXCAND][3];   // pad frame in each candidate's frame (fast classification)
   bool near[1 + TS_MAXCAND];   // candidate may touch a marker (bounding-sphere test)
 };
 template <class T>
@@ -816,6 +900,7 @@ HDN void sensor_frames(const SceneView& S, const Work<T>& W, const int* sr, cons
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
     F.near[1 + c] = !(dx * dx + dy * dy + dz * dz > rr * rr);
+    if (F.near[1 + c]) rel_frame(F.R[0], F.p[0], F.R[1 + c], F.p[1 + c], F.R21[c], F.r21[c]);
   }
 }
 
@@ -833,17 +918,17 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
   const int nc = sr[3];
   const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
   const double* R1 = F.R[0]; const double* p1 = F.p[0]; const double* ph1 = F.ph[0];
-  double xw[3];
-  mv3(R1, xi1, xw);
-  for (int i = 0; i < 3; ++i) xw[i] += p1[i];
   H.cand = -1;
   for (int c = 0; c < nc; ++c) {
     if (!F.near[1 + c]) continue;
     const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
-    double y[3], x[3];
-    for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
+    if (cuboid_classify(F.R21[c], F.r21[c], xi1, hs) < 0) continue;   // surely outside
+    // reference evaluation order (TactileSensor.cpp:44-47); also yields the exact box-frame point
+    double xw[3], y[3], x[3];
+    mv3(R1, xi1, xw);
+    for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - F.p[1 + c][i];
     mtv3(F.R[1 + c], y, x);
-    if (cuboid_distance(x, hs) < 0.0) { H.cand = c; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
+    if (cuboid_inside(x, hs)) { H.cand = c; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
   }
   F1[0] = F1[1] = F1[2] = 0.0;
   if (H.cand < 0) return;
