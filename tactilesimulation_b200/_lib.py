@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtactilesim_b200.so")
+# TSIM_B200_LIB: development override to A/B-test kernel build variants (still a CUDA library of this ABI)
+LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_b200.so")
 
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes",
            "tsim_forward", "tsim_readout", "tsim_backward"]

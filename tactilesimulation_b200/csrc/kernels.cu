@@ -12,6 +12,9 @@
 #include <string.h>
 #include <string>
 
+#ifndef TS_NO_SYNC_EVALS
+#define TS_SYNC_EVALS 1
+#endif
 #include "../../include/tactilesim_b200.h"
 #include "scene_lower.h"
 #include "sim_core.cuh"
@@ -42,6 +45,18 @@ struct DevTile {
 #endif
     return v;
   }
+  HD void cta_sync() const {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+  }
+  HD bool cta_any(bool p) const {
+#ifdef __CUDA_ARCH__
+    return __syncthreads_or(p) != 0;
+#else
+    return p;
+#endif
+  }
   // predicate of every lane of the tile, bit i = lane i
   HD unsigned ballot(bool p) const {
 #ifdef __CUDA_ARCH__
@@ -53,7 +68,11 @@ struct DevTile {
   }
 };
 
-#define TS_BLOCK 128
+// 224 threads = 7 warps = 28 environments per block: 4096 environments make 147 blocks, one per SM
+// (148 SMs), and the block is the lockstep domain of TS_SYNC_EVALS (sim_core.cuh, step_forward).
+#ifndef TS_BLOCK
+#define TS_BLOCK 224
+#endif
 
 // stage the scene blob in shared memory (ints first, then doubles, 8-byte aligned)
 __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni, const double* db, int nd,
@@ -81,10 +100,9 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
   SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
-  if (env >= a.B) return;
   DevTile<LPE> tl = make_tile<LPE>();
   __align__(16) unsigned char wb[sizeof(Work<Dual>)];
-  env_forward(tl, S, a, env, wb);
+  env_forward(tl, S, a, env, wb);     // tiles past the batch stay in the block-wide votes
 }
 
 template <int LPE>

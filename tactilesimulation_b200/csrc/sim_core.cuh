@@ -606,6 +606,8 @@ struct HostTile {
   HD int bcasti(int v, int) const { return v; }
   HD double sum(double v) const { return v; }
   HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  HD void cta_sync() const {}
+  HD bool cta_any(bool p) const { return p; }
 };
 
 #define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
@@ -613,68 +615,63 @@ struct HostTile {
 // Partial-pivot LU solve of the n x n system whose columns are dealt round-robin to the lanes
 // (column k lives in lane k % LPE at slot k / LPE); rhs is replicated and overwritten with the
 // solution.  Pivot = first row of maximal |a| (Eigen partialPivLu, DH/Simulation.cpp:1178).
+// The matrix is first all-gathered (one shuffle per entry), then every lane factors its own copy
+// in registers with compile-time indices: no cross-lane traffic inside the elimination, and the
+// solution comes out replicated, which is how the Newton update needs it.
 template <class Tile>
 HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
   const int L = Tile::LPE;
-  for (int j = 0; j < n; ++j) {
-    const int own = j % L, sl = j / L;
+  double A[TS_MAXN][TS_MAXN];           // A[i][c], every index below is a compile-time constant
+#pragma unroll
+  for (int c = 0; c < TS_MAXN; ++c)
+#pragma unroll
+    for (int i = 0; i < TS_MAXN; ++i) {
+      double v = tl.bcast(col[c / L][i], c % L);
+      A[i][c] = (i < n && c < n) ? v : ((i == c) ? 1.0 : 0.0);   // identity padding keeps the 8x8 factorisation regular
+    }
+  double b[TS_MAXN];
+#pragma unroll
+  for (int i = 0; i < TS_MAXN; ++i) b[i] = (i < n) ? rhs[i] : 0.0;
+#pragma unroll
+  for (int j = 0; j < TS_MAXN; ++j) {
     int p = j;
-    if (tl.lane == own) {
-      double best = fabs(col[sl][j]);
-      for (int i = j + 1; i < n; ++i) {
-        double v = fabs(col[sl][i]);
-        if (v > best) { best = v; p = i; }
-      }
+    double best = fabs(A[j][j]);
+#pragma unroll
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const double v = fabs(A[i][j]);
+      if (v > best) { best = v; p = i; }
     }
-    p = tl.bcasti(p, own);
-    if (p != j) {
-      for (int c = 0; c < TS_NC(L); ++c) {
-        double t = 0.0, s = 0.0;
-        for (int i = 0; i < TS_MAXN; ++i) { if (i == j) t = col[c][i]; if (i == p) s = col[c][i]; }
-        for (int i = 0; i < TS_MAXN; ++i) { if (i == j) col[c][i] = s; if (i == p) col[c][i] = t; }
+#pragma unroll
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const bool sw = (p == i);
+#pragma unroll
+      for (int c = j; c < TS_MAXN; ++c) {
+        const double t = A[j][c], s2 = A[i][c];
+        A[j][c] = sw ? s2 : t;
+        A[i][c] = sw ? t : s2;
       }
-      double t = 0.0, s = 0.0;
-      for (int i = 0; i < TS_MAXN; ++i) { if (i == j) t = rhs[i]; if (i == p) s = rhs[i]; }
-      for (int i = 0; i < TS_MAXN; ++i) { if (i == j) rhs[i] = s; if (i == p) rhs[i] = t; }
+      const double t = b[j], s2 = b[i];
+      b[j] = sw ? s2 : t;
+      b[i] = sw ? t : s2;
     }
-    double piv = 0.0, rj = 0.0;
-    for (int i = 0; i < TS_MAXN; ++i) if (i == j) rj = rhs[i];
-    if (tl.lane == own) for (int i = 0; i < TS_MAXN; ++i) if (i == j) piv = col[sl][i];
-    for (int i = 0; i < TS_MAXN; ++i) {
-      if (i <= j || i >= n) continue;
-      double l = 0.0;
-      if (tl.lane == own) l = col[sl][i] / piv;
-      l = tl.bcast(l, own);
-      for (int c = 0; c < TS_NC(L); ++c) {
-        const int k = tl.lane + c * L;
-        if (k > j && k < n) {
-          double cj = 0.0;
-          for (int m = 0; m < TS_MAXN; ++m) if (m == j) cj = col[c][m];
-          col[c][i] -= l * cj;
-        }
-      }
-      rhs[i] -= l * rj;
+    const double piv = A[j][j];
+#pragma unroll
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const double l = A[i][j] / piv;
+#pragma unroll
+      for (int c = j + 1; c < TS_MAXN; ++c) A[i][c] -= l * A[j][c];
+      b[i] -= l * b[j];
     }
   }
-  for (int k = n - 1; k >= 0; --k) {
-    const int own = k % L, sl = k / L;
-    double xk = 0.0;
-    if (tl.lane == own) {
-      double rk = 0.0, ukk = 1.0;
-      for (int i = 0; i < TS_MAXN; ++i) if (i == k) { rk = rhs[i]; ukk = col[sl][i]; }
-      xk = rk / ukk;
-    }
-    xk = tl.bcast(xk, own);
-    for (int i = 0; i < TS_MAXN; ++i) {
-      if (i == k) rhs[i] = xk;
-      if (i < k) {
-        double c = 0.0;
-        if (tl.lane == own) c = col[sl][i] * xk;
-        c = tl.bcast(c, own);
-        rhs[i] -= c;
-      }
-    }
+#pragma unroll
+  for (int k = TS_MAXN - 1; k >= 0; --k) {
+    const double xk = b[k] / A[k][k];
+    b[k] = xk;
+#pragma unroll
+    for (int i = 0; i < k; ++i) b[i] -= A[i][k] * xk;
   }
+#pragma unroll
+  for (int i = 0; i < TS_MAXN; ++i) rhs[i] = b[i];
 }
 
 HD double norm_n(const double* v, int n) {
@@ -783,7 +780,7 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
 // On return the work space holds the kinematics (values) of the new state.
 template <class Tile>
 HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, const double* u,
-                     double* tape, void* workbuf) {
+                     double* tape, void* workbuf, bool active) {
   const int L = Tile::LPE;
   const int n = S.n;
   Work<Dual>& WD = *(Work<Dual>*)workbuf;
@@ -796,7 +793,18 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
   int phase = 0, fail_strike = 0, iters = 0, ls = 0, trial = 0;
   double alpha = 1.0, gnorm = 0.0;
   bool converged = false;
-  for (;;) {
+#ifdef TS_SYNC_EVALS
+  // CTA-wide lockstep: every warp of the block enters each residual evaluation together, so the
+  // instruction stream is fetched once per block instead of once per warp.  Tiles that are done keep
+  // voting until the whole block is done.
+  bool live = active;
+  while (tl.cta_any(live)) {
+    if (!live) continue;
+#define TS_STEP_DONE { live = false; continue; }
+#else
+  if (active) for (;;) {
+#define TS_STEP_DONE break
+#endif
     for (int i = 0; i < TS_MAXN; ++i) xe[i] = (phase == 1) ? xn[i] : x[i];
     eval_columns(tl, S, xe, q, qd, u, phase == 3 ? 1 : 0, WD, ge, cole);
     if (phase == 3) {
@@ -812,7 +820,7 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
           }
         }
       }
-      break;
+      TS_STEP_DONE;
     }
     bool finished = false, fresh = (phase == 2);   // fresh: (ge, cole) belong to the final x
     if (phase == 1) {
@@ -844,7 +852,7 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
     }
     if (finished || phase == 2) {
       if (!fresh) { phase = 2; continue; }         // (H) and the work space must be at the final x
-      if (!tape) break;
+      if (!tape) TS_STEP_DONE;
       for (int c = 0; c < TS_NC(L); ++c) {
         const int k = tl.lane + c * L;
         if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = cole[c][i];
@@ -862,6 +870,7 @@ HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, 
     for (int i = 0; i < n; ++i) xn[i] = x[i] + dx[i];
     phase = 1;
   }
+#undef TS_STEP_DONE
   int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
   for (int i = 0; i < n; ++i) {
     double q1 = x[i];
@@ -1306,15 +1315,21 @@ HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const 
 }
 
 template <class Tile>
-HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env, void* wb) {
+HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env_, void* wb) {
   const int n = S.n, nu = S.nu, B = a.B;
+  const bool active = env_ < B;          // surplus tiles of the last block only keep the block-wide votes balanced
+  const int env = active ? env_ : B - 1;
   double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
   for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   for (int t = 0; t < a.T; ++t) {
+#ifdef TS_SYNC_STEPS
+    tl.cta_sync();
+#endif
     for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
     const long long es = (long long)t * B + env;
     double* tp = a.tape ? a.tape + es * 3 * n * n : (double*)0;
-    int stat = step_forward(tl, S, q, qd, u, tp, wb);
+    int stat = step_forward(tl, S, q, qd, u, tp, wb, active);
+    if (!active) continue;
     if (tl.lane == 0) {
       if (a.status) a.status[es] = stat;
       if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = q[i];
@@ -1331,7 +1346,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
                         a.cmask ? a.cmask + es * 4 : (unsigned*)0);
     }
   }
-  if (tl.lane == 0)
+  if (active && tl.lane == 0)
     for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = q[i]; a.qd[(long long)env * n + i] = qd[i]; }
 }
 
