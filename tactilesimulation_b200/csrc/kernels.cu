@@ -50,9 +50,19 @@ struct DevTile {
     __syncthreads();
 #endif
   }
+  // block-wide vote; with TS_NO_SYNC_EVALS (A/B builds) every warp runs free
   HD bool cta_any(bool p) const {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(TS_SYNC_EVALS)
     return __syncthreads_or(p) != 0;
+#elif defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+  }
+  HD bool warp_all(bool p) const {
+#ifdef __CUDA_ARCH__
+    return __all_sync(0xffffffffu, p) != 0;
 #else
     return p;
 #endif

@@ -608,6 +608,7 @@ struct HostTile {
   HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
   HD void cta_sync() const {}
   HD bool cta_any(bool p) const { return p; }
+  HD bool warp_all(bool p) const { return p; }
 };
 
 #define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
@@ -774,111 +775,101 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
 #define TS_STAT_NOT_CONVERGED (1 << 16)
 #define TS_STAT_NAN (1 << 17)
 
-// One implicit step (DH/Simulation.cpp:1325-1351 with the Newton of :1150-1225).
-// q, qd: in = state at t, out = state at t+h (replicated over the tile).
-// tape (grad mode): H, G0, G1 as [3][n][n] row-major, columns written by their owner lanes.
-// On return the work space holds the kinematics (values) of the new state.
+// State of one implicit step in flight (DH/Simulation.cpp:1325-1351 with the Newton of :1150-1225).
+// phase 0: (g, H) at x, then iterate | 1: line-search trial at xn | 2: (H) at the final x | 3: G0 at the final x
+struct StepVars {
+  double x[TS_MAXN], xn[TS_MAXN], dx[TS_MAXN];
+  double alpha, gnorm;
+  int phase, fail_strike, iters, ls, trial;
+  bool converged;
+};
+
+HD void step_begin(const SceneView& S, StepVars& v, const double* q, const double* qd) {
+  for (int i = 0; i < TS_MAXN; ++i) { v.x[i] = 0.0; v.dx[i] = 0.0; v.xn[i] = 0.0; }
+  for (int i = 0; i < S.n; ++i) v.x[i] = q[i] + S.h * qd[i];
+  v.phase = 0; v.fail_strike = 0; v.iters = 0; v.ls = 0; v.trial = 0;
+  v.alpha = 1.0; v.gnorm = 0.0; v.converged = false;
+}
+
+// One round = ONE residual evaluation (with Jacobian columns) plus the bookkeeping that follows it.
+// Returns true when the step is complete: v.x is the new q, the tape (grad mode: H, G0, G1 as
+// [3][n][n] row-major, columns written by their owner lanes) is written and the work space holds the
+// kinematics (values) of the new state.
+// Every line-search trial carries its Jacobian, so an accepted trial is at once the next iterate's
+// (g, H) and -- when converged -- the tape's H.
 template <class Tile>
-HDN int step_forward(const Tile& tl, const SceneView& S, double* q, double* qd, const double* u,
-                     double* tape, void* workbuf, bool active) {
+HD bool step_round(const Tile& tl, const SceneView& S, StepVars& v, const double* q, const double* qd, const double* u,
+                   double* tape, Work<Dual>& WD) {
   const int L = Tile::LPE;
   const int n = S.n;
-  Work<Dual>& WD = *(Work<Dual>*)workbuf;
-  double x[TS_MAXN], xn[TS_MAXN], xe[TS_MAXN], dx[TS_MAXN], ge[TS_MAXN];
-  double cole[TS_NC(L)][TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) { x[i] = 0.0; dx[i] = 0.0; xn[i] = 0.0; ge[i] = 0.0; }
-  for (int i = 0; i < n; ++i) x[i] = q[i] + S.h * qd[i];
   const int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
-  // phase 0: (g, H) at x, then iterate | 1: line-search trial at xn | 2: (H) at the final x | 3: G0 at the final x
-  int phase = 0, fail_strike = 0, iters = 0, ls = 0, trial = 0;
-  double alpha = 1.0, gnorm = 0.0;
-  bool converged = false;
-#ifdef TS_SYNC_EVALS
-  // CTA-wide lockstep: every warp of the block enters each residual evaluation together, so the
-  // instruction stream is fetched once per block instead of once per warp.  Tiles that are done keep
-  // voting until the whole block is done.
-  bool live = active;
-  while (tl.cta_any(live)) {
-    if (!live) continue;
-#define TS_STEP_DONE { live = false; continue; }
-#else
-  if (active) for (;;) {
-#define TS_STEP_DONE break
-#endif
-    for (int i = 0; i < TS_MAXN; ++i) xe[i] = (phase == 1) ? xn[i] : x[i];
-    eval_columns(tl, S, xe, q, qd, u, phase == 3 ? 1 : 0, WD, ge, cole);
-    if (phase == 3) {
-      // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
-      for (int c = 0; c < TS_NC(L); ++c) {
-        const int k = tl.lane + c * L;
-        if (k < n) {
-          double Mc[TS_MAXN];
-          mass_column(S, WD, k, Mc);
-          for (int i = 0; i < n; ++i) {
-            tape[n * n + i * n + k] = cole[c][i];
-            tape[2 * n * n + i * n + k] = -S.h * Mc[i];
-          }
+  double xe[TS_MAXN], ge[TS_MAXN];
+  double cole[TS_NC(L)][TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) xe[i] = (v.phase == 1) ? v.xn[i] : v.x[i];
+  eval_columns(tl, S, xe, q, qd, u, v.phase == 3 ? 1 : 0, WD, ge, cole);
+  if (v.phase == 3) {
+    // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      if (k < n) {
+        double Mc[TS_MAXN];
+        mass_column(S, WD, k, Mc);
+        for (int i = 0; i < n; ++i) {
+          tape[n * n + i * n + k] = cole[c][i];
+          tape[2 * n * n + i * n + k] = -S.h * Mc[i];
         }
       }
-      TS_STEP_DONE;
     }
-    bool finished = false, fresh = (phase == 2);   // fresh: (ge, cole) belong to the final x
-    if (phase == 1) {
-      ++ls;
-      const double gnn = norm_n(ge, n);
-      if (gnn < gnorm) {                           // trial accepted: it is the next iterate
-        for (int i = 0; i < n; ++i) x[i] = xn[i];
-        fail_strike = 0;
-        fresh = true;
-        if (gnn < S.tol) { converged = true; finished = true; }
-      } else {
-        ++trial;
-        alpha *= 0.5;
-        if (trial < S.max_ls) {
-          for (int i = 0; i < n; ++i) xn[i] = x[i] + alpha * dx[i];
-          continue;
-        }
-        // line search exhausted (DH/Simulation.cpp:1201-1214): strike, else step with the last alpha
-        ++fail_strike;
-        if (fail_strike >= 10) finished = true;
-        else {
-          for (int i = 0; i < n; ++i) x[i] = x[i] + alpha * dx[i];
-          if (gnn < S.tol) { converged = true; finished = true; }
-          else if (iters >= max_newton) finished = true;
-          else { phase = 0; continue; }
-        }
-      }
-      if (!finished && iters >= max_newton) finished = true;
-    }
-    if (finished || phase == 2) {
-      if (!fresh) { phase = 2; continue; }         // (H) and the work space must be at the final x
-      if (!tape) TS_STEP_DONE;
-      for (int c = 0; c < TS_NC(L); ++c) {
-        const int k = tl.lane + c * L;
-        if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = cole[c][i];
-      }
-      phase = 3;
-      continue;
-    }
-    // Newton iteration from (x, ge, cole): dx = -H^-1 g, then line search from alpha = 1
-    ++iters;
-    gnorm = norm_n(ge, n);
-    for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -ge[i] : 0.0;
-    lu_solve(tl, cole, dx, n);
-    alpha = 1.0;
-    trial = 0;
-    for (int i = 0; i < n; ++i) xn[i] = x[i] + dx[i];
-    phase = 1;
+    return true;
   }
-#undef TS_STEP_DONE
-  int stat = (iters & 0xff) | ((ls & 0xff) << 8) | (converged ? 0 : TS_STAT_NOT_CONVERGED);
-  for (int i = 0; i < n; ++i) {
-    double q1 = x[i];
-    qd[i] = (q1 - q[i]) / S.h;
-    q[i] = q1;
-    if (!(q1 == q1)) stat |= TS_STAT_NAN;
+  bool finished = false, fresh = (v.phase == 2);   // fresh: (ge, cole) belong to the final x
+  if (v.phase == 1) {
+    ++v.ls;
+    const double gnn = norm_n(ge, n);
+    if (gnn < v.gnorm) {                           // trial accepted: it is the next iterate
+      for (int i = 0; i < n; ++i) v.x[i] = v.xn[i];
+      v.fail_strike = 0;
+      fresh = true;
+      if (gnn < S.tol) { v.converged = true; finished = true; }
+    } else {
+      ++v.trial;
+      v.alpha *= 0.5;
+      if (v.trial < S.max_ls) {
+        for (int i = 0; i < n; ++i) v.xn[i] = v.x[i] + v.alpha * v.dx[i];
+        return false;
+      }
+      // line search exhausted (DH/Simulation.cpp:1201-1214): strike, else step with the last alpha
+      ++v.fail_strike;
+      if (v.fail_strike >= 10) finished = true;
+      else {
+        for (int i = 0; i < n; ++i) v.x[i] = v.x[i] + v.alpha * v.dx[i];
+        if (gnn < S.tol) { v.converged = true; finished = true; }
+        else if (v.iters >= max_newton) finished = true;
+        else { v.phase = 0; return false; }
+      }
+    }
+    if (!finished && v.iters >= max_newton) finished = true;
   }
-  return stat;
+  if (finished || v.phase == 2) {
+    if (!fresh) { v.phase = 2; return false; }     // (H) and the work space must be at the final x
+    if (!tape) return true;
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = cole[c][i];
+    }
+    v.phase = 3;
+    return false;
+  }
+  // Newton iteration from (x, ge, cole): dx = -H^-1 g, then line search from alpha = 1
+  ++v.iters;
+  v.gnorm = norm_n(ge, n);
+  for (int i = 0; i < TS_MAXN; ++i) v.dx[i] = (i < n) ? -ge[i] : 0.0;
+  lu_solve(tl, cole, v.dx, n);
+  v.alpha = 1.0;
+  v.trial = 0;
+  for (int i = 0; i < n; ++i) v.xn[i] = v.x[i] + v.dx[i];
+  v.phase = 1;
+  return false;
 }
 
 // ------------------------------------------------------------------ readouts at a state
@@ -1314,36 +1305,62 @@ HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const 
   readout_from_work(tl, S, WS, var_o, tac_o, mb_o, cm_o);
 }
 
+// T steps of one environment.  Scheduling: the tiles of a warp advance step by step together; the
+// warps of a block advance ROUND by round together (one block-wide vote per residual evaluation), so
+// the whole block streams through the residual code at the same time -- the kernel is bound by
+// instruction fetch otherwise -- while a warp whose environments need extra Newton rounds delays
+// only itself, not the block.
 template <class Tile>
 HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env_, void* wb) {
   const int n = S.n, nu = S.nu, B = a.B;
-  const bool active = env_ < B;          // surplus tiles of the last block only keep the block-wide votes balanced
+  const bool active = env_ < B;          // surplus tiles of the last block only keep the votes balanced
   const int env = active ? env_ : B - 1;
+  Work<Dual>& WD = *(Work<Dual>*)wb;
   double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
   for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
-  for (int t = 0; t < a.T; ++t) {
-#ifdef TS_SYNC_STEPS
-    tl.cta_sync();
-#endif
-    for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+  StepVars v;
+  int t = 0;                             // warp-uniform
+  bool tile_done = !active;
+  if (a.T > 0) {
+    for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[(long long)env * nu + i] : 0.0;
+    step_begin(S, v, q, qd);
+  }
+  while (tl.cta_any(t < a.T)) {
+    if (t >= a.T) continue;
     const long long es = (long long)t * B + env;
-    double* tp = a.tape ? a.tape + es * 3 * n * n : (double*)0;
-    int stat = step_forward(tl, S, q, qd, u, tp, wb, active);
-    if (!active) continue;
-    if (tl.lane == 0) {
-      if (a.status) a.status[es] = stat;
-      if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = q[i];
-      if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qd[i];
+    if (!tile_done)
+      tile_done = step_round(tl, S, v, q, qd, u, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD);
+    if (!tl.warp_all(tile_done)) continue;
+    // ---- the step is complete for every tile of this warp
+    if (active) {
+      int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
+      for (int i = 0; i < n; ++i) {
+        const double q1 = v.x[i];
+        qd[i] = (q1 - q[i]) / S.h;
+        q[i] = q1;
+        if (!(q1 == q1)) stat |= TS_STAT_NAN;
+      }
+      if (tl.lane == 0) {
+        if (a.status) a.status[es] = stat;
+        if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = q[i];
+        if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qd[i];
+      }
+      const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
+      const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
+      if (vr >= 0 || tr >= 0 || a.cmask) {
+        // the work space already holds the kinematics of the new state (last residual evaluation)
+        readout_from_work(tl, S, WD,
+                          vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
+                          tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
+                          (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
+                          a.cmask ? a.cmask + es * 4 : (unsigned*)0);
+      }
     }
-    const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
-    const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
-    if (vr >= 0 || tr >= 0 || a.cmask) {
-      // the work space already holds the kinematics of the new state (last residual evaluation)
-      readout_from_work(tl, S, *(const Work<Dual>*)wb,
-                        vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
-                        tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
-                        (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
-                        a.cmask ? a.cmask + es * 4 : (unsigned*)0);
+    ++t;
+    if (t < a.T) {
+      for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+      step_begin(S, v, q, qd);
+      tile_done = !active;
     }
   }
   if (active && tl.lane == 0)

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--case", default="pusher32x13_episodic_s0")
     ap.add_argument("--lanes", type=int, nargs="+", default=[8, 16, 32])
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--zero-u", action="store_true", help="zero actions: the pad never touches the box")
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
@@ -43,6 +44,8 @@ def main():
         sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=lanes)
         dev = sim.device
         q0, qd0, u = inputs(g, a.B, a.T, dev)
+        if a.zero_u:
+            u = torch.zeros_like(u)
         for rep in range(a.reps):
             q, qd = q0.clone(), qd0.clone()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
