@@ -231,7 +231,9 @@ def run_b200(a):
     B, T = a.batch, a.horizon
     core = BatchedSim((g["ibuf"], g["dbuf"]), device=dev, lanes=a.lanes)
     n, nu, nvar, ntac = core.ndof_r, core.ndof_u, core.ndof_var, core.ndof_tactile
-    q0_h, qd0_h, u_h, goal_h = make_inputs(g["q0"], B, T, seed=1234 + rank)
+    from tactilesimulation_b200.distributed import rank_seed
+    # weak scaling: every rank owns B environments of the global batch [rank*B, (rank+1)*B), own RNG stream
+    q0_h, qd0_h, u_h, goal_h = make_inputs(g["q0"], B, T, seed=rank_seed(1234, rank))
     q0, qd0 = torch.tensor(q0_h, device=dev), torch.tensor(qd0_h, device=dev)
     u, goal = torch.tensor(u_h, device=dev), torch.tensor(goal_h, device=dev)
     dtac = torch.full((T, B, ntac), 1e-3, dtype=torch.float64, device=dev)   # tactile cotangent, resident
@@ -356,7 +358,8 @@ def run_b200(a):
     fwd_bytes = (8 * nu + 16 * n + 8 * nvar + 24 * M) * B * T           # u in; q, qd, var, tactile out
     achieved = fwd_bytes / (fwd_ms * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+    tp = os.path.join(ROOT, "profiles", tp[-1]) if tp else ""
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("fwd_kernel_dram_bytes_per_launch")
