@@ -58,16 +58,20 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 // ground contact: int {body, point_off, point_cnt, -}; dbl {kn kt mu damping}
 #define KG_ISTRIDE 4
 #define KG_DSTRIDE 4
-// general-primitive contact: int {body1, body2, point_off, point_cnt}; dbl {kn kt mu damping r_points - - -}
+// general-primitive contact: int {body1, body2, point_off, point_cnt};
+// dbl {kn kt mu damping r_points | bounding box of the points in the body-1 frame: lo(3) hi(3)}
 #define KP_ISTRIDE 4
-#define KP_DSTRIDE 8
+#define KP_DSTRIDE 12
+#define KP_BBOX 5
 // actuator: int {moving joint, mode, uoff, ndof}; dbl {cmin[3] cmax[3] P[3] D[3]}
 #define KA_ISTRIDE 4
 #define KA_DSTRIDE 12
 // end effector: int {moving joint (-1 = world), -}; dbl {pos(3) in that frame, -}
 #define KE_ISTRIDE 2
 #define KE_DSTRIDE 4
-// sensor: int {body, marker_off, marker_cnt, ncand, cand[4]}; dbl {kn kt mu damping axis0 axis1 normal r_markers}
+// sensor: int {body, marker_off, marker_cnt, ncand, cand[4]};
+// dbl {kn kt mu damping axis0 axis1 normal r_markers | bounding box of the markers in the pad frame: lo(3) hi(3)}
 #define KS_ISTRIDE 8
-#define KS_DSTRIDE 16
+#define KS_DSTRIDE 24
 #define KS_RMARK 13
+#define KS_BBOX 14

@@ -182,8 +182,15 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     if (J[r[1] * TS_JI_STRIDE + 4] != TS_SH_CUBOID) return "general-primitive contact: only cuboid primitives are supported";
     if (r[3] > 96) return "more than 96 contact points per general body are not supported";
     oi.insert(oi.end(), r, r + KP_ISTRIDE);
-    double d[KP_DSTRIDE] = {c[0], c[1], c[2], c[3], 0, 0, 0, 0};
-    for (int k = 0; k < r[3]; ++k) d[4] = fmax(d[4], norm3(P + 3 * (r[2] + k)));
+    double d[KP_DSTRIDE] = {c[0], c[1], c[2], c[3], 0};
+    for (int i = 0; i < 3; ++i) { d[KP_BBOX + i] = 1e300; d[KP_BBOX + 3 + i] = -1e300; }
+    for (int k = 0; k < r[3]; ++k) {
+      d[4] = fmax(d[4], norm3(P + 3 * (r[2] + k)));
+      for (int i = 0; i < 3; ++i) {
+        d[KP_BBOX + i] = fmin(d[KP_BBOX + i], P[3 * (r[2] + k) + i]);
+        d[KP_BBOX + 3 + i] = fmax(d[KP_BBOX + 3 + i], P[3 * (r[2] + k) + i]);
+      }
+    }
     od.insert(od.end(), d, d + KP_DSTRIDE);
   }
   // ---- actuators
@@ -220,7 +227,14 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     oi.insert(oi.end(), r, r + KS_ISTRIDE);
     double d[KS_DSTRIDE] = {0};
     for (int i = 0; i < 13; ++i) d[i] = c[i];
-    for (int k = 0; k < r[2]; ++k) d[KS_RMARK] = fmax(d[KS_RMARK], norm3(MK + 3 * (r[1] + k)));
+    for (int i = 0; i < 3; ++i) { d[KS_BBOX + i] = 1e300; d[KS_BBOX + 3 + i] = -1e300; }
+    for (int k = 0; k < r[2]; ++k) {
+      d[KS_RMARK] = fmax(d[KS_RMARK], norm3(MK + 3 * (r[1] + k)));
+      for (int i = 0; i < 3; ++i) {
+        d[KS_BBOX + i] = fmin(d[KS_BBOX + i], MK[3 * (r[1] + k) + i]);
+        d[KS_BBOX + 3 + i] = fmax(d[KS_BBOX + 3 + i], MK[3 * (r[1] + k) + i]);
+      }
+    }
     od.insert(od.end(), d, d + KS_DSTRIDE);
   }
   oi[KI_D_POINTS] = (int)od.size();

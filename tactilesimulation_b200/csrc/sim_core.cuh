@@ -342,6 +342,21 @@ HD void rel_frame(const double* R1, const double* p1, const double* R2, const do
   double d[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
   mtv3(R2, d, r);
 }
+// Exact-safe cull of a whole point set: its bounding box (lo, hi in frame 1), mapped into the box frame
+// by the precomposed relative transform, lies strictly beyond one face plane of the box (with the same
+// slack band as cuboid_classify) => by convexity no point of the set is inside the box.
+HD bool bbox_outside_box(const double* R21, const double* r, const double* lo, const double* hi, const double* hs) {
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int cidx = 0; cidx < 8; ++cidx) {
+    const double c[3] = {(cidx & 1) ? hi[0] : lo[0], (cidx & 2) ? hi[1] : lo[1], (cidx & 4) ? hi[2] : lo[2]};
+    double x[3];
+    mv3(R21, c, x);
+    for (int i = 0; i < 3; ++i) { const double v = x[i] + r[i]; mn[i] = fmin(mn[i], v); mx[i] = fmax(mx[i], v); }
+  }
+  for (int i = 0; i < 3; ++i)
+    if (mn[i] - hs[i] > TS_BAND || -mx[i] - hs[i] > TS_BAND) return true;
+  return false;
+}
 HD int ts_ffs(unsigned m) {   // index of the lowest set bit (m != 0)
 #ifdef __CUDA_ARCH__
   return __ffs((int)m) - 1;
@@ -438,6 +453,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
     // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
     double R21[9], r21[3];
     rel_frame(R1v, p1v, R2v, p2v, R21, r21);
+    if (bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs)) continue;
     unsigned act[3] = {0u, 0u, 0u};
     for (int base = 0; base < pc; base += L) {
       const int k = base + tl.lane;
@@ -458,10 +474,19 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
       act[base >> 5] |= bits << (base & 31);
     }
     if (!(act[0] | act[1] | act[2])) continue;
+    // relative kinematics of the pad in the BOX frame, once per evaluation (dual numbers):
+    //   R21 = R2^T R1, r = R2^T (p1 - p2), pad twist rotated into box coordinates
     T R1[9], p1[3], ph1[6], R2[9], p2[3], ph2[6];
-    T w1[6], w2[6];
     body_frame(S, W, b1, R1, p1, ph1);
     body_frame(S, W, b2, R2, p2, ph2);
+    T Q[9], rr[3], dp[3], w1b[3], v1b[3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Q[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
+    for (int i = 0; i < 3; ++i) dp[i] = p1[i] - p2[i];
+    mtv3(R2, dp, rr);
+    mv3(Q, ph1, w1b);
+    mv3(Q, ph1 + 3, v1b);
+    T w1[6], w2[6];          // wrenches on body 1 / body 2, both in box coordinates about the box origin
     for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
     for (int wd = 0; wd < 3; ++wd) {
       unsigned m = act[wd];
@@ -469,23 +494,22 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
         const int k = 32 * wd + ts_ffs(m);
         m &= m - 1;
         const double* xi1 = S.db + S.d_points + 3 * (po + k);
-        T xw[3], y[3], x[3];
-        mv3(R1, xi1, xw);
-        for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
-        mtv3(R2, y, x);
-        double xv[3];
-        vals3(x, xv);
+        // face pick on the reference's evaluation order (BodyCuboid.cpp:162-173), values only
+        double xwv[3], yv[3], xv[3];
+        mv3(R1v, xi1, xwv);
+        for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
+        mtv3(R2v, yv, xv);
         int ax; double sg;
         cuboid_face(xv, hs, ax, sg);
+        T ap[3], x[3];
+        mv3(Q, xi1, ap);                                   // pad point relative to the pad origin, box coordinates
+        for (int i = 0; i < 3; ++i) x[i] = ap[i] + rr[i];
         T d = sg * x[ax] - hs[ax];
-        // velocities: point of body 1 (pad frame), relative velocity in the box frame
-        T v1[3], xwd[3], u[3], t3[3];
-        cross3(ph1, xi1, v1);
-        v1[0] = v1[0] + ph1[3]; v1[1] = v1[1] + ph1[4]; v1[2] = v1[2] + ph1[5];
-        mv3(R1, v1, xwd);
-        mtv3(R2, xwd, u);
+        // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
+        T u[3], t3[3];
+        cross3(w1b, ap, u);
         cross3(ph2, x, t3);
-        for (int i = 0; i < 3; ++i) u[i] = u[i] - t3[i] - ph2[3 + i];          // u = R2^T xw_dot - w2 x x - v2
+        for (int i = 0; i < 3; ++i) u[i] = ((u[i] + v1b[i]) - t3[i]) - ph2[3 + i];
         T ddot = sg * u[ax];
         // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
         T tb[3];
@@ -495,15 +519,14 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
         for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
         tb[ax] = tb[ax] - sg * (sg * tb[ax]);
         T s = kn * d - damp * ddot * d;
-        // n1 = R1^T R2 e ; normal wrench on body 1 = -s (xi1 x n1; n1)
-        T nw[3], n1[3], m1[3];
-        for (int i = 0; i < 3; ++i) nw[i] = sg * R2[3 * i + ax];
-        mtv3(R1, nw, n1);
-        cross3(xi1, n1, m1);
         T Fb[3];
         for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
         if (mu > TS_EPS) {
-          // the reference uses the norm of the 6-vector wrench on body 1 (:208)
+          // the reference uses the norm of the 6-vector wrench on body 1 (:208): n1 = R1^T R2 e = row `ax` of
+          // R21 times sg, m1 = xi1 x n1
+          T n1[3], m1[3];
+          for (int i = 0; i < 3; ++i) n1[i] = sg * Q[3 * ax + i];
+          cross3(xi1, n1, m1);
           double n6 = 0.0;
           for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
           double fcn = fabs(val(s)) * sqrt(n6);
@@ -518,18 +541,16 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
             for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
           }
         }
-        // wrenches: body 2 gets -Gamma(xi2)^T Fb with xi2 = x - d e ; body 1 gets Gamma(xi1)^T R1^T R2 Fb
-        T xi2[3], tq[3], Fw[3], F1[3];
+        // body 2 gets -Fb at the surface point xi2 = x - d e, body 1 gets +Fb at the pad point x
+        T xi2[3], tq[3];
         for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
         cross3(xi2, Fb, tq);
         for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
-        mv3(R2, Fb, Fw);
-        mtv3(R1, Fw, F1);
-        cross3(xi1, F1, tq);
-        for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + F1[i]; }
+        cross3(x, Fb, tq);
+        for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
       }
     }
-    push_wrench(W, j1, R1, p1, w1, -h2);
+    push_wrench(W, j1, R2, p2, w1, -h2);
     push_wrench(W, j2, R2, p2, w2, -h2);
   }
 }
@@ -619,20 +640,12 @@ struct HostTile {
 // The matrix is first all-gathered (one shuffle per entry), then every lane factors its own copy
 // in registers with compile-time indices: no cross-lane traffic inside the elimination, and the
 // solution comes out replicated, which is how the Newton update needs it.
-template <class Tile>
-HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
-  const int L = Tile::LPE;
-  double A[TS_MAXN][TS_MAXN];           // A[i][c], every index below is a compile-time constant
-#pragma unroll
-  for (int c = 0; c < TS_MAXN; ++c)
-#pragma unroll
-    for (int i = 0; i < TS_MAXN; ++i) {
-      double v = tl.bcast(col[c / L][i], c % L);
-      A[i][c] = (i < n && c < n) ? v : ((i == c) ? 1.0 : 0.0);   // identity padding keeps the 8x8 factorisation regular
-    }
-  double b[TS_MAXN];
-#pragma unroll
-  for (int i = 0; i < TS_MAXN; ++i) b[i] = (i < n) ? rhs[i] : 0.0;
+// PIVOT=false is the same elimination without row exchanges; it reports whether partial pivoting
+// would have exchanged any row (then the caller redoes the solve with PIVOT=true).  Newton matrices
+// H = M - h^2 K - h D are mass dominated, so the exchange-free pass almost always stands.
+template <bool PIVOT>
+HD bool lu_factor_solve(double (*A)[TS_MAXN], double* b) {
+  bool exchanged = false;
 #pragma unroll
   for (int j = 0; j < TS_MAXN; ++j) {
     int p = j;
@@ -642,18 +655,22 @@ HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
       const double v = fabs(A[i][j]);
       if (v > best) { best = v; p = i; }
     }
+    if (PIVOT) {
 #pragma unroll
-    for (int i = j + 1; i < TS_MAXN; ++i) {
-      const bool sw = (p == i);
+      for (int i = j + 1; i < TS_MAXN; ++i) {
+        const bool sw = (p == i);
 #pragma unroll
-      for (int c = j; c < TS_MAXN; ++c) {
-        const double t = A[j][c], s2 = A[i][c];
-        A[j][c] = sw ? s2 : t;
-        A[i][c] = sw ? t : s2;
+        for (int c = j; c < TS_MAXN; ++c) {
+          const double t = A[j][c], s2 = A[i][c];
+          A[j][c] = sw ? s2 : t;
+          A[i][c] = sw ? t : s2;
+        }
+        const double t = b[j], s2 = b[i];
+        b[j] = sw ? s2 : t;
+        b[i] = sw ? t : s2;
       }
-      const double t = b[j], s2 = b[i];
-      b[j] = sw ? s2 : t;
-      b[i] = sw ? t : s2;
+    } else if (p != j) {
+      exchanged = true;
     }
     const double piv = A[j][j];
 #pragma unroll
@@ -670,6 +687,36 @@ HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
     b[k] = xk;
 #pragma unroll
     for (int i = 0; i < k; ++i) b[i] -= A[i][k] * xk;
+  }
+  return exchanged;
+}
+
+template <class Tile>
+HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
+  const int L = Tile::LPE;
+  double A[TS_MAXN][TS_MAXN];           // A[i][c], every index below is a compile-time constant
+  double b[TS_MAXN];
+#pragma unroll
+  for (int c = 0; c < TS_MAXN; ++c)
+#pragma unroll
+    for (int i = 0; i < TS_MAXN; ++i) {
+      double v = tl.bcast(col[c / L][i], c % L);
+      A[i][c] = (i < n && c < n) ? v : ((i == c) ? 1.0 : 0.0);   // identity padding keeps the 8x8 factorisation regular
+    }
+#pragma unroll
+  for (int i = 0; i < TS_MAXN; ++i) b[i] = (i < n) ? rhs[i] : 0.0;
+  if (lu_factor_solve<false>(A, b)) {
+    // rare: a row exchange is needed -- gather again and run the pivoting elimination
+#pragma unroll
+    for (int c = 0; c < TS_MAXN; ++c)
+#pragma unroll
+      for (int i = 0; i < TS_MAXN; ++i) {
+        double v = tl.bcast(col[c / L][i], c % L);
+        A[i][c] = (i < n && c < n) ? v : ((i == c) ? 1.0 : 0.0);
+      }
+#pragma unroll
+    for (int i = 0; i < TS_MAXN; ++i) b[i] = (i < n) ? rhs[i] : 0.0;
+    lu_factor_solve<true>(A, b);
   }
 #pragma unroll
   for (int i = 0; i < TS_MAXN; ++i) rhs[i] = b[i];
@@ -900,7 +947,11 @@ HDN void sensor_frames(const SceneView& S, const Work<T>& W, const int* sr, cons
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
     F.near[1 + c] = !(dx * dx + dy * dy + dz * dz > rr * rr);
-    if (F.near[1 + c]) rel_frame(F.R[0], F.p[0], F.R[1 + c], F.p[1 + c], F.R21[c], F.r21[c]);
+    if (F.near[1 + c]) {
+      rel_frame(F.R[0], F.p[0], F.R[1 + c], F.p[1 + c], F.R21[c], F.r21[c]);
+      if (bbox_outside_box(F.R21[c], F.r21[c], sd + KS_BBOX, sd + KS_BBOX + 3, S.db + S.d_body + b2 * KB_DSTRIDE + KB_HALF))
+        F.near[1 + c] = false;
+    }
   }
 }
 

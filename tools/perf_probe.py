@@ -37,11 +37,15 @@ def main():
     ap.add_argument("--lanes", type=int, nargs="+", default=[8, 16, 32])
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--zero-u", action="store_true", help="zero actions: the pad never touches the box")
+    ap.add_argument("--no-gp", action="store_true", help="timing experiment: drop the pad-box contact force")
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
     for lanes in a.lanes:
-        sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=lanes)
+        ib = g["ibuf"].copy()
+        if a.no_gp:
+            ib[8] = 0
+        sim = BatchedSim((ib, g["dbuf"]), "cuda:0", lanes=lanes)
         dev = sim.device
         q0, qd0, u = inputs(g, a.B, a.T, dev)
         if a.zero_u:
