@@ -19,11 +19,18 @@
 #include "scene_lower.h"
 #include "sim_core.cuh"
 
+#ifdef TS_PROFILE
+__device__ long long* g_prof = 0;      // [threads][8] cycle accumulators (development builds only)
+#endif
+
 template <int LPE_>
 struct DevTile {
   static const int LPE = LPE_;
   int lane;
   unsigned mask;
+#ifdef TS_PROFILE
+  mutable long long acc[8];
+#endif
   HD double bcast(double v, int src) const {
 #ifdef __CUDA_ARCH__
     return __shfl_sync(mask, v, src, LPE_);
@@ -66,6 +73,43 @@ struct DevTile {
 #else
     return p;
 #endif
+  }
+  // ---- whole-warp helpers: every lane of the warp must call them together
+  static const int TPW = 32 / LPE_;
+  HD int tile_in_warp() const { return (threadIdx.x & 31) / LPE_; }
+  // bit t = predicate of tile t (the predicate is uniform inside a tile)
+  HD unsigned tiles_ballot(bool p) const {
+#ifdef __CUDA_ARCH__
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    unsigned r = 0;
+#pragma unroll
+    for (int t = 0; t < 32 / LPE_; ++t) r |= ((b >> (t * LPE_)) & 1u) << t;
+    return r;
+#else
+    return p ? 1u : 0u;
+#endif
+  }
+  HD double warp_shfl(double v, int src) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(0xffffffffu, v, src);
+#else
+    return v;
+#endif
+  }
+  HD unsigned warp_shfl_u(unsigned v, int src) const {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(0xffffffffu, v, src);
+#else
+    return v;
+#endif
+  }
+  // sum over the tiles of the warp of the value held by the same tile-lane
+  HD double sum_tiles(double v) const {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = LPE_; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
   }
   // predicate of every lane of the tile, bit i = lane i
   HD unsigned ballot(bool p) const {
@@ -112,7 +156,15 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   DevTile<LPE> tl = make_tile<LPE>();
   __align__(16) unsigned char wb[sizeof(Work<Dual>)];
+#ifdef TS_PROFILE
+  for (int i = 0; i < 8; ++i) tl.acc[i] = 0;
+  const long long t_begin = clock64();
+#endif
   env_forward(tl, S, a, env, wb);     // tiles past the batch stay in the block-wide votes
+#ifdef TS_PROFILE
+  tl.acc[7] = clock64() - t_begin;
+  if (g_prof) for (int i = 0; i < 8; ++i) g_prof[(long long)(blockIdx.x * blockDim.x + threadIdx.x) * 8 + i] = tl.acc[i];
+#endif
 }
 
 template <int LPE>
@@ -176,6 +228,10 @@ static int prep(K kern, size_t smem) {
 }
 
 extern "C" {
+
+#ifdef TS_PROFILE
+int tsim_debug_set_prof(void* p) { return cudaMemcpyToSymbol(g_prof, &p, sizeof(p)) != cudaSuccess; }
+#endif
 
 const char* tsim_last_error(void) { return g_err.c_str(); }
 

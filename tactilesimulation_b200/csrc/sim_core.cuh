@@ -45,6 +45,19 @@
 #define TS_NOINLINE __attribute__((noinline))
 #endif
 
+// optional clock64 instrumentation of the forward kernel (development builds only: -DTS_PROFILE)
+#if defined(TS_PROFILE) && defined(__CUDA_ARCH__)
+#define TS_TIC(tl) const long long ts_t0_ = clock64()
+#define TS_TOC(tl, slot) (tl).acc[slot] += clock64() - ts_t0_
+#define TS_TIC2(tl) const long long ts_t1_ = clock64()
+#define TS_TOC2(tl, slot) (tl).acc[slot] += clock64() - ts_t1_
+#else
+#define TS_TIC(tl)
+#define TS_TOC(tl, slot)
+#define TS_TIC2(tl)
+#define TS_TOC2(tl, slot)
+#endif
+
 #define TS_MAXJ KT_MAXJ
 #define TS_MAXN KT_MAXN
 #define TS_MAXU KT_MAXU
@@ -112,6 +125,20 @@ template <class A, class B, class C> HD void twist_to_frame(const A* R, const A*
   t[0] = t[0] + in[3]; t[1] = t[1] + in[4]; t[2] = t[2] + in[5];
   mtv3(R, in, out);
   mtv3(R, t, out + 3);
+}
+
+// momentum-like product of the composite spatial inertia of joint j with a joint-frame twist:
+//   h_ang = Ibar w + mc x v,  h_lin = m v + w x mc
+template <class T>
+HD void inertia_mul(const double* jd, const T* tw, T* hm) {
+  const double* Ib = jd + KJ_IBAR;
+  const double* mc = jd + KJ_MC;
+  const double m = jd[KJ_MASS];
+  T a[3], b[3];
+  mv3(Ib, tw, hm);
+  cross3(mc, tw + 3, a);
+  cross3(tw, mc, b);
+  for (int i = 0; i < 3; ++i) { hm[i] = hm[i] + a[i]; hm[3 + i] = m * tw[3 + i] + b[i]; }
 }
 
 // ------------------------------------------------------------------ per-lane work space
@@ -192,20 +219,47 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
       mv3(Ra, vq, sq + 3);               // pure translations: screw = (0, Ra axis)
       if (dyn) mv3(Ra, vl, sl + 3);
     }
-    T* V = W.V[j];
-    for (int i = 0; i < 6; ++i) V[i] = Vp[i] + sq[i];
+    T Vl[6];
+    for (int i = 0; i < 6; ++i) { Vl[i] = Vp[i] + sq[i]; W.V[j][i] = Vl[i]; }
     if (dyn) {
       // X_j = X_p + S dl + h^2 ad(V_p)(S qd): the joint axes are fixed in the parent body
-      T c0[3], c1v[3], c2[3];
+      T c0[3], c1v[3], c2[3], Xl[6];
       cross3(Vp, sq, c0);                // w_p x s_w
       cross3(Vp, sq + 3, c1v);           // w_p x s_v
       cross3(Vp + 3, sq, c2);            // v_p x s_w
-      T* X = W.X[j];
       for (int i = 0; i < 3; ++i) {
-        X[i] = Xp[i] + sl[i] + h2 * c0[i];
-        X[3 + i] = Xp[3 + i] + sl[3 + i] + h2 * (c1v[i] + c2[i]);
+        Xl[i] = Xp[i] + sl[i] + h2 * c0[i];
+        Xl[3 + i] = Xp[3 + i] + sl[3 + i] + h2 * (c1v[i] + c2[i]);
       }
-      for (int i = 0; i < 6; ++i) W.Wa[j][i] = 0.0;
+      for (int i = 0; i < 6; ++i) W.X[j][i] = Xl[i];
+      // composite rigid body of this joint, while its frame is still in registers:
+      // a_j = I chi_j - h^2 (coriolis + gravity) in the joint frame (per reference body:
+      // DH/Body/Body.cpp:234-247; summed by linearity of the spatial inertia), pushed to the world frame
+      if (ji[5]) {
+        T ph[6], ch[6], hp[6], a[6];
+        twist_to_frame(R0, p0, Vl, ph);
+        twist_to_frame(R0, p0, Xl, ch);
+        inertia_mul(jd, ph, hp);
+        inertia_mul(jd, ch, a);
+        // coriolis ad(phi)^T h = (h_ang x w + h_lin x v ; h_lin x w), gravity (mc x R^T g ; m R^T g)
+        T d0[3], d1[3], d2[3], gb[3], gm[3];
+        cross3(hp, ph, d0);
+        cross3(hp + 3, ph + 3, d1);
+        cross3(hp + 3, ph, d2);
+        mtv3(R0, S.grav, gb);
+        cross3(jd + KJ_MC, gb, gm);
+        for (int i = 0; i < 3; ++i) {
+          a[i] = a[i] - h2 * ((d0[i] + d1[i]) + gm[i]);
+          a[3 + i] = a[3 + i] - h2 * (d2[i] + jd[KJ_MASS] * gb[i]);
+        }
+        T f[3], t[3], pf[3];
+        mv3(R0, a + 3, f);
+        mv3(R0, a, t);
+        cross3(p0, f, pf);
+        for (int i = 0; i < 3; ++i) { W.Wa[j][i] = t[i] + pf[i]; W.Wa[j][3 + i] = f[i]; }
+      } else {
+        for (int i = 0; i < 6; ++i) W.Wa[j][i] = 0.0;
+      }
     }
   }
 }
@@ -258,48 +312,6 @@ HD void push_wrench(Work<T>& W, int j, const T* R, const T* p, const T* wr, doub
   cross3(p, f, pf);
   T* A = W.Wa[j];
   for (int i = 0; i < 3; ++i) { A[i] = A[i] + scale * (t[i] + pf[i]); A[3 + i] = A[3 + i] + scale * f[i]; }
-}
-
-// momentum-like product of the composite spatial inertia of joint j with a joint-frame twist:
-//   h_ang = Ibar w + mc x v,  h_lin = m v + w x mc
-template <class T>
-HD void inertia_mul(const double* jd, const T* tw, T* hm) {
-  const double* Ib = jd + KJ_IBAR;
-  const double* mc = jd + KJ_MC;
-  const double m = jd[KJ_MASS];
-  T a[3], b[3];
-  mv3(Ib, tw, hm);
-  cross3(mc, tw + 3, a);
-  cross3(tw, mc, b);
-  for (int i = 0; i < 3; ++i) { hm[i] = hm[i] + a[i]; hm[3 + i] = m * tw[3 + i] + b[i]; }
-}
-
-// a_j = I chi_j - h^2 (coriolis + gravity) for the composite body of every moving joint, in the joint
-// frame (per reference body: DH/Body/Body.cpp:234-247; summed here by linearity of the spatial inertia)
-template <class T>
-HDN void joint_dynamics(const SceneView& S, Work<T>& W) {
-  const double h2 = S.h * S.h;
-  for (int j = 0; j < S.nj; ++j) {
-    if (!S.ib[S.o_joint + j * KJ_ISTRIDE + 5]) continue;
-    const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
-    T ph[6], ch[6], hp[6], a[6];
-    twist_to_frame(W.R0[j], W.p0[j], W.V[j], ph);
-    twist_to_frame(W.R0[j], W.p0[j], W.X[j], ch);
-    inertia_mul(jd, ph, hp);
-    inertia_mul(jd, ch, a);
-    // coriolis ad(phi)^T h = (h_ang x w + h_lin x v ; h_lin x w), gravity (mc x R^T g ; m R^T g)
-    T c0[3], c1[3], c2[3], gb[3], gm[3];
-    cross3(hp, ph, c0);
-    cross3(hp + 3, ph + 3, c1);
-    cross3(hp + 3, ph, c2);
-    mtv3(W.R0[j], S.grav, gb);
-    cross3(jd + KJ_MC, gb, gm);
-    for (int i = 0; i < 3; ++i) {
-      a[i] = a[i] - h2 * ((c0[i] + c1[i]) + gm[i]);
-      a[3 + i] = a[3 + i] - h2 * (c2[i] + jd[KJ_MASS] * gb[i]);
-    }
-    push_wrench(W, j, W.R0[j], W.p0[j], a, 1.0);
-  }
 }
 
 // ------------------------------------------------------------------ cuboid SDF face pick
@@ -427,11 +439,91 @@ HDN void ground_contacts(const SceneView& S, Work<T>& W) {
   }
 }
 
+// Relative kinematics of the contact pair in the BOX frame (dual numbers, once per evaluation) plus
+// the values the exact face pick needs: everything one contact point evaluation reads.
+template <class T> struct GpPair {
+  T Q[9], rr[3], w1b[3], v1b[3], ph2[6];    // R21 = R2^T R1, r = R2^T (p1 - p2), pad twist in box coordinates, box twist
+  double R1v[9], p1v[3], R2v[9], p2v[3];    // values of the two body frames (reference evaluation order of the face pick)
+};
+
+// Penalty force of ONE active sampled point (DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
+// DH/Body/BodyCuboid.cpp:146-184), accumulated as wrenches on body 1 / body 2, both in box coordinates
+// about the box origin.
+template <class T>
+HD void gp_point_force(const GpPair<T>& P, const double* xi1, const double* hs, double kn, double kt, double mu,
+                       double damp, T* w1, T* w2) {
+  // face pick on the reference's evaluation order (BodyCuboid.cpp:162-173), values only
+  double xwv[3], yv[3], xv[3];
+  mv3(P.R1v, xi1, xwv);
+  for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
+  mtv3(P.R2v, yv, xv);
+  int ax; double sg;
+  cuboid_face(xv, hs, ax, sg);
+  T ap[3], x[3];
+  mv3(P.Q, xi1, ap);                                   // pad point relative to the pad origin, box coordinates
+  for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
+  T d = sg * x[ax] - hs[ax];
+  // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
+  T u[3], t3[3];
+  cross3(P.w1b, ap, u);
+  cross3(P.ph2, x, t3);
+  for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
+  T ddot = sg * u[ax];
+  // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
+  T tb[3];
+  double e[3] = {0.0, 0.0, 0.0};
+  e[ax] = sg;
+  cross3(P.ph2, e, t3);
+  for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
+  tb[ax] = tb[ax] - sg * (sg * tb[ax]);
+  T s = kn * d - damp * ddot * d;
+  T Fb[3];
+  for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
+  if (mu > TS_EPS) {
+    // the reference uses the norm of the 6-vector wrench on body 1 (:208): n1 = R1^T R2 e = row `ax` of
+    // R21 times sg, m1 = xi1 x n1
+    T n1[3], m1[3];
+    for (int i = 0; i < 3; ++i) n1[i] = sg * P.Q[3 * ax + i];
+    cross3(xi1, n1, m1);
+    double n6 = 0.0;
+    for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
+    double fcn = fabs(val(s)) * sqrt(n6);
+    double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
+    if (mu * fcn >= kt * tn - TS_EPS) {
+      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
+    } else {
+      T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+      T fcT = dabs(s) * dsqrt(n6T);
+      T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
+      T sc = mu * fcT / tnT;
+      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+    }
+  }
+  // body 2 gets -Fb at the surface point xi2 = x - d e, body 1 gets +Fb at the pad point x
+  T xi2[3], tq[3];
+  for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
+  cross3(xi2, Fb, tq);
+  for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
+  cross3(x, Fb, tq);
+  for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
+}
+
+template <class Tile> HD double tile_xfer(const Tile& tl, double v, int src) { return tl.warp_shfl(v, src); }
+template <class Tile> HD Dual tile_xfer(const Tile& tl, Dual v, int src) { return mkdual(tl.warp_shfl(v.v, src), tl.warp_shfl(v.d, src)); }
+template <class Tile> HD double tiles_sum(const Tile& tl, double v) { return tl.sum_tiles(v); }
+template <class Tile> HD Dual tiles_sum(const Tile& tl, Dual v) { return mkdual(tl.sum_tiles(v.v), tl.sum_tiles(v.d)); }
+
 // sampled points of a general body vs a cuboid SDF: DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
-// DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83
+// DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83.
+// Detection is dealt to the lanes of the tile and gathered by ballot.
+// Experimental (-DTS_COOP_CONTACTS, off: measured slower on B200 because of the register pressure of the
+// extra path): when only few tiles of the warp are in contact, their active points are dealt to ALL
+// tiles of the warp and the partial wrenches summed back by shuffles; the function must then be
+// reached by every lane of the warp together.
 template <class Tile, class T>
 HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
   const int L = Tile::LPE;
+  const int TPW = Tile::TPW;
   const double h2 = S.h * S.h;
   for (int fi = 0; fi < S.ngp; ++fi) {
     const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
@@ -441,117 +533,118 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
     const double* hs = bd2 + KB_HALF;
-    // exact-safe cull on values: a point of body 1 inside the box needs |p1 - p2| <= r_points + |half|
-    double R1v[9], p1v[3], R2v[9], p2v[3], phv[6];
-    body_frame_v(S, W, b1, R1v, p1v, phv);
-    body_frame_v(S, W, b2, R2v, p2v, phv);
-    {
-      const double rr = c[4] + bd2[KB_RBOUND] + TS_CULL_MARGIN;
-      const double dx = p1v[0] - p2v[0], dy = p1v[1] - p2v[1], dz = p1v[2] - p2v[2];
-      if (dx * dx + dy * dy + dz * dz > rr * rr) continue;
-    }
-    // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
-    double R21[9], r21[3];
-    rel_frame(R1v, p1v, R2v, p2v, R21, r21);
-    if (bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs)) continue;
+    GpPair<T> P;
+    double phv[6];
+    body_frame_v(S, W, b1, P.R1v, P.p1v, phv);
+    body_frame_v(S, W, b2, P.R2v, P.p2v, phv);
     unsigned act[3] = {0u, 0u, 0u};
-    for (int base = 0; base < pc; base += L) {
-      const int k = base + tl.lane;
-      bool in = false;
-      if (k < pc) {
-        const double* xi1 = S.db + S.d_points + 3 * (po + k);
-        const int cls = cuboid_classify(R21, r21, xi1, hs);
-        if (cls > 0) in = true;
-        else if (cls == 0) {                 // reference evaluation order (CollisionDetection.cpp:73-79)
-          double xwv[3], yv[3], xv[3];
-          mv3(R1v, xi1, xwv);
-          for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
-          mtv3(R2v, yv, xv);
-          in = cuboid_inside(xv, hs);
+    {
+      // exact-safe culls on values: bounding spheres, then the bounding box of the point set against the
+      // face planes of the box
+      const double rr = c[4] + bd2[KB_RBOUND] + TS_CULL_MARGIN;
+      const double dx = P.p1v[0] - P.p2v[0], dy = P.p1v[1] - P.p2v[1], dz = P.p1v[2] - P.p2v[2];
+      double R21[9], r21[3];
+      rel_frame(P.R1v, P.p1v, P.R2v, P.p2v, R21, r21);
+      const bool maybe = !(dx * dx + dy * dy + dz * dz > rr * rr) && !bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs);
+      // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
+      if (maybe) {
+        for (int base = 0; base < pc; base += L) {
+          const int k = base + tl.lane;
+          bool in = false;
+          if (k < pc) {
+            const double* xi1 = S.db + S.d_points + 3 * (po + k);
+            const int cls = cuboid_classify(R21, r21, xi1, hs);
+            if (cls > 0) in = true;
+            else if (cls == 0) {                 // reference evaluation order (CollisionDetection.cpp:73-79)
+              double xwv[3], yv[3], xv[3];
+              mv3(P.R1v, xi1, xwv);
+              for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
+              mtv3(P.R2v, yv, xv);
+              in = cuboid_inside(xv, hs);
+            }
+          }
+          const unsigned bits = tl.ballot(in);
+          act[base >> 5] |= bits << (base & 31);
         }
       }
-      const unsigned bits = tl.ballot(in);
-      act[base >> 5] |= bits << (base & 31);
     }
-    if (!(act[0] | act[1] | act[2])) continue;
-    // relative kinematics of the pad in the BOX frame, once per evaluation (dual numbers):
-    //   R21 = R2^T R1, r = R2^T (p1 - p2), pad twist rotated into box coordinates
-    T R1[9], p1[3], ph1[6], R2[9], p2[3], ph2[6];
-    body_frame(S, W, b1, R1, p1, ph1);
-    body_frame(S, W, b2, R2, p2, ph2);
-    T Q[9], rr[3], dp[3], w1b[3], v1b[3];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Q[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
-    for (int i = 0; i < 3; ++i) dp[i] = p1[i] - p2[i];
-    mtv3(R2, dp, rr);
-    mv3(Q, ph1, w1b);
-    mv3(Q, ph1 + 3, v1b);
+    const bool has = (act[0] | act[1] | act[2]) != 0u;
+#ifdef TS_COOP_CONTACTS
+    const unsigned tmask = tl.tiles_ballot(has);      // bit t: tile t of this warp is in contact (warp-uniform)
+#else
+    const unsigned tmask = has ? 1u : 0u;
+#endif
+    if (!tmask) continue;
+    // the tile's own relative kinematics in the BOX frame (dual numbers)
+    T R2[9], p2[3];
+    for (int i = 0; i < 9; ++i) P.Q[i] = 0.0;
+    for (int i = 0; i < 3; ++i) { P.rr[i] = 0.0; P.w1b[i] = 0.0; P.v1b[i] = 0.0; }
+    for (int i = 0; i < 6; ++i) P.ph2[i] = 0.0;
+    if (has) {
+      T R1[9], p1[3], ph1[6], dp[3];
+      body_frame(S, W, b1, R1, p1, ph1);
+      body_frame(S, W, b2, R2, p2, P.ph2);
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) P.Q[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
+      for (int i = 0; i < 3; ++i) dp[i] = p1[i] - p2[i];
+      mtv3(R2, dp, P.rr);
+      mv3(P.Q, ph1, P.w1b);
+      mv3(P.Q, ph1 + 3, P.v1b);
+    }
     T w1[6], w2[6];          // wrenches on body 1 / body 2, both in box coordinates about the box origin
     for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
-    for (int wd = 0; wd < 3; ++wd) {
-      unsigned m = act[wd];
-      while (m) {
-        const int k = 32 * wd + ts_ffs(m);
-        m &= m - 1;
-        const double* xi1 = S.db + S.d_points + 3 * (po + k);
-        // face pick on the reference's evaluation order (BodyCuboid.cpp:162-173), values only
-        double xwv[3], yv[3], xv[3];
-        mv3(R1v, xi1, xwv);
-        for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + p1v[i]) - p2v[i];
-        mtv3(R2v, yv, xv);
-        int ax; double sg;
-        cuboid_face(xv, hs, ax, sg);
-        T ap[3], x[3];
-        mv3(Q, xi1, ap);                                   // pad point relative to the pad origin, box coordinates
-        for (int i = 0; i < 3; ++i) x[i] = ap[i] + rr[i];
-        T d = sg * x[ax] - hs[ax];
-        // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
-        T u[3], t3[3];
-        cross3(w1b, ap, u);
-        cross3(ph2, x, t3);
-        for (int i = 0; i < 3; ++i) u[i] = ((u[i] + v1b[i]) - t3[i]) - ph2[3 + i];
-        T ddot = sg * u[ax];
-        // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
-        T tb[3];
-        double e[3] = {0.0, 0.0, 0.0};
-        e[ax] = sg;
-        cross3(ph2, e, t3);
-        for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
-        tb[ax] = tb[ax] - sg * (sg * tb[ax]);
-        T s = kn * d - damp * ddot * d;
-        T Fb[3];
-        for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
-        if (mu > TS_EPS) {
-          // the reference uses the norm of the 6-vector wrench on body 1 (:208): n1 = R1^T R2 e = row `ax` of
-          // R21 times sg, m1 = xi1 x n1
-          T n1[3], m1[3];
-          for (int i = 0; i < 3; ++i) n1[i] = sg * Q[3 * ax + i];
-          cross3(xi1, n1, m1);
-          double n6 = 0.0;
-          for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
-          double fcn = fabs(val(s)) * sqrt(n6);
-          double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
-          if (mu * fcn >= kt * tn - TS_EPS) {
-            for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
-          } else {
-            T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
-            T fcT = dabs(s) * dsqrt(n6T);
-            T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
-            T sc = mu * fcT / tnT;
-            for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+    int nct = 0;
+    for (unsigned tm = tmask; tm; tm &= tm - 1) ++nct;
+#ifdef TS_COOP_CONTACTS
+    const bool coop = TPW > 1 && 2 * nct <= TPW;
+#else
+    const bool coop = false;   // measured slower on B200 (register pressure of the extra path): kept for experiments
+#endif
+    if (coop) {
+      // few tiles in contact: deal the active points of each of them to all tiles of the warp
+      const int mytile = tl.tile_in_warp();
+      for (unsigned tm = tmask; tm; tm &= tm - 1) {
+        const int A = ts_ffs(tm);
+        const int src = A * L + tl.lane;               // the lane of tile A that carries my tangent
+        GpPair<T> PA;
+        for (int i = 0; i < 9; ++i) { PA.Q[i] = tile_xfer(tl, P.Q[i], src); PA.R1v[i] = tl.warp_shfl(P.R1v[i], src); PA.R2v[i] = tl.warp_shfl(P.R2v[i], src); }
+        for (int i = 0; i < 3; ++i) {
+          PA.rr[i] = tile_xfer(tl, P.rr[i], src); PA.w1b[i] = tile_xfer(tl, P.w1b[i], src); PA.v1b[i] = tile_xfer(tl, P.v1b[i], src);
+          PA.p1v[i] = tl.warp_shfl(P.p1v[i], src); PA.p2v[i] = tl.warp_shfl(P.p2v[i], src);
+        }
+        for (int i = 0; i < 6; ++i) PA.ph2[i] = tile_xfer(tl, P.ph2[i], src);
+        T a1[6], a2[6];
+        for (int i = 0; i < 6; ++i) { a1[i] = 0.0; a2[i] = 0.0; }
+        for (int wd = 0; wd < 3; ++wd) {
+          unsigned m = tl.warp_shfl_u(act[wd], src);
+          while (m) {
+            // the next TPW active points, one per tile, so that all tiles work in the same pass
+            int myk = -1;
+            for (int t = 0; t < TPW && m; ++t) {
+              const int kk = ts_ffs(m);
+              m &= m - 1;
+              if (t == mytile) myk = kk;
+            }
+            if (myk >= 0) gp_point_force(PA, S.db + S.d_points + 3 * (po + 32 * wd + myk), hs, kn, kt, mu, damp, a1, a2);
           }
         }
-        // body 2 gets -Fb at the surface point xi2 = x - d e, body 1 gets +Fb at the pad point x
-        T xi2[3], tq[3];
-        for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
-        cross3(xi2, Fb, tq);
-        for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
-        cross3(x, Fb, tq);
-        for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
+        for (int i = 0; i < 6; ++i) { a1[i] = tiles_sum(tl, a1[i]); a2[i] = tiles_sum(tl, a2[i]); }
+        if (mytile == A) for (int i = 0; i < 6; ++i) { w1[i] = a1[i]; w2[i] = a2[i]; }
+      }
+    } else if (has) {
+      for (int wd = 0; wd < 3; ++wd) {
+        unsigned m = act[wd];
+        while (m) {
+          const int k = 32 * wd + ts_ffs(m);
+          m &= m - 1;
+          gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
+        }
       }
     }
-    push_wrench(W, j1, R2, p2, w1, -h2);
-    push_wrench(W, j2, R2, p2, w2, -h2);
+    if (has) {
+      push_wrench(W, j1, R2, p2, w1, -h2);
+      push_wrench(W, j2, R2, p2, w2, -h2);
+    }
   }
 }
 
@@ -611,11 +704,10 @@ HDN void eval_g(const Tile& tl, const SceneView& S, const T* q1, const T* q0, co
     qd1[i] = (q1[i] - q0[i]) / S.h;
     dl[i] = q1[i] - q0[i] - S.h * qd0[i];
   }
-  kinematics<T>(S, q1, qd1, dl, W, true);
-  joint_dynamics<T>(S, W);
-  ground_contacts<T>(S, W);
-  gp_contacts(tl, S, W);
-  inward<T>(S, W, q1, qd1, u, g);
+  { TS_TIC(tl); kinematics<T>(S, q1, qd1, dl, W, true); TS_TOC(tl, 0); }
+  { TS_TIC(tl); ground_contacts<T>(S, W); TS_TOC(tl, 1); }
+  { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
+  { TS_TIC(tl); inward<T>(S, W, q1, qd1, u, g); TS_TOC(tl, 3); }
 }
 
 // ------------------------------------------------------------------ tile policies
@@ -630,6 +722,13 @@ struct HostTile {
   HD void cta_sync() const {}
   HD bool cta_any(bool p) const { return p; }
   HD bool warp_all(bool p) const { return p; }
+  // whole-warp helpers (one tile per "warp" on the host)
+  static const int TPW = 1;
+  HD int tile_in_warp() const { return 0; }
+  HD unsigned tiles_ballot(bool p) const { return p ? 1u : 0u; }
+  HD double warp_shfl(double v, int) const { return v; }
+  HD unsigned warp_shfl_u(unsigned v, int) const { return v; }
+  HD double sum_tiles(double v) const { return v; }
 };
 
 #define TS_NC(LPE) ((TS_MAXN + (LPE)-1) / (LPE))
@@ -844,16 +943,22 @@ HD void step_begin(const SceneView& S, StepVars& v, const double* q, const doubl
 // kinematics (values) of the new state.
 // Every line-search trial carries its Jacobian, so an accepted trial is at once the next iterate's
 // (g, H) and -- when converged -- the tape's H.
+// step_eval is the evaluation (every tile of a warp runs it together, also tiles whose step is already
+// complete: the residual code votes and shuffles across the warp); step_post is the bookkeeping.
 template <class Tile>
-HD bool step_round(const Tile& tl, const SceneView& S, StepVars& v, const double* q, const double* qd, const double* u,
-                   double* tape, Work<Dual>& WD) {
+HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, const double* q, const double* qd,
+                  const double* u, Work<Dual>& WD, double* ge, double (*cole)[TS_MAXN]) {
+  double xe[TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) xe[i] = (v.phase == 1) ? v.xn[i] : v.x[i];
+  eval_columns(tl, S, xe, q, qd, u, v.phase == 3 ? 1 : 0, WD, ge, cole);
+}
+
+template <class Tile>
+HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape, Work<Dual>& WD, double* ge,
+                  double (*cole)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
   const int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
-  double xe[TS_MAXN], ge[TS_MAXN];
-  double cole[TS_NC(L)][TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) xe[i] = (v.phase == 1) ? v.xn[i] : v.x[i];
-  eval_columns(tl, S, xe, q, qd, u, v.phase == 3 ? 1 : 0, WD, ge, cole);
   if (v.phase == 3) {
     // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
     for (int c = 0; c < TS_NC(L); ++c) {
@@ -1376,12 +1481,27 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[(long long)env * nu + i] : 0.0;
     step_begin(S, v, q, qd);
   }
-  while (tl.cta_any(t < a.T)) {
+  for (;;) {
+    { TS_TIC(tl); const bool go = tl.cta_any(t < a.T); TS_TOC(tl, 4); if (!go) break; }
     if (t >= a.T) continue;
     const long long es = (long long)t * B + env;
-    if (!tile_done)
-      tile_done = step_round(tl, S, v, q, qd, u, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD);
+    {
+      TS_TIC2(tl);
+      double ge[TS_MAXN];
+      double cole[TS_NC(Tile::LPE)][TS_MAXN];
+#ifdef TS_COOP_CONTACTS
+      step_eval(tl, S, v, q, qd, u, WD, ge, cole);       // whole-warp votes inside: every tile evaluates
+      if (!tile_done) tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, ge, cole);
+#else
+      if (!tile_done) {
+        step_eval(tl, S, v, q, qd, u, WD, ge, cole);
+        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, ge, cole);
+      }
+#endif
+      TS_TOC2(tl, 5);
+    }
     if (!tl.warp_all(tile_done)) continue;
+    TS_TIC(tl);
     // ---- the step is complete for every tile of this warp
     if (active) {
       int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
@@ -1413,6 +1533,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
       step_begin(S, v, q, qd);
       tile_done = !active;
     }
+    TS_TOC(tl, 6);
   }
   if (active && tl.lane == 0)
     for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = q[i]; a.qd[(long long)env * n + i] = qd[i]; }

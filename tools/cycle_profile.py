@@ -1,0 +1,31 @@
+"""Development probe: clock64 breakdown of the forward kernel (needs a -DTS_PROFILE build of the library,
+pointed to by TSIM_B200_LIB)."""
+import ctypes, os, sys
+import numpy as np, torch
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from bench import make_inputs
+from tactilesimulation_b200.sim import BatchedSim
+g = np.load(os.path.join(ROOT, "tests", "golden", "pusher32x13_episodic_s0.npz"))
+sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=8)
+dev = sim.device
+B, T = 4096, 50
+nthreads = ((B * 8 + 223) // 224) * 224
+prof = torch.zeros((nthreads, 8), dtype=torch.int64, device=dev)
+sim.lib.tsim_debug_set_prof(ctypes.c_void_p(prof.data_ptr()))
+q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
+ut = torch.tensor(u, device=dev)
+for rep in range(3):
+    q, qd = torch.tensor(q0, device=dev), torch.tensor(qd0, device=dev)
+    out = sim.forward(q, qd, ut, T, grad=True)
+    torch.cuda.synchronize()
+p = prof.cpu().numpy().reshape(-1, 28, 8, 8)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
+names = ["kinematics+dyn", "ground", "gp", "inward", "vote wait", "step_round total", "epilogue", "kernel total"]
+tot = p[:, :, 7].astype(float)
+print("blocks", p.shape[0], "kernel cycles: mean %.3g max %.3g (%.2f ms at 1.965 GHz)" % (tot.mean(), tot.max(), tot.max() / 1.965e6))
+for i, nm in enumerate(names):
+    v = p[:, :, i].astype(float)
+    print(f"{nm:18s} mean {v.mean():.4g} ({100 * v.mean() / tot.mean():5.1f}% of kernel)  max-tile {v.max():.4g}")
+# slowest block
+b = int(tot.mean(axis=1).argmax())
+print("slowest block", b, {nm: float(p[b, :, i].mean()) for i, nm in enumerate(names)})

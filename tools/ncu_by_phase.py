@@ -4,7 +4,7 @@ charged to the phase that called them.  Usage: ncu_by_phase.py <src.csv> <lib.so
 import collections, csv, os, re, subprocess, sys, tempfile
 csvp, so, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 PHASES = ["tactile_values", "tactile_vjp", "contact_sets", "mass_column", "lu_solve", "kinematics", "joint_dynamics",
-          "ground_contacts", "gp_contacts", "inward", "eval_columns", "eval_g", "readout_from_work", "step_round",
+          "ground_contacts", "gp_contacts", "inward", "eval_columns", "eval_g", "readout_from_work", "step_eval", "step_post",
           "step_backward", "step_begin", "env_forward", "env_backward", "stage_scene"]
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -48,7 +48,7 @@ for l in sass:
     if m:
         ph = None
         for f in chain:            # chain is innermost -> outermost; keep the outermost phase below the drivers
-            if f in PHASES and f not in ("eval_columns", "eval_g", "step_round", "env_forward", "env_backward", "readout_from_work", "step_backward"):
+            if f in PHASES and f not in ("eval_columns", "eval_g", "step_eval", "step_post", "env_forward", "env_backward", "readout_from_work", "step_backward"):
                 ph = f
         if ph is None:
             for f in chain:
