@@ -459,23 +459,28 @@ HD void gp_point_force(const GpPair<T>& P, const double* xi1, const double* hs, 
   mtv3(P.R2v, yv, xv);
   int ax; double sg;
   cuboid_face(xv, hs, ax, sg);
+  // the face axis is data: select instead of indexing so that every vector stays in registers
+  const bool a0 = (ax == 0), a1 = (ax == 1), a2 = (ax == 2);
+  const double e[3] = {a0 ? sg : 0.0, a1 ? sg : 0.0, a2 ? sg : 0.0};
+  const double hsa = a0 ? hs[0] : (a1 ? hs[1] : hs[2]);
   T ap[3], x[3];
   mv3(P.Q, xi1, ap);                                   // pad point relative to the pad origin, box coordinates
   for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
-  T d = sg * x[ax] - hs[ax];
+  T d = sg * (a0 ? x[0] : (a1 ? x[1] : x[2])) - hsa;
   // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
   T u[3], t3[3];
   cross3(P.w1b, ap, u);
   cross3(P.ph2, x, t3);
   for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
-  T ddot = sg * u[ax];
+  T ddot = sg * (a0 ? u[0] : (a1 ? u[1] : u[2]));
   // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
   T tb[3];
-  double e[3] = {0.0, 0.0, 0.0};
-  e[ax] = sg;
   cross3(P.ph2, e, t3);
   for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
-  tb[ax] = tb[ax] - sg * (sg * tb[ax]);
+  {
+    T c0 = tb[0] - sg * (sg * tb[0]), c1 = tb[1] - sg * (sg * tb[1]), c2 = tb[2] - sg * (sg * tb[2]);
+    tb[0] = a0 ? c0 : tb[0]; tb[1] = a1 ? c1 : tb[1]; tb[2] = a2 ? c2 : tb[2];
+  }
   T s = kn * d - damp * ddot * d;
   T Fb[3];
   for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
@@ -483,7 +488,7 @@ HD void gp_point_force(const GpPair<T>& P, const double* xi1, const double* hs, 
     // the reference uses the norm of the 6-vector wrench on body 1 (:208): n1 = R1^T R2 e = row `ax` of
     // R21 times sg, m1 = xi1 x n1
     T n1[3], m1[3];
-    for (int i = 0; i < 3; ++i) n1[i] = sg * P.Q[3 * ax + i];
+    for (int i = 0; i < 3; ++i) n1[i] = sg * (a0 ? P.Q[i] : (a1 ? P.Q[3 + i] : P.Q[6 + i]));
     cross3(xi1, n1, m1);
     double n6 = 0.0;
     for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
