@@ -700,15 +700,10 @@ HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const d
   }
 }
 
-// residual of the BDF1 step for (q1; q0, qd0)
+// residual of the BDF1 step for q1, given qd1 = (q1 - q0) / h and dl = q1 - q0 - h qd0
 template <class Tile, class T>
-HDN void eval_g(const Tile& tl, const SceneView& S, const T* q1, const T* q0, const T* qd0, const double* u, Work<T>& W,
+HDN void eval_g(const Tile& tl, const SceneView& S, const T* q1, const T* qd1, const T* dl, const double* u, Work<T>& W,
                 T* g) {
-  T qd1[TS_MAXN], dl[TS_MAXN];
-  for (int i = 0; i < S.n; ++i) {
-    qd1[i] = (q1[i] - q0[i]) / S.h;
-    dl[i] = q1[i] - q0[i] - S.h * qd0[i];
-  }
   { TS_TIC(tl); kinematics<T>(S, q1, qd1, dl, W, true); TS_TOC(tl, 0); }
   { TS_TIC(tl); ground_contacts<T>(S, W); TS_TOC(tl, 1); }
   { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
@@ -838,21 +833,30 @@ HD double norm_n(const double* v, int n) {
 // (scene tables: shared memory, work space: local memory).
 template <class Tile>
 HD void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
-                                  const double* qd0, const double* u, int seed, Work<Dual>& W, double* g,
-                                  double (*col)[TS_MAXN]) {
+                     const double* qd0, const double* u, int seed, Work<Dual>& W, double* g,
+                     double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
+  const int n = S.n;
+  // tangents of (q1, qd1, dl) per unit of the seeded variable:  q1: (1, 1/h, 1)   q0: (0, -1/h, -1)   qd0: (0, 0, -h)
+  const double t_q = (seed == 0) ? 1.0 : 0.0;
+  const double t_v = (seed == 0) ? (1.0 - 0.0) / S.h : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
+  const double t_l = (seed == 0) ? 1.0 : ((seed == 1) ? -1.0 : -S.h);
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;
-    Dual xq[TS_MAXN], xq0[TS_MAXN], xqd0[TS_MAXN], gD[TS_MAXN];
-    for (int i = 0; i < S.n; ++i) {
-      xq[i] = mkdual(x[i], (seed == 0 && i == k) ? 1.0 : 0.0);
-      xq0[i] = mkdual(q0[i], (seed == 1 && i == k) ? 1.0 : 0.0);
-      xqd0[i] = mkdual(qd0[i], (seed == 2 && i == k) ? 1.0 : 0.0);
-    }
-    eval_g(tl, S, xq, xq0, xqd0, u, W, gD);
+    Dual xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN], gD[TS_MAXN];
+#pragma unroll
     for (int i = 0; i < TS_MAXN; ++i) {
-      if (i < S.n) { g[i] = gD[i].v; col[c][i] = (k < S.n) ? gD[i].d : 0.0; }
-      else { g[i] = 0.0; col[c][i] = 0.0; }
+      const double xi = (i < n) ? x[i] : 0.0, qi = (i < n) ? q0[i] : 0.0, vi = (i < n) ? qd0[i] : 0.0;
+      const double on = (i == k) ? 1.0 : 0.0;
+      xq[i] = mkdual(xi, on * t_q);
+      xv[i] = mkdual((xi - qi) / S.h, on * t_v);
+      xl[i] = mkdual(xi - qi - S.h * vi, on * t_l);
+    }
+    eval_g(tl, S, xq, xv, xl, u, W, gD);
+#pragma unroll
+    for (int i = 0; i < TS_MAXN; ++i) {
+      g[i] = (i < n) ? gD[i].v : 0.0;
+      col[c][i] = (i < n && k < n) ? gD[i].d : 0.0;
     }
   }
 }
@@ -1141,13 +1145,14 @@ HDN void tactile_values(const Tile& tl, const SceneView& S, const Work<T>& W, do
     sensor_frames(S, W, sr, sd, F);
     bool anynear = false;
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
+    if (!anynear) {
+      // no candidate body can reach the pad: zero field, written with unit stride across the lanes
+      for (int i = tl.lane; i < 3 * mc; i += Tile::LPE) out[3 * mo + i] = (i % 3 == 2) ? -0.0 : 0.0;
+      if (body_out) for (int m = tl.lane; m < mc; m += Tile::LPE) body_out[mo + m] = -1;
+      continue;
+    }
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
       double* o = out + 3 * (mo + m);
-      if (!anynear) {
-        o[0] = 0.0; o[1] = 0.0; o[2] = -0.0;
-        if (body_out) body_out[mo + m] = -1;
-        continue;
-      }
       const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
       MarkerHit H;
       double F1[3];
