@@ -57,6 +57,12 @@ struct DevTile {
     __syncthreads();
 #endif
   }
+  // the lanes of a tile share the value half of their work space (WorkSplit): converge + order memory
+  HD void tile_sync() const {
+#ifdef __CUDA_ARCH__
+    __syncwarp(mask);
+#endif
+  }
   // block-wide vote; with TS_NO_SYNC_EVALS (A/B builds) every warp runs free
   HD bool cta_any(bool p) const {
 #if defined(__CUDA_ARCH__) && defined(TS_SYNC_EVALS)
@@ -128,7 +134,7 @@ struct DevTile {
 #define TS_BLOCK 224
 #endif
 
-// stage the scene blob in shared memory (ints first, then doubles, 8-byte aligned)
+// stage the scene blob in shared memory (doubles first, then ints, 8-byte aligned)
 __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni, const double* db, int nd,
                                             unsigned char* smem) {
   double* sd = (double*)smem;
@@ -137,6 +143,23 @@ __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni,
   for (int i = threadIdx.x; i < ni; i += blockDim.x) si[i] = ib[i];
   __syncthreads();
   scene_view_init(S, si, sd);
+}
+
+// Shared memory after the scene: one region per tile holding the VALUE half of the Dual work space
+// (identical in every lane of the tile) and the sensor/candidate frames.  The stride is odd (in
+// doubles) so that the tiles of a warp, which read the same offset of their own region, hit
+// different banks.
+__host__ __device__ inline int tile_region_doubles(int nmj) {
+  return (nmj * WK_REC + (int)((sizeof(Frames) + 7) / 8)) | 1;
+}
+__host__ __device__ inline size_t scene_bytes(int ni, int nd) {
+  return (((size_t)nd * sizeof(double) + (size_t)ni * sizeof(int)) + 15) & ~(size_t)15;
+}
+template <int LPE>
+__device__ __forceinline__ void bind_work(WorkSplit& W, const SceneView& S, int ni, int nd, unsigned char* smem) {
+  double* base = (double*)(smem + scene_bytes(ni, nd)) + (size_t)(threadIdx.x / LPE) * tile_region_doubles(S.nj);
+  W.sv = base;
+  W.fr = (Frames*)(base + S.nj * WK_REC);
 }
 
 template <int LPE>
@@ -155,12 +178,13 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   DevTile<LPE> tl = make_tile<LPE>();
-  __align__(16) unsigned char wb[sizeof(Work<Dual>)];
+  WorkSplit WD;
+  bind_work<LPE>(WD, S, ni, nd, smem);
 #ifdef TS_PROFILE
   for (int i = 0; i < 8; ++i) tl.acc[i] = 0;
   const long long t_begin = clock64();
 #endif
-  env_forward(tl, S, a, env, wb);     // tiles past the batch stay in the block-wide votes
+  env_forward(tl, S, a, env, WD);     // tiles past the batch stay in the block-wide votes
 #ifdef TS_PROFILE
   tl.acc[7] = clock64() - t_begin;
   if (g_prof) for (int i = 0; i < 8; ++i) g_prof[(long long)(blockIdx.x * blockDim.x + threadIdx.x) * 8 + i] = tl.acc[i];
@@ -175,8 +199,9 @@ __global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, co
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= a.B) return;
   DevTile<LPE> tl = make_tile<LPE>();
-  __align__(16) unsigned char wb[sizeof(Work<Dual>)];
-  env_backward(tl, S, a, env, wb);
+  WorkSplit WD;
+  bind_work<LPE>(WD, S, ni, nd, smem);
+  env_backward(tl, S, a, env, WD);
 }
 
 template <int LPE>
@@ -189,7 +214,7 @@ __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= B) return;
   DevTile<LPE> tl = make_tile<LPE>();
-  __align__(16) unsigned char wb[sizeof(Work<double>)];
+  Work<double> wb;
   double ql[TS_MAXN], qdl[TS_MAXN];
   for (int i = 0; i < TS_MAXN; ++i) {
     ql[i] = (i < S.n) ? q[(long long)env * S.n + i] : 0.0;
@@ -208,6 +233,7 @@ struct tsim_scene {
   double* d_db;
   int ni, nd;
   int lanes;
+  int nmj;                 // moving joints of the lowered scene
   int sizes[TSIM_N_SIZES];
 };
 
@@ -219,11 +245,21 @@ static int fail(const std::string& m) { g_err = m; return 1; }
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));               \
   } while (0)
 
-static size_t scene_smem(const tsim_scene* s) { return (size_t)s->nd * sizeof(double) + (size_t)s->ni * sizeof(int) + 16; }
+// scene tables + one work-space region per tile of the block
+static size_t scene_smem(const tsim_scene* s) {
+  return scene_bytes(s->ni, s->nd) + (size_t)(TS_BLOCK / s->lanes) * tile_region_doubles(s->nmj) * sizeof(double);
+}
 
 template <class K>
 static int prep(K kern, size_t smem) {
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one block per SM: ask for no more shared memory than the block uses, the rest of the 256 KB is L1
+  // for the per-lane tangents (local memory)
+#ifndef TS_NO_CARVEOUT
+  int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
+  if (pct > 100) pct = 100;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+#endif
   return 0;
 }
 
@@ -250,6 +286,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->ni = (int)kt.ib.size();
   s->nd = (int)kt.db.size();
   s->lanes = 8;
+  s->nmj = kt.ib[KI_NMJ];
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
   CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));

@@ -144,17 +144,57 @@ HD void inertia_mul(const double* jd, const T* tw, T* hm) {
 // ------------------------------------------------------------------ per-lane work space
 // One record per MOVING joint, world frame: pose, twist V = J qd, X = J dl + h^2 Jdot qd and the
 // wrench accumulator of the joint's own bodies (summed over the subtree by the inward sweep).
-template <class T> struct Work {
-  T R0[TS_MAXJ][9], p0[TS_MAXJ][3];
-  T V[TS_MAXJ][6], X[TS_MAXJ][6];
-  T Wa[TS_MAXJ][6];
+// Two storage policies behind the same accessors:
+//   Work<T>    plain per-lane arrays (host harness, value-only readout kernel);
+//   WorkSplit  Dual numbers on the GPU: the VALUES are identical in every lane of a tile (same code on the
+//              same inputs), so they are kept ONCE per tile in shared memory; only the tangents are per-lane
+//              (local memory).  This halves the local-memory working set, which is what spilled out of L2.
+enum { WK_R0 = 0, WK_P0 = 9, WK_V = 12, WK_X = 18, WK_WA = 24, WK_REC = 30 };
+
+// world frames of the sensor body (slot 0) and its candidate bodies (slots 1..ncand), values only
+struct Frames {
+  double R[1 + TS_MAXCAND][9], p[1 + TS_MAXCAND][3], ph[1 + TS_MAXCAND][6];
+  double R21[TS_MAXCAND][9], r21[TS_MAXCAND][3];   // pad frame in each candidate's frame (fast classification)
+  bool near[1 + TS_MAXCAND];   // candidate may touch a marker (bounding-sphere test)
 };
+
+template <class T> struct Work {
+  typedef T Scalar;
+  T rec[TS_MAXJ][WK_REC];
+  Frames fr;
+  HD T get(int j, int o) const { return rec[j][o]; }
+  HD double getv(int j, int o) const { return val(rec[j][o]); }
+  HD void put(int j, int o, const T& x) { rec[j][o] = x; }
+  HD Frames& frames() { return fr; }
+};
+
+struct WorkSplit {
+  typedef Dual Scalar;
+  double* sv;                      // [nj][WK_REC] values, shared by the lanes of the tile
+  Frames* fr;                      // per tile, shared memory
+  double dt[TS_MAXJ][WK_REC];      // tangents of this lane
+  HD Dual get(int j, int o) const { return mkdual(sv[j * WK_REC + o], dt[j][o]); }
+  HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
+  HD void put(int j, int o, const Dual& x) { sv[j * WK_REC + o] = x.v; dt[j][o] = x.d; }
+  HD Frames& frames() { return *fr; }
+};
+template <class WK, class T> HD void wk_ld(const WK& W, int j, int o, int n, T* out) {
+  for (int i = 0; i < n; ++i) out[i] = W.get(j, o + i);
+}
+template <class WK> HD void wk_ldv(const WK& W, int j, int o, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = W.getv(j, o + i);
+}
+template <class WK, class T> HD void wk_st(WK& W, int j, int o, int n, const T* in) {
+  for (int i = 0; i < n; ++i) W.put(j, o + i, in[i]);
+}
 
 // Outward sweep over the moving joints.  dyn=false computes poses and twists only.
 // Joint models: DH/Joint/JointRevolute.cpp:38-69, JointPrismatic.cpp:22-45, JointPlanar.cpp:7-33,
 // JointTranslational.cpp:9-40; recursion DH/Joint/Joint.cpp:119-165.
-template <class T>
-HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Work<T>& W, bool dyn) {
+template <class WK>
+HDN void kinematics(const SceneView& S, const typename WK::Scalar* q, const typename WK::Scalar* qd,
+                    const typename WK::Scalar* dl, WK& W, bool dyn) {
+  typedef typename WK::Scalar T;
   const double h2 = S.h * S.h;
   for (int j = 0; j < S.nj; ++j) {
     const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
@@ -171,16 +211,20 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
       for (int i = 0; i < 3; ++i) pa[i] = pc[i];
       for (int i = 0; i < 6; ++i) { Vp[i] = 0.0; Xp[i] = 0.0; }
     } else {
-      mm3(W.R0[par], Rc, Ra);
-      mv3(W.R0[par], pc, pa);
-      for (int i = 0; i < 3; ++i) pa[i] = pa[i] + W.p0[par][i];
-      for (int i = 0; i < 6; ++i) { Vp[i] = W.V[par][i]; if (dyn) Xp[i] = W.X[par][i]; else Xp[i] = 0.0; }
+      T Rp[9], pp[3];
+      wk_ld(W, par, WK_R0, 9, Rp);
+      wk_ld(W, par, WK_P0, 3, pp);
+      mm3(Rp, Rc, Ra);
+      mv3(Rp, pc, pa);
+      for (int i = 0; i < 3; ++i) pa[i] = pa[i] + pp[i];
+      wk_ld(W, par, WK_V, 6, Vp);
+      if (dyn) wk_ld(W, par, WK_X, 6, Xp);
+      else for (int i = 0; i < 6; ++i) Xp[i] = 0.0;
     }
     // world screw sums  sq = sum_d S_d qd_d,  sl = sum_d S_d dl_d
     T sq[6], sl[6];
     for (int i = 0; i < 6; ++i) { sq[i] = 0.0; sl[i] = 0.0; }
-    T* R0 = W.R0[j];
-    T* p0 = W.p0[j];
+    T R0[9], p0[3];
     if (jt == TS_JT_REVOLUTE) {          // Q = exp([axis] q)
       T s, c;
       dsincos(q[qo], s, c);
@@ -219,8 +263,11 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
       mv3(Ra, vq, sq + 3);               // pure translations: screw = (0, Ra axis)
       if (dyn) mv3(Ra, vl, sl + 3);
     }
+    wk_st(W, j, WK_R0, 9, R0);
+    wk_st(W, j, WK_P0, 3, p0);
     T Vl[6];
-    for (int i = 0; i < 6; ++i) { Vl[i] = Vp[i] + sq[i]; W.V[j][i] = Vl[i]; }
+    for (int i = 0; i < 6; ++i) Vl[i] = Vp[i] + sq[i];
+    wk_st(W, j, WK_V, 6, Vl);
     if (dyn) {
       // X_j = X_p + S dl + h^2 ad(V_p)(S qd): the joint axes are fixed in the parent body
       T c0[3], c1v[3], c2[3], Xl[6];
@@ -231,7 +278,7 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
         Xl[i] = Xp[i] + sl[i] + h2 * c0[i];
         Xl[3 + i] = Xp[3 + i] + sl[3 + i] + h2 * (c1v[i] + c2[i]);
       }
-      for (int i = 0; i < 6; ++i) W.X[j][i] = Xl[i];
+      wk_st(W, j, WK_X, 6, Xl);
       // composite rigid body of this joint, while its frame is still in registers:
       // a_j = I chi_j - h^2 (coriolis + gravity) in the joint frame (per reference body:
       // DH/Body/Body.cpp:234-247; summed by linearity of the spatial inertia), pushed to the world frame
@@ -256,17 +303,17 @@ HDN void kinematics(const SceneView& S, const T* q, const T* qd, const T* dl, Wo
         mv3(R0, a + 3, f);
         mv3(R0, a, t);
         cross3(p0, f, pf);
-        for (int i = 0; i < 3; ++i) { W.Wa[j][i] = t[i] + pf[i]; W.Wa[j][3 + i] = f[i]; }
+        for (int i = 0; i < 3; ++i) { W.put(j, WK_WA + i, t[i] + pf[i]); W.put(j, WK_WA + 3 + i, f[i]); }
       } else {
-        for (int i = 0; i < 6; ++i) W.Wa[j][i] = 0.0;
+        for (int i = 0; i < 6; ++i) W.put(j, WK_WA + i, T(0.0));
       }
     }
   }
 }
 
 // pose of body b (and its twist in body coordinates) from the work space
-template <class T>
-HD void body_frame(const SceneView& S, const Work<T>& W, int b, T* R, T* p, T* ph) {
+template <class WK, class T>
+HD void body_frame(const SceneView& S, const WK& W, int b, T* R, T* p, T* ph) {
   const int j = S.ib[S.o_body + b * KB_ISTRIDE];
   const double* bd = S.db + S.d_body + b * KB_DSTRIDE;
   if (j < 0) {
@@ -275,14 +322,21 @@ HD void body_frame(const SceneView& S, const Work<T>& W, int b, T* R, T* p, T* p
     if (ph) for (int i = 0; i < 6; ++i) ph[i] = 0.0;
     return;
   }
-  mm3(W.R0[j], bd + KB_RMI, R);
-  mv3(W.R0[j], bd + KB_PMI, p);
-  for (int i = 0; i < 3; ++i) p[i] = p[i] + W.p0[j][i];
-  if (ph) twist_to_frame(R, p, W.V[j], ph);
+  T R0[9], p0[3];
+  wk_ld(W, j, WK_R0, 9, R0);
+  wk_ld(W, j, WK_P0, 3, p0);
+  mm3(R0, bd + KB_RMI, R);
+  mv3(R0, bd + KB_PMI, p);
+  for (int i = 0; i < 3; ++i) p[i] = p[i] + p0[i];
+  if (ph) {
+    T V[6];
+    wk_ld(W, j, WK_V, 6, V);
+    twist_to_frame(R, p, V, ph);
+  }
 }
 // value-only variant (readouts run on the values of whatever scalar the work space holds)
-template <class T>
-HD void body_frame_v(const SceneView& S, const Work<T>& W, int b, double* R, double* p, double* ph) {
+template <class WK>
+HD void body_frame_v(const SceneView& S, const WK& W, int b, double* R, double* p, double* ph) {
   const int j = S.ib[S.o_body + b * KB_ISTRIDE];
   const double* bd = S.db + S.d_body + b * KB_DSTRIDE;
   if (j < 0) {
@@ -292,9 +346,9 @@ HD void body_frame_v(const SceneView& S, const Work<T>& W, int b, double* R, dou
     return;
   }
   double R0[9], p0[3], V[6];
-  for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
-  for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
-  for (int i = 0; i < 6; ++i) V[i] = val(W.V[j][i]);
+  wk_ldv(W, j, WK_R0, 9, R0);
+  wk_ldv(W, j, WK_P0, 3, p0);
+  wk_ldv(W, j, WK_V, 6, V);
   mm3(R0, bd + KB_RMI, R);
   mv3(R0, bd + KB_PMI, p);
   for (int i = 0; i < 3; ++i) p[i] += p0[i];
@@ -303,15 +357,17 @@ HD void body_frame_v(const SceneView& S, const Work<T>& W, int b, double* R, dou
 
 // body-frame wrench (moment; force) of the body at (R,p) -> world wrench about the origin, added
 // (times scale) to the accumulator of moving joint j
-template <class T>
-HD void push_wrench(Work<T>& W, int j, const T* R, const T* p, const T* wr, double scale) {
+template <class WK, class T>
+HD void push_wrench(WK& W, int j, const T* R, const T* p, const T* wr, double scale) {
   if (j < 0) return;
   T f[3], t[3], pf[3];
   mv3(R, wr + 3, f);
   mv3(R, wr, t);
   cross3(p, f, pf);
-  T* A = W.Wa[j];
-  for (int i = 0; i < 3; ++i) { A[i] = A[i] + scale * (t[i] + pf[i]); A[3 + i] = A[3 + i] + scale * f[i]; }
+  for (int i = 0; i < 3; ++i) {
+    W.put(j, WK_WA + i, W.get(j, WK_WA + i) + scale * (t[i] + pf[i]));
+    W.put(j, WK_WA + 3 + i, W.get(j, WK_WA + 3 + i) + scale * f[i]);
+  }
 }
 
 // ------------------------------------------------------------------ cuboid SDF face pick
@@ -382,8 +438,9 @@ template <class T> HD void vals9(const T* a, double* o) { for (int i = 0; i < 9;
 // ------------------------------------------------------------------ contact forces
 // ground plane vs sampled body points: DH/Force/ForceGroundContact.cpp:105-147,
 // detection d <= 0: DH/CollisionDetection/CollisionDetection.cpp:13-42
-template <class T>
-HDN void ground_contacts(const SceneView& S, Work<T>& W) {
+template <class WK>
+HDN void ground_contacts(const SceneView& S, WK& W) {
+  typedef typename WK::Scalar T;
   const double h2 = S.h * S.h;
   for (int gi = 0; gi < S.nground; ++gi) {
     const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
@@ -525,8 +582,9 @@ template <class Tile> HD Dual tiles_sum(const Tile& tl, Dual v) { return mkdual(
 // extra path): when only few tiles of the warp are in contact, their active points are dealt to ALL
 // tiles of the warp and the partial wrenches summed back by shuffles; the function must then be
 // reached by every lane of the warp together.
-template <class Tile, class T>
-HDN void gp_contacts(const Tile& tl, const SceneView& S, Work<T>& W) {
+template <class Tile, class WK>
+HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
+  typedef typename WK::Scalar T;
   const int L = Tile::LPE;
   const int TPW = Tile::TPW;
   const double h2 = S.h * S.h;
@@ -661,23 +719,28 @@ HD double motor_force(double u, double cmin, double cmax) {
 }
 
 // Inward sweep: g = S^T (subtree wrench) - h^2 (joint damping + limit springs + motors)
-template <class T>
-HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const double* u, T* g) {
+template <class WK>
+HDN void inward(const SceneView& S, WK& W, const typename WK::Scalar* q, const typename WK::Scalar* qd, const double* u,
+                typename WK::Scalar* g) {
+  typedef typename WK::Scalar T;
   const double h2 = S.h * S.h;
   for (int j = S.nj - 1; j >= 0; --j) {
     const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     const int jt = ji[0], par = ji[1], qo = ji[2], nd = ji[3];
-    const T* A = W.Wa[j];
+    T A[6], R0[9], p0[3];
+    wk_ld(W, j, WK_WA, 6, A);
+    wk_ld(W, j, WK_R0, 9, R0);
+    wk_ld(W, j, WK_P0, 3, p0);
     const double* a0 = jd + KJ_AX0;
     const double* a1 = jd + KJ_AX1;
     T fj[3];
-    mtv3(W.R0[j], A + 3, fj);            // force in joint coordinates
+    mtv3(R0, A + 3, fj);                 // force in joint coordinates
     if (jt == TS_JT_REVOLUTE) {
       T pf[3], t[3], nj3[3];
-      cross3(W.p0[j], A + 3, pf);        // moment about the joint origin
+      cross3(p0, A + 3, pf);             // moment about the joint origin
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
-      mtv3(W.R0[j], t, nj3);
+      mtv3(R0, t, nj3);
       g[qo] = dot3(a0, nj3);
     } else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, fj);
     else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, fj); g[qo + 1] = dot3(a1, fj); }
@@ -690,7 +753,7 @@ HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const d
       if (val(q[qo + i]) > hi) fr = fr + lk * (hi - q[qo + i]);
       g[qo + i] = g[qo + i] - h2 * fr;
     }
-    if (par >= 0) for (int i = 0; i < 6; ++i) W.Wa[par][i] = W.Wa[par][i] + A[i];
+    if (par >= 0) for (int i = 0; i < 6; ++i) W.put(par, WK_WA + i, W.get(par, WK_WA + i) + A[i]);
   }
   for (int ai = 0; ai < S.nact; ++ai) {
     const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
@@ -701,13 +764,14 @@ HDN void inward(const SceneView& S, Work<T>& W, const T* q, const T* qd, const d
 }
 
 // residual of the BDF1 step for q1, given qd1 = (q1 - q0) / h and dl = q1 - q0 - h qd0
-template <class Tile, class T>
-HDN void eval_g(const Tile& tl, const SceneView& S, const T* q1, const T* qd1, const T* dl, const double* u, Work<T>& W,
-                T* g) {
-  { TS_TIC(tl); kinematics<T>(S, q1, qd1, dl, W, true); TS_TOC(tl, 0); }
-  { TS_TIC(tl); ground_contacts<T>(S, W); TS_TOC(tl, 1); }
+template <class Tile, class WK>
+HDN void eval_g(const Tile& tl, const SceneView& S, const typename WK::Scalar* q1, const typename WK::Scalar* qd1,
+                const typename WK::Scalar* dl, const double* u, WK& W, typename WK::Scalar* g) {
+  tl.tile_sync();          // the lanes of a tile share the value half of the work space (WorkSplit)
+  { TS_TIC(tl); kinematics(S, q1, qd1, dl, W, true); TS_TOC(tl, 0); }
+  { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
   { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
-  { TS_TIC(tl); inward<T>(S, W, q1, qd1, u, g); TS_TOC(tl, 3); }
+  { TS_TIC(tl); inward(S, W, q1, qd1, u, g); TS_TOC(tl, 3); }
 }
 
 // ------------------------------------------------------------------ tile policies
@@ -720,6 +784,7 @@ struct HostTile {
   HD double sum(double v) const { return v; }
   HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
   HD void cta_sync() const {}
+  HD void tile_sync() const {}
   HD bool cta_any(bool p) const { return p; }
   HD bool warp_all(bool p) const { return p; }
   // whole-warp helpers (one tile per "warp" on the host)
@@ -831,9 +896,9 @@ HD double norm_n(const double* v, int n) {
 // dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  step_forward calls it from exactly ONE place, so the
 // residual code exists once per kernel and everything it touches keeps its address space
 // (scene tables: shared memory, work space: local memory).
-template <class Tile>
+template <class Tile, class WK>
 HD void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
-                     const double* qd0, const double* u, int seed, Work<Dual>& W, double* g,
+                     const double* qd0, const double* u, int seed, WK& W, double* g,
                      double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
@@ -863,8 +928,8 @@ HD void eval_columns(const Tile& tl, const SceneView& S, const double* x, const 
 
 // Column k of the mass matrix M = J^T Mm J at the poses held in W (values), value arithmetic only:
 // psi = S_k on every joint of the subtree of dof k's joint, a_i = I psi_i, projected inward.
-template <class T>
-HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) {
+template <class WK>
+HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
   for (int i = 0; i < TS_MAXN; ++i) Mcol[i] = 0.0;
   if (k >= S.n) return;
   // joint and world screw of dof k
@@ -876,8 +941,8 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
     jk = j;
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     double R0[9], p0[3];
-    for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
-    for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
+    wk_ldv(W, j, WK_R0, 9, R0);
+    wk_ldv(W, j, WK_P0, 3, p0);
     const int jt = ji[0], loc = k - ji[2];
     if (jt == TS_JT_REVOLUTE) {
       mv3(R0, jd + KJ_AX0, Sk);            // R0 a = Ra a for a rotation about a
@@ -894,8 +959,8 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
     if (!ji[5] || !((ji[4] >> jk) & 1)) continue;      // massless, or not in the subtree of jk
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     double R[9], p[3], ps[6], a[6];
-    for (int i = 0; i < 9; ++i) R[i] = val(W.R0[j][i]);
-    for (int i = 0; i < 3; ++i) p[i] = val(W.p0[j][i]);
+    wk_ldv(W, j, WK_R0, 9, R);
+    wk_ldv(W, j, WK_P0, 3, p);
     twist_to_frame(R, p, Sk, ps);
     inertia_mul(jd, ps, a);
     double f[3], t[3], pf[3];
@@ -909,8 +974,8 @@ HDN void mass_column(const SceneView& S, const Work<T>& W, int k, double* Mcol) 
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
     const int jt = ji[0], par = ji[1], qo = ji[2];
     double R0[9], p0[3], fj[3];
-    for (int i = 0; i < 9; ++i) R0[i] = val(W.R0[j][i]);
-    for (int i = 0; i < 3; ++i) p0[i] = val(W.p0[j][i]);
+    wk_ldv(W, j, WK_R0, 9, R0);
+    wk_ldv(W, j, WK_P0, 3, p0);
     const double* A = Wm[j];
     mtv3(R0, A + 3, fj);
     if (jt == TS_JT_REVOLUTE) {
@@ -954,16 +1019,16 @@ HD void step_begin(const SceneView& S, StepVars& v, const double* q, const doubl
 // (g, H) and -- when converged -- the tape's H.
 // step_eval is the evaluation (every tile of a warp runs it together, also tiles whose step is already
 // complete: the residual code votes and shuffles across the warp); step_post is the bookkeeping.
-template <class Tile>
+template <class Tile, class WK>
 HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, const double* q, const double* qd,
-                  const double* u, Work<Dual>& WD, double* ge, double (*cole)[TS_MAXN]) {
+                  const double* u, WK& WD, double* ge, double (*cole)[TS_MAXN]) {
   double xe[TS_MAXN];
   for (int i = 0; i < TS_MAXN; ++i) xe[i] = (v.phase == 1) ? v.xn[i] : v.x[i];
   eval_columns(tl, S, xe, q, qd, u, v.phase == 3 ? 1 : 0, WD, ge, cole);
 }
 
-template <class Tile>
-HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape, Work<Dual>& WD, double* ge,
+template <class Tile, class WK>
+HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape, WK& WD, double* ge,
                   double (*cole)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
@@ -1035,23 +1100,19 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
 
 // ------------------------------------------------------------------ readouts at a state
 // end-effector positions (DH/EndEffector/EndEffector.cpp:31-36)
-template <class T>
-HD void variable_of(const SceneView& S, const Work<T>& W, int e, T* out) {
+template <class WK, class T>
+HD void variable_of(const SceneView& S, const WK& W, int e, T* out) {
   const int j = S.ib[S.o_ee + e * KE_ISTRIDE];
   const double* pos = S.db + S.d_ee + e * KE_DSTRIDE;
   if (j < 0) { for (int i = 0; i < 3; ++i) out[i] = pos[i]; return; }
-  mv3(W.R0[j], pos, out);
-  for (int i = 0; i < 3; ++i) out[i] = out[i] + W.p0[j][i];
+  T R0[9];
+  wk_ld(W, j, WK_R0, 9, R0);
+  mv3(R0, pos, out);
+  for (int i = 0; i < 3; ++i) out[i] = out[i] + W.get(j, WK_P0 + i);
 }
 
-// world frames of the sensor body (slot 0) and its candidate bodies (slots 1..ncand), values only
-struct Frames {
-  double R[1 + TS_MAXCAND][9], p[1 + TS_MAXCAND][3], ph[1 + TS_MAXCAND][6];
-  double R21[TS_MAXCAND][9], r21[TS_MAXCAND][3];   // pad frame in each candidate's frame (fast classification)
-  bool near[1 + TS_MAXCAND];   // candidate may touch a marker (bounding-sphere test)
-};
-template <class T>
-HDN void sensor_frames(const SceneView& S, const Work<T>& W, const int* sr, const double* sd, Frames& F) {
+template <class WK>
+HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const double* sd, Frames& F) {
   const int nc = sr[3];
   body_frame_v(S, W, sr[0], F.R[0], F.p[0], F.ph[0]);
   F.near[0] = true;
@@ -1135,14 +1196,16 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
 
 // tactile values of this env, markers strided over the tile's lanes.
 // out: [M][3] = (shear . axis0, shear . axis1, normal)      (TactileSensor.cpp:74-81)
-template <class Tile, class T>
-HDN void tactile_values(const Tile& tl, const SceneView& S, const Work<T>& W, double* out, int* body_out) {
+template <class Tile, class WK>
+HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, int* body_out) {
   for (int si = 0; si < S.nsens; ++si) {
     const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
     const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
     const int mo = sr[1], mc = sr[2];
-    Frames F;
+    Frames& F = W.frames();
+    tl.tile_sync();
     sensor_frames(S, W, sr, sd, F);
+    tl.tile_sync();
     bool anynear = false;
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
     if (!anynear) {
@@ -1173,8 +1236,8 @@ struct TacAcc {
 
 // Reverse-mode through marker_force for every marker of this lane's stride.  Returns (tile-wide)
 // whether any marker is in contact; acc is only meaningful then.
-template <class Tile, class T>
-HDN bool tactile_vjp(const Tile& tl, const SceneView& S, const Work<T>& W, const double* wbar, TacAcc* acc) {
+template <class Tile, class WK>
+HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, const double* wbar, TacAcc* acc) {
   for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = 0.0;
   double hits = 0.0;
   for (int si = 0; si < S.nsens; ++si) {
@@ -1182,8 +1245,10 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, const Work<T>& W, const
     const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
     const int mo = sr[1], mc = sr[2];
     const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
-    Frames F;
+    Frames& F = W.frames();
+    tl.tile_sync();
     sensor_frames(S, W, sr, sd, F);
+    tl.tile_sync();
     bool anynear = false;
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
     if (!anynear) continue;
@@ -1281,11 +1346,11 @@ HD void jac_col(const Dual* R, const Dual* p, double* J) {
 //   pendA' = pendB + (G0 + G1/h)^T z_k + (1/h) dtac_dqdot^T w ;  pendB' = -(G1/h)^T z_k
 // out_g0z / out_g1z (optional, distributed) expose G0^T z (+ pending terms) and G1^T z for the
 // q0 / qdot0 gradients of the first step.
-template <class Tile>
+template <class Tile, class WK>
 HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, const double* qdk, const double* uk,
                        const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
                        double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
-                       void* workbuf) {
+                       WK& WD) {
   const int L = Tile::LPE;
   const int n = S.n;
   double y[TS_NC(L)], cterm[TS_NC(L)];
@@ -1299,19 +1364,19 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
   bool have_tac = dtac_cot != 0 && S.nmark > 0;
   if (have_var || have_tac) {
     TacAcc acc[TS_MAXCAND];
-    Work<Dual>& WD = *(Work<Dual>*)workbuf;
     for (int c = 0; c < TS_NC(L); ++c) {
       const int k = tl.lane + c * L;
       Dual xq[TS_MAXN], xqd[TS_MAXN];
       for (int i = 0; i < n; ++i) { xq[i] = mkdual(qk[i], (i == k) ? 1.0 : 0.0); xqd[i] = mkdual(qdk[i], 0.0); }
-      kinematics<Dual>(S, xq, xqd, (const Dual*)0, WD, false);
+      tl.tile_sync();
+      kinematics(S, xq, xqd, (const Dual*)0, WD, false);
       // the values of the Dual work space are the kinematics of the state: the marker pass reads them
       if (c == 0 && have_tac) have_tac = tactile_vjp(tl, S, WD, dtac_cot, acc);
       double yk = 0.0, ck = 0.0;
       if (have_var) {
         for (int e = 0; e < S.nee; ++e) {
           Dual v[3];
-          variable_of<Dual>(S, WD, e, v);
+          variable_of(S, WD, e, v);
           yk += v[0].d * dvar_cot[3 * e] + v[1].d * dvar_cot[3 * e + 1] + v[2].d * dvar_cot[3 * e + 2];
         }
       }
@@ -1401,8 +1466,8 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
 
 // ------------------------------------------------------------------ contact index sets (diagnostic outputs)
 // word 0: ground force 0, points 0..31; words 1..3: general-primitive force 0, points 0..95.
-template <class T>
-HDN void contact_sets(const SceneView& S, const Work<T>& W, unsigned* m4) {
+template <class WK>
+HDN void contact_sets(const SceneView& S, const WK& W, unsigned* m4) {
   m4[0] = m4[1] = m4[2] = m4[3] = 0u;
   double R1[9], p1[3], R2[9], p2[3], ph[6];
   if (S.nground > 0) {
@@ -1449,13 +1514,14 @@ struct FwdArgs {
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
-template <class Tile, class T>
-HDN void readout_from_work(const Tile& tl, const SceneView& S, const Work<T>& W, double* var_o, double* tac_o,
+template <class Tile, class WK>
+HDN void readout_from_work(const Tile& tl, const SceneView& S, WK& W, double* var_o, double* tac_o,
                            int* mb_o, unsigned* cm_o) {
+  typedef typename WK::Scalar T;
   if (var_o && tl.lane == 0)
     for (int e = 0; e < S.nee; ++e) {
       T v[3];
-      variable_of<T>(S, W, e, v);
+      variable_of(S, W, e, v);
       for (int i = 0; i < 3; ++i) var_o[3 * e + i] = val(v[i]);
     }
   if (tac_o) tactile_values(tl, S, W, tac_o, mb_o);
@@ -1463,11 +1529,10 @@ HDN void readout_from_work(const Tile& tl, const SceneView& S, const Work<T>& W,
 }
 
 // readouts of a given state (q,qd)
-template <class Tile>
+template <class Tile, class WK>
 HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const double* qd, double* var_o,
-                     double* tac_o, int* mb_o, unsigned* cm_o, void* wb) {
-  Work<double>& WS = *(Work<double>*)wb;
-  kinematics<double>(S, q, qd, (const double*)0, WS, false);
+                     double* tac_o, int* mb_o, unsigned* cm_o, WK& WS) {
+  kinematics(S, q, qd, (const double*)0, WS, false);
   readout_from_work(tl, S, WS, var_o, tac_o, mb_o, cm_o);
 }
 
@@ -1476,12 +1541,11 @@ HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const 
 // the whole block streams through the residual code at the same time -- the kernel is bound by
 // instruction fetch otherwise -- while a warp whose environments need extra Newton rounds delays
 // only itself, not the block.
-template <class Tile>
-HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env_, void* wb) {
+template <class Tile, class WK>
+HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int env_, WK& WD) {
   const int n = S.n, nu = S.nu, B = a.B;
   const bool active = env_ < B;          // surplus tiles of the last block only keep the votes balanced
   const int env = active ? env_ : B - 1;
-  Work<Dual>& WD = *(Work<Dual>*)wb;
   double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
   for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   StepVars v;
@@ -1562,8 +1626,8 @@ struct BwdArgs {
   double* df_dq0; double* df_dqdot0;             // [B,n] or null: MINUS the adjoint terms of step 0
 };
 
-template <class Tile>
-HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int env, void* wb) {
+template <class Tile, class WK>
+HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int env, WK& WD) {
   const int L = Tile::LPE;
   const int n = S.n, nu = S.nu, B = a.B;
   double pA[TS_NC(L)], pB[TS_NC(L)], g0z[TS_NC(L)], g1z[TS_NC(L)];
@@ -1585,7 +1649,7 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
                   r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
                   r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
                   r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,
-                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, wb);
+                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, WD);
   }
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;

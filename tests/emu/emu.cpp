@@ -23,9 +23,9 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
   a.status = status; a.cmask = cmask; a.marker_body = marker_body;
-  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  std::vector<Work<Dual> > wb(1);
   HostTile tl;
-  for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb.data());
+  for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb[0]);
   return 0;
 }
 
@@ -41,9 +41,9 @@ int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, 
   a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_stride; a.tape = tape;
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
-  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  std::vector<Work<Dual> > wb(1);
   HostTile tl;
-  for (int env = 0; env < B; ++env) env_backward(tl, S, a, env, wb.data());
+  for (int env = 0; env < B; ++env) env_backward(tl, S, a, env, wb[0]);
   return 0;
 }
 
@@ -53,12 +53,12 @@ int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double
   if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return 1;
   SceneView S;
   scene_view_init(S, kt.ib.data(), kt.db.data());
-  std::vector<unsigned char> wb(sizeof(Work<Dual>));
+  std::vector<Work<double> > wb(1);
   HostTile tl;
   for (int env = 0; env < B; ++env)
     env_readout(tl, S, q + (long long)env * S.n, qd + (long long)env * S.n,
                 var_out ? var_out + (long long)env * 3 * S.nee : 0, tac_out ? tac_out + (long long)env * 3 * S.nmark : 0,
-                marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * 4 : 0, wb.data());
+                marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * 4 : 0, wb[0]);
   return 0;
 }
 }
