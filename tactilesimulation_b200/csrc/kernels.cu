@@ -142,7 +142,8 @@ __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni,
   for (int i = threadIdx.x; i < nd; i += blockDim.x) sd[i] = db[i];
   for (int i = threadIdx.x; i < ni; i += blockDim.x) si[i] = ib[i];
   __syncthreads();
-  scene_view_init(S, si, sd);
+  if (threadIdx.x == 0) scene_view_init(S, si, sd);   // S is the block's shared view: registers stay free for the math
+  __syncthreads();
 }
 
 // Shared memory after the scene: one region per tile holding the VALUE half of the Dual work space
@@ -150,7 +151,7 @@ __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni,
 // doubles) so that the tiles of a warp, which read the same offset of their own region, hit
 // different banks.
 __host__ __device__ inline int tile_region_doubles(int nmj) {
-  return (nmj * WK_REC + (int)((sizeof(Frames) + 7) / 8)) | 1;
+  return (nmj * WK_REC + (int)((sizeof(Frames) + 7) / 8) + (int)(sizeof(TileState) / 8)) | 1;
 }
 __host__ __device__ inline size_t scene_bytes(int ni, int nd) {
   return (((size_t)nd * sizeof(double) + (size_t)ni * sizeof(int)) + 15) & ~(size_t)15;
@@ -159,7 +160,8 @@ template <int LPE>
 __device__ __forceinline__ void bind_work(WorkSplit& W, const SceneView& S, int ni, int nd, unsigned char* smem) {
   double* base = (double*)(smem + scene_bytes(ni, nd)) + (size_t)(threadIdx.x / LPE) * tile_region_doubles(S.nj);
   W.sv = base;
-  W.fr = (Frames*)(base + S.nj * WK_REC);
+  W.ts = (TileState*)(base + S.nj * WK_REC);
+  W.fr = (Frames*)(base + S.nj * WK_REC + sizeof(TileState) / 8);
 }
 
 template <int LPE>
@@ -174,7 +176,7 @@ __device__ __forceinline__ DevTile<LPE> make_tile() {
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  SceneView S;
+  __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   DevTile<LPE> tl = make_tile<LPE>();
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  SceneView S;
+  __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= a.B) return;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni
                                                           const double* q, const double* qd, double* var_out,
                                                           double* tac_out, int* marker_body, unsigned* cmask) {
   extern __shared__ __align__(16) unsigned char smem[];
-  SceneView S;
+  __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= B) return;

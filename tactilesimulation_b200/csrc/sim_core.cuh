@@ -158,10 +158,41 @@ struct Frames {
   bool near[1 + TS_MAXCAND];   // candidate may touch a marker (bounding-sphere test)
 };
 
+// Step state that is identical in every lane of a tile (the lanes run the same value arithmetic):
+// kept once per tile (shared memory on the GPU).  Read-modify-write updates go through registers
+// with a tile_sync between the reads and the writes.
+struct TileState {
+  double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];       // state at the start of the step, controls of the step
+  double x[TS_MAXN], xn[TS_MAXN], dx[TS_MAXN];     // Newton iterate, line-search trial, Newton direction
+  double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN];    // inputs (q1, qd1, dl) of the evaluation in flight
+  double g[TS_MAXN];                               // residual of the last evaluation
+};
+
+// inputs (q, qd, dl) of one evaluation: plain arrays ...
+template <class T> struct ArrIn {
+  const T *q_, *qd_, *dl_;
+  HD T q(int i) const { return q_[i]; }
+  HD T qd(int i) const { return qd_[i]; }
+  HD T dl(int i) const { return dl_[i]; }
+};
+// ... or Dual numbers whose values live in the tile state and whose tangent is a unit seed on dof k
+struct SeedIn {
+  const double *xq, *xv, *xl;
+  int k;
+  double tq, tv, tl;
+  HD Dual q(int i) const { return mkdual(xq[i], i == k ? tq : 0.0); }
+  HD Dual qd(int i) const { return mkdual(xv[i], i == k ? tv : 0.0); }
+  HD Dual dl(int i) const { return mkdual(xl[i], i == k ? tl : 0.0); }
+};
+
+static_assert(sizeof(Frames) >= sizeof(double) * TS_MAXN * TS_MAXN, "the frames region doubles as the LU scratch");
 template <class T> struct Work {
   typedef T Scalar;
   T rec[TS_MAXJ][WK_REC];
   Frames fr;
+  TileState ts;
+  HD TileState& state() { return ts; }
+  HD double* scratch() { return (double*)&fr; }      // >= TS_MAXN^2 doubles, free while no readout is in flight
   HD T get(int j, int o) const { return rec[j][o]; }
   HD double getv(int j, int o) const { return val(rec[j][o]); }
   HD void put(int j, int o, const T& x) { rec[j][o] = x; }
@@ -172,6 +203,9 @@ struct WorkSplit {
   typedef Dual Scalar;
   double* sv;                      // [nj][WK_REC] values, shared by the lanes of the tile
   Frames* fr;                      // per tile, shared memory
+  TileState* ts;                   // per tile, shared memory
+  HD TileState& state() { return *ts; }
+  HD double* scratch() { return (double*)fr; }
   double dt[TS_MAXJ][WK_REC];      // tangents of this lane
   HD Dual get(int j, int o) const { return mkdual(sv[j * WK_REC + o], dt[j][o]); }
   HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
@@ -191,9 +225,8 @@ template <class WK, class T> HD void wk_st(WK& W, int j, int o, int n, const T* 
 // Outward sweep over the moving joints.  dyn=false computes poses and twists only.
 // Joint models: DH/Joint/JointRevolute.cpp:38-69, JointPrismatic.cpp:22-45, JointPlanar.cpp:7-33,
 // JointTranslational.cpp:9-40; recursion DH/Joint/Joint.cpp:119-165.
-template <class WK>
-HDN void kinematics(const SceneView& S, const typename WK::Scalar* q, const typename WK::Scalar* qd,
-                    const typename WK::Scalar* dl, WK& W, bool dyn) {
+template <class WK, class In>
+HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
   typedef typename WK::Scalar T;
   const double h2 = S.h * S.h;
   for (int j = 0; j < S.nj; ++j) {
@@ -227,7 +260,7 @@ HDN void kinematics(const SceneView& S, const typename WK::Scalar* q, const type
     T R0[9], p0[3];
     if (jt == TS_JT_REVOLUTE) {          // Q = exp([axis] q)
       T s, c;
-      dsincos(q[qo], s, c);
+      dsincos(in.q(qo), s, c);
       T c1 = 1.0 - c;
       T Rq[9];
       Rq[0] = c + c1 * (a0[0] * a0[0]); Rq[1] = c1 * (a0[0] * a0[1]) - s * a0[2]; Rq[2] = c1 * (a0[0] * a0[2]) + s * a0[1];
@@ -239,23 +272,23 @@ HDN void kinematics(const SceneView& S, const typename WK::Scalar* q, const type
       mv3(Ra, a0, w);                    // world axis; screw = (w, p x w)
       cross3(pa, w, m);
       for (int i = 0; i < 3; ++i) {
-        sq[i] = w[i] * qd[qo]; sq[3 + i] = m[i] * qd[qo];
-        if (dyn) { sl[i] = w[i] * dl[qo]; sl[3 + i] = m[i] * dl[qo]; }
+        sq[i] = w[i] * in.qd(qo); sq[3 + i] = m[i] * in.qd(qo);
+        if (dyn) { sl[i] = w[i] * in.dl(qo); sl[3 + i] = m[i] * in.dl(qo); }
       }
     } else {
       for (int i = 0; i < 9; ++i) R0[i] = Ra[i];
       T pq[3], vq[3], vl[3];
       for (int i = 0; i < 3; ++i) { pq[i] = 0.0; vq[i] = 0.0; vl[i] = 0.0; }
       if (jt == TS_JT_PRISMATIC) {
-        for (int i = 0; i < 3; ++i) { pq[i] = a0[i] * q[qo]; vq[i] = a0[i] * qd[qo]; if (dyn) vl[i] = a0[i] * dl[qo]; }
+        for (int i = 0; i < 3; ++i) { pq[i] = a0[i] * in.q(qo); vq[i] = a0[i] * in.qd(qo); if (dyn) vl[i] = a0[i] * in.dl(qo); }
       } else if (jt == TS_JT_PLANAR) {
         for (int i = 0; i < 3; ++i) {
-          pq[i] = a0[i] * q[qo] + a1[i] * q[qo + 1];
-          vq[i] = a0[i] * qd[qo] + a1[i] * qd[qo + 1];
-          if (dyn) vl[i] = a0[i] * dl[qo] + a1[i] * dl[qo + 1];
+          pq[i] = a0[i] * in.q(qo) + a1[i] * in.q(qo + 1);
+          vq[i] = a0[i] * in.qd(qo) + a1[i] * in.qd(qo + 1);
+          if (dyn) vl[i] = a0[i] * in.dl(qo) + a1[i] * in.dl(qo + 1);
         }
       } else if (jt == TS_JT_TRANSLATIONAL) {
-        for (int i = 0; i < 3; ++i) { pq[i] = q[qo + i]; vq[i] = qd[qo + i]; if (dyn) vl[i] = dl[qo + i]; }
+        for (int i = 0; i < 3; ++i) { pq[i] = in.q(qo + i); vq[i] = in.qd(qo + i); if (dyn) vl[i] = in.dl(qo + i); }
       }
       T t[3];
       mv3(Ra, pq, t);
@@ -719,9 +752,8 @@ HD double motor_force(double u, double cmin, double cmax) {
 }
 
 // Inward sweep: g = S^T (subtree wrench) - h^2 (joint damping + limit springs + motors)
-template <class WK>
-HDN void inward(const SceneView& S, WK& W, const typename WK::Scalar* q, const typename WK::Scalar* qd, const double* u,
-                typename WK::Scalar* g) {
+template <class WK, class In>
+HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typename WK::Scalar* g) {
   typedef typename WK::Scalar T;
   const double h2 = S.h * S.h;
   for (int j = S.nj - 1; j >= 0; --j) {
@@ -748,9 +780,10 @@ HDN void inward(const SceneView& S, WK& W, const typename WK::Scalar* q, const t
     // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
     const double damp = jd[KJ_DAMP], lo = jd[KJ_LIMLO], hi = jd[KJ_LIMHI], lk = jd[KJ_LIMK];
     for (int i = 0; i < nd; ++i) {
-      T fr = -(damp * qd[qo + i]);
-      if (val(q[qo + i]) < lo) fr = fr + lk * (lo - q[qo + i]);
-      if (val(q[qo + i]) > hi) fr = fr + lk * (hi - q[qo + i]);
+      T fr = -(damp * in.qd(qo + i));
+      const T qi = in.q(qo + i);
+      if (val(qi) < lo) fr = fr + lk * (lo - qi);
+      if (val(qi) > hi) fr = fr + lk * (hi - qi);
       g[qo + i] = g[qo + i] - h2 * fr;
     }
     if (par >= 0) for (int i = 0; i < 6; ++i) W.put(par, WK_WA + i, W.get(par, WK_WA + i) + A[i]);
@@ -764,14 +797,12 @@ HDN void inward(const SceneView& S, WK& W, const typename WK::Scalar* q, const t
 }
 
 // residual of the BDF1 step for q1, given qd1 = (q1 - q0) / h and dl = q1 - q0 - h qd0
-template <class Tile, class WK>
-HDN void eval_g(const Tile& tl, const SceneView& S, const typename WK::Scalar* q1, const typename WK::Scalar* qd1,
-                const typename WK::Scalar* dl, const double* u, WK& W, typename WK::Scalar* g) {
-  tl.tile_sync();          // the lanes of a tile share the value half of the work space (WorkSplit)
-  { TS_TIC(tl); kinematics(S, q1, qd1, dl, W, true); TS_TOC(tl, 0); }
+template <class Tile, class WK, class In>
+HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g) {
+  { TS_TIC(tl); kinematics(S, in, W, true); TS_TOC(tl, 0); }
   { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
   { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
-  { TS_TIC(tl); inward(S, W, q1, qd1, u, g); TS_TOC(tl, 3); }
+  { TS_TIC(tl); inward(S, W, in, u, g); TS_TOC(tl, 3); }
 }
 
 // ------------------------------------------------------------------ tile policies
@@ -886,42 +917,73 @@ HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
   for (int i = 0; i < TS_MAXN; ++i) rhs[i] = b[i];
 }
 
+// Row-owner elimination for tiles with one lane per row (LPE >= TS_MAXN): lane i holds row i (a) and
+// b_i; pivot rows travel by shuffles, the solution comes out replicated in x.  Same operations on the
+// same numbers as lu_factor_solve<false> (no row exchanges), at 1/8 of the per-lane work and without
+// the 8x8 register copy.  Returns true (tile-wide) when partial pivoting would have exchanged a row:
+// the caller then runs the replicated pivoting solve instead.
+template <class Tile>
+HD bool lu_rows_solve(const Tile& tl, double* a, double b, double* x) {
+  bool exch = false;
+#pragma unroll
+  for (int j = 0; j < TS_MAXN; ++j) {
+    const double pjj = tl.bcast(a[j], j);
+    const bool below = tl.lane > j;
+    exch = exch || (below && fabs(a[j]) > fabs(pjj));
+    const double l = a[j] / pjj;
+#pragma unroll
+    for (int c = j + 1; c < TS_MAXN; ++c) {
+      const double pjc = tl.bcast(a[c], j);
+      if (below) a[c] -= l * pjc;
+    }
+    const double bj = tl.bcast(b, j);
+    if (below) b -= l * bj;
+  }
+#pragma unroll
+  for (int k = TS_MAXN - 1; k >= 0; --k) {
+    const double xk = tl.bcast(b / a[k], k);
+    x[k] = xk;
+    if (tl.lane < k) b -= a[k] * xk;
+  }
+  return tl.ballot(exch) != 0u;
+}
+
 HD double norm_n(const double* v, int n) {
   double s = 0.0;
   for (int i = 0; i < n; ++i) s += v[i] * v[i];
   return sqrt(s);
 }
 
-// One Dual evaluation per owned column: returns g (replicated) and the owned columns of
-// dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  step_forward calls it from exactly ONE place, so the
-// residual code exists once per kernel and everything it touches keeps its address space
-// (scene tables: shared memory, work space: local memory).
+// One Dual evaluation per owned column at the point x (an array of the tile state): leaves g in
+// ts.g and returns the owned columns of dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  The step state
+// machine calls it from exactly ONE place, so the residual code exists once per kernel.
 template <class Tile, class WK>
-HD void eval_columns(const Tile& tl, const SceneView& S, const double* x, const double* q0,
-                     const double* qd0, const double* u, int seed, WK& W, double* g,
+HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const double* x, int seed, WK& W,
                      double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
+  SeedIn in;
+  in.xq = ts.xq; in.xv = ts.xv; in.xl = ts.xl;
   // tangents of (q1, qd1, dl) per unit of the seeded variable:  q1: (1, 1/h, 1)   q0: (0, -1/h, -1)   qd0: (0, 0, -h)
-  const double t_q = (seed == 0) ? 1.0 : 0.0;
-  const double t_v = (seed == 0) ? (1.0 - 0.0) / S.h : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
-  const double t_l = (seed == 0) ? 1.0 : ((seed == 1) ? -1.0 : -S.h);
+  in.tq = (seed == 0) ? 1.0 : 0.0;
+  in.tv = (seed == 0) ? (1.0 - 0.0) / S.h : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
+  in.tl = (seed == 0) ? 1.0 : ((seed == 1) ? -1.0 : -S.h);
+  tl.tile_sync();          // every lane of the tile is done with the previous evaluation and its bookkeeping
+#pragma unroll
+  for (int i = 0; i < TS_MAXN; ++i) {
+    const double xi = (i < n) ? x[i] : 0.0, qi = (i < n) ? ts.q[i] : 0.0, vi = (i < n) ? ts.qd[i] : 0.0;
+    ts.xq[i] = xi;
+    ts.xv[i] = (xi - qi) / S.h;
+    ts.xl[i] = xi - qi - S.h * vi;
+  }
   for (int c = 0; c < TS_NC(L); ++c) {
-    const int k = tl.lane + c * L;
-    Dual xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN], gD[TS_MAXN];
+    in.k = tl.lane + c * L;
+    Dual gD[TS_MAXN];
+    eval_g(tl, S, in, ts.u, W, gD);
 #pragma unroll
     for (int i = 0; i < TS_MAXN; ++i) {
-      const double xi = (i < n) ? x[i] : 0.0, qi = (i < n) ? q0[i] : 0.0, vi = (i < n) ? qd0[i] : 0.0;
-      const double on = (i == k) ? 1.0 : 0.0;
-      xq[i] = mkdual(xi, on * t_q);
-      xv[i] = mkdual((xi - qi) / S.h, on * t_v);
-      xl[i] = mkdual(xi - qi - S.h * vi, on * t_l);
-    }
-    eval_g(tl, S, xq, xv, xl, u, W, gD);
-#pragma unroll
-    for (int i = 0; i < TS_MAXN; ++i) {
-      g[i] = (i < n) ? gD[i].v : 0.0;
-      col[c][i] = (i < n && k < n) ? gD[i].d : 0.0;
+      ts.g[i] = (i < n) ? gD[i].v : 0.0;
+      col[c][i] = (i < n && in.k < n) ? gD[i].d : 0.0;
     }
   }
 }
@@ -998,15 +1060,13 @@ HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
 // State of one implicit step in flight (DH/Simulation.cpp:1325-1351 with the Newton of :1150-1225).
 // phase 0: (g, H) at x, then iterate | 1: line-search trial at xn | 2: (H) at the final x | 3: G0 at the final x
 struct StepVars {
-  double x[TS_MAXN], xn[TS_MAXN], dx[TS_MAXN];
   double alpha, gnorm;
   int phase, fail_strike, iters, ls, trial;
   bool converged;
 };
 
-HD void step_begin(const SceneView& S, StepVars& v, const double* q, const double* qd) {
-  for (int i = 0; i < TS_MAXN; ++i) { v.x[i] = 0.0; v.dx[i] = 0.0; v.xn[i] = 0.0; }
-  for (int i = 0; i < S.n; ++i) v.x[i] = q[i] + S.h * qd[i];
+HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
+  for (int i = 0; i < TS_MAXN; ++i) { ts.x[i] = (i < S.n) ? ts.q[i] + S.h * ts.qd[i] : 0.0; ts.dx[i] = 0.0; ts.xn[i] = 0.0; }
   v.phase = 0; v.fail_strike = 0; v.iters = 0; v.ls = 0; v.trial = 0;
   v.alpha = 1.0; v.gnorm = 0.0; v.converged = false;
 }
@@ -1020,18 +1080,17 @@ HD void step_begin(const SceneView& S, StepVars& v, const double* q, const doubl
 // step_eval is the evaluation (every tile of a warp runs it together, also tiles whose step is already
 // complete: the residual code votes and shuffles across the warp); step_post is the bookkeeping.
 template <class Tile, class WK>
-HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, const double* q, const double* qd,
-                  const double* u, WK& WD, double* ge, double (*cole)[TS_MAXN]) {
-  double xe[TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) xe[i] = (v.phase == 1) ? v.xn[i] : v.x[i];
-  eval_columns(tl, S, xe, q, qd, u, v.phase == 3 ? 1 : 0, WD, ge, cole);
+HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, WK& WD, double (*cole)[TS_MAXN]) {
+  TileState& ts = WD.state();
+  eval_columns(tl, S, ts, (v.phase == 1) ? ts.xn : ts.x, v.phase == 3 ? 1 : 0, WD, cole);
 }
 
 template <class Tile, class WK>
-HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape, WK& WD, double* ge,
-                  double (*cole)[TS_MAXN]) {
+HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape, WK& WD, double (*cole)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
+  TileState& ts = WD.state();
+  const double* ge = ts.g;
   const int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
   if (v.phase == 3) {
     // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
@@ -1053,7 +1112,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     ++v.ls;
     const double gnn = norm_n(ge, n);
     if (gnn < v.gnorm) {                           // trial accepted: it is the next iterate
-      for (int i = 0; i < n; ++i) v.x[i] = v.xn[i];
+      for (int i = 0; i < n; ++i) ts.x[i] = ts.xn[i];
       v.fail_strike = 0;
       fresh = true;
       if (gnn < S.tol) { v.converged = true; finished = true; }
@@ -1061,14 +1120,17 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
       ++v.trial;
       v.alpha *= 0.5;
       if (v.trial < S.max_ls) {
-        for (int i = 0; i < n; ++i) v.xn[i] = v.x[i] + v.alpha * v.dx[i];
+        for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
         return false;
       }
       // line search exhausted (DH/Simulation.cpp:1201-1214): strike, else step with the last alpha
       ++v.fail_strike;
       if (v.fail_strike >= 10) finished = true;
       else {
-        for (int i = 0; i < n; ++i) v.x[i] = v.x[i] + v.alpha * v.dx[i];
+        double xs[TS_MAXN];                    // read-modify-write of shared tile state: reads, sync, writes
+        for (int i = 0; i < TS_MAXN; ++i) xs[i] = (i < n) ? ts.x[i] + v.alpha * ts.dx[i] : 0.0;
+        tl.tile_sync();
+        for (int i = 0; i < TS_MAXN; ++i) ts.x[i] = xs[i];
         if (gnn < S.tol) { v.converged = true; finished = true; }
         else if (v.iters >= max_newton) finished = true;
         else { v.phase = 0; return false; }
@@ -1089,11 +1151,29 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   // Newton iteration from (x, ge, cole): dx = -H^-1 g, then line search from alpha = 1
   ++v.iters;
   v.gnorm = norm_n(ge, n);
-  for (int i = 0; i < TS_MAXN; ++i) v.dx[i] = (i < n) ? -ge[i] : 0.0;
-  lu_solve(tl, cole, v.dx, n);
+  double dx[TS_MAXN];
+  bool solved = false;
+  if (L >= TS_MAXN) {
+    // lane k holds column k of H: transpose through the tile's scratch so that lane i holds row i
+    double* Hs = WD.scratch();
+    double a[TS_MAXN];
+    tl.tile_sync();
+    if (tl.lane < TS_MAXN)
+      for (int i = 0; i < TS_MAXN; ++i) Hs[i * TS_MAXN + tl.lane] = (i < n && tl.lane < n) ? cole[0][i] : ((i == tl.lane) ? 1.0 : 0.0);
+    tl.tile_sync();
+    for (int c = 0; c < TS_MAXN; ++c) a[c] = (tl.lane < TS_MAXN) ? Hs[tl.lane * TS_MAXN + c] : 0.0;
+    double bsel = 0.0;
+    for (int i = 0; i < TS_MAXN; ++i) if (i == tl.lane && i < n) bsel = -ge[i];
+    solved = !lu_rows_solve(tl, a, bsel, dx);
+    tl.tile_sync();
+  }
+  if (!solved) {
+    for (int i = 0; i < TS_MAXN; ++i) dx[i] = (i < n) ? -ge[i] : 0.0;
+    lu_solve(tl, cole, dx, n);
+  }
   v.alpha = 1.0;
   v.trial = 0;
-  for (int i = 0; i < n; ++i) v.xn[i] = v.x[i] + v.dx[i];
+  for (int i = 0; i < TS_MAXN; ++i) { ts.dx[i] = dx[i]; ts.xn[i] = (i < n) ? ts.x[i] + dx[i] : 0.0; }
   v.phase = 1;
   return false;
 }
@@ -1347,8 +1427,7 @@ HD void jac_col(const Dual* R, const Dual* p, double* J) {
 // out_g0z / out_g1z (optional, distributed) expose G0^T z (+ pending terms) and G1^T z for the
 // q0 / qdot0 gradients of the first step.
 template <class Tile, class WK>
-HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, const double* qdk, const double* uk,
-                       const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
+HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
                        double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
                        WK& WD) {
   const int L = Tile::LPE;
@@ -1364,12 +1443,16 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
   bool have_tac = dtac_cot != 0 && S.nmark > 0;
   if (have_var || have_tac) {
     TacAcc acc[TS_MAXCAND];
+    // unit tangent on q_k; the values come from the tile state (written by the caller)
+    TileState& ts = WD.state();
+    SeedIn in;
+    in.xq = ts.q; in.xv = ts.qd; in.xl = ts.qd;      // dl is not read by the kinematics-only pass
+    in.tq = 1.0; in.tv = 0.0; in.tl = 0.0;
     for (int c = 0; c < TS_NC(L); ++c) {
       const int k = tl.lane + c * L;
-      Dual xq[TS_MAXN], xqd[TS_MAXN];
-      for (int i = 0; i < n; ++i) { xq[i] = mkdual(qk[i], (i == k) ? 1.0 : 0.0); xqd[i] = mkdual(qdk[i], 0.0); }
+      in.k = k;
       tl.tile_sync();
-      kinematics(S, xq, xqd, (const Dual*)0, WD, false);
+      kinematics(S, in, WD, false);
       // the values of the Dual work space are the kinematics of the state: the marker pass reads them
       if (c == 0 && have_tac) have_tac = tactile_vjp(tl, S, WD, dtac_cot, acc);
       double yk = 0.0, ck = 0.0;
@@ -1418,21 +1501,32 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* qk, con
       if (k < n) { cterm[c] = ck / S.h; y[c] += yk + cterm[c]; }
     }
   }
-  // gather y, solve H^T z = y (lane owning dof k loads row k of H = column k of H^T)
+  // solve H^T z = y
   double z[TS_MAXN];
-  double col[TS_NC(L)][TS_MAXN];
-  for (int i = 0; i < TS_MAXN; ++i) z[i] = 0.0;
-  for (int k = 0; k < n; ++k) {
-    double v = 0.0;
-    for (int c = 0; c < TS_NC(L); ++c) if (tl.lane + c * L == k) v = y[c];
-    v = tl.bcast(v, k % L);
-    for (int i = 0; i < TS_MAXN; ++i) if (i == k) z[i] = v;
+  bool solved = false;
+  if (L >= TS_MAXN) {
+    // row-owner elimination: lane i holds row i of H^T = column i of H, and y_i
+    double a[TS_MAXN];
+    for (int c = 0; c < TS_MAXN; ++c)
+      a[c] = (tl.lane < n && c < n) ? tape[c * n + tl.lane] : ((c == tl.lane) ? 1.0 : 0.0);
+    solved = !lu_rows_solve(tl, a, (tl.lane < n) ? y[0] : 0.0, z);
   }
-  for (int c = 0; c < TS_NC(L); ++c) {
-    const int k = tl.lane + c * L;
-    for (int i = 0; i < TS_MAXN; ++i) col[c][i] = (k < n && i < n) ? tape[k * n + i] : 0.0;
+  if (!solved) {
+    // replicated pivoting solve: gather y; the lane owning dof k loads row k of H = column k of H^T
+    double col[TS_NC(L)][TS_MAXN];
+    for (int i = 0; i < TS_MAXN; ++i) z[i] = 0.0;
+    for (int k = 0; k < n; ++k) {
+      double v = 0.0;
+      for (int c = 0; c < TS_NC(L); ++c) if (tl.lane + c * L == k) v = y[c];
+      v = tl.bcast(v, k % L);
+      for (int i = 0; i < TS_MAXN; ++i) if (i == k) z[i] = v;
+    }
+    for (int c = 0; c < TS_NC(L); ++c) {
+      const int k = tl.lane + c * L;
+      for (int i = 0; i < TS_MAXN; ++i) col[c][i] = (k < n && i < n) ? tape[k * n + i] : 0.0;
+    }
+    lu_solve(tl, col, z, n);
   }
-  lu_solve(tl, col, z, n);
   // controls: dg/du = -h^2 dfr/du, FORCE motors (DH/Actuator/ActuatorMotor.cpp:48-55)
   if (du_out && tl.lane == 0) {
     for (int ai = 0; ai < S.nact; ++ai) {
@@ -1532,7 +1626,9 @@ HDN void readout_from_work(const Tile& tl, const SceneView& S, WK& W, double* va
 template <class Tile, class WK>
 HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const double* qd, double* var_o,
                      double* tac_o, int* mb_o, unsigned* cm_o, WK& WS) {
-  kinematics(S, q, qd, (const double*)0, WS, false);
+  ArrIn<double> in;
+  in.q_ = q; in.qd_ = qd; in.dl_ = qd;
+  kinematics(S, in, WS, false);
   readout_from_work(tl, S, WS, var_o, tac_o, mb_o, cm_o);
 }
 
@@ -1546,14 +1642,15 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   const int n = S.n, nu = S.nu, B = a.B;
   const bool active = env_ < B;          // surplus tiles of the last block only keep the votes balanced
   const int env = active ? env_ : B - 1;
-  double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
-  for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
+  TileState& ts = WD.state();            // tile-uniform step state (shared memory on the GPU)
+  for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   StepVars v;
   int t = 0;                             // warp-uniform
   bool tile_done = !active;
   if (a.T > 0) {
-    for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[(long long)env * nu + i] : 0.0;
-    step_begin(S, v, q, qd);
+    for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[(long long)env * nu + i] : 0.0;
+    tl.tile_sync();
+    step_begin(S, v, ts);
   }
   for (;;) {
     { TS_TIC(tl); const bool go = tl.cta_any(t < a.T); TS_TOC(tl, 4); if (!go) break; }
@@ -1561,15 +1658,14 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     const long long es = (long long)t * B + env;
     {
       TS_TIC2(tl);
-      double ge[TS_MAXN];
       double cole[TS_NC(Tile::LPE)][TS_MAXN];
 #ifdef TS_COOP_CONTACTS
-      step_eval(tl, S, v, q, qd, u, WD, ge, cole);       // whole-warp votes inside: every tile evaluates
-      if (!tile_done) tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, ge, cole);
+      step_eval(tl, S, v, WD, cole);                     // whole-warp votes inside: every tile evaluates
+      if (!tile_done) tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, cole);
 #else
       if (!tile_done) {
-        step_eval(tl, S, v, q, qd, u, WD, ge, cole);
-        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, ge, cole);
+        step_eval(tl, S, v, WD, cole);
+        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, cole);
       }
 #endif
       TS_TOC2(tl, 5);
@@ -1579,16 +1675,19 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     // ---- the step is complete for every tile of this warp
     if (active) {
       int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
-      for (int i = 0; i < n; ++i) {
-        const double q1 = v.x[i];
-        qd[i] = (q1 - q[i]) / S.h;
-        q[i] = q1;
-        if (!(q1 == q1)) stat |= TS_STAT_NAN;
+      double qn[TS_MAXN], qdn[TS_MAXN];        // read-modify-write of shared tile state: reads, sync, writes
+      for (int i = 0; i < TS_MAXN; ++i) {
+        const double q1 = ts.x[i];
+        qdn[i] = (i < n) ? (q1 - ts.q[i]) / S.h : 0.0;
+        qn[i] = (i < n) ? q1 : 0.0;
+        if (i < n && !(q1 == q1)) stat |= TS_STAT_NAN;
       }
+      tl.tile_sync();
+      for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = qn[i]; ts.qd[i] = qdn[i]; }
       if (tl.lane == 0) {
         if (a.status) a.status[es] = stat;
-        if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = q[i];
-        if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qd[i];
+        if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = qn[i];
+        if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qdn[i];
       }
       const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
       const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
@@ -1603,14 +1702,16 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     }
     ++t;
     if (t < a.T) {
-      for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
-      step_begin(S, v, q, qd);
+      tl.tile_sync();                    // readouts of this step are done in every lane of the tile
+      for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+      step_begin(S, v, ts);
       tile_done = !active;
     }
     TS_TOC(tl, 6);
   }
+  tl.tile_sync();
   if (active && tl.lane == 0)
-    for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = q[i]; a.qd[(long long)env * n + i] = qd[i]; }
+    for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = ts.q[i]; a.qd[(long long)env * n + i] = ts.qd[i]; }
 }
 
 struct BwdArgs {
@@ -1639,13 +1740,15 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
   }
   for (int t = a.T - 1; t >= 0; --t) {
     const long long es = (long long)t * B + env;
-    double q[TS_MAXN], qd[TS_MAXN], u[TS_MAXU];
-    for (int i = 0; i < TS_MAXN; ++i) { q[i] = (i < n) ? a.q_traj[es * n + i] : 0.0; qd[i] = (i < n) ? a.qd_traj[es * n + i] : 0.0; }
+    TileState& ts = WD.state();
+    double u[TS_MAXU];
+    tl.tile_sync();                      // the previous (later-in-time) step is done reading the tile state
+    for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q_traj[es * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd_traj[es * n + i] : 0.0; }
     for (int i = 0; i < TS_MAXU; ++i) u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
     const int r0 = a.df_dq ? (a.dq_row ? a.dq_row[t] : t) : -1;
     const int r1 = a.df_dvar ? (a.dvar_row ? a.dvar_row[t] : t) : -1;
     const int r2 = a.df_dtac ? (a.dtac_row ? a.dtac_row[t] : t) : -1;
-    step_backward(tl, S, q, qd, u, a.tape + es * 3 * n * n,
+    step_backward(tl, S, u, a.tape + es * 3 * n * n,
                   r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
                   r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
                   r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,
