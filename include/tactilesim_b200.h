@@ -51,6 +51,11 @@ void tsim_scene_destroy(tsim_scene* scene);
 int tsim_scene_sizes(const tsim_scene* scene, int32_t* out /* [TSIM_N_SIZES] */);
 /* lanes cooperating on one environment: 8, 16 or 32 (default 8) */
 int tsim_scene_set_lanes(tsim_scene* scene, int lanes_per_env);
+/* Solver options of a scene handle (no reference counterpart: the reference searches sequentially).
+ *   TSIM_OPT_LS_BATCH  1 (default): after two rejected line-search trials the lanes of the tile evaluate the
+ *                      following step lengths at once; 0: strictly sequential search.  Same accepted step. */
+enum { TSIM_OPT_LS_BATCH = 0, TSIM_N_OPTS };
+int tsim_scene_set_option(tsim_scene* scene, int key, int value);
 
 /* Advances B environments by T implicit (BDF1/Newton) steps.
  *   q, qd        [B,n]        state, in/out

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # TSIM_B200_LIB: development override to A/B-test kernel build variants (still a CUDA library of this ABI)
 LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_b200.so")
 
-SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes",
+SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
            "tsim_forward", "tsim_readout", "tsim_backward"]
 (NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, N_SIZES) = range(9)
 
@@ -36,6 +36,7 @@ def load():
     lib.tsim_scene_destroy.restype = None
     lib.tsim_scene_sizes.argtypes = [vp, vp]
     lib.tsim_scene_set_lanes.argtypes = [vp, ctypes.c_int]
+    lib.tsim_scene_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.tsim_forward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_readout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_backward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -14,10 +14,23 @@
 //   * ancestor bitmasks per moving joint (mass-matrix columns).
 #pragma once
 
+// Compile-time capacities.  The library holds the kernels twice (build.py): variant 8 (defaults below,
+// 8 lanes per environment: TactilePush) and variant 16 (-DTS_VARIANT=16: up to 16 reduced dofs, 16 lanes per
+// environment: DClaw, TactileInsertion); csrc/cabi.cpp picks the variant per scene.
+#ifndef TS_VARIANT
+#define TS_VARIANT 8
+#endif
+#if TS_VARIANT == 16
+#define KT_MAXJ 12       // moving joints
+#define KT_MAXN 16       // reduced dofs
+#define KT_MAXB 24       // bodies
+#define KT_MAXU 16       // controls
+#else
 #define KT_MAXJ 8        // moving joints
 #define KT_MAXN 8        // reduced dofs
 #define KT_MAXB 16       // bodies
 #define KT_MAXU 8        // controls
+#endif
 #define KT_MAXCAND 4     // tactile candidate bodies per sensor
 
 enum {

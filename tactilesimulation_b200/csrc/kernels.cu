@@ -236,6 +236,7 @@ struct tsim_scene {
   int ni, nd;
   int lanes;
   int nmj;                 // moving joints of the lowered scene
+  int opts[TSIM_N_OPTS];
   int sizes[TSIM_N_SIZES];
 };
 
@@ -289,6 +290,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->nd = (int)kt.db.size();
   s->lanes = 8;
   s->nmj = kt.ib[KI_NMJ];
+  s->opts[TSIM_OPT_LS_BATCH] = 1;
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
   CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
@@ -328,6 +330,13 @@ int tsim_scene_set_lanes(tsim_scene* s, int lanes) {
 }
 
 
+int tsim_scene_set_option(tsim_scene* s, int key, int value) {
+  if (!s) return fail("tsim_scene_set_option: null scene");
+  if (key < 0 || key >= TSIM_N_OPTS) return fail("tsim_scene_set_option: unknown option");
+  s->opts[key] = value;
+  return 0;
+}
+
 int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, const double* u,
                  int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
                  double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
@@ -341,6 +350,7 @@ int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* q
   a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_step_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
   a.status = status; a.cmask = contact_masks; a.marker_body = marker_body;
+  a.ls_batch = s->opts[TSIM_OPT_LS_BATCH];
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);

@@ -186,16 +186,18 @@ struct SeedIn {
 };
 
 static_assert(sizeof(Frames) >= sizeof(double) * TS_MAXN * TS_MAXN, "the frames region doubles as the LU scratch");
-template <class T> struct Work {
+template <class T> struct WorkRec {          // the joint records alone (value-only line-search trials)
   typedef T Scalar;
   T rec[TS_MAXJ][WK_REC];
+  HD T get(int j, int o) const { return rec[j][o]; }
+  HD double getv(int j, int o) const { return val(rec[j][o]); }
+  HD void put(int j, int o, const T& x) { rec[j][o] = x; }
+};
+template <class T> struct Work : WorkRec<T> {
   Frames fr;
   TileState ts;
   HD TileState& state() { return ts; }
   HD double* scratch() { return (double*)&fr; }      // >= TS_MAXN^2 doubles, free while no readout is in flight
-  HD T get(int j, int o) const { return rec[j][o]; }
-  HD double getv(int j, int o) const { return val(rec[j][o]); }
-  HD void put(int j, int o, const T& x) { rec[j][o] = x; }
   HD Frames& frames() { return fr; }
 };
 
@@ -809,7 +811,10 @@ HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* 
 struct HostTile {
   static const int LPE = 1;
   int lane;
-  HostTile() : lane(0) {}
+#ifdef TS_PROFILE
+  mutable long long acc[8];
+#endif
+  HD HostTile() : lane(0) {}
   HD double bcast(double v, int) const { return v; }
   HD int bcasti(int v, int) const { return v; }
   HD double sum(double v) const { return v; }
@@ -1053,6 +1058,27 @@ HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
   }
 }
 
+// ||g(x + alpha dx)|| by a value-only evaluation that this lane runs ALONE (one-lane tile policy, plain
+// per-lane work space): the lanes of a tile evaluate different step lengths of a struggling line
+// search at the same time.
+HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha) {
+  const int n = S.n;
+  double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN], g[TS_MAXN];
+  for (int i = 0; i < TS_MAXN; ++i) {
+    const double xi = (i < n) ? ts.x[i] + alpha * ts.dx[i] : 0.0, qi = (i < n) ? ts.q[i] : 0.0, vi = (i < n) ? ts.qd[i] : 0.0;
+    xq[i] = xi;
+    xv[i] = (xi - qi) / S.h;
+    xl[i] = xi - qi - S.h * vi;
+    g[i] = 0.0;
+  }
+  ArrIn<double> in;
+  in.q_ = xq; in.qd_ = xv; in.dl_ = xl;
+  WorkRec<double> Wv;
+  HostTile solo;
+  eval_g(solo, S, in, ts.u, Wv, g);
+  return norm_n(g, n);
+}
+
 // status word per env-step: newton iterations | line-search evaluations << 8 | flags << 16
 #define TS_STAT_NOT_CONVERGED (1 << 16)
 #define TS_STAT_NAN (1 << 17)
@@ -1062,7 +1088,7 @@ HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
 struct StepVars {
   double alpha, gnorm;
   int phase, fail_strike, iters, ls, trial;
-  bool converged;
+  bool converged, batch_ls;
 };
 
 HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
@@ -1110,7 +1136,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   bool finished = false, fresh = (v.phase == 2);   // fresh: (ge, cole) belong to the final x
   if (v.phase == 1) {
     ++v.ls;
-    const double gnn = norm_n(ge, n);
+    double gnn = norm_n(ge, n);
     if (gnn < v.gnorm) {                           // trial accepted: it is the next iterate
       for (int i = 0; i < n; ++i) ts.x[i] = ts.xn[i];
       v.fail_strike = 0;
@@ -1119,9 +1145,42 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     } else {
       ++v.trial;
       v.alpha *= 0.5;
-      if (v.trial < S.max_ls) {
+      if (v.trial < S.max_ls && !(L >= TS_MAXN && v.batch_ls && v.trial >= 2)) {
         for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
         return false;
+      }
+      if (v.trial < S.max_ls) {
+        // Two trials already failed: a struggling line search (up to max_ls = 20 trials per iteration,
+        // DH/Simulation.cpp:1186-1200) would serialise the whole block behind this tile.  The lanes of the
+        // tile evaluate the next LPE step lengths at once (value only); the first one, in the reference's
+        // order, that reduces ||g|| is then evaluated with its Jacobian by the normal path, which also
+        // re-checks the acceptance.  Same accepted step length as the sequential search.
+        bool found = false;
+        while (v.trial < S.max_ls) {
+          const int left = S.max_ls - v.trial;
+          const int nb = left < L ? left : L;
+          double my_alpha = v.alpha;
+          for (int i = 0; i < tl.lane; ++i) my_alpha *= 0.5;
+          double my_norm = 0.0;
+          if (tl.lane < nb) my_norm = trial_norm(S, ts, my_alpha);
+          const unsigned okbits = tl.ballot(tl.lane < nb && my_norm < v.gnorm);
+          if (okbits) {
+            const int k = ts_ffs(okbits);
+            v.trial += k;
+            v.ls += k;                           // the rejected trials the sequential search would have evaluated
+            for (int i = 0; i < k; ++i) v.alpha *= 0.5;
+            found = true;
+            break;
+          }
+          gnn = tl.bcast(my_norm, nb - 1);       // ||g|| of the last trial evaluated (used by the exhausted path)
+          v.trial += nb;
+          v.ls += nb;
+          for (int i = 0; i < nb; ++i) v.alpha *= 0.5;
+        }
+        if (found) {
+          for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
+          return false;
+        }
       }
       // line search exhausted (DH/Simulation.cpp:1201-1214): strike, else step with the last alpha
       ++v.fail_strike;
@@ -1605,6 +1664,7 @@ struct FwdArgs {
   int* status;                        // [T,B] or null
   unsigned* cmask;                    // [T,B,4] or null
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
+  int ls_batch;                       // TSIM_OPT_LS_BATCH
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
@@ -1645,6 +1705,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   TileState& ts = WD.state();            // tile-uniform step state (shared memory on the GPU)
   for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   StepVars v;
+  v.batch_ls = a.ls_batch != 0;
   int t = 0;                             // warp-uniform
   bool tile_done = !active;
   if (a.T > 0) {

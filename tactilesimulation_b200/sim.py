@@ -53,6 +53,10 @@ class BatchedSim:
         if lanes != 8:
             self.set_lanes(lanes)
 
+    def set_option(self, key: int, value: int):
+        """tsim_scene_set_option (include/tactilesim_b200.h): 0 = TSIM_OPT_LS_BATCH."""
+        _lib.check(self.lib.tsim_scene_set_option(self.handle, key, value), self.lib)
+
     def set_lanes(self, lanes: int):
         _lib.check(self.lib.tsim_scene_set_lanes(self.handle, lanes), self.lib)
         self.lanes = lanes

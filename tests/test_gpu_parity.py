@@ -109,3 +109,30 @@ def test_readout_matches_step_outputs():
     assert rel_err(r["tactile"][0].cpu().numpy(), g["tactile"][t]) <= 1e-8
     assert rel_err(r["var"][0].cpu().numpy(), g["var"][t]) <= 1e-9
     assert np.array_equal(r["marker_body"][0].cpu().numpy(), g["marker_body"][t])
+
+
+def test_batched_line_search_equals_sequential_search():
+    """TSIM_OPT_LS_BATCH evaluates the step lengths of a struggling line search in parallel; the accepted
+    step, the iterate sequence and the evaluation counts must be those of the sequential search
+    (DH/Simulation.cpp:1186-1200).  The bench inputs hold an environment whose Newton runs into the
+    iteration cap (140 iterations of up to 20 trials): both searches must agree bit for bit there too."""
+    from bench import make_inputs
+    g = np.load(os.path.join(GOLDEN, "pusher32x13_episodic_s0.npz"))
+    B, T = 4096, 200
+    q0, qd0, u, _ = make_inputs(g["q0"], B, T, 1234)
+    sel = np.r_[2800:2828, 1940:1968, 0:8]           # the block with the non-converging env, a hard one, easy ones
+    outs = []
+    for batch in (1, 0):
+        sim = _sim(g)
+        sim.set_option(0, batch)
+        dev = sim.device
+        q, qd = torch.tensor(q0[sel], device=dev), torch.tensor(qd0[sel], device=dev)
+        ut = torch.tensor(np.ascontiguousarray(u[:, sel]), device=dev)
+        o = sim.forward(q, qd, ut, T, grad=True, want_status=True, want_tactile=False)
+        torch.cuda.synchronize()
+        outs.append((o["q_traj"].cpu().numpy(), o["status"].cpu().numpy(), o["tape"].cpu().numpy()))
+    (qa, sa, ta), (qb, sb, tb) = outs
+    assert int(((sa >> 8) & 255).max()) >= 3 and int((sa & 255).max()) >= 100, "inputs no longer exercise a struggling search"
+    assert np.array_equal(sa, sb)
+    assert np.array_equal(qa, qb)
+    assert np.array_equal(ta, tb)

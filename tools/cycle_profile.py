@@ -9,7 +9,7 @@ from tactilesimulation_b200.sim import BatchedSim
 g = np.load(os.path.join(ROOT, "tests", "golden", "pusher32x13_episodic_s0.npz"))
 sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=8)
 dev = sim.device
-B, T = 4096, 50
+B, T = int(os.environ.get('PB', 4096)), int(os.environ.get('PT', 50))
 nthreads = ((B * 8 + 223) // 224) * 224
 prof = torch.zeros((nthreads, 8), dtype=torch.int64, device=dev)
 sim.lib.tsim_debug_set_prof(ctypes.c_void_p(prof.data_ptr()))
@@ -22,6 +22,8 @@ for rep in range(3):
 p = prof.cpu().numpy().reshape(-1, 28, 8, 8)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
 names = ["kinematics+dyn", "ground", "gp", "inward", "vote wait", "step_round total", "epilogue", "kernel total"]
 tot = p[:, :, 7].astype(float)
+bt = tot.max(axis=1)
+print("per-block kernel cycles percentiles (min/25/50/75/90/99/max):", np.percentile(bt, [0, 25, 50, 75, 90, 99, 100]).round(-3))
 print("blocks", p.shape[0], "kernel cycles: mean %.3g max %.3g (%.2f ms at 1.965 GHz)" % (tot.mean(), tot.max(), tot.max() / 1.965e6))
 for i, nm in enumerate(names):
     v = p[:, :, i].astype(float)

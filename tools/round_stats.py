@@ -29,3 +29,11 @@ print("contact fraction", incontact.mean(), " per-env contact-steps: max", incon
 cw = incontact.reshape(T, B // 4, 4).any(axis=2)
 print("warp has a contact env: frac of warp-steps", cw.mean())
 print("rounds/step when in contact", rounds[incontact].mean(), "when not", rounds[~incontact].mean())
+# worst envs
+order = np.argsort(-per_env)[:8]
+for e in order:
+    it = (st[:, e] & 255)
+    print("env", int(e), "block", int(e) // 28, "total rounds", int(per_env[e]), "newton iters: max", int(it.max()), "sum", int(it.sum()),
+          "ls max", int(ls[:, e].max()), "flags", int((st[:, e] >> 16).max()), "contact steps", int(incontact[:, e].sum()))
+print("per-block totals sorted (top 8):", np.sort(blk)[-8:], "median", np.median(blk))
+print("histogram of per-env totals:", np.histogram(per_env, bins=[0, 600, 700, 800, 900, 1000, 1200, 1500, 2000, 5000, 100000])[0])
