@@ -1,15 +1,19 @@
-"""In-tree build of the CUDA library (sm_100a only).  nvcc cross-compiles without a GPU."""
+"""In-tree build of the CUDA library (sm_100a only).  nvcc cross-compiles without a GPU.
+
+The kernels are compiled twice from csrc/kernels.cu (compile-time capacities, csrc/kernel_layout.h):
+variant 8 (<= 8 reduced dofs) and variant 16 (<= 16 reduced dofs); csrc/cabi.cpp owns the public C ABI
+and dispatches per scene.  The two kernel objects compile in parallel."""
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtactilesim_b200.so")
-SOURCES = ["kernels.cu"]
-DEPS = ["kernels.cu", "sim_core.cuh", "dual.cuh", "scene_layout.h",
+OBJ = os.path.join(HERE, "_obj")
+VARIANTS = (8, 16)
+DEPS = ["kernels.cu", "cabi.cpp", "sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h",
         os.path.join("..", "..", "include", "tactilesim_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def needs_build() -> bool:
@@ -19,12 +23,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    os.makedirs(OBJ, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else [])
+    jobs, objs = [], []
+    for v in VARIANTS:
+        o = os.path.join(OBJ, f"kernels_v{v}.o")
+        objs.append(o)
+        jobs.append(subprocess.Popen([nvcc] + flags + [f"-DTS_VARIANT={v}", "-c", "kernels.cu", "-o", o], cwd=CSRC))
+    o = os.path.join(OBJ, "cabi.o")
+    objs.append(o)
+    jobs.append(subprocess.Popen([nvcc] + flags + ["-c", "cabi.cpp", "-o", o], cwd=CSRC))
+    rcs = [j.wait() for j in jobs]
+    if any(rcs):
+        raise RuntimeError(f"nvcc failed (exit codes {rcs})")
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs, cwd=CSRC)
     return LIB
 
 

@@ -10,11 +10,33 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include <string>
+#include <vector>
 
 #ifndef TS_NO_SYNC_EVALS
 #define TS_SYNC_EVALS 1
 #endif
+#include "kernel_layout.h"
+// this translation unit is one VARIANT of the library (kernel_layout.h): every ABI name gets the variant's
+// suffix; csrc/cabi.cpp owns the public names and dispatches per scene
+#define TS_CAT_(a, b) a##b
+#define TS_CAT(a, b) TS_CAT_(a, b)
+#define TSV(x) TS_CAT(x, TS_CAT(_v, TS_VARIANT))
+#define tsim_scene TSV(tsim_scene)
+#define tsim_last_error TSV(tsim_last_error)
+#define tsim_scene_create TSV(tsim_scene_create)
+#define tsim_scene_destroy TSV(tsim_scene_destroy)
+#define tsim_scene_sizes TSV(tsim_scene_sizes)
+#define tsim_scene_set_lanes TSV(tsim_scene_set_lanes)
+#define tsim_scene_set_option TSV(tsim_scene_set_option)
+#define tsim_forward TSV(tsim_forward)
+#define tsim_readout TSV(tsim_readout)
+#define tsim_backward TSV(tsim_backward)
+#define tsim_debug_set_prof TSV(tsim_debug_set_prof)
+// Everything below lives in a per-variant namespace: the two variants instantiate templates and kernels
+// with identical signatures but different capacities, and must not share symbols.
+namespace TSV(tsimns) {
 #include "../../include/tactilesim_b200.h"
 #include "scene_lower.h"
 #include "sim_core.cuh"
@@ -288,7 +310,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->device = device;
   s->ni = (int)kt.ib.size();
   s->nd = (int)kt.db.size();
-  s->lanes = 8;
+  s->lanes = TS_MAXN;        // one lane per reduced coordinate
   s->nmj = kt.ib[KI_NMJ];
   s->opts[TSIM_OPT_LS_BATCH] = 1;
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
@@ -324,7 +346,8 @@ int tsim_scene_sizes(const tsim_scene* s, int32_t* out) {
 
 int tsim_scene_set_lanes(tsim_scene* s, int lanes) {
   if (!s) return fail("tsim_scene_set_lanes: null scene");
-  if (lanes != 8 && lanes != 16 && lanes != 32) return fail("tsim_scene_set_lanes: lanes must be 8, 16 or 32");
+  if ((lanes != 8 && lanes != 16 && lanes != 32) || lanes < TS_MAXN)
+    return fail("tsim_scene_set_lanes: lanes must be 8, 16 or 32 and at least the dof capacity of the scene's kernel variant");
   s->lanes = lanes;
   return 0;
 }
@@ -355,8 +378,11 @@ int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* q
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
+#if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else
+#endif
+  if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else { if (prep(fwd_kernel<32>, smem)) return 1; fwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
   return 0;
@@ -371,8 +397,11 @@ int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* 
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
+#if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(readout_kernel<8>, smem)) return 1; readout_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
-  else if (s->lanes == 16) { if (prep(readout_kernel<16>, smem)) return 1; readout_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
+  else
+#endif
+  if (s->lanes == 16) { if (prep(readout_kernel<16>, smem)) return 1; readout_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
   else { if (prep(readout_kernel<32>, smem)) return 1; readout_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
   CK(cudaGetLastError());
   return 0;
@@ -396,11 +425,15 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
+#if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(bwd_kernel<8>, smem)) return 1; bwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  else
+#endif
+  if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
   return 0;
 }
 
 }  // extern "C"
+}  // namespace

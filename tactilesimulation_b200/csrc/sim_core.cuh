@@ -166,6 +166,7 @@ struct TileState {
   double x[TS_MAXN], xn[TS_MAXN], dx[TS_MAXN];     // Newton iterate, line-search trial, Newton direction
   double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN];    // inputs (q1, qd1, dl) of the evaluation in flight
   double g[TS_MAXN];                               // residual of the last evaluation
+  double hs[TS_MAXN * TS_MAXN];                    // transposition scratch of the cooperative LU
 };
 
 // inputs (q, qd, dl) of one evaluation: plain arrays ...
@@ -185,7 +186,6 @@ struct SeedIn {
   HD Dual dl(int i) const { return mkdual(xl[i], i == k ? tl : 0.0); }
 };
 
-static_assert(sizeof(Frames) >= sizeof(double) * TS_MAXN * TS_MAXN, "the frames region doubles as the LU scratch");
 template <class T> struct WorkRec {          // the joint records alone (value-only line-search trials)
   typedef T Scalar;
   T rec[TS_MAXJ][WK_REC];
@@ -197,7 +197,7 @@ template <class T> struct Work : WorkRec<T> {
   Frames fr;
   TileState ts;
   HD TileState& state() { return ts; }
-  HD double* scratch() { return (double*)&fr; }      // >= TS_MAXN^2 doubles, free while no readout is in flight
+  HD double* scratch() { return ts.hs; }
   HD Frames& frames() { return fr; }
 };
 
@@ -207,7 +207,7 @@ struct WorkSplit {
   Frames* fr;                      // per tile, shared memory
   TileState* ts;                   // per tile, shared memory
   HD TileState& state() { return *ts; }
-  HD double* scratch() { return (double*)fr; }
+  HD double* scratch() { return ts->hs; }
   double dt[TS_MAXJ][WK_REC];      // tangents of this lane
   HD Dual get(int j, int o) const { return mkdual(sv[j * WK_REC + o], dt[j][o]); }
   HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
@@ -843,6 +843,41 @@ struct HostTile {
 // PIVOT=false is the same elimination without row exchanges; it reports whether partial pivoting
 // would have exchanged any row (then the caller redoes the solve with PIVOT=true).  Newton matrices
 // H = M - h^2 K - h D are mass dominated, so the exchange-free pass almost always stands.
+#if TS_MAXN > 8
+// 16-dof variant: the replicated solve is only the rare fallback of lu_rows_solve (and the host harness):
+// plain loops, the matrix lives in local memory
+template <bool PIVOT>
+HDN bool lu_factor_solve(double (*A)[TS_MAXN], double* b) {
+  bool exchanged = false;
+  for (int j = 0; j < TS_MAXN; ++j) {
+    int p = j;
+    double best = fabs(A[j][j]);
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const double v = fabs(A[i][j]);
+      if (v > best) { best = v; p = i; }
+    }
+    if (p != j) {
+      if (!PIVOT) exchanged = true;
+      else {
+        for (int c = 0; c < TS_MAXN; ++c) { const double t = A[j][c]; A[j][c] = A[p][c]; A[p][c] = t; }
+        const double t = b[j]; b[j] = b[p]; b[p] = t;
+      }
+    }
+    const double piv = A[j][j];
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const double l = A[i][j] / piv;
+      for (int c = j + 1; c < TS_MAXN; ++c) A[i][c] -= l * A[j][c];
+      b[i] -= l * b[j];
+    }
+  }
+  for (int k = TS_MAXN - 1; k >= 0; --k) {
+    const double xk = b[k] / A[k][k];
+    b[k] = xk;
+    for (int i = 0; i < k; ++i) b[i] -= A[i][k] * xk;
+  }
+  return exchanged;
+}
+#else
 template <bool PIVOT>
 HD bool lu_factor_solve(double (*A)[TS_MAXN], double* b) {
   bool exchanged = false;
@@ -890,6 +925,7 @@ HD bool lu_factor_solve(double (*A)[TS_MAXN], double* b) {
   }
   return exchanged;
 }
+#endif
 
 template <class Tile>
 HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {

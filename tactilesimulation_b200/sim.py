@@ -21,7 +21,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class BatchedSim:
-    def __init__(self, scene, device="cuda:0", lanes: int = 8):
+    def __init__(self, scene, device="cuda:0", lanes: Optional[int] = None):
+        """lanes: lanes of a warp cooperating on one environment (None = the default of the kernel variant
+        the scene runs on: one lane per reduced coordinate, 8 or 16)."""
         if not torch.cuda.is_available():
             raise _lib.TactileSimError("no CUDA device visible: tactilesimulation_b200 has no CPU fallback")
         self.lib = _lib.load()
@@ -49,8 +51,8 @@ class BatchedSim:
         self.nj, self.ndof_r, self.ndof_m, self.ndof_u, self.ndof_var, self.ndof_tactile, self.n_markers, \
             self.tape_doubles = (int(x) for x in sizes[:8])
         self.h = float(self.dbuf[0])
-        self.lanes = 8
-        if lanes != 8:
+        self.lanes = None
+        if lanes is not None:
             self.set_lanes(lanes)
 
     def set_option(self, key: int, value: int):

@@ -25,16 +25,23 @@ def _ids(words):
     return out
 
 
-def _sim(g, lanes=8):
+def _sim(g, lanes=8, variant=8):
+    """variant 16 = the 16-dof build of the kernels (csrc/kernel_layout.h), forced through the
+    TSIM_B200_VARIANT development knob of csrc/cabi.cpp."""
     from tactilesimulation_b200.sim import BatchedSim
-    return BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0", lanes=lanes)
+    if variant == 16:
+        os.environ["TSIM_B200_VARIANT"] = "16"
+    try:
+        return BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0", lanes=lanes)
+    finally:
+        os.environ.pop("TSIM_B200_VARIANT", None)
 
 
-@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("lanes,variant", [(8, 8), (16, 8), (32, 8), (16, 16), (32, 16)])
 @pytest.mark.parametrize("name", CASES)
-def test_forward_and_adjoint_match_reference(name, lanes):
+def test_forward_and_adjoint_match_reference(name, lanes, variant):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    sim = _sim(g, lanes)
+    sim = _sim(g, lanes, variant)
     dev = sim.device
     T = g["u"].shape[0]
     B = 3   # three identical envs: also checks that tiles do not interfere
