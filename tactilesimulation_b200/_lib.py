@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_
 
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
            "tsim_forward", "tsim_readout", "tsim_backward"]
-(NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, N_SIZES) = range(9)
+(NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, CMASK_WORDS, N_SIZES) = range(10)
 
 _lib = None
 

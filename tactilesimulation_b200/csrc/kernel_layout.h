@@ -25,17 +25,19 @@
 #define KT_MAXN 16       // reduced dofs
 #define KT_MAXB 24       // bodies
 #define KT_MAXU 16       // controls
+#define KT_MAXPW 5       // 32-bit words of an active-point bitmask: <= 160 sampled points per general body
 #else
 #define KT_MAXJ 8        // moving joints
 #define KT_MAXN 8        // reduced dofs
 #define KT_MAXB 16       // bodies
 #define KT_MAXU 8        // controls
+#define KT_MAXPW 3       // <= 96 sampled points per general body
 #endif
 #define KT_MAXCAND 4     // tactile candidate bodies per sensor
 
 enum {
   KI_NMJ = 0, KI_N, KI_NU, KI_NEE, KI_NMARK, KI_NGROUND, KI_NGP, KI_NACT, KI_NSENS, KI_MAX_ITER, KI_MAX_LS,
-  KI_NBODY, KI_NPOINTS,
+  KI_NBODY, KI_NPOINTS, KI_CMW /* words of the per-env-step contact bitmask output */,
   KI_O_JOINT = 16, KI_O_BODY, KI_O_GROUND, KI_O_GP, KI_O_ACT, KI_O_EE, KI_O_SENSOR,
   KI_D_JOINT = 24, KI_D_BODY, KI_D_GROUND, KI_D_GP, KI_D_ACT, KI_D_EE, KI_D_SENSOR, KI_D_POINTS, KI_D_MARKERS,
   KI_HEADER = 40
@@ -61,19 +63,20 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 #define KJ_MASS 34
 // body: int {moving joint (-1 = static), shape, dynamic (has mass and a moving joint), unused}
 #define KB_ISTRIDE 4
-// dbl {Rmi(9) pmi(3): body frame in its moving joint frame | inertia(6) | half-size(3) | bounding radius}
+// dbl {Rmi(9) pmi(3): body frame in its moving joint frame | inertia(6) | cuboid: half-size(3), cylinder: radius,
+//      half-length, - | bounding radius}
 #define KB_DSTRIDE 24
 #define KB_RMI 0
 #define KB_PMI 9
 #define KB_INERTIA 12
 #define KB_HALF 18
 #define KB_RBOUND 21
-// ground contact: int {body, point_off, point_cnt, -}; dbl {kn kt mu damping}
+// ground contact: int {body, point_off, point_cnt, first word in the contact bitmask output}; dbl {kn kt mu damping}
 #define KG_ISTRIDE 4
 #define KG_DSTRIDE 4
-// general-primitive contact: int {body1, body2, point_off, point_cnt};
-// dbl {kn kt mu damping r_points | bounding box of the points in the body-1 frame: lo(3) hi(3)}
-#define KP_ISTRIDE 4
+// general-primitive contact: int {body1, body2, point_off, point_cnt, first word in the contact bitmask output,
+// shape of body2}; dbl {kn kt mu damping r_points | bounding box of the points in the body-1 frame: lo(3) hi(3)}
+#define KP_ISTRIDE 6
 #define KP_DSTRIDE 12
 #define KP_BBOX 5
 // actuator: int {moving joint, mode, uoff, ndof}; dbl {cmin[3] cmax[3] P[3] D[3]}
@@ -82,6 +85,9 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 // end effector: int {moving joint (-1 = world), -}; dbl {pos(3) in that frame, -}
 #define KE_ISTRIDE 2
 #define KE_DSTRIDE 4
+// markers: KM_STRIDE doubles each {position(3) axis0(3) axis1(3) normal(3)} in the pad body frame; they stay in
+// global memory (read once per marker and readout), everything before them is staged in shared memory
+#define KM_STRIDE 12
 // sensor: int {body, marker_off, marker_cnt, ncand, cand[4]};
 // dbl {kn kt mu damping axis0 axis1 normal r_markers | bounding box of the markers in the pad frame: lo(3) hi(3)}
 #define KS_ISTRIDE 8

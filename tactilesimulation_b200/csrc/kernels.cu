@@ -157,6 +157,7 @@ struct DevTile {
 #endif
 
 // stage the scene blob in shared memory (doubles first, then ints, 8-byte aligned)
+// nd = doubles BEFORE the marker table; the markers (the bulk of a scene with dense sensors) stay in global memory
 __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni, const double* db, int nd,
                                             unsigned char* smem) {
   double* sd = (double*)smem;
@@ -164,7 +165,10 @@ __device__ __forceinline__ void stage_scene(SceneView& S, const int* ib, int ni,
   for (int i = threadIdx.x; i < nd; i += blockDim.x) sd[i] = db[i];
   for (int i = threadIdx.x; i < ni; i += blockDim.x) si[i] = ib[i];
   __syncthreads();
-  if (threadIdx.x == 0) scene_view_init(S, si, sd);   // S is the block's shared view: registers stay free for the math
+  if (threadIdx.x == 0) {
+    scene_view_init(S, si, sd);   // S is the block's shared view: registers stay free for the math
+    S.mk = db + si[KI_D_MARKERS];
+  }
   __syncthreads();
 }
 
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni
   env_readout(tl, S, ql, qdl, var_out ? var_out + (long long)env * 3 * S.nee : (double*)0,
               tac_out ? tac_out + (long long)env * 3 * S.nmark : (double*)0,
               marker_body ? marker_body + (long long)env * S.nmark : (int*)0,
-              cmask ? cmask + (long long)env * 4 : (unsigned*)0, wb);
+              cmask ? cmask + (long long)env * S.cmw : (unsigned*)0, wb);
 }
 
 // ------------------------------------------------------------------ host side of the C ABI
@@ -255,7 +259,7 @@ struct tsim_scene {
   int device;
   int* d_ib;
   double* d_db;
-  int ni, nd;
+  int ni, nd, nd_all;
   int lanes;
   int nmj;                 // moving joints of the lowered scene
   int opts[TSIM_N_OPTS];
@@ -309,14 +313,15 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   tsim_scene* s = new tsim_scene();
   s->device = device;
   s->ni = (int)kt.ib.size();
-  s->nd = (int)kt.db.size();
+  s->nd_all = (int)kt.db.size();
+  s->nd = kt.ib[KI_D_MARKERS];       // doubles staged in shared memory: everything before the marker table
   s->lanes = TS_MAXN;        // one lane per reduced coordinate
   s->nmj = kt.ib[KI_NMJ];
   s->opts[TSIM_OPT_LS_BATCH] = 1;
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
-  CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd));
+  CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd_all));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(s->d_db, kt.db.data(), sizeof(double) * s->nd, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->d_db, kt.db.data(), sizeof(double) * s->nd_all, cudaMemcpyHostToDevice));
   const int n = ibuf[TS_I_NDOF_R];
   s->sizes[TSIM_NJ] = ibuf[TS_I_NJ];
   s->sizes[TSIM_NDOF_R] = n;
@@ -326,6 +331,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->sizes[TSIM_NDOF_TACTILE] = 3 * ibuf[TS_I_NMARKERS];
   s->sizes[TSIM_N_MARKERS] = ibuf[TS_I_NMARKERS];
   s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n;
+  s->sizes[TSIM_CMASK_WORDS] = kt.ib[KI_CMW];
   *out = s;
   return 0;
 }

@@ -28,6 +28,9 @@ enum {
   TS_I_RES0, TS_I_RES1,
   // offsets (in elements) of the int sections
   TS_I_OFF_JOINT = 16, TS_I_OFF_GROUND, TS_I_OFF_GP, TS_I_OFF_ACT, TS_I_OFF_EE, TS_I_OFF_SENSOR,
+  // offset (doubles) of the optional per-marker (axis0, axis1, normal) section, 9 doubles per marker; 0 = the
+  // per-sensor axes of the sensor record apply to all its markers (blobs written before abstract sensors)
+  TS_I_DOFF_MARKER_AXES = 22,
   // offsets (in elements) of the double sections
   TS_I_DOFF_JOINT = 24, TS_I_DOFF_GROUND, TS_I_DOFF_GP, TS_I_DOFF_ACT, TS_I_DOFF_EE,
   TS_I_DOFF_SENSOR, TS_I_DOFF_POINTS, TS_I_DOFF_MARKERS,

@@ -52,7 +52,6 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   const int npoints = ib[TS_I_NPOINTS];
   if (nj > KT_MAXB) return "scene exceeds the compiled capacity (bodies)";
   if (n > KT_MAXN || nu > KT_MAXU) return "scene exceeds the compiled capacities (dofs/controls)";
-  if (nsens > 1) return "at most one tactile sensor is supported";
   const int* J = ib + ib[TS_I_OFF_JOINT];
   const double* JD = db + ib[TS_I_DOFF_JOINT];
   // nearest moving ancestor-or-self and the constant transform from its frame to each joint frame
@@ -159,19 +158,29 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     for (int i = 0; i < 9; ++i) d[KB_RMI + i] = emi.R[i];
     for (int i = 0; i < 3; ++i) d[KB_PMI + i] = emi.p[i];
     for (int i = 0; i < 6; ++i) d[KB_INERTIA + i] = s[TS_JD_INERTIA + i];
-    for (int i = 0; i < 3; ++i) d[KB_HALF + i] = s[TS_JD_HALF + i];
-    d[KB_RBOUND] = norm3(s + TS_JD_HALF);
+    if (J[j * TS_JI_STRIDE + 4] == TS_SH_CYLINDER) {      // blob: (radius, length, -)
+      d[KB_HALF] = s[TS_JD_HALF];
+      d[KB_HALF + 1] = s[TS_JD_HALF + 1] / 2.;
+      d[KB_RBOUND] = sqrt(d[KB_HALF] * d[KB_HALF] + d[KB_HALF + 1] * d[KB_HALF + 1]);
+    } else {
+      for (int i = 0; i < 3; ++i) d[KB_HALF + i] = s[TS_JD_HALF + i];
+      d[KB_RBOUND] = norm3(s + TS_JD_HALF);
+    }
     od.insert(od.end(), d, d + KB_DSTRIDE);
   }
   const double* P = db + ib[TS_I_DOFF_POINTS];
   const double* MK = db + ib[TS_I_DOFF_MARKERS];
+  const double* MAX = ib[TS_I_DOFF_MARKER_AXES] > 0 ? db + ib[TS_I_DOFF_MARKER_AXES] : (const double*)0;
+  int cmw = 0;               // words of the contact bitmask output, force by force (ground first)
   // ---- ground contacts
   oi[KI_O_GROUND] = (int)oi.size(); oi[KI_D_GROUND] = (int)od.size();
   for (int g = 0; g < nground; ++g) {
     const int* r = ib + ib[TS_I_OFF_GROUND] + g * TS_GI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GROUND] + g * TS_CD_STRIDE;
-    if (g == 0 && r[2] > 32) return "more than 32 ground contact points per body are not supported";
-    oi.insert(oi.end(), r, r + KG_ISTRIDE);
+    if (r[2] > 32) return "more than 32 ground contact points per body are not supported";
+    int rec[KG_ISTRIDE] = {r[0], r[1], r[2], cmw};
+    cmw += 1;
+    oi.insert(oi.end(), rec, rec + KG_ISTRIDE);
     od.insert(od.end(), c, c + KG_DSTRIDE);
   }
   // ---- general-primitive contacts
@@ -179,9 +188,13 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int f = 0; f < ngp; ++f) {
     const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GP] + f * TS_CD_STRIDE;
-    if (J[r[1] * TS_JI_STRIDE + 4] != TS_SH_CUBOID) return "general-primitive contact: only cuboid primitives are supported";
-    if (r[3] > 96) return "more than 96 contact points per general body are not supported";
-    oi.insert(oi.end(), r, r + KP_ISTRIDE);
+    const int shape2 = J[r[1] * TS_JI_STRIDE + 4];
+    if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER)
+      return "general-primitive contact: only cuboid and cylinder primitives are supported";
+    if (r[3] > 32 * KT_MAXPW) return "scene exceeds the compiled capacity (sampled points per general body)";
+    int rec[KP_ISTRIDE] = {r[0], r[1], r[2], r[3], cmw, shape2};
+    cmw += (r[3] + 31) / 32;
+    oi.insert(oi.end(), rec, rec + KP_ISTRIDE);
     double d[KP_DSTRIDE] = {c[0], c[1], c[2], c[3], 0};
     for (int i = 0; i < 3; ++i) { d[KP_BBOX + i] = 1e300; d[KP_BBOX + 3 + i] = -1e300; }
     for (int k = 0; k < r[3]; ++k) {
@@ -222,8 +235,10 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int* r = ib + ib[TS_I_OFF_SENSOR] + s * TS_SI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_SENSOR] + s * TS_SD_STRIDE;
     if (r[3] > KT_MAXCAND) return "too many tactile candidate bodies";
-    for (int k = 0; k < r[3]; ++k)
-      if (J[r[4 + k] * TS_JI_STRIDE + 4] != TS_SH_CUBOID) return "tactile candidates must be cuboids";
+    for (int k = 0; k < r[3]; ++k) {
+      const int sh = J[r[4 + k] * TS_JI_STRIDE + 4];
+      if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER) return "tactile candidates must be cuboids or cylinders";
+    }
     oi.insert(oi.end(), r, r + KS_ISTRIDE);
     double d[KS_DSTRIDE] = {0};
     for (int i = 0; i < 13; ++i) d[i] = c[i];
@@ -239,8 +254,18 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   }
   oi[KI_D_POINTS] = (int)od.size();
   od.insert(od.end(), P, P + 3 * npoints);
+  oi[KI_CMW] = cmw;
+  // markers last (the kernels stage everything before them in shared memory): position + per-marker axes
   oi[KI_D_MARKERS] = (int)od.size();
-  od.insert(od.end(), MK, MK + 3 * nmark);
+  for (int s = 0; s < nsens; ++s) {
+    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * TS_SI_STRIDE;
+    const double* c = db + ib[TS_I_DOFF_SENSOR] + s * TS_SD_STRIDE;
+    for (int k = r[1]; k < r[1] + r[2]; ++k) {
+      od.insert(od.end(), MK + 3 * k, MK + 3 * k + 3);
+      if (MAX) od.insert(od.end(), MAX + 9 * k, MAX + 9 * k + 9);
+      else od.insert(od.end(), c + 4, c + 13);
+    }
+  }
   (void)nd;
   return "";
 }

@@ -66,6 +66,8 @@
 struct SceneView {
   const int* ib;
   const double* db;
+  const double* mk;      // marker table (KM_STRIDE doubles per marker): global memory on the GPU
+  int cmw;               // words of the contact bitmask output per env-step
   int nj, n, nu, nee, nmark, nground, ngp, nact, nsens, max_iter, max_ls, nbody;
   int o_joint, o_body, o_ground, o_gp, o_act, o_ee, o_sensor;
   int d_joint, d_body, d_ground, d_gp, d_act, d_ee, d_sensor, d_points, d_markers;
@@ -78,6 +80,8 @@ HDN inline void scene_view_init(SceneView& S, const int* ib, const double* db) {
   S.nmark = ib[KI_NMARK]; S.nground = ib[KI_NGROUND]; S.ngp = ib[KI_NGP];
   S.nact = ib[KI_NACT]; S.nsens = ib[KI_NSENS]; S.nbody = ib[KI_NBODY];
   S.max_iter = ib[KI_MAX_ITER]; S.max_ls = ib[KI_MAX_LS];
+  S.cmw = ib[KI_CMW];
+  S.mk = db + ib[KI_D_MARKERS];
   S.o_joint = ib[KI_O_JOINT]; S.o_body = ib[KI_O_BODY]; S.o_ground = ib[KI_O_GROUND]; S.o_gp = ib[KI_O_GP];
   S.o_act = ib[KI_O_ACT]; S.o_ee = ib[KI_O_EE]; S.o_sensor = ib[KI_O_SENSOR];
   S.d_joint = ib[KI_D_JOINT]; S.d_body = ib[KI_D_BODY]; S.d_ground = ib[KI_D_GROUND]; S.d_gp = ib[KI_D_GP];
@@ -605,28 +609,85 @@ HD void gp_point_force(const GpPair<T>& P, const double* xi1, const double* hs, 
   for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
 }
 
-template <class Tile> HD double tile_xfer(const Tile& tl, double v, int src) { return tl.warp_shfl(v, src); }
-template <class Tile> HD Dual tile_xfer(const Tile& tl, Dual v, int src) { return mkdual(tl.warp_shfl(v.v, src), tl.warp_shfl(v.d, src)); }
-template <class Tile> HD double tiles_sum(const Tile& tl, double v) { return tl.sum_tiles(v); }
-template <class Tile> HD Dual tiles_sum(const Tile& tl, Dual v) { return mkdual(tl.sum_tiles(v.v), tl.sum_tiles(v.d)); }
+// ---- cylinder SDF (DH/Body/BodyCylinder.cpp:88-139: radial distance only, no contact with the caps)
+// distance(xw) < 0 with the reference's evaluation order: x = R2^T xw + (-(R2^T p2))  (E_i0 = Einv(E_0i))
+HD bool cylinder_inside_world(const double* R2, const double* p2, const double* xw, const double* rh) {
+  double t[3], x[3];
+  mtv3(R2, p2, t);
+  mtv3(R2, xw, x);
+  for (int i = 0; i < 3; ++i) x[i] = x[i] + (-t[i]);
+  if (x[2] < -rh[1]) return false;
+  if (x[2] > rh[1]) return false;
+  return sqrt(x[0] * x[0] + x[1] * x[1]) - rh[0] < 0.0;
+}
 
-// sampled points of a general body vs a cuboid SDF: DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
-// DH/Body/BodyCuboid.cpp:146-184, detection d < 0: CollisionDetection.cpp:66-83.
-// Detection is dealt to the lanes of the tile and gathered by ballot.
-// Experimental (-DTS_COOP_CONTACTS, off: measured slower on B200 because of the register pressure of the
-// extra path): when only few tiles of the warp are in contact, their active points are dealt to ALL
-// tiles of the warp and the partial wrenches summed back by shuffles; the function must then be
-// reached by every lane of the warp together.
+// Penalty force of ONE active sampled point against a CYLINDER (DH/Force/ForceGeneralPrimitiveContact.cpp:154-229
+// with DH/Body/BodyCylinder.cpp:105-139): same structure as gp_point_force, the normal e = x_r / |x_r| now
+// depends on the point.  Wrenches in cylinder coordinates about the cylinder origin.
+template <class T>
+HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* rh, double kn, double kt, double mu,
+                           double damp, T* w1, T* w2) {
+  T ap[3], x[3];
+  mv3(P.Q, xi1, ap);
+  for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
+  T u[3], t3[3];
+  cross3(P.w1b, ap, u);
+  cross3(P.ph2, x, t3);
+  for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
+  T r = dsqrt(x[0] * x[0] + x[1] * x[1]);
+  T e[3];
+  e[0] = x[0] / r; e[1] = x[1] / r; e[2] = 0.0;
+  T d = r - rh[0];
+  T ddot = dot3(e, u);
+  T tb[3];
+  cross3(P.ph2, e, t3);
+  for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
+  T et = dot3(e, tb);
+  for (int i = 0; i < 3; ++i) tb[i] = tb[i] - e[i] * et;
+  T s = kn * d - damp * ddot * d;
+  T Fb[3];
+  for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
+  if (mu > TS_EPS) {
+    T n1[3], m1[3];
+    mtv3(P.Q, e, n1);                       // normal in body-1 coordinates: R1^T R2 e
+    cross3(xi1, n1, m1);
+    double n6 = 0.0;
+    for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
+    double fcn = fabs(val(s)) * sqrt(n6);
+    double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
+    if (mu * fcn >= kt * tn - TS_EPS) {
+      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
+    } else {
+      T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
+      T fcT = dabs(s) * dsqrt(n6T);
+      T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
+      T sc = mu * fcT / tnT;
+      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+    }
+  }
+  T xi2[3], tq[3];
+  for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
+  cross3(xi2, Fb, tq);
+  for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
+  cross3(x, Fb, tq);
+  for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
+}
+
+// sampled points of a general body vs a primitive SDF (cuboid or cylinder):
+// DH/Force/ForceGeneralPrimitiveContact.cpp:154-229, DH/Body/BodyCuboid.cpp:146-184, BodyCylinder.cpp:105-139,
+// detection d < 0: CollisionDetection.cpp:66-83.
+// Detection is dealt to the lanes of the tile and gathered by ballot.  (A warp-cooperative evaluation of the
+// active points was measured slower on B200 -- register pressure -- and is kept as tools/experiments/*.patch.)
 template <class Tile, class WK>
 HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
   typedef typename WK::Scalar T;
   const int L = Tile::LPE;
-  const int TPW = Tile::TPW;
   const double h2 = S.h * S.h;
   for (int fi = 0; fi < S.ngp; ++fi) {
     const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
     const double* c = S.db + S.d_gp + fi * KP_DSTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
+    const bool cyl = r[5] == TS_SH_CYLINDER;
     const int j1 = S.ib[S.o_body + b1 * KB_ISTRIDE], j2 = S.ib[S.o_body + b2 * KB_ISTRIDE];
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
@@ -635,15 +696,19 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     double phv[6];
     body_frame_v(S, W, b1, P.R1v, P.p1v, phv);
     body_frame_v(S, W, b2, P.R2v, P.p2v, phv);
-    unsigned act[3] = {0u, 0u, 0u};
+    unsigned act[KT_MAXPW];
+    for (int i = 0; i < KT_MAXPW; ++i) act[i] = 0u;
     {
-      // exact-safe culls on values: bounding spheres, then the bounding box of the point set against the
-      // face planes of the box
+      // exact-safe culls on values: bounding spheres, then (cuboid) the bounding box of the point set against
+      // the face planes of the box
       const double rr = c[4] + bd2[KB_RBOUND] + TS_CULL_MARGIN;
       const double dx = P.p1v[0] - P.p2v[0], dy = P.p1v[1] - P.p2v[1], dz = P.p1v[2] - P.p2v[2];
       double R21[9], r21[3];
-      rel_frame(P.R1v, P.p1v, P.R2v, P.p2v, R21, r21);
-      const bool maybe = !(dx * dx + dy * dy + dz * dz > rr * rr) && !bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs);
+      bool maybe = !(dx * dx + dy * dy + dz * dz > rr * rr);
+      if (maybe && !cyl) {
+        rel_frame(P.R1v, P.p1v, P.R2v, P.p2v, R21, r21);
+        maybe = !bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs);
+      }
       // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
       if (maybe) {
         for (int base = 0; base < pc; base += L) {
@@ -651,14 +716,21 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
           bool in = false;
           if (k < pc) {
             const double* xi1 = S.db + S.d_points + 3 * (po + k);
-            const int cls = cuboid_classify(R21, r21, xi1, hs);
-            if (cls > 0) in = true;
-            else if (cls == 0) {                 // reference evaluation order (CollisionDetection.cpp:73-79)
-              double xwv[3], yv[3], xv[3];
+            if (cyl) {
+              double xwv[3];
               mv3(P.R1v, xi1, xwv);
-              for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
-              mtv3(P.R2v, yv, xv);
-              in = cuboid_inside(xv, hs);
+              for (int i = 0; i < 3; ++i) xwv[i] = xwv[i] + P.p1v[i];
+              in = cylinder_inside_world(P.R2v, P.p2v, xwv, hs);
+            } else {
+              const int cls = cuboid_classify(R21, r21, xi1, hs);
+              if (cls > 0) in = true;
+              else if (cls == 0) {                 // reference evaluation order (CollisionDetection.cpp:73-79)
+                double xwv[3], yv[3], xv[3];
+                mv3(P.R1v, xi1, xwv);
+                for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
+                mtv3(P.R2v, yv, xv);
+                in = cuboid_inside(xv, hs);
+              }
             }
           }
           const unsigned bits = tl.ballot(in);
@@ -666,19 +738,12 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
         }
       }
     }
-    const bool has = (act[0] | act[1] | act[2]) != 0u;
-#ifdef TS_COOP_CONTACTS
-    const unsigned tmask = tl.tiles_ballot(has);      // bit t: tile t of this warp is in contact (warp-uniform)
-#else
-    const unsigned tmask = has ? 1u : 0u;
-#endif
-    if (!tmask) continue;
-    // the tile's own relative kinematics in the BOX frame (dual numbers)
+    unsigned any = 0u;
+    for (int i = 0; i < KT_MAXPW; ++i) any |= act[i];
+    if (!any) continue;
+    // the tile's own relative kinematics in the frame of body 2 (dual numbers)
     T R2[9], p2[3];
-    for (int i = 0; i < 9; ++i) P.Q[i] = 0.0;
-    for (int i = 0; i < 3; ++i) { P.rr[i] = 0.0; P.w1b[i] = 0.0; P.v1b[i] = 0.0; }
-    for (int i = 0; i < 6; ++i) P.ph2[i] = 0.0;
-    if (has) {
+    {
       T R1[9], p1[3], ph1[6], dp[3];
       body_frame(S, W, b1, R1, p1, ph1);
       body_frame(S, W, b2, R2, p2, P.ph2);
@@ -689,60 +754,19 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
       mv3(P.Q, ph1, P.w1b);
       mv3(P.Q, ph1 + 3, P.v1b);
     }
-    T w1[6], w2[6];          // wrenches on body 1 / body 2, both in box coordinates about the box origin
+    T w1[6], w2[6];          // wrenches on body 1 / body 2, both in body-2 coordinates about its origin
     for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
-    int nct = 0;
-    for (unsigned tm = tmask; tm; tm &= tm - 1) ++nct;
-#ifdef TS_COOP_CONTACTS
-    const bool coop = TPW > 1 && 2 * nct <= TPW;
-#else
-    const bool coop = false;   // measured slower on B200 (register pressure of the extra path): kept for experiments
-#endif
-    if (coop) {
-      // few tiles in contact: deal the active points of each of them to all tiles of the warp
-      const int mytile = tl.tile_in_warp();
-      for (unsigned tm = tmask; tm; tm &= tm - 1) {
-        const int A = ts_ffs(tm);
-        const int src = A * L + tl.lane;               // the lane of tile A that carries my tangent
-        GpPair<T> PA;
-        for (int i = 0; i < 9; ++i) { PA.Q[i] = tile_xfer(tl, P.Q[i], src); PA.R1v[i] = tl.warp_shfl(P.R1v[i], src); PA.R2v[i] = tl.warp_shfl(P.R2v[i], src); }
-        for (int i = 0; i < 3; ++i) {
-          PA.rr[i] = tile_xfer(tl, P.rr[i], src); PA.w1b[i] = tile_xfer(tl, P.w1b[i], src); PA.v1b[i] = tile_xfer(tl, P.v1b[i], src);
-          PA.p1v[i] = tl.warp_shfl(P.p1v[i], src); PA.p2v[i] = tl.warp_shfl(P.p2v[i], src);
-        }
-        for (int i = 0; i < 6; ++i) PA.ph2[i] = tile_xfer(tl, P.ph2[i], src);
-        T a1[6], a2[6];
-        for (int i = 0; i < 6; ++i) { a1[i] = 0.0; a2[i] = 0.0; }
-        for (int wd = 0; wd < 3; ++wd) {
-          unsigned m = tl.warp_shfl_u(act[wd], src);
-          while (m) {
-            // the next TPW active points, one per tile, so that all tiles work in the same pass
-            int myk = -1;
-            for (int t = 0; t < TPW && m; ++t) {
-              const int kk = ts_ffs(m);
-              m &= m - 1;
-              if (t == mytile) myk = kk;
-            }
-            if (myk >= 0) gp_point_force(PA, S.db + S.d_points + 3 * (po + 32 * wd + myk), hs, kn, kt, mu, damp, a1, a2);
-          }
-        }
-        for (int i = 0; i < 6; ++i) { a1[i] = tiles_sum(tl, a1[i]); a2[i] = tiles_sum(tl, a2[i]); }
-        if (mytile == A) for (int i = 0; i < 6; ++i) { w1[i] = a1[i]; w2[i] = a2[i]; }
-      }
-    } else if (has) {
-      for (int wd = 0; wd < 3; ++wd) {
-        unsigned m = act[wd];
-        while (m) {
-          const int k = 32 * wd + ts_ffs(m);
-          m &= m - 1;
-          gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
-        }
+    for (int wd = 0; wd < KT_MAXPW; ++wd) {
+      unsigned m = act[wd];
+      while (m) {
+        const int k = 32 * wd + ts_ffs(m);
+        m &= m - 1;
+        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
+        else gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
       }
     }
-    if (has) {
-      push_wrench(W, j1, R2, p2, w1, -h2);
-      push_wrench(W, j2, R2, p2, w2, -h2);
-    }
+    push_wrench(W, j1, R2, p2, w1, -h2);
+    push_wrench(W, j2, R2, p2, w2, -h2);
   }
 }
 
@@ -1293,11 +1317,12 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
   F.near[0] = true;
   for (int c = 0; c < nc; ++c) {
     const int b2 = sr[4 + c];
+    const bool cyl = S.ib[S.o_body + b2 * KB_ISTRIDE + 1] == TS_SH_CYLINDER;
     body_frame_v(S, W, b2, F.R[1 + c], F.p[1 + c], F.ph[1 + c]);
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
     F.near[1 + c] = !(dx * dx + dy * dy + dz * dz > rr * rr);
-    if (F.near[1 + c]) {
+    if (F.near[1 + c] && !cyl) {
       rel_frame(F.R[0], F.p[0], F.R[1 + c], F.p[1 + c], F.R21[c], F.r21[c]);
       if (bbox_outside_box(F.R21[c], F.r21[c], sd + KS_BBOX, sd + KS_BBOX + 3, S.db + S.d_body + b2 * KB_DSTRIDE + KB_HALF))
         F.near[1 + c] = false;
@@ -1308,34 +1333,57 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
 // per-marker intermediate of the tactile force, shared by the value pass and its adjoint
 struct MarkerHit {
   int cand;           // index of the contacted candidate (last candidate with d < 0), -1 if none
-  int ax; double sg;  // face of the box
-  double x[3], u[3], d, ddot, tb[3], s, tn;
+  bool cyl;           // the candidate is a cylinder (normal depends on the point), else a cuboid (face normal)
+  double e[3];        // contact normal in the candidate's frame
+  double x[3], u[3], d, ddot, tb[3], s, tn, rad;
   bool dynamic;
 };
 
-// Evaluate one marker of sensor record (sr, sd).  DH/Sensor/TactileSensor.cpp:29-87
+// Evaluate one marker of sensor record (sr, sd).  DH/Sensor/TactileSensor.cpp:29-87 with the SDFs of
+// DH/Body/BodyCuboid.cpp:135-184 and DH/Body/BodyCylinder.cpp:88-139.
 HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const double* sd, const double* xi1,
                      MarkerHit& H, double* F1 /* force in the pad frame */) {
   const int nc = sr[3];
   const double kn = sd[0], kt = sd[1], mu = sd[2], damp = sd[3];
   const double* R1 = F.R[0]; const double* p1 = F.p[0]; const double* ph1 = F.ph[0];
   H.cand = -1;
+  H.cyl = false;
   for (int c = 0; c < nc; ++c) {
     if (!F.near[1 + c]) continue;
     const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
+    double xw[3], y[3], x[3];
+    if (S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CYLINDER) {
+      mv3(R1, xi1, xw);
+      for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+      if (!cylinder_inside_world(F.R[1 + c], F.p[1 + c], xw, hs)) continue;
+      // the force is evaluated at x = R2^T (xw - p2)  (BodyCylinder.cpp:118)
+      for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
+      mtv3(F.R[1 + c], y, x);
+      H.cand = c; H.cyl = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
+      continue;
+    }
     if (cuboid_classify(F.R21[c], F.r21[c], xi1, hs) < 0) continue;   // surely outside
     // reference evaluation order (TactileSensor.cpp:44-47); also yields the exact box-frame point
-    double xw[3], y[3], x[3];
     mv3(R1, xi1, xw);
     for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - F.p[1 + c][i];
     mtv3(F.R[1 + c], y, x);
-    if (cuboid_inside(x, hs)) { H.cand = c; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
+    if (cuboid_inside(x, hs)) { H.cand = c; H.cyl = false; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
   }
   F1[0] = F1[1] = F1[2] = 0.0;
   if (H.cand < 0) return;
   const double* hs = S.db + S.d_body + sr[4 + H.cand] * KB_DSTRIDE + KB_HALF;
   const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
-  H.d = cuboid_face(H.x, hs, H.ax, H.sg);
+  if (H.cyl) {
+    H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1]);
+    H.d = H.rad - hs[0];
+    H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = 0.0;
+  } else {
+    int ax; double sg;
+    H.d = cuboid_face(H.x, hs, ax, sg);
+    H.e[0] = H.e[1] = H.e[2] = 0.0;
+    H.e[ax] = sg;
+    H.rad = 0.0;
+  }
   double v1[3], xwd[3], t3[3];
   cross3(ph1, xi1, v1);
   for (int i = 0; i < 3; ++i) v1[i] += ph1[3 + i];
@@ -1343,15 +1391,14 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
   mtv3(R2, xwd, H.u);
   cross3(ph2, H.x, t3);
   for (int i = 0; i < 3; ++i) H.u[i] = H.u[i] - t3[i] - ph2[3 + i];
-  H.ddot = H.sg * H.u[H.ax];
-  double e[3] = {0.0, 0.0, 0.0};
-  e[H.ax] = H.sg;
-  cross3(ph2, e, t3);
+  H.ddot = dot3(H.e, H.u);
+  cross3(ph2, H.e, t3);
   for (int i = 0; i < 3; ++i) H.tb[i] = H.u[i] + H.d * t3[i];
-  H.tb[H.ax] -= H.sg * (H.sg * H.tb[H.ax]);
+  const double et = dot3(H.e, H.tb);
+  for (int i = 0; i < 3; ++i) H.tb[i] -= H.e[i] * et;
   H.s = kn * H.d - damp * H.ddot * H.d;
   double Fb[3];
-  for (int i = 0; i < 3; ++i) Fb[i] = -(H.s * e[i]);
+  for (int i = 0; i < 3; ++i) Fb[i] = -(H.s * H.e[i]);
   H.dynamic = false;
   H.tn = sqrt(H.tb[0] * H.tb[0] + H.tb[1] * H.tb[1] + H.tb[2] * H.tb[2]);
   if (mu > TS_EPS) {
@@ -1391,13 +1438,13 @@ HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, 
     }
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
       double* o = out + 3 * (mo + m);
-      const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
+      const double* mk = S.mk + KM_STRIDE * (mo + m);     // position, axis0, axis1, normal
       MarkerHit H;
       double F1[3];
-      marker_force(S, F, sr, sd, xi1, H, F1);
-      o[0] = dot3(F1, sd + 4);
-      o[1] = dot3(F1, sd + 7);
-      o[2] = -dot3(F1, sd + 10);
+      marker_force(S, F, sr, sd, mk, H, F1);
+      o[0] = dot3(F1, mk + 3);
+      o[1] = dot3(F1, mk + 6);
+      o[2] = -dot3(F1, mk + 9);
       if (body_out) body_out[mo + m] = H.cand < 0 ? -1 : sr[4 + H.cand];
     }
   }
@@ -1409,13 +1456,13 @@ struct TacAcc {
   double v[24];
 };
 
-// Reverse-mode through marker_force for every marker of this lane's stride.  Returns (tile-wide)
-// whether any marker is in contact; acc is only meaningful then.
+// Reverse-mode through marker_force for every marker of sensor si in this lane's stride.  Returns
+// (tile-wide) whether any marker is in contact; acc is only meaningful then.
 template <class Tile, class WK>
-HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, const double* wbar, TacAcc* acc) {
+HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, int si, const double* wbar, TacAcc* acc) {
   for (int c = 0; c < TS_MAXCAND; ++c) for (int i = 0; i < 24; ++i) acc[c].v[i] = 0.0;
   double hits = 0.0;
-  for (int si = 0; si < S.nsens; ++si) {
+  {
     const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
     const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
     const int mo = sr[1], mc = sr[2];
@@ -1426,10 +1473,11 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, const double* wb
     tl.tile_sync();
     bool anynear = false;
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
-    if (!anynear) continue;
+    if (!anynear) return false;
     const double* R1 = F.R[0]; const double* ph1 = F.ph[0];
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
-      const double* xi1 = S.db + S.d_markers + 3 * (mo + m);
+      const double* mk = S.mk + KM_STRIDE * (mo + m);
+      const double* xi1 = mk;
       const double* wb = wbar + 3 * (mo + m);
       MarkerHit H;
       double F1[3];
@@ -1438,16 +1486,15 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, const double* wb
       hits += 1.0;
       double* A = acc[H.cand].v;
       const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
+      const double* e = H.e;
       double R21[9];
       for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R21[3 * i + j] = R2[i] * R1[j] + R2[3 + i] * R1[3 + j] + R2[6 + i] * R1[6 + j];
-      double e[3] = {0.0, 0.0, 0.0};
-      e[H.ax] = H.sg;
-      // F1 = R21^T Fb ; tau = P^T F1 with P = [axis0, axis1, -normal]
+      // F1 = R21^T Fb ; tau = P^T F1 with P = [axis0, axis1, -normal] of this marker
       double F1b[3], Fbb[3], Fb[3];
-      for (int i = 0; i < 3; ++i) F1b[i] = sd[4 + i] * wb[0] + sd[7 + i] * wb[1] - sd[10 + i] * wb[2];
+      for (int i = 0; i < 3; ++i) F1b[i] = mk[3 + i] * wb[0] + mk[6 + i] * wb[1] - mk[9 + i] * wb[2];
       mv3(R21, F1b, Fbb);
-      // recompute Fb (box frame) for the R21 cotangent
+      // recompute Fb (candidate frame) for the R21 cotangent
       for (int i = 0; i < 3; ++i) Fb[i] = -(H.s * e[i]);
       double sbar, tbar[3];
       if (!(mu > TS_EPS)) {
@@ -1470,15 +1517,26 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, const double* wb
       double ddbar = -sbar * damp * H.d;
       // tb = (I - e e^T) u + d (w2 x e)
       double ubar[3], w2e[3], t3[3];
-      for (int i = 0; i < 3; ++i) ubar[i] = tbar[i];
-      ubar[H.ax] -= H.sg * (H.sg * tbar[H.ax]);
+      const double etb = dot3(e, tbar);
+      for (int i = 0; i < 3; ++i) ubar[i] = tbar[i] - e[i] * etb;
       cross3(ph2, e, w2e);
       dbar += dot3(tbar, w2e);
       cross3(e, tbar, t3);
       double w2bar[3], v2bar[3], xbar[3];
       for (int i = 0; i < 3; ++i) w2bar[i] = H.d * t3[i];
+      if (H.cyl) {
+        // the normal e = x_r / |x_r| moves with the point: Fb = -s e - ..., ddot = e.u, tb = u - e (e.u) + d (w2 x e)
+        double ebar[3], tw[3];
+        const double eu = dot3(e, H.u);
+        cross3(tbar, ph2, tw);
+        for (int i = 0; i < 3; ++i) ebar[i] = -H.s * Fbb[i] + ddbar * H.u[i] - eu * tbar[i] - etb * H.u[i] + H.d * tw[i];
+        ebar[2] = 0.0;
+        const double ee = dot3(e, ebar);
+        for (int i = 0; i < 3; ++i) xbar[i] = dbar * e[i] + (ebar[i] - e[i] * ee) / H.rad;
+      } else {
+        for (int i = 0; i < 3; ++i) xbar[i] = dbar * e[i];
+      }
       for (int i = 0; i < 3; ++i) ubar[i] += ddbar * e[i];
-      for (int i = 0; i < 3; ++i) xbar[i] = dbar * e[i];
       // u = R21 w - w2 x x - v2 ,  w = w1 x xi1 + v1
       double w[3], wbar_[3];
       cross3(ph1, xi1, w);
@@ -1548,8 +1606,6 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
       in.k = k;
       tl.tile_sync();
       kinematics(S, in, WD, false);
-      // the values of the Dual work space are the kinematics of the state: the marker pass reads them
-      if (c == 0 && have_tac) have_tac = tactile_vjp(tl, S, WD, dtac_cot, acc);
       double yk = 0.0, ck = 0.0;
       if (have_var) {
         for (int e = 0; e < S.nee; ++e) {
@@ -1560,6 +1616,8 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
       }
       if (have_tac) {
         for (int si = 0; si < S.nsens; ++si) {
+          // the values of the Dual work space are the kinematics of the state: the marker pass reads them
+          if (!tactile_vjp(tl, S, WD, si, dtac_cot, acc)) continue;
           const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
           const int b1 = sr[0], nc = sr[3];
           Dual R1[9], p1[3], ph1[6];
@@ -1654,13 +1712,15 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
 }
 
 // ------------------------------------------------------------------ contact index sets (diagnostic outputs)
-// word 0: ground force 0, points 0..31; words 1..3: general-primitive force 0, points 0..95.
+// S.cmw words per env-step, force by force in scene order (ground forces first, one word each; then the
+// general-primitive forces, ceil(points / 32) words each): bit k of a force = its sampled point k is active.
+// TactilePush: word 0 = ground force, words 1..3 = pad-box force.
 template <class WK>
-HDN void contact_sets(const SceneView& S, const WK& W, unsigned* m4) {
-  m4[0] = m4[1] = m4[2] = m4[3] = 0u;
+HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
+  for (int i = 0; i < S.cmw; ++i) mw[i] = 0u;
   double R1[9], p1[3], R2[9], p2[3], ph[6];
-  if (S.nground > 0) {
-    const int* r = S.ib + S.o_ground;
+  for (int gi = 0; gi < S.nground; ++gi) {
+    const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
     const int b = r[0], po = r[1], pc = r[2];
     body_frame_v(S, W, b, R1, p1, ph);
     for (int k = 0; k < pc && k < 32; ++k) {
@@ -1669,22 +1729,29 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* m4) {
       mv3(R1, xi, xw);
       double d = (xw[0] + p1[0] - S.gx[0]) * S.gn[0] + (xw[1] + p1[1] - S.gx[1]) * S.gn[1] +
                  (xw[2] + p1[2] - S.gx[2]) * S.gn[2];
-      if (d <= 0.0) m4[0] |= (1u << k);
+      if (d <= 0.0) mw[r[3]] |= (1u << k);
     }
   }
-  if (S.ngp > 0) {
-    const int* r = S.ib + S.o_gp;
+  for (int fi = 0; fi < S.ngp; ++fi) {
+    const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
     const double* hs = S.db + S.d_body + b2 * KB_DSTRIDE + KB_HALF;
     body_frame_v(S, W, b1, R1, p1, ph);
     body_frame_v(S, W, b2, R2, p2, ph);
-    for (int k = 0; k < pc && k < 96; ++k) {
+    for (int k = 0; k < pc; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
       double xw[3], y[3], x[3];
       mv3(R1, xi, xw);
-      for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
-      mtv3(R2, y, x);
-      if (cuboid_distance(x, hs) < 0.0) m4[1 + (k >> 5)] |= (1u << (k & 31));
+      bool in;
+      if (r[5] == TS_SH_CYLINDER) {
+        for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+        in = cylinder_inside_world(R2, p2, xw, hs);
+      } else {
+        for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - p2[i];
+        mtv3(R2, y, x);
+        in = cuboid_distance(x, hs) < 0.0;
+      }
+      if (in) mw[r[4] + (k >> 5)] |= (1u << (k & 31));
     }
   }
 }
@@ -1698,7 +1765,7 @@ struct FwdArgs {
   double* tac_out; const int* tac_row; // [rows,B,3M]
   double* tape;                       // [T,B,3,n,n] or null
   int* status;                        // [T,B] or null
-  unsigned* cmask;                    // [T,B,4] or null
+  unsigned* cmask;                    // [T,B,cmw] or null
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
   int ls_batch;                       // TSIM_OPT_LS_BATCH
 };
@@ -1756,15 +1823,10 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     {
       TS_TIC2(tl);
       double cole[TS_NC(Tile::LPE)][TS_MAXN];
-#ifdef TS_COOP_CONTACTS
-      step_eval(tl, S, v, WD, cole);                     // whole-warp votes inside: every tile evaluates
-      if (!tile_done) tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, cole);
-#else
       if (!tile_done) {
         step_eval(tl, S, v, WD, cole);
         tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, cole);
       }
-#endif
       TS_TOC2(tl, 5);
     }
     if (!tl.warp_all(tile_done)) continue;
@@ -1794,7 +1856,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
                           vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
                           tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
                           (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
-                          a.cmask ? a.cmask + es * 4 : (unsigned*)0);
+                          a.cmask ? a.cmask + es * S.cmw : (unsigned*)0);
       }
     }
     ++t;

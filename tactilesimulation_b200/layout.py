@@ -8,7 +8,8 @@ from . import scene as S
 
 TS_MAGIC = 0x54533230
 TS_VERSION = 3
-MAXB, MAXN, MAXCAND = 16, 8, 4   # kernel capacities (csrc/kernel_layout.h): bodies, dofs, candidates
+MAXB, MAXN, MAXCAND = 24, 16, 4   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
+I_DOFF_MARKER_AXES = 22           # header slot: offset of the per-marker (axis0, axis1, normal) section, 0 = none
 I_HEADER, D_HEADER = 32, 16
 JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 8
 JD, CD, AD, ED, SD = 48, 4, 12, 4, 16
@@ -19,8 +20,6 @@ def pack_scene(sc: "S.Scene"):
         raise S.SceneError(f"integrator {sc.integrator} is not supported by the B200 path yet (BDF1 only)")
     if sc.nj > MAXB or sc.ndof_r > MAXN:
         raise S.SceneError(f"scene too large for this build: nj={sc.nj} (max {MAXB}), ndof_r={sc.ndof_r} (max {MAXN})")
-    if len(sc.sensors) > 1:
-        raise S.SceneError("more than one tactile sensor is not supported by the B200 path yet")
     for a in sc.actuators:
         if a["mode"] != S.ACT_FORCE:
             raise S.SceneError("position-controlled motors are not supported by the B200 path yet")
@@ -122,9 +121,6 @@ def pack_scene(sc: "S.Scene"):
     for i, s in enumerate(sc.sensors):
         if len(s.candidates) > MAXCAND:
             raise S.SceneError(f"more than {MAXCAND} tactile candidate bodies are not supported yet")
-        for arr in (s.axis0, s.axis1, s.normal):
-            if np.abs(arr - arr[0]).max() > 0:
-                raise S.SceneError("per-marker tactile axes are not supported by the B200 path yet")
         si[i, :4] = [s.body, moff, len(s.pos), len(s.candidates)]
         si[i, 4:4 + len(s.candidates)] = s.candidates
         sd[i, :4] = [s.kn, s.kt, s.mu, s.damping]
@@ -143,6 +139,11 @@ def pack_scene(sc: "S.Scene"):
     hdr[31] = doff()
     Mk = np.concatenate(markers, axis=0) if markers else np.zeros((0, 3))
     dbls.append(Mk.reshape(-1))
+    # per-marker (axis0, axis1, normal): abstract sensors carry them per marker (DH/Sensor/TactileSensorAbstract.cpp)
+    if sc.sensors:
+        hdr[I_DOFF_MARKER_AXES] = doff()
+        ax = np.concatenate([np.concatenate([s.axis0, s.axis1, s.normal], axis=1) for s in sc.sensors], axis=0)
+        dbls.append(ax.reshape(-1))
     ibuf = np.concatenate(ints).astype(np.int32)
     dbuf = np.concatenate(dbls).astype(np.float64)
     return ibuf, dbuf
@@ -205,9 +206,13 @@ def scene_from_blob(ibuf, dbuf):
     for i in range(nsens):
         r = ib[ib[21] + i * SI: ib[21] + (i + 1) * SI]; d = db[ib[29] + i * SD: ib[29] + (i + 1) * SD]
         M = int(r[2])
+        if ib[I_DOFF_MARKER_AXES] > 0:
+            A = db[ib[I_DOFF_MARKER_AXES] + 9 * r[1]: ib[I_DOFF_MARKER_AXES] + 9 * (r[1] + M)].reshape(M, 9)
+            a0, a1, nr = A[:, 0:3].copy(), A[:, 3:6].copy(), A[:, 6:9].copy()
+        else:
+            a0, a1, nr = np.tile(d[4:7], (M, 1)), np.tile(d[7:10], (M, 1)), np.tile(d[10:13], (M, 1))
         sc.sensors.append(S.TactileSensor(name=f"sensor{i}", body=int(r[0]), kn=d[0], kt=d[1], mu=d[2], damping=d[3],
-                                          pos=Mk[r[1]:r[1] + M].copy(), axis0=np.tile(d[4:7], (M, 1)),
-                                          axis1=np.tile(d[7:10], (M, 1)), normal=np.tile(d[10:13], (M, 1)),
+                                          pos=Mk[r[1]:r[1] + M].copy(), axis0=a0, axis1=a1, normal=nr,
                                           image_pos=np.zeros((M, 2), dtype=np.int64),
                                           candidates=[int(c) for c in r[4:4 + r[3]]]))
     return sc

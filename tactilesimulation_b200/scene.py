@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -199,6 +200,7 @@ class Scene:
     E_ji: List[np.ndarray] = field(default_factory=list)
     inertia: List[np.ndarray] = field(default_factory=list)   # (6,) Ixx Iyy Izz m m m
     shape: List[int] = field(default_factory=list)
+    btype: List[str] = field(default_factory=list)            # XML body type
     size: List[np.ndarray] = field(default_factory=list)      # cuboid: lengths; cylinder: (r, l, 0)
     contact_points: List[np.ndarray] = field(default_factory=list)
     E_g: np.ndarray = field(default_factory=lambda: np.eye(4))
@@ -454,11 +456,34 @@ def compile_scene(xml_path: str) -> Scene:
                 raise SceneError("Transform type error: " + tt)
             # mesh vertices sampled as contact points are never used by the supported
             # force types (general_primitive_contact needs them only on the general body)
+        elif btype == "abstract":
+            # DH/Simulation_Constructor.cpp:619-657, DH/Body/BodyAbstract.cpp:7-75: given mass and principal
+            # inertia; contact points from a text file (read as fp32), mapped by the <collision> frame
+            mass = _f32(bn.get("mass"))
+            I = _vec(bn.get("inertia"))
+            if I.shape[0] != 3:
+                raise SceneError("abstract bodies with a full inertia tensor are not supported by the B200 path yet")
+            inertia[:3] = I
+            inertia[3:] = mass
+            cfile, cpos, cR = bn.get("contacts"), np.zeros(3), np.eye(3)
+            cn = bn.find("collision")
+            if cfile is None and cn is not None and cn.get("contacts") is not None:
+                cfile = cn.get("contacts")
+                if cn.get("pos") is not None:
+                    cpos = _vec(cn.get("pos"))
+                if cn.get("quat") is not None:
+                    cR = quat2mat(_vec(cn.get("quat")))
+            if cfile is not None:
+                toks = open(os.path.join(asset_dir, cfile)).read().split()
+                npts = int(toks[0])
+                raw = np.array([np.float32(t) for t in toks[1:1 + 3 * npts]], dtype=np.float64).reshape(npts, 3)
+                pts = raw @ cR.T + cpos[None, :]
         else:
             raise SceneError(f"Body type not supported by the B200 path yet: {btype}")
         sc.E_ji.append(E_ji)
         sc.inertia.append(inertia)
         sc.shape.append(shape)
+        sc.btype.append(btype)
         sc.size.append(np.asarray(size, dtype=np.float64))
         sc.contact_points.append(pts)
         bname = bn.get("name", f"body{idx}")
@@ -532,10 +557,35 @@ def compile_scene(xml_path: str) -> Scene:
                 v = _attr(t, default, "tactile", key)
                 coef[key] = _f32(v) if v is not None else 0.0
             ttype = t.get("type")
+            cands = [k for k in range(sc.nj) if sc.shape[k] != SH_NONE and k != b]
+            if ttype == "abstract":
+                # DH/Sensor/TactileSensorAbstract.cpp:8-124.  Markers, normals and axes are all mapped by
+                # R_it v + p_it (the translation is applied to the direction vectors too, as the reference does);
+                # for mesh / abstract bodies the frame is first composed with E_io (identity for the
+                # principal-inertia abstract bodies supported here).
+                if sc.btype[b] == "mesh":
+                    raise SceneError("abstract tactile sensors on mesh bodies are not supported by the B200 path yet")
+                p_it = _vec(t.get("pos"))
+                R_it = quat2mat(_vec(t.get("quat")))
+                txt = open(os.path.join(asset_dir, t.get("spec"))).read()
+                N = int(txt.split()[0])
+                fields = re.findall(r'"([^"]*)"', txt)
+                if len(fields) < 5 * N:
+                    raise SceneError("Tactile spec file is incomplete: " + str(t.get("spec")))
+                pos, ipos, nrm, a0s, a1s = [], [], [], [], []
+                for i in range(N):
+                    f = fields[5 * i:5 * i + 5]
+                    pos.append(R_it @ _vec(f[0]) + p_it)
+                    ipos.append(_ivec(f[1]))
+                    nrm.append(R_it @ _vec(f[2]) + p_it)
+                    a0s.append(R_it @ _vec(f[3]) + p_it)
+                    a1s.append(R_it @ _vec(f[4]) + p_it)
+                sc.sensors.append(TactileSensor(
+                    name=t.get("name", ""), body=b, pos=np.array(pos), axis0=np.array(a0s), axis1=np.array(a1s),
+                    normal=np.array(nrm), image_pos=np.array(ipos, dtype=np.int64), candidates=cands, **coef))
+                continue
             if ttype != "rect_array":
                 raise SceneError(f"Tactile type {ttype} is not supported by the B200 path yet")
-            if sc.shape[b] == SH_NONE:
-                raise SceneError("rect_array tactile sensors need a primitive pad body")
             p0 = _vec(t.get("rect_pos0"))
             p1 = _vec(t.get("rect_pos1"))
             ax0 = _vec(t.get("axis0"))
@@ -554,7 +604,6 @@ def compile_scene(xml_path: str) -> Scene:
                     pos.append(p0 + s0 * i + s1 * j)
                     ipos.append([i, j])
             M = len(pos)
-            cands = [k for k in range(sc.nj) if sc.shape[k] != SH_NONE and k != b]
             sc.sensors.append(TactileSensor(
                 name=t.get("name", ""), body=b, pos=np.array(pos), axis0=np.tile(ax0, (M, 1)),
                 axis1=np.tile(ax1, (M, 1)), normal=np.tile(normal, (M, 1)),
@@ -606,11 +655,11 @@ def compile_scene(xml_path: str) -> Scene:
                 sc.virtual_names.append(e.get("name", ""))
     for s in sc.sensors:
         for k in s.candidates:
-            if sc.shape[k] != SH_CUBOID:
-                raise SceneError("tactile candidates other than cuboids are not supported by the B200 path yet")
+            if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER):
+                raise SceneError("tactile candidates other than cuboids and cylinders are not supported by the B200 path yet")
     for gp in sc.gp_contacts:
-        if sc.shape[gp["body2"]] != SH_CUBOID:
-            raise SceneError("primitive contact bodies other than cuboids are not supported by the B200 path yet")
+        if sc.shape[gp["body2"]] not in (SH_CUBOID, SH_CYLINDER):
+            raise SceneError("primitive contact bodies other than cuboids and cylinders are not supported by the B200 path yet")
     return sc
 
 

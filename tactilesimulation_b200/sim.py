@@ -50,6 +50,7 @@ class BatchedSim:
         _lib.check(self.lib.tsim_scene_sizes(self.handle, sizes.ctypes.data), self.lib)
         self.nj, self.ndof_r, self.ndof_m, self.ndof_u, self.ndof_var, self.ndof_tactile, self.n_markers, \
             self.tape_doubles = (int(x) for x in sizes[:8])
+        self.cmask_words = int(sizes[_lib.CMASK_WORDS])
         self.h = float(self.dbuf[0])
         self.lanes = None
         if lanes is not None:
@@ -125,7 +126,7 @@ class BatchedSim:
                           if (want_tactile and self.ndof_tactile) else None)
         out["tape"] = torch.empty((T, B, 3, n, n), dtype=torch.float64, device=dev) if grad else None
         out["status"] = torch.zeros((T, B), dtype=torch.int32, device=dev) if want_status else None
-        out["contact_masks"] = torch.zeros((T, B, 4), dtype=torch.int32, device=dev) if want_contacts else None
+        out["contact_masks"] = torch.zeros((T, B, self.cmask_words), dtype=torch.int32, device=dev) if want_contacts else None
         out["marker_body"] = (torch.full((ntr, B, self.n_markers), -1, dtype=torch.int32, device=dev)
                               if (want_contacts and out["tactile"] is not None) else None)
         with torch.cuda.device(dev):
@@ -145,7 +146,7 @@ class BatchedSim:
         var = torch.zeros((B, self.ndof_var), dtype=torch.float64, device=dev) if self.ndof_var else None
         tac = torch.zeros((B, self.ndof_tactile), dtype=torch.float64, device=dev) if self.ndof_tactile else None
         mb = torch.full((B, self.n_markers), -1, dtype=torch.int32, device=dev) if want_contacts else None
-        cm = torch.zeros((B, 4), dtype=torch.int32, device=dev) if want_contacts else None
+        cm = torch.zeros((B, self.cmask_words), dtype=torch.int32, device=dev) if want_contacts else None
         with torch.cuda.device(dev):
             _lib.check(self.lib.tsim_readout(self.handle, B, _ptr(q), _ptr(qd), _ptr(var), _ptr(tac), _ptr(mb),
                                              _ptr(cm), self._stream()), self.lib)

@@ -11,6 +11,13 @@
 
 extern "C" {
 
+// words of the contact bitmask output per env-step (tsim_scene_sizes[TSIM_CMASK_WORDS]); < 0: scene rejected
+int emu_cmask_words(const int32_t* ibuf, const double* dbuf) {
+  KernelTables kt;
+  if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return -1;
+  return kt.ib[KI_CMW];
+}
+
 int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, double* q, double* qd,
                 const double* u, int64_t u_stride, double* q_traj, double* qd_traj, double* var_out,
                 const int32_t* var_row, double* tac_out, const int32_t* tac_row, double* tape, int32_t* status,
@@ -58,7 +65,7 @@ int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double
   for (int env = 0; env < B; ++env)
     env_readout(tl, S, q + (long long)env * S.n, qd + (long long)env * S.n,
                 var_out ? var_out + (long long)env * 3 * S.nee : 0, tac_out ? tac_out + (long long)env * 3 * S.nmark : 0,
-                marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * 4 : 0, wb[0]);
+                marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * S.cmw : 0, wb[0]);
   return 0;
 }
 }

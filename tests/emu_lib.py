@@ -8,20 +8,31 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "emu.cpp")
-LIB = os.path.join(HERE, "emu", "libtsim_emu.so")
+LIB = os.path.join(HERE, "emu", "libtsim_emu_v%d.so")
 CORE = os.path.join(HERE, "..", "tactilesimulation_b200", "csrc")
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(variant=8):
+    """The harness compiled with the capacities of kernel variant 8 or 16 (csrc/kernel_layout.h)."""
+    if variant not in _libs:
+        path = LIB % variant
         deps = [SRC] + [os.path.join(CORE, f) for f in ("sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h")]
-        if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", "-o", LIB, SRC])
-        _lib = ctypes.CDLL(LIB)
-    return _lib
+        if not os.path.exists(path) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", f"-DTS_VARIANT={variant}", "-o", path, SRC])
+        _libs[variant] = ctypes.CDLL(path)
+    return _libs[variant]
+
+
+def lib_for(ibuf, dbuf):
+    """(library, contact bitmask words) of the smallest variant that accepts the scene."""
+    for variant in (8, 16):
+        l = lib(variant)
+        w = l.emu_cmask_words(_p(ibuf, ctypes.c_int32), _p(dbuf))
+        if w >= 0:
+            return l, w
+    raise RuntimeError("scene rejected by both kernel variants")
 
 
 def _p(a, t=ctypes.c_double):
@@ -44,12 +55,13 @@ def forward(ibuf, dbuf, q0, qd0, u, grad=False, var_row=None, tac_row=None, want
     vr, tr = _rows(var_row), _rows(tac_row)
     nv = T if vr is None else int(vr.max()) + 1
     nt = T if tr is None else int(tr.max()) + 1
+    l, cmw = lib_for(ibuf, dbuf)
     out = dict(q=np.zeros((T, B, n)), qd=np.zeros((T, B, n)), var=np.zeros((nv, B, 3 * nee)),
                tactile=np.zeros((nt, B, 3 * M)), status=np.zeros((T, B), dtype=np.int32),
                tape=np.zeros((T, B, 3, n, n)) if grad else None,
-               cmask=np.zeros((T, B, 4), dtype=np.uint32) if want_masks else None,
+               cmask=np.zeros((T, B, cmw), dtype=np.uint32) if want_masks else None,
                marker_body=np.zeros((nt, B, M), dtype=np.int32))
-    lib().emu_forward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(q), _p(qd), _p(u), ctypes.c_int64(B * nu),
+    l.emu_forward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(q), _p(qd), _p(u), ctypes.c_int64(B * nu),
                       _p(out["q"]), _p(out["qd"]), _p(out["var"]), _p(vr, ctypes.c_int32), _p(out["tactile"]),
                       _p(tr, ctypes.c_int32), _p(out["tape"]), _p(out["status"], ctypes.c_int32),
                       _p(out["cmask"], ctypes.c_uint32), _p(out["marker_body"], ctypes.c_int32))
@@ -71,7 +83,7 @@ def backward(ibuf, dbuf, fwd, u, df_dq=None, df_dvar=None, df_dtac=None, dq_row=
     df_du = np.zeros((T, B, nu))
     dq0 = np.zeros((B, n)) if want_q0 else None
     dqd0 = np.zeros((B, n)) if want_q0 else None
-    lib().emu_backward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(fwd["q"]), _p(fwd["qd"]), _p(u),
+    lib_for(ibuf, dbuf)[0].emu_backward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(fwd["q"]), _p(fwd["qd"]), _p(u),
                        ctypes.c_int64(B * nu), _p(fwd["tape"]), _p(cots[0]), _p(rows[0], ctypes.c_int32), _p(cots[1]),
                        _p(rows[1], ctypes.c_int32), _p(cots[2]), _p(rows[2], ctypes.c_int32), _p(carry), _p(df_du),
                        _p(dq0), _p(dqd0))

@@ -136,15 +136,86 @@ def stepsim_case(xml, nsteps, frame_skip, seed):
                 tactile=np.array(tac), df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac, df_du=df_du)
 
 
+def multi_case(xml, q0, u, seed):
+    """Scenes with several contact forces / sensors (DClaw): same content as episodic_case, with the contact
+    index sets as per-force lists padded into [T, forces, max points] and marker->body ids over all sensors."""
+    sim = redmax_py.Simulation(xml)
+    probe = redmax_probe.ProbeSimulation(xml)
+    sc = compile_scene(xml)
+    T = u.shape[0]
+    n, nv, nt = sim.ndof_r, sim.ndof_var, sim.ndof_tactile
+    for s in (sim, probe):
+        s.set_state_init(q0, np.zeros(n))
+        s.reset(True)
+    q, qd, var, tac, ground, gp, mb = [], [], [], [], [], [], []
+    for t in range(T):
+        for s in (sim, probe):
+            s.set_u(u[t])
+            s.forward(1)
+        assert np.array_equal(sim.get_q(), probe.get_q())
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        var.append(sim.get_variables().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+        cs = probe.contact_sets()
+        ground.append([list(x) for x in cs["ground"]])
+        gp.append([list(x) for x in cs["gp"]])
+        mb.append(np.concatenate([np.asarray(x, dtype=np.int32) for x in cs["marker_body"]]))
+    rng = np.random.default_rng(1000 + seed)
+    df_dq = rng.normal(size=(T, n))
+    df_dvar = rng.normal(size=(T, nv))
+    df_dtac = 1e-3 * rng.normal(size=(T, nt))
+    bi = sim.backward_info
+    bi.set_flags(True, True, False, True)
+    bi.df_dq, bi.df_dvar, bi.df_dtactile = df_dq.reshape(-1), df_dvar.reshape(-1), df_dtac.reshape(-1)
+    bi.df_dq0, bi.df_dqdot0, bi.df_du = np.zeros(n), np.zeros(n), np.zeros(sim.ndof_u * T)
+    sim.backward()
+    br = sim.backward_results
+
+    def pad3(lists, nforce, width):
+        out = -np.ones((T, max(nforce, 1), max(width, 1)), dtype=np.int32)
+        for t, per_force in enumerate(lists):
+            for f, ids in enumerate(per_force):
+                out[t, f, :len(ids)] = ids
+        return out
+
+    ib, db = sc.pack()
+    gw = max([len(sc.contact_points[g["body"]]) for g in sc.ground_contacts] + [0])
+    pw = max([len(sc.contact_points[f["body1"]]) for f in sc.gp_contacts] + [0])
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(n), u=u, q=np.array(q), qd=np.array(qd), var=np.array(var),
+                tactile=np.array(tac), ground_ids_f=pad3(ground, len(sc.ground_contacts), gw),
+                gp_ids_f=pad3(gp, len(sc.gp_contacts), pw), marker_body=np.array(mb, dtype=np.int32),
+                df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac, df_dq0=np.array(br.df_dq0),
+                df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, sim.ndof_u))
+
+
+def dclaw_case(T, seed):
+    """DClaw rotate-cap (R/envs/assets/dclaw_rotate/dclaw_torque_control.xml, BASELINE configs[3]): initial pose of
+    R/envs/dclaw_rotate_env.py:76-77, actions U(-1,1)^9 with the middle joints biased to close on the cap."""
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
+    q0 = np.zeros(10)
+    q0[[1, 4, 7]] = -0.5
+    q0[[2, 5, 8]] = 0.8
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1, 1, (T, 9))
+    u[:, 1::3] = 0.6 + 0.4 * u[:, 1::3]
+    return multi_case(xml, q0, u, seed)
+
+
 def main():
     x13 = os.path.join(ASSETS, "pusher.xml")
     x32 = os.path.join(ASSETS, "pusher_32x13.xml")
     cases = {
-        "pusher13x10_episodic_s0": episodic_case(x13, 60, 0),
-        "pusher13x10_episodic_s1": episodic_case(x13, 60, 1, push=False),
-        "pusher32x13_episodic_s0": episodic_case(x32, 30, 0),
-        "pusher13x10_stepsim_s0": stepsim_case(x13, 8, 5, 0),
+        "pusher13x10_episodic_s0": lambda: episodic_case(x13, 60, 0),
+        "pusher13x10_episodic_s1": lambda: episodic_case(x13, 60, 1, push=False),
+        "pusher32x13_episodic_s0": lambda: episodic_case(x32, 30, 0),
+        "pusher13x10_stepsim_s0": lambda: stepsim_case(x13, 8, 5, 0),
+        "dclaw_episodic_s0": lambda: dclaw_case(40, 0),
     }
+    only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
+    if only:
+        cases = {k: v for k, v in cases.items() if k in only}
+    cases = {k: v() for k, v in cases.items()}
     for name, c in cases.items():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **c)

@@ -94,3 +94,28 @@ def test_emulated_matches_oracle_on_fresh_seed():
     assert rel_err(bw["df_du"][:, 0], ref["df_du"]) <= 1e-6
     assert rel_err(bw["df_dq0"][0], ref["df_dq0"]) <= 1e-6
     assert rel_err(bw["df_dqdot0"][0], ref["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_dclaw_matches_reference():
+    """DClaw rotate-cap (BASELINE configs[3], the reference's own asset): 10 reduced dofs (16-dof kernel variant),
+    abstract bodies with sampled contact points, cylinder SDF (cap), three abstract 302-marker sensors."""
+    from tests.blob_scene import scene_from_blob
+    from tests.multi_force import expected_words
+    g = np.load(os.path.join(GOLDEN, "dclaw_episodic_s0.npz"))
+    sc = scene_from_blob(g["ibuf"], g["dbuf"])
+    T = g["u"].shape[0]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    assert float(np.abs(g["tactile"]).max()) > 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["var"][t, 0], g["var"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert np.array_equal(out["cmask"][t, 0].astype(np.uint64), expected_words(sc, g["ground_ids_f"][t], g["gp_ids_f"][t])), t
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], g["df_dq"][:, None, :],
+                          g["df_dvar"][:, None, :], g["df_dtactile"][:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
