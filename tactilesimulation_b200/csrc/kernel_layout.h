@@ -26,12 +26,14 @@
 #define KT_MAXB 24       // bodies
 #define KT_MAXU 16       // controls
 #define KT_MAXPW 5       // 32-bit words of an active-point bitmask: <= 160 sampled points per general body
+#define KT_CYLINDER 1    // cylinder SDF primitives (contact force, tactile candidates)
 #else
 #define KT_MAXJ 8        // moving joints
 #define KT_MAXN 8        // reduced dofs
 #define KT_MAXB 16       // bodies
 #define KT_MAXU 8        // controls
 #define KT_MAXPW 3       // <= 96 sampled points per general body
+#define KT_CYLINDER 0    // cuboid primitives only: the TactilePush hot path carries no cylinder code
 #endif
 #define KT_MAXCAND 4     // tactile candidate bodies per sensor
 

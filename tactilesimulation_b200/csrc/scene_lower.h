@@ -191,6 +191,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int shape2 = J[r[1] * TS_JI_STRIDE + 4];
     if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER)
       return "general-primitive contact: only cuboid and cylinder primitives are supported";
+    if (shape2 == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
     if (r[3] > 32 * KT_MAXPW) return "scene exceeds the compiled capacity (sampled points per general body)";
     int rec[KP_ISTRIDE] = {r[0], r[1], r[2], r[3], cmw, shape2};
     cmw += (r[3] + 31) / 32;
@@ -238,6 +239,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     for (int k = 0; k < r[3]; ++k) {
       const int sh = J[r[4 + k] * TS_JI_STRIDE + 4];
       if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER) return "tactile candidates must be cuboids or cylinders";
+      if (sh == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
     }
     oi.insert(oi.end(), r, r + KS_ISTRIDE);
     double d[KS_DSTRIDE] = {0};

@@ -687,7 +687,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
     const double* c = S.db + S.d_gp + fi * KP_DSTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
-    const bool cyl = r[5] == TS_SH_CYLINDER;
+    const bool cyl = KT_CYLINDER && r[5] == TS_SH_CYLINDER;
     const int j1 = S.ib[S.o_body + b1 * KB_ISTRIDE], j2 = S.ib[S.o_body + b2 * KB_ISTRIDE];
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
@@ -1317,7 +1317,7 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
   F.near[0] = true;
   for (int c = 0; c < nc; ++c) {
     const int b2 = sr[4 + c];
-    const bool cyl = S.ib[S.o_body + b2 * KB_ISTRIDE + 1] == TS_SH_CYLINDER;
+    const bool cyl = KT_CYLINDER && S.ib[S.o_body + b2 * KB_ISTRIDE + 1] == TS_SH_CYLINDER;
     body_frame_v(S, W, b2, F.R[1 + c], F.p[1 + c], F.ph[1 + c]);
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
@@ -1352,7 +1352,7 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
     if (!F.near[1 + c]) continue;
     const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
     double xw[3], y[3], x[3];
-    if (S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CYLINDER) {
+    if (KT_CYLINDER && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CYLINDER) {
       mv3(R1, xi1, xw);
       for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
       if (!cylinder_inside_world(F.R[1 + c], F.p[1 + c], xw, hs)) continue;
@@ -1373,7 +1373,7 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
   if (H.cand < 0) return;
   const double* hs = S.db + S.d_body + sr[4 + H.cand] * KB_DSTRIDE + KB_HALF;
   const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
-  if (H.cyl) {
+  if (KT_CYLINDER && H.cyl) {
     H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1]);
     H.d = H.rad - hs[0];
     H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = 0.0;
@@ -1524,7 +1524,7 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, int si, const do
       cross3(e, tbar, t3);
       double w2bar[3], v2bar[3], xbar[3];
       for (int i = 0; i < 3; ++i) w2bar[i] = H.d * t3[i];
-      if (H.cyl) {
+      if (KT_CYLINDER && H.cyl) {
         // the normal e = x_r / |x_r| moves with the point: Fb = -s e - ..., ddot = e.u, tb = u - e (e.u) + d (w2 x e)
         double ebar[3], tw[3];
         const double eu = dot3(e, H.u);
@@ -1743,7 +1743,7 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
       double xw[3], y[3], x[3];
       mv3(R1, xi, xw);
       bool in;
-      if (r[5] == TS_SH_CYLINDER) {
+      if (KT_CYLINDER && r[5] == TS_SH_CYLINDER) {
         for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
         in = cylinder_inside_world(R2, p2, xw, hs);
       } else {

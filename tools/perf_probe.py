@@ -16,6 +16,11 @@ def inputs(g, B, T, dev, seed=0):
     rng = np.random.default_rng(seed)
     n, nu = len(g["q0"]), g["u"].shape[1]
     q0 = np.tile(g["q0"], (B, 1))
+    if n == 10:      # DClaw rotate-cap (BASELINE configs[3]): U(-1,1)^9 with the middle joints closing on the cap
+        u = rng.uniform(-1, 1, (T, B, nu))
+        u[:, :, 1::3] = 0.6 + 0.4 * u[:, :, 1::3]
+        q0[:, :9] += rng.uniform(-0.05, 0.05, (B, 9))
+        return (torch.tensor(q0, device=dev), torch.zeros((B, n), dtype=torch.float64, device=dev), torch.tensor(u, device=dev))
     q0[:, 1] = -0.001
     q0[:, 4] = rng.uniform(-0.02, 0.02, B)
     u = np.zeros((T, B, nu))
@@ -45,6 +50,8 @@ def main():
         ib = g["ibuf"].copy()
         if a.no_gp:
             ib[8] = 0
+        if int(ib[3]) > 8 and lanes < 16:
+            continue
         sim = BatchedSim((ib, g["dbuf"]), "cuda:0", lanes=lanes)
         dev = sim.device
         q0, qd0, u = inputs(g, a.B, a.T, dev)
