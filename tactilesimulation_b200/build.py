@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtactilesim_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 VARIANTS = (8, 16)
-DEPS = ["kernels.cu", "cabi.cpp", "sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h",
+DEPS = ["kernels.cu", "kernels_v8.cu", "kernels_v16.cu", "cabi.cpp", "sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h",
         os.path.join("..", "..", "include", "tactilesim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -33,10 +33,10 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     for v in VARIANTS:
         o = os.path.join(OBJ, f"kernels_v{v}.o")
         objs.append(o)
-        jobs.append(subprocess.Popen([nvcc] + flags + [f"-DTS_VARIANT={v}", "-c", "kernels.cu", "-o", o], cwd=CSRC))
+        jobs.append(subprocess.Popen([nvcc] + flags + ["-c", f"kernels_v{v}.cu", "-o", o], cwd=CSRC))
     o = os.path.join(OBJ, "cabi.o")
     objs.append(o)
-    jobs.append(subprocess.Popen([nvcc] + flags + ["-c", "cabi.cpp", "-o", o], cwd=CSRC))
+    jobs.append(subprocess.Popen([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-c", "cabi.cpp", "-o", o], cwd=CSRC))
     rcs = [j.wait() for j in jobs]
     if any(rcs):
         raise RuntimeError(f"nvcc failed (exit codes {rcs})")

@@ -5,8 +5,12 @@ import collections, csv, os, re, subprocess, sys, tempfile
 csvp, so, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.split("\n")
+sass = []          # the library holds one cubin per kernel variant: keep the one that has the kernel
+for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):
+    txt = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
+    if any(l.startswith(".text.") and pat in l for l in txt.split("\n")):
+        sass = txt.split("\n")
+        break
 
 def func_ranges(path):
     out, cur = [], None

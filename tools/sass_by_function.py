@@ -4,8 +4,12 @@ import re, subprocess, sys, os, tempfile, collections
 so, pat = sys.argv[1], sys.argv[2]
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.split("\n")
+sass = []          # the library holds one cubin per kernel variant: keep the one that has the kernel
+for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):
+    txt = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
+    if any(l.startswith(".text.") and pat in l for l in txt.split("\n")):
+        sass = txt.split("\n")
+        break
 # function line ranges from the sources
 def func_ranges(path):
     out = []
