@@ -39,7 +39,7 @@ typedef struct tsim_scene tsim_scene;
 
 /* indices into the array filled by tsim_scene_sizes */
 enum { TSIM_NJ = 0, TSIM_NDOF_R, TSIM_NDOF_M, TSIM_NDOF_U, TSIM_NDOF_VAR, TSIM_NDOF_TACTILE, TSIM_N_MARKERS,
-       TSIM_TAPE_DOUBLES /* per env-step: 3*ndof_r^2 */,
+       TSIM_TAPE_DOUBLES /* per env-step: 3*ndof_r^2 + ndof_u */,
        TSIM_CMASK_WORDS /* 32-bit words of the active contact-point bitmask per env-step */, TSIM_N_SIZES };
 
 const char* tsim_last_error(void);
@@ -65,11 +65,12 @@ int tsim_scene_set_option(tsim_scene* scene, int key, int value);
  *   var_out      [rows,B,nvar]   end-effector variables of step t at row var_row[t] (NULL map: row t;
  *                                row < 0: skipped), or NULL
  *   tac_out      [rows,B,ntac]   tactile field (marker-major: shear.axis0, shear.axis1, normal)
- *   tape         [T,B,3,n,n]  adjoint tape (H = dg/dq1, G0 = dg/dq0, G1 = dg/dqdot0), or NULL = no-grad mode
+ *   tape         [T,B,W]      adjoint tape, W = sizes[TSIM_TAPE_DOUBLES] = 3 n^2 + nu per env-step: H = dg/dq1,
+ *                             G0 = dg/dq0, G1 = dg/dqdot0 (n x n, row-major) and d f_r/d u per control; NULL = no-grad mode
  *   status       [T,B] or NULL
  *   contact_masks [T,B,W] or NULL: active contact-point bitmasks, W = sizes[TSIM_CMASK_WORDS] words per
- *                                env-step, force by force in scene order: one word per ground contact, then
- *                                ceil(points/32) words per general-primitive contact (TactilePush: W = 4,
+ *                                env-step, force by force in scene order: ground contacts first, then the
+ *                                general-primitive contacts, ceil(points/32) words each (TactilePush: W = 4,
  *                                word 0 ground-box, words 1-3 pad-box); bit k = sampled point k is active
  *   marker_body  [rows,B,M] or NULL: contacted body id per marker (-1 none), rows as tac_out */
 int tsim_forward(const tsim_scene* scene, int32_t B, int32_t T, double* q, double* qd, const double* u,

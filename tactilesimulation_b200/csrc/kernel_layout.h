@@ -27,6 +27,7 @@
 #define KT_MAXU 16       // controls
 #define KT_MAXPW 5       // 32-bit words of an active-point bitmask: <= 160 sampled points per general body
 #define KT_CYLINDER 1    // cylinder SDF primitives (contact force, tactile candidates)
+#define KT_MAXCAND 8     // tactile candidate bodies per sensor
 #else
 #define KT_MAXJ 8        // moving joints
 #define KT_MAXN 8        // reduced dofs
@@ -34,8 +35,8 @@
 #define KT_MAXU 8        // controls
 #define KT_MAXPW 3       // <= 96 sampled points per general body
 #define KT_CYLINDER 0    // cuboid primitives only: the TactilePush hot path carries no cylinder code
-#endif
 #define KT_MAXCAND 4     // tactile candidate bodies per sensor
+#endif
 
 enum {
   KI_NMJ = 0, KI_N, KI_NU, KI_NEE, KI_NMARK, KI_NGROUND, KI_NGP, KI_NACT, KI_NSENS, KI_MAX_ITER, KI_MAX_LS,
@@ -90,9 +91,9 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 // markers: KM_STRIDE doubles each {position(3) axis0(3) axis1(3) normal(3)} in the pad body frame; they stay in
 // global memory (read once per marker and readout), everything before them is staged in shared memory
 #define KM_STRIDE 12
-// sensor: int {body, marker_off, marker_cnt, ncand, cand[4]};
+// sensor: int {body, marker_off, marker_cnt, ncand, cand[KT_MAXCAND]};
 // dbl {kn kt mu damping axis0 axis1 normal r_markers | bounding box of the markers in the pad frame: lo(3) hi(3)}
-#define KS_ISTRIDE 8
+#define KS_ISTRIDE (4 + KT_MAXCAND)
 #define KS_DSTRIDE 24
 #define KS_RMARK 13
 #define KS_BBOX 14

@@ -303,7 +303,7 @@ const char* tsim_last_error(void) { return g_err.c_str(); }
 int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, int64_t n_dbl, int device,
                       tsim_scene** out) {
   if (!ibuf || !dbuf || !out) return fail("tsim_scene_create: null argument");
-  if (n_int < TS_I_HEADER || ibuf[TS_I_MAGIC] != TS_MAGIC || ibuf[TS_I_VERSION] != TS_VERSION)
+  if (n_int < TS_I_HEADER || ibuf[TS_I_MAGIC] != TS_MAGIC || ibuf[TS_I_VERSION] < TS_VERSION_MIN || ibuf[TS_I_VERSION] > TS_VERSION)
     return fail("tsim_scene_create: not a scene blob of this version");
   // lower the portable scene description to the kernel tables (fixed joints folded, culling radii, ...)
   KernelTables kt;
@@ -330,7 +330,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->sizes[TSIM_NDOF_VAR] = 3 * ibuf[TS_I_NEE];
   s->sizes[TSIM_NDOF_TACTILE] = 3 * ibuf[TS_I_NMARKERS];
   s->sizes[TSIM_N_MARKERS] = ibuf[TS_I_NMARKERS];
-  s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n;
+  s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n + ibuf[TS_I_NDOF_U];
   s->sizes[TSIM_CMASK_WORDS] = kt.ib[KI_CMW];
   *out = s;
   return 0;

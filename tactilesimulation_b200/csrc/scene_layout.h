@@ -5,7 +5,8 @@
 #pragma once
 
 #define TS_MAGIC 0x54533230  // "TS20"
-#define TS_VERSION 3
+#define TS_VERSION 4         // 3: sensor records carry up to 4 candidate bodies; 4: up to 8 (both are accepted)
+#define TS_VERSION_MIN 3
 
 // ---- joint types / shapes / actuator modes (scene.py uses the same values)
 #define TS_JT_FIXED 0
@@ -13,6 +14,7 @@
 #define TS_JT_PRISMATIC 2
 #define TS_JT_PLANAR 3
 #define TS_JT_TRANSLATIONAL 4
+#define TS_JT_FREE3D_EULER 5    // q = (p, r): translation + XYZ Euler angles (DH/Joint/JointFree3DEuler.cpp)
 #define TS_SH_NONE 0
 #define TS_SH_CUBOID 1
 #define TS_SH_CYLINDER 2
@@ -43,7 +45,8 @@ enum {
 #define TS_PI_STRIDE 4      // body1, body2, point_off, point_cnt
 #define TS_AI_STRIDE 4      // joint, mode, uoff, ndof
 #define TS_EI_STRIDE 2      // joint, unused
-#define TS_SI_STRIDE 8      // body, marker_off, marker_cnt, ncand, cand[4]
+#define TS_SI_STRIDE_V3 8   // body, marker_off, marker_cnt, ncand, cand[4]
+#define TS_SI_STRIDE 12     // body, marker_off, marker_cnt, ncand, cand[8]
 
 // double header: h, g(3), tol, ground normal(3), ground origin(3)
 enum { TS_D_H = 0, TS_D_GRAV = 1, TS_D_TOL = 4, TS_D_GN = 5, TS_D_GX = 8, TS_D_HEADER = 16 };

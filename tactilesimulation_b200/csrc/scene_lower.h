@@ -45,8 +45,9 @@ inline double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v
 // Returns "" on success, otherwise an error message.
 inline std::string lower_scene(const int* ib, long long ni, const double* db, long long nd, KernelTables& out) {
   using namespace tsim_lower;
-  if (ni < TS_I_HEADER || ib[TS_I_MAGIC] != TS_MAGIC || ib[TS_I_VERSION] != TS_VERSION)
+  if (ni < TS_I_HEADER || ib[TS_I_MAGIC] != TS_MAGIC || ib[TS_I_VERSION] < TS_VERSION_MIN || ib[TS_I_VERSION] > TS_VERSION)
     return "not a scene blob of this version";
+  const int si_stride = ib[TS_I_VERSION] >= 4 ? TS_SI_STRIDE : TS_SI_STRIDE_V3;
   const int nj = ib[TS_I_NJ], n = ib[TS_I_NDOF_R], nu = ib[TS_I_NDOF_U], nee = ib[TS_I_NEE], nmark = ib[TS_I_NMARKERS];
   const int nground = ib[TS_I_NGROUND], ngp = ib[TS_I_NGP], nact = ib[TS_I_NACT], nsens = ib[TS_I_NSENSORS];
   const int npoints = ib[TS_I_NPOINTS];
@@ -177,9 +178,8 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int g = 0; g < nground; ++g) {
     const int* r = ib + ib[TS_I_OFF_GROUND] + g * TS_GI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GROUND] + g * TS_CD_STRIDE;
-    if (r[2] > 32) return "more than 32 ground contact points per body are not supported";
     int rec[KG_ISTRIDE] = {r[0], r[1], r[2], cmw};
-    cmw += 1;
+    cmw += (r[2] + 31) / 32;
     oi.insert(oi.end(), rec, rec + KG_ISTRIDE);
     od.insert(od.end(), c, c + KG_DSTRIDE);
   }
@@ -212,7 +212,6 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int a = 0; a < nact; ++a) {
     const int* r = ib + ib[TS_I_OFF_ACT] + a * TS_AI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_ACT] + a * TS_AD_STRIDE;
-    if (r[1] != TS_ACT_FORCE) return "position-controlled motors are not supported yet";
     if (midx[r[0]] < 0) return "actuator on a fixed joint";
     int rec[KA_ISTRIDE] = {midx[r[0]], r[1], r[2], r[3]};
     oi.insert(oi.end(), rec, rec + KA_ISTRIDE);
@@ -233,15 +232,17 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   // ---- sensors
   oi[KI_O_SENSOR] = (int)oi.size(); oi[KI_D_SENSOR] = (int)od.size();
   for (int s = 0; s < nsens; ++s) {
-    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * TS_SI_STRIDE;
+    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * si_stride;
     const double* c = db + ib[TS_I_DOFF_SENSOR] + s * TS_SD_STRIDE;
-    if (r[3] > KT_MAXCAND) return "too many tactile candidate bodies";
+    if (r[3] > KT_MAXCAND) return "scene exceeds the compiled capacity (tactile candidate bodies)";
     for (int k = 0; k < r[3]; ++k) {
       const int sh = J[r[4 + k] * TS_JI_STRIDE + 4];
       if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER) return "tactile candidates must be cuboids or cylinders";
       if (sh == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
     }
-    oi.insert(oi.end(), r, r + KS_ISTRIDE);
+    int rec[KS_ISTRIDE] = {r[0], r[1], r[2], r[3]};
+    for (int k = 0; k < r[3]; ++k) rec[4 + k] = r[4 + k];
+    oi.insert(oi.end(), rec, rec + KS_ISTRIDE);
     double d[KS_DSTRIDE] = {0};
     for (int i = 0; i < 13; ++i) d[i] = c[i];
     for (int i = 0; i < 3; ++i) { d[KS_BBOX + i] = 1e300; d[KS_BBOX + 3 + i] = -1e300; }
@@ -260,7 +261,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   // markers last (the kernels stage everything before them in shared memory): position + per-marker axes
   oi[KI_D_MARKERS] = (int)od.size();
   for (int s = 0; s < nsens; ++s) {
-    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * TS_SI_STRIDE;
+    const int* r = ib + ib[TS_I_OFF_SENSOR] + s * si_stride;
     const double* c = db + ib[TS_I_DOFF_SENSOR] + s * TS_SD_STRIDE;
     for (int k = r[1]; k < r[1] + r[2]; ++k) {
       od.insert(od.end(), MK + 3 * k, MK + 3 * k + 3);

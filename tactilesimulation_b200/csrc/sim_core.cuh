@@ -68,6 +68,7 @@ struct SceneView {
   const double* db;
   const double* mk;      // marker table (KM_STRIDE doubles per marker): global memory on the GPU
   int cmw;               // words of the contact bitmask output per env-step
+  int ntape;             // doubles of the adjoint tape per env-step: H, G0, G1 (n x n each) + d f_r / d u per control
   int nj, n, nu, nee, nmark, nground, ngp, nact, nsens, max_iter, max_ls, nbody;
   int o_joint, o_body, o_ground, o_gp, o_act, o_ee, o_sensor;
   int d_joint, d_body, d_ground, d_gp, d_act, d_ee, d_sensor, d_points, d_markers;
@@ -81,6 +82,7 @@ HDN inline void scene_view_init(SceneView& S, const int* ib, const double* db) {
   S.nact = ib[KI_NACT]; S.nsens = ib[KI_NSENS]; S.nbody = ib[KI_NBODY];
   S.max_iter = ib[KI_MAX_ITER]; S.max_ls = ib[KI_MAX_LS];
   S.cmw = ib[KI_CMW];
+  S.ntape = 3 * S.n * S.n + S.nu;
   S.mk = db + ib[KI_D_MARKERS];
   S.o_joint = ib[KI_O_JOINT]; S.o_body = ib[KI_O_BODY]; S.o_ground = ib[KI_O_GROUND]; S.o_gp = ib[KI_O_GP];
   S.o_act = ib[KI_O_ACT]; S.o_ee = ib[KI_O_EE]; S.o_sensor = ib[KI_O_SENSOR];
@@ -176,18 +178,24 @@ struct TileState {
 // inputs (q, qd, dl) of one evaluation: plain arrays ...
 template <class T> struct ArrIn {
   const T *q_, *qd_, *dl_;
+  const double *q0_, *qd0_;                 // state at the start of the step (position-controlled motors)
   HD T q(int i) const { return q_[i]; }
   HD T qd(int i) const { return qd_[i]; }
   HD T dl(int i) const { return dl_[i]; }
+  HD T q0(int i) const { return T(q0_[i]); }
+  HD T qd0(int i) const { return T(qd0_[i]); }
 };
 // ... or Dual numbers whose values live in the tile state and whose tangent is a unit seed on dof k
 struct SeedIn {
   const double *xq, *xv, *xl;
+  const double *q0v, *qd0v;                 // state at the start of the step (position-controlled motors)
   int k;
-  double tq, tv, tl;
+  double tq, tv, tl, tq0, tqd0;
   HD Dual q(int i) const { return mkdual(xq[i], i == k ? tq : 0.0); }
   HD Dual qd(int i) const { return mkdual(xv[i], i == k ? tv : 0.0); }
   HD Dual dl(int i) const { return mkdual(xl[i], i == k ? tl : 0.0); }
+  HD Dual q0(int i) const { return mkdual(q0v[i], i == k ? tq0 : 0.0); }
+  HD Dual qd0(int i) const { return mkdual(qd0v[i], i == k ? tqd0 : 0.0); }
 };
 
 template <class T> struct WorkRec {          // the joint records alone (value-only line-search trials)
@@ -280,6 +288,67 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
       for (int i = 0; i < 3; ++i) {
         sq[i] = w[i] * in.qd(qo); sq[3 + i] = m[i] * in.qd(qo);
         if (dyn) { sl[i] = w[i] * in.dl(qo); sl[3 + i] = m[i] * in.dl(qo); }
+      }
+    } else if (jt == TS_JT_FREE3D_EULER) {
+      // q = (p, r): Q = [R(r) p; 0 1], R = Rx(r1) Ry(r2) Rz(r3)   (DH/Joint/JointFree3DEuler.cpp:14-104,
+      // JointSphericalEuler.cpp:15-60).  In the pre-motion frame a the child moves with the twist
+      // xi = (G rdot, pdot + p x G rdot) about a's origin, G = [e_x, Rx e_y, Rx Ry e_z]; the rotation axes move
+      // with r, which adds xi_dot = (Gdot rdot, pdot x G rdot + p x Gdot rdot) to the velocity-product term.
+      T s1, c1, s2, c2, s3, c3;
+      dsincos(in.q(qo + 3), s1, c1);
+      dsincos(in.q(qo + 4), s2, c2);
+      dsincos(in.q(qo + 5), s3, c3);
+      T Rq[9];
+      Rq[0] = c2 * c3; Rq[1] = -(c2 * s3); Rq[2] = s2;
+      Rq[3] = c1 * s3 + c3 * (s1 * s2); Rq[4] = c1 * c3 - (s1 * s2) * s3; Rq[5] = -(c2 * s1);
+      Rq[6] = s1 * s3 - (c1 * c3) * s2; Rq[7] = c3 * s1 + (c1 * s2) * s3; Rq[8] = c1 * c2;
+      mm3(Ra, Rq, R0);
+      T pq[3], t[3];
+      for (int i = 0; i < 3; ++i) pq[i] = in.q(qo + i);
+      mv3(Ra, pq, t);
+      for (int i = 0; i < 3; ++i) p0[i] = pa[i] + t[i];
+      T g2[3], g3[3];
+      g2[0] = 0.0; g2[1] = c1; g2[2] = s1;
+      g3[0] = s2; g3[1] = -(s1 * c2); g3[2] = c1 * c2;
+      for (int pass = 0; pass < (dyn ? 2 : 1); ++pass) {
+        T rd[3], pd[3];
+        for (int i = 0; i < 3; ++i) {
+          pd[i] = pass ? in.dl(qo + i) : in.qd(qo + i);
+          rd[i] = pass ? in.dl(qo + 3 + i) : in.qd(qo + 3 + i);
+        }
+        T wa[3], va[3], c[3];
+        wa[0] = rd[0] + g3[0] * rd[2];
+        wa[1] = g2[1] * rd[1] + g3[1] * rd[2];
+        wa[2] = g2[2] * rd[1] + g3[2] * rd[2];
+        cross3(pq, wa, c);
+        for (int i = 0; i < 3; ++i) va[i] = pd[i] + c[i];
+        T* so = pass ? sl : sq;
+        T w[3], v[3], pw[3];
+        mv3(Ra, wa, w);
+        mv3(Ra, va, v);
+        cross3(pa, w, pw);
+        for (int i = 0; i < 3; ++i) { so[i] = w[i]; so[3 + i] = v[i] + pw[i]; }
+      }
+      if (dyn) {
+        // h^2 Ad(E_0a) xi_dot, folded into sl (X_j = X_p + sl + h^2 ad(V_p) sq)
+        T r1 = in.qd(qo + 3), r2 = in.qd(qo + 4), r3 = in.qd(qo + 5);
+        T wd[3], wa[3], vd[3], c0[3], c1v[3], pd[3];
+        // Gdot rdot = r2 * d(g2)/dt + r3 * d(g3)/dt,  d(g2)/dt = r1 (0,-s1,c1),  d(g3)/dt = r1 (0,-c1 c2,-s1 c2) + r2 (c2, s1 s2, -c1 s2)
+        wd[0] = r3 * (r2 * c2);
+        wd[1] = r2 * (r1 * (-s1)) + r3 * (r1 * (-(c1 * c2)) + r2 * (s1 * s2));
+        wd[2] = r2 * (r1 * c1) + r3 * (r1 * (-(s1 * c2)) + r2 * (-(c1 * s2)));
+        wa[0] = r1 + g3[0] * r3;
+        wa[1] = g2[1] * r2 + g3[1] * r3;
+        wa[2] = g2[2] * r2 + g3[2] * r3;
+        for (int i = 0; i < 3; ++i) pd[i] = in.qd(qo + i);
+        cross3(pd, wa, c0);
+        cross3(pq, wd, c1v);
+        for (int i = 0; i < 3; ++i) vd[i] = c0[i] + c1v[i];
+        T w[3], v[3], pw[3];
+        mv3(Ra, wd, w);
+        mv3(Ra, vd, v);
+        cross3(pa, w, pw);
+        for (int i = 0; i < 3; ++i) { sl[i] = sl[i] + h2 * w[i]; sl[3 + i] = sl[3 + i] + h2 * (v[i] + pw[i]); }
       }
     } else {
       for (int i = 0; i < 9; ++i) R0[i] = Ra[i];
@@ -770,6 +839,35 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
   }
 }
 
+// World axes of the six coordinates of a free3d-euler joint whose frame is (R0, .): translations along
+// Ra e_i = R0 (row i of R(r)), rotations about R0 T_i with T = R^T G = [[c2c3, s3, 0], [-c2s3, c3, 0], [s2, 0, 1]]
+// (the S_j of DH/Joint/JointSphericalEuler.cpp:62-66).
+template <class T>
+HD void euler_world_axes(const T* R0, T r1, T r2, T r3, T (*tax)[3], T (*rax)[3]) {
+  T s1, c1, s2, c2, s3, c3;
+  dsincos(r1, s1, c1);
+  dsincos(r2, s2, c2);
+  dsincos(r3, s3, c3);
+  T rows[3][3], tc[3][3];
+  rows[0][0] = c2 * c3; rows[0][1] = -(c2 * s3); rows[0][2] = s2;
+  rows[1][0] = c1 * s3 + c3 * (s1 * s2); rows[1][1] = c1 * c3 - (s1 * s2) * s3; rows[1][2] = -(c2 * s1);
+  rows[2][0] = s1 * s3 - (c1 * c3) * s2; rows[2][1] = c3 * s1 + (c1 * s2) * s3; rows[2][2] = c1 * c2;
+  tc[0][0] = c2 * c3; tc[0][1] = -(c2 * s3); tc[0][2] = s2;
+  tc[1][0] = s3; tc[1][1] = c3; tc[1][2] = 0.0;
+  tc[2][0] = 0.0; tc[2][1] = 0.0; tc[2][2] = 1.0;
+  for (int i = 0; i < 3; ++i) { mv3(R0, rows[i], tax[i]); mv3(R0, tc[i], rax[i]); }
+}
+
+// position-controlled motor on one coordinate: PD on the state at the START of the step, clamped
+// (DH/Actuator/ActuatorMotor.cpp:37-41); dfdu / dfdq0 / dfdqd0 are P / -P / -D while unclamped (:56-73)
+template <class T>
+HD T pos_motor_force(double u, T q0, T qd0, double P, double D, double cmin, double cmax) {
+  T f = P * (u - q0) + D * (-qd0);
+  if (val(f) > cmax) return T(cmax);
+  if (val(f) < cmin) return T(cmin);
+  return f;
+}
+
 // FORCE motor: clamp, affine map to ctrl_range, clamp  (DH/Actuator/ActuatorMotor.cpp:31-36, Utils.h:384-386)
 HD double motor_force(double u, double cmin, double cmax) {
   double uc = fmax(fmin(u, 1.0), -1.0);
@@ -803,6 +901,13 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     } else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, fj);
     else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, fj); g[qo + 1] = dot3(a1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = fj[0]; g[qo + 1] = fj[1]; g[qo + 2] = fj[2]; }
+    else if (jt == TS_JT_FREE3D_EULER) {
+      T tax[3][3], rax[3][3], pf[3], t[3];
+      euler_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
+      cross3(p0, A + 3, pf);             // moment about the joint origin
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      for (int i = 0; i < 3; ++i) { g[qo + i] = dot3(tax[i], A + 3); g[qo + 3 + i] = dot3(rax[i], t); }
+    }
     // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
     const double damp = jd[KJ_DAMP], lo = jd[KJ_LIMLO], hi = jd[KJ_LIMHI], lk = jd[KJ_LIMK];
     for (int i = 0; i < nd; ++i) {
@@ -818,7 +923,12 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
     const double* c = S.db + S.d_act + ai * KA_DSTRIDE;
     const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
-    for (int i = 0; i < r[3]; ++i) g[qo + i] = g[qo + i] - h2 * motor_force(u[r[2] + i], c[i], c[3 + i]);
+    if (r[1] == TS_ACT_POS) {
+      for (int i = 0; i < r[3]; ++i)
+        g[qo + i] = g[qo + i] - h2 * pos_motor_force(u[r[2] + i], in.q0(qo + i), in.qd0(qo + i), c[6 + i], c[9 + i], c[i], c[3 + i]);
+    } else {
+      for (int i = 0; i < r[3]; ++i) g[qo + i] = g[qo + i] - h2 * motor_force(u[r[2] + i], c[i], c[3 + i]);
+    }
   }
 }
 
@@ -1033,6 +1143,9 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
   in.tq = (seed == 0) ? 1.0 : 0.0;
   in.tv = (seed == 0) ? (1.0 - 0.0) / S.h : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
   in.tl = (seed == 0) ? 1.0 : ((seed == 1) ? -1.0 : -S.h);
+  in.q0v = ts.q; in.qd0v = ts.qd;
+  in.tq0 = (seed == 1) ? 1.0 : 0.0;
+  in.tqd0 = (seed == 2) ? 1.0 : 0.0;
   tl.tile_sync();          // every lane of the tile is done with the previous evaluation and its bookkeeping
 #pragma unroll
   for (int i = 0; i < TS_MAXN; ++i) {
@@ -1056,7 +1169,7 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
 // Column k of the mass matrix M = J^T Mm J at the poses held in W (values), value arithmetic only:
 // psi = S_k on every joint of the subtree of dof k's joint, a_i = I psi_i, projected inward.
 template <class WK>
-HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
+HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, double* Mcol) {
   for (int i = 0; i < TS_MAXN; ++i) Mcol[i] = 0.0;
   if (k >= S.n) return;
   // joint and world screw of dof k
@@ -1076,7 +1189,15 @@ HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
       cross3(p0, Sk, Sk + 3);
     } else if (jt == TS_JT_PRISMATIC) mv3(R0, jd + KJ_AX0, Sk + 3);
     else if (jt == TS_JT_PLANAR) mv3(R0, loc == 0 ? jd + KJ_AX0 : jd + KJ_AX1, Sk + 3);
-    else { for (int i = 0; i < 3; ++i) Sk[3 + i] = R0[3 * i + loc]; }
+    else if (jt == TS_JT_FREE3D_EULER) {
+      double tax[3][3], rax[3][3];
+      euler_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
+      if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
+      else {
+        for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - 3][i];
+        cross3(p0, Sk, Sk + 3);
+      }
+    } else { for (int i = 0; i < 3; ++i) Sk[3 + i] = R0[3 * i + loc]; }
   }
   if (jk < 0) return;
   double Wm[TS_MAXJ][6];
@@ -1114,6 +1235,13 @@ HDN void mass_column(const SceneView& S, const WK& W, int k, double* Mcol) {
     } else if (jt == TS_JT_PRISMATIC) Mcol[qo] = dot3(jd + KJ_AX0, fj);
     else if (jt == TS_JT_PLANAR) { Mcol[qo] = dot3(jd + KJ_AX0, fj); Mcol[qo + 1] = dot3(jd + KJ_AX1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { Mcol[qo] = fj[0]; Mcol[qo + 1] = fj[1]; Mcol[qo + 2] = fj[2]; }
+    else if (jt == TS_JT_FREE3D_EULER) {
+      double tax[3][3], rax[3][3], pf[3], t[3];
+      euler_world_axes(R0, qv[qo + 3], qv[qo + 4], qv[qo + 5], tax, rax);
+      cross3(p0, A + 3, pf);
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      for (int i = 0; i < 3; ++i) { Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[qo + 3 + i] = dot3(rax[i], t); }
+    }
     if (par >= 0) for (int i = 0; i < 6; ++i) Wm[par][i] += A[i];
   }
 }
@@ -1132,7 +1260,7 @@ HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha) {
     g[i] = 0.0;
   }
   ArrIn<double> in;
-  in.q_ = xq; in.qd_ = xv; in.dl_ = xl;
+  in.q_ = xq; in.qd_ = xv; in.dl_ = xl; in.q0_ = ts.q; in.qd0_ = ts.qd;
   WorkRec<double> Wv;
   HostTile solo;
   eval_g(solo, S, in, ts.u, Wv, g);
@@ -1184,10 +1312,33 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
       const int k = tl.lane + c * L;
       if (k < n) {
         double Mc[TS_MAXN];
-        mass_column(S, WD, k, Mc);
+        mass_column(S, WD, ts.xq, k, Mc);
         for (int i = 0; i < n; ++i) {
           tape[n * n + i * n + k] = cole[c][i];
           tape[2 * n * n + i * n + k] = -S.h * Mc[i];
+        }
+      }
+    }
+    // d f_r / d u per control (the gain the reverse sweep needs: DH/Actuator/ActuatorMotor.cpp:48-62), and the
+    // velocity feedback of position-controlled motors, which enters G1 = dg/dqdot0 = -h M + h^2 diag(D)
+    tl.tile_sync();
+    if (tl.lane == 0) {
+      for (int ai = 0; ai < S.nact; ++ai) {
+        const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
+        const double* cdat = S.db + S.d_act + ai * KA_DSTRIDE;
+        const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
+        for (int i = 0; i < r[3]; ++i) {
+          const double uu = ts.u[r[2] + i];
+          double gain;
+          if (r[1] == TS_ACT_POS) {
+            const double f = cdat[6 + i] * (uu - ts.q[qo + i]) + cdat[9 + i] * (-ts.qd[qo + i]);
+            const bool open = f >= cdat[i] && f <= cdat[3 + i];
+            gain = open ? cdat[6 + i] : 0.0;
+            if (open) tape[2 * n * n + (qo + i) * n + (qo + i)] += S.h * S.h * cdat[9 + i];
+          } else {
+            gain = (uu >= -1.0 && uu <= 1.0) ? (cdat[3 + i] - cdat[i]) / 2.0 : 0.0;
+          }
+          tape[3 * n * n + r[2] + i] = gain;
         }
       }
     }
@@ -1601,6 +1752,7 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
     SeedIn in;
     in.xq = ts.q; in.xv = ts.qd; in.xl = ts.qd;      // dl is not read by the kinematics-only pass
     in.tq = 1.0; in.tv = 0.0; in.tl = 0.0;
+    in.q0v = ts.q; in.qd0v = ts.qd; in.tq0 = 0.0; in.tqd0 = 0.0;
     for (int c = 0; c < TS_NC(L); ++c) {
       const int k = tl.lane + c * L;
       in.k = k;
@@ -1680,15 +1832,13 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
     }
     lu_solve(tl, col, z, n);
   }
-  // controls: dg/du = -h^2 dfr/du, FORCE motors (DH/Actuator/ActuatorMotor.cpp:48-55)
+  // controls: dg/du = -h^2 dfr/du; dfr/du was taped by the forward pass (DH/Actuator/ActuatorMotor.cpp:48-62)
   if (du_out && tl.lane == 0) {
     for (int ai = 0; ai < S.nact; ++ai) {
       const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
-      const double* cdat = S.db + S.d_act + ai * KA_DSTRIDE;
       const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
       for (int i = 0; i < r[3]; ++i) {
-        const double uu = uk[r[2] + i];
-        double gain = (uu >= -1.0 && uu <= 1.0) ? (cdat[3 + i] - cdat[i]) / 2.0 : 0.0;
+        const double gain = tape[3 * n * n + r[2] + i];
         double zz = 0.0;
         for (int m = 0; m < TS_MAXN; ++m) if (m == qo + i) zz = z[m];
         du_out[r[2] + i] = S.h * S.h * gain * zz;
@@ -1712,8 +1862,8 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
 }
 
 // ------------------------------------------------------------------ contact index sets (diagnostic outputs)
-// S.cmw words per env-step, force by force in scene order (ground forces first, one word each; then the
-// general-primitive forces, ceil(points / 32) words each): bit k of a force = its sampled point k is active.
+// S.cmw words per env-step, force by force in scene order (ground forces first, then the general-primitive
+// forces, ceil(points / 32) words each): bit k of a force = its sampled point k is active.
 // TactilePush: word 0 = ground force, words 1..3 = pad-box force.
 template <class WK>
 HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
@@ -1723,13 +1873,13 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
     const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
     const int b = r[0], po = r[1], pc = r[2];
     body_frame_v(S, W, b, R1, p1, ph);
-    for (int k = 0; k < pc && k < 32; ++k) {
+    for (int k = 0; k < pc; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
       double xw[3];
       mv3(R1, xi, xw);
       double d = (xw[0] + p1[0] - S.gx[0]) * S.gn[0] + (xw[1] + p1[1] - S.gx[1]) * S.gn[1] +
                  (xw[2] + p1[2] - S.gx[2]) * S.gn[2];
-      if (d <= 0.0) mw[r[3]] |= (1u << k);
+      if (d <= 0.0) mw[r[3] + (k >> 5)] |= (1u << (k & 31));
     }
   }
   for (int fi = 0; fi < S.ngp; ++fi) {
@@ -1763,7 +1913,7 @@ struct FwdArgs {
   double* q_traj; double* qd_traj;    // [T,B,n] or null
   double* var_out; const int* var_row; // [rows,B,nvar]; row of step t (null map = t), <0 = skip
   double* tac_out; const int* tac_row; // [rows,B,3M]
-  double* tape;                       // [T,B,3,n,n] or null
+  double* tape;                       // [T,B,ntape] or null (ntape = 3 n^2 + nu: H, G0, G1, dfr/du)
   int* status;                        // [T,B] or null
   unsigned* cmask;                    // [T,B,cmw] or null
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
@@ -1790,7 +1940,7 @@ template <class Tile, class WK>
 HDN void env_readout(const Tile& tl, const SceneView& S, const double* q, const double* qd, double* var_o,
                      double* tac_o, int* mb_o, unsigned* cm_o, WK& WS) {
   ArrIn<double> in;
-  in.q_ = q; in.qd_ = qd; in.dl_ = qd;
+  in.q_ = q; in.qd_ = qd; in.dl_ = qd; in.q0_ = q; in.qd0_ = qd;
   kinematics(S, in, WS, false);
   readout_from_work(tl, S, WS, var_o, tac_o, mb_o, cm_o);
 }
@@ -1825,7 +1975,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
       double cole[TS_NC(Tile::LPE)][TS_MAXN];
       if (!tile_done) {
         step_eval(tl, S, v, WD, cole);
-        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * 3 * n * n : (double*)0, WD, cole);
+        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * S.ntape : (double*)0, WD, cole);
       }
       TS_TOC2(tl, 5);
     }
@@ -1877,7 +2027,7 @@ struct BwdArgs {
   int B, T;
   const double* q_traj; const double* qd_traj;   // [T,B,n] states AFTER each step
   const double* u; long long u_stride;
-  const double* tape;                            // [T,B,3,n,n]
+  const double* tape;                            // [T,B,ntape]
   const double* df_dq; const int* dq_row;        // cotangents [rows,B,*]; row maps as in FwdArgs
   const double* df_dvar; const int* dvar_row;
   const double* df_dtac; const int* dtac_row;
@@ -1907,7 +2057,7 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
     const int r0 = a.df_dq ? (a.dq_row ? a.dq_row[t] : t) : -1;
     const int r1 = a.df_dvar ? (a.dvar_row ? a.dvar_row[t] : t) : -1;
     const int r2 = a.df_dtac ? (a.dtac_row ? a.dtac_row[t] : t) : -1;
-    step_backward(tl, S, u, a.tape + es * 3 * n * n,
+    step_backward(tl, S, u, a.tape + es * S.ntape,
                   r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
                   r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
                   r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,

@@ -7,11 +7,12 @@ import numpy as np
 from . import scene as S
 
 TS_MAGIC = 0x54533230
-TS_VERSION = 3
-MAXB, MAXN, MAXCAND = 24, 16, 4   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
+TS_VERSION = 4          # written; version-3 blobs (sensor records with 4 candidate slots) are still read
+MAXB, MAXN, MAXCAND = 24, 16, 8   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
 I_DOFF_MARKER_AXES = 22           # header slot: offset of the per-marker (axis0, axis1, normal) section, 0 = none
 I_HEADER, D_HEADER = 32, 16
-JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 8
+JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 12
+SI_V3 = 8
 JD, CD, AD, ED, SD = 48, 4, 12, 4, 16
 
 
@@ -20,9 +21,6 @@ def pack_scene(sc: "S.Scene"):
         raise S.SceneError(f"integrator {sc.integrator} is not supported by the B200 path yet (BDF1 only)")
     if sc.nj > MAXB or sc.ndof_r > MAXN:
         raise S.SceneError(f"scene too large for this build: nj={sc.nj} (max {MAXB}), ndof_r={sc.ndof_r} (max {MAXN})")
-    for a in sc.actuators:
-        if a["mode"] != S.ACT_FORCE:
-            raise S.SceneError("position-controlled motors are not supported by the B200 path yet")
     ints = [np.zeros(I_HEADER, dtype=np.int64)]
     dbls = [np.zeros(D_HEADER, dtype=np.float64)]
     hdr, dh = ints[0], dbls[0]
@@ -150,7 +148,7 @@ def pack_scene(sc: "S.Scene"):
 
 
 def unpack_sizes(ibuf):
-    if int(ibuf[0]) != TS_MAGIC or int(ibuf[1]) != TS_VERSION:
+    if int(ibuf[0]) != TS_MAGIC or int(ibuf[1]) not in (3, TS_VERSION):
         raise S.SceneError("not a tactilesimulation_b200 scene blob (magic/version mismatch)")
     nj, n, nu, nee, nm = (int(ibuf[i]) for i in (2, 3, 4, 5, 6))
     return dict(nj=nj, ndof_r=n, ndof_m=6 * nj, ndof_u=nu, ndof_var=3 * nee, n_markers=nm, ndof_tactile=3 * nm)
@@ -203,8 +201,9 @@ def scene_from_blob(ibuf, dbuf):
     for i in range(nee):
         r = ib[ib[20] + i * EI: ib[20] + (i + 1) * EI]; d = db[ib[28] + i * ED: ib[28] + (i + 1) * ED]
         sc.end_effectors.append(dict(joint=int(r[0]), pos=d[:3].copy(), name=""))
+    si = SI if int(ib[1]) >= 4 else SI_V3
     for i in range(nsens):
-        r = ib[ib[21] + i * SI: ib[21] + (i + 1) * SI]; d = db[ib[29] + i * SD: ib[29] + (i + 1) * SD]
+        r = ib[ib[21] + i * si: ib[21] + (i + 1) * si]; d = db[ib[29] + i * SD: ib[29] + (i + 1) * SD]
         M = int(r[2])
         if ib[I_DOFF_MARKER_AXES] > 0:
             A = db[ib[I_DOFF_MARKER_AXES] + 9 * r[1]: ib[I_DOFF_MARKER_AXES] + 9 * (r[1] + M)].reshape(M, 9)

@@ -40,10 +40,12 @@ from typing import Dict, List, Optional
 import numpy as np
 
 # joint types (values are shared with csrc/scene_layout.h)
-JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL = 0, 1, 2, 3, 4
-JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3}
+JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL, JT_FREE3D_EULER = 0, 1, 2, 3, 4, 5
+JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3, JT_FREE3D_EULER: 6}
+# "free3d" is the XYZ-Euler chart in the reference too (DH/Simulation_Constructor.cpp:483-484)
 JOINT_TYPES = {"fixed": JT_FIXED, "revolute": JT_REVOLUTE, "prismatic": JT_PRISMATIC,
-               "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL}
+               "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL,
+               "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER}
 # body shapes
 SH_NONE, SH_CUBOID, SH_CYLINDER, SH_SPHERE = 0, 1, 2, 3
 # actuator modes

@@ -103,7 +103,7 @@ class BatchedSim:
                 want_contacts=False, want_traj=True):
         """Advance (q, qd) [B,n] in place by T steps.  u: [T,B,nu], or [B,nu] held for all T steps.
         Returns a dict with q_traj, qd_traj [T,B,n], var [rows,B,nvar], tactile [rows,B,ntac] and, when
-        ``grad``, the adjoint tape [T,B,3,n,n]."""
+        ``grad``, the adjoint tape [T,B,3 n^2 + nu] (H, G0, G1 row-major, then d f_r/d u per control)."""
         B, n, nu = q.shape[0], self.ndof_r, self.ndof_u
         self._chk(q, (B, n), "q")
         self._chk(qd, (B, n), "qd")
@@ -124,7 +124,7 @@ class BatchedSim:
                       if (want_var and self.ndof_var) else None)
         out["tactile"] = (torch.zeros((ntr, B, self.ndof_tactile), dtype=torch.float64, device=dev)
                           if (want_tactile and self.ndof_tactile) else None)
-        out["tape"] = torch.empty((T, B, 3, n, n), dtype=torch.float64, device=dev) if grad else None
+        out["tape"] = torch.empty((T, B, self.tape_doubles), dtype=torch.float64, device=dev) if grad else None
         out["status"] = torch.zeros((T, B), dtype=torch.int32, device=dev) if want_status else None
         out["contact_masks"] = torch.zeros((T, B, self.cmask_words), dtype=torch.int32, device=dev) if want_contacts else None
         out["marker_body"] = (torch.full((ntr, B, self.n_markers), -1, dtype=torch.int32, device=dev)

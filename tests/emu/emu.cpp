@@ -5,6 +5,7 @@
 // fails loudly when the CUDA extension is missing.
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <vector>
 #include "../../tactilesimulation_b200/csrc/scene_lower.h"
 #include "../../tactilesimulation_b200/csrc/sim_core.cuh"
@@ -68,4 +69,11 @@ int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double
                 marker_body ? marker_body + (long long)env * S.nmark : 0, cmask ? cmask + (long long)env * S.cmw : 0, wb[0]);
   return 0;
 }
+}
+
+extern "C" const char* emu_lower_error(const int32_t* ibuf, const double* dbuf) {
+  static std::string err;
+  KernelTables kt;
+  err = lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt);
+  return err.c_str();
 }

@@ -58,7 +58,7 @@ def forward(ibuf, dbuf, q0, qd0, u, grad=False, var_row=None, tac_row=None, want
     l, cmw = lib_for(ibuf, dbuf)
     out = dict(q=np.zeros((T, B, n)), qd=np.zeros((T, B, n)), var=np.zeros((nv, B, 3 * nee)),
                tactile=np.zeros((nt, B, 3 * M)), status=np.zeros((T, B), dtype=np.int32),
-               tape=np.zeros((T, B, 3, n, n)) if grad else None,
+               tape=np.zeros((T, B, 3 * n * n + nu)) if grad else None,
                cmask=np.zeros((T, B, cmw), dtype=np.uint32) if want_masks else None,
                marker_body=np.zeros((nt, B, M), dtype=np.int32))
     l.emu_forward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(q), _p(qd), _p(u), ctypes.c_int64(B * nu),

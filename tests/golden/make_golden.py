@@ -202,6 +202,25 @@ def dclaw_case(T, seed):
     return multi_case(xml, q0, u, seed)
 
 
+def insertion_case(T, seed):
+    """TactileInsertion (R/envs/assets/tactile_insertion/tactile_insertion.xml, BASELINE configs[4]): position-controlled
+    gripper base (translational + revolute), force-controlled fingers, free3d-euler box in a hole of four cuboids,
+    two 13x10 pads.  Grasp as in R/envs/tactile_insertion_env.py:126-164 (fingers ramped closed), then the base is
+    driven sideways / rotated / down so that the box meets the hole walls."""
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_insertion", "tactile_insertion.xml")
+    q0 = np.zeros(12)
+    q0[2] = 0.2
+    q0[4] = q0[5] = -0.03
+    rng = np.random.default_rng(seed)
+    u = np.zeros((T, 6))
+    for t in range(T):
+        g = min(1.0, (t + 1) / 15.0)
+        m = max(0.0, (t - 25) / float(max(T - 25, 1)))
+        u[t] = [0.004 * m, -0.003 * m, 0.2 - 0.002 * m, 0.15 * m, g, g]
+    u[:, :4] += 1e-4 * rng.normal(size=(T, 4))
+    return multi_case(xml, q0, u, seed)
+
+
 def main():
     x13 = os.path.join(ASSETS, "pusher.xml")
     x32 = os.path.join(ASSETS, "pusher_32x13.xml")
@@ -211,6 +230,7 @@ def main():
         "pusher32x13_episodic_s0": lambda: episodic_case(x32, 30, 0),
         "pusher13x10_stepsim_s0": lambda: stepsim_case(x13, 8, 5, 0),
         "dclaw_episodic_s0": lambda: dclaw_case(40, 0),
+        "insertion_episodic_s0": lambda: insertion_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
     if only:

@@ -85,9 +85,10 @@ def test_emulated_matches_oracle_on_fresh_seed():
         assert (out["status"][t, 0] & 255) == o.newton_iters[t]
         # tape: H and the adjoint blocks G0 = -M + hD, G1 = -hM (FORCE motors)
         H, M, D = o.tape["H"][t], o.tape["M"][t], o.tape["D"][t]
-        assert rel_err(out["tape"][t, 0, 0], H) <= 1e-8
-        assert rel_err(out["tape"][t, 0, 1], -M + o.h * D) <= 1e-8
-        assert rel_err(out["tape"][t, 0, 2], -o.h * M) <= 1e-8
+        tp = out["tape"][t, 0, :3 * 49].reshape(3, 7, 7)
+        assert rel_err(tp[0], H) <= 1e-8
+        assert rel_err(tp[1], -M + o.h * D) <= 1e-8
+        assert rel_err(tp[2], -o.h * M) <= 1e-8
     dq, dv, dt = rng.normal(size=(T, 7)), rng.normal(size=(T, 6)), 1e-3 * rng.normal(size=(T, 390))
     ref = o.backward(dq, dv, dt)
     bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, u[:, None, :], dq[:, None], dv[:, None], dt[:, None])
@@ -116,6 +117,30 @@ def test_emulated_dclaw_matches_reference():
         assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
     bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], g["df_dq"][:, None, :],
                           g["df_dvar"][:, None, :], g["df_dtactile"][:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_insertion_matches_reference():
+    """TactileInsertion (BASELINE configs[4], the reference's own asset): 12 reduced dofs, position-controlled base
+    (PD on the previous state: extra adjoint terms), free3d-euler box, prismatic fingers, ten general-primitive
+    contacts, two sensors with 7 candidate bodies each (one of them the other pad, a cylinder)."""
+    from tests.blob_scene import scene_from_blob
+    from tests.multi_force import expected_words
+    g = np.load(os.path.join(GOLDEN, "insertion_episodic_s0.npz"))
+    sc = scene_from_blob(g["ibuf"], g["dbuf"])
+    T = g["u"].shape[0]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert np.array_equal(out["cmask"][t, 0].astype(np.uint64), expected_words(sc, g["ground_ids_f"][t], g["gp_ids_f"][t])), t
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], g["df_dq"][:, None, :], None,
+                          g["df_dtactile"][:, None, :])
     assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
     assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
     assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
