@@ -28,6 +28,8 @@
 #define KT_MAXPW 5       // 32-bit words of an active-point bitmask: <= 160 sampled points per general body
 #define KT_CYLINDER 1    // cylinder SDF primitives (contact force, tactile candidates)
 #define KT_MAXCAND 8     // tactile candidate bodies per sensor
+#define KT_FREE3D 1      // free3d-euler joints
+#define KT_POS_MOTOR 1   // position-controlled motors
 #else
 #define KT_MAXJ 8        // moving joints
 #define KT_MAXN 8        // reduced dofs
@@ -36,6 +38,8 @@
 #define KT_MAXPW 3       // <= 96 sampled points per general body
 #define KT_CYLINDER 0    // cuboid primitives only: the TactilePush hot path carries no cylinder code
 #define KT_MAXCAND 4     // tactile candidate bodies per sensor
+#define KT_FREE3D 0      // revolute / prismatic / planar / translational joints only
+#define KT_POS_MOTOR 0   // force-controlled motors only
 #endif
 
 enum {

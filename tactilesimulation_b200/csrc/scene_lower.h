@@ -62,6 +62,8 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int j = 0; j < nj; ++j) {
     const int jt = J[j * TS_JI_STRIDE], par = J[j * TS_JI_STRIDE + 1];
     if (par >= j) return "joints are not in parent-first order";
+    if (jt == TS_JT_FREE3D_EULER && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler joints)";
+    if (jt < TS_JT_FIXED || jt > TS_JT_FREE3D_EULER) return "unknown joint type";
     const Xf e0 = xf_load(JD + j * TS_JD_STRIDE + TS_JD_RPJ, JD + j * TS_JD_STRIDE + TS_JD_PPJ);
     const Xf up = (par < 0) ? e0 : xf_mul(erel[par], e0);
     if (jt == TS_JT_FIXED) {
@@ -213,6 +215,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int* r = ib + ib[TS_I_OFF_ACT] + a * TS_AI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_ACT] + a * TS_AD_STRIDE;
     if (midx[r[0]] < 0) return "actuator on a fixed joint";
+    if (r[1] == TS_ACT_POS && !KT_POS_MOTOR) return "scene exceeds the compiled capacity (position-controlled motors)";
     int rec[KA_ISTRIDE] = {midx[r[0]], r[1], r[2], r[3]};
     oi.insert(oi.end(), rec, rec + KA_ISTRIDE);
     od.insert(od.end(), c, c + KA_DSTRIDE);

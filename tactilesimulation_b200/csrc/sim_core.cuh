@@ -289,7 +289,7 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         sq[i] = w[i] * in.qd(qo); sq[3 + i] = m[i] * in.qd(qo);
         if (dyn) { sl[i] = w[i] * in.dl(qo); sl[3 + i] = m[i] * in.dl(qo); }
       }
-    } else if (jt == TS_JT_FREE3D_EULER) {
+    } else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       // q = (p, r): Q = [R(r) p; 0 1], R = Rx(r1) Ry(r2) Rz(r3)   (DH/Joint/JointFree3DEuler.cpp:14-104,
       // JointSphericalEuler.cpp:15-60).  In the pre-motion frame a the child moves with the twist
       // xi = (G rdot, pdot + p x G rdot) about a's origin, G = [e_x, Rx e_y, Rx Ry e_z]; the rotation axes move
@@ -901,7 +901,7 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     } else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, fj);
     else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, fj); g[qo + 1] = dot3(a1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = fj[0]; g[qo + 1] = fj[1]; g[qo + 2] = fj[2]; }
-    else if (jt == TS_JT_FREE3D_EULER) {
+    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       T tax[3][3], rax[3][3], pf[3], t[3];
       euler_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
       cross3(p0, A + 3, pf);             // moment about the joint origin
@@ -923,7 +923,7 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     const int* r = S.ib + S.o_act + ai * KA_ISTRIDE;
     const double* c = S.db + S.d_act + ai * KA_DSTRIDE;
     const int qo = S.ib[S.o_joint + r[0] * KJ_ISTRIDE + 2];
-    if (r[1] == TS_ACT_POS) {
+    if (KT_POS_MOTOR && r[1] == TS_ACT_POS) {
       for (int i = 0; i < r[3]; ++i)
         g[qo + i] = g[qo + i] - h2 * pos_motor_force(u[r[2] + i], in.q0(qo + i), in.qd0(qo + i), c[6 + i], c[9 + i], c[i], c[3 + i]);
     } else {
@@ -1189,7 +1189,7 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
       cross3(p0, Sk, Sk + 3);
     } else if (jt == TS_JT_PRISMATIC) mv3(R0, jd + KJ_AX0, Sk + 3);
     else if (jt == TS_JT_PLANAR) mv3(R0, loc == 0 ? jd + KJ_AX0 : jd + KJ_AX1, Sk + 3);
-    else if (jt == TS_JT_FREE3D_EULER) {
+    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       double tax[3][3], rax[3][3];
       euler_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
       if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
@@ -1235,7 +1235,7 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
     } else if (jt == TS_JT_PRISMATIC) Mcol[qo] = dot3(jd + KJ_AX0, fj);
     else if (jt == TS_JT_PLANAR) { Mcol[qo] = dot3(jd + KJ_AX0, fj); Mcol[qo + 1] = dot3(jd + KJ_AX1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { Mcol[qo] = fj[0]; Mcol[qo + 1] = fj[1]; Mcol[qo + 2] = fj[2]; }
-    else if (jt == TS_JT_FREE3D_EULER) {
+    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       double tax[3][3], rax[3][3], pf[3], t[3];
       euler_world_axes(R0, qv[qo + 3], qv[qo + 4], qv[qo + 5], tax, rax);
       cross3(p0, A + 3, pf);
@@ -1330,7 +1330,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         for (int i = 0; i < r[3]; ++i) {
           const double uu = ts.u[r[2] + i];
           double gain;
-          if (r[1] == TS_ACT_POS) {
+          if (KT_POS_MOTOR && r[1] == TS_ACT_POS) {
             const double f = cdat[6 + i] * (uu - ts.q[qo + i]) + cdat[9 + i] * (-ts.qd[qo + i]);
             const bool open = f >= cdat[i] && f <= cdat[3 + i];
             gain = open ? cdat[6 + i] : 0.0;
