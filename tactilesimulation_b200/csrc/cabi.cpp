@@ -60,7 +60,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   int rc = 1;
   const bool skip8 = force && atoi(force) == 16;
   if (!skip8) rc = tsim_scene_create_v8(ibuf, n_int, dbuf, n_dbl, device, &inner);
-  if (skip8 || std::string(tsim_last_error_v8()).find("compiled capacit") != std::string::npos) {
+  if (skip8 || (rc != 0 && std::string(tsim_last_error_v8()).find("compiled capacit") != std::string::npos)) {
     variant = 16;
     rc = tsim_scene_create_v16(ibuf, n_int, dbuf, n_dbl, device, &inner);
   }

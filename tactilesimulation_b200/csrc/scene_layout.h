@@ -33,6 +33,8 @@ enum {
   // offset (doubles) of the optional per-marker (axis0, axis1, normal) section, 9 doubles per marker; 0 = the
   // per-sensor axes of the sensor record apply to all its markers (blobs written before abstract sensors)
   TS_I_DOFF_MARKER_AXES = 22,
+  // int offset of the per-marker image positions (row, col); host-side only (flow images), 0 = none
+  TS_I_OFF_MARKER_IMAGE = 23,
   // offsets (in elements) of the double sections
   TS_I_DOFF_JOINT = 24, TS_I_DOFF_GROUND, TS_I_DOFF_GP, TS_I_DOFF_ACT, TS_I_DOFF_EE,
   TS_I_DOFF_SENSOR, TS_I_DOFF_POINTS, TS_I_DOFF_MARKERS,

@@ -9,6 +9,7 @@ from . import scene as S
 TS_MAGIC = 0x54533230
 TS_VERSION = 4          # written; version-3 blobs (sensor records with 4 candidate slots) are still read
 MAXB, MAXN, MAXCAND = 24, 16, 8   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
+I_OFF_MARKER_IMAGE = 23           # header slot: int offset of the per-marker image positions (row, col), 0 = none
 I_DOFF_MARKER_AXES = 22           # header slot: offset of the per-marker (axis0, axis1, normal) section, 0 = none
 I_HEADER, D_HEADER = 32, 16
 JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 12
@@ -129,6 +130,10 @@ def pack_scene(sc: "S.Scene"):
         moff += len(s.pos)
     ints.append(si.reshape(-1))
     dbls.append(sd.reshape(-1))
+    if sc.sensors:
+        # image positions of the markers (host-side only: get_tactile_image_pos / get_tactile_flow_images)
+        hdr[I_OFF_MARKER_IMAGE] = ioff()
+        ints.append(np.concatenate([np.asarray(s.image_pos, dtype=np.int64).reshape(-1, 2) for s in sc.sensors], axis=0).reshape(-1))
 
     hdr[30] = doff()
     P = np.concatenate(pts, axis=0) if pts else np.zeros((0, 3))
@@ -210,8 +215,12 @@ def scene_from_blob(ibuf, dbuf):
             a0, a1, nr = A[:, 0:3].copy(), A[:, 3:6].copy(), A[:, 6:9].copy()
         else:
             a0, a1, nr = np.tile(d[4:7], (M, 1)), np.tile(d[7:10], (M, 1)), np.tile(d[10:13], (M, 1))
+        if ib[I_OFF_MARKER_IMAGE] > 0:
+            ipos = ib[ib[I_OFF_MARKER_IMAGE] + 2 * r[1]: ib[I_OFF_MARKER_IMAGE] + 2 * (r[1] + M)].reshape(M, 2).copy()
+        else:
+            ipos = np.zeros((M, 2), dtype=np.int64)
         sc.sensors.append(S.TactileSensor(name=f"sensor{i}", body=int(r[0]), kn=d[0], kt=d[1], mu=d[2], damping=d[3],
                                           pos=Mk[r[1]:r[1] + M].copy(), axis0=a0, axis1=a1, normal=nr,
-                                          image_pos=np.zeros((M, 2), dtype=np.int64),
+                                          image_pos=ipos,
                                           candidates=[int(c) for c in r[4:4 + r[3]]]))
     return sc

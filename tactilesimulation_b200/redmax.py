@@ -88,11 +88,12 @@ class _Chunk:
 
 
 class Simulation:
-    def __init__(self, xml_file_path, verbose: bool = False, batch: int = 1, device="cuda:0", lanes: int = 8):
+    def __init__(self, xml_file_path, verbose: bool = False, batch: int = 1, device="cuda:0", lanes: Optional[int] = None):
         if isinstance(xml_file_path, Scene):
             self.scene = xml_file_path
         else:
             self.scene = compile_scene(str(xml_file_path))
+        self._lanes = lanes
         self.core = BatchedSim(self.scene, device=device, lanes=lanes)
         self.device = self.core.device
         self.batch = int(batch)
@@ -200,6 +201,79 @@ class Simulation:
                 return [vec[off + 3 * i: off + 3 * i + 3].copy() for i in range(M)]
             off += 3 * M
         raise TactileSimError(f"tactile sensor {name} not found")
+
+    def _sensor(self, name):
+        for i, s in enumerate(self.scene.sensors):
+            if s.name == name:
+                return i, s
+        raise TactileSimError(f"tactile sensor {name} not found")
+
+    def _sensor_forces(self, name):
+        i, s = self._sensor(name)
+        off = 3 * sum(len(t.pos) for t in self.scene.sensors[:i])
+        return self.get_tactile_force_vector()[off:off + 3 * len(s.pos)].reshape(-1, 3)
+
+    def get_tactile_normal_force(self, name):
+        """python_interface.cpp:150-152: the normal component per marker."""
+        return [float(f[2]) for f in self._sensor_forces(name)]
+
+    def get_tactile_shear_force(self, name):
+        """python_interface.cpp:153-155: (shear . axis0, shear . axis1) per marker."""
+        return [f[:2].copy() for f in self._sensor_forces(name)]
+
+    def get_tactile_flow_images(self):
+        """DH/Robot.cpp:372-387: per sensor, the force vectors scattered to their image positions
+        (rows x cols x 3, zero where the sensor has no marker)."""
+        vec = self.get_tactile_force_vector()
+        out, off = [], 0
+        for s in self.scene.sensors:
+            M = len(s.pos)
+            ip = np.asarray(s.image_pos, dtype=np.int64).reshape(M, 2)
+            img = np.zeros((int(ip[:, 0].max()) + 1, int(ip[:, 1].max()) + 1, 3))
+            img[ip[:, 0], ip[:, 1]] = vec[off:off + 3 * M].reshape(M, 3)
+            out.append(img)
+            off += 3 * M
+        return out
+
+    # ------------------------------------------------------------------ parameter updates (domain randomisation)
+    # The scene tables are batch-invariant and live once per handle: an update edits the host scene and
+    # uploads a new handle (python_interface.cpp:181-211; DH/Robot.cpp update_* walk the pointer graph).
+    def _rebuild(self):
+        self.core = BatchedSim(self.scene, device=self.device, lanes=self._lanes)
+
+    def update_contact_parameters(self, body1, body2, kn, kt, mu, damping):
+        names = self.scene.body_names
+        hit = False
+        for f in self.scene.gp_contacts:
+            if names[f["body1"]] == body1 and names[f["body2"]] == body2:
+                f.update(kn=float(kn), kt=float(kt), mu=float(mu), damping=float(damping))
+                hit = True
+        if not hit:
+            raise TactileSimError(f"contact {body1} - {body2} not found")
+        self._rebuild()
+
+    def update_tactile_parameters(self, name, kn, kt, mu, damping):
+        _, s = self._sensor(name)
+        s.kn, s.kt, s.mu, s.damping = float(kn), float(kt), float(mu), float(damping)
+        self._rebuild()
+
+    def update_joint_damping(self, joint_name, damping):
+        if joint_name not in self.scene.joint_names:
+            raise TactileSimError(f"joint {joint_name} not found")
+        self.scene.damping[self.scene.joint_names.index(joint_name)] = float(damping)
+        self._rebuild()
+
+    def update_endeffector_position(self, endeffector_name, position):
+        for e in self.scene.end_effectors:
+            if e["name"] == endeffector_name:
+                e["pos"] = np.asarray(position, dtype=np.float64).copy()
+                self._rebuild()
+                return
+        raise TactileSimError(f"endeffector {endeffector_name} not found")
+
+    def update_body_color(self, body_name, color):
+        """Render-only."""
+        return None
 
     def update_virtual_object(self, name, data):
         """Render-only objects (goal marker) do not enter the dynamics: accepted as a no-op."""
@@ -373,7 +447,15 @@ class Simulation:
         return None
 
     def export_replay(self, path):
-        raise TactileSimError("export_replay is out of scope of the B200 path (no viewer)")
+        """Trajectory export for an offline viewer (the role of DH/Simulation.cpp export_replay): one text line
+        per recorded sim-step holding the reduced coordinates q (environment 0), preceded by a header line
+        `ndof_r num_steps h`.  Only grad-mode rollouts keep their q history on the device."""
+        rows = [c.fwd["q_traj"][:, 0].cpu().numpy() for c in self._chunks if c.fwd.get("q_traj") is not None]
+        qs = np.concatenate(rows, axis=0) if rows else np.zeros((0, self.ndof_r))
+        with open(path, "w") as f:
+            f.write(f"{self.ndof_r} {len(qs)} {self.options.h!r}\n")
+            for q in qs:
+                f.write(" ".join(repr(float(x)) for x in q) + "\n")
 
     def print_time_report(self):
         print("[tactilesimulation_b200] timing lives in CUDA events / ncu; see bench.py")

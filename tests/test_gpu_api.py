@@ -124,3 +124,48 @@ def test_batched_stepsim_function_autograd_chain():
     loss.backward()
     for t in range(ns):
         assert rel_err(us[t].grad[1].cpu().numpy(), g["df_du"][t].sum(axis=0)) <= 1e-6, t
+
+
+def test_compat_simulation_dclaw_surface():
+    """The calls R/envs/dclaw_rotate_env.py and tactile_insertion_env.py make beyond the TactilePush set:
+    get_tactile_flow_images (DH/Robot.cpp:372-387), get_tactile_image_pos, update_tactile_parameters /
+    update_contact_parameters / update_joint_damping (domain randomisation), export_replay."""
+    from tactilesimulation_b200 import TactileSimError
+    from tactilesimulation_b200.redmax import Simulation
+    g = np.load(os.path.join(GOLDEN, "dclaw_episodic_s0.npz"))
+    sc = _scene(g)
+    for i, s in enumerate(sc.sensors):
+        s.name = f"finger{i}"
+    sim = Simulation(sc)
+    assert (sim.ndof_r, sim.ndof_u, sim.ndof_var, sim.ndof_tactile) == (10, 9, 12, 2718)
+    t = 12
+    sim.set_state_init(g["q"][t], g["qd"][t])
+    sim.reset(backward_flag=False)
+    vec = sim.get_tactile_force_vector()
+    assert rel_err(vec, g["tactile"][t]) <= 1e-8 and np.abs(vec).max() > 0
+    imgs = sim.get_tactile_flow_images()
+    assert len(imgs) == 3 and all(im.shape[2] == 3 for im in imgs)
+    for i, sen in enumerate(sc.sensors):                     # reference semantics: a later marker overwrites
+        ref = np.zeros_like(imgs[i])
+        for m, (r, c) in enumerate(sen.image_pos):
+            ref[r, c] = vec.reshape(3, 302, 3)[i, m]
+        assert np.array_equal(imgs[i], ref) and imgs[i].shape[:2] == (20, 20)
+    nf = np.array(sim.get_tactile_normal_force("finger1"))
+    assert nf.shape == (302,) and np.allclose(nf, vec.reshape(3, 302, 3)[1, :, 2])
+    s1 = sc.sensors[1]
+    sim.update_tactile_parameters("finger1", s1.kn * 2.0, s1.kt * 2.0, s1.mu, s1.damping * 2.0)
+    vec2 = sim.get_tactile_force_vector().reshape(3, 302, 3)
+    assert np.allclose(vec2[0], vec.reshape(3, 302, 3)[0]) and not np.allclose(vec2[1], vec.reshape(3, 302, 3)[1])
+    with pytest.raises(TactileSimError):
+        sim.update_tactile_parameters("nope", 1, 1, 1, 1)
+    with pytest.raises(TactileSimError):
+        sim.update_contact_parameters("a", "b", 1, 1, 1, 1)
+    sim.update_joint_damping(sc.joint_names[3], 0.5)
+    sim.reset(backward_flag=True)
+    sim.set_u(g["u"][t])
+    sim.forward(3)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        sim.export_replay(os.path.join(d, "replay.txt"))
+        lines = open(os.path.join(d, "replay.txt")).read().strip().split("\n")
+        assert lines[0].split()[:2] == ["10", "3"] and len(lines) == 4
