@@ -59,10 +59,13 @@ else
 fi
 # Scene assets the reference binary needs at run time (XML + meshes are data, not source;
 # they live only in the git-ignored _ref directory so the reference arm can run on the GPU box).
-for scene in pusher; do
+for scene in pusher dclaw_rotate tactile_insertion; do
   mkdir -p "$OUT/assets/$scene"
-  cp -f "$REF/envs/assets/$scene"/* "$OUT/assets/$scene/"
+  cp -rf "$REF/envs/assets/$scene"/* "$OUT/assets/$scene/"
 done
+# BASELINE configs[0] (RollingBallExp test_sim_speed.py): reference-only plumbing case, tools/ref_config0.py
+mkdir -p "$OUT/assets/tactile_pad"
+cp -rf "$REF/assets/tactile_pad"/* "$OUT/assets/tactile_pad/"
 # synthetic 32x13 variant named by BASELINE.json (same scene, denser marker grid)
 sed 's/resolution="13 10"/resolution="32 13"/' "$OUT/assets/pusher/pusher.xml" > "$OUT/assets/pusher/pusher_32x13.xml"
 echo "build_ref: assets in $OUT/assets"
