@@ -65,7 +65,7 @@ def test_sub_batch_reproduces_its_slice(full):
 
 def _cot(out, seed):
     gen = torch.Generator(device=out["q_traj"].device).manual_seed(seed)
-    mk = lambda t, s: (s * torch.randn(t.shape, generator=gen, device=t.device, dtype=torch.float64)).contiguous()
+    mk = lambda t, s: None if t is None else (s * torch.randn(t.shape, generator=gen, device=t.device, dtype=torch.float64)).contiguous()
     return mk(out["q_traj"], 1.0), mk(out["var"], 1.0), mk(out["tactile"], 1e-3)
 
 
@@ -136,3 +136,42 @@ def test_adjoint_matches_directional_finite_differences():
     assert (rel <= 1e-3).mean() >= 0.75, (rel <= 1e-3).mean()
     rel = _fd_check(contact=True, Ts=30, eps=1e-4)
     assert np.median(rel) <= 0.1, np.median(rel)
+
+
+@pytest.mark.parametrize("name", ["dclaw_episodic_s0", "insertion_episodic_s0"])
+def test_variant16_batch_independence_and_chunked_adjoint(name):
+    """16-dof kernel variant (DClaw, TactileInsertion) at a batch that fills several CTAs: environments with
+    perturbed actions do not interfere (permutation bit-exactness), the golden environment embedded in the batch
+    reproduces the reference, and the chunked reverse sweep equals the one-shot sweep."""
+    from tactilesimulation_b200.sim import BatchedSim
+    from tests.conftest import rel_err
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sim = BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0")
+    dev = sim.device
+    Bv, T = 200, g["u"].shape[0]
+    rng = np.random.default_rng(5)
+    u = np.tile(g["u"][:, None, :], (1, Bv, 1))
+    u[:, 1:] += 0.02 * rng.normal(size=(T, Bv - 1, u.shape[2])) * (np.abs(u[:, 1:]) > 0)
+    q0 = torch.tensor(np.tile(g["q0"], (Bv, 1)), device=dev)
+    qd0 = torch.zeros_like(q0)
+    tu = torch.tensor(u, device=dev)
+    out = sim.forward(q0.clone(), qd0.clone(), tu, T, grad=True, want_status=True)
+    perm = torch.randperm(Bv, generator=torch.Generator().manual_seed(1)).to(dev)
+    o2 = sim.forward(q0[perm].contiguous(), qd0[perm].contiguous(), tu[:, perm].contiguous(), T, grad=True, want_status=True)
+    torch.cuda.synchronize()
+    for k in ("q_traj", "tactile", "tape", "status"):
+        assert torch.equal(o2[k], out[k][:, perm]), k
+    assert rel_err(out["q_traj"][-1, 0].cpu().numpy(), g["q"][-1]) <= 1e-9
+    assert rel_err(out["tactile"][-1, 0].cpu().numpy(), g["tactile"][-1]) <= 1e-8
+    wq, wv, wt = _cot(out, 3)
+    full = sim.backward(out, tu, T, wq, wv, wt, want_q0=True)
+    half = T // 2
+    carry, parts = None, []
+    for c0, c1 in ((half, T), (0, half)):
+        sub = {k: out[k][c0:c1] for k in ("q_traj", "qd_traj", "tape")}
+        r = sim.backward(sub, tu[c0:c1], c1 - c0, wq[c0:c1], None if wv is None else wv[c0:c1], wt[c0:c1], carry=carry,
+                         want_q0=(c0 == 0))
+        carry = r["carry"]
+        parts.insert(0, r["df_du"])
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(parts, 0), full["df_du"]) and torch.equal(r["df_dq0"], full["df_dq0"])
