@@ -59,7 +59,7 @@ else
 fi
 # Scene assets the reference binary needs at run time (XML + meshes are data, not source;
 # they live only in the git-ignored _ref directory so the reference arm can run on the GPU box).
-for scene in pusher dclaw_rotate tactile_insertion; do
+for scene in pusher dclaw_rotate tactile_insertion stable_grasp; do
   mkdir -p "$OUT/assets/$scene"
   cp -rf "$REF/envs/assets/$scene"/* "$OUT/assets/$scene/"
 done

@@ -27,7 +27,7 @@
 #define KT_MAXU 16       // controls
 #define KT_MAXPW 5       // 32-bit words of an active-point bitmask: <= 160 sampled points per general body
 #define KT_CYLINDER 1    // cylinder SDF primitives (contact force, tactile candidates)
-#define KT_MAXCAND 8     // tactile candidate bodies per sensor
+#define KT_MAXCAND 16    // tactile candidate bodies per sensor (StableGrasp: 15)
 #define KT_FREE3D 1      // free3d-euler joints
 #define KT_POS_MOTOR 1   // position-controlled motors
 #else

@@ -5,7 +5,7 @@
 #pragma once
 
 #define TS_MAGIC 0x54533230  // "TS20"
-#define TS_VERSION 4         // 3: sensor records carry up to 4 candidate bodies; 4: up to 8 (both are accepted)
+#define TS_VERSION 5         // sensor records carry up to 4 (version 3), 8 (4) or 16 (5) candidate bodies; all are accepted
 #define TS_VERSION_MIN 3
 
 // ---- joint types / shapes / actuator modes (scene.py uses the same values)
@@ -48,7 +48,8 @@ enum {
 #define TS_AI_STRIDE 4      // joint, mode, uoff, ndof
 #define TS_EI_STRIDE 2      // joint, unused
 #define TS_SI_STRIDE_V3 8   // body, marker_off, marker_cnt, ncand, cand[4]
-#define TS_SI_STRIDE 12     // body, marker_off, marker_cnt, ncand, cand[8]
+#define TS_SI_STRIDE_V4 12  // body, marker_off, marker_cnt, ncand, cand[8]
+#define TS_SI_STRIDE 20     // body, marker_off, marker_cnt, ncand, cand[16]
 
 // double header: h, g(3), tol, ground normal(3), ground origin(3)
 enum { TS_D_H = 0, TS_D_GRAV = 1, TS_D_TOL = 4, TS_D_GN = 5, TS_D_GX = 8, TS_D_HEADER = 16 };

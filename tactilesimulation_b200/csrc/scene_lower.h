@@ -47,7 +47,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   using namespace tsim_lower;
   if (ni < TS_I_HEADER || ib[TS_I_MAGIC] != TS_MAGIC || ib[TS_I_VERSION] < TS_VERSION_MIN || ib[TS_I_VERSION] > TS_VERSION)
     return "not a scene blob of this version";
-  const int si_stride = ib[TS_I_VERSION] >= 4 ? TS_SI_STRIDE : TS_SI_STRIDE_V3;
+  const int si_stride = ib[TS_I_VERSION] >= 5 ? TS_SI_STRIDE : (ib[TS_I_VERSION] == 4 ? TS_SI_STRIDE_V4 : TS_SI_STRIDE_V3);
   const int nj = ib[TS_I_NJ], n = ib[TS_I_NDOF_R], nu = ib[TS_I_NDOF_U], nee = ib[TS_I_NEE], nmark = ib[TS_I_NMARKERS];
   const int nground = ib[TS_I_NGROUND], ngp = ib[TS_I_NGP], nact = ib[TS_I_NACT], nsens = ib[TS_I_NSENSORS];
   const int npoints = ib[TS_I_NPOINTS];

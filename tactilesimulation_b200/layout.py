@@ -7,13 +7,13 @@ import numpy as np
 from . import scene as S
 
 TS_MAGIC = 0x54533230
-TS_VERSION = 4          # written; version-3 blobs (sensor records with 4 candidate slots) are still read
-MAXB, MAXN, MAXCAND = 24, 16, 8   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
+TS_VERSION = 5          # written; version-3 / 4 blobs (sensor records with 4 / 8 candidate slots) are still read
+MAXB, MAXN, MAXCAND = 24, 16, 16   # largest kernel capacities (csrc/kernel_layout.h, variant 16): bodies, dofs, candidates
 I_OFF_MARKER_IMAGE = 23           # header slot: int offset of the per-marker image positions (row, col), 0 = none
 I_DOFF_MARKER_AXES = 22           # header slot: offset of the per-marker (axis0, axis1, normal) section, 0 = none
 I_HEADER, D_HEADER = 32, 16
-JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 12
-SI_V3 = 8
+JI, GI, PI, AI, EI, SI = 8, 4, 4, 4, 2, 20
+SI_BY_VERSION = {3: 8, 4: 12, 5: 20}
 JD, CD, AD, ED, SD = 48, 4, 12, 4, 16
 
 
@@ -153,7 +153,7 @@ def pack_scene(sc: "S.Scene"):
 
 
 def unpack_sizes(ibuf):
-    if int(ibuf[0]) != TS_MAGIC or int(ibuf[1]) not in (3, TS_VERSION):
+    if int(ibuf[0]) != TS_MAGIC or int(ibuf[1]) not in SI_BY_VERSION:
         raise S.SceneError("not a tactilesimulation_b200 scene blob (magic/version mismatch)")
     nj, n, nu, nee, nm = (int(ibuf[i]) for i in (2, 3, 4, 5, 6))
     return dict(nj=nj, ndof_r=n, ndof_m=6 * nj, ndof_u=nu, ndof_var=3 * nee, n_markers=nm, ndof_tactile=3 * nm)
@@ -206,7 +206,7 @@ def scene_from_blob(ibuf, dbuf):
     for i in range(nee):
         r = ib[ib[20] + i * EI: ib[20] + (i + 1) * EI]; d = db[ib[28] + i * ED: ib[28] + (i + 1) * ED]
         sc.end_effectors.append(dict(joint=int(r[0]), pos=d[:3].copy(), name=""))
-    si = SI if int(ib[1]) >= 4 else SI_V3
+    si = SI_BY_VERSION[int(ib[1])]
     for i in range(nsens):
         r = ib[ib[21] + i * si: ib[21] + (i + 1) * si]; d = db[ib[29] + i * SD: ib[29] + (i + 1) * SD]
         M = int(r[2])

@@ -221,6 +221,30 @@ def insertion_case(T, seed):
     return multi_case(xml, q0, u, seed)
 
 
+def stable_grasp_case(T, seed):
+    """StableGrasp (R/envs/assets/stable_grasp/stable_grasp.xml): position-controlled gripper closing on a bar of eleven
+    rigidly connected boxes (free3d-euler), lifting it; 44 general-primitive and 11 ground contacts, two pads with 15
+    candidate bodies each.  Stages 2-3 of R/envs/stable_grasp_env.py:197-246, shortened."""
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "stable_grasp", "stable_grasp.xml")
+    q0 = np.zeros(12)
+    q0[2] = 0.2029862
+    q0[4] = q0[5] = -0.03
+    rng = np.random.default_rng(seed)
+    gp = 0.01                                  # grasp position along the bar: off-centre, the bar tilts when lifted
+    q0[1] = gp
+    stages = [np.array([0.0, gp, 0.2029862, 0.0, -0.03, -0.03]), np.array([0.0, gp, 0.2029862, 0.0, -0.008, -0.008]),
+              np.array([0.0, gp, 0.2029862, 0.0, -0.008, -0.008]), np.array([0.0, gp, 0.2329862, 0.0, -0.008, -0.008])]
+    steps = [20, 8, T - 28]
+    u = []
+    for st in range(3):
+        for i in range(steps[st]):
+            u.append((stages[st + 1] - stages[st]) / steps[st] * (i + 1) + stages[st])
+    u = np.array(u)
+    u[:, 2] += 0.003
+    u[:, :4] += 1e-5 * rng.normal(size=(T, 4))
+    return multi_case(xml, q0, u, seed)
+
+
 def main():
     x13 = os.path.join(ASSETS, "pusher.xml")
     x32 = os.path.join(ASSETS, "pusher_32x13.xml")
@@ -231,6 +255,7 @@ def main():
         "pusher13x10_stepsim_s0": lambda: stepsim_case(x13, 8, 5, 0),
         "dclaw_episodic_s0": lambda: dclaw_case(40, 0),
         "insertion_episodic_s0": lambda: insertion_case(60, 0),
+        "stable_grasp_episodic_s0": lambda: stable_grasp_case(50, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
     if only:

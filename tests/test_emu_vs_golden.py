@@ -122,13 +122,16 @@ def test_emulated_dclaw_matches_reference():
     assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
 
 
-def test_emulated_insertion_matches_reference():
+@pytest.mark.parametrize("name", ["insertion_episodic_s0", "stable_grasp_episodic_s0"])
+def test_emulated_insertion_and_stable_grasp_match_reference(name):
     """TactileInsertion (BASELINE configs[4], the reference's own asset): 12 reduced dofs, position-controlled base
     (PD on the previous state: extra adjoint terms), free3d-euler box, prismatic fingers, ten general-primitive
-    contacts, two sensors with 7 candidate bodies each (one of them the other pad, a cylinder)."""
+    contacts, two sensors with 7 candidate bodies each (one of them the other pad, a cylinder).
+    StableGrasp: all four motors position-controlled, a bar of eleven boxes on a free3d-euler joint, 44
+    general-primitive + 11 ground contacts, 15 candidate bodies per sensor."""
     from tests.blob_scene import scene_from_blob
     from tests.multi_force import expected_words
-    g = np.load(os.path.join(GOLDEN, "insertion_episodic_s0.npz"))
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
     sc = scene_from_blob(g["ibuf"], g["dbuf"])
     T = g["u"].shape[0]
     out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)

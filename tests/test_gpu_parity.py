@@ -145,7 +145,8 @@ def test_batched_line_search_equals_sequential_search():
     assert np.array_equal(ta, tb)
 
 
-MULTI = {"dclaw_episodic_s0": (10, 90, 9, 12, 2718), "insertion_episodic_s0": (12, 78, 6, 0, 780)}
+MULTI = {"dclaw_episodic_s0": (10, 90, 9, 12, 2718), "insertion_episodic_s0": (12, 78, 6, 0, 780),
+         "stable_grasp_episodic_s0": (12, 126, 6, 0, 780)}
 
 
 @pytest.mark.parametrize("lanes", [16, 32])
@@ -155,7 +156,8 @@ def test_dclaw_and_insertion_match_reference(name, lanes):
     DClaw rotate-cap: 10 reduced dofs, abstract bodies, cylinder SDF, three abstract 302-marker sensors, three
     contact forces.  TactileInsertion: 12 reduced dofs, position-controlled base (extra adjoint terms),
     free3d-euler box, prismatic fingers, ground + ten general-primitive contacts, two 13x10 pads with seven
-    candidate bodies each."""
+    candidate bodies each.  StableGrasp (the fourth env of the reference): four position-controlled motors, a bar
+    of eleven boxes, 44 + 11 contact forces, fifteen candidate bodies per pad."""
     from tests.blob_scene import scene_from_blob
     from tests.multi_force import expected_words
     from tactilesimulation_b200.sim import BatchedSim
