@@ -54,8 +54,12 @@ int tsim_scene_sizes(const tsim_scene* scene, int32_t* out /* [TSIM_N_SIZES] */)
 int tsim_scene_set_lanes(tsim_scene* scene, int lanes_per_env);
 /* Solver options of a scene handle (no reference counterpart: the reference searches sequentially).
  *   TSIM_OPT_LS_BATCH  1 (default): after two rejected line-search trials the lanes of the tile evaluate the
- *                      following step lengths at once; 0: strictly sequential search.  Same accepted step. */
-enum { TSIM_OPT_LS_BATCH = 0, TSIM_N_OPTS };
+ *                      following step lengths at once; 0: strictly sequential search.  Same accepted step.
+ *   TSIM_OPT_MAX_NEWTON 0 (default): the reference's cap on Newton iterations per step, max(20 ndof_r, max_iter)
+ *                      (DH/Simulation.cpp:1155); > 0: a lower cap.  A step that hits the cap is reported as not
+ *                      converged in `status`, like in the reference; in a lock-step batch one such step can cost as
+ *                      much as a whole trajectory, so throughput-bound users may trade exactness on those steps. */
+enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_N_OPTS };
 int tsim_scene_set_option(tsim_scene* scene, int key, int value);
 
 /* Advances B environments by T implicit (BDF1/Newton) steps.

@@ -318,6 +318,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->lanes = TS_MAXN;        // one lane per reduced coordinate
   s->nmj = kt.ib[KI_NMJ];
   s->opts[TSIM_OPT_LS_BATCH] = 1;
+  s->opts[TSIM_OPT_MAX_NEWTON] = 0;
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
   CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd_all));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
@@ -380,6 +381,7 @@ int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* q
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
   a.status = status; a.cmask = contact_masks; a.marker_body = marker_body;
   a.ls_batch = s->opts[TSIM_OPT_LS_BATCH];
+  a.max_newton = s->opts[TSIM_OPT_MAX_NEWTON];
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);

@@ -1277,6 +1277,7 @@ struct StepVars {
   double alpha, gnorm;
   int phase, fail_strike, iters, ls, trial;
   bool converged, batch_ls;
+  int cap_newton;
 };
 
 HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
@@ -1305,7 +1306,8 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   const int n = S.n;
   TileState& ts = WD.state();
   const double* ge = ts.g;
-  const int max_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;
+  const int ref_newton = 20 * n > S.max_iter ? 20 * n : S.max_iter;      // DH/Simulation.cpp:1155
+  const int max_newton = (v.cap_newton > 0 && v.cap_newton < ref_newton) ? v.cap_newton : ref_newton;
   if (v.phase == 3) {
     // G0 = dg/dq0 from this evaluation, G1 = dg/dqdot0 = -h M from mass-matrix columns
     for (int c = 0; c < TS_NC(L); ++c) {
@@ -1918,6 +1920,7 @@ struct FwdArgs {
   unsigned* cmask;                    // [T,B,cmw] or null
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
   int ls_batch;                       // TSIM_OPT_LS_BATCH
+  int max_newton;                     // TSIM_OPT_MAX_NEWTON (0 = the reference's rule)
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
@@ -1959,6 +1962,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   StepVars v;
   v.batch_ls = a.ls_batch != 0;
+  v.cap_newton = a.max_newton;
   int t = 0;                             // warp-uniform
   bool tile_done = !active;
   if (a.T > 0) {

@@ -30,7 +30,7 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   FwdArgs a;
   a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
-  a.status = status; a.cmask = cmask; a.marker_body = marker_body; a.ls_batch = 0;
+  a.status = status; a.cmask = cmask; a.marker_body = marker_body; a.ls_batch = 0; a.max_newton = 0;
   std::vector<Work<Dual> > wb(1);
   HostTile tl;
   for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb[0]);

@@ -195,3 +195,28 @@ def test_dclaw_and_insertion_match_reference(name, lanes):
         assert rel_err(bw["df_du"][:, e].cpu().numpy(), g["df_du"]) <= 1e-6
         assert rel_err(bw["df_dq0"][e].cpu().numpy(), g["df_dq0"]) <= 1e-6
         assert rel_err(bw["df_dqdot0"][e].cpu().numpy(), g["df_dqdot0"]) <= 1e-6
+
+
+def test_newton_cap_option_only_touches_steps_that_hit_it():
+    """TSIM_OPT_MAX_NEWTON lowers the reference's iteration cap (DH/Simulation.cpp:1155).  Environments whose steps
+    all converge below the cap are bit-identical; a step that hits it is flagged not-converged, as in the reference."""
+    from bench import make_inputs
+    g = np.load(os.path.join(GOLDEN, "pusher32x13_episodic_s0.npz"))
+    q0, qd0, u, _ = make_inputs(g["q0"], 4096, 200, 1234)
+    sel = np.r_[2800:2828, 0:28]                     # env 2826 runs into the reference cap of 140 iterations
+    res = []
+    for cap in (0, 25):
+        sim = _sim(g)
+        sim.set_option(1, cap)
+        dev = sim.device
+        o = sim.forward(torch.tensor(q0[sel], device=dev), torch.tensor(qd0[sel], device=dev),
+                        torch.tensor(np.ascontiguousarray(u[:, sel]), device=dev), 200, want_status=True, want_tactile=False)
+        torch.cuda.synchronize()
+        res.append((o["q_traj"].cpu().numpy(), o["status"].cpu().numpy()))
+    (qa, sa), (qb, sb) = res
+    assert int((sa & 255).max()) == 140 and int((sb & 255).max()) == 25
+    easy = (sa & 255).max(axis=0) < 25               # environments that never reach the lower cap
+    assert easy.sum() >= 40 and not easy.all()
+    assert np.array_equal(qa[:, easy], qb[:, easy]) and np.array_equal(sa[:, easy], sb[:, easy])
+    hit = (sb & 255) == 25
+    assert ((sb[hit] >> 16) & 1).all()

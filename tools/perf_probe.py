@@ -21,6 +21,11 @@ def inputs(g, B, T, dev, seed=0):
         u[:, :, 1::3] = 0.6 + 0.4 * u[:, :, 1::3]
         q0[:, :9] += rng.uniform(-0.05, 0.05, (B, 9))
         return (torch.tensor(q0, device=dev), torch.zeros((B, n), dtype=torch.float64, device=dev), torch.tensor(u, device=dev))
+    if n != 7:       # TactileInsertion / StableGrasp: the golden action schedule (cycled), perturbed per environment
+        gu = g["u"]
+        u = np.stack([gu[t % len(gu)] for t in range(T)])[:, None, :].repeat(B, axis=1)
+        u[:, :, :4] += 2e-4 * rng.normal(size=(T, B, 4))
+        return (torch.tensor(q0, device=dev), torch.zeros((B, n), dtype=torch.float64, device=dev), torch.tensor(u, device=dev))
     q0[:, 1] = -0.001
     q0[:, 4] = rng.uniform(-0.02, 0.02, B)
     u = np.zeros((T, B, nu))
@@ -44,6 +49,7 @@ def main():
     ap.add_argument("--zero-u", action="store_true", help="zero actions: the pad never touches the box")
     ap.add_argument("--no-gp", action="store_true", help="timing experiment: drop the pad-box contact force")
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
+    ap.add_argument("--max-newton", type=int, default=0, help="TSIM_OPT_MAX_NEWTON (0 = the reference's cap)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
     for lanes in a.lanes:
@@ -54,6 +60,8 @@ def main():
             continue
         sim = BatchedSim((ib, g["dbuf"]), "cuda:0", lanes=lanes)
         dev = sim.device
+        if a.max_newton:
+            sim.set_option(1, a.max_newton)
         q0, qd0, u = inputs(g, a.B, a.T, dev)
         if a.zero_u:
             u = torch.zeros_like(u)
@@ -69,7 +77,7 @@ def main():
             out = sim.forward(q, qd, u, a.T, grad=True, want_status=True)
             e[2].record()
             dq = torch.ones_like(out["q_traj"])
-            dv = torch.ones_like(out["var"])
+            dv = torch.ones_like(out["var"]) if out["var"] is not None else None
             dt = torch.full_like(out["tactile"], 1e-3)
             bw = sim.backward(out, u, a.T, dq, dv, dt, want_q0=True)
             e[3].record()
