@@ -372,7 +372,7 @@ def run_b200(a):
 
     # ---- CPU baseline beside it: unmodified reference C++ on the host cores, bounded sample
     cpu = None
-    if ref_available() and not a.no_cpu_baseline:
+    if world == 1 and ref_available() and not a.no_cpu_baseline:       # reported at N=1 only (rank 0)
         import multiprocessing as mp
         cores = host_cores()
         with mp.get_context("fork").Pool(cores) as pool:
