@@ -40,7 +40,9 @@ typedef struct tsim_scene tsim_scene;
 /* indices into the array filled by tsim_scene_sizes */
 enum { TSIM_NJ = 0, TSIM_NDOF_R, TSIM_NDOF_M, TSIM_NDOF_U, TSIM_NDOF_VAR, TSIM_NDOF_TACTILE, TSIM_N_MARKERS,
        TSIM_TAPE_DOUBLES /* per env-step: 3*ndof_r^2 + ndof_u */,
-       TSIM_CMASK_WORDS /* 32-bit words of the active contact-point bitmask per env-step */, TSIM_N_SIZES };
+       TSIM_CMASK_WORDS /* 32-bit words of the active contact-point bitmask per env-step */,
+       TSIM_INTEGRATOR /* TSIM_INT_*: options.integrator of the scene, DH/python_interface.cpp:36-44 */, TSIM_N_SIZES };
+enum { TSIM_INT_BDF1 = 0, TSIM_INT_BDF2 = 1 /* first step SDIRK2, DH/Simulation.cpp:1079-1086 */, TSIM_INT_SDIRK2 = 2 };
 
 const char* tsim_last_error(void);
 
@@ -81,6 +83,22 @@ int tsim_forward(const tsim_scene* scene, int32_t B, int32_t T, double* q, doubl
                  int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
                  double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
                  int32_t* marker_body, void* stream);
+
+/* tsim_forward for scenes whose integrator keeps more than one state (options.integrator = "BDF2", the default of
+ * the reference and the integrator of examples/RollingBallExp; DH/Simulation.cpp:1076-1092, 1353-1564): the
+ * reference keeps _q_his inside the Simulation, here the caller owns it.
+ *   q_prev, qd_prev [B,n]  state one step before (q, qd), in/out: read when steps_done > 0, always written
+ *                          (the state before the last step of this call); may be NULL for a whole trajectory
+ *                          simulated by ONE call from reset (steps_done = 0)
+ *   steps_done             steps already taken since reset(): 0 makes the first step of this call the SDIRK2
+ *                          start-up step of BDF2
+ * BDF1 scenes ignore the three arguments; tsim_forward(...) is tsim_forward_multistep(..., NULL, NULL, 0, ...).
+ * The adjoint tape exists for BDF1 only (tape must be NULL otherwise), like Simulation::backward. */
+int tsim_forward_multistep(const tsim_scene* scene, int32_t B, int32_t T, double* q, double* qd, double* q_prev,
+                           double* qd_prev, int32_t steps_done, const double* u, int64_t u_step_stride,
+                           double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row, double* tac_out,
+                           const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
+                           int32_t* marker_body, void* stream);
 
 /* Readouts at a given state (no stepping). Any output may be NULL. */
 int tsim_readout(const tsim_scene* scene, int32_t B, const double* q, const double* qd, double* var_out,

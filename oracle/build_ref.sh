@@ -68,4 +68,6 @@ mkdir -p "$OUT/assets/tactile_pad"
 cp -rf "$REF/assets/tactile_pad"/* "$OUT/assets/tactile_pad/"
 # synthetic 32x13 variant named by BASELINE.json (same scene, denser marker grid)
 sed 's/resolution="13 10"/resolution="32 13"/' "$OUT/assets/pusher/pusher.xml" > "$OUT/assets/pusher/pusher_32x13.xml"
+# rolling-ball scene with a 40x40 marker grid (same dynamics, small golden fixture)
+sed 's/resolution="200 200"/resolution="40 40"/' "$OUT/assets/tactile_pad/tactile_pad.xml" > "$OUT/assets/tactile_pad/tactile_pad_40x40.xml"
 echo "build_ref: assets in $OUT/assets"

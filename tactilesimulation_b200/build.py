@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtactilesim_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-VARIANTS = (8, 16)
-DEPS = ["kernels.cu", "kernels_v8.cu", "kernels_v16.cu", "cabi.cpp", "sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h",
+VARIANTS = (8, 16, 17)
+DEPS = ["kernels.cu", "kernels_v8.cu", "kernels_v16.cu", "kernels_v17.cu", "cabi.cpp", "sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h",
         os.path.join("..", "..", "include", "tactilesim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

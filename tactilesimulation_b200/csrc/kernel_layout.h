@@ -20,7 +20,22 @@
 #ifndef TS_VARIANT
 #define TS_VARIANT 8
 #endif
-#if TS_VARIANT == 16
+#if TS_VARIANT == 17
+// variant 17 = the capacities of variant 16 plus the forward-only features of the rolling-ball scene
+// (BASELINE configs[0]): sphere primitives, free3d-exp joints, BDF2 / SDIRK2 time integration, dense point sets
+#define KT_MAXJ 12
+#define KT_MAXN 16
+#define KT_MAXB 24
+#define KT_MAXU 16
+#define KT_MAXPW 72      // <= 2304 sampled points per general body (20x20x20 cuboid surface grid: 2168)
+#define KT_CYLINDER 1
+#define KT_MAXCAND 16
+#define KT_FREE3D 1
+#define KT_POS_MOTOR 1
+#define KT_SPHERE 1      // sphere SDF primitives (contact force, tactile candidates, ground contact of a sphere)
+#define KT_EXP3D 1       // free3d-exp joints
+#define KT_MULTISTEP 1   // BDF2 / SDIRK2 integrators (no adjoint: the reference has none for them on this path)
+#elif TS_VARIANT == 16
 #define KT_MAXJ 12       // moving joints
 #define KT_MAXN 16       // reduced dofs
 #define KT_MAXB 24       // bodies
@@ -42,9 +57,15 @@
 #define KT_POS_MOTOR 0   // force-controlled motors only
 #endif
 
+#ifndef KT_SPHERE
+#define KT_SPHERE 0
+#define KT_EXP3D 0
+#define KT_MULTISTEP 0
+#endif
+
 enum {
   KI_NMJ = 0, KI_N, KI_NU, KI_NEE, KI_NMARK, KI_NGROUND, KI_NGP, KI_NACT, KI_NSENS, KI_MAX_ITER, KI_MAX_LS,
-  KI_NBODY, KI_NPOINTS, KI_CMW /* words of the per-env-step contact bitmask output */,
+  KI_NBODY, KI_NPOINTS, KI_CMW /* words of the per-env-step contact bitmask output */, KI_INTEGRATOR /* TS_INT_* */,
   KI_O_JOINT = 16, KI_O_BODY, KI_O_GROUND, KI_O_GP, KI_O_ACT, KI_O_EE, KI_O_SENSOR,
   KI_D_JOINT = 24, KI_D_BODY, KI_D_GROUND, KI_D_GP, KI_D_ACT, KI_D_EE, KI_D_SENSOR, KI_D_POINTS, KI_D_MARKERS,
   KI_HEADER = 40
@@ -78,7 +99,8 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 #define KB_INERTIA 12
 #define KB_HALF 18
 #define KB_RBOUND 21
-// ground contact: int {body, point_off, point_cnt, first word in the contact bitmask output}; dbl {kn kt mu damping}
+// ground contact: int {body, point_off, point_cnt (-1: the body is a sphere, one state-dependent contact point),
+// first word in the contact bitmask output}; dbl {kn kt mu damping}
 #define KG_ISTRIDE 4
 #define KG_DSTRIDE 4
 // general-primitive contact: int {body1, body2, point_off, point_cnt, first word in the contact bitmask output,

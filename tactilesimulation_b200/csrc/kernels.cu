@@ -188,6 +188,7 @@ __device__ __forceinline__ void bind_work(WorkSplit& W, const SceneView& S, int 
   W.sv = base;
   W.ts = (TileState*)(base + S.nj * WK_REC);
   W.fr = (Frames*)(base + S.nj * WK_REC + sizeof(TileState) / 8);
+  W.beta = 0.0;
 }
 
 template <int LPE>
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
 #endif
 }
 
+#if !KT_MULTISTEP     // variant 17 is forward-only (no adjoint of BDF2 / SDIRK2, sphere tactile VJP not written)
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, co
   bind_work<LPE>(WD, S, ni, nd, smem);
   env_backward(tl, S, a, env, WD);
 }
+#endif
 
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni, const double* db, int nd, int B,
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni
   if (env >= B) return;
   DevTile<LPE> tl = make_tile<LPE>();
   Work<double> wb;
+  wb.beta = 0.0;
   double ql[TS_MAXN], qdl[TS_MAXN];
   for (int i = 0; i < TS_MAXN; ++i) {
     ql[i] = (i < S.n) ? q[(long long)env * S.n + i] : 0.0;
@@ -333,6 +337,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->sizes[TSIM_N_MARKERS] = ibuf[TS_I_NMARKERS];
   s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n + ibuf[TS_I_NDOF_U];
   s->sizes[TSIM_CMASK_WORDS] = kt.ib[KI_CMW];
+  s->sizes[TSIM_INTEGRATOR] = kt.ib[KI_INTEGRATOR];
   *out = s;
   return 0;
 }
@@ -370,10 +375,15 @@ int tsim_scene_set_option(tsim_scene* s, int key, int value) {
 int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, const double* u,
                  int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
                  double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
-                 int32_t* marker_body, void* stream) {
+                 int32_t* marker_body, double* q_prev, double* qd_prev, int32_t steps_done, void* stream) {
   if (!s) return fail("tsim_forward: null scene");
   if (B <= 0 || T < 0) return fail("tsim_forward: bad batch or step count");
   if (!q || !qd || !u) return fail("tsim_forward: q, qd and u are required");
+  if (s->sizes[TSIM_INTEGRATOR] != TSIM_INT_BDF1 && tape)
+    return fail("tsim_forward: the adjoint tape exists for BDF1 scenes only (as Simulation::backward of the reference)");
+  if (steps_done < 0 || (steps_done > 0 && s->sizes[TSIM_INTEGRATOR] == TSIM_INT_BDF2 && (!q_prev || !qd_prev)))
+    return fail("tsim_forward_multistep: continuing a BDF2 trajectory needs q_prev and qd_prev");
+  if ((q_prev == 0) != (qd_prev == 0)) return fail("tsim_forward_multistep: q_prev and qd_prev go together");
   if (T == 0) return 0;
   CK(cudaSetDevice(s->device));
   FwdArgs a;
@@ -382,6 +392,7 @@ int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* q
   a.status = status; a.cmask = contact_masks; a.marker_body = marker_body;
   a.ls_batch = s->opts[TSIM_OPT_LS_BATCH];
   a.max_newton = s->opts[TSIM_OPT_MAX_NEWTON];
+  a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
@@ -421,6 +432,9 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
                   const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0,
                   void* stream) {
   if (!s) return fail("tsim_backward: null scene");
+#if KT_MULTISTEP
+  return fail("tsim_backward: scenes with sphere primitives, free3d-exp joints or BDF2 / SDIRK2 integration are forward-only");
+#else
   if (B <= 0 || T <= 0) return fail("tsim_backward: bad batch or step count");
   if (!q_traj || !qd_traj || !u || !tape || !carry)
     return fail("tsim_backward: q_traj, qd_traj, u, tape and carry are required (run tsim_forward with a tape first)");
@@ -441,6 +455,7 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
   return 0;
+#endif
 }
 
 }  // extern "C"

@@ -15,9 +15,15 @@
 #define TS_JT_PLANAR 3
 #define TS_JT_TRANSLATIONAL 4
 #define TS_JT_FREE3D_EULER 5    // q = (p, r): translation + XYZ Euler angles (DH/Joint/JointFree3DEuler.cpp)
+#define TS_JT_FREE3D_EXP 6      // q = (p, r): translation + exponential coordinates (DH/Joint/JointFree3DExp.cpp)
 #define TS_SH_NONE 0
 #define TS_SH_CUBOID 1
 #define TS_SH_CYLINDER 2
+#define TS_SH_SPHERE 3
+// time integrators (DH/Simulation.cpp:1076-1092); header slot TS_I_INTEGRATOR, 0 in blobs written before it existed
+#define TS_INT_BDF1 0
+#define TS_INT_BDF2 1           // first step SDIRK2, then BDF2
+#define TS_INT_SDIRK2 2
 #define TS_ACT_FORCE 0
 #define TS_ACT_POS 1
 
@@ -27,7 +33,7 @@
 enum {
   TS_I_MAGIC = 0, TS_I_VERSION, TS_I_NJ, TS_I_NDOF_R, TS_I_NDOF_U, TS_I_NEE, TS_I_NMARKERS,
   TS_I_NGROUND, TS_I_NGP, TS_I_NACT, TS_I_NSENSORS, TS_I_MAX_ITER, TS_I_MAX_LS, TS_I_NPOINTS,
-  TS_I_RES0, TS_I_RES1,
+  TS_I_INTEGRATOR, TS_I_RES1,
   // offsets (in elements) of the int sections
   TS_I_OFF_JOINT = 16, TS_I_OFF_GROUND, TS_I_OFF_GP, TS_I_OFF_ACT, TS_I_OFF_EE, TS_I_OFF_SENSOR,
   // offset (doubles) of the optional per-marker (axis0, axis1, normal) section, 9 doubles per marker; 0 = the

@@ -51,6 +51,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   const int nj = ib[TS_I_NJ], n = ib[TS_I_NDOF_R], nu = ib[TS_I_NDOF_U], nee = ib[TS_I_NEE], nmark = ib[TS_I_NMARKERS];
   const int nground = ib[TS_I_NGROUND], ngp = ib[TS_I_NGP], nact = ib[TS_I_NACT], nsens = ib[TS_I_NSENSORS];
   const int npoints = ib[TS_I_NPOINTS];
+  const int integrator = ib[TS_I_INTEGRATOR];
+  if (integrator < TS_INT_BDF1 || integrator > TS_INT_SDIRK2) return "unknown integrator";
+  if (integrator != TS_INT_BDF1 && !KT_MULTISTEP) return "scene exceeds the compiled capacity (BDF2 / SDIRK2 integrators)";
   if (nj > KT_MAXB) return "scene exceeds the compiled capacity (bodies)";
   if (n > KT_MAXN || nu > KT_MAXU) return "scene exceeds the compiled capacities (dofs/controls)";
   const int* J = ib + ib[TS_I_OFF_JOINT];
@@ -63,7 +66,8 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int jt = J[j * TS_JI_STRIDE], par = J[j * TS_JI_STRIDE + 1];
     if (par >= j) return "joints are not in parent-first order";
     if (jt == TS_JT_FREE3D_EULER && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler joints)";
-    if (jt < TS_JT_FIXED || jt > TS_JT_FREE3D_EULER) return "unknown joint type";
+    if (jt == TS_JT_FREE3D_EXP && !KT_EXP3D) return "scene exceeds the compiled capacity (free3d-exp joints)";
+    if (jt < TS_JT_FIXED || jt > TS_JT_FREE3D_EXP) return "unknown joint type";
     const Xf e0 = xf_load(JD + j * TS_JD_STRIDE + TS_JD_RPJ, JD + j * TS_JD_STRIDE + TS_JD_PPJ);
     const Xf up = (par < 0) ? e0 : xf_mul(erel[par], e0);
     if (jt == TS_JT_FIXED) {
@@ -88,6 +92,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   oi[KI_NMJ] = nmj; oi[KI_N] = n; oi[KI_NU] = nu; oi[KI_NEE] = nee; oi[KI_NMARK] = nmark; oi[KI_NGROUND] = nground;
   oi[KI_NGP] = ngp; oi[KI_NACT] = nact; oi[KI_NSENS] = nsens; oi[KI_MAX_ITER] = ib[TS_I_MAX_ITER];
   oi[KI_MAX_LS] = ib[TS_I_MAX_LS]; oi[KI_NBODY] = nj; oi[KI_NPOINTS] = npoints;
+  oi[KI_INTEGRATOR] = integrator;
 
   // ---- composite spatial inertia per moving joint: sum over the attached bodies of X^T diag(I_i) X,
   //      X = twist transform joint frame -> body frame (DH/Robot.cpp:652-658 gathers diag(I_i) per body)
@@ -165,6 +170,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
       d[KB_HALF] = s[TS_JD_HALF];
       d[KB_HALF + 1] = s[TS_JD_HALF + 1] / 2.;
       d[KB_RBOUND] = sqrt(d[KB_HALF] * d[KB_HALF] + d[KB_HALF + 1] * d[KB_HALF + 1]);
+    } else if (J[j * TS_JI_STRIDE + 4] == TS_SH_SPHERE) {  // blob: (radius, -, -)
+      d[KB_HALF] = s[TS_JD_HALF];
+      d[KB_RBOUND] = s[TS_JD_HALF];
     } else {
       for (int i = 0; i < 3; ++i) d[KB_HALF + i] = s[TS_JD_HALF + i];
       d[KB_RBOUND] = norm3(s + TS_JD_HALF);
@@ -180,8 +188,11 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int g = 0; g < nground; ++g) {
     const int* r = ib + ib[TS_I_OFF_GROUND] + g * TS_GI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GROUND] + g * TS_CD_STRIDE;
-    int rec[KG_ISTRIDE] = {r[0], r[1], r[2], cmw};
-    cmw += (r[2] + 31) / 32;
+    // a sphere touches the ground at ONE state-dependent point (DH/CollisionDetection/CollisionDetection.cpp:17-25)
+    const bool sph = J[r[0] * TS_JI_STRIDE + 4] == TS_SH_SPHERE;
+    if (sph && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
+    int rec[KG_ISTRIDE] = {r[0], r[1], sph ? -1 : r[2], cmw};
+    cmw += sph ? 1 : (r[2] + 31) / 32;
     oi.insert(oi.end(), rec, rec + KG_ISTRIDE);
     od.insert(od.end(), c, c + KG_DSTRIDE);
   }
@@ -191,9 +202,10 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GP] + f * TS_CD_STRIDE;
     const int shape2 = J[r[1] * TS_JI_STRIDE + 4];
-    if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER)
-      return "general-primitive contact: only cuboid and cylinder primitives are supported";
+    if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER && shape2 != TS_SH_SPHERE)
+      return "general-primitive contact: only cuboid, cylinder and sphere primitives are supported";
     if (shape2 == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
+    if (shape2 == TS_SH_SPHERE && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
     if (r[3] > 32 * KT_MAXPW) return "scene exceeds the compiled capacity (sampled points per general body)";
     int rec[KP_ISTRIDE] = {r[0], r[1], r[2], r[3], cmw, shape2};
     cmw += (r[3] + 31) / 32;
@@ -240,8 +252,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     if (r[3] > KT_MAXCAND) return "scene exceeds the compiled capacity (tactile candidate bodies)";
     for (int k = 0; k < r[3]; ++k) {
       const int sh = J[r[4 + k] * TS_JI_STRIDE + 4];
-      if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER) return "tactile candidates must be cuboids or cylinders";
+      if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER && sh != TS_SH_SPHERE) return "tactile candidates must be cuboids, cylinders or spheres";
       if (sh == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
+      if (sh == TS_SH_SPHERE && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
     }
     int rec[KS_ISTRIDE] = {r[0], r[1], r[2], r[3]};
     for (int k = 0; k < r[3]; ++k) rec[4 + k] = r[4 + k];

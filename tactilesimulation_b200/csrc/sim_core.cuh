@@ -58,6 +58,24 @@
 #define TS_TOC2(tl, slot)
 #endif
 
+// Output streams (tactile field, tape, trajectory) are written once and never re-read by the forward kernel:
+// evict-first stores keep them from displacing the per-lane tangent work space (local memory) in L2, whose
+// write-back was the bulk of the DRAM traffic above the algorithmic bytes (profiles/r01_traffic.json).
+HD void st_stream(double* p, double v) {
+#ifdef __CUDA_ARCH__
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+HD void st_stream(int* p, int v) {
+#ifdef __CUDA_ARCH__
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 #define TS_MAXJ KT_MAXJ
 #define TS_MAXN KT_MAXN
 #define TS_MAXU KT_MAXU
@@ -173,7 +191,57 @@ struct TileState {
   double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN];    // inputs (q1, qd1, dl) of the evaluation in flight
   double g[TS_MAXN];                               // residual of the last evaluation
   double hs[TS_MAXN * TS_MAXN];                    // transposition scratch of the cooperative LU
+#if KT_MULTISTEP
+  double pq[TS_MAXN], pqd[TS_MAXN];                // second state of the two-state formulas: BDF2 (q, qd) one step back,
+                                                   // SDIRK2 second stage (q_alpha, qd_alpha)
+#endif
 };
+
+// ---- implicit stages (DH/Simulation.cpp:1076-1092, 1227-1235, 1353-1364, 1425-1450, 1466-1475, 1536-1548).
+// Every stage solves g(x) = M(x) dl(x) - beta f(x, qd(x)) = 0 with affine qd(x), dl(x):
+//   TS_ST_BDF1    qd = (x - q0) / h                        dl = x - q0 - h qd0                               beta = h^2
+//   TS_ST_SDIRK_A the same with h := alpha h, alpha = (2 - sqrt 2) / 2  (first stage of SDIRK2 -> q_alpha, qd_alpha)
+//   TS_ST_SDIRK_B qd = (x + (1/alpha - 2) q0 - (1 - alpha)/alpha q_alpha) / (alpha h)
+//                 dl = x - q0 - (2 alpha - 1) h qd0 - 2 (1 - alpha) h qd_alpha                            beta = alpha^2 h^2
+//   TS_ST_BDF2    qd = 3/(2h) (x - 4/3 q1 + 1/3 q0)        dl = x - 4/3 q1 + 1/3 q0 - 8/9 h qd1 + 2/9 h qd0   beta = 4/9 h^2
+// (q, qd) of the tile state is the state at the start of the step (q1 of BDF2), (pq, pqd) the second state.
+enum { TS_ST_BDF1 = 0, TS_ST_SDIRK_A = 1, TS_ST_SDIRK_B = 2, TS_ST_BDF2 = 3 };
+#define TS_SDIRK_ALPHA ((2. - sqrt(2.)) / 2.)
+
+// d qd / d x of the stage and its force scale
+HD void stage_coef(const SceneView& S, int mode, double& tv, double& beta) {
+  const double h = S.h;
+  if (KT_MULTISTEP && mode == TS_ST_SDIRK_A) { const double ha = TS_SDIRK_ALPHA * h; tv = 1.0 / ha; beta = ha * ha; }
+  else if (KT_MULTISTEP && mode == TS_ST_SDIRK_B) { const double al = TS_SDIRK_ALPHA; tv = 1.0 / (al * h); beta = al * al * h * h; }
+  else if (KT_MULTISTEP && mode == TS_ST_BDF2) { tv = 3. / (2. * h); beta = 4. / 9. * h * h; }
+  else { tv = (1.0 - 0.0) / h; beta = h * h; }
+}
+
+// (qd, dl) of coordinate i at the stage point xi
+HD void stage_inputs(const SceneView& S, const TileState& ts, int mode, int i, double xi, double& xv, double& xl) {
+  const double h = S.h, qi = ts.q[i], vi = ts.qd[i];
+#if KT_MULTISTEP
+  if (mode == TS_ST_SDIRK_A) {
+    const double ha = TS_SDIRK_ALPHA * h;
+    xv = (xi - qi) / ha;
+    xl = xi - qi - ha * vi;
+    return;
+  }
+  if (mode == TS_ST_SDIRK_B) {
+    const double al = TS_SDIRK_ALPHA;
+    xv = (xi + (1. / al - 2.) * qi - (1. - al) / al * ts.pq[i]) / (al * h);
+    xl = xi - qi - (2. * al - 1.) * h * vi - 2. * (1. - al) * h * ts.pqd[i];
+    return;
+  }
+  if (mode == TS_ST_BDF2) {
+    xv = 3. / (2. * h) * (xi - 4. / 3. * qi + 1. / 3. * ts.pq[i]);
+    xl = xi - 4. / 3. * qi + 1. / 3. * ts.pq[i] - 8. / 9. * h * vi + 2. / 9. * h * ts.pqd[i];
+    return;
+  }
+#endif
+  xv = (xi - qi) / h;
+  xl = xi - qi - h * vi;
+}
 
 // inputs (q, qd, dl) of one evaluation: plain arrays ...
 template <class T> struct ArrIn {
@@ -200,6 +268,7 @@ struct SeedIn {
 
 template <class T> struct WorkRec {          // the joint records alone (value-only line-search trials)
   typedef T Scalar;
+  double beta;                               // force scale of the residual in flight (h^2 for BDF1), set by eval_g
   T rec[TS_MAXJ][WK_REC];
   HD T get(int j, int o) const { return rec[j][o]; }
   HD double getv(int j, int o) const { return val(rec[j][o]); }
@@ -220,6 +289,7 @@ struct WorkSplit {
   TileState* ts;                   // per tile, shared memory
   HD TileState& state() { return *ts; }
   HD double* scratch() { return ts->hs; }
+  double beta;                     // force scale of the residual in flight (h^2 for BDF1), set by eval_g
   double dt[TS_MAXJ][WK_REC];      // tangents of this lane
   HD Dual get(int j, int o) const { return mkdual(sv[j * WK_REC + o], dt[j][o]); }
   HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
@@ -236,13 +306,72 @@ template <class WK, class T> HD void wk_st(WK& W, int j, int o, int n, const T* 
   for (int i = 0; i < n; ++i) W.put(j, o + i, in[i]);
 }
 
+// ------------------------------------------------------------------ exponential coordinates (free3d-exp joints)
+// Coefficient functions of t = |r|^2:  A = sin(th)/th,  B = (1 - cos th)/th^2,  C = (th - sin th)/th^3  and dB/dt,
+// dC/dt.  R(r) = 1 + A [r] + B [r]^2 is math::exp of the reference (DH/Utils.h:82-98); the left Jacobian
+// JL(r) = 1 + B [r] + C [r]^2 has the columns unskew(dR/dr_j R^T) that DH/Joint/JointSphericalExp.cpp:98-108
+// writes as (r_j [r] + [[r](1 - R) e_j]) / |r|^2.  Power series below t = 1e-4: no 0/0 at r = 0 (where the ball of
+// the rolling-ball scene starts) and differentiable there by the same dual-number code.
+template <class T>
+HD void so3_coefs(T t, T& A, T& B, T& C, T& dB, T& dC) {
+  if (val(t) < 1e-4) {
+    A = 1.0 + t * (-1.0 / 6.0 + t * (1.0 / 120.0 + t * (-1.0 / 5040.0 + t * (1.0 / 362880.0))));
+    B = 0.5 + t * (-1.0 / 24.0 + t * (1.0 / 720.0 + t * (-1.0 / 40320.0)));
+    C = 1.0 / 6.0 + t * (-1.0 / 120.0 + t * (1.0 / 5040.0 + t * (-1.0 / 362880.0)));
+    dB = -1.0 / 24.0 + t * (1.0 / 360.0 + t * (-1.0 / 13440.0));
+    dC = -1.0 / 120.0 + t * (1.0 / 2520.0 + t * (-1.0 / 120960.0));
+  } else {
+    T th = dsqrt(t), sn, cs;
+    dsincos(th, sn, cs);
+    A = sn / th;
+    B = (1.0 - cs) / t;
+    C = (th - sn) / (t * th);
+    dB = (A - 2.0 * B) / (2.0 * t);
+    dC = (B - 3.0 * C) / (2.0 * t);
+  }
+}
+// R = 1 + A [r] + B (r r^T - t 1), row-major
+template <class T>
+HD void so3_exp(const T* r, T A, T B, T t, T* R) {
+  R[0] = 1.0 + B * (r[0] * r[0] - t); R[1] = B * (r[0] * r[1]) - A * r[2]; R[2] = B * (r[0] * r[2]) + A * r[1];
+  R[3] = B * (r[1] * r[0]) + A * r[2]; R[4] = 1.0 + B * (r[1] * r[1] - t); R[5] = B * (r[1] * r[2]) - A * r[0];
+  R[6] = B * (r[2] * r[0]) - A * r[1]; R[7] = B * (r[2] * r[1]) + A * r[0]; R[8] = 1.0 + B * (r[2] * r[2] - t);
+}
+// o = (1 + sB [r] + C [r]^2) v :  sB = +B left Jacobian (angular velocity in the pre-motion frame per unit rdot),
+// sB = -B right Jacobian (the same in the child frame: the S_j of DH/Joint/JointSphericalExp.cpp:172-175)
+template <class T, class V>
+HD void so3_jac_mul(const T* r, T sB, T C, const V* v, T* o) {
+  T c1[3], c2[3];
+  cross3(r, v, c1);
+  cross3(r, c1, c2);
+  for (int i = 0; i < 3; ++i) o[i] = v[i] + sB * c1[i] + C * c2[i];
+}
+// World axes of the six coordinates of a free3d-exp joint whose child frame is (R0, .): translations along
+// Ra e_i = R0 (row i of R(r)), rotations about R0 JR(r) e_i.
+template <class T>
+HD void exp_world_axes(const T* R0, T r1, T r2, T r3, T (*tax)[3], T (*rax)[3]) {
+  T r[3] = {r1, r2, r3};
+  T t = r1 * r1 + r2 * r2 + r3 * r3, A, B, C, dB, dC;
+  so3_coefs(t, A, B, C, dB, dC);
+  T Rq[9];
+  so3_exp(r, A, B, t, Rq);
+  for (int i = 0; i < 3; ++i) {
+    T row[3] = {Rq[3 * i], Rq[3 * i + 1], Rq[3 * i + 2]};
+    mv3(R0, row, tax[i]);
+    double ei[3] = {i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0};
+    T jc[3];
+    so3_jac_mul(r, -B, C, ei, jc);
+    mv3(R0, jc, rax[i]);
+  }
+}
+
 // Outward sweep over the moving joints.  dyn=false computes poses and twists only.
 // Joint models: DH/Joint/JointRevolute.cpp:38-69, JointPrismatic.cpp:22-45, JointPlanar.cpp:7-33,
 // JointTranslational.cpp:9-40; recursion DH/Joint/Joint.cpp:119-165.
 template <class WK, class In>
 HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
   typedef typename WK::Scalar T;
-  const double h2 = S.h * S.h;
+  const double h2 = W.beta;             // only read when dyn
   for (int j = 0; j < S.nj; ++j) {
     const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
@@ -341,6 +470,55 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         wa[1] = g2[1] * r2 + g3[1] * r3;
         wa[2] = g2[2] * r2 + g3[2] * r3;
         for (int i = 0; i < 3; ++i) pd[i] = in.qd(qo + i);
+        cross3(pd, wa, c0);
+        cross3(pq, wd, c1v);
+        for (int i = 0; i < 3; ++i) vd[i] = c0[i] + c1v[i];
+        T w[3], v[3], pw[3];
+        mv3(Ra, wd, w);
+        mv3(Ra, vd, v);
+        cross3(pa, w, pw);
+        for (int i = 0; i < 3; ++i) { sl[i] = sl[i] + h2 * w[i]; sl[3 + i] = sl[3 + i] + h2 * (v[i] + pw[i]); }
+      }
+    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
+      // q = (p, r): Q = [exp([r]) p; 0 1]   (DH/Joint/JointFree3DExp.cpp:13-103, JointSphericalExp.cpp:22-245).
+      // Same structure as the Euler chart above with G replaced by the left Jacobian JL(r) of SO(3):
+      // xi = (JL rdot, pdot + p x JL rdot),  xi_dot = (JLdot rdot, pdot x JL rdot + p x JLdot rdot) with
+      // JLdot rdot = Bdot (r x rdot) + Cdot r x (r x rdot) + C rdot x (r x rdot)   (B [rdot] rdot = 0).
+      T rr[3], pq[3];
+      for (int i = 0; i < 3; ++i) { pq[i] = in.q(qo + i); rr[i] = in.q(qo + 3 + i); }
+      T t2 = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2], cA, cB, cC, dB, dC;
+      so3_coefs(t2, cA, cB, cC, dB, dC);
+      T Rq[9], t[3];
+      so3_exp(rr, cA, cB, t2, Rq);
+      mm3(Ra, Rq, R0);
+      mv3(Ra, pq, t);
+      for (int i = 0; i < 3; ++i) p0[i] = pa[i] + t[i];
+      for (int pass = 0; pass < (dyn ? 2 : 1); ++pass) {
+        T rd[3], pd[3];
+        for (int i = 0; i < 3; ++i) {
+          pd[i] = pass ? in.dl(qo + i) : in.qd(qo + i);
+          rd[i] = pass ? in.dl(qo + 3 + i) : in.qd(qo + 3 + i);
+        }
+        T wa[3], va[3], c[3];
+        so3_jac_mul(rr, cB, cC, rd, wa);
+        cross3(pq, wa, c);
+        for (int i = 0; i < 3; ++i) va[i] = pd[i] + c[i];
+        T* so = pass ? sl : sq;
+        T w[3], v[3], pw[3];
+        mv3(Ra, wa, w);
+        mv3(Ra, va, v);
+        cross3(pa, w, pw);
+        for (int i = 0; i < 3; ++i) { so[i] = w[i]; so[3 + i] = v[i] + pw[i]; }
+      }
+      if (dyn) {
+        T rd[3], pd[3], wa[3], wd[3], c1[3], c2[3], c3[3], vd[3], c0[3], c1v[3];
+        for (int i = 0; i < 3; ++i) { pd[i] = in.qd(qo + i); rd[i] = in.qd(qo + 3 + i); }
+        so3_jac_mul(rr, cB, cC, rd, wa);
+        T rdr = 2.0 * (rr[0] * rd[0] + rr[1] * rd[1] + rr[2] * rd[2]);     // d|r|^2/dt
+        cross3(rr, rd, c1);
+        cross3(rr, c1, c2);
+        cross3(rd, c1, c3);
+        for (int i = 0; i < 3; ++i) wd[i] = (dB * rdr) * c1[i] + (dC * rdr) * c2[i] + cC * c3[i];
         cross3(pd, wa, c0);
         cross3(pq, wd, c1v);
         for (int i = 0; i < 3; ++i) vd[i] = c0[i] + c1v[i];
@@ -549,7 +727,7 @@ template <class T> HD void vals9(const T* a, double* o) { for (int i = 0; i < 9;
 template <class WK>
 HDN void ground_contacts(const SceneView& S, WK& W) {
   typedef typename WK::Scalar T;
-  const double h2 = S.h * S.h;
+  const double h2 = W.beta;
   for (int gi = 0; gi < S.nground; ++gi) {
     const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
     const double* c = S.db + S.d_ground + gi * KG_DSTRIDE;
@@ -565,12 +743,26 @@ HDN void ground_contacts(const SceneView& S, WK& W) {
     T wr[6];
     for (int i = 0; i < 6; ++i) wr[i] = 0.0;
     bool any = false;
-    for (int k = 0; k < pc; ++k) {
-      const double* xi = S.db + S.d_points + 3 * (po + k);
+    // a sphere has ONE contact point, found from the values of its pose and then held fixed in the body frame
+    // while the force is differentiated (DH/CollisionDetection/CollisionDetection.cpp:17-25)
+    double xs[3] = {0.0, 0.0, 0.0};
+    const bool sph = KT_SPHERE && pc < 0;
+    if (sph) {
+      const double rad = S.db[S.d_body + b * KB_DSTRIDE + KB_HALF];
+      const double dc = (S.gn[0] * (pv[0] - S.gx[0]) + S.gn[1] * (pv[1] - S.gx[1]) + S.gn[2] * (pv[2] - S.gx[2])) - rad;
+      if (!(dc <= 0.0)) continue;
+      double xw[3], tp[3];
+      for (int i = 0; i < 3; ++i) xw[i] = pv[i] - S.gn[i] * rad;
+      mtv3(Rv, xw, xs);                     // xi = E_i0 xw = R^T xw + (-(R^T p))
+      mtv3(Rv, pv, tp);
+      for (int i = 0; i < 3; ++i) xs[i] = xs[i] + (-tp[i]);
+    }
+    for (int k = 0; k < (sph ? 1 : pc); ++k) {
+      const double* xi = sph ? xs : S.db + S.d_points + 3 * (po + k);
       double xv[3];
       mv3(Rv, xi, xv);
       const double dv = (xv[0] + pv[0] - S.gx[0]) * S.gn[0] + (xv[1] + pv[1] - S.gx[1]) * S.gn[1] + (xv[2] + pv[2] - S.gx[2]) * S.gn[2];
-      if (!(dv <= 0.0)) continue;
+      if (!sph && !(dv <= 0.0)) continue;
       any = true;
       T xw[3];
       mv3(R, xi, xw);
@@ -690,12 +882,19 @@ HD bool cylinder_inside_world(const double* R2, const double* p2, const double* 
   return sqrt(x[0] * x[0] + x[1] * x[1]) - rh[0] < 0.0;
 }
 
+// sphere SDF (DH/Body/BodySphere.cpp:79-83): distance(xw) = |xw - p2| - radius < 0
+HD bool sphere_inside_world(const double* p2, const double* xw, double radius) {
+  const double a = xw[0] - p2[0], b = xw[1] - p2[1], c = xw[2] - p2[2];
+  return sqrt(a * a + b * b + c * c) - radius < 0.0;
+}
+
 // Penalty force of ONE active sampled point against a CYLINDER (DH/Force/ForceGeneralPrimitiveContact.cpp:154-229
 // with DH/Body/BodyCylinder.cpp:105-139): same structure as gp_point_force, the normal e = x_r / |x_r| now
 // depends on the point.  Wrenches in cylinder coordinates about the cylinder origin.
+// sph: SPHERE (DH/Body/BodySphere.cpp:79-107): the same with the 3-d radial normal e = x / |x|.
 template <class T>
 HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* rh, double kn, double kt, double mu,
-                           double damp, T* w1, T* w2) {
+                           double damp, T* w1, T* w2, bool sph = false) {
   T ap[3], x[3];
   mv3(P.Q, xi1, ap);
   for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
@@ -703,9 +902,10 @@ HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* 
   cross3(P.w1b, ap, u);
   cross3(P.ph2, x, t3);
   for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
-  T r = dsqrt(x[0] * x[0] + x[1] * x[1]);
+  T r = (KT_SPHERE && sph) ? dsqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) : dsqrt(x[0] * x[0] + x[1] * x[1]);
   T e[3];
   e[0] = x[0] / r; e[1] = x[1] / r; e[2] = 0.0;
+  if (KT_SPHERE && sph) e[2] = x[2] / r;
   T d = r - rh[0];
   T ddot = dot3(e, u);
   T tb[3];
@@ -751,12 +951,13 @@ template <class Tile, class WK>
 HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
   typedef typename WK::Scalar T;
   const int L = Tile::LPE;
-  const double h2 = S.h * S.h;
+  const double h2 = W.beta;
   for (int fi = 0; fi < S.ngp; ++fi) {
     const int* r = S.ib + S.o_gp + fi * KP_ISTRIDE;
     const double* c = S.db + S.d_gp + fi * KP_DSTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
-    const bool cyl = KT_CYLINDER && r[5] == TS_SH_CYLINDER;
+    const bool sph = KT_SPHERE && r[5] == TS_SH_SPHERE;
+    const bool cyl = (KT_CYLINDER && r[5] == TS_SH_CYLINDER) || sph;      // point-dependent normal
     const int j1 = S.ib[S.o_body + b1 * KB_ISTRIDE], j2 = S.ib[S.o_body + b2 * KB_ISTRIDE];
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
@@ -789,7 +990,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
               double xwv[3];
               mv3(P.R1v, xi1, xwv);
               for (int i = 0; i < 3; ++i) xwv[i] = xwv[i] + P.p1v[i];
-              in = cylinder_inside_world(P.R2v, P.p2v, xwv, hs);
+              in = sph ? sphere_inside_world(P.p2v, xwv, hs[0]) : cylinder_inside_world(P.R2v, P.p2v, xwv, hs);
             } else {
               const int cls = cuboid_classify(R21, r21, xi1, hs);
               if (cls > 0) in = true;
@@ -830,7 +1031,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
       while (m) {
         const int k = 32 * wd + ts_ffs(m);
         m &= m - 1;
-        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
+        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2, sph);
         else gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
       }
     }
@@ -879,7 +1080,7 @@ HD double motor_force(double u, double cmin, double cmax) {
 template <class WK, class In>
 HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typename WK::Scalar* g) {
   typedef typename WK::Scalar T;
-  const double h2 = S.h * S.h;
+  const double h2 = W.beta;
   for (int j = S.nj - 1; j >= 0; --j) {
     const int* ji = S.ib + S.o_joint + j * KJ_ISTRIDE;
     const double* jd = S.db + S.d_joint + j * KJ_DSTRIDE;
@@ -904,6 +1105,12 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       T tax[3][3], rax[3][3], pf[3], t[3];
       euler_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
+      cross3(p0, A + 3, pf);             // moment about the joint origin
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      for (int i = 0; i < 3; ++i) { g[qo + i] = dot3(tax[i], A + 3); g[qo + 3 + i] = dot3(rax[i], t); }
+    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
+      T tax[3][3], rax[3][3], pf[3], t[3];
+      exp_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
       cross3(p0, A + 3, pf);             // moment about the joint origin
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
       for (int i = 0; i < 3; ++i) { g[qo + i] = dot3(tax[i], A + 3); g[qo + 3 + i] = dot3(rax[i], t); }
@@ -932,9 +1139,12 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
   }
 }
 
-// residual of the BDF1 step for q1, given qd1 = (q1 - q0) / h and dl = q1 - q0 - h qd0
+// residual g = M(q) dl - beta f(q, qd) of one implicit stage.  BDF1: qd = (q - q0) / h, dl = q - q0 - h qd0,
+// beta = h^2 (DH/Simulation.cpp:1227-1235); the other integrators only change (qd, dl, beta): stage_inputs().
 template <class Tile, class WK, class In>
-HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g) {
+HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g,
+                double beta) {
+  W.beta = beta;
   { TS_TIC(tl); kinematics(S, in, W, true); TS_TOC(tl, 0); }
   { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
   { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
@@ -1133,7 +1343,7 @@ HD double norm_n(const double* v, int n) {
 // ts.g and returns the owned columns of dg/d(seed).  seed: 0 = q1, 1 = q0, 2 = qd0.  The step state
 // machine calls it from exactly ONE place, so the residual code exists once per kernel.
 template <class Tile, class WK>
-HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const double* x, int seed, WK& W,
+HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const double* x, int seed, int mode, WK& W,
                      double (*col)[TS_MAXN]) {
   const int L = Tile::LPE;
   const int n = S.n;
@@ -1141,7 +1351,9 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
   in.xq = ts.xq; in.xv = ts.xv; in.xl = ts.xl;
   // tangents of (q1, qd1, dl) per unit of the seeded variable:  q1: (1, 1/h, 1)   q0: (0, -1/h, -1)   qd0: (0, 0, -h)
   in.tq = (seed == 0) ? 1.0 : 0.0;
-  in.tv = (seed == 0) ? (1.0 - 0.0) / S.h : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
+  double stv, sbeta;
+  stage_coef(S, mode, stv, sbeta);
+  in.tv = (seed == 0) ? stv : ((seed == 1) ? (0.0 - 1.0) / S.h : 0.0);
   in.tl = (seed == 0) ? 1.0 : ((seed == 1) ? -1.0 : -S.h);
   in.q0v = ts.q; in.qd0v = ts.qd;
   in.tq0 = (seed == 1) ? 1.0 : 0.0;
@@ -1149,15 +1361,17 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
   tl.tile_sync();          // every lane of the tile is done with the previous evaluation and its bookkeeping
 #pragma unroll
   for (int i = 0; i < TS_MAXN; ++i) {
-    const double xi = (i < n) ? x[i] : 0.0, qi = (i < n) ? ts.q[i] : 0.0, vi = (i < n) ? ts.qd[i] : 0.0;
+    const double xi = (i < n) ? x[i] : 0.0;
+    double xv = 0.0, xl = 0.0;
+    if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
     ts.xq[i] = xi;
-    ts.xv[i] = (xi - qi) / S.h;
-    ts.xl[i] = xi - qi - S.h * vi;
+    ts.xv[i] = xv;
+    ts.xl[i] = xl;
   }
   for (int c = 0; c < TS_NC(L); ++c) {
     in.k = tl.lane + c * L;
     Dual gD[TS_MAXN];
-    eval_g(tl, S, in, ts.u, W, gD);
+    eval_g(tl, S, in, ts.u, W, gD, sbeta);
 #pragma unroll
     for (int i = 0; i < TS_MAXN; ++i) {
       ts.g[i] = (i < n) ? gD[i].v : 0.0;
@@ -1192,6 +1406,14 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
     else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
       double tax[3][3], rax[3][3];
       euler_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
+      if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
+      else {
+        for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - 3][i];
+        cross3(p0, Sk, Sk + 3);
+      }
+    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
+      double tax[3][3], rax[3][3];
+      exp_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
       if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
       else {
         for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - 3][i];
@@ -1241,6 +1463,12 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
       cross3(p0, A + 3, pf);
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
       for (int i = 0; i < 3; ++i) { Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[qo + 3 + i] = dot3(rax[i], t); }
+    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
+      double tax[3][3], rax[3][3], pf[3], t[3];
+      exp_world_axes(R0, qv[qo + 3], qv[qo + 4], qv[qo + 5], tax, rax);
+      cross3(p0, A + 3, pf);
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      for (int i = 0; i < 3; ++i) { Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[qo + 3 + i] = dot3(rax[i], t); }
     }
     if (par >= 0) for (int i = 0; i < 6; ++i) Wm[par][i] += A[i];
   }
@@ -1249,21 +1477,24 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
 // ||g(x + alpha dx)|| by a value-only evaluation that this lane runs ALONE (one-lane tile policy, plain
 // per-lane work space): the lanes of a tile evaluate different step lengths of a struggling line
 // search at the same time.
-HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha) {
+HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha, int mode) {
   const int n = S.n;
   double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN], g[TS_MAXN];
   for (int i = 0; i < TS_MAXN; ++i) {
-    const double xi = (i < n) ? ts.x[i] + alpha * ts.dx[i] : 0.0, qi = (i < n) ? ts.q[i] : 0.0, vi = (i < n) ? ts.qd[i] : 0.0;
+    const double xi = (i < n) ? ts.x[i] + alpha * ts.dx[i] : 0.0;
     xq[i] = xi;
-    xv[i] = (xi - qi) / S.h;
-    xl[i] = xi - qi - S.h * vi;
+    xv[i] = 0.0;
+    xl[i] = 0.0;
+    if (i < n) stage_inputs(S, ts, mode, i, xi, xv[i], xl[i]);
     g[i] = 0.0;
   }
   ArrIn<double> in;
   in.q_ = xq; in.qd_ = xv; in.dl_ = xl; in.q0_ = ts.q; in.qd0_ = ts.qd;
   WorkRec<double> Wv;
   HostTile solo;
-  eval_g(solo, S, in, ts.u, Wv, g);
+  double stv, sbeta;
+  stage_coef(S, mode, stv, sbeta);
+  eval_g(solo, S, in, ts.u, Wv, g, sbeta);
   return norm_n(g, n);
 }
 
@@ -1278,10 +1509,20 @@ struct StepVars {
   int phase, fail_strike, iters, ls, trial;
   bool converged, batch_ls;
   int cap_newton;
+  int mode;                 // TS_ST_*: implicit stage in flight
 };
 
 HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
-  for (int i = 0; i < TS_MAXN; ++i) { ts.x[i] = (i < S.n) ? ts.q[i] + S.h * ts.qd[i] : 0.0; ts.dx[i] = 0.0; ts.xn[i] = 0.0; }
+  // initial guesses: q0 + h qd0 (BDF1, with h := alpha h in the first SDIRK2 stage), q1 + h qd1 (BDF2),
+  // q_alpha + (1 - alpha) h qd_alpha (second SDIRK2 stage)
+  for (int i = 0; i < TS_MAXN; ++i) {
+    double x0 = (i < S.n) ? ts.q[i] + S.h * ts.qd[i] : 0.0;
+#if KT_MULTISTEP
+    if (i < S.n && v.mode == TS_ST_SDIRK_A) x0 = ts.q[i] + (TS_SDIRK_ALPHA * S.h) * ts.qd[i];
+    if (i < S.n && v.mode == TS_ST_SDIRK_B) x0 = ts.pq[i] + (1 - TS_SDIRK_ALPHA) * S.h * ts.pqd[i];
+#endif
+    ts.x[i] = x0; ts.dx[i] = 0.0; ts.xn[i] = 0.0;
+  }
   v.phase = 0; v.fail_strike = 0; v.iters = 0; v.ls = 0; v.trial = 0;
   v.alpha = 1.0; v.gnorm = 0.0; v.converged = false;
 }
@@ -1297,7 +1538,7 @@ HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
 template <class Tile, class WK>
 HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, WK& WD, double (*cole)[TS_MAXN]) {
   TileState& ts = WD.state();
-  eval_columns(tl, S, ts, (v.phase == 1) ? ts.xn : ts.x, v.phase == 3 ? 1 : 0, WD, cole);
+  eval_columns(tl, S, ts, (v.phase == 1) ? ts.xn : ts.x, v.phase == 3 ? 1 : 0, v.mode, WD, cole);
 }
 
 template <class Tile, class WK>
@@ -1316,8 +1557,8 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         double Mc[TS_MAXN];
         mass_column(S, WD, ts.xq, k, Mc);
         for (int i = 0; i < n; ++i) {
-          tape[n * n + i * n + k] = cole[c][i];
-          tape[2 * n * n + i * n + k] = -S.h * Mc[i];
+          st_stream(tape + n * n + i * n + k, cole[c][i]);
+          tape[2 * n * n + i * n + k] = -S.h * Mc[i];      // (read-modify-written below by position motors)
         }
       }
     }
@@ -1375,7 +1616,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
           double my_alpha = v.alpha;
           for (int i = 0; i < tl.lane; ++i) my_alpha *= 0.5;
           double my_norm = 0.0;
-          if (tl.lane < nb) my_norm = trial_norm(S, ts, my_alpha);
+          if (tl.lane < nb) my_norm = trial_norm(S, ts, my_alpha, v.mode);
           const unsigned okbits = tl.ballot(tl.lane < nb && my_norm < v.gnorm);
           if (okbits) {
             const int k = ts_ffs(okbits);
@@ -1415,7 +1656,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     if (!tape) return true;
     for (int c = 0; c < TS_NC(L); ++c) {
       const int k = tl.lane + c * L;
-      if (k < n) for (int i = 0; i < n; ++i) tape[i * n + k] = cole[c][i];
+      if (k < n) for (int i = 0; i < n; ++i) st_stream(tape + i * n + k, cole[c][i]);
     }
     v.phase = 3;
     return false;
@@ -1470,7 +1711,8 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
   F.near[0] = true;
   for (int c = 0; c < nc; ++c) {
     const int b2 = sr[4 + c];
-    const bool cyl = KT_CYLINDER && S.ib[S.o_body + b2 * KB_ISTRIDE + 1] == TS_SH_CYLINDER;
+    const int sh2 = S.ib[S.o_body + b2 * KB_ISTRIDE + 1];
+    const bool cyl = (KT_CYLINDER && sh2 == TS_SH_CYLINDER) || (KT_SPHERE && sh2 == TS_SH_SPHERE);
     body_frame_v(S, W, b2, F.R[1 + c], F.p[1 + c], F.ph[1 + c]);
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
@@ -1486,7 +1728,8 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
 // per-marker intermediate of the tactile force, shared by the value pass and its adjoint
 struct MarkerHit {
   int cand;           // index of the contacted candidate (last candidate with d < 0), -1 if none
-  bool cyl;           // the candidate is a cylinder (normal depends on the point), else a cuboid (face normal)
+  bool cyl;           // the candidate is a cylinder or a sphere (normal depends on the point), else a cuboid (face normal)
+  bool sph;           // ... a sphere
   double e[3];        // contact normal in the candidate's frame
   double x[3], u[3], d, ddot, tb[3], s, tn, rad;
   bool dynamic;
@@ -1501,10 +1744,21 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
   const double* R1 = F.R[0]; const double* p1 = F.p[0]; const double* ph1 = F.ph[0];
   H.cand = -1;
   H.cyl = false;
+  H.sph = false;
   for (int c = 0; c < nc; ++c) {
     if (!F.near[1 + c]) continue;
     const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
     double xw[3], y[3], x[3];
+    if (KT_SPHERE && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_SPHERE) {
+      // TactileSensor.cpp:44-47 with BodySphere::distance; the force is evaluated at x = R2^T (xw - p2)
+      mv3(R1, xi1, xw);
+      for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+      if (!sphere_inside_world(F.p[1 + c], xw, hs[0])) continue;
+      for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
+      mtv3(F.R[1 + c], y, x);
+      H.cand = c; H.cyl = true; H.sph = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
+      continue;
+    }
     if (KT_CYLINDER && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CYLINDER) {
       mv3(R1, xi1, xw);
       for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
@@ -1512,7 +1766,7 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
       // the force is evaluated at x = R2^T (xw - p2)  (BodyCylinder.cpp:118)
       for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
       mtv3(F.R[1 + c], y, x);
-      H.cand = c; H.cyl = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
+      H.cand = c; H.cyl = true; H.sph = false; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
       continue;
     }
     if (cuboid_classify(F.R21[c], F.r21[c], xi1, hs) < 0) continue;   // surely outside
@@ -1520,13 +1774,17 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
     mv3(R1, xi1, xw);
     for (int i = 0; i < 3; ++i) y[i] = (xw[i] + p1[i]) - F.p[1 + c][i];
     mtv3(F.R[1 + c], y, x);
-    if (cuboid_inside(x, hs)) { H.cand = c; H.cyl = false; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
+    if (cuboid_inside(x, hs)) { H.cand = c; H.cyl = false; H.sph = false; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; }
   }
   F1[0] = F1[1] = F1[2] = 0.0;
   if (H.cand < 0) return;
   const double* hs = S.db + S.d_body + sr[4 + H.cand] * KB_DSTRIDE + KB_HALF;
   const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
-  if (KT_CYLINDER && H.cyl) {
+  if (KT_SPHERE && H.sph) {
+    H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1] + H.x[2] * H.x[2]);
+    H.d = H.rad - hs[0];
+    H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = H.x[2] / H.rad;
+  } else if (KT_CYLINDER && H.cyl) {
     H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1]);
     H.d = H.rad - hs[0];
     H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = 0.0;
@@ -1585,8 +1843,8 @@ HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, 
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
     if (!anynear) {
       // no candidate body can reach the pad: zero field, written with unit stride across the lanes
-      for (int i = tl.lane; i < 3 * mc; i += Tile::LPE) out[3 * mo + i] = (i % 3 == 2) ? -0.0 : 0.0;
-      if (body_out) for (int m = tl.lane; m < mc; m += Tile::LPE) body_out[mo + m] = -1;
+      for (int i = tl.lane; i < 3 * mc; i += Tile::LPE) st_stream(out + 3 * mo + i, (i % 3 == 2) ? -0.0 : 0.0);
+      if (body_out) for (int m = tl.lane; m < mc; m += Tile::LPE) st_stream(body_out + mo + m, -1);
       continue;
     }
     for (int m = tl.lane; m < mc; m += Tile::LPE) {
@@ -1595,10 +1853,10 @@ HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, 
       MarkerHit H;
       double F1[3];
       marker_force(S, F, sr, sd, mk, H, F1);
-      o[0] = dot3(F1, mk + 3);
-      o[1] = dot3(F1, mk + 6);
-      o[2] = -dot3(F1, mk + 9);
-      if (body_out) body_out[mo + m] = H.cand < 0 ? -1 : sr[4 + H.cand];
+      st_stream(o + 0, dot3(F1, mk + 3));
+      st_stream(o + 1, dot3(F1, mk + 6));
+      st_stream(o + 2, -dot3(F1, mk + 9));
+      if (body_out) st_stream(body_out + mo + m, H.cand < 0 ? -1 : sr[4 + H.cand]);
     }
   }
 }
@@ -1875,6 +2133,12 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
     const int* r = S.ib + S.o_ground + gi * KG_ISTRIDE;
     const int b = r[0], po = r[1], pc = r[2];
     body_frame_v(S, W, b, R1, p1, ph);
+    if (KT_SPHERE && pc < 0) {               // sphere: one contact, bit 0
+      const double rad = S.db[S.d_body + b * KB_DSTRIDE + KB_HALF];
+      const double dc = (S.gn[0] * (p1[0] - S.gx[0]) + S.gn[1] * (p1[1] - S.gx[1]) + S.gn[2] * (p1[2] - S.gx[2])) - rad;
+      if (dc <= 0.0) mw[r[3]] |= 1u;
+      continue;
+    }
     for (int k = 0; k < pc; ++k) {
       const double* xi = S.db + S.d_points + 3 * (po + k);
       double xw[3];
@@ -1895,7 +2159,10 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
       double xw[3], y[3], x[3];
       mv3(R1, xi, xw);
       bool in;
-      if (KT_CYLINDER && r[5] == TS_SH_CYLINDER) {
+      if (KT_SPHERE && r[5] == TS_SH_SPHERE) {
+        for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+        in = sphere_inside_world(p2, xw, hs[0]);
+      } else if (KT_CYLINDER && r[5] == TS_SH_CYLINDER) {
         for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
         in = cylinder_inside_world(R2, p2, xw, hs);
       } else {
@@ -1921,6 +2188,9 @@ struct FwdArgs {
   int* marker_body;                   // [rows,B,M] (rows as tac_out) or null
   int ls_batch;                       // TSIM_OPT_LS_BATCH
   int max_newton;                     // TSIM_OPT_MAX_NEWTON (0 = the reference's rule)
+  // two-state integrators (BDF2): state one step back [B,n], in/out, or null; steps already taken since reset
+  double* q_prev; double* qd_prev;
+  int steps_done;
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
@@ -1963,8 +2233,20 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   StepVars v;
   v.batch_ls = a.ls_batch != 0;
   v.cap_newton = a.max_newton;
+  v.mode = TS_ST_BDF1;
   int t = 0;                             // warp-uniform
   bool tile_done = !active;
+#if KT_MULTISTEP
+  const int integ = S.ib[KI_INTEGRATOR];
+  // BDF2 starts with one SDIRK2 step (DH/Simulation.cpp:1079-1086); SDIRK2 runs its two stages every step
+  if (integ == TS_INT_SDIRK2 || (integ == TS_INT_BDF2 && a.steps_done == 0)) v.mode = TS_ST_SDIRK_A;
+  else if (integ == TS_INT_BDF2) v.mode = TS_ST_BDF2;
+  for (int i = 0; i < TS_MAXN; ++i) {
+    const bool have = i < n && a.q_prev && a.steps_done > 0;
+    ts.pq[i] = have ? a.q_prev[(long long)env * n + i] : 0.0;
+    ts.pqd[i] = have ? a.qd_prev[(long long)env * n + i] : 0.0;
+  }
+#endif
   if (a.T > 0) {
     for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[(long long)env * nu + i] : 0.0;
     tl.tile_sync();
@@ -1985,22 +2267,53 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     }
     if (!tl.warp_all(tile_done)) continue;
     TS_TIC(tl);
+#if KT_MULTISTEP
+    if (v.mode == TS_ST_SDIRK_A) {
+      // first SDIRK2 stage solved: (q_alpha, qd_alpha) become the second state, the second stage starts
+      double qa[TS_MAXN], qda[TS_MAXN];
+      for (int i = 0; i < TS_MAXN; ++i) {
+        qa[i] = (i < n) ? ts.x[i] : 0.0;
+        qda[i] = (i < n) ? (ts.x[i] - ts.q[i]) / (TS_SDIRK_ALPHA * S.h) : 0.0;
+      }
+      tl.tile_sync();
+      for (int i = 0; i < TS_MAXN; ++i) { ts.pq[i] = qa[i]; ts.pqd[i] = qda[i]; }
+      v.mode = TS_ST_SDIRK_B;
+      tl.tile_sync();
+      step_begin(S, v, ts);
+      tile_done = !active;
+      TS_TOC(tl, 6);
+      continue;
+    }
+#endif
     // ---- the step is complete for every tile of this warp
     if (active) {
       int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
       double qn[TS_MAXN], qdn[TS_MAXN];        // read-modify-write of shared tile state: reads, sync, writes
+#if KT_MULTISTEP
+      double qo[TS_MAXN], qdo[TS_MAXN];
+#endif
       for (int i = 0; i < TS_MAXN; ++i) {
         const double q1 = ts.x[i];
-        qdn[i] = (i < n) ? (q1 - ts.q[i]) / S.h : 0.0;
+        double xv = 0.0, xl = 0.0;
+        if (i < n) stage_inputs(S, ts, v.mode, i, q1, xv, xl);
+        qdn[i] = xv;
         qn[i] = (i < n) ? q1 : 0.0;
         if (i < n && !(q1 == q1)) stat |= TS_STAT_NAN;
+#if KT_MULTISTEP
+        qo[i] = ts.q[i]; qdo[i] = ts.qd[i];
+#endif
       }
       tl.tile_sync();
-      for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = qn[i]; ts.qd[i] = qdn[i]; }
+      for (int i = 0; i < TS_MAXN; ++i) {
+        ts.q[i] = qn[i]; ts.qd[i] = qdn[i];
+#if KT_MULTISTEP
+        ts.pq[i] = qo[i]; ts.pqd[i] = qdo[i];      // state one step back (BDF2)
+#endif
+      }
       if (tl.lane == 0) {
         if (a.status) a.status[es] = stat;
-        if (a.q_traj) for (int i = 0; i < n; ++i) a.q_traj[es * n + i] = qn[i];
-        if (a.qd_traj) for (int i = 0; i < n; ++i) a.qd_traj[es * n + i] = qdn[i];
+        if (a.q_traj) for (int i = 0; i < n; ++i) st_stream(a.q_traj + es * n + i, qn[i]);
+        if (a.qd_traj) for (int i = 0; i < n; ++i) st_stream(a.qd_traj + es * n + i, qdn[i]);
       }
       const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
       const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
@@ -2014,6 +2327,9 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
       }
     }
     ++t;
+#if KT_MULTISTEP
+    v.mode = (integ == TS_INT_SDIRK2) ? TS_ST_SDIRK_A : ((integ == TS_INT_BDF2) ? TS_ST_BDF2 : TS_ST_BDF1);
+#endif
     if (t < a.T) {
       tl.tile_sync();                    // readouts of this step are done in every lane of the tile
       for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
@@ -2022,6 +2338,11 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     }
     TS_TOC(tl, 6);
   }
+#if KT_MULTISTEP
+  tl.tile_sync();
+  if (active && tl.lane == 0 && a.q_prev)
+    for (int i = 0; i < n; ++i) { a.q_prev[(long long)env * n + i] = ts.pq[i]; a.qd_prev[(long long)env * n + i] = ts.pqd[i]; }
+#endif
   tl.tile_sync();
   if (active && tl.lane == 0)
     for (int i = 0; i < n; ++i) { a.q[(long long)env * n + i] = ts.q[i]; a.qd[(long long)env * n + i] = ts.qd[i]; }

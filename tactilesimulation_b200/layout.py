@@ -18,8 +18,8 @@ JD, CD, AD, ED, SD = 48, 4, 12, 4, 16
 
 
 def pack_scene(sc: "S.Scene"):
-    if sc.integrator != "BDF1":
-        raise S.SceneError(f"integrator {sc.integrator} is not supported by the B200 path yet (BDF1 only)")
+    if sc.integrator not in S.INTEGRATORS:
+        raise S.SceneError("Integrator " + sc.integrator + " has not been implemented.")
     if sc.nj > MAXB or sc.ndof_r > MAXN:
         raise S.SceneError(f"scene too large for this build: nj={sc.nj} (max {MAXB}), ndof_r={sc.ndof_r} (max {MAXN})")
     ints = [np.zeros(I_HEADER, dtype=np.int64)]
@@ -43,7 +43,7 @@ def pack_scene(sc: "S.Scene"):
 
     hdr[0:16] = [TS_MAGIC, TS_VERSION, sc.nj, sc.ndof_r, sc.ndof_u, len(sc.end_effectors), sc.n_markers,
                  len(sc.ground_contacts), len(sc.gp_contacts), len(sc.actuators), len(sc.sensors),
-                 sc.max_iter, sc.max_ls, 0, 0, 0]
+                 sc.max_iter, sc.max_ls, 0, S.INTEGRATORS[sc.integrator], 0]
     dh[0] = sc.h
     dh[1:4] = sc.gravity
     dh[4] = sc.tol
@@ -167,7 +167,7 @@ def scene_from_blob(ibuf, dbuf):
     db = np.asarray(dbuf, dtype=np.float64)
     sc = S.Scene()
     nj, n, nu, nee, nm, ng, ngp, nact, nsens, max_iter, max_ls, npts = (int(x) for x in ib[2:14])
-    sc.integrator = "BDF1"
+    sc.integrator = {v: k for k, v in S.INTEGRATORS.items()}[int(ib[14])]
     sc.h = float(db[0]); sc.gravity = db[1:4].copy(); sc.tol = float(db[4])
     sc.max_iter, sc.max_ls = max_iter, max_ls
     sc.E_g = np.eye(4); sc.E_g[:3, 2] = db[5:8]; sc.E_g[:3, 3] = db[8:11]

@@ -40,12 +40,15 @@ from typing import Dict, List, Optional
 import numpy as np
 
 # joint types (values are shared with csrc/scene_layout.h)
-JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL, JT_FREE3D_EULER = 0, 1, 2, 3, 4, 5
-JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3, JT_FREE3D_EULER: 6}
+JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL, JT_FREE3D_EULER, JT_FREE3D_EXP = 0, 1, 2, 3, 4, 5, 6
+JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3, JT_FREE3D_EULER: 6,
+              JT_FREE3D_EXP: 6}
 # "free3d" is the XYZ-Euler chart in the reference too (DH/Simulation_Constructor.cpp:483-484)
 JOINT_TYPES = {"fixed": JT_FIXED, "revolute": JT_REVOLUTE, "prismatic": JT_PRISMATIC,
                "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL,
-               "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER}
+               "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER, "free3d-exp": JT_FREE3D_EXP}
+# time integrators (DH/Simulation.cpp:1076-1092); codes shared with csrc/scene_layout.h
+INTEGRATORS = {"BDF1": 0, "BDF2": 1, "SDIRK2": 2}
 # body shapes
 SH_NONE, SH_CUBOID, SH_CYLINDER, SH_SPHERE = 0, 1, 2, 3
 # actuator modes
@@ -435,6 +438,14 @@ def compile_scene(xml_path: str) -> Scene:
             inertia[3:] = mass
             shape, size = SH_CYLINDER, np.array([radius, length, 0.0])
             pts = _cylinder_points(radius, length, ares, rres)
+        elif btype == "sphere":
+            # DH/Simulation_Constructor.cpp:597-599, DH/Body/BodySphere.cpp:17-21; no sampled contact points: a sphere
+            # is a primitive body and touches the ground at one state-dependent point (CollisionDetection.cpp:17-25)
+            radius = _f32(bn.get("radius"))
+            mass = 4.0 / 3.0 * math.pi * radius * radius * radius * density
+            inertia[:3] = 0.4 * mass * radius * radius
+            inertia[3:] = mass
+            shape, size = SH_SPHERE, np.array([radius, 0.0, 0.0])
         elif btype == "mesh":
             V, F = _load_obj(os.path.join(asset_dir, bn.get("filename")))
             V = V * scale[None, :]
@@ -624,8 +635,6 @@ def compile_scene(xml_path: str) -> Scene:
                 bname = c.get("body")
                 if bname not in body_map:
                     raise SceneError("Ground contact body name error: " + str(bname))
-                if sc.shape[body_map[bname]] == SH_SPHERE:
-                    raise SceneError("sphere ground contact is not supported by the B200 path yet")
                 sc.ground_contacts.append(dict(body=body_map[bname], **coef))
             elif c.tag == "general_primitive_contact":
                 b1, b2 = c.get("general_body"), c.get("primitive_body")
@@ -657,11 +666,13 @@ def compile_scene(xml_path: str) -> Scene:
                 sc.virtual_names.append(e.get("name", ""))
     for s in sc.sensors:
         for k in s.candidates:
-            if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER):
-                raise SceneError("tactile candidates other than cuboids and cylinders are not supported by the B200 path yet")
+            if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE):
+                raise SceneError("tactile candidates other than cuboids, cylinders and spheres are not supported by the B200 path yet")
     for gp in sc.gp_contacts:
-        if sc.shape[gp["body2"]] not in (SH_CUBOID, SH_CYLINDER):
-            raise SceneError("primitive contact bodies other than cuboids and cylinders are not supported by the B200 path yet")
+        if sc.shape[gp["body2"]] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE):
+            raise SceneError("primitive contact bodies other than cuboids, cylinders and spheres are not supported by the B200 path yet")
+    if sc.integrator not in INTEGRATORS:
+        raise SceneError("Integrator " + sc.integrator + " has not been implemented.")
     return sc
 
 

@@ -22,7 +22,7 @@ int emu_cmask_words(const int32_t* ibuf, const double* dbuf) {
 int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, double* q, double* qd,
                 const double* u, int64_t u_stride, double* q_traj, double* qd_traj, double* var_out,
                 const int32_t* var_row, double* tac_out, const int32_t* tac_row, double* tape, int32_t* status,
-                uint32_t* cmask, int32_t* marker_body) {
+                uint32_t* cmask, int32_t* marker_body, double* q_prev, double* qd_prev, int32_t steps_done) {
   KernelTables kt;
   if (!lower_scene(ibuf, 1 << 30, dbuf, 1 << 30, kt).empty()) return 1;
   SceneView S;
@@ -31,6 +31,7 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   a.B = B; a.T = T; a.q = q; a.qd = qd; a.u = u; a.u_stride = u_stride; a.q_traj = q_traj; a.qd_traj = qd_traj;
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
   a.status = status; a.cmask = cmask; a.marker_body = marker_body; a.ls_batch = 0; a.max_newton = 0;
+  a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
   std::vector<Work<Dual> > wb(1);
   HostTile tl;
   for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb[0]);
@@ -62,6 +63,7 @@ int emu_readout(const int32_t* ibuf, const double* dbuf, int32_t B, const double
   SceneView S;
   scene_view_init(S, kt.ib.data(), kt.db.data());
   std::vector<Work<double> > wb(1);
+  wb[0].beta = 0.0;
   HostTile tl;
   for (int env = 0; env < B; ++env)
     env_readout(tl, S, q + (long long)env * S.n, qd + (long long)env * S.n,

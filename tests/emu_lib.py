@@ -15,7 +15,7 @@ _libs = {}
 
 
 def lib(variant=8):
-    """The harness compiled with the capacities of kernel variant 8 or 16 (csrc/kernel_layout.h)."""
+    """The harness compiled with the capacities of kernel variant 8, 16 or 17 (csrc/kernel_layout.h)."""
     if variant not in _libs:
         path = LIB % variant
         deps = [SRC] + [os.path.join(CORE, f) for f in ("sim_core.cuh", "dual.cuh", "scene_layout.h", "kernel_layout.h", "scene_lower.h")]
@@ -27,12 +27,12 @@ def lib(variant=8):
 
 def lib_for(ibuf, dbuf):
     """(library, contact bitmask words) of the smallest variant that accepts the scene."""
-    for variant in (8, 16):
+    for variant in (8, 16, 17):
         l = lib(variant)
         w = l.emu_cmask_words(_p(ibuf, ctypes.c_int32), _p(dbuf))
         if w >= 0:
             return l, w
-    raise RuntimeError("scene rejected by both kernel variants")
+    raise RuntimeError("scene rejected by every kernel variant")
 
 
 def _p(a, t=ctypes.c_double):
@@ -43,8 +43,9 @@ def _rows(x):
     return None if x is None else np.ascontiguousarray(x, dtype=np.int32)
 
 
-def forward(ibuf, dbuf, q0, qd0, u, grad=False, var_row=None, tac_row=None, want_masks=True):
-    """u: [T,B,nu].  Returns dict of trajectories."""
+def forward(ibuf, dbuf, q0, qd0, u, grad=False, var_row=None, tac_row=None, want_masks=True, hist=None, steps_done=0):
+    """u: [T,B,nu].  Returns dict of trajectories.  hist = (q_prev, qd_prev) [B,n] arrays (in/out) and steps_done:
+    the multistep state of tsim_forward_multistep."""
     ibuf = np.ascontiguousarray(ibuf, dtype=np.int32)
     dbuf = np.ascontiguousarray(dbuf, dtype=np.float64)
     n, nu, nee, M = int(ibuf[3]), int(ibuf[4]), int(ibuf[5]), int(ibuf[6])
@@ -64,7 +65,8 @@ def forward(ibuf, dbuf, q0, qd0, u, grad=False, var_row=None, tac_row=None, want
     l.emu_forward(_p(ibuf, ctypes.c_int32), _p(dbuf), B, T, _p(q), _p(qd), _p(u), ctypes.c_int64(B * nu),
                       _p(out["q"]), _p(out["qd"]), _p(out["var"]), _p(vr, ctypes.c_int32), _p(out["tactile"]),
                       _p(tr, ctypes.c_int32), _p(out["tape"]), _p(out["status"], ctypes.c_int32),
-                      _p(out["cmask"], ctypes.c_uint32), _p(out["marker_body"], ctypes.c_int32))
+                      _p(out["cmask"], ctypes.c_uint32), _p(out["marker_body"], ctypes.c_int32),
+                      _p(None if hist is None else hist[0]), _p(None if hist is None else hist[1]), ctypes.c_int32(steps_done))
     out["q_final"], out["qd_final"] = q, qd
     return out
 

@@ -245,6 +245,58 @@ def stable_grasp_case(T, seed):
     return multi_case(xml, q0, u, seed)
 
 
+def rolling_ball_case():
+    """examples/RollingBallExp/test_sim_speed.py (BASELINE configs[0]): the unmodified tactile_pad.xml scene (BDF2 with
+    an SDIRK2 start-up step, free3d-exp ball, sphere SDF, 2168 sampled pad points) under the script's action
+    schedule, 350 steps.  The trajectory and the tactile field every 5 steps come from the 40x40-marker variant
+    (identical dynamics: sensors do not act on the bodies); of the real 200x200 field four frames are kept as
+    sparse (index, value) lists."""
+    adir = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_pad")
+    xml40, xml200 = os.path.join(adir, "tactile_pad_40x40.xml"), os.path.join(adir, "tactile_pad.xml")
+    acts = [np.array([0., 0., 0.2]), np.array([0.1, 0., 0.2]), np.array([-0.2, 0., 0.2]), np.array([0., 0.1, 0.2]),
+            np.array([0., -0.2, 0.2])]
+    steps = [0, 100, 150, 200, 250, 350]
+    u = np.zeros((350, 3))
+    for i in range(5):
+        u[steps[i]:steps[i + 1]] = acts[i]
+    T = len(u)
+    sim, probe, big = redmax_py.Simulation(xml40), redmax_probe.ProbeSimulation(xml40), redmax_py.Simulation(xml200)
+    sc = compile_scene(xml40)
+    for s in (sim, probe, big):
+        s.reset(False)
+    frames200 = (75, 150, 250, 349)
+    q, qd, tac, ground, gp, mb, big_idx, big_val = [], [], [], [], [], [], [], []
+    for t in range(T):
+        for s in (sim, probe, big):
+            s.set_u(u[t])
+            s.forward(1)
+        assert np.array_equal(sim.get_q(), probe.get_q()) and np.array_equal(sim.get_q(), big.get_q())
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        cs = probe.contact_sets()
+        ground.append(cs["ground"][0])
+        gp.append(cs["gp"][0])
+        if t % 5 == 0:
+            tac.append(sim.get_tactile_force_vector().copy())
+            mb.append(np.asarray(cs["marker_body"][0], dtype=np.int32))
+        if t in frames200:
+            f = big.get_tactile_force_vector().copy()
+            nz = np.nonzero(f)[0]
+            big_idx.append(nz.astype(np.int32))
+            big_val.append(f[nz])
+    ib, db = sc.pack()
+    width = max(len(x) for x in big_idx)
+    bi = -np.ones((len(frames200), width), dtype=np.int32)
+    bv = np.zeros((len(frames200), width))
+    for k in range(len(frames200)):
+        bi[k, :len(big_idx[k])] = big_idx[k]
+        bv[k, :len(big_val[k])] = big_val[k]
+    return dict(ibuf=ib, dbuf=db, q0=np.zeros(sim.ndof_r), qd0=np.zeros(sim.ndof_r), u=u, q=np.array(q), qd=np.array(qd),
+                tactile=np.array(tac), tactile_every=5, marker_body=np.array(mb, dtype=np.int32),
+                ground_ids=pad_ids(ground, 1), gp_ids=pad_ids(gp, max(len(x) for x in gp)),
+                frames200=np.array(frames200), tactile200_idx=bi, tactile200_val=bv)
+
+
 def main():
     x13 = os.path.join(ASSETS, "pusher.xml")
     x32 = os.path.join(ASSETS, "pusher_32x13.xml")
@@ -256,6 +308,7 @@ def main():
         "dclaw_episodic_s0": lambda: dclaw_case(40, 0),
         "insertion_episodic_s0": lambda: insertion_case(60, 0),
         "stable_grasp_episodic_s0": lambda: stable_grasp_case(50, 0),
+        "rollingball_bdf2_s0": rolling_ball_case,
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
     if only:

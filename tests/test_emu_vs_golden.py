@@ -147,3 +147,37 @@ def test_emulated_insertion_and_stable_grasp_match_reference(name):
     assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
     assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
     assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_rolling_ball_matches_reference():
+    """examples/RollingBallExp (BASELINE configs[0], the reference's own scene and action schedule): BDF2 with its
+    SDIRK2 start-up step, free3d-exp ball, sphere SDF (ground, pad contact, tactile), 2168 sampled pad points;
+    kernel variant 17.  Then the same trajectory in chunks through the multistep state (tsim_forward_multistep),
+    and four frames of the real 200x200 tactile field."""
+    from tests import rolling_ball as rb
+    g = np.load(os.path.join(GOLDEN, "rollingball_bdf2_s0.npz"))
+    T = g["u"].shape[0]
+    rows = rb.tactile_rows(T, int(g["tactile_every"]))
+    u = g["u"][:, None, :]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], u, tac_row=rows)
+    rb.check_trajectory(out["q"][:, 0], out["qd"][:, 0], out["status"][:, 0], out["cmask"][:, 0], out["tactile"][:, 0],
+                        out["marker_body"][:, 0], g)
+    # chunked: 1 + 4 + 95 steps, history carried by the caller; bit-identical to the single call
+    n = len(g["q0"])
+    q, qd = g["q0"].copy()[None], g["qd0"].copy()[None]
+    hist = (np.zeros((1, n)), np.zeros((1, n)))
+    done = 0
+    for chunk in (1, 4, 95):
+        o = emu_lib.forward(g["ibuf"], g["dbuf"], q, qd, u[done:done + chunk], want_masks=False, hist=hist, steps_done=done)
+        assert np.array_equal(o["q"][:, 0], out["q"][done:done + chunk, 0])
+        q, qd = o["q_final"], o["qd_final"]
+        done += chunk
+    assert np.array_equal(hist[0][0], out["q"][done - 2, 0])
+    # the real 200x200 sensor at four steps
+    ib, db = rb.full_resolution_blob(g["ibuf"], g["dbuf"])
+    frames = [int(f) for f in g["frames200"]]
+    rows = np.full(T, -1, dtype=np.int32)
+    rows[frames] = np.arange(len(frames))
+    big = emu_lib.forward(ib, db, g["q0"], g["qd0"], u, tac_row=rows, want_masks=False)
+    assert np.array_equal(big["q"], out["q"])
+    rb.check_full_resolution_frames(big["tactile"][:, 0], g)
