@@ -19,9 +19,9 @@
   int tsim_scene_sizes_v##V(const void*, int32_t*);                                                                   \
   int tsim_scene_set_lanes_v##V(void*, int);                                                                          \
   int tsim_scene_set_option_v##V(void*, int, int);                                                                    \
-  int tsim_forward_v##V(const void*, int32_t, int32_t, double*, double*, const double*, int64_t, double*, double*,   \
-                        double*, const int32_t*, double*, const int32_t*, double*, int32_t*, uint32_t*, int32_t*,     \
-                        double*, double*, int32_t, void*);                                                                                    \
+  int tsim_forward_multistep_v##V(const void*, int32_t, int32_t, double*, double*, double*, double*, int32_t,        \
+                                  const double*, int64_t, double*, double*, double*, const int32_t*, double*,        \
+                                  const int32_t*, double*, int32_t*, uint32_t*, int32_t*, void*);                     \
   int tsim_readout_v##V(const void*, int32_t, const double*, const double*, double*, double*, int32_t*, uint32_t*,    \
                         void*);                                                                                       \
   int tsim_backward_v##V(const void*, int32_t, int32_t, const double*, const double*, const double*, int64_t,        \
@@ -110,9 +110,10 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
                            double* var_out, const int32_t* var_row, double* tac_out, const int32_t* tac_row, double* tape,
                            int32_t* status, uint32_t* contact_masks, int32_t* marker_body, void* stream) {
   if (!s) return own_fail("tsim_forward: null scene");
-#define TS_FWD_ARGS s->inner, B, T, q, qd, u, u_step_stride, q_traj, qd_traj, var_out, var_row, tac_out, tac_row, tape, status, \
-                    contact_masks, marker_body, q_prev, qd_prev, steps_done, stream
-  return DISPATCH(s, tsim_forward_v8(TS_FWD_ARGS), tsim_forward_v16(TS_FWD_ARGS), tsim_forward_v17(TS_FWD_ARGS));
+#define TS_FWD_ARGS s->inner, B, T, q, qd, q_prev, qd_prev, steps_done, u, u_step_stride, q_traj, qd_traj, var_out, var_row, \
+                    tac_out, tac_row, tape, status, contact_masks, marker_body, stream
+  return DISPATCH(s, tsim_forward_multistep_v8(TS_FWD_ARGS), tsim_forward_multistep_v16(TS_FWD_ARGS),
+                  tsim_forward_multistep_v17(TS_FWD_ARGS));
 #undef TS_FWD_ARGS
 }
 

@@ -31,6 +31,7 @@
 #define tsim_scene_set_lanes TSV(tsim_scene_set_lanes)
 #define tsim_scene_set_option TSV(tsim_scene_set_option)
 #define tsim_forward TSV(tsim_forward)
+#define tsim_forward_multistep TSV(tsim_forward_multistep)
 #define tsim_readout TSV(tsim_readout)
 #define tsim_backward TSV(tsim_backward)
 #define tsim_debug_set_prof TSV(tsim_debug_set_prof)
@@ -372,10 +373,12 @@ int tsim_scene_set_option(tsim_scene* s, int key, int value) {
   return 0;
 }
 
-int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, const double* u,
-                 int64_t u_step_stride, double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row,
-                 double* tac_out, const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
-                 int32_t* marker_body, double* q_prev, double* qd_prev, int32_t steps_done, void* stream) {
+// (the public tsim_forward is tsim_forward_multistep(..., NULL, NULL, 0, ...): csrc/cabi.cpp)
+int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, double* q_prev,
+                           double* qd_prev, int32_t steps_done, const double* u, int64_t u_step_stride,
+                           double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row, double* tac_out,
+                           const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
+                           int32_t* marker_body, void* stream) {
   if (!s) return fail("tsim_forward: null scene");
   if (B <= 0 || T < 0) return fail("tsim_forward: bad batch or step count");
   if (!q || !qd || !u) return fail("tsim_forward: q, qd and u are required");

@@ -16,6 +16,8 @@
 #define TS_JT_TRANSLATIONAL 4
 #define TS_JT_FREE3D_EULER 5    // q = (p, r): translation + XYZ Euler angles (DH/Joint/JointFree3DEuler.cpp)
 #define TS_JT_FREE3D_EXP 6      // q = (p, r): translation + exponential coordinates (DH/Joint/JointFree3DExp.cpp)
+#define TS_JT_SPHERICAL_EULER 7 // q = r: XYZ Euler angles (DH/Joint/JointSphericalEuler.cpp)
+#define TS_JT_SPHERICAL_EXP 8   // q = r: exponential coordinates (DH/Joint/JointSphericalExp.cpp)
 #define TS_SH_NONE 0
 #define TS_SH_CUBOID 1
 #define TS_SH_CYLINDER 2

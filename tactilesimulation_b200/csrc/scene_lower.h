@@ -65,9 +65,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   for (int j = 0; j < nj; ++j) {
     const int jt = J[j * TS_JI_STRIDE], par = J[j * TS_JI_STRIDE + 1];
     if (par >= j) return "joints are not in parent-first order";
-    if (jt == TS_JT_FREE3D_EULER && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler joints)";
-    if (jt == TS_JT_FREE3D_EXP && !KT_EXP3D) return "scene exceeds the compiled capacity (free3d-exp joints)";
-    if (jt < TS_JT_FIXED || jt > TS_JT_FREE3D_EXP) return "unknown joint type";
+    if ((jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER) && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler / spherical-euler joints)";
+    if ((jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP) && !KT_EXP3D) return "scene exceeds the compiled capacity (free3d-exp / spherical-exp joints)";
+    if (jt < TS_JT_FIXED || jt > TS_JT_SPHERICAL_EXP) return "unknown joint type";
     const Xf e0 = xf_load(JD + j * TS_JD_STRIDE + TS_JD_RPJ, JD + j * TS_JD_STRIDE + TS_JD_PPJ);
     const Xf up = (par < 0) ? e0 : xf_mul(erel[par], e0);
     if (jt == TS_JT_FIXED) {

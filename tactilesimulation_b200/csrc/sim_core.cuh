@@ -418,22 +418,25 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         sq[i] = w[i] * in.qd(qo); sq[3 + i] = m[i] * in.qd(qo);
         if (dyn) { sl[i] = w[i] * in.dl(qo); sl[3 + i] = m[i] * in.dl(qo); }
       }
-    } else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
+    } else if (KT_FREE3D && (jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER)) {
+      // (spherical-euler, DH/Joint/JointSphericalEuler.cpp: the rotation alone, q = r, p = 0)
+      const bool trans = jt == TS_JT_FREE3D_EULER;
+      const int ro = trans ? qo + 3 : qo;
       // q = (p, r): Q = [R(r) p; 0 1], R = Rx(r1) Ry(r2) Rz(r3)   (DH/Joint/JointFree3DEuler.cpp:14-104,
       // JointSphericalEuler.cpp:15-60).  In the pre-motion frame a the child moves with the twist
       // xi = (G rdot, pdot + p x G rdot) about a's origin, G = [e_x, Rx e_y, Rx Ry e_z]; the rotation axes move
       // with r, which adds xi_dot = (Gdot rdot, pdot x G rdot + p x Gdot rdot) to the velocity-product term.
       T s1, c1, s2, c2, s3, c3;
-      dsincos(in.q(qo + 3), s1, c1);
-      dsincos(in.q(qo + 4), s2, c2);
-      dsincos(in.q(qo + 5), s3, c3);
+      dsincos(in.q(ro), s1, c1);
+      dsincos(in.q(ro + 1), s2, c2);
+      dsincos(in.q(ro + 2), s3, c3);
       T Rq[9];
       Rq[0] = c2 * c3; Rq[1] = -(c2 * s3); Rq[2] = s2;
       Rq[3] = c1 * s3 + c3 * (s1 * s2); Rq[4] = c1 * c3 - (s1 * s2) * s3; Rq[5] = -(c2 * s1);
       Rq[6] = s1 * s3 - (c1 * c3) * s2; Rq[7] = c3 * s1 + (c1 * s2) * s3; Rq[8] = c1 * c2;
       mm3(Ra, Rq, R0);
       T pq[3], t[3];
-      for (int i = 0; i < 3; ++i) pq[i] = in.q(qo + i);
+      for (int i = 0; i < 3; ++i) pq[i] = trans ? in.q(qo + i) : T(0.0);
       mv3(Ra, pq, t);
       for (int i = 0; i < 3; ++i) p0[i] = pa[i] + t[i];
       T g2[3], g3[3];
@@ -442,8 +445,8 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
       for (int pass = 0; pass < (dyn ? 2 : 1); ++pass) {
         T rd[3], pd[3];
         for (int i = 0; i < 3; ++i) {
-          pd[i] = pass ? in.dl(qo + i) : in.qd(qo + i);
-          rd[i] = pass ? in.dl(qo + 3 + i) : in.qd(qo + 3 + i);
+          pd[i] = trans ? (pass ? in.dl(qo + i) : in.qd(qo + i)) : T(0.0);
+          rd[i] = pass ? in.dl(ro + i) : in.qd(ro + i);
         }
         T wa[3], va[3], c[3];
         wa[0] = rd[0] + g3[0] * rd[2];
@@ -460,7 +463,7 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
       }
       if (dyn) {
         // h^2 Ad(E_0a) xi_dot, folded into sl (X_j = X_p + sl + h^2 ad(V_p) sq)
-        T r1 = in.qd(qo + 3), r2 = in.qd(qo + 4), r3 = in.qd(qo + 5);
+        T r1 = in.qd(ro), r2 = in.qd(ro + 1), r3 = in.qd(ro + 2);
         T wd[3], wa[3], vd[3], c0[3], c1v[3], pd[3];
         // Gdot rdot = r2 * d(g2)/dt + r3 * d(g3)/dt,  d(g2)/dt = r1 (0,-s1,c1),  d(g3)/dt = r1 (0,-c1 c2,-s1 c2) + r2 (c2, s1 s2, -c1 s2)
         wd[0] = r3 * (r2 * c2);
@@ -469,7 +472,7 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         wa[0] = r1 + g3[0] * r3;
         wa[1] = g2[1] * r2 + g3[1] * r3;
         wa[2] = g2[2] * r2 + g3[2] * r3;
-        for (int i = 0; i < 3; ++i) pd[i] = in.qd(qo + i);
+        for (int i = 0; i < 3; ++i) pd[i] = trans ? in.qd(qo + i) : T(0.0);
         cross3(pd, wa, c0);
         cross3(pq, wd, c1v);
         for (int i = 0; i < 3; ++i) vd[i] = c0[i] + c1v[i];
@@ -479,13 +482,15 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         cross3(pa, w, pw);
         for (int i = 0; i < 3; ++i) { sl[i] = sl[i] + h2 * w[i]; sl[3 + i] = sl[3 + i] + h2 * (v[i] + pw[i]); }
       }
-    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
+    } else if (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP)) {
+      const bool trans = jt == TS_JT_FREE3D_EXP;      // spherical-exp: the rotation alone, q = r, p = 0
+      const int ro = trans ? qo + 3 : qo;
       // q = (p, r): Q = [exp([r]) p; 0 1]   (DH/Joint/JointFree3DExp.cpp:13-103, JointSphericalExp.cpp:22-245).
       // Same structure as the Euler chart above with G replaced by the left Jacobian JL(r) of SO(3):
       // xi = (JL rdot, pdot + p x JL rdot),  xi_dot = (JLdot rdot, pdot x JL rdot + p x JLdot rdot) with
       // JLdot rdot = Bdot (r x rdot) + Cdot r x (r x rdot) + C rdot x (r x rdot)   (B [rdot] rdot = 0).
       T rr[3], pq[3];
-      for (int i = 0; i < 3; ++i) { pq[i] = in.q(qo + i); rr[i] = in.q(qo + 3 + i); }
+      for (int i = 0; i < 3; ++i) { pq[i] = trans ? in.q(qo + i) : T(0.0); rr[i] = in.q(ro + i); }
       T t2 = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2], cA, cB, cC, dB, dC;
       so3_coefs(t2, cA, cB, cC, dB, dC);
       T Rq[9], t[3];
@@ -496,8 +501,8 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
       for (int pass = 0; pass < (dyn ? 2 : 1); ++pass) {
         T rd[3], pd[3];
         for (int i = 0; i < 3; ++i) {
-          pd[i] = pass ? in.dl(qo + i) : in.qd(qo + i);
-          rd[i] = pass ? in.dl(qo + 3 + i) : in.qd(qo + 3 + i);
+          pd[i] = trans ? (pass ? in.dl(qo + i) : in.qd(qo + i)) : T(0.0);
+          rd[i] = pass ? in.dl(ro + i) : in.qd(ro + i);
         }
         T wa[3], va[3], c[3];
         so3_jac_mul(rr, cB, cC, rd, wa);
@@ -512,7 +517,7 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
       }
       if (dyn) {
         T rd[3], pd[3], wa[3], wd[3], c1[3], c2[3], c3[3], vd[3], c0[3], c1v[3];
-        for (int i = 0; i < 3; ++i) { pd[i] = in.qd(qo + i); rd[i] = in.qd(qo + 3 + i); }
+        for (int i = 0; i < 3; ++i) { pd[i] = trans ? in.qd(qo + i) : T(0.0); rd[i] = in.qd(ro + i); }
         so3_jac_mul(rr, cB, cC, rd, wa);
         T rdr = 2.0 * (rr[0] * rd[0] + rr[1] * rd[1] + rr[2] * rd[2]);     // d|r|^2/dt
         cross3(rr, rd, c1);
@@ -1102,18 +1107,16 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
     } else if (jt == TS_JT_PRISMATIC) g[qo] = dot3(a0, fj);
     else if (jt == TS_JT_PLANAR) { g[qo] = dot3(a0, fj); g[qo + 1] = dot3(a1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { g[qo] = fj[0]; g[qo + 1] = fj[1]; g[qo + 2] = fj[2]; }
-    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
+    else if ((KT_FREE3D && (jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER)) ||
+             (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP))) {
+      const int nt = (jt == TS_JT_FREE3D_EULER || jt == TS_JT_FREE3D_EXP) ? 3 : 0;
+      const int ro = qo + nt;
       T tax[3][3], rax[3][3], pf[3], t[3];
-      euler_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
+      if (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP)) exp_world_axes(R0, in.q(ro), in.q(ro + 1), in.q(ro + 2), tax, rax);
+      else euler_world_axes(R0, in.q(ro), in.q(ro + 1), in.q(ro + 2), tax, rax);
       cross3(p0, A + 3, pf);             // moment about the joint origin
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
-      for (int i = 0; i < 3; ++i) { g[qo + i] = dot3(tax[i], A + 3); g[qo + 3 + i] = dot3(rax[i], t); }
-    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
-      T tax[3][3], rax[3][3], pf[3], t[3];
-      exp_world_axes(R0, in.q(qo + 3), in.q(qo + 4), in.q(qo + 5), tax, rax);
-      cross3(p0, A + 3, pf);             // moment about the joint origin
-      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
-      for (int i = 0; i < 3; ++i) { g[qo + i] = dot3(tax[i], A + 3); g[qo + 3 + i] = dot3(rax[i], t); }
+      for (int i = 0; i < 3; ++i) { if (nt) g[qo + i] = dot3(tax[i], A + 3); g[ro + i] = dot3(rax[i], t); }
     }
     // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
     const double damp = jd[KJ_DAMP], lo = jd[KJ_LIMLO], hi = jd[KJ_LIMHI], lk = jd[KJ_LIMK];
@@ -1403,20 +1406,16 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
       cross3(p0, Sk, Sk + 3);
     } else if (jt == TS_JT_PRISMATIC) mv3(R0, jd + KJ_AX0, Sk + 3);
     else if (jt == TS_JT_PLANAR) mv3(R0, loc == 0 ? jd + KJ_AX0 : jd + KJ_AX1, Sk + 3);
-    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
+    else if ((KT_FREE3D && (jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER)) ||
+             (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP))) {
+      const int nt = (jt == TS_JT_FREE3D_EULER || jt == TS_JT_FREE3D_EXP) ? 3 : 0;     // translational coordinates first
+      const int ro = ji[2] + nt;
       double tax[3][3], rax[3][3];
-      euler_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
-      if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
+      if (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP)) exp_world_axes(R0, qv[ro], qv[ro + 1], qv[ro + 2], tax, rax);
+      else euler_world_axes(R0, qv[ro], qv[ro + 1], qv[ro + 2], tax, rax);
+      if (loc < nt) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
       else {
-        for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - 3][i];
-        cross3(p0, Sk, Sk + 3);
-      }
-    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
-      double tax[3][3], rax[3][3];
-      exp_world_axes(R0, qv[ji[2] + 3], qv[ji[2] + 4], qv[ji[2] + 5], tax, rax);
-      if (loc < 3) { for (int i = 0; i < 3; ++i) Sk[3 + i] = tax[loc][i]; }
-      else {
-        for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - 3][i];
+        for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - nt][i];
         cross3(p0, Sk, Sk + 3);
       }
     } else { for (int i = 0; i < 3; ++i) Sk[3 + i] = R0[3 * i + loc]; }
@@ -1457,18 +1456,16 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
     } else if (jt == TS_JT_PRISMATIC) Mcol[qo] = dot3(jd + KJ_AX0, fj);
     else if (jt == TS_JT_PLANAR) { Mcol[qo] = dot3(jd + KJ_AX0, fj); Mcol[qo + 1] = dot3(jd + KJ_AX1, fj); }
     else if (jt == TS_JT_TRANSLATIONAL) { Mcol[qo] = fj[0]; Mcol[qo + 1] = fj[1]; Mcol[qo + 2] = fj[2]; }
-    else if (KT_FREE3D && jt == TS_JT_FREE3D_EULER) {
+    else if ((KT_FREE3D && (jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER)) ||
+             (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP))) {
+      const int nt = (jt == TS_JT_FREE3D_EULER || jt == TS_JT_FREE3D_EXP) ? 3 : 0;
+      const int ro = qo + nt;
       double tax[3][3], rax[3][3], pf[3], t[3];
-      euler_world_axes(R0, qv[qo + 3], qv[qo + 4], qv[qo + 5], tax, rax);
+      if (KT_EXP3D && (jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP)) exp_world_axes(R0, qv[ro], qv[ro + 1], qv[ro + 2], tax, rax);
+      else euler_world_axes(R0, qv[ro], qv[ro + 1], qv[ro + 2], tax, rax);
       cross3(p0, A + 3, pf);
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
-      for (int i = 0; i < 3; ++i) { Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[qo + 3 + i] = dot3(rax[i], t); }
-    } else if (KT_EXP3D && jt == TS_JT_FREE3D_EXP) {
-      double tax[3][3], rax[3][3], pf[3], t[3];
-      exp_world_axes(R0, qv[qo + 3], qv[qo + 4], qv[qo + 5], tax, rax);
-      cross3(p0, A + 3, pf);
-      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
-      for (int i = 0; i < 3; ++i) { Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[qo + 3 + i] = dot3(rax[i], t); }
+      for (int i = 0; i < 3; ++i) { if (nt) Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[ro + i] = dot3(rax[i], t); }
     }
     if (par >= 0) for (int i = 0; i < 6; ++i) Wm[par][i] += A[i];
   }

@@ -107,6 +107,7 @@ class Simulation:
         z = lambda: torch.zeros((self.batch, self.ndof_r), dtype=torch.float64, device=self.device)
         self._q_init, self._qd_init = z(), z()
         self._q, self._qd = z(), z()
+        self._q_prev, self._qd_prev = z(), z()       # state one step back (BDF2: Simulation::_q_his of the reference)
         self._u = torch.zeros((self.batch, self.ndof_u), dtype=torch.float64, device=self.device)
         self._reset_done = False
         self._grad = False
@@ -283,6 +284,9 @@ class Simulation:
     def reset(self, backward_flag: bool = False, backward_design_params_flag: bool = False):
         if backward_design_params_flag:
             raise TactileSimError("design-parameter gradients are out of scope of the B200 path")
+        if backward_flag and self.core.integrator != 0:
+            raise TactileSimError("gradients exist for integrator BDF1 only on the B200 path (options.integrator is "
+                                  + str(self.options.integrator) + ")")
         self._q = self._q_init.clone()
         self._qd = self._qd_init.clone()
         self._grad = bool(backward_flag)
@@ -324,7 +328,8 @@ class Simulation:
         trows = rows if tac_rows is None else tac_rows
         u = u.contiguous()
         fwd = self.core.forward(self._q, self._qd, u, T, grad=self._grad, var_rows=rows, tac_rows=trows,
-                                want_var=want_outputs, want_tactile=want_outputs, want_traj=want_outputs or self._grad)
+                                want_var=want_outputs, want_tactile=want_outputs, want_traj=want_outputs or self._grad,
+                                q_prev=self._q_prev, qd_prev=self._qd_prev, steps_done=self._nsteps)
         if self._grad:
             self._chunks.append(_Chunk(T, u, fwd, rows, self._nsteps))
             self._current_backward_step += T

@@ -41,12 +41,14 @@ import numpy as np
 
 # joint types (values are shared with csrc/scene_layout.h)
 JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL, JT_FREE3D_EULER, JT_FREE3D_EXP = 0, 1, 2, 3, 4, 5, 6
+JT_SPHERICAL_EULER, JT_SPHERICAL_EXP = 7, 8
 JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3, JT_FREE3D_EULER: 6,
-              JT_FREE3D_EXP: 6}
+              JT_FREE3D_EXP: 6, JT_SPHERICAL_EULER: 3, JT_SPHERICAL_EXP: 3}
 # "free3d" is the XYZ-Euler chart in the reference too (DH/Simulation_Constructor.cpp:483-484)
 JOINT_TYPES = {"fixed": JT_FIXED, "revolute": JT_REVOLUTE, "prismatic": JT_PRISMATIC,
                "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL,
-               "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER, "free3d-exp": JT_FREE3D_EXP}
+               "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER, "free3d-exp": JT_FREE3D_EXP,
+               "spherical": JT_SPHERICAL_EULER, "spherical-euler": JT_SPHERICAL_EULER, "spherical-exp": JT_SPHERICAL_EXP}
 # time integrators (DH/Simulation.cpp:1076-1092); codes shared with csrc/scene_layout.h
 INTEGRATORS = {"BDF1": 0, "BDF2": 1, "SDIRK2": 2}
 # body shapes

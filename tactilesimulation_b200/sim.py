@@ -51,6 +51,7 @@ class BatchedSim:
         self.nj, self.ndof_r, self.ndof_m, self.ndof_u, self.ndof_var, self.ndof_tactile, self.n_markers, \
             self.tape_doubles = (int(x) for x in sizes[:8])
         self.cmask_words = int(sizes[_lib.CMASK_WORDS])
+        self.integrator = int(sizes[_lib.INTEGRATOR])      # _lib.INT_BDF1 / INT_BDF2 / INT_SDIRK2
         self.h = float(self.dbuf[0])
         self.lanes = None
         if lanes is not None:
@@ -100,8 +101,11 @@ class BatchedSim:
     # ------------------------------------------------------------------ kernels
     def forward(self, q: torch.Tensor, qd: torch.Tensor, u: torch.Tensor, T: int, grad: bool = False,
                 var_rows=None, tac_rows=None, want_var=True, want_tactile=True, want_status=False,
-                want_contacts=False, want_traj=True):
+                want_contacts=False, want_traj=True, q_prev: Optional[torch.Tensor] = None,
+                qd_prev: Optional[torch.Tensor] = None, steps_done: int = 0):
         """Advance (q, qd) [B,n] in place by T steps.  u: [T,B,nu], or [B,nu] held for all T steps.
+        BDF2 scenes (tsim_forward_multistep): q_prev, qd_prev [B,n] hold the state one step back (in/out) and
+        steps_done the steps taken since reset; omit them for a whole trajectory from reset in one call.
         Returns a dict with q_traj, qd_traj [T,B,n], var [rows,B,nvar], tactile [rows,B,ntac] and, when
         ``grad``, the adjoint tape [T,B,3 n^2 + nu] (H, G0, G1 row-major, then d f_r/d u per control)."""
         B, n, nu = q.shape[0], self.ndof_r, self.ndof_u
@@ -113,6 +117,10 @@ class BatchedSim:
         else:
             self._chk(u, (T, B, nu), "u")
             ustride = B * nu
+        self._chk(q_prev, (B, n), "q_prev")
+        self._chk(qd_prev, (B, n), "qd_prev")
+        if grad and self.integrator != _lib.INT_BDF1:
+            raise _lib.TactileSimError("the adjoint exists for BDF1 scenes only (as Simulation::backward of the reference)")
         dev = self.device
         out = {}
         need_traj = want_traj or grad
@@ -130,11 +138,11 @@ class BatchedSim:
         out["marker_body"] = (torch.full((ntr, B, self.n_markers), -1, dtype=torch.int32, device=dev)
                               if (want_contacts and out["tactile"] is not None) else None)
         with torch.cuda.device(dev):
-            _lib.check(self.lib.tsim_forward(self.handle, B, T, _ptr(q), _ptr(qd), _ptr(u), ustride,
-                                             _ptr(out["q_traj"]), _ptr(out["qd_traj"]), _ptr(out["var"]), _ptr(vr),
-                                             _ptr(out["tactile"]), _ptr(tr), _ptr(out["tape"]), _ptr(out["status"]),
-                                             _ptr(out["contact_masks"]), _ptr(out["marker_body"]), self._stream()),
-                       self.lib)
+            _lib.check(self.lib.tsim_forward_multistep(
+                self.handle, B, T, _ptr(q), _ptr(qd), _ptr(q_prev), _ptr(qd_prev), int(steps_done), _ptr(u), ustride,
+                _ptr(out["q_traj"]), _ptr(out["qd_traj"]), _ptr(out["var"]), _ptr(vr), _ptr(out["tactile"]), _ptr(tr),
+                _ptr(out["tape"]), _ptr(out["status"]), _ptr(out["contact_masks"]), _ptr(out["marker_body"]),
+                self._stream()), self.lib)
         out["_keep"] = (vr, tr)
         return out
 

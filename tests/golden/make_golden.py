@@ -297,6 +297,119 @@ def rolling_ball_case():
                 frames200=np.array(frames200), tactile200_idx=bi, tactile200_val=bv)
 
 
+def integrators_case(T, seed):
+    """The TactilePush scene under the other two integrators of DH/Simulation.cpp:1076-1092 (forward only: the
+    reference has no adjoint for them on this path either): options.integrator = BDF2 (SDIRK2 start-up step) and
+    SDIRK2, same inputs as pusher13x10_episodic_s0.  The blob is the BDF1 one; only header slot 14 differs."""
+    src = os.path.join(ASSETS, "pusher.xml")
+    out = {}
+    for name in ("BDF2", "SDIRK2"):
+        xml = os.path.join(ASSETS, "pusher_%s.xml" % name.lower())
+        txt = open(src).read()
+        assert 'integrator="BDF1"' in txt
+        open(xml, "w").write(txt.replace('integrator="BDF1"', 'integrator="%s"' % name))
+        sim = redmax_py.Simulation(xml)
+        probe = redmax_probe.ProbeSimulation(xml)
+        assert sim.options.integrator == name
+        q0, u = make_inputs(sim, T, seed)
+        for s in (sim, probe):
+            s.set_state_init(q0, np.zeros(sim.ndof_r))
+            s.reset(False)
+        q, qd, var, tac, gp = [], [], [], [], []
+        for t in range(T):
+            for s in (sim, probe):
+                s.set_u(u[t])
+                s.forward(1)
+            q.append(sim.get_q().copy())
+            qd.append(sim.get_qdot().copy())
+            var.append(sim.get_variables().copy())
+            tac.append(sim.get_tactile_force_vector().copy())
+            gp.append(probe.contact_sets()["gp"][0])
+        sc = compile_scene(xml)
+        assert sc.integrator == name
+        out.update({"q_" + name: np.array(q), "qd_" + name: np.array(qd), "var_" + name: np.array(var),
+                    "tactile_" + name: np.array(tac), "gp_ids_" + name: pad_ids(gp, 66)})
+    ib, db = compile_scene(src).pack()
+    out.update(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(len(q0)), u=u)
+    return out
+
+
+# a two-link arm on spherical joints (our own synthetic scene: no reference asset uses these joint types): ground
+# contact at the tip, a 4x4 pad on the upper link pressed by the lower link, one end-effector, six force motors
+SPHERICAL_TEMPLATE = '''<redmax model="spherical-chain">
+    <option integrator="{integ}" timestep="5e-3" unit="m-kg" gravity="0. 0. -9.8"/>
+    <ground pos="0 0 0" normal="0 0 1"/>
+    <default>
+        <ground_contact kn="2e3" kt="10" mu="0.8" damping="3"/>
+        <tactile kn="50" kt="4" mu="1.0" damping="2"/>
+        <motor ctrl="force" ctrl_range="-0.3 0.3"/>
+    </default>
+    <robot>
+        <link name="upper">
+            <joint name="shoulder" type="spherical-euler" pos="0 0 0.3" quat="1 0 0 0" damping="0.02"/>
+            <body name="upper_body" type="cuboid" size="0.04 0.04 0.2" pos="0 0 -0.1" quat="1 0 0 0" density="800." general_contact_resolution="2 2 2"/>
+            <link name="lower">
+                <joint name="elbow" type="{elbow}" pos="0 0 -0.2" quat="1 0 0 0" damping="0.01"/>
+                <body name="lower_body" type="cuboid" size="0.03 0.03 0.15" pos="0 0 -0.06" quat="1 0 0 0" density="800." general_contact_resolution="3 3 3"/>
+            </link>
+        </link>
+    </robot>
+    <actuator>
+        <motor joint="shoulder" ctrl="force"/>
+        <motor joint="elbow" ctrl="force"/>
+    </actuator>
+    <sensor>
+        <tactile body="upper_body" name="pad" type="rect_array" rect_pos0="-0.015 -0.015 -0.1" rect_pos1="0.015 0.015 -0.1" axis0="1 0 0" axis1="0 1 0" resolution="4 4"/>
+    </sensor>
+    <contact>
+        <ground_contact body="lower_body"/>
+    </contact>
+    <variable>
+        <endeffector joint="elbow" pos="0 0 -0.135" name="tip"/>
+    </variable>
+</redmax>
+'''
+
+
+def spherical_xml(name, integ, elbow):
+    d = os.path.join(ROOT, "oracle", "_ref", "assets", "synthetic")
+    os.makedirs(d, exist_ok=True)
+    xml = os.path.join(d, name + ".xml")
+    open(xml, "w").write(SPHERICAL_TEMPLATE.format(integ=integ, elbow=elbow))
+    return xml
+
+
+def spherical_euler_case(T, seed):
+    """spherical-euler joints (DH/Joint/JointSphericalEuler.cpp), BDF1, forward + backward()."""
+    xml = spherical_xml("spherical_euler_bdf1", "BDF1", "spherical-euler")
+    rng = np.random.default_rng(seed)
+    return multi_case(xml, np.array([0.3, -0.2, 0.1, 0.2, 0.4, -0.3]), rng.uniform(-1, 1, (T, 6)), seed)
+
+
+def spherical_exp_case(T, seed):
+    """spherical-euler shoulder + spherical-exp elbow (DH/Joint/JointSphericalExp.cpp) under BDF2, forward only."""
+    xml = spherical_xml("spherical_exp_bdf2", "BDF2", "spherical-exp")
+    sim, probe, sc = redmax_py.Simulation(xml), redmax_probe.ProbeSimulation(xml), compile_scene(xml)
+    rng = np.random.default_rng(seed)
+    q0, u = np.array([0.3, -0.2, 0.1, 0.2, 0.4, -0.3]), rng.uniform(-1, 1, (T, 6))
+    for s in (sim, probe):
+        s.set_state_init(q0, np.zeros(6))
+        s.reset(False)
+    q, qd, var, tac, ground = [], [], [], [], []
+    for t in range(T):
+        for s in (sim, probe):
+            s.set_u(u[t])
+            s.forward(1)
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        var.append(sim.get_variables().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+        ground.append(probe.contact_sets()["ground"][0])
+    ib, db = sc.pack()
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(6), u=u, q=np.array(q), qd=np.array(qd), var=np.array(var),
+                tactile=np.array(tac), ground_ids=pad_ids(ground, len(sc.contact_points[1])))
+
+
 def main():
     x13 = os.path.join(ASSETS, "pusher.xml")
     x32 = os.path.join(ASSETS, "pusher_32x13.xml")
@@ -309,6 +422,9 @@ def main():
         "insertion_episodic_s0": lambda: insertion_case(60, 0),
         "stable_grasp_episodic_s0": lambda: stable_grasp_case(50, 0),
         "rollingball_bdf2_s0": rolling_ball_case,
+        "pusher13x10_integrators_s0": lambda: integrators_case(40, 0),
+        "spherical_euler_bdf1_s0": lambda: spherical_euler_case(60, 0),
+        "spherical_exp_bdf2_s0": lambda: spherical_exp_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
     if only:

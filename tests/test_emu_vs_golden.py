@@ -181,3 +181,61 @@ def test_emulated_rolling_ball_matches_reference():
     big = emu_lib.forward(ib, db, g["q0"], g["qd0"], u, tac_row=rows, want_masks=False)
     assert np.array_equal(big["q"], out["q"])
     rb.check_full_resolution_frames(big["tactile"][:, 0], g)
+
+
+@pytest.mark.parametrize("name,code", [("BDF2", 1), ("SDIRK2", 2)])
+def test_emulated_other_integrators_match_reference(name, code):
+    """options.integrator = BDF2 / SDIRK2 (DH/Simulation.cpp:1076-1092, 1353-1564) on the TactilePush scene, forward only."""
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_integrators_s0.npz"))
+    ib = g["ibuf"].copy()
+    ib[14] = code
+    T = g["u"].shape[0]
+    out = emu_lib.forward(ib, g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :])
+    assert int((out["status"] >> 16).max()) == 0
+    assert int((g["gp_ids_" + name] >= 0).sum()) > 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q_" + name][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd_" + name][t]) <= 1e-9, t
+        assert rel_err(out["var"][t, 0], g["var_" + name][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile_" + name][t]) <= 1e-8, t
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, 1:4]) == [int(x) for x in g["gp_ids_" + name][t] if x >= 0], t
+
+
+def test_emulated_spherical_euler_chain_matches_reference():
+    """spherical-euler joints (DH/Joint/JointSphericalEuler.cpp) in a two-link arm of our own (no reference asset uses
+    them): ground contact at the tip, a pad pressed by the neighbouring link, BDF1 forward + Simulation::backward."""
+    from tests.blob_scene import scene_from_blob
+    from tests.multi_force import expected_words
+    g = np.load(os.path.join(GOLDEN, "spherical_euler_bdf1_s0.npz"))
+    sc = scene_from_blob(g["ibuf"], g["dbuf"])
+    T = g["u"].shape[0]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    assert float(np.abs(g["tactile"]).max()) > 0 and int((g["ground_ids_f"] >= 0).sum()) > 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["var"][t, 0], g["var"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert np.array_equal(out["cmask"][t, 0].astype(np.uint64), expected_words(sc, g["ground_ids_f"][t], g["gp_ids_f"][t])), t
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], g["df_dq"][:, None, :],
+                          g["df_dvar"][:, None, :], g["df_dtactile"][:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_spherical_exp_chain_matches_reference():
+    """spherical-exp elbow (DH/Joint/JointSphericalExp.cpp) under BDF2, forward only (kernel variant 17)."""
+    g = np.load(os.path.join(GOLDEN, "spherical_exp_bdf2_s0.npz"))
+    T = g["u"].shape[0]
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :])
+    assert int((out["status"] >> 16).max()) == 0
+    assert int((g["ground_ids"] >= 0).sum()) > 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["var"][t, 0], g["var"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0]) == [int(x) for x in g["ground_ids"][t] if x >= 0], t

@@ -146,7 +146,8 @@ def test_batched_line_search_equals_sequential_search():
 
 
 MULTI = {"dclaw_episodic_s0": (10, 90, 9, 12, 2718), "insertion_episodic_s0": (12, 78, 6, 0, 780),
-         "stable_grasp_episodic_s0": (12, 126, 6, 0, 780)}
+         "stable_grasp_episodic_s0": (12, 126, 6, 0, 780),
+         "spherical_euler_bdf1_s0": (6, 12, 6, 3, 48)}        # our own two-link arm on spherical-euler joints
 
 
 @pytest.mark.parametrize("lanes", [16, 32])
@@ -220,3 +221,111 @@ def test_newton_cap_option_only_touches_steps_that_hit_it():
     assert np.array_equal(qa[:, easy], qb[:, easy]) and np.array_equal(sa[:, easy], sb[:, easy])
     hit = (sb & 255) == 25
     assert ((sb[hit] >> 16) & 1).all()
+
+
+@pytest.mark.parametrize("lanes", [16, 32])
+def test_rolling_ball_matches_reference(lanes):
+    """examples/RollingBallExp (BASELINE configs[0]): BDF2 with the SDIRK2 start-up step, free3d-exp ball, sphere SDF,
+    2168 sampled pad points, kernel variant 17; tolerances in tests/rolling_ball.py.  Three identical environments,
+    then the same trajectory in chunks through the compat Simulation (forward(1) per step, as test_sim_speed.py does)."""
+    from tests import rolling_ball as rb
+    from tactilesimulation_b200.sim import BatchedSim
+    g = np.load(os.path.join(GOLDEN, "rollingball_bdf2_s0.npz"))
+    sim = BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0", lanes=lanes)
+    assert sim.integrator == 1
+    dev = sim.device
+    T, B = g["u"].shape[0], 3
+    rows = rb.tactile_rows(T, int(g["tactile_every"]))
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.tensor(np.tile(g["qd0"], (B, 1)), device=dev)
+    u = torch.tensor(np.tile(g["u"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    out = sim.forward(q, qd, u, T, tac_rows=rows, want_status=True, want_contacts=True)
+    torch.cuda.synchronize()
+    qt, qdt, st = out["q_traj"].cpu().numpy(), out["qd_traj"].cpu().numpy(), out["status"].cpu().numpy()
+    cm, tac, mb = out["contact_masks"].cpu().numpy(), out["tactile"].cpu().numpy(), out["marker_body"].cpu().numpy()
+    for e in range(B):
+        rb.check_trajectory(qt[:, e], qdt[:, e], st[:, e], cm[:, e], tac[:, e], mb[:, e], g)
+    with pytest.raises(Exception):
+        sim.forward(q, qd, u, 2, grad=True)          # no adjoint for BDF2, as in the reference
+    # chunked through the multistep state: bit-identical to the single call
+    q2 = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd2 = torch.zeros_like(q2)
+    qp, qdp = torch.zeros_like(q2), torch.zeros_like(q2)
+    done = 0
+    for chunk in (1, 4, 45):
+        o = sim.forward(q2, qd2, u[done:done + chunk].contiguous(), chunk, want_tactile=False, q_prev=qp, qd_prev=qdp,
+                        steps_done=done)
+        assert torch.equal(o["q_traj"], out["q_traj"][done:done + chunk])
+        done += chunk
+
+
+def test_rolling_ball_full_resolution_through_compat_simulation():
+    """The real 200x200 sensor (120 000 tactile values per frame) driven like examples/RollingBallExp/test_sim_speed.py:
+    set_u + forward(1) per step on the drop-in Simulation, tactile read at four steps."""
+    from tests import rolling_ball as rb
+    from tactilesimulation_b200.layout import scene_from_blob
+    from tactilesimulation_b200.redmax import Simulation
+    g = np.load(os.path.join(GOLDEN, "rollingball_bdf2_s0.npz"))
+    ib, db = rb.full_resolution_blob(g["ibuf"], g["dbuf"])
+    sim = Simulation(scene_from_blob(ib, db))
+    assert (sim.ndof_r, sim.ndof_u, sim.ndof_tactile, sim.options.integrator) == (9, 3, 120000, "BDF2")
+    with pytest.raises(Exception):
+        sim.reset(backward_flag=True)
+    sim.reset(backward_flag=False)
+    frames = [int(f) for f in g["frames200"]]
+    got = []
+    for t in range(frames[-1] + 1):
+        sim.set_u(g["u"][t])
+        sim.forward(1, verbose=False, test_derivatives=False)
+        if t in frames:
+            got.append(sim.get_tactile_force_vector().copy())
+            assert rel_err(sim.get_q(), g["q"][t]) <= rb.TOL_STATE
+    rb.check_full_resolution_frames(np.array(got), g)
+
+
+@pytest.mark.parametrize("name,code", [("BDF2", 1), ("SDIRK2", 2)])
+def test_other_integrators_match_reference(name, code):
+    """options.integrator = BDF2 / SDIRK2 on the TactilePush scene (kernel variant 17), forward only."""
+    from tactilesimulation_b200.sim import BatchedSim
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_integrators_s0.npz"))
+    ib = g["ibuf"].copy()
+    ib[14] = code
+    sim = BatchedSim((ib, g["dbuf"]), device="cuda:0")
+    dev = sim.device
+    T, B = g["u"].shape[0], 2
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.zeros_like(q)
+    u = torch.tensor(np.tile(g["u"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    out = sim.forward(q, qd, u, T, want_status=True, want_contacts=True)
+    qt, qdt, tac = out["q_traj"].cpu().numpy(), out["qd_traj"].cpu().numpy(), out["tactile"].cpu().numpy()
+    cm = out["contact_masks"].cpu().numpy()
+    assert int((out["status"] >> 16).max().item()) == 0
+    for e in range(B):
+        for t in range(T):
+            assert rel_err(qt[t, e], g["q_" + name][t]) <= 1e-9, (t, e)
+            assert rel_err(qdt[t, e], g["qd_" + name][t]) <= 1e-9, (t, e)
+            assert rel_err(tac[t, e], g["tactile_" + name][t]) <= 1e-8, (t, e)
+            assert _ids(cm[t, e, 1:4]) == [int(x) for x in g["gp_ids_" + name][t] if x >= 0], (t, e)
+
+
+def test_spherical_exp_chain_matches_reference():
+    """spherical-euler shoulder + spherical-exp elbow under BDF2 (kernel variant 17), forward only."""
+    from tactilesimulation_b200.sim import BatchedSim
+    g = np.load(os.path.join(GOLDEN, "spherical_exp_bdf2_s0.npz"))
+    sim = BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0")
+    dev = sim.device
+    T, B = g["u"].shape[0], 2
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.zeros_like(q)
+    u = torch.tensor(np.tile(g["u"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    out = sim.forward(q, qd, u, T, want_status=True, want_contacts=True)
+    qt, qdt, tac = out["q_traj"].cpu().numpy(), out["qd_traj"].cpu().numpy(), out["tactile"].cpu().numpy()
+    var, cm = out["var"].cpu().numpy(), out["contact_masks"].cpu().numpy()
+    assert int((out["status"] >> 16).max().item()) == 0
+    for e in range(B):
+        for t in range(T):
+            assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
+            assert rel_err(qdt[t, e], g["qd"][t]) <= 1e-9, (t, e)
+            assert rel_err(var[t, e], g["var"][t]) <= 1e-9, (t, e)
+            assert rel_err(tac[t, e], g["tactile"][t]) <= 1e-8, (t, e)
+            assert _ids(cm[t, e]) == [int(x) for x in g["ground_ids"][t] if x >= 0], (t, e)

@@ -1,7 +1,8 @@
 """BASELINE configs[0] -- RollingBallExp test_sim_speed.py, 1 env, CPU DiffRedMax -- is the reference's own
 CPU-runnable case: it is run on the UNMODIFIED reference (oracle/_ref, built by oracle/build_ref.sh) as a plumbing
-check of the reference arm.  The B200 path does not implement its scene (BDF2, sphere SDF, free3d-exp joint) and
-must say so by name instead of falling back."""
+check of the reference arm.  The B200 path runs the same scene on kernel variant 17 (BDF2 + SDIRK2 start-up, sphere SDF,
+free3d-exp joint: tests/test_emu_vs_golden.py, tests/test_gpu_parity.py); what it still does not implement it must
+reject by name instead of falling back."""
 import os
 
 import numpy as np
@@ -28,8 +29,25 @@ def test_rolling_ball_speed_test_runs_on_the_reference():
 
 
 @needs_ref
-def test_b200_path_rejects_the_rolling_ball_scene_by_name():
+def test_b200_scene_compiler_reads_the_rolling_ball_scene():
+    """The native XML compiler on the reference's own file; and the fixture helper that rebuilds the 200x200 scene from
+    the 40x40 blob (used by the GPU tests, where the XML does not exist) gives exactly the compiled scene."""
+    from tactilesimulation_b200.scene import compile_scene
+    from tests import rolling_ball as rb
+    sc = compile_scene(XML)
+    assert (sc.ndof_r, sc.ndof_u, sc.ndof_tactile, sc.integrator) == (9, 3, 120000, "BDF2")
+    ib, db = sc.pack()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rollingball_bdf2_s0.npz"))
+    ib2, db2 = rb.full_resolution_blob(g["ibuf"], g["dbuf"])
+    assert np.array_equal(ib, ib2) and np.allclose(db, db2, rtol=0, atol=1e-15)
+
+
+def test_b200_path_rejects_unsupported_features_by_name(tmp_path):
     from tactilesimulation_b200.scene import SceneError, compile_scene
+    xml = tmp_path / "capsule.xml"
+    xml.write_text('''<redmax model="x"><option integrator="BDF1" timestep="5e-3" gravity="0 0 -9.8"/>
+<robot><link name="a"><joint name="j" type="free2d" pos="0 0 0" quat="1 0 0 0"/>
+<body name="b" type="capsule" pos="0 0 0" quat="1 0 0 0" radius="0.1" length="0.2" density="1"/></link></robot></redmax>''')
     with pytest.raises(SceneError) as e:
-        compile_scene(XML).pack()
+        compile_scene(str(xml))
     assert "not supported" in str(e.value)

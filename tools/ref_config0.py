@@ -1,6 +1,6 @@
 """BASELINE configs[0]: RollingBallExp test_sim_speed.py logic (R/examples/RollingBallExp/test_sim_speed.py:36-104) on
 the UNMODIFIED reference built by oracle/build_ref.sh -- 1 env, CPU, no GPU: a plumbing check of the reference
-arm (the scene uses BDF2, a sphere and a free3d-exp joint, which the B200 path rejects by name).
+arm (the B200 path runs the same scene on kernel variant 17: tools/rolling_ball_probe.py is the GPU counterpart).
 Usage: python tools/ref_config0.py   -> prints one JSON line {"fps": ..., "steps": 350, ...}"""
 import json
 import os
