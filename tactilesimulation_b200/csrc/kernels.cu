@@ -156,6 +156,10 @@ struct DevTile {
 #ifndef TS_BLOCK
 #define TS_BLOCK 224
 #endif
+// resident blocks per SM the launch bounds and the shared-memory carve-out are sized for
+#ifndef TS_BPS
+#define TS_BPS 1
+#endif
 
 // stage the scene blob in shared memory (doubles first, then ints, 8-byte aligned)
 // nd = doubles BEFORE the marker table; the markers (the bulk of a scene with dense sensors) stay in global memory
@@ -202,7 +206,7 @@ __device__ __forceinline__ DevTile<LPE> make_tile() {
 }
 
 template <int LPE>
-__global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(TS_BLOCK) fwd_kernel(const int* ib, int ni, co
 
 #if !KT_MULTISTEP     // variant 17 is forward-only (no adjoint of BDF2 / SDIRK2, sphere tactile VJP not written)
 template <int LPE>
-__global__ void __launch_bounds__(TS_BLOCK) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
@@ -290,7 +294,7 @@ static int prep(K kern, size_t smem) {
   // one block per SM: ask for no more shared memory than the block uses, the rest of the 256 KB is L1
   // for the per-lane tangents (local memory)
 #ifndef TS_NO_CARVEOUT
-  int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
+  int pct = (int)((smem + 1024) * TS_BPS * 100 / (228 * 1024)) + 1;
   if (pct > 100) pct = 100;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
 #endif

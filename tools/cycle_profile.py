@@ -12,7 +12,7 @@ dev = sim.device
 B, T = int(os.environ.get('PB', 4096)), int(os.environ.get('PT', 50))
 nthreads = ((B * 8 + 223) // 224) * 224
 prof = torch.zeros((nthreads, 8), dtype=torch.int64, device=dev)
-sim.lib.tsim_debug_set_prof(ctypes.c_void_p(prof.data_ptr()))
+sim.lib.tsim_debug_set_prof_v8(ctypes.c_void_p(prof.data_ptr()))
 q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
 ut = torch.tensor(u, device=dev)
 for rep in range(3):

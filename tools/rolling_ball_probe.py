@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--B", type=int, nargs="+", default=[256, 1024])
     ap.add_argument("--res", type=int, default=200)
     ap.add_argument("--lanes", type=int, default=16)
+    ap.add_argument("--noise", type=float, default=0.02, help="std of the per-environment perturbation of the x/y pad force")
+    ap.add_argument("--max-newton", type=int, default=0, help="TSIM_OPT_MAX_NEWTON (0 = the reference's cap)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", "rollingball_bdf2_s0.npz"))
     ib, db = rb.full_resolution_blob(g["ibuf"], g["dbuf"], a.res)
@@ -43,12 +45,14 @@ def main():
         print(f"compat Simulation, 1 env, {a.res}x{a.res} markers: time elapsed = {dt:.3f} s, FPS = {T / dt:.1f}", flush=True)
     # (b) batched
     core = BatchedSim((ib, db), "cuda:0", lanes=a.lanes)
+    if a.max_newton:
+        core.set_option(1, a.max_newton)
     dev = core.device
     rows = rb.tactile_rows(T, 5)
     rng = np.random.default_rng(0)
     for B in a.B:
         u = np.tile(g["u"][:, None, :], (1, B, 1))
-        u[:, :, :2] += 0.02 * rng.normal(size=(1, B, 2))
+        u[:, :, :2] += a.noise * rng.normal(size=(1, B, 2))
         ut = torch.tensor(u, device=dev)
         for rep in range(2):
             q = torch.zeros((B, core.ndof_r), dtype=torch.float64, device=dev)
@@ -62,7 +66,8 @@ def main():
             ms = e0.elapsed_time(e1)
             st = out["status"]
             print(f"batched B={B} T={T} tactile every 5 steps ({a.res}x{a.res}): {ms:.1f} ms, {B * T / ms * 1e3:.3e} env-steps/s, "
-                  f"newton mean {(st & 255).double().mean().item():.2f} max {(st & 255).max().item()} flags {(st >> 16).max().item()}", flush=True)
+                  f"newton mean {(st & 255).double().mean().item():.2f} max {(st & 255).max().item()} flags {(st >> 16).max().item()} "
+                  f"steps with >20 iterations {((st & 255) > 20).sum().item()}", flush=True)
             del out
 
 
