@@ -51,11 +51,19 @@
 #define TS_TOC(tl, slot) (tl).acc[slot] += clock64() - ts_t0_
 #define TS_TIC2(tl) const long long ts_t1_ = clock64()
 #define TS_TOC2(tl, slot) (tl).acc[slot] += clock64() - ts_t1_
+#ifdef TS_PROFILE_GP
+#define TS_GPT(tl, slot) do { const long long ts_now_ = clock64(); (tl).acc[slot] += ts_now_ - ts_gp_; ts_gp_ = ts_now_; } while (0)
+#define TS_GPT0() long long ts_gp_ = clock64()
+#endif
 #else
 #define TS_TIC(tl)
 #define TS_TOC(tl, slot)
 #define TS_TIC2(tl)
 #define TS_TOC2(tl, slot)
+#endif
+#ifndef TS_GPT
+#define TS_GPT(tl, slot)
+#define TS_GPT0()
 #endif
 
 // Output streams (tactile field, tape, trajectory) are written once and never re-read by the forward kernel:
@@ -951,7 +959,9 @@ HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* 
 // DH/Force/ForceGeneralPrimitiveContact.cpp:154-229, DH/Body/BodyCuboid.cpp:146-184, BodyCylinder.cpp:105-139,
 // detection d < 0: CollisionDetection.cpp:66-83.
 // Detection is dealt to the lanes of the tile and gathered by ballot.  (A warp-cooperative evaluation of the
-// active points was measured slower on B200 -- register pressure -- and is kept as tools/experiments/*.patch.)
+// active points -- pair kinematics by shuffles, points dealt to the tiles of the warp, xor-tree reduction -- was
+// measured slower on B200 twice: 144 vs 125-140 ms, the pair structs end up in local memory; kept as
+// tools/experiments/warp_cooperative_contacts_v2.patch.)
 template <class Tile, class WK>
 HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
   typedef typename WK::Scalar T;
@@ -967,6 +977,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
     const double* hs = bd2 + KB_HALF;
+    TS_GPT0();
     GpPair<T> P;
     double phv[6];
     body_frame_v(S, W, b1, P.R1v, P.p1v, phv);
@@ -1015,6 +1026,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     }
     unsigned any = 0u;
     for (int i = 0; i < KT_MAXPW; ++i) any |= act[i];
+    TS_GPT(tl, 0);
     if (!any) continue;
     // the tile's own relative kinematics in the frame of body 2 (dual numbers)
     T R2[9], p2[3];
@@ -1029,6 +1041,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
       mv3(P.Q, ph1, P.w1b);
       mv3(P.Q, ph1 + 3, P.v1b);
     }
+    TS_GPT(tl, 1);
     T w1[6], w2[6];          // wrenches on body 1 / body 2, both in body-2 coordinates about its origin
     for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
     for (int wd = 0; wd < KT_MAXPW; ++wd) {
@@ -1042,6 +1055,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     }
     push_wrench(W, j1, R2, p2, w1, -h2);
     push_wrench(W, j2, R2, p2, w2, -h2);
+    TS_GPT(tl, 3);
   }
 }
 
@@ -1148,10 +1162,17 @@ template <class Tile, class WK, class In>
 HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g,
                 double beta) {
   W.beta = beta;
+#ifdef TS_PROFILE_GP      // slots 0, 1, 3 are re-used for the phases INSIDE gp_contacts (detect / pair setup / point forces)
+  kinematics(S, in, W, true);
+  ground_contacts(S, W);
+  { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
+  inward(S, W, in, u, g);
+#else
   { TS_TIC(tl); kinematics(S, in, W, true); TS_TOC(tl, 0); }
   { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
   { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
   { TS_TIC(tl); inward(S, W, in, u, g); TS_TOC(tl, 3); }
+#endif
 }
 
 // ------------------------------------------------------------------ tile policies

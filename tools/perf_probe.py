@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--no-gp", action="store_true", help="timing experiment: drop the pad-box contact force")
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     ap.add_argument("--max-newton", type=int, default=0, help="TSIM_OPT_MAX_NEWTON (0 = the reference's cap)")
+    ap.add_argument("--identical", type=int, default=-1, help="timing experiment: every environment gets the inputs of this one (perfect balance)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
     for lanes in a.lanes:
@@ -65,6 +66,9 @@ def main():
         q0, qd0, u = inputs(g, a.B, a.T, dev)
         if a.zero_u:
             u = torch.zeros_like(u)
+        if a.identical >= 0:
+            q0 = q0[a.identical:a.identical + 1].repeat(a.B, 1).contiguous()
+            u = u[:, a.identical:a.identical + 1].repeat(1, a.B, 1).contiguous()
         for rep in range(a.reps):
             q, qd = q0.clone(), qd0.clone()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
