@@ -60,8 +60,11 @@ int tsim_scene_set_lanes(tsim_scene* scene, int lanes_per_env);
  *   TSIM_OPT_MAX_NEWTON 0 (default): the reference's cap on Newton iterations per step, max(20 ndof_r, max_iter)
  *                      (DH/Simulation.cpp:1155); > 0: a lower cap.  A step that hits the cap is reported as not
  *                      converged in `status`, like in the reference; in a lock-step batch one such step can cost as
- *                      much as a whole trajectory, so throughput-bound users may trade exactness on those steps. */
-enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_N_OPTS };
+ *                      much as a whole trajectory, so throughput-bound users may trade exactness on those steps.
+ *   TSIM_OPT_VJP_PASS  1 (default): tsim_backward pulls the readout cotangents (df_dvar, df_dtactile) back in a pass of
+ *                      its own over all T x B env-steps, spread over the whole GPU, before the reverse sweep (which is
+ *                      sequential per environment); 0: inside the sweep.  Bit-identical results. */
+enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_OPT_VJP_PASS = 2, TSIM_N_OPTS };
 int tsim_scene_set_option(tsim_scene* scene, int key, int value);
 
 /* Advances B environments by T implicit (BDF1/Newton) steps.

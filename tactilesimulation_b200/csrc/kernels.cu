@@ -238,6 +238,30 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, in
   bind_work<LPE>(WD, S, ni, nd, smem);
   env_backward(tl, S, a, env, WD);
 }
+
+// Readout pull-backs of all T x B env-steps (vjp_terms), one tile per env-step.  The work per env-step depends on
+// whether markers are in contact, so the warps draw their env-steps from a counter (TPW consecutive ones at a time:
+// consecutive environments of one step, whose loads coalesce) instead of owning a fixed share.
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  DevTile<LPE> tl = make_tile<LPE>();
+  WorkSplit WD;
+  bind_work<LPE>(WD, S, ni, nd, smem);
+  const long long items = (long long)a.T * a.B;
+  const int tpw = 32 / LPE;
+  for (;;) {
+    unsigned base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(a.work_counter, (unsigned)tpw);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= items) break;
+    const long long item = (long long)base + (threadIdx.x & 31) / LPE;
+    if (item < items) env_vjp(tl, S, a, item, WD);
+    __syncwarp();
+  }
+}
 #endif
 
 template <int LPE>
@@ -328,6 +352,15 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->nmj = kt.ib[KI_NMJ];
   s->opts[TSIM_OPT_LS_BATCH] = 1;
   s->opts[TSIM_OPT_MAX_NEWTON] = 0;
+  s->opts[TSIM_OPT_VJP_PASS] = 1;
+  {
+    // keep the stream-ordered scratch of tsim_backward in the pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
   CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd_all));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
@@ -450,10 +483,34 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_step_stride; a.tape = tape;
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
+  a.vjp_y = 0; a.vjp_c = 0; a.work_counter = 0;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
+  // Pass 1: readout pull-backs of all env-steps (balanced over the whole GPU); pass 2: the reverse sweep reads them.
+  // Scratch: 2 x [T,B,n] doubles + the work counter, stream-ordered allocation (retained by the device's pool).
+  void* scratch = 0;
+  const bool split = (df_dvar || df_dtac) && s->opts[TSIM_OPT_VJP_PASS] != 0 && (long long)T * B < (1ll << 31) - 64;
+  if (split) {
+    const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R];
+    CK(cudaMallocAsync(&scratch, 2 * nvec * sizeof(double) + 16, st));
+    a.vjp_y = (double*)scratch;
+    a.vjp_c = a.vjp_y + nvec;
+    a.work_counter = (unsigned*)(a.vjp_c + nvec);
+    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned), st));
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
+    const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
+    const int vgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
+#if TS_MAXN <= 8
+    if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else
+#endif
+    if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else { if (prep(vjp_kernel<32>, smem)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    CK(cudaGetLastError());
+  }
 #if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(bwd_kernel<8>, smem)) return 1; bwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else
@@ -461,6 +518,7 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
+  if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;
 #endif
 }

@@ -2008,19 +2008,16 @@ HD void jac_col(const Dual* R, const Dual* p, double* J) {
 //   pendA' = pendB + (G0 + G1/h)^T z_k + (1/h) dtac_dqdot^T w ;  pendB' = -(G1/h)^T z_k
 // out_g0z / out_g1z (optional, distributed) expose G0^T z (+ pending terms) and G1^T z for the
 // q0 / qdot0 gradients of the first step.
+// Cotangent pull-back of the readouts of ONE state (the tile state holds q, qd): per owned dof k,
+//   yk = d(var)/dq_k . w_var + d(tactile)/dq_k . w_tac   and   ck = d(tactile)/dqdot_k . w_tac
+// (the rows dvar_dq^T w, dtactile_dq^T w, dtactile_dqdot^T w of DH/Simulation.cpp:1640-1650).  It depends on the state
+// and the cotangents only, not on the adjoint recursion: tsim_backward evaluates it for all env-steps in a balanced
+// pass of its own (vjp_kernel) and the reverse sweep reads the two n-vectors.
 template <class Tile, class WK>
-HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
-                       double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
-                       WK& WD) {
+HDN void vjp_terms(const Tile& tl, const SceneView& S, const double* dvar_cot, const double* dtac_cot, WK& WD,
+                   double* yk_out, double* ck_out) {
   const int L = Tile::LPE;
-  const int n = S.n;
-  double y[TS_NC(L)], cterm[TS_NC(L)];
-  for (int c = 0; c < TS_NC(L); ++c) {
-    const int k = tl.lane + c * L;
-    y[c] = (k < n && dq_cot) ? dq_cot[k] : 0.0;
-    if (k < n) y[c] -= pendA[c];
-    cterm[c] = 0.0;
-  }
+  for (int c = 0; c < TS_NC(L); ++c) { yk_out[c] = 0.0; ck_out[c] = 0.0; }
   const bool have_var = dvar_cot != 0 && S.nee > 0;
   bool have_tac = dtac_cot != 0 && S.nmark > 0;
   if (have_var || have_tac) {
@@ -2081,7 +2078,42 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
           }
         }
       }
-      if (k < n) { cterm[c] = ck / S.h; y[c] += yk + cterm[c]; }
+      yk_out[c] = yk;
+      ck_out[c] = ck;
+    }
+  }
+}
+
+template <class Tile, class WK>
+HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, const double* tape, const double* dq_cot, const double* dvar_cot, const double* dtac_cot,
+                       double* pendA, double* pendB, double* du_out, double* out_g0z, double* out_g1z,
+                       WK& WD, const double* pre_y = 0, const double* pre_c = 0) {
+  const int L = Tile::LPE;
+  const int n = S.n;
+  double y[TS_NC(L)], cterm[TS_NC(L)];
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    y[c] = (k < n && dq_cot) ? dq_cot[k] : 0.0;
+    if (k < n) y[c] -= pendA[c];
+    cterm[c] = 0.0;
+  }
+  // readout pull-back: precomputed by the balanced pass (pre_y, pre_c: n doubles each), or evaluated here
+  {
+    double yk[TS_NC(L)], ck[TS_NC(L)];
+    if (pre_y) {
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        yk[c] = (k < n) ? pre_y[k] : 0.0;
+        ck[c] = (k < n) ? pre_c[k] : 0.0;
+      }
+    } else {
+      vjp_terms(tl, S, dvar_cot, dtac_cot, WD, yk, ck);
+    }
+    if ((dvar_cot != 0 && S.nee > 0) || (dtac_cot != 0 && S.nmark > 0)) {
+      for (int c = 0; c < TS_NC(L); ++c) {
+        const int k = tl.lane + c * L;
+        if (k < n) { cterm[c] = ck[c] / S.h; y[c] += yk[c] + cterm[c]; }
+      }
     }
   }
   // solve H^T z = y
@@ -2377,6 +2409,8 @@ struct BwdArgs {
   double* carry;                                 // [B,2,n] pending vectors, in/out
   double* df_du;                                 // [T,B,nu] or null
   double* df_dq0; double* df_dqdot0;             // [B,n] or null: MINUS the adjoint terms of step 0
+  double* vjp_y; double* vjp_c;                  // [T,B,n] readout pull-backs (vjp_terms): written by env_vjp, read by the sweep; or null
+  unsigned* work_counter;                        // dynamic distribution of the env-steps of the vjp pass
 };
 
 template <class Tile, class WK>
@@ -2404,7 +2438,8 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
                   r0 >= 0 ? a.df_dq + ((long long)r0 * B + env) * n : (const double*)0,
                   r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
                   r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0,
-                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, WD);
+                  pA, pB, a.df_du ? a.df_du + es * nu : (double*)0, g0z, g1z, WD,
+                  a.vjp_y ? a.vjp_y + es * n : (const double*)0, a.vjp_c ? a.vjp_c + es * n : (const double*)0);
   }
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;
@@ -2413,5 +2448,26 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
     a.carry[((long long)env * 2 + 1) * n + k] = pB[c];
     if (a.df_dq0) a.df_dq0[(long long)env * n + k] = -g0z[c];
     if (a.df_dqdot0) a.df_dqdot0[(long long)env * n + k] = -g1z[c];
+  }
+}
+
+// Readout pull-back of ONE env-step (item = t * B + env) into vjp_y / vjp_c: the balanced pass of tsim_backward.
+template <class Tile, class WK>
+HDN void env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long item, WK& WD) {
+  const int L = Tile::LPE;
+  const int n = S.n, B = a.B;
+  const int t = (int)(item / B);
+  TileState& ts = WD.state();
+  tl.tile_sync();                        // the previous item of this tile is done reading the tile state
+  for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q_traj[item * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd_traj[item * n + i] : 0.0; }
+  const int r1 = a.df_dvar ? (a.dvar_row ? a.dvar_row[t] : t) : -1;
+  const int r2 = a.df_dtac ? (a.dtac_row ? a.dtac_row[t] : t) : -1;
+  const long long env = item - (long long)t * B;
+  double yk[TS_NC(L)], ck[TS_NC(L)];
+  vjp_terms(tl, S, r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
+            r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0, WD, yk, ck);
+  for (int c = 0; c < TS_NC(L); ++c) {
+    const int k = tl.lane + c * L;
+    if (k < n) { a.vjp_y[item * n + k] = yk[c]; a.vjp_c[item * n + k] = ck[c]; }
   }
 }

@@ -130,7 +130,9 @@ class BatchedSim:
         tr, ntr = self._rows(tac_rows, T)
         out["var"] = (torch.zeros((nvr, B, self.ndof_var), dtype=torch.float64, device=dev)
                       if (want_var and self.ndof_var) else None)
-        out["tactile"] = (torch.zeros((ntr, B, self.ndof_tactile), dtype=torch.float64, device=dev)
+        # every row of an identity row map is written by the kernel: no 8 GB memset in front of it
+        alloc = torch.empty if tac_rows is None else torch.zeros
+        out["tactile"] = (alloc((ntr, B, self.ndof_tactile), dtype=torch.float64, device=dev)
                           if (want_tactile and self.ndof_tactile) else None)
         out["tape"] = torch.empty((T, B, self.tape_doubles), dtype=torch.float64, device=dev) if grad else None
         out["status"] = torch.zeros((T, B), dtype=torch.int32, device=dev) if want_status else None

@@ -50,6 +50,14 @@ int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, 
   a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_stride; a.tape = tape;
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
+  // the readout pull-backs in a pass of their own, as tsim_backward does (vjp_kernel), then the sweep
+  std::vector<double> vy((size_t)T * B * S.n), vc((size_t)T * B * S.n);
+  a.vjp_y = vy.data(); a.vjp_c = vc.data(); a.work_counter = 0;
+  {
+    std::vector<Work<Dual> > wv(1);
+    HostTile tv;
+    for (long long item = 0; item < (long long)T * B; ++item) env_vjp(tv, S, a, item, wv[0]);
+  }
   std::vector<Work<Dual> > wb(1);
   HostTile tl;
   for (int env = 0; env < B; ++env) env_backward(tl, S, a, env, wb[0]);

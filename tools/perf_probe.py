@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--no-gp", action="store_true", help="timing experiment: drop the pad-box contact force")
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     ap.add_argument("--max-newton", type=int, default=0, help="TSIM_OPT_MAX_NEWTON (0 = the reference's cap)")
+    ap.add_argument("--vjp-pass", type=int, default=1, help="TSIM_OPT_VJP_PASS (1 = readout pull-backs in a balanced pass of their own)")
     ap.add_argument("--identical", type=int, default=-1, help="timing experiment: every environment gets the inputs of this one (perfect balance)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
@@ -63,6 +64,7 @@ def main():
         dev = sim.device
         if a.max_newton:
             sim.set_option(1, a.max_newton)
+        sim.set_option(2, a.vjp_pass)
         q0, qd0, u = inputs(g, a.B, a.T, dev)
         if a.zero_u:
             u = torch.zeros_like(u)
