@@ -283,8 +283,10 @@ def run_b200(a):
     barrier()
     ms_total = t_start.elapsed_time(t_end)
     clocks = sampler.stop()
-    fwd_ms = ev[0].elapsed_time(ev[1])
-    bwd_ms = ev[2].elapsed_time(ev[3])
+    fwd_call_ms = ev[0].elapsed_time(ev[1])
+    bwd_call_ms = ev[2].elapsed_time(ev[3])
+    kt = core.kernel_times()           # CUDA events recorded inside the C ABI around each kernel of the last step
+    fwd_ms = kt["fwd_kernel"]
     nan = bool(torch.isnan(bw["df_du"]).any().item())
     ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -355,8 +357,18 @@ def run_b200(a):
     else:
         peak, peak_src = 6650.0, "fallback"
     M = core.n_markers
-    fwd_bytes = (8 * nu + 16 * n + 8 * nvar + 24 * M) * B * T           # u in; q, qd, var, tactile out
+    # algorithmic HBM bytes per env-step of each kernel: the step loop moves u in, q / qd / var and
+    # the H block of the tape out; the tactile field (24 M) is written by tac_kernel, G0 / G1 / gains by tape_kernel
+    per_step = {"fwd_kernel": 8 * nu + 16 * n + 8 * nvar + 8 * n * n,
+                "tape_kernel": 8 * nu + 32 * n + 16 * n * n + 8 * nu,
+                "tac_kernel": 16 * n + 24 * M,
+                "vjp_kernel": 16 * n + 8 * nvar + 24 * M + 16 * n,
+                "bwd_kernel": 8 * n + 16 * n + 8 * (3 * n * n + nu) + 8 * nu}
+    fwd_bytes = per_step["fwd_kernel"] * B * T
     achieved = fwd_bytes / (fwd_ms * 1e-3) / 1e9
+    kernels = {k: {"ms": kt[k], "algorithmic_bytes_per_launch": per_step[k] * B * T,
+                   "achieved_gbs": per_step[k] * B * T / (kt[k] * 1e-3) / 1e9, "frac": per_step[k] * B * T / (kt[k] * 1e-3) / 1e9 / peak}
+               for k in per_step if kt.get(k)}
     traffic = None
     tp = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
     tp = os.path.join(ROOT, "profiles", tp[-1]) if tp else ""
@@ -367,8 +379,10 @@ def run_b200(a):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "fwd_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": fwd_bytes, "kernel_ms": fwd_ms, "adjoint_kernel_ms": bwd_ms,
-                "note": "fp64 latency/ALU-bound path: HBM fraction is small by construction (DESIGN.md roofline section)"}
+                "algorithmic_bytes_per_launch": fwd_bytes, "kernel_ms": fwd_ms,
+                "forward_call_ms": fwd_call_ms, "adjoint_call_ms": bwd_call_ms, "kernels": kernels,
+                "note": "fwd_kernel (the step loop) is fp64 latency-bound: its HBM fraction is small by construction; "
+                        "tac_kernel, the tactile read-out pass, is the kernel that streams (DESIGN.md roofline section)"}
 
     # ---- CPU baseline beside it: unmodified reference C++ on the host cores, bounded sample
     cpu = None
@@ -391,7 +405,7 @@ def run_b200(a):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "EpisodicSimFunction.apply + loss.backward(), pinned host q0/qdot0/actions in, grads + loss out"},
-            "gpu_launches": 2 * a.steps,
+            "gpu_launches": sum(1 for v in kt.values() if v) * a.steps,
             "roofline": roofline, "cpu_baseline": cpu, "nan": nan}
     print(json.dumps(line), flush=True)
     if world > 1:

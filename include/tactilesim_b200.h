@@ -63,8 +63,15 @@ int tsim_scene_set_lanes(tsim_scene* scene, int lanes_per_env);
  *                      much as a whole trajectory, so throughput-bound users may trade exactness on those steps.
  *   TSIM_OPT_VJP_PASS  1 (default): tsim_backward pulls the readout cotangents (df_dvar, df_dtactile) back in a pass of
  *                      its own over all T x B env-steps, spread over the whole GPU, before the reverse sweep (which is
- *                      sequential per environment); 0: inside the sweep.  Bit-identical results. */
-enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_OPT_VJP_PASS = 2, TSIM_N_OPTS };
+ *                      sequential per environment); 0: inside the sweep.  Bit-identical results.
+ *   TSIM_OPT_TAC_PASS  1 (default): tsim_forward calls of 4 steps or more read the tactile field out in a pass of
+ *                      their own over the recorded trajectory, spread over the whole GPU, after the step loop;
+ *                      0: at the end of every step inside the loop.  Same values.
+ *   TSIM_OPT_TAPE_PASS 1 (default): likewise for the blocks G0, G1 and d f_r/d u of the adjoint tape (one residual
+ *                      evaluation per env-step at the converged state, which depends on the trajectory only); needs
+ *                      q_traj and qd_traj.  0: evaluated inside the step loop.  Same values. */
+enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_OPT_VJP_PASS = 2, TSIM_OPT_TAC_PASS = 3, TSIM_OPT_TAPE_PASS = 4,
+       TSIM_N_OPTS };
 int tsim_scene_set_option(tsim_scene* scene, int key, int value);
 
 /* Advances B environments by T implicit (BDF1/Newton) steps.
@@ -102,6 +109,13 @@ int tsim_forward_multistep(const tsim_scene* scene, int32_t B, int32_t T, double
                            double* q_traj, double* qd_traj, double* var_out, const int32_t* var_row, double* tac_out,
                            const int32_t* tac_row, double* tape, int32_t* status, uint32_t* contact_masks,
                            int32_t* marker_body, void* stream);
+
+/* Device time (ms, CUDA events on the call's stream) of the kernels of the LAST tsim_forward / tsim_backward call on this
+ * handle: ms[TSIM_K_*], -1 for a kernel that did not run.  The caller synchronises the stream first.  (Measurement aid:
+ * bench.py's roofline figures; no reference counterpart -- the reference's print_time_report is host timing.) */
+enum { TSIM_K_FWD = 0 /* step loop */, TSIM_K_TAPE /* G0 / G1 pass */, TSIM_K_TAC /* tactile readout pass */,
+       TSIM_K_VJP /* readout pull-back pass */, TSIM_K_BWD /* reverse sweep */, TSIM_N_KERNELS };
+int tsim_scene_kernel_times(const tsim_scene* scene, double* ms /* [TSIM_N_KERNELS] */);
 
 /* Readouts at a given state (no stepping). Any output may be NULL. */
 int tsim_readout(const tsim_scene* scene, int32_t B, const double* q, const double* qd, double* var_out,

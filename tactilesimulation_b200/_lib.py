@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_b200.so")
 
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
-           "tsim_forward", "tsim_forward_multistep", "tsim_readout", "tsim_backward"]
+           "tsim_forward", "tsim_forward_multistep", "tsim_scene_kernel_times", "tsim_readout", "tsim_backward"]
+KERNELS = ("fwd_kernel", "tape_kernel", "tac_kernel", "vjp_kernel", "bwd_kernel")
 (NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, CMASK_WORDS, INTEGRATOR, N_SIZES) = range(11)
 INT_BDF1, INT_BDF2, INT_SDIRK2 = 0, 1, 2
 
@@ -40,6 +41,7 @@ def load():
     lib.tsim_scene_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.tsim_forward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_forward_multistep.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsim_scene_kernel_times.argtypes = [vp, vp]
     lib.tsim_readout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_backward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib

@@ -22,6 +22,7 @@
   int tsim_forward_multistep_v##V(const void*, int32_t, int32_t, double*, double*, double*, double*, int32_t,        \
                                   const double*, int64_t, double*, double*, double*, const int32_t*, double*,        \
                                   const int32_t*, double*, int32_t*, uint32_t*, int32_t*, void*);                     \
+  int tsim_scene_kernel_times_v##V(const void*, double*);                                                             \
   int tsim_readout_v##V(const void*, int32_t, const double*, const double*, double*, double*, int32_t*, uint32_t*,    \
                         void*);                                                                                       \
   int tsim_backward_v##V(const void*, int32_t, int32_t, const double*, const double*, const double*, int64_t,        \
@@ -123,6 +124,12 @@ int tsim_forward(const tsim_scene* s, int32_t B, int32_t T, double* q, double* q
                  void* stream) {
   return tsim_forward_multistep(s, B, T, q, qd, 0, 0, 0, u, u_step_stride, q_traj, qd_traj, var_out, var_row, tac_out, tac_row,
                                 tape, status, contact_masks, marker_body, stream);
+}
+
+int tsim_scene_kernel_times(const tsim_scene* s, double* ms) {
+  if (!s) return own_fail("tsim_scene_kernel_times: null scene");
+  return DISPATCH(s, tsim_scene_kernel_times_v8(s->inner, ms), tsim_scene_kernel_times_v16(s->inner, ms),
+                  tsim_scene_kernel_times_v17(s->inner, ms));
 }
 
 int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* qd, double* var_out, double* tac_out,

@@ -35,6 +35,7 @@
 #define tsim_readout TSV(tsim_readout)
 #define tsim_backward TSV(tsim_backward)
 #define tsim_debug_set_prof TSV(tsim_debug_set_prof)
+#define tsim_scene_kernel_times TSV(tsim_scene_kernel_times)
 // Everything below lives in a per-variant namespace: the two variants instantiate templates and kernels
 // with identical signatures but different capacities, and must not share symbols.
 namespace TSV(tsimns) {
@@ -225,7 +226,55 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
 #endif
 }
 
+// Tactile fields of all T x B env-steps of a forward call (env_tactile), one tile per env-step, env-steps drawn from a
+// counter like in vjp_kernel.
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tac_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  DevTile<LPE> tl = make_tile<LPE>();
+  WorkSplit WD;
+  bind_work<LPE>(WD, S, ni, nd, smem);
+  const long long items = (long long)a.T * a.B;
+  const int tpw = 32 / LPE;
+  for (;;) {
+    unsigned base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(a.work_counter, (unsigned)tpw);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= items) break;
+    const long long item = (long long)base + (threadIdx.x & 31) / LPE;
+    if (item < items) env_tactile(tl, S, a, item, WD);
+    __syncwarp();
+  }
+}
+
 #if !KT_MULTISTEP     // variant 17 is forward-only (no adjoint of BDF2 / SDIRK2, sphere tactile VJP not written)
+// G0 / G1 / gain blocks of the tape for all T x B env-steps of a forward call (env_tape), env-steps drawn from a counter.
+template <int LPE>
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tape_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ SceneView S;
+  stage_scene(S, ib, ni, db, nd, smem);
+  DevTile<LPE> tl = make_tile<LPE>();
+  WorkSplit WD;
+  bind_work<LPE>(WD, S, ni, nd, smem);
+  const long long items = (long long)a.T * a.B;
+  unsigned* counter = a.work_counter + 1;
+  // the residual code is large: the warps of a block take their env-steps together (one block-wide fetch per round)
+  // so that the block streams through it at the same time, as in fwd_kernel
+  __shared__ unsigned sbase;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sbase = atomicAdd(counter, (unsigned)(TS_BLOCK / LPE));
+    __syncthreads();
+    const unsigned base = sbase;
+    if ((long long)base >= items) break;
+    const long long slot = (long long)base + threadIdx.x / LPE;
+    if (slot < items) env_tape(tl, S, a, a.tape_order ? (long long)a.tape_order[slot] : slot, WD);
+  }
+}
+
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -297,6 +346,9 @@ struct tsim_scene {
   int nmj;                 // moving joints of the lowered scene
   int opts[TSIM_N_OPTS];
   int sizes[TSIM_N_SIZES];
+  // events around the kernels of the last tsim_forward / tsim_backward call (tsim_scene_kernel_times)
+  cudaEvent_t ev[7];
+  mutable int ran[TSIM_N_KERNELS];
 };
 
 static thread_local std::string g_err;
@@ -350,9 +402,13 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->nd = kt.ib[KI_D_MARKERS];       // doubles staged in shared memory: everything before the marker table
   s->lanes = TS_MAXN;        // one lane per reduced coordinate
   s->nmj = kt.ib[KI_NMJ];
+  for (int i = 0; i < 7; ++i) CK(cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < TSIM_N_KERNELS; ++i) s->ran[i] = 0;
   s->opts[TSIM_OPT_LS_BATCH] = 1;
   s->opts[TSIM_OPT_MAX_NEWTON] = 0;
   s->opts[TSIM_OPT_VJP_PASS] = 1;
+  s->opts[TSIM_OPT_TAC_PASS] = 1;
+  s->opts[TSIM_OPT_TAPE_PASS] = 1;
   {
     // keep the stream-ordered scratch of tsim_backward in the pool between calls
     cudaMemPool_t pool;
@@ -385,6 +441,7 @@ void tsim_scene_destroy(tsim_scene* s) {
   cudaSetDevice(s->device);
   cudaFree(s->d_ib);
   cudaFree(s->d_db);
+  for (int i = 0; i < 7; ++i) cudaEventDestroy(s->ev[i]);
   delete s;
 }
 
@@ -433,10 +490,45 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   a.ls_batch = s->opts[TSIM_OPT_LS_BATCH];
   a.max_newton = s->opts[TSIM_OPT_MAX_NEWTON];
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
+  a.defer_tac = 0; a.work_counter = 0;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
+  // The tactile field is read out by a pass of its own over the recorded trajectory (tac_kernel) when the call covers
+  // more than a few steps; scratch (trajectory if the caller keeps none, work counter) is stream-ordered.
+  void* scratch = 0;
+  const bool big = T >= 4 && (long long)T * B < (1ll << 31) - 64;
+  const bool tac_pass = tac_out && s->opts[TSIM_OPT_TAC_PASS] != 0 && big;
+  // ... and so are the G0 / G1 / gain blocks of the tape (tape_kernel), which need the state at the start of the call
+  bool tape_pass = false;
+#if !KT_MULTISTEP
+  tape_pass = tape && q_traj && qd_traj && s->opts[TSIM_OPT_TAPE_PASS] != 0 && big;
+#endif
+  a.defer_g0 = 0; a.q_start = 0; a.qd_start = 0; a.tape_order = 0;
+  if (tac_pass || tape_pass) {
+    const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R], nst = (size_t)B * s->sizes[TSIM_NDOF_R];
+    const bool own_traj = !(q_traj && qd_traj);
+    const size_t norder = (((size_t)T * B * sizeof(int)) + 15) & ~(size_t)15;
+    const size_t need = 16 + (own_traj ? 2 * nvec * sizeof(double) : 0) + (tape_pass ? 2 * nst * sizeof(double) + norder : 0);
+    CK(cudaMallocAsync(&scratch, need, st));
+    unsigned char* p = (unsigned char*)scratch;
+    a.work_counter = (unsigned*)p;
+    p += 16;
+    if (own_traj) { a.q_traj = (double*)p; a.qd_traj = a.q_traj + nvec; p += 2 * nvec * sizeof(double); }
+    CK(cudaMemsetAsync(a.work_counter, 0, 16, st));
+    a.defer_tac = tac_pass ? 1 : 0;
+    if (tape_pass) {
+      double* qs = (double*)p;
+      CK(cudaMemcpyAsync(qs, q, nst * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(qs + nst, qd, nst * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      a.q_start = qs; a.qd_start = qs + nst;
+      a.tape_order = (int*)(qs + 2 * nst);
+      a.defer_g0 = 1;
+    }
+  }
+  s->ran[TSIM_K_FWD] = 1; s->ran[TSIM_K_TAPE] = tape_pass ? 1 : 0; s->ran[TSIM_K_TAC] = tac_pass ? 1 : 0;
+  CK(cudaEventRecord(s->ev[0], st));
 #if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else
@@ -444,6 +536,37 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else { if (prep(fwd_kernel<32>, smem)) return 1; fwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
+  CK(cudaEventRecord(s->ev[1], st));
+  int tgrid = 1;
+  if (tac_pass || tape_pass) {
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
+    const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
+    tgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
+  }
+#if !KT_MULTISTEP
+  if (tape_pass) {
+#if TS_MAXN <= 8
+    if (s->lanes == 8) { if (prep(tape_kernel<8>, smem)) return 1; tape_kernel<8><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else
+#endif
+    if (s->lanes == 16) { if (prep(tape_kernel<16>, smem)) return 1; tape_kernel<16><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else { if (prep(tape_kernel<32>, smem)) return 1; tape_kernel<32><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    CK(cudaGetLastError());
+  }
+#endif
+  CK(cudaEventRecord(s->ev[2], st));
+  if (tac_pass) {
+#if TS_MAXN <= 8
+    if (s->lanes == 8) { if (prep(tac_kernel<8>, smem)) return 1; tac_kernel<8><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else
+#endif
+    if (s->lanes == 16) { if (prep(tac_kernel<16>, smem)) return 1; tac_kernel<16><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else { if (prep(tac_kernel<32>, smem)) return 1; tac_kernel<32><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s->ev[3], st));
+  if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;
 }
 
@@ -490,6 +613,7 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   cudaStream_t st = (cudaStream_t)stream;
   // Pass 1: readout pull-backs of all env-steps (balanced over the whole GPU); pass 2: the reverse sweep reads them.
   // Scratch: 2 x [T,B,n] doubles + the work counter, stream-ordered allocation (retained by the device's pool).
+  CK(cudaEventRecord(s->ev[4], st));
   void* scratch = 0;
   const bool split = (df_dvar || df_dtac) && s->opts[TSIM_OPT_VJP_PASS] != 0 && (long long)T * B < (1ll << 31) - 64;
   if (split) {
@@ -511,6 +635,8 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
     else { if (prep(vjp_kernel<32>, smem)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
     CK(cudaGetLastError());
   }
+  s->ran[TSIM_K_VJP] = split ? 1 : 0; s->ran[TSIM_K_BWD] = 1;
+  CK(cudaEventRecord(s->ev[5], st));
 #if TS_MAXN <= 8
   if (s->lanes == 8) { if (prep(bwd_kernel<8>, smem)) return 1; bwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else
@@ -518,9 +644,24 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   CK(cudaGetLastError());
+  CK(cudaEventRecord(s->ev[6], st));
   if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;
 #endif
+}
+
+int tsim_scene_kernel_times(const tsim_scene* s, double* ms) {
+  if (!s || !ms) return fail("tsim_scene_kernel_times: null argument");
+  CK(cudaSetDevice(s->device));
+  const int a0[TSIM_N_KERNELS] = {0, 1, 2, 4, 5}, a1[TSIM_N_KERNELS] = {1, 2, 3, 5, 6};
+  for (int k = 0; k < TSIM_N_KERNELS; ++k) {
+    ms[k] = -1.0;
+    if (!s->ran[k]) continue;
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, s->ev[a0[k]], s->ev[a1[k]]));
+    ms[k] = (double)t;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -277,6 +277,7 @@ struct SeedIn {
 template <class T> struct WorkRec {          // the joint records alone (value-only line-search trials)
   typedef T Scalar;
   double beta;                               // force scale of the residual in flight (h^2 for BDF1), set by eval_g
+  int gp_any;                                // the last evaluation had an active general-primitive contact point
   T rec[TS_MAXJ][WK_REC];
   HD T get(int j, int o) const { return rec[j][o]; }
   HD double getv(int j, int o) const { return val(rec[j][o]); }
@@ -298,6 +299,7 @@ struct WorkSplit {
   HD TileState& state() { return *ts; }
   HD double* scratch() { return ts->hs; }
   double beta;                     // force scale of the residual in flight (h^2 for BDF1), set by eval_g
+  int gp_any;                      // the last evaluation had an active general-primitive contact point
   double dt[TS_MAXJ][WK_REC];      // tangents of this lane
   HD Dual get(int j, int o) const { return mkdual(sv[j * WK_REC + o], dt[j][o]); }
   HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
@@ -1028,6 +1030,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     for (int i = 0; i < KT_MAXPW; ++i) any |= act[i];
     TS_GPT(tl, 0);
     if (!any) continue;
+    W.gp_any = 1;
     // the tile's own relative kinematics in the frame of body 2 (dual numbers)
     T R2[9], p2[3];
     {
@@ -1162,6 +1165,7 @@ template <class Tile, class WK, class In>
 HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g,
                 double beta) {
   W.beta = beta;
+  W.gp_any = 0;
 #ifdef TS_PROFILE_GP      // slots 0, 1, 3 are re-used for the phases INSIDE gp_contacts (detect / pair setup / point forces)
   kinematics(S, in, W, true);
   ground_contacts(S, W);
@@ -1528,6 +1532,7 @@ struct StepVars {
   bool converged, batch_ls;
   int cap_newton;
   int mode;                 // TS_ST_*: implicit stage in flight
+  bool defer_g0;            // the G0 / G1 blocks of the tape are written by the pass of their own (env_tape), not by phase 3
 };
 
 HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
@@ -1676,6 +1681,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
       const int k = tl.lane + c * L;
       if (k < n) for (int i = 0; i < n; ++i) st_stream(tape + i * n + k, cole[c][i]);
     }
+    if (v.defer_g0) return true;
     v.phase = 3;
     return false;
   }
@@ -2241,6 +2247,12 @@ struct FwdArgs {
   // two-state integrators (BDF2): state one step back [B,n], in/out, or null; steps already taken since reset
   double* q_prev; double* qd_prev;
   int steps_done;
+  int defer_g0;                       // G0, G1, dfr/du of the tape are written by the pass of their own (env_tape)
+  const double* q_start; const double* qd_start;   // [B,n] copy of the state at the start of the call (env_tape, step 0)
+  int* tape_order;                    // [T*B] env-steps in the order env_tape takes them: steps in contact first (appended
+                                      // from the front), the others from the back; counters work_counter[2], [3]
+  int defer_tac;                      // the tactile field is read out by the pass of its own (env_tactile), not by the step loop
+  unsigned* work_counter;             // dynamic distribution of the env-steps of that pass
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
@@ -2284,6 +2296,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   v.batch_ls = a.ls_batch != 0;
   v.cap_newton = a.max_newton;
   v.mode = TS_ST_BDF1;
+  v.defer_g0 = a.defer_g0 != 0;
   int t = 0;                             // warp-uniform
   bool tile_done = !active;
 #if KT_MULTISTEP
@@ -2361,12 +2374,22 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
 #endif
       }
       if (tl.lane == 0) {
+#ifdef __CUDA_ARCH__
+        if (a.tape_order) {
+          // contact and contact-free evaluations cost 3:1; the tape pass takes its env-steps grouped by kind so that
+          // the tiles of a warp and the warps of a block run evaluations of the same cost together
+          const long long items = (long long)a.T * B;
+          const unsigned pos = WD.gp_any ? atomicAdd(a.work_counter + 2, 1u)
+                                         : (unsigned)(items - 1) - atomicAdd(a.work_counter + 3, 1u);
+          a.tape_order[pos] = (int)es;
+        }
+#endif
         if (a.status) a.status[es] = stat;
         if (a.q_traj) for (int i = 0; i < n; ++i) st_stream(a.q_traj + es * n + i, qn[i]);
         if (a.qd_traj) for (int i = 0; i < n; ++i) st_stream(a.qd_traj + es * n + i, qdn[i]);
       }
       const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
-      const int tr = a.tac_out ? (a.tac_row ? a.tac_row[t] : t) : -1;
+      const int tr = (a.tac_out && !a.defer_tac) ? (a.tac_row ? a.tac_row[t] : t) : -1;
       if (vr >= 0 || tr >= 0 || a.cmask) {
         // the work space already holds the kinematics of the new state (last residual evaluation)
         readout_from_work(tl, S, WD,
@@ -2470,4 +2493,57 @@ HDN void env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long
     const int k = tl.lane + c * L;
     if (k < n) { a.vjp_y[item * n + k] = yk[c]; a.vjp_c[item * n + k] = ck[c]; }
   }
+}
+
+// Tactile field of ONE env-step (item = t * B + env) from the recorded trajectory: the readout pass of tsim_forward.
+// Same code and work space as the readout at the end of a step (kinematics of the state, then tactile_values), so the
+// field is the same value for value; it only runs where the whole GPU can share it instead of inside the step loop,
+// where one warp's readout made the other warps of its block wait.
+template <class Tile, class WK>
+HDN void env_tactile(const Tile& tl, const SceneView& S, const FwdArgs& a, long long item, WK& WD) {
+  const int n = S.n, B = a.B;
+  const int t = (int)(item / B);
+  const int tr = a.tac_row ? a.tac_row[t] : t;
+  if (tr < 0) return;
+  const long long env = item - (long long)t * B;
+  TileState& ts = WD.state();
+  tl.tile_sync();
+  for (int i = 0; i < TS_MAXN; ++i) { ts.xq[i] = (i < n) ? a.q_traj[item * n + i] : 0.0; ts.xv[i] = (i < n) ? a.qd_traj[item * n + i] : 0.0; }
+  SeedIn in;
+  in.xq = ts.xq; in.xv = ts.xv; in.xl = ts.xv;     // dl is not read by the kinematics-only pass
+  in.k = -1; in.tq = 0.0; in.tv = 0.0; in.tl = 0.0;
+  in.q0v = ts.xq; in.qd0v = ts.xv; in.tq0 = 0.0; in.tqd0 = 0.0;
+  tl.tile_sync();
+  kinematics(S, in, WD, false);
+  tactile_values(tl, S, WD, a.tac_out + ((long long)tr * B + env) * 3 * S.nmark,
+                 a.marker_body ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0);
+}
+
+// Adjoint blocks G0 = dg/dq0, G1 = dg/dqdot0 and the control gains of ONE env-step (item = t * B + env) from the recorded
+// trajectory: what phase 3 of the step state machine evaluates at the converged point.  They depend on the states
+// before and after the step and on the controls only, so tsim_forward evaluates them for all env-steps in a pass of
+// its own spread over the whole GPU; the step loop -- sequential per environment, its blocks in lock-step -- loses one
+// residual evaluation in about five.
+template <class Tile, class WK>
+HDN void env_tape(const Tile& tl, const SceneView& S, const FwdArgs& a, long long item, WK& WD) {
+  const int n = S.n, nu = S.nu, B = a.B;
+  const int t = (int)(item / B);
+  const long long env = item - (long long)t * B;
+  TileState& ts = WD.state();
+  tl.tile_sync();
+  const double* qs = t ? a.q_traj + (item - B) * n : a.q_start + env * n;
+  const double* qds = t ? a.qd_traj + (item - B) * n : a.qd_start + env * n;
+  for (int i = 0; i < TS_MAXN; ++i) {
+    ts.q[i] = (i < n) ? qs[i] : 0.0;
+    ts.qd[i] = (i < n) ? qds[i] : 0.0;
+    ts.x[i] = (i < n) ? a.q_traj[item * n + i] : 0.0;
+  }
+  for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[t * a.u_stride + env * nu + i] : 0.0;
+  StepVars v;
+  v.phase = 3; v.mode = TS_ST_BDF1; v.defer_g0 = false; v.batch_ls = false; v.cap_newton = 0;
+  v.iters = 0; v.ls = 0; v.trial = 0; v.fail_strike = 0; v.alpha = 1.0; v.gnorm = 0.0; v.converged = true;
+  double cole[TS_NC(Tile::LPE)][TS_MAXN];
+  tl.tile_sync();
+  step_eval(tl, S, v, WD, cole);
+  step_post(tl, S, v, a.tape + item * S.ntape, WD, cole);
 }

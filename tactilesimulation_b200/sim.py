@@ -61,6 +61,14 @@ class BatchedSim:
         """tsim_scene_set_option (include/tactilesim_b200.h): 0 = TSIM_OPT_LS_BATCH."""
         _lib.check(self.lib.tsim_scene_set_option(self.handle, key, value), self.lib)
 
+    def kernel_times(self):
+        """Device time (ms) of each kernel of the last forward / backward call on this handle (None: did not run);
+        synchronises the device first.  tsim_scene_kernel_times."""
+        torch.cuda.synchronize(self.device)
+        ms = np.zeros(len(_lib.KERNELS), dtype=np.float64)
+        _lib.check(self.lib.tsim_scene_kernel_times(self.handle, ms.ctypes.data), self.lib)
+        return {k: (None if v < 0 else float(v)) for k, v in zip(_lib.KERNELS, ms)}
+
     def set_lanes(self, lanes: int):
         _lib.check(self.lib.tsim_scene_set_lanes(self.handle, lanes), self.lib)
         self.lanes = lanes

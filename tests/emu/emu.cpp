@@ -32,9 +32,20 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   a.var_out = var_out; a.var_row = var_row; a.tac_out = tac_out; a.tac_row = tac_row; a.tape = tape;
   a.status = status; a.cmask = cmask; a.marker_body = marker_body; a.ls_batch = 0; a.max_newton = 0;
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
+  // as tsim_forward: calls of 4 steps or more read the tactile field out in a pass of its own over the trajectory
+  a.defer_tac = (tac_out && q_traj && qd_traj && T >= 4) ? 1 : 0;
+  a.work_counter = 0;
+  // ... and write the G0 / G1 / gain blocks of the tape in a pass of their own (BDF1 scenes)
+  std::vector<double> qs(q, q + (size_t)B * S.n), qds(qd, qd + (size_t)B * S.n);
+  a.defer_g0 = (tape && q_traj && qd_traj && T >= 4 && !KT_MULTISTEP) ? 1 : 0;
+  a.q_start = qs.data(); a.qd_start = qds.data(); a.tape_order = 0;
   std::vector<Work<Dual> > wb(1);
   HostTile tl;
   for (int env = 0; env < B; ++env) env_forward(tl, S, a, env, wb[0]);
+  if (a.defer_g0)
+    for (long long item = 0; item < (long long)T * B; ++item) env_tape(tl, S, a, item, wb[0]);
+  if (a.defer_tac)
+    for (long long item = 0; item < (long long)T * B; ++item) env_tactile(tl, S, a, item, wb[0]);
   return 0;
 }
 

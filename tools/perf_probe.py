@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--grad-only", action="store_true", help="skip the no-grad forward (for ncu captures)")
     ap.add_argument("--max-newton", type=int, default=0, help="TSIM_OPT_MAX_NEWTON (0 = the reference's cap)")
     ap.add_argument("--vjp-pass", type=int, default=1, help="TSIM_OPT_VJP_PASS (1 = readout pull-backs in a balanced pass of their own)")
+    ap.add_argument("--tac-pass", type=int, default=1, help="TSIM_OPT_TAC_PASS (1 = tactile readout in a balanced pass of its own)")
+    ap.add_argument("--tape-pass", type=int, default=1, help="TSIM_OPT_TAPE_PASS (1 = G0 / G1 blocks of the tape in a balanced pass of their own)")
     ap.add_argument("--identical", type=int, default=-1, help="timing experiment: every environment gets the inputs of this one (perfect balance)")
     a = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests", "golden", a.case + ".npz"))
@@ -65,6 +67,8 @@ def main():
         if a.max_newton:
             sim.set_option(1, a.max_newton)
         sim.set_option(2, a.vjp_pass)
+        sim.set_option(3, a.tac_pass)
+        sim.set_option(4, a.tape_pass)
         q0, qd0, u = inputs(g, a.B, a.T, dev)
         if a.zero_u:
             u = torch.zeros_like(u)
@@ -96,6 +100,7 @@ def main():
                   f"fwd+adjoint {steps / (t_f + t_b) * 1e3:.3e} env-steps/s | newton mean {(st & 255).double().mean().item():.2f} "
                   f"max {(st & 255).max().item()} ls mean {((st >> 8) & 255).double().mean().item():.2f} flags {(st >> 16).max().item()} "
                   f"nan {torch.isnan(bw['df_du']).any().item()}", flush=True)
+        print("  kernel ms:", {k: (None if v is None else round(v, 2)) for k, v in sim.kernel_times().items()}, flush=True)
 
 
 if __name__ == "__main__":
