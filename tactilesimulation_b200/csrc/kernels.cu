@@ -291,23 +291,30 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, in
 // Readout pull-backs of all T x B env-steps (vjp_terms), one tile per env-step.  The work per env-step depends on
 // whether markers are in contact, so the warps draw their env-steps from a counter (TPW consecutive ones at a time:
 // consecutive environments of one step, whose loads coalesce) instead of owning a fixed share.
+// Two launches: phase 0 takes every env-step, finishes those whose pads nothing can reach (kinematics + variables
+// only) and lists the others; phase 1 takes the listed ones -- so the tiles of a warp run work of the same kind.
 template <int LPE>
-__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
+__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a,
+                                                               int phase) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   DevTile<LPE> tl = make_tile<LPE>();
   WorkSplit WD;
   bind_work<LPE>(WD, S, ni, nd, smem);
-  const long long items = (long long)a.T * a.B;
+  const long long items = phase ? (long long)a.work_counter[2] : (long long)a.T * a.B;
   const int tpw = 32 / LPE;
   for (;;) {
     unsigned base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(a.work_counter, (unsigned)tpw);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(a.work_counter + phase, (unsigned)tpw);
     base = __shfl_sync(0xffffffffu, base, 0);
     if ((long long)base >= items) break;
-    const long long item = (long long)base + (threadIdx.x & 31) / LPE;
-    if (item < items) env_vjp(tl, S, a, item, WD);
+    const long long slot = (long long)base + (threadIdx.x & 31) / LPE;
+    if (slot < items) {
+      const long long item = phase ? (long long)a.vjp_list[slot] : slot;
+      const bool deferred = env_vjp(tl, S, a, item, WD, phase == 0);
+      if (deferred && tl.lane == 0) a.vjp_list[atomicAdd(a.work_counter + 2, 1u)] = (int)item;
+    }
     __syncwarp();
   }
 }
@@ -490,7 +497,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   a.ls_batch = s->opts[TSIM_OPT_LS_BATCH];
   a.max_newton = s->opts[TSIM_OPT_MAX_NEWTON];
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
-  a.defer_tac = 0; a.work_counter = 0;
+  a.defer_tac = 0; a.tac_prezeroed = 0; a.work_counter = 0;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
@@ -518,6 +525,12 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     if (own_traj) { a.q_traj = (double*)p; a.qd_traj = a.q_traj + nvec; p += 2 * nvec * sizeof(double); }
     CK(cudaMemsetAsync(a.work_counter, 0, 16, st));
     a.defer_tac = tac_pass ? 1 : 0;
+    // identity row map: the whole [T,B,3M] field is this call's; a memset runs at the HBM rate and the pass then
+    // only writes where a body can reach a pad (the sign of a zero is not part of the contract)
+    if (tac_pass && !tac_row) {
+      CK(cudaMemsetAsync(tac_out, 0, (size_t)T * B * s->sizes[TSIM_NDOF_TACTILE] * sizeof(double), st));
+      a.tac_prezeroed = 1;
+    }
     if (tape_pass) {
       double* qs = (double*)p;
       CK(cudaMemcpyAsync(qs, q, nst * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -606,7 +619,7 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   a.B = B; a.T = T; a.q_traj = q_traj; a.qd_traj = qd_traj; a.u = u; a.u_stride = u_step_stride; a.tape = tape;
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
-  a.vjp_y = 0; a.vjp_c = 0; a.work_counter = 0;
+  a.vjp_y = 0; a.vjp_c = 0; a.work_counter = 0; a.vjp_list = 0;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
@@ -618,22 +631,25 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   const bool split = (df_dvar || df_dtac) && s->opts[TSIM_OPT_VJP_PASS] != 0 && (long long)T * B < (1ll << 31) - 64;
   if (split) {
     const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R];
-    CK(cudaMallocAsync(&scratch, 2 * nvec * sizeof(double) + 16, st));
+    CK(cudaMallocAsync(&scratch, 2 * nvec * sizeof(double) + 16 + (size_t)T * B * sizeof(int), st));
     a.vjp_y = (double*)scratch;
     a.vjp_c = a.vjp_y + nvec;
     a.work_counter = (unsigned*)(a.vjp_c + nvec);
-    CK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned), st));
+    a.vjp_list = (int*)(a.work_counter + 4);
+    CK(cudaMemsetAsync(a.work_counter, 0, 16, st));
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
     const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
     const int vgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
+    for (int phase = 0; phase < 2; ++phase) {
 #if TS_MAXN <= 8
-    if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else
+      if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      else
 #endif
-    if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else { if (prep(vjp_kernel<32>, smem)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    CK(cudaGetLastError());
+      if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      else { if (prep(vjp_kernel<32>, smem)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      CK(cudaGetLastError());
+    }
   }
   s->ran[TSIM_K_VJP] = split ? 1 : 0; s->ran[TSIM_K_BWD] = 1;
   CK(cudaEventRecord(s->ev[5], st));

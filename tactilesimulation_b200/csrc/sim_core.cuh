@@ -1853,8 +1853,9 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
 
 // tactile values of this env, markers strided over the tile's lanes.
 // out: [M][3] = (shear . axis0, shear . axis1, normal)      (TactileSensor.cpp:74-81)
+// prezeroed: `out` is already all zeros (tac_kernel after a memset): sensors that nothing can reach are skipped.
 template <class Tile, class WK>
-HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, int* body_out) {
+HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, int* body_out, bool prezeroed = false) {
   for (int si = 0; si < S.nsens; ++si) {
     const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
     const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
@@ -1867,7 +1868,7 @@ HDN void tactile_values(const Tile& tl, const SceneView& S, WK& W, double* out, 
     for (int c = 0; c < sr[3]; ++c) anynear = anynear || F.near[1 + c];
     if (!anynear) {
       // no candidate body can reach the pad: zero field, written with unit stride across the lanes
-      for (int i = tl.lane; i < 3 * mc; i += Tile::LPE) st_stream(out + 3 * mo + i, (i % 3 == 2) ? -0.0 : 0.0);
+      if (!prezeroed) for (int i = tl.lane; i < 3 * mc; i += Tile::LPE) st_stream(out + 3 * mo + i, (i % 3 == 2) ? -0.0 : 0.0);
       if (body_out) for (int m = tl.lane; m < mc; m += Tile::LPE) st_stream(body_out + mo + m, -1);
       continue;
     }
@@ -2020,8 +2021,10 @@ HD void jac_col(const Dual* R, const Dual* p, double* J) {
 // and the cotangents only, not on the adjoint recursion: tsim_backward evaluates it for all env-steps in a balanced
 // pass of its own (vjp_kernel) and the reverse sweep reads the two n-vectors.
 template <class Tile, class WK>
-HDN void vjp_terms(const Tile& tl, const SceneView& S, const double* dvar_cot, const double* dtac_cot, WK& WD,
-                   double* yk_out, double* ck_out) {
+// light_only: when a candidate body can reach a pad (the expensive case: marker loop + reverse mode) nothing is
+// evaluated and true is returned -- the caller defers the env-step to a pass that holds only such env-steps.
+HDN bool vjp_terms(const Tile& tl, const SceneView& S, const double* dvar_cot, const double* dtac_cot, WK& WD,
+                   double* yk_out, double* ck_out, bool light_only = false) {
   const int L = Tile::LPE;
   for (int c = 0; c < TS_NC(L); ++c) { yk_out[c] = 0.0; ck_out[c] = 0.0; }
   const bool have_var = dvar_cot != 0 && S.nee > 0;
@@ -2039,6 +2042,19 @@ HDN void vjp_terms(const Tile& tl, const SceneView& S, const double* dvar_cot, c
       in.k = k;
       tl.tile_sync();
       kinematics(S, in, WD, false);
+      if (light_only && have_tac && c == 0) {
+        bool anynear = false;
+        for (int si = 0; si < S.nsens; ++si) {
+          const int* sr = S.ib + S.o_sensor + si * KS_ISTRIDE;
+          const double* sd = S.db + S.d_sensor + si * KS_DSTRIDE;
+          Frames& F = WD.frames();
+          tl.tile_sync();
+          sensor_frames(S, WD, sr, sd, F);
+          tl.tile_sync();
+          for (int cc = 0; cc < sr[3]; ++cc) anynear = anynear || F.near[1 + cc];
+        }
+        if (anynear) return true;
+      }
       double yk = 0.0, ck = 0.0;
       if (have_var) {
         for (int e = 0; e < S.nee; ++e) {
@@ -2088,6 +2104,7 @@ HDN void vjp_terms(const Tile& tl, const SceneView& S, const double* dvar_cot, c
       ck_out[c] = ck;
     }
   }
+  return false;
 }
 
 template <class Tile, class WK>
@@ -2252,6 +2269,7 @@ struct FwdArgs {
   int* tape_order;                    // [T*B] env-steps in the order env_tape takes them: steps in contact first (appended
                                       // from the front), the others from the back; counters work_counter[2], [3]
   int defer_tac;                      // the tactile field is read out by the pass of its own (env_tactile), not by the step loop
+  int tac_prezeroed;                  // ... into a buffer that tsim_forward has already set to zero
   unsigned* work_counter;             // dynamic distribution of the env-steps of that pass
 };
 
@@ -2433,7 +2451,8 @@ struct BwdArgs {
   double* df_du;                                 // [T,B,nu] or null
   double* df_dq0; double* df_dqdot0;             // [B,n] or null: MINUS the adjoint terms of step 0
   double* vjp_y; double* vjp_c;                  // [T,B,n] readout pull-backs (vjp_terms): written by env_vjp, read by the sweep; or null
-  unsigned* work_counter;                        // dynamic distribution of the env-steps of the vjp pass
+  unsigned* work_counter;                        // [4] dynamic distribution of the env-steps of the vjp passes
+  int* vjp_list;                                 // [T*B] env-steps deferred by the first vjp pass (count: work_counter[2])
 };
 
 template <class Tile, class WK>
@@ -2476,7 +2495,7 @@ HDN void env_backward(const Tile& tl, const SceneView& S, const BwdArgs& a, int 
 
 // Readout pull-back of ONE env-step (item = t * B + env) into vjp_y / vjp_c: the balanced pass of tsim_backward.
 template <class Tile, class WK>
-HDN void env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long item, WK& WD) {
+HDN bool env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long item, WK& WD, bool light_only = false) {
   const int L = Tile::LPE;
   const int n = S.n, B = a.B;
   const int t = (int)(item / B);
@@ -2487,12 +2506,14 @@ HDN void env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long
   const int r2 = a.df_dtac ? (a.dtac_row ? a.dtac_row[t] : t) : -1;
   const long long env = item - (long long)t * B;
   double yk[TS_NC(L)], ck[TS_NC(L)];
-  vjp_terms(tl, S, r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
-            r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0, WD, yk, ck);
+  if (vjp_terms(tl, S, r1 >= 0 ? a.df_dvar + ((long long)r1 * B + env) * 3 * S.nee : (const double*)0,
+                r2 >= 0 ? a.df_dtac + ((long long)r2 * B + env) * 3 * S.nmark : (const double*)0, WD, yk, ck, light_only))
+    return true;                         // deferred to the pass of the env-steps whose pads can be reached
   for (int c = 0; c < TS_NC(L); ++c) {
     const int k = tl.lane + c * L;
     if (k < n) { a.vjp_y[item * n + k] = yk[c]; a.vjp_c[item * n + k] = ck[c]; }
   }
+  return false;
 }
 
 // Tactile field of ONE env-step (item = t * B + env) from the recorded trajectory: the readout pass of tsim_forward.
@@ -2516,7 +2537,7 @@ HDN void env_tactile(const Tile& tl, const SceneView& S, const FwdArgs& a, long 
   tl.tile_sync();
   kinematics(S, in, WD, false);
   tactile_values(tl, S, WD, a.tac_out + ((long long)tr * B + env) * 3 * S.nmark,
-                 a.marker_body ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0);
+                 a.marker_body ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0, a.tac_prezeroed != 0);
 }
 
 // Adjoint blocks G0 = dg/dq0, G1 = dg/dqdot0 and the control gains of ONE env-step (item = t * B + env) from the recorded

@@ -34,7 +34,7 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
   // as tsim_forward: calls of 4 steps or more read the tactile field out in a pass of its own over the trajectory
   a.defer_tac = (tac_out && q_traj && qd_traj && T >= 4) ? 1 : 0;
-  a.work_counter = 0;
+  a.work_counter = 0; a.tac_prezeroed = 0;
   // ... and write the G0 / G1 / gain blocks of the tape in a pass of their own (BDF1 scenes)
   std::vector<double> qs(q, q + (size_t)B * S.n), qds(qd, qd + (size_t)B * S.n);
   a.defer_g0 = (tape && q_traj && qd_traj && T >= 4 && !KT_MULTISTEP) ? 1 : 0;
@@ -63,11 +63,15 @@ int emu_backward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, 
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
   // the readout pull-backs in a pass of their own, as tsim_backward does (vjp_kernel), then the sweep
   std::vector<double> vy((size_t)T * B * S.n), vc((size_t)T * B * S.n);
-  a.vjp_y = vy.data(); a.vjp_c = vc.data(); a.work_counter = 0;
+  a.vjp_y = vy.data(); a.vjp_c = vc.data(); a.work_counter = 0; a.vjp_list = 0;
   {
+    // two phases as vjp_kernel: env-steps whose pads can be reached are deferred to a second sweep
     std::vector<Work<Dual> > wv(1);
     HostTile tv;
-    for (long long item = 0; item < (long long)T * B; ++item) env_vjp(tv, S, a, item, wv[0]);
+    std::vector<long long> deferred;
+    for (long long item = 0; item < (long long)T * B; ++item)
+      if (env_vjp(tv, S, a, item, wv[0], true)) deferred.push_back(item);
+    for (size_t i = 0; i < deferred.size(); ++i) env_vjp(tv, S, a, deferred[i], wv[0], false);
   }
   std::vector<Work<Dual> > wb(1);
   HostTile tl;
