@@ -15,6 +15,6 @@ tail -c 3000 $OUT/${TAG}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --horizon 40 --e2e-steps 1 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 # full capture of the two kernels (small horizon keeps the ~40 replays short)
-ncu --set full --clock-control none --import-source on -k regex:'fwd_kernel|tape_kernel|tac_kernel|vjp_kernel|bwd_kernel' -c 5 -f -o $OUT/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:'fwd_kernel|tape_kernel|tac_kernel|vjp_kernel|bwd_kernel' -c 6 -f -o $OUT/${TAG}_prof \
     python tools/perf_probe.py --B 4096 --T 20 --lanes 8 --reps 1 --grad-only > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
