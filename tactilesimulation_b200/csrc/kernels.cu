@@ -161,6 +161,16 @@ struct DevTile {
 #ifndef TS_BPS
 #define TS_BPS 1
 #endif
+// ... of the read-out / pull-back passes (tac_kernel, vjp_kernel): value-heavy marker loops that gain from occupancy
+// (variant 8: two blocks of 128-register threads per SM, tac_kernel 5.2 -> 4.0 ms, vjp_kernel 6.0 -> 5.6 ms; the tile
+// regions of the larger variants do not fit twice in shared memory)
+#ifndef TS_PASS_BPS
+#if TS_VARIANT == 8
+#define TS_PASS_BPS 2
+#else
+#define TS_PASS_BPS 1
+#endif
+#endif
 
 // stage the scene blob in shared memory (doubles first, then ints, 8-byte aligned)
 // nd = doubles BEFORE the marker table; the markers (the bulk of a scene with dense sensors) stay in global memory
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
 // Tactile fields of all T x B env-steps of a forward call (env_tactile), one tile per env-step, env-steps drawn from a
 // counter like in vjp_kernel.
 template <int LPE>
-__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tac_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
+__global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) tac_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, in
 // Two launches: phase 0 takes every env-step, finishes those whose pads nothing can reach (kinematics + variables
 // only) and lists the others; phase 1 takes the listed ones -- so the tiles of a warp run work of the same kind.
 template <int LPE>
-__global__ void __launch_bounds__(TS_BLOCK, TS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a,
+__global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a,
                                                                int phase) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
@@ -372,12 +382,12 @@ static size_t scene_smem(const tsim_scene* s) {
 }
 
 template <class K>
-static int prep(K kern, size_t smem) {
+static int prep(K kern, size_t smem, int bps = TS_BPS) {
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one block per SM: ask for no more shared memory than the block uses, the rest of the 256 KB is L1
   // for the per-lane tangents (local memory)
 #ifndef TS_NO_CARVEOUT
-  int pct = (int)((smem + 1024) * TS_BPS * 100 / (228 * 1024)) + 1;
+  int pct = (int)((smem + 1024) * bps * 100 / (228 * 1024)) + 1;
   if (pct > 100) pct = 100;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
 #endif
@@ -571,11 +581,11 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   CK(cudaEventRecord(s->ev[2], st));
   if (tac_pass) {
 #if TS_MAXN <= 8
-    if (s->lanes == 8) { if (prep(tac_kernel<8>, smem)) return 1; tac_kernel<8><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    if (s->lanes == 8) { if (prep(tac_kernel<8>, smem, TS_PASS_BPS)) return 1; tac_kernel<8><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
     else
 #endif
-    if (s->lanes == 16) { if (prep(tac_kernel<16>, smem)) return 1; tac_kernel<16><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else { if (prep(tac_kernel<32>, smem)) return 1; tac_kernel<32><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    if (s->lanes == 16) { if (prep(tac_kernel<16>, smem, TS_PASS_BPS)) return 1; tac_kernel<16><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+    else { if (prep(tac_kernel<32>, smem, TS_PASS_BPS)) return 1; tac_kernel<32><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(s->ev[3], st));
@@ -640,14 +650,14 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
     const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
-    const int vgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
+    const int vgrid = (int)(want < (long long)nsm * TS_PASS_BPS ? want : (long long)nsm * TS_PASS_BPS);
     for (int phase = 0; phase < 2; ++phase) {
 #if TS_MAXN <= 8
-      if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem, TS_PASS_BPS)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
       else
 #endif
-      if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
-      else { if (prep(vjp_kernel<32>, smem)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem, TS_PASS_BPS)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
+      else { if (prep(vjp_kernel<32>, smem, TS_PASS_BPS)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
       CK(cudaGetLastError());
     }
   }
