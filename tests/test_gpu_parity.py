@@ -329,3 +329,42 @@ def test_spherical_exp_chain_matches_reference():
             assert rel_err(var[t, e], g["var"][t]) <= 1e-9, (t, e)
             assert rel_err(tac[t, e], g["tactile"][t]) <= 1e-8, (t, e)
             assert _ids(cm[t, e]) == [int(x) for x in g["ground_ids"][t] if x >= 0], (t, e)
+
+
+def test_trajectory_only_passes_equal_the_in_loop_evaluation():
+    """TSIM_OPT_TAC_PASS / TAPE_PASS / VJP_PASS (tactile read-out, G0 / G1 tape blocks, cotangent pull-back in passes of
+    their own over the recorded trajectory, the default) against the evaluation inside the step loop / reverse sweep:
+    the same code on the same inputs.  The trajectory is bit-identical; fields, tape and gradients agree to rounding
+    (different kernels, so fused multiply-adds may be placed differently)."""
+    g = np.load(os.path.join(GOLDEN, "pusher32x13_episodic_s0.npz"))
+    T, B = g["u"].shape[0], 40
+    rng = np.random.default_rng(5)
+    q0 = np.tile(g["q0"], (B, 1))
+    q0[:, 4] += rng.uniform(-0.01, 0.01, B)
+    u = np.tile(g["u"][:, None, :], (1, B, 1))
+    u[:, :, :3] += 0.05 * rng.normal(size=(T, B, 3))
+    res = []
+    for on in (1, 0):
+        sim = _sim(g)
+        for key in (2, 3, 4):
+            sim.set_option(key, on)
+        dev = sim.device
+        q, qd = torch.tensor(q0, device=dev), torch.zeros((B, 7), dtype=torch.float64, device=dev)
+        ut = torch.tensor(u, device=dev).contiguous()
+        out = sim.forward(q, qd, ut, T, grad=True, want_status=True)
+        dq = torch.ones_like(out["q_traj"])
+        dv = torch.ones_like(out["var"])
+        dt = torch.full_like(out["tactile"], 1e-3)
+        bw = sim.backward(out, ut, T, dq, dv, dt, want_q0=True)
+        kt = sim.kernel_times()
+        assert (kt["tac_kernel"] is not None) == bool(on) and (kt["tape_kernel"] is not None) == bool(on)
+        assert (kt["vjp_kernel"] is not None) == bool(on)
+        res.append({k: v.cpu().numpy() for k, v in dict(q=out["q_traj"], tac=out["tactile"], tape=out["tape"], var=out["var"],
+                                                         du=bw["df_du"], dq0=bw["df_dq0"], dqd0=bw["df_dqdot0"]).items()})
+    a, b = res
+    assert float(np.abs(a["tac"]).max()) > 0
+    assert np.array_equal(a["q"], b["q"]) and np.array_equal(a["var"], b["var"])
+    assert rel_err(a["tac"], b["tac"]) <= 1e-13
+    assert rel_err(a["tape"], b["tape"]) <= 1e-13
+    for k in ("du", "dq0", "dqd0"):
+        assert rel_err(a[k], b[k]) <= 1e-10, k
