@@ -3,7 +3,7 @@
 // The kernels are compiled three times from csrc/kernels.cu with different compile-time capacities
 // (kernel_layout.h): variant 8 (<= 8 reduced dofs, 8 lanes per environment: TactilePush), variant 16
 // (<= 16 reduced dofs, 16 lanes per environment: DClaw, TactileInsertion, StableGrasp) and variant 17 (variant 16
-// plus sphere primitives, free3d-exp joints, BDF2 / SDIRK2 integration; forward only: RollingBall).  Each variant
+// plus sphere primitives, free3d-exp joints, BDF2 / SDIRK2 integration: RollingBall).  Each variant
 // exports the whole ABI under suffixed names (tsim_*_v8 / _v16 / _v17); this file owns the public names, picks
 // the smallest variant a scene fits at tsim_scene_create time and forwards every other call to it.
 #include <stdint.h>

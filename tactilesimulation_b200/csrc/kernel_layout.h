@@ -21,8 +21,8 @@
 #define TS_VARIANT 8
 #endif
 #if TS_VARIANT == 17
-// variant 17 = the capacities of variant 16 plus the forward-only features of the rolling-ball scene
-// (BASELINE configs[0]): sphere primitives, free3d-exp joints, BDF2 / SDIRK2 time integration, dense point sets
+// variant 17 = the capacities of variant 16 plus the features of the rolling-ball scene (BASELINE configs[0]):
+// sphere primitives, free3d-exp joints, dense point sets, BDF2 / SDIRK2 time integration (the adjoint is BDF1's)
 #define KT_MAXJ 12
 #define KT_MAXN 16
 #define KT_MAXB 24
@@ -34,7 +34,7 @@
 #define KT_POS_MOTOR 1
 #define KT_SPHERE 1      // sphere SDF primitives (contact force, tactile candidates, ground contact of a sphere)
 #define KT_EXP3D 1       // free3d-exp joints
-#define KT_MULTISTEP 1   // BDF2 / SDIRK2 integrators (no adjoint: the reference has none for them on this path)
+#define KT_MULTISTEP 1   // BDF2 / SDIRK2 integrators (forward only: the tactile adjoint of the reference is backward_BDF1)
 #elif TS_VARIANT == 16
 #define KT_MAXJ 12       // moving joints
 #define KT_MAXN 16       // reduced dofs

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) tac_kernel(const int* i
   }
 }
 
-#if !KT_MULTISTEP     // variant 17 is forward-only (no adjoint of BDF2 / SDIRK2, sphere tactile VJP not written)
+// (the adjoint exists for BDF1 scenes; tsim_forward / tsim_backward refuse a tape for the other integrators)
 // G0 / G1 / gain blocks of the tape for all T x B env-steps of a forward call (env_tape), env-steps drawn from a counter.
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tape_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) vjp_kernel(const int* i
     __syncwarp();
   }
 }
-#endif
 
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni, const double* db, int nd, int B,
@@ -518,10 +517,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   const bool big = T >= 4 && (long long)T * B < (1ll << 31) - 64;
   const bool tac_pass = tac_out && s->opts[TSIM_OPT_TAC_PASS] != 0 && big;
   // ... and so are the G0 / G1 / gain blocks of the tape (tape_kernel), which need the state at the start of the call
-  bool tape_pass = false;
-#if !KT_MULTISTEP
-  tape_pass = tape && q_traj && qd_traj && s->opts[TSIM_OPT_TAPE_PASS] != 0 && big;
-#endif
+  const bool tape_pass = tape && q_traj && qd_traj && s->opts[TSIM_OPT_TAPE_PASS] != 0 && big;
   a.defer_g0 = 0; a.q_start = 0; a.qd_start = 0; a.tape_order = 0;
   if (tac_pass || tape_pass) {
     const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R], nst = (size_t)B * s->sizes[TSIM_NDOF_R];
@@ -567,7 +563,6 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
     tgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
   }
-#if !KT_MULTISTEP
   if (tape_pass) {
 #if TS_MAXN <= 8
     if (s->lanes == 8) { if (prep(tape_kernel<8>, smem)) return 1; tape_kernel<8><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
@@ -577,7 +572,6 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     else { if (prep(tape_kernel<32>, smem)) return 1; tape_kernel<32><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
     CK(cudaGetLastError());
   }
-#endif
   CK(cudaEventRecord(s->ev[2], st));
   if (tac_pass) {
 #if TS_MAXN <= 8
@@ -618,9 +612,8 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
                   const int32_t* dtac_row, double* carry, double* df_du, double* df_dq0, double* df_dqdot0,
                   void* stream) {
   if (!s) return fail("tsim_backward: null scene");
-#if KT_MULTISTEP
-  return fail("tsim_backward: scenes with sphere primitives, free3d-exp joints or BDF2 / SDIRK2 integration are forward-only");
-#else
+  if (s->sizes[TSIM_INTEGRATOR] != TSIM_INT_BDF1)
+    return fail("tsim_backward: the adjoint exists for BDF1 scenes only (as Simulation::backward of the reference)");
   if (B <= 0 || T <= 0) return fail("tsim_backward: bad batch or step count");
   if (!q_traj || !qd_traj || !u || !tape || !carry)
     return fail("tsim_backward: q_traj, qd_traj, u, tape and carry are required (run tsim_forward with a tape first)");
@@ -673,7 +666,6 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   CK(cudaEventRecord(s->ev[6], st));
   if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;
-#endif
 }
 
 int tsim_scene_kernel_times(const tsim_scene* s, double* ms) {

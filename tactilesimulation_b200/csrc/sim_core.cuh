@@ -1966,7 +1966,7 @@ HDN bool tactile_vjp(const Tile& tl, const SceneView& S, WK& W, int si, const do
         const double eu = dot3(e, H.u);
         cross3(tbar, ph2, tw);
         for (int i = 0; i < 3; ++i) ebar[i] = -H.s * Fbb[i] + ddbar * H.u[i] - eu * tbar[i] - etb * H.u[i] + H.d * tw[i];
-        ebar[2] = 0.0;
+        if (!(KT_SPHERE && H.sph)) ebar[2] = 0.0;        // cylinder: e is radial in the x-y plane; sphere: in all three
         const double ee = dot3(e, ebar);
         for (int i = 0; i < 3; ++i) xbar[i] = dbar * e[i] + (ebar[i] - e[i] * ee) / H.rad;
       } else {

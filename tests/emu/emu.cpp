@@ -37,7 +37,7 @@ int emu_forward(const int32_t* ibuf, const double* dbuf, int32_t B, int32_t T, d
   a.work_counter = 0; a.tac_prezeroed = 0;
   // ... and write the G0 / G1 / gain blocks of the tape in a pass of their own (BDF1 scenes)
   std::vector<double> qs(q, q + (size_t)B * S.n), qds(qd, qd + (size_t)B * S.n);
-  a.defer_g0 = (tape && q_traj && qd_traj && T >= 4 && !KT_MULTISTEP) ? 1 : 0;
+  a.defer_g0 = (tape && q_traj && qd_traj && T >= 4) ? 1 : 0;
   a.q_start = qs.data(); a.qd_start = qds.data(); a.tape_order = 0;
   std::vector<Work<Dual> > wb(1);
   HostTile tl;

@@ -297,6 +297,53 @@ def rolling_ball_case():
                 frames200=np.array(frames200), tactile200_idx=bi, tactile200_val=bv)
 
 
+def rolling_ball_bdf1_case(T, seed):
+    """The rolling-ball scene (40x40 markers) under BDF1 with Simulation::backward(): the adjoint through the free3d-exp
+    joint, the sphere SDF (ground, pad contact, tactile field) and the 2168-point pad.  Inputs: the script's action
+    schedule compressed to T steps (press, then roll in x)."""
+    adir = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_pad")
+    src = os.path.join(adir, "tactile_pad_40x40.xml")
+    xml = os.path.join(adir, "tactile_pad_40x40_bdf1.xml")
+    txt = open(src).read()
+    assert 'integrator="BDF2"' in txt
+    open(xml, "w").write(txt.replace('integrator="BDF2"', 'integrator="BDF1"'))
+    sim, probe, sc = redmax_py.Simulation(xml), redmax_probe.ProbeSimulation(xml), compile_scene(xml)
+    n, nt, nu = sim.ndof_r, sim.ndof_tactile, sim.ndof_u
+    u = np.zeros((T, nu))
+    u[:, 2] = 0.2
+    u[T // 2:, 0] = 0.1
+    q0 = np.zeros(n)
+    q0[2] = -0.012                      # pad just above the ball: contact within a few steps
+    for s_ in (sim, probe):
+        s_.set_state_init(q0, np.zeros(n))
+        s_.reset(True)
+    q, qd, tac, gp, mb = [], [], [], [], []
+    for t in range(T):
+        for s_ in (sim, probe):
+            s_.set_u(u[t])
+            s_.forward(1)
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+        cs = probe.contact_sets()
+        gp.append(cs["gp"][0])
+        mb.append(np.asarray(cs["marker_body"][0], dtype=np.int32))
+    rng = np.random.default_rng(1000 + seed)
+    df_dq = rng.normal(size=(T, n))
+    df_dtac = 1e-3 * rng.normal(size=(T, nt))
+    bi = sim.backward_info
+    bi.set_flags(True, True, False, True)
+    bi.df_dq, bi.df_dtactile = df_dq.reshape(-1), df_dtac.reshape(-1)
+    bi.df_dq0, bi.df_dqdot0, bi.df_du = np.zeros(n), np.zeros(n), np.zeros(nu * T)
+    sim.backward()
+    br = sim.backward_results
+    ib, db = sc.pack()
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(n), u=u, q=np.array(q), qd=np.array(qd), tactile=np.array(tac),
+                gp_ids=pad_ids(gp, max(max(len(x) for x in gp), 1)), marker_body=np.array(mb, dtype=np.int32),
+                cot_seed=1000 + seed,      # df_dq = N(0,1) [T,n], df_dtactile = 1e-3 N(0,1) [T,nt] from default_rng(cot_seed), in this order
+                df_dq0=np.array(br.df_dq0), df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, nu))
+
+
 def integrators_case(T, seed):
     """The TactilePush scene under the other two integrators of DH/Simulation.cpp:1076-1092 (forward only: the
     reference has no adjoint for them on this path either): options.integrator = BDF2 (SDIRK2 start-up step) and
@@ -424,6 +471,7 @@ def main():
         "rollingball_bdf2_s0": rolling_ball_case,
         "pusher13x10_integrators_s0": lambda: integrators_case(40, 0),
         "spherical_euler_bdf1_s0": lambda: spherical_euler_case(60, 0),
+        "rollingball_bdf1_adjoint_s0": lambda: rolling_ball_bdf1_case(60, 0),
         "spherical_exp_bdf2_s0": lambda: spherical_exp_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate

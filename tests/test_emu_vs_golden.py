@@ -239,3 +239,26 @@ def test_emulated_spherical_exp_chain_matches_reference():
         assert rel_err(out["var"][t, 0], g["var"][t]) <= 1e-9, t
         assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
         assert emu_lib.mask_to_ids(out["cmask"][t, 0]) == [int(x) for x in g["ground_ids"][t] if x >= 0], t
+
+
+def test_emulated_rolling_ball_adjoint_matches_reference():
+    """The rolling-ball scene under BDF1 with Simulation::backward(): adjoint through the free3d-exp joint, the sphere SDF
+    (ground point, pad contact, tactile field with its hand-written reverse mode) and the 2168-point pad; kernel variant 17."""
+    g = np.load(os.path.join(GOLDEN, "rollingball_bdf1_adjoint_s0.npz"))
+    T, n = g["u"].shape[0], len(g["q0"])
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    assert float(np.abs(g["tactile"]).max()) > 0 and int((g["gp_ids"] >= 0).sum()) > 0
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, 1:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], t
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
+    rng = np.random.default_rng(int(g["cot_seed"]))
+    df_dq = rng.normal(size=(T, n))
+    df_dtac = 1e-3 * rng.normal(size=(T, g["tactile"].shape[1]))
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], df_dq[:, None, :], None, df_dtac[:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6

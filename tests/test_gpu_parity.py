@@ -368,3 +368,37 @@ def test_trajectory_only_passes_equal_the_in_loop_evaluation():
     assert rel_err(a["tape"], b["tape"]) <= 1e-13
     for k in ("du", "dq0", "dqd0"):
         assert rel_err(a[k], b[k]) <= 1e-10, k
+
+
+def test_rolling_ball_adjoint_matches_reference():
+    """The rolling-ball scene under BDF1 with Simulation::backward() (kernel variant 17): adjoint through the free3d-exp
+    joint, the sphere SDF (ground point, pad contact, tactile field) and the 2168-point pad."""
+    from tactilesimulation_b200.sim import BatchedSim
+    g = np.load(os.path.join(GOLDEN, "rollingball_bdf1_adjoint_s0.npz"))
+    sim = BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0")
+    assert sim.integrator == 0
+    dev = sim.device
+    T, B, n = g["u"].shape[0], 2, len(g["q0"])
+    q = torch.tensor(np.tile(g["q0"], (B, 1)), device=dev)
+    qd = torch.zeros_like(q)
+    u = torch.tensor(np.tile(g["u"][:, None, :], (1, B, 1)), device=dev).contiguous()
+    out = sim.forward(q, qd, u, T, grad=True, want_status=True, want_contacts=True)
+    qt, tac = out["q_traj"].cpu().numpy(), out["tactile"].cpu().numpy()
+    cm, mb = out["contact_masks"].cpu().numpy(), out["marker_body"].cpu().numpy()
+    assert int((out["status"] >> 16).max().item()) == 0
+    for e in range(B):
+        for t in range(T):
+            assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
+            assert rel_err(tac[t, e], g["tactile"][t]) <= 1e-8, (t, e)
+            assert _ids(cm[t, e, 1:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], (t, e)
+            assert np.array_equal(mb[t, e], g["marker_body"][t]), (t, e)
+    rng = np.random.default_rng(int(g["cot_seed"]))
+    df_dq = rng.normal(size=(T, n))
+    df_dtac = 1e-3 * rng.normal(size=(T, g["tactile"].shape[1]))
+    dq = torch.tensor(np.tile(df_dq[:, None, :], (1, B, 1)), device=dev).contiguous()
+    dt = torch.tensor(np.tile(df_dtac[:, None, :], (1, B, 1)), device=dev).contiguous()
+    bw = sim.backward(out, u, T, dq, None, dt, want_q0=True)
+    for e in range(B):
+        assert rel_err(bw["df_du"][:, e].cpu().numpy(), g["df_du"]) <= 1e-6
+        assert rel_err(bw["df_dq0"][e].cpu().numpy(), g["df_dq0"]) <= 1e-6
+        assert rel_err(bw["df_dqdot0"][e].cpu().numpy(), g["df_dqdot0"]) <= 1e-6
