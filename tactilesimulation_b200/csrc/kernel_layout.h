@@ -104,8 +104,11 @@ enum { KD_H = 0, KD_GRAV = 1, KD_TOL = 4, KD_GN = 5, KD_GX = 8, KD_HEADER = 16 }
 #define KG_ISTRIDE 4
 #define KG_DSTRIDE 4
 // general-primitive contact: int {body1, body2, point_off, point_cnt, first word in the contact bitmask output,
-// shape of body2}; dbl {kn kt mu damping r_points | bounding box of the points in the body-1 frame: lo(3) hi(3)}
-#define KP_ISTRIDE 6
+// shape of body2, offset (doubles) of the per-word boxes, -}; dbl {kn kt mu damping r_points | bounding box of the
+// points in the body-1 frame: lo(3) hi(3)}.  Per-word boxes: lo(3) hi(3) of every 32 consecutive points in the body-1
+// frame (dense point sets are walked word by word: a word whose box the primitive cannot reach is skipped).
+#define KP_ISTRIDE 8
+#define KP_WBOX 6
 #define KP_DSTRIDE 12
 #define KP_BBOX 5
 // actuator: int {moving joint, mode, uoff, ndof}; dbl {cmin[3] cmax[3] P[3] D[3]}

@@ -197,6 +197,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     od.insert(od.end(), c, c + KG_DSTRIDE);
   }
   // ---- general-primitive contacts
+  std::vector<int> gp_rec_pos;
   oi[KI_O_GP] = (int)oi.size(); oi[KI_D_GP] = (int)od.size();
   for (int f = 0; f < ngp; ++f) {
     const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
@@ -207,8 +208,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     if (shape2 == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
     if (shape2 == TS_SH_SPHERE && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
     if (r[3] > 32 * KT_MAXPW) return "scene exceeds the compiled capacity (sampled points per general body)";
-    int rec[KP_ISTRIDE] = {r[0], r[1], r[2], r[3], cmw, shape2};
+    int rec[KP_ISTRIDE] = {r[0], r[1], r[2], r[3], cmw, shape2, 0, 0};
     cmw += (r[3] + 31) / 32;
+    gp_rec_pos.push_back((int)oi.size());
     oi.insert(oi.end(), rec, rec + KP_ISTRIDE);
     double d[KP_DSTRIDE] = {c[0], c[1], c[2], c[3], 0};
     for (int i = 0; i < 3; ++i) { d[KP_BBOX + i] = 1e300; d[KP_BBOX + 3 + i] = -1e300; }
@@ -273,6 +275,20 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   }
   oi[KI_D_POINTS] = (int)od.size();
   od.insert(od.end(), P, P + 3 * npoints);
+  // per-word boxes of the general-primitive point sets
+  for (int f = 0; f < ngp; ++f) {
+    const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
+    oi[gp_rec_pos[f] + KP_WBOX] = (int)od.size();
+    for (int w0 = 0; w0 < r[3]; w0 += 32) {
+      double bx[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+      for (int k = w0; k < r[3] && k < w0 + 32; ++k)
+        for (int i = 0; i < 3; ++i) {
+          bx[i] = fmin(bx[i], P[3 * (r[2] + k) + i]);
+          bx[3 + i] = fmax(bx[3 + i], P[3 * (r[2] + k) + i]);
+        }
+      od.insert(od.end(), bx, bx + 6);
+    }
+  }
   oi[KI_CMW] = cmw;
   // markers last (the kernels stage everything before them in shared memory): position + per-marker axes
   oi[KI_D_MARKERS] = (int)od.size();

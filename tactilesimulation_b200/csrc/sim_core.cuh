@@ -998,7 +998,38 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
         maybe = !bbox_outside_box(R21, r21, c + KP_BBOX, c + KP_BBOX + 3, hs);
       }
       // detection (values only), points dealt to the lanes of the tile, results gathered by ballot
-      if (maybe) {
+      if (KT_SPHERE && maybe && sph) {
+        // dense point sets against a sphere, word by word: the centre in the body-1 frame against the box of each
+        // 32 consecutive points (exact-safe with the cull margin); only words the sphere can reach are tested
+        const double* wbox = S.db + r[KP_WBOX];
+        double dc[3], c1[3];
+        for (int i = 0; i < 3; ++i) dc[i] = P.p2v[i] - P.p1v[i];
+        mtv3(P.R1v, dc, c1);
+        const double rs = hs[0] + TS_CULL_MARGIN;
+        for (int w0 = 0; w0 < pc; w0 += 32) {
+          const double* bx = wbox + 6 * (w0 >> 5);
+          double d2 = 0.0;
+          for (int i = 0; i < 3; ++i) {
+            const double lo = bx[i] - c1[i], hi = c1[i] - bx[3 + i];
+            const double e = lo > 0.0 ? lo : (hi > 0.0 ? hi : 0.0);
+            d2 += e * e;
+          }
+          if (d2 > rs * rs) continue;
+          for (int base = w0; base < pc && base < w0 + 32; base += L) {
+            const int k = base + tl.lane;
+            bool in = false;
+            if (k < pc && k < w0 + 32) {
+              const double* xi1 = S.db + S.d_points + 3 * (po + k);
+              double xwv[3];
+              mv3(P.R1v, xi1, xwv);
+              for (int i = 0; i < 3; ++i) xwv[i] = xwv[i] + P.p1v[i];
+              in = sphere_inside_world(P.p2v, xwv, hs[0]);
+            }
+            const unsigned bits = tl.ballot(in);
+            act[base >> 5] |= bits << (base & 31);
+          }
+        }
+      } else if (maybe) {
         for (int base = 0; base < pc; base += L) {
           const int k = base + tl.lane;
           bool in = false;
