@@ -17,6 +17,11 @@
  *                           df_dtactile in, backward_results.df_du/df_dq0/df_dqdot0 out
  *                           DH/python_interface.cpp:64-83,232-236 ; DH/Simulation.cpp:1569-1713,1876-1971
  *
+ * A scene handle is not thread-safe (like a Simulation object of the reference): issue the calls on one handle from one
+ * thread, on one stream at a time.  tsim_forward / tsim_backward take their scratch (work counters, per-env-step
+ * vectors of the trajectory-only passes) from the device's stream-ordered pool (cudaMallocAsync) and return it before
+ * they return; nothing is retained between calls except the pool's cache.
+ *
  * Conventions: all data pointers are DEVICE pointers (fp64, C-contiguous, env-major inside a
  * step: [step][env][component]); `stream` is a cudaStream_t passed as void*; every call is
  * asynchronous on that stream.  Functions return 0 on success, non-zero on error with a message
