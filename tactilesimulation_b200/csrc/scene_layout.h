@@ -18,10 +18,12 @@
 #define TS_JT_FREE3D_EXP 6      // q = (p, r): translation + exponential coordinates (DH/Joint/JointFree3DExp.cpp)
 #define TS_JT_SPHERICAL_EULER 7 // q = r: XYZ Euler angles (DH/Joint/JointSphericalEuler.cpp)
 #define TS_JT_SPHERICAL_EXP 8   // q = r: exponential coordinates (DH/Joint/JointSphericalExp.cpp)
+#define TS_JT_FREE2D 9          // q = (x, y, theta): planar motion in the joint's x-y plane (DH/Joint/JointFree2D.cpp)
 #define TS_SH_NONE 0
 #define TS_SH_CUBOID 1
 #define TS_SH_CYLINDER 2
 #define TS_SH_SPHERE 3
+#define TS_SH_CAPSULE 4         // axis z; blob: (radius, length, -)   (DH/Body/BodyCapsule.cpp)
 // time integrators (DH/Simulation.cpp:1076-1092); header slot TS_I_INTEGRATOR, 0 in blobs written before it existed
 #define TS_INT_BDF1 0
 #define TS_INT_BDF2 1           // first step SDIRK2, then BDF2

@@ -67,7 +67,8 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     if (par >= j) return "joints are not in parent-first order";
     if ((jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER) && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler / spherical-euler joints)";
     if ((jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP) && !KT_EXP3D) return "scene exceeds the compiled capacity (free3d-exp / spherical-exp joints)";
-    if (jt < TS_JT_FIXED || jt > TS_JT_SPHERICAL_EXP) return "unknown joint type";
+    if (jt == TS_JT_FREE2D && !KT_FREE3D) return "scene exceeds the compiled capacity (free2d joints)";
+    if (jt < TS_JT_FIXED || jt > TS_JT_FREE2D) return "unknown joint type";
     const Xf e0 = xf_load(JD + j * TS_JD_STRIDE + TS_JD_RPJ, JD + j * TS_JD_STRIDE + TS_JD_PPJ);
     const Xf up = (par < 0) ? e0 : xf_mul(erel[par], e0);
     if (jt == TS_JT_FIXED) {
@@ -166,7 +167,11 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     for (int i = 0; i < 9; ++i) d[KB_RMI + i] = emi.R[i];
     for (int i = 0; i < 3; ++i) d[KB_PMI + i] = emi.p[i];
     for (int i = 0; i < 6; ++i) d[KB_INERTIA + i] = s[TS_JD_INERTIA + i];
-    if (J[j * TS_JI_STRIDE + 4] == TS_SH_CYLINDER) {      // blob: (radius, length, -)
+    if (J[j * TS_JI_STRIDE + 4] == TS_SH_CAPSULE) {        // blob: (radius, length, -)
+      d[KB_HALF] = s[TS_JD_HALF];
+      d[KB_HALF + 1] = s[TS_JD_HALF + 1] / 2.;
+      d[KB_RBOUND] = d[KB_HALF] + d[KB_HALF + 1];
+    } else if (J[j * TS_JI_STRIDE + 4] == TS_SH_CYLINDER) {      // blob: (radius, length, -)
       d[KB_HALF] = s[TS_JD_HALF];
       d[KB_HALF + 1] = s[TS_JD_HALF + 1] / 2.;
       d[KB_RBOUND] = sqrt(d[KB_HALF] * d[KB_HALF] + d[KB_HALF + 1] * d[KB_HALF + 1]);
@@ -203,8 +208,9 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     const int* r = ib + ib[TS_I_OFF_GP] + f * TS_PI_STRIDE;
     const double* c = db + ib[TS_I_DOFF_GP] + f * TS_CD_STRIDE;
     const int shape2 = J[r[1] * TS_JI_STRIDE + 4];
-    if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER && shape2 != TS_SH_SPHERE)
-      return "general-primitive contact: only cuboid, cylinder and sphere primitives are supported";
+    if (shape2 != TS_SH_CUBOID && shape2 != TS_SH_CYLINDER && shape2 != TS_SH_SPHERE && shape2 != TS_SH_CAPSULE)
+      return "general-primitive contact: only cuboid, cylinder, sphere and capsule primitives are supported";
+    if (shape2 == TS_SH_CAPSULE && !KT_SPHERE) return "scene exceeds the compiled capacity (capsule primitives)";
     if (shape2 == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
     if (shape2 == TS_SH_SPHERE && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
     if (r[3] > 32 * KT_MAXPW) return "scene exceeds the compiled capacity (sampled points per general body)";
@@ -254,7 +260,8 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
     if (r[3] > KT_MAXCAND) return "scene exceeds the compiled capacity (tactile candidate bodies)";
     for (int k = 0; k < r[3]; ++k) {
       const int sh = J[r[4 + k] * TS_JI_STRIDE + 4];
-      if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER && sh != TS_SH_SPHERE) return "tactile candidates must be cuboids, cylinders or spheres";
+      if (sh != TS_SH_CUBOID && sh != TS_SH_CYLINDER && sh != TS_SH_SPHERE && sh != TS_SH_CAPSULE) return "tactile candidates must be cuboids, cylinders, spheres or capsules";
+      if (sh == TS_SH_CAPSULE && !KT_SPHERE) return "scene exceeds the compiled capacity (capsule primitives)";
       if (sh == TS_SH_CYLINDER && !KT_CYLINDER) return "scene exceeds the compiled capacity (cylinder primitives)";
       if (sh == TS_SH_SPHERE && !KT_SPHERE) return "scene exceeds the compiled capacity (sphere primitives)";
     }

@@ -428,6 +428,42 @@ HDN void kinematics(const SceneView& S, const In& in, WK& W, bool dyn) {
         sq[i] = w[i] * in.qd(qo); sq[3 + i] = m[i] * in.qd(qo);
         if (dyn) { sl[i] = w[i] * in.dl(qo); sl[3 + i] = m[i] * in.dl(qo); }
       }
+    } else if (KT_FREE3D && jt == TS_JT_FREE2D) {
+      // q = (x, y, theta): Q = [Rz(theta) (x, y, 0); 0 1]   (DH/Joint/JointFree2D.cpp).  The free3d-euler chart below
+      // restricted to (p_x, p_y, r_3): twist xi = (theta_dot e_z, pdot + p x theta_dot e_z) about a's origin; the axis
+      // does not move, so the velocity-product term is xi_dot = (0, pdot x theta_dot e_z).
+      T s3, c3;
+      dsincos(in.q(qo + 2), s3, c3);
+      T Rq[9];
+      Rq[0] = c3; Rq[1] = -s3; Rq[2] = 0.0;
+      Rq[3] = s3; Rq[4] = c3; Rq[5] = 0.0;
+      Rq[6] = 0.0; Rq[7] = 0.0; Rq[8] = 1.0;
+      mm3(Ra, Rq, R0);
+      T pq[3], t[3];
+      pq[0] = in.q(qo); pq[1] = in.q(qo + 1); pq[2] = 0.0;
+      mv3(Ra, pq, t);
+      for (int i = 0; i < 3; ++i) p0[i] = pa[i] + t[i];
+      for (int pass = 0; pass < (dyn ? 2 : 1); ++pass) {
+        T pd[3], wa[3], va[3], c[3];
+        pd[0] = pass ? in.dl(qo) : in.qd(qo); pd[1] = pass ? in.dl(qo + 1) : in.qd(qo + 1); pd[2] = 0.0;
+        wa[0] = 0.0; wa[1] = 0.0; wa[2] = pass ? in.dl(qo + 2) : in.qd(qo + 2);
+        cross3(pq, wa, c);
+        for (int i = 0; i < 3; ++i) va[i] = pd[i] + c[i];
+        T* so = pass ? sl : sq;
+        T w[3], v[3], pw[3];
+        mv3(Ra, wa, w);
+        mv3(Ra, va, v);
+        cross3(pa, w, pw);
+        for (int i = 0; i < 3; ++i) { so[i] = w[i]; so[3 + i] = v[i] + pw[i]; }
+      }
+      if (dyn) {
+        T pd[3], wa[3], vd[3], v[3];
+        pd[0] = in.qd(qo); pd[1] = in.qd(qo + 1); pd[2] = 0.0;
+        wa[0] = 0.0; wa[1] = 0.0; wa[2] = in.qd(qo + 2);
+        cross3(pd, wa, vd);
+        mv3(Ra, vd, v);
+        for (int i = 0; i < 3; ++i) sl[3 + i] = sl[3 + i] + h2 * v[i];
+      }
     } else if (KT_FREE3D && (jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER)) {
       // (spherical-euler, DH/Joint/JointSphericalEuler.cpp: the rotation alone, q = r, p = 0)
       const bool trans = jt == TS_JT_FREE3D_EULER;
@@ -897,6 +933,20 @@ HD bool cylinder_inside_world(const double* R2, const double* p2, const double* 
   return sqrt(x[0] * x[0] + x[1] * x[1]) - rh[0] < 0.0;
 }
 
+// capsule SDF (DH/Body/BodyCapsule.cpp:126-138): x = E_i0 xw, distance to the segment (0,0,[-s,s]) minus the radius
+HD bool capsule_inside_world(const double* R2, const double* p2, const double* xw, const double* rh) {
+  double t[3], x[3];
+  mtv3(R2, p2, t);
+  mtv3(R2, xw, x);
+  for (int i = 0; i < 3; ++i) x[i] = x[i] + (-t[i]);
+  const double s = rh[1];
+  double d;
+  if (x[2] < -s) d = sqrt(x[0] * x[0] + x[1] * x[1] + (x[2] - (-s)) * (x[2] - (-s))) - rh[0];
+  else if (x[2] > s) d = sqrt(x[0] * x[0] + x[1] * x[1] + (x[2] - s) * (x[2] - s)) - rh[0];
+  else d = sqrt(x[0] * x[0] + x[1] * x[1]) - rh[0];
+  return d < 0.0;
+}
+
 // sphere SDF (DH/Body/BodySphere.cpp:79-83): distance(xw) = |xw - p2| - radius < 0
 HD bool sphere_inside_world(const double* p2, const double* xw, double radius) {
   const double a = xw[0] - p2[0], b = xw[1] - p2[1], c = xw[2] - p2[2];
@@ -907,9 +957,11 @@ HD bool sphere_inside_world(const double* p2, const double* xw, double radius) {
 // with DH/Body/BodyCylinder.cpp:105-139): same structure as gp_point_force, the normal e = x_r / |x_r| now
 // depends on the point.  Wrenches in cylinder coordinates about the cylinder origin.
 // sph: SPHERE (DH/Body/BodySphere.cpp:79-107): the same with the 3-d radial normal e = x / |x|.
+// caps > 0: CAPSULE of half-length caps (DH/Body/BodyCapsule.cpp:140-172): radial from the nearest point of the segment
+// (0,0,[-caps, caps]) -- the cylinder formula between the caps, the sphere formula about (0,0,+-caps) beyond them.
 template <class T>
 HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* rh, double kn, double kt, double mu,
-                           double damp, T* w1, T* w2, bool sph = false) {
+                           double damp, T* w1, T* w2, bool sph = false, double caps = -1.0) {
   T ap[3], x[3];
   mv3(P.Q, xi1, ap);
   for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
@@ -917,10 +969,17 @@ HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* 
   cross3(P.w1b, ap, u);
   cross3(P.ph2, x, t3);
   for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
-  T r = (KT_SPHERE && sph) ? dsqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) : dsqrt(x[0] * x[0] + x[1] * x[1]);
+  T vz = 0.0;                            // axial component of the radial vector
+  if (KT_SPHERE && sph) vz = x[2];
+  if (KT_SPHERE && caps > 0.0) {
+    if (val(x[2]) < -caps) vz = x[2] + caps;
+    else if (val(x[2]) > caps) vz = x[2] - caps;
+  }
+  const bool zfree = KT_SPHERE && (sph || (caps > 0.0 && (val(x[2]) < -caps || val(x[2]) > caps)));
+  T r = zfree ? dsqrt(x[0] * x[0] + x[1] * x[1] + vz * vz) : dsqrt(x[0] * x[0] + x[1] * x[1]);
   T e[3];
   e[0] = x[0] / r; e[1] = x[1] / r; e[2] = 0.0;
-  if (KT_SPHERE && sph) e[2] = x[2] / r;
+  if (zfree) e[2] = vz / r;
   T d = r - rh[0];
   T ddot = dot3(e, u);
   T tb[3];
@@ -974,7 +1033,8 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     const double* c = S.db + S.d_gp + fi * KP_DSTRIDE;
     const int b1 = r[0], b2 = r[1], po = r[2], pc = r[3];
     const bool sph = KT_SPHERE && r[5] == TS_SH_SPHERE;
-    const bool cyl = (KT_CYLINDER && r[5] == TS_SH_CYLINDER) || sph;      // point-dependent normal
+    const bool cap = KT_SPHERE && r[5] == TS_SH_CAPSULE;
+    const bool cyl = (KT_CYLINDER && r[5] == TS_SH_CYLINDER) || sph || cap;      // point-dependent normal
     const int j1 = S.ib[S.o_body + b1 * KB_ISTRIDE], j2 = S.ib[S.o_body + b2 * KB_ISTRIDE];
     const double kn = c[0], kt = c[1], mu = c[2], damp = c[3];
     const double* bd2 = S.db + S.d_body + b2 * KB_DSTRIDE;
@@ -1039,7 +1099,8 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
               double xwv[3];
               mv3(P.R1v, xi1, xwv);
               for (int i = 0; i < 3; ++i) xwv[i] = xwv[i] + P.p1v[i];
-              in = sph ? sphere_inside_world(P.p2v, xwv, hs[0]) : cylinder_inside_world(P.R2v, P.p2v, xwv, hs);
+              in = sph ? sphere_inside_world(P.p2v, xwv, hs[0])
+                       : (cap ? capsule_inside_world(P.R2v, P.p2v, xwv, hs) : cylinder_inside_world(P.R2v, P.p2v, xwv, hs));
             } else {
               const int cls = cuboid_classify(R21, r21, xi1, hs);
               if (cls > 0) in = true;
@@ -1083,7 +1144,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
       while (m) {
         const int k = 32 * wd + ts_ffs(m);
         m &= m - 1;
-        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2, sph);
+        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2, sph, cap ? hs[1] : -1.0);
         else gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
       }
     }
@@ -1165,6 +1226,18 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
       cross3(p0, A + 3, pf);             // moment about the joint origin
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
       for (int i = 0; i < 3; ++i) { if (nt) g[qo + i] = dot3(tax[i], A + 3); g[ro + i] = dot3(rax[i], t); }
+    } else if (KT_FREE3D && jt == TS_JT_FREE2D) {
+      // translations along Ra e_x, Ra e_y = R0 (rows 0, 1 of Rz(theta)); rotation about Ra e_z = R0 e_z through p0
+      T s3, c3, pf[3], t[3];
+      dsincos(in.q(qo + 2), s3, c3);
+      T r0[3] = {c3, -s3, T(0.0)}, r1[3] = {s3, c3, T(0.0)}, ax0[3], ax1[3];
+      mv3(R0, r0, ax0);
+      mv3(R0, r1, ax1);
+      cross3(p0, A + 3, pf);
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      g[qo] = dot3(ax0, A + 3);
+      g[qo + 1] = dot3(ax1, A + 3);
+      g[qo + 2] = R0[2] * t[0] + R0[5] * t[1] + R0[8] * t[2];
     }
     // joint damping and one-sided limit springs                (DH/Joint/Joint.cpp:251-263)
     const double damp = jd[KJ_DAMP], lo = jd[KJ_LIMLO], hi = jd[KJ_LIMHI], lk = jd[KJ_LIMK];
@@ -1474,6 +1547,14 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
         for (int i = 0; i < 3; ++i) Sk[i] = rax[loc - nt][i];
         cross3(p0, Sk, Sk + 3);
       }
+    } else if (KT_FREE3D && jt == TS_JT_FREE2D) {
+      const double s3 = sin(qv[ji[2] + 2]), c3 = cos(qv[ji[2] + 2]);
+      if (loc == 0) { const double r0[3] = {c3, -s3, 0.0}; mv3(R0, r0, Sk + 3); }
+      else if (loc == 1) { const double r1[3] = {s3, c3, 0.0}; mv3(R0, r1, Sk + 3); }
+      else {
+        Sk[0] = R0[2]; Sk[1] = R0[5]; Sk[2] = R0[8];
+        cross3(p0, Sk, Sk + 3);
+      }
     } else { for (int i = 0; i < 3; ++i) Sk[3 + i] = R0[3 * i + loc]; }
   }
   if (jk < 0) return;
@@ -1522,6 +1603,17 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
       cross3(p0, A + 3, pf);
       for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
       for (int i = 0; i < 3; ++i) { if (nt) Mcol[qo + i] = dot3(tax[i], A + 3); Mcol[ro + i] = dot3(rax[i], t); }
+    } else if (KT_FREE3D && jt == TS_JT_FREE2D) {
+      const double s3 = sin(qv[qo + 2]), c3 = cos(qv[qo + 2]);
+      const double r0[3] = {c3, -s3, 0.0}, r1[3] = {s3, c3, 0.0};
+      double ax0[3], ax1[3], pf[3], t[3];
+      mv3(R0, r0, ax0);
+      mv3(R0, r1, ax1);
+      cross3(p0, A + 3, pf);
+      for (int i = 0; i < 3; ++i) t[i] = A[i] - pf[i];
+      Mcol[qo] = dot3(ax0, A + 3);
+      Mcol[qo + 1] = dot3(ax1, A + 3);
+      Mcol[qo + 2] = R0[2] * t[0] + R0[5] * t[1] + R0[8] * t[2];
     }
     if (par >= 0) for (int i = 0; i < 6; ++i) Wm[par][i] += A[i];
   }
@@ -1767,7 +1859,7 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
   for (int c = 0; c < nc; ++c) {
     const int b2 = sr[4 + c];
     const int sh2 = S.ib[S.o_body + b2 * KB_ISTRIDE + 1];
-    const bool cyl = (KT_CYLINDER && sh2 == TS_SH_CYLINDER) || (KT_SPHERE && sh2 == TS_SH_SPHERE);
+    const bool cyl = (KT_CYLINDER && sh2 == TS_SH_CYLINDER) || (KT_SPHERE && (sh2 == TS_SH_SPHERE || sh2 == TS_SH_CAPSULE));
     body_frame_v(S, W, b2, F.R[1 + c], F.p[1 + c], F.ph[1 + c]);
     const double rr = sd[KS_RMARK] + S.db[S.d_body + b2 * KB_DSTRIDE + KB_RBOUND] + TS_CULL_MARGIN;
     const double dx = F.p[0][0] - F.p[1 + c][0], dy = F.p[0][1] - F.p[1 + c][1], dz = F.p[0][2] - F.p[1 + c][2];
@@ -1784,7 +1876,8 @@ HDN void sensor_frames(const SceneView& S, const WK& W, const int* sr, const dou
 struct MarkerHit {
   int cand;           // index of the contacted candidate (last candidate with d < 0), -1 if none
   bool cyl;           // the candidate is a cylinder or a sphere (normal depends on the point), else a cuboid (face normal)
-  bool sph;           // ... a sphere
+  bool sph;           // ... a sphere (or the cap of a capsule): the normal has an axial component
+  double vz;          // axial component of the radial vector
   double e[3];        // contact normal in the candidate's frame
   double x[3], u[3], d, ddot, tb[3], s, tn, rad;
   bool dynamic;
@@ -1804,6 +1897,19 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
     if (!F.near[1 + c]) continue;
     const double* hs = S.db + S.d_body + sr[4 + c] * KB_DSTRIDE + KB_HALF;
     double xw[3], y[3], x[3];
+    if (KT_SPHERE && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CAPSULE) {
+      // TactileSensor.cpp:44-47 with BodyCapsule::distance; between the caps the cylinder formula, beyond them the
+      // sphere formula about the end of the axis
+      mv3(R1, xi1, xw);
+      for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+      if (!capsule_inside_world(F.R[1 + c], F.p[1 + c], xw, hs)) continue;
+      for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
+      mtv3(F.R[1 + c], y, x);
+      H.cand = c; H.cyl = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
+      H.sph = x[2] < -hs[1] || x[2] > hs[1];
+      H.vz = x[2] < -hs[1] ? x[2] + hs[1] : (x[2] > hs[1] ? x[2] - hs[1] : 0.0);
+      continue;
+    }
     if (KT_SPHERE && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_SPHERE) {
       // TactileSensor.cpp:44-47 with BodySphere::distance; the force is evaluated at x = R2^T (xw - p2)
       mv3(R1, xi1, xw);
@@ -1811,7 +1917,7 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
       if (!sphere_inside_world(F.p[1 + c], xw, hs[0])) continue;
       for (int i = 0; i < 3; ++i) y[i] = xw[i] - F.p[1 + c][i];
       mtv3(F.R[1 + c], y, x);
-      H.cand = c; H.cyl = true; H.sph = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2];
+      H.cand = c; H.cyl = true; H.sph = true; H.x[0] = x[0]; H.x[1] = x[1]; H.x[2] = x[2]; H.vz = x[2];
       continue;
     }
     if (KT_CYLINDER && S.ib[S.o_body + sr[4 + c] * KB_ISTRIDE + 1] == TS_SH_CYLINDER) {
@@ -1836,9 +1942,9 @@ HD void marker_force(const SceneView& S, const Frames& F, const int* sr, const d
   const double* hs = S.db + S.d_body + sr[4 + H.cand] * KB_DSTRIDE + KB_HALF;
   const double* R2 = F.R[1 + H.cand]; const double* ph2 = F.ph[1 + H.cand];
   if (KT_SPHERE && H.sph) {
-    H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1] + H.x[2] * H.x[2]);
+    H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1] + H.vz * H.vz);
     H.d = H.rad - hs[0];
-    H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = H.x[2] / H.rad;
+    H.e[0] = H.x[0] / H.rad; H.e[1] = H.x[1] / H.rad; H.e[2] = H.vz / H.rad;
   } else if (KT_CYLINDER && H.cyl) {
     H.rad = sqrt(H.x[0] * H.x[0] + H.x[1] * H.x[1]);
     H.d = H.rad - hs[0];
@@ -2263,7 +2369,10 @@ HDN void contact_sets(const SceneView& S, const WK& W, unsigned* mw) {
       double xw[3], y[3], x[3];
       mv3(R1, xi, xw);
       bool in;
-      if (KT_SPHERE && r[5] == TS_SH_SPHERE) {
+      if (KT_SPHERE && r[5] == TS_SH_CAPSULE) {
+        for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
+        in = capsule_inside_world(R2, p2, xw, hs);
+      } else if (KT_SPHERE && r[5] == TS_SH_SPHERE) {
         for (int i = 0; i < 3; ++i) xw[i] = xw[i] + p1[i];
         in = sphere_inside_world(p2, xw, hs[0]);
       } else if (KT_CYLINDER && r[5] == TS_SH_CYLINDER) {

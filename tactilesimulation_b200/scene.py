@@ -41,18 +41,18 @@ import numpy as np
 
 # joint types (values are shared with csrc/scene_layout.h)
 JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_PLANAR, JT_TRANSLATIONAL, JT_FREE3D_EULER, JT_FREE3D_EXP = 0, 1, 2, 3, 4, 5, 6
-JT_SPHERICAL_EULER, JT_SPHERICAL_EXP = 7, 8
+JT_SPHERICAL_EULER, JT_SPHERICAL_EXP, JT_FREE2D = 7, 8, 9
 JOINT_NDOF = {JT_FIXED: 0, JT_REVOLUTE: 1, JT_PRISMATIC: 1, JT_PLANAR: 2, JT_TRANSLATIONAL: 3, JT_FREE3D_EULER: 6,
-              JT_FREE3D_EXP: 6, JT_SPHERICAL_EULER: 3, JT_SPHERICAL_EXP: 3}
+              JT_FREE3D_EXP: 6, JT_SPHERICAL_EULER: 3, JT_SPHERICAL_EXP: 3, JT_FREE2D: 3}
 # "free3d" is the XYZ-Euler chart in the reference too (DH/Simulation_Constructor.cpp:483-484)
 JOINT_TYPES = {"fixed": JT_FIXED, "revolute": JT_REVOLUTE, "prismatic": JT_PRISMATIC,
                "planar": JT_PLANAR, "translational": JT_TRANSLATIONAL,
                "free3d": JT_FREE3D_EULER, "free3d-euler": JT_FREE3D_EULER, "free3d-exp": JT_FREE3D_EXP,
-               "spherical": JT_SPHERICAL_EULER, "spherical-euler": JT_SPHERICAL_EULER, "spherical-exp": JT_SPHERICAL_EXP}
+               "spherical": JT_SPHERICAL_EULER, "spherical-euler": JT_SPHERICAL_EULER, "spherical-exp": JT_SPHERICAL_EXP, "free2d": JT_FREE2D}
 # time integrators (DH/Simulation.cpp:1076-1092); codes shared with csrc/scene_layout.h
 INTEGRATORS = {"BDF1": 0, "BDF2": 1, "SDIRK2": 2}
 # body shapes
-SH_NONE, SH_CUBOID, SH_CYLINDER, SH_SPHERE = 0, 1, 2, 3
+SH_NONE, SH_CUBOID, SH_CYLINDER, SH_SPHERE, SH_CAPSULE = 0, 1, 2, 3, 4
 # actuator modes
 ACT_FORCE, ACT_POS = 0, 1
 
@@ -281,6 +281,16 @@ def _cylinder_points(radius, length, ares, rres):
     return np.array(pts, dtype=np.float64)
 
 
+def _capsule_points(radius, length, res):
+    """DH/Body/BodyCapsule.cpp:34-50: the two poles, then res[0] rings of res[1] points on the cylindrical part."""
+    pts = [[0.0, 0.0, length / 2.0 + radius], [0.0, 0.0, -length / 2.0 - radius]]
+    for i in range(res[0]):
+        z = i / (res[0] - 1) * length - length / 2.0
+        for j in range(res[1]):
+            pts.append([radius * math.cos(2.0 * math.pi * j / res[1]), radius * math.sin(2.0 * math.pi * j / res[1]), z])
+    return np.array(pts, dtype=np.float64)
+
+
 def compile_scene(xml_path: str) -> Scene:
     """Parse a redmax XML scene file into a :class:`Scene`."""
     if not os.path.isfile(xml_path):
@@ -440,6 +450,20 @@ def compile_scene(xml_path: str) -> Scene:
             inertia[3:] = mass
             shape, size = SH_CYLINDER, np.array([radius, length, 0.0])
             pts = _cylinder_points(radius, length, ares, rres)
+        elif btype == "capsule":
+            # DH/Simulation_Constructor.cpp:589-596, DH/Body/BodyCapsule.cpp:22-31 (axis z)
+            length = _f32(bn.get("length"))
+            radius = _f32(bn.get("radius"))
+            res = _ivec(bn.get("general_contact_resolution")) if bn.get("general_contact_resolution") else np.array([5, 4])
+            m_cy = density * length * math.pi * radius * radius
+            m_hs = density * 2.0 / 3.0 * math.pi * radius * radius * radius
+            mass = m_cy + 2.0 * m_hs
+            inertia[0] = m_cy * (length * length / 12.0 + radius * radius / 4.0) + 2.0 * m_hs * (2.0 * radius * radius / 5.0 + length * length / 2.0 + 3.0 * length * radius / 8.0)
+            inertia[1] = inertia[0]
+            inertia[2] = m_cy * radius * radius / 2.0 + 2.0 * m_hs * 2.0 * radius * radius / 5.0
+            inertia[3:] = mass
+            shape, size = SH_CAPSULE, np.array([radius, length, 0.0])
+            pts = _capsule_points(radius, length, res)
         elif btype == "sphere":
             # DH/Simulation_Constructor.cpp:597-599, DH/Body/BodySphere.cpp:17-21; no sampled contact points: a sphere
             # is a primitive body and touches the ground at one state-dependent point (CollisionDetection.cpp:17-25)
@@ -668,11 +692,11 @@ def compile_scene(xml_path: str) -> Scene:
                 sc.virtual_names.append(e.get("name", ""))
     for s in sc.sensors:
         for k in s.candidates:
-            if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE):
-                raise SceneError("tactile candidates other than cuboids, cylinders and spheres are not supported by the B200 path yet")
+            if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE, SH_CAPSULE):
+                raise SceneError("tactile candidates other than cuboids, cylinders, spheres and capsules are not supported by the B200 path yet")
     for gp in sc.gp_contacts:
-        if sc.shape[gp["body2"]] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE):
-            raise SceneError("primitive contact bodies other than cuboids, cylinders and spheres are not supported by the B200 path yet")
+        if sc.shape[gp["body2"]] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE, SH_CAPSULE):
+            raise SceneError("primitive contact bodies other than cuboids, cylinders, spheres and capsules are not supported by the B200 path yet")
     if sc.integrator not in INTEGRATORS:
         raise SceneError("Integrator " + sc.integrator + " has not been implemented.")
     return sc

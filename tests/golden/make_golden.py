@@ -297,6 +297,133 @@ def rolling_ball_case():
                 frames200=np.array(frames200), tactile200_idx=bi, tactile200_val=bv)
 
 
+# a plate on a free2d joint in a tilted plane carrying a revolute arm (our own synthetic scene): ground contact at the
+# arm, a 4x3 pad on the plate pressed by the arm, one end-effector, four force motors
+FREE2D_TEMPLATE = '''<redmax model="free2d-plate">
+    <option integrator="BDF1" timestep="5e-3" unit="m-kg" gravity="0. 0. -9.8"/>
+    <ground pos="0 0 0" normal="0 0 1"/>
+    <default>
+        <ground_contact kn="2e3" kt="10" mu="0.8" damping="3"/>
+        <tactile kn="50" kt="4" mu="1.0" damping="2"/>
+        <motor ctrl="force" ctrl_range="-0.5 0.5"/>
+    </default>
+    <robot>
+        <link name="plate">
+            <joint name="plate_joint" type="free2d" pos="0 0 0.06" quat="0.9887711 0.1494381 0 0" damping="0.5"/>
+            <body name="plate_body" type="cuboid" size="0.08 0.05 0.02" pos="0 0 0" quat="1 0 0 0" density="500." general_contact_resolution="2 2 2"/>
+            <link name="arm">
+                <joint name="arm_joint" type="revolute" axis="0 0 1" pos="0.04 0 0.01" quat="1 0 0 0" damping="0.002"/>
+                <body name="arm_body" type="cuboid" size="0.06 0.02 0.02" pos="0.03 0 0" quat="1 0 0 0" density="500." general_contact_resolution="3 2 2"/>
+            </link>
+        </link>
+    </robot>
+    <actuator>
+        <motor joint="plate_joint" ctrl="force"/>
+        <motor joint="arm_joint" ctrl="force"/>
+    </actuator>
+    <sensor>
+        <tactile body="plate_body" name="pad" type="rect_array" rect_pos0="0.03 -0.008 0.01" rect_pos1="0.039 0.008 0.01" axis0="1 0 0" axis1="0 1 0" resolution="4 3"/>
+    </sensor>
+    <contact>
+        <ground_contact body="arm_body"/>
+    </contact>
+    <variable>
+        <endeffector joint="arm_joint" pos="0.06 0 0" name="tip"/>
+    </variable>
+</redmax>
+'''
+
+
+def free2d_case(T, seed):
+    """free2d joint (DH/Joint/JointFree2D.cpp) in a tilted plane, BDF1, forward + backward()."""
+    d = os.path.join(ROOT, "oracle", "_ref", "assets", "synthetic")
+    os.makedirs(d, exist_ok=True)
+    xml = os.path.join(d, "free2d_plate.xml")
+    open(xml, "w").write(FREE2D_TEMPLATE)
+    rng = np.random.default_rng(seed)
+    return multi_case(xml, np.array([0.01, -0.02, 0.3, 0.4]), rng.uniform(-1, 1, (T, 4)), seed)
+
+
+# a pad pressed on a capsule lying on the ground and rolling it (our own synthetic scene: no reference asset has a capsule)
+CAPSULE_TEMPLATE = '''<redmax model="capsule-press">
+    <option integrator="BDF1" timestep="5e-3" unit="m-kg" gravity="0. 0. -9.8"/>
+    <ground pos="0 0 0" normal="0 0 1"/>
+    <default>
+        <general_primitive_contact kn="20" kt="1" mu="1.0" damping="1"/>
+        <tactile kn="1" kt="0.05" mu="2." damping="0.003"/>
+    </default>
+    <robot>
+        <link name="pad">
+            <joint name="pad_joint" type="translational" pos="0 0 0.045" quat="1 0 0 0" damping="1"/>
+            <body name="pad_body" type="cuboid" size="0.05 0.05 0.01" pos="0 0 0" quat="1 0 0 0" density="1000." general_contact_resolution="8 8 2"/>
+        </link>
+    </robot>
+    <robot>
+        <link name="object">
+            <joint name="object_joint" type="free3d-euler" pos="0.004 0. 0.015" quat="1 0 0 0"/>
+            <body name="object" type="capsule" pos="0 0 0" radius="0.015" length="0.012" quat="0.7071068 0 0.7071068 0" density="300." general_contact_resolution="5 8"/>
+        </link>
+    </robot>
+    <actuator>
+        <motor joint="pad_joint" ctrl="force" ctrl_range="-1 1"/>
+    </actuator>
+    <sensor>
+        <tactile body="pad_body" name="pad" type="rect_array" rect_pos0="-0.025 0.025 -0.005" rect_pos1="0.025 -0.025 -0.005" axis0="0 -1 0" axis1="1 0 0" resolution="12 12"/>
+    </sensor>
+    <contact>
+        <ground_contact body="object" kn="5e3" kt="1" mu="0.8" damping="0.03"/>
+        <general_primitive_contact general_body="pad_body" primitive_body="object"/>
+    </contact>
+</redmax>
+'''
+
+
+def capsule_case(T, seed):
+    """capsule SDF (DH/Body/BodyCapsule.cpp) as contact primitive, tactile candidate and -- through its sampled points --
+    ground contact body; free3d-euler joint; BDF1 forward + backward()."""
+    d = os.path.join(ROOT, "oracle", "_ref", "assets", "synthetic")
+    os.makedirs(d, exist_ok=True)
+    xml = os.path.join(d, "capsule_press.xml")
+    open(xml, "w").write(CAPSULE_TEMPLATE)
+    sim, probe, sc = redmax_py.Simulation(xml), redmax_probe.ProbeSimulation(xml), compile_scene(xml)
+    n, nt, nu = sim.ndof_r, sim.ndof_tactile, sim.ndof_u
+    u = np.zeros((T, nu))
+    u[:, 2] = 0.1
+    u[T // 2:, 1] = 0.15
+    u[T // 2:, 0] = 0.05
+    q0 = np.zeros(n)
+    q0[2] = -0.008
+    for s_ in (sim, probe):
+        s_.set_state_init(q0, np.zeros(n))
+        s_.reset(True)
+    q, qd, tac, ground, gp, mb = [], [], [], [], [], []
+    for t in range(T):
+        for s_ in (sim, probe):
+            s_.set_u(u[t])
+            s_.forward(1)
+        q.append(sim.get_q().copy())
+        qd.append(sim.get_qdot().copy())
+        tac.append(sim.get_tactile_force_vector().copy())
+        cs = probe.contact_sets()
+        ground.append(cs["ground"][0])
+        gp.append(cs["gp"][0])
+        mb.append(np.asarray(cs["marker_body"][0], dtype=np.int32))
+    rng = np.random.default_rng(1000 + seed)
+    df_dq = rng.normal(size=(T, n))
+    df_dtac = 1e-3 * rng.normal(size=(T, nt))
+    bi = sim.backward_info
+    bi.set_flags(True, True, False, True)
+    bi.df_dq, bi.df_dtactile = df_dq.reshape(-1), df_dtac.reshape(-1)
+    bi.df_dq0, bi.df_dqdot0, bi.df_du = np.zeros(n), np.zeros(n), np.zeros(nu * T)
+    sim.backward()
+    br = sim.backward_results
+    ib, db = sc.pack()
+    return dict(ibuf=ib, dbuf=db, q0=q0, qd0=np.zeros(n), u=u, q=np.array(q), qd=np.array(qd), tactile=np.array(tac),
+                ground_ids=pad_ids(ground, len(sc.contact_points[1])), gp_ids=pad_ids(gp, len(sc.contact_points[0])),
+                marker_body=np.array(mb, dtype=np.int32), cot_seed=1000 + seed,
+                df_dq0=np.array(br.df_dq0), df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, nu))
+
+
 def rolling_ball_bdf1_case(T, seed):
     """The rolling-ball scene (40x40 markers) under BDF1 with Simulation::backward(): the adjoint through the free3d-exp
     joint, the sphere SDF (ground, pad contact, tactile field) and the 2168-point pad.  Inputs: the script's action
@@ -472,6 +599,8 @@ def main():
         "pusher13x10_integrators_s0": lambda: integrators_case(40, 0),
         "spherical_euler_bdf1_s0": lambda: spherical_euler_case(60, 0),
         "rollingball_bdf1_adjoint_s0": lambda: rolling_ball_bdf1_case(60, 0),
+        "free2d_plate_bdf1_s0": lambda: free2d_case(60, 0),
+        "capsule_press_bdf1_s0": lambda: capsule_case(60, 0),
         "spherical_exp_bdf2_s0": lambda: spherical_exp_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate

@@ -201,17 +201,20 @@ def test_emulated_other_integrators_match_reference(name, code):
         assert emu_lib.mask_to_ids(out["cmask"][t, 0, 1:4]) == [int(x) for x in g["gp_ids_" + name][t] if x >= 0], t
 
 
-def test_emulated_spherical_euler_chain_matches_reference():
-    """spherical-euler joints (DH/Joint/JointSphericalEuler.cpp) in a two-link arm of our own (no reference asset uses
-    them): ground contact at the tip, a pad pressed by the neighbouring link, BDF1 forward + Simulation::backward."""
+@pytest.mark.parametrize("name", ["spherical_euler_bdf1_s0", "free2d_plate_bdf1_s0"])
+def test_emulated_spherical_euler_chain_matches_reference(name):
+    """spherical-euler joints (DH/Joint/JointSphericalEuler.cpp) in a two-link arm, and a free2d joint
+    (DH/Joint/JointFree2D.cpp) in a tilted plane carrying a revolute arm -- scenes of our own, no reference asset uses
+    these joint types: a pad pressed by the neighbouring link, BDF1 forward + Simulation::backward."""
     from tests.blob_scene import scene_from_blob
     from tests.multi_force import expected_words
-    g = np.load(os.path.join(GOLDEN, "spherical_euler_bdf1_s0.npz"))
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
     sc = scene_from_blob(g["ibuf"], g["dbuf"])
     T = g["u"].shape[0]
     out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
     assert int((out["status"] >> 16).max()) == 0
-    assert float(np.abs(g["tactile"]).max()) > 0 and int((g["ground_ids_f"] >= 0).sum()) > 0
+    assert float(np.abs(g["tactile"]).max()) > 0
+    assert int((g["ground_ids_f"] >= 0).sum()) > 0 or name.startswith("free2d")
     for t in range(T):
         assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
         assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
@@ -254,6 +257,32 @@ def test_emulated_rolling_ball_adjoint_matches_reference():
         assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
         assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
         assert emu_lib.mask_to_ids(out["cmask"][t, 0, 1:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], t
+        assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
+    rng = np.random.default_rng(int(g["cot_seed"]))
+    df_dq = rng.normal(size=(T, n))
+    df_dtac = 1e-3 * rng.normal(size=(T, g["tactile"].shape[1]))
+    bw = emu_lib.backward(g["ibuf"], g["dbuf"], out, g["u"][:, None, :], df_dq[:, None, :], None, df_dtac[:, None, :])
+    assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
+    assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
+    assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_capsule_scene_matches_reference():
+    """capsule SDF (DH/Body/BodyCapsule.cpp) in a scene of our own: a pad pressed on a capsule that lies on the ground and
+    rolls -- contact primitive, tactile candidate (reverse mode between and beyond the caps), ground contact through
+    its sampled points; BDF1 forward + Simulation::backward; kernel variant 17."""
+    g = np.load(os.path.join(GOLDEN, "capsule_press_bdf1_s0.npz"))
+    T, n = g["u"].shape[0], len(g["q0"])
+    out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
+    assert int((out["status"] >> 16).max()) == 0
+    assert float(np.abs(g["tactile"]).max()) > 0 and int((g["gp_ids"] >= 0).sum()) > 0 and int((g["ground_ids"] >= 0).sum()) > 0
+    gw = (g["ground_ids"].shape[1] + 31) // 32
+    for t in range(T):
+        assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9, t
+        assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9, t
+        assert rel_err(out["tactile"][t, 0], g["tactile"][t]) <= 1e-8, t
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, :gw]) == [int(x) for x in g["ground_ids"][t] if x >= 0], t
+        assert emu_lib.mask_to_ids(out["cmask"][t, 0, gw:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], t
         assert np.array_equal(out["marker_body"][t, 0], g["marker_body"][t]), t
     rng = np.random.default_rng(int(g["cot_seed"]))
     df_dq = rng.normal(size=(T, n))

@@ -147,7 +147,8 @@ def test_batched_line_search_equals_sequential_search():
 
 MULTI = {"dclaw_episodic_s0": (10, 90, 9, 12, 2718), "insertion_episodic_s0": (12, 78, 6, 0, 780),
          "stable_grasp_episodic_s0": (12, 126, 6, 0, 780),
-         "spherical_euler_bdf1_s0": (6, 12, 6, 3, 48)}        # our own two-link arm on spherical-euler joints
+         "spherical_euler_bdf1_s0": (6, 12, 6, 3, 48),        # our own two-link arm on spherical-euler joints
+         "free2d_plate_bdf1_s0": (4, 12, 4, 3, 36)}           # our own plate on a free2d joint carrying a revolute arm
 
 
 @pytest.mark.parametrize("lanes", [16, 32])
@@ -370,11 +371,14 @@ def test_trajectory_only_passes_equal_the_in_loop_evaluation():
         assert rel_err(a[k], b[k]) <= 1e-10, k
 
 
-def test_rolling_ball_adjoint_matches_reference():
+@pytest.mark.parametrize("name", ["rollingball_bdf1_adjoint_s0", "capsule_press_bdf1_s0"])
+def test_rolling_ball_adjoint_matches_reference(name):
     """The rolling-ball scene under BDF1 with Simulation::backward() (kernel variant 17): adjoint through the free3d-exp
-    joint, the sphere SDF (ground point, pad contact, tactile field) and the 2168-point pad."""
+    joint, the sphere SDF (ground point, pad contact, tactile field) and the 2168-point pad.  And a scene of our own with
+    a capsule (contact primitive, tactile candidate between and beyond its caps, ground contact through sampled points)."""
     from tactilesimulation_b200.sim import BatchedSim
-    g = np.load(os.path.join(GOLDEN, "rollingball_bdf1_adjoint_s0.npz"))
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    gw = (g["ground_ids"].shape[1] + 31) // 32 if "ground_ids" in g.files else 1
     sim = BatchedSim((g["ibuf"], g["dbuf"]), device="cuda:0")
     assert sim.integrator == 0
     dev = sim.device
@@ -390,7 +394,9 @@ def test_rolling_ball_adjoint_matches_reference():
         for t in range(T):
             assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
             assert rel_err(tac[t, e], g["tactile"][t]) <= 1e-8, (t, e)
-            assert _ids(cm[t, e, 1:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], (t, e)
+            assert _ids(cm[t, e, gw:]) == [int(x) for x in g["gp_ids"][t] if x >= 0], (t, e)
+            if "ground_ids" in g.files:
+                assert _ids(cm[t, e, :gw]) == [int(x) for x in g["ground_ids"][t] if x >= 0], (t, e)
             assert np.array_equal(mb[t, e], g["marker_body"][t]), (t, e)
     rng = np.random.default_rng(int(g["cot_seed"]))
     df_dq = rng.normal(size=(T, n))

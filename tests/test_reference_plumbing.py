@@ -43,11 +43,15 @@ def test_b200_scene_compiler_reads_the_rolling_ball_scene():
 
 
 def test_b200_path_rejects_unsupported_features_by_name(tmp_path):
+    """What is still not built (cuboid-cuboid contact, DH/Force/ForceCuboidCuboidContact.cpp) is refused by name."""
     from tactilesimulation_b200.scene import SceneError, compile_scene
-    xml = tmp_path / "capsule.xml"
+    xml = tmp_path / "boxes.xml"
     xml.write_text('''<redmax model="x"><option integrator="BDF1" timestep="5e-3" gravity="0 0 -9.8"/>
 <robot><link name="a"><joint name="j" type="free2d" pos="0 0 0" quat="1 0 0 0"/>
-<body name="b" type="capsule" pos="0 0 0" quat="1 0 0 0" radius="0.1" length="0.2" density="1"/></link></robot></redmax>''')
+<body name="b" type="capsule" pos="0 0 0" quat="1 0 0 0" radius="0.1" length="0.2" density="1"/></link></robot>
+<robot><link name="c"><joint name="k" type="free3d" pos="0 0 1" quat="1 0 0 0"/>
+<body name="d" type="cuboid" pos="0 0 0" quat="1 0 0 0" size="0.1 0.1 0.1" density="1"/></link></robot>
+<contact><cuboid_cuboid_contact body1="d" body2="d"/></contact></redmax>''')
     with pytest.raises(SceneError) as e:
         compile_scene(str(xml))
     assert "not supported" in str(e.value)
