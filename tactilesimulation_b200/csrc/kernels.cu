@@ -521,14 +521,15 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   a.defer_g0 = 0; a.q_start = 0; a.qd_start = 0; a.tape_order = 0;
   if (tac_pass || tape_pass) {
     const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R], nst = (size_t)B * s->sizes[TSIM_NDOF_R];
-    const bool own_traj = !(q_traj && qd_traj);
+    const int own_traj = (q_traj ? 0 : 1) + (qd_traj ? 0 : 1);    // trajectories the caller does not keep: scratch
     const size_t norder = (((size_t)T * B * sizeof(int)) + 15) & ~(size_t)15;
-    const size_t need = 16 + (own_traj ? 2 * nvec * sizeof(double) : 0) + (tape_pass ? 2 * nst * sizeof(double) + norder : 0);
+    const size_t need = 16 + own_traj * nvec * sizeof(double) + (tape_pass ? 2 * nst * sizeof(double) + norder : 0);
     CK(cudaMallocAsync(&scratch, need, st));
     unsigned char* p = (unsigned char*)scratch;
     a.work_counter = (unsigned*)p;
     p += 16;
-    if (own_traj) { a.q_traj = (double*)p; a.qd_traj = a.q_traj + nvec; p += 2 * nvec * sizeof(double); }
+    if (!q_traj) { a.q_traj = (double*)p; p += nvec * sizeof(double); }
+    if (!qd_traj) { a.qd_traj = (double*)p; p += nvec * sizeof(double); }
     CK(cudaMemsetAsync(a.work_counter, 0, 16, st));
     a.defer_tac = tac_pass ? 1 : 0;
     // identity row map: the whole [T,B,3M] field is this call's; a memset runs at the HBM rate and the pass then
