@@ -5,15 +5,17 @@ pad), forward + reverse-time adjoint, horizon T sim-steps, batch B environments 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 * one "step" = one pass of the hot path over one batch: tsim_forward (T implicit steps with
-  tape, q / var / tactile written every step) + tsim_backward (reverse sweep with cotangents on
-  q, var and the tactile field) for B environments; for N > 1 followed by ONE NCCL all-reduce of a
+  tape, q / var / tactile written every step: step loop + tape pass + tactile pass) + tsim_backward
+  (cotangent pull-back pass + reverse sweep, cotangents on q, var and the tactile field) for B environments; for N > 1 followed by ONE NCCL all-reduce of a
   policy-gradient sized buffer.  unit of `value`: env-steps/s, 1 env-step = one
   simulation timestep of one environment including its share of the reverse sweep.
 * `value`   : device-timed, inputs already resident in HBM.
 * `e2e`     : the same metric through the public plugin API (EpisodicSimFunction.apply +
   loss.backward()) with pinned HOST inputs copied in and gradients/loss copied out every step.
-* `roofline`: dominant kernel (forward) against the measured HBM peak; this path is fp64
-  latency/ALU bound, so the fraction is small by construction.
+* `roofline`: dominant kernel (fwd_kernel, the step loop) against the measured HBM peak, timed by CUDA
+  events recorded inside the C ABI around every kernel (tsim_scene_kernel_times); `roofline.kernels` lists
+  all five kernels of a step.  The step loop is fp64 latency-bound, its fraction is small by construction;
+  the read-out / pull-back passes are the ones that stream.
 * `cpu_baseline` / `--impl reference`: the unmodified reference C++ (oracle/_ref/redmax_py, built
   by oracle/build_ref.sh) on the host cores, one process per core, on a bounded sample.
 
@@ -405,7 +407,8 @@ def run_b200(a):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "EpisodicSimFunction.apply + loss.backward(), pinned host q0/qdot0/actions in, grads + loss out"},
-            "gpu_launches": sum(1 for v in kt.values() if v) * a.steps,
+            # launches of this library's kernels inside the timed region (vjp_kernel runs two phases per step)
+            "gpu_launches": sum((2 if k == "vjp_kernel" else 1) for k, v in kt.items() if v) * a.steps,
             "roofline": roofline, "cpu_baseline": cpu, "nan": nan}
     print(json.dumps(line), flush=True)
     if world > 1:
