@@ -113,3 +113,28 @@ def test_backward_steps_matches_reference():
         c = np.zeros((fs, nt)); c[-1] = g["df_dtactile"][t]
         r = o.backward_steps(fs, a, b, c)
         assert rel_err(r["df_du"], g["df_du"][t]) <= 1e-6
+
+
+@pytest.mark.parametrize("name,T", [("BDF2", 24), ("SDIRK2", 20)])
+def test_other_integrators_match_reference(name, T):
+    """The oracle's restatement of integration_BDF2 (with its SDIRK2 start-up step) and integration_SDIRK2
+    (DH/Simulation.cpp:1076-1092, 1353-1564) against the reference on the TactilePush scene."""
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_integrators_s0.npz"))
+    ib = g["ibuf"].copy()
+    ib[14] = {"BDF2": 1, "SDIRK2": 2}[name]
+    sc = scene_from_blob(ib, g["dbuf"])
+    assert sc.integrator == name
+    o = OracleSim(sc)
+    o.set_state_init(g["q0"], g["qd0"])
+    o.reset(False)
+    for t in range(T):
+        o.set_u(g["u"][t])
+        o.forward(1)
+        assert rel_err(o.get_q(), g["q_" + name][t]) <= 1e-9, t
+        assert rel_err(o.get_qdot(), g["qd_" + name][t]) <= 1e-9, t
+        if t % 4 == 3 or t == T - 1:
+            assert rel_err(o.get_tactile_force_vector(), g["tactile_" + name][t]) <= 1e-8, t
+            assert o.contact_sets()["gp"][0] == _ids(g["gp_ids_" + name][t]), t
+    with pytest.raises(RuntimeError):
+        o.reset(True)
+        o.forward(1)
