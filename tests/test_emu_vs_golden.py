@@ -291,3 +291,25 @@ def test_emulated_capsule_scene_matches_reference():
     assert rel_err(bw["df_du"][:, 0], g["df_du"]) <= 1e-6
     assert rel_err(bw["df_dq0"][0], g["df_dq0"]) <= 1e-6
     assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
+
+
+def test_emulated_passes_equal_in_loop_evaluation():
+    """The trajectory-only passes (tactile read-out, G0 / G1 tape blocks: calls of 4 steps or more) against the evaluation
+    inside the step loop (calls of fewer steps, chained): same trajectory, fields, tape and gradients."""
+    g = np.load(os.path.join(GOLDEN, "pusher13x10_episodic_s0.npz"))
+    T = 24
+    u = g["u"][:T, None, :]
+    one = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], u, grad=True)
+    q, qd = g["q0"][None].copy(), g["qd0"][None].copy()
+    parts = []
+    for t0 in range(0, T, 3):
+        o = emu_lib.forward(g["ibuf"], g["dbuf"], q, qd, u[t0:t0 + 3], grad=True)
+        q, qd = o["q_final"], o["qd_final"]
+        parts.append(o)
+    for key, tol in (("q", 0.0), ("tactile", 1e-13), ("tape", 1e-13), ("var", 0.0)):
+        cat = np.concatenate([p[key] for p in parts], axis=0)
+        if tol == 0.0:
+            assert np.array_equal(cat, one[key]), key
+        else:
+            assert rel_err(cat, one[key]) <= tol, key
+    assert float(np.abs(one["tactile"]).max()) > 0
