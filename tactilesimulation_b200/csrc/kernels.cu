@@ -6,6 +6,12 @@
 // coordinate k: it carries the Dual tangent along q_k through the matrix-free residual, holds
 // column k of the Newton matrix for the shuffle-based pivoted LU, and strides over tactile
 // markers / contact points in the readout and adjoint passes.  See sim_core.cuh.
+//
+// A forward call is three kernels and a backward call three launches: only what is sequential per environment (the
+// Newton step loop, the reverse sweep) runs in the persistent one-tile-per-environment kernels fwd_kernel / bwd_kernel;
+// what depends on the recorded trajectory only -- tactile read-out (tac_kernel), the G0 / G1 blocks of the tape
+// (tape_kernel), the pull-back of the readout cotangents (vjp_kernel, two phases) -- runs over all T x B env-steps in
+// persistent kernels that draw env-steps from a work counter.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

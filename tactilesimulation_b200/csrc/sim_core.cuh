@@ -26,6 +26,9 @@
 //   * Newton with backtracking line search (DH/Simulation.cpp:1150-1225): every line-search trial is
 //     evaluated WITH its Jacobian columns, so an accepted trial is at once the next iterate's
 //     (g, H) and -- when converged -- the tape's H; no residual is evaluated twice.
+//   * joints: revolute, prismatic, planar, translational, free2d, free3d / spherical in the XYZ-Euler and in the
+//     exponential chart; primitives: cuboid, cylinder, sphere, capsule; integrators: BDF1 (with the adjoint), BDF2 and
+//     SDIRK2 as stages of one residual (stage_inputs / stage_coef).  Features are gated per kernel variant (kernel_layout.h).
 //   * tactile readout: per-marker penalty force in the contacted box's frame
 //     (DH/Sensor/TactileSensor.cpp:29-87); its adjoint is hand-written reverse mode
 //     accumulating cotangents on (R2^T R1, R2^T(p1-p2), phi1, phi2) per candidate body
