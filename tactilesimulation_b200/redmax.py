@@ -272,6 +272,33 @@ class Simulation:
                 return
         raise TactileSimError(f"endeffector {endeffector_name} not found")
 
+    def update_body_density(self, body_name, density):
+        """DH/python_interface.cpp:181-211, DH/Robot.cpp:596-610 (R/envs/stable_grasp_env.py:122)."""
+        from . import scene as _scene
+        try:
+            _scene.update_body_density(self.scene, body_name, density)
+        except _scene.SceneError as e:
+            raise TactileSimError(str(e))
+        self._rebuild()
+
+    def update_body_size(self, body_name, body_size):
+        """DH/Robot.cpp:612-626 (R/envs/dclaw_rotate_env.py:175: the cap's (length, radius))."""
+        from . import scene as _scene
+        try:
+            _scene.update_body_size(self.scene, body_name, body_size)
+        except _scene.SceneError as e:
+            raise TactileSimError(str(e))
+        self._rebuild()
+
+    def update_joint_location(self, joint_name, joint_location):
+        """DH/Robot.cpp:636-650, DH/Joint/Joint.cpp:98-117 (R/envs/dclaw_rotate_env.py:178)."""
+        from . import scene as _scene
+        try:
+            _scene.update_joint_location(self.scene, joint_name, joint_location)
+        except _scene.SceneError as e:
+            raise TactileSimError(str(e))
+        self._rebuild()
+
     def update_body_color(self, body_name, color):
         """Render-only."""
         return None

@@ -218,6 +218,12 @@ class Scene:
     end_effectors: List[dict] = field(default_factory=list)    # joint,pos
     sensors: List[TactileSensor] = field(default_factory=list)
     virtual_names: List[str] = field(default_factory=list)
+    # host-only construction parameters (not in the blob): what the update_* calls of the reference need to redo a part
+    # of the construction (DH/Robot.cpp:571-650).  Empty for scenes rebuilt from a blob.
+    body_density: List[float] = field(default_factory=list)
+    body_res: List[Optional[np.ndarray]] = field(default_factory=list)     # contact sampling resolution of the body
+    joint_R0: List[np.ndarray] = field(default_factory=list)
+    joint_frame: List[str] = field(default_factory=list)
     ndof_r: int = 0
     ndof_u: int = 0
 
@@ -395,6 +401,8 @@ def compile_scene(xml_path: str) -> Scene:
         sc.qoff.append(-1)
         sc.E_pj0.append(E_pj0)
         sc.E_j0_0.append(E_j00)
+        sc.joint_R0.append(R)
+        sc.joint_frame.append(frame)
         sc.axis0.append(a0)
         sc.axis1.append(a1)
         name = jn.get("name", f"joint{idx}")
@@ -525,6 +533,9 @@ def compile_scene(xml_path: str) -> Scene:
         sc.btype.append(btype)
         sc.size.append(np.asarray(size, dtype=np.float64))
         sc.contact_points.append(pts)
+        sc.body_density.append(density)
+        sc.body_res.append({"cuboid": lambda: res, "cylinder": lambda: np.array([ares, rres]), "capsule": lambda: res}
+                           .get(btype, lambda: None)())
         bname = bn.get("name", f"body{idx}")
         sc.body_names.append(bname)
         if bn.get("name") is not None:
@@ -716,3 +727,111 @@ def joint_Q(jt: int, a0, a1, q):
     elif jt == JT_TRANSLATIONAL:
         Q[:3, 3] = q
     return Q
+
+
+# ------------------------------------------------------------------ parameter updates (DH/Robot.cpp:571-650)
+def primitive_inertia(shape: int, size, density: float) -> np.ndarray:
+    """(Ixx, Iyy, Izz, m, m, m) of a primitive body: BodyCuboid.cpp:20-26, BodyCylinder.cpp:21-27, BodySphere.cpp:17-21,
+    BodyCapsule.cpp:22-31 (the formulas compile_scene uses)."""
+    inertia = np.zeros(6)
+    if shape == SH_CUBOID:
+        length = np.asarray(size, dtype=np.float64)
+        mass = float(np.prod(length)) * density
+        inertia[0] = mass / 12.0 * (length[1] * length[1] + length[2] * length[2])
+        inertia[1] = mass / 12.0 * (length[0] * length[0] + length[2] * length[2])
+        inertia[2] = mass / 12.0 * (length[0] * length[0] + length[1] * length[1])
+    elif shape == SH_CYLINDER:
+        radius, length = float(size[0]), float(size[1])
+        mass = math.pi * radius * radius * length * density
+        inertia[0] = mass * length * length / 12.0 + mass * radius * radius / 4.0
+        inertia[1] = mass * length * length / 12.0 + mass * radius * radius / 4.0
+        inertia[2] = mass * radius * radius / 2.0
+    elif shape == SH_SPHERE:
+        radius = float(size[0])
+        mass = 4.0 / 3.0 * math.pi * radius * radius * radius * density
+        inertia[:3] = 0.4 * mass * radius * radius
+    elif shape == SH_CAPSULE:
+        radius, length = float(size[0]), float(size[1])
+        m_cy = density * length * math.pi * radius * radius
+        m_hs = density * 2.0 / 3.0 * math.pi * radius * radius * radius
+        mass = m_cy + 2.0 * m_hs
+        inertia[0] = m_cy * (length * length / 12.0 + radius * radius / 4.0) + 2.0 * m_hs * (2.0 * radius * radius / 5.0 + length * length / 2.0 + 3.0 * length * radius / 8.0)
+        inertia[1] = inertia[0]
+        inertia[2] = m_cy * radius * radius / 2.0 + 2.0 * m_hs * 2.0 * radius * radius / 5.0
+    else:
+        raise SceneError("not a primitive body")
+    inertia[3:] = mass
+    return inertia
+
+
+def _body_index(sc: Scene, body_name: str) -> int:
+    """-1 for an unknown name: the reference walks its bodies and silently does nothing when none matches
+    (DH/Robot.cpp:596-650)."""
+    return sc.body_names.index(body_name) if body_name in sc.body_names else -1
+
+
+def update_body_density(sc: Scene, body_name: str, density: float) -> None:
+    """Simulation::update_body_density (DH/Robot.cpp:596-610): primitives recompute their mass matrix with the new
+    density (Body*.cpp update_density); a mesh body re-runs process_mesh, i.e. mass and principal inertia scale with
+    the density; abstract bodies ignore the call (Body.h:129)."""
+    b = _body_index(sc, body_name)
+    if b < 0:
+        return
+    density = float(density)
+    if sc.shape[b] != SH_NONE:
+        sc.inertia[b] = primitive_inertia(sc.shape[b], sc.size[b], density)
+    elif b < len(sc.btype) and sc.btype[b] == "mesh":
+        if b >= len(sc.body_density):
+            raise SceneError("update_body_density on a mesh body needs a scene compiled from XML")
+        sc.inertia[b] = sc.inertia[b] * (density / sc.body_density[b])
+    if b < len(sc.body_density):
+        sc.body_density[b] = density
+
+
+def update_body_size(sc: Scene, body_name: str, body_size) -> None:
+    """Simulation::update_body_size (DH/Robot.cpp:612-626): cuboid size = (lx, ly, lz) (BodyCuboid.cpp:289-294), cylinder
+    size = (length, radius) (BodyCylinder.cpp:277-283): new sampled contact points and mass matrix; other bodies ignore
+    the call (Body.h:130).  The density is the body's current one."""
+    b = _body_index(sc, body_name)
+    size = np.asarray(body_size, dtype=np.float64)
+    if b < 0 or sc.shape[b] not in (SH_CUBOID, SH_CYLINDER):
+        return
+    if sc.shape[b] == SH_CUBOID:
+        if size.shape[0] != 3:
+            raise SceneError("update_body_size: a cuboid takes 3 values")
+        mass_old, vol_old = sc.inertia[b][3], float(np.prod(sc.size[b]))
+        new_size = size.copy()
+    else:
+        if size.shape[0] != 2:
+            raise SceneError("update_body_size: a cylinder takes (length, radius)")
+        mass_old, vol_old = sc.inertia[b][3], math.pi * sc.size[b][0] * sc.size[b][0] * sc.size[b][1]
+        new_size = np.array([size[1], size[0], 0.0])
+    density = sc.body_density[b] if b < len(sc.body_density) else mass_old / vol_old
+    res = sc.body_res[b] if b < len(sc.body_res) else None
+    if res is not None:
+        sc.contact_points[b] = (_cuboid_points(new_size, res) if sc.shape[b] == SH_CUBOID
+                                else _cylinder_points(new_size[0], new_size[1], int(res[0]), int(res[1])))
+    elif len(sc.contact_points[b]):
+        raise SceneError("update_body_size on a body whose sampled points are in use needs a scene compiled from XML")
+    sc.size[b] = new_size
+    sc.inertia[b] = primitive_inertia(sc.shape[b], new_size, density)
+
+
+def update_joint_location(sc: Scene, joint_name: str, location) -> None:
+    """Simulation::update_joint_location (DH/Joint/Joint.cpp:98-117): the joint's rest position in its parent (LOCAL
+    frame) or in the world (WORLD frame); the children keep their transforms relative to this joint."""
+    if joint_name not in sc.joint_names:
+        return                             # as the reference: no joint of that name, nothing happens
+    j = sc.joint_names.index(joint_name)
+    p = np.asarray(location, dtype=np.float64)
+    R0 = sc.joint_R0[j] if j < len(sc.joint_R0) else sc.E_pj0[j][:3, :3]
+    frame = sc.joint_frame[j] if j < len(sc.joint_frame) else "LOCAL"
+    par = sc.parent[j]
+    if frame == "WORLD" and par >= 0:
+        E_pj0 = sc.E_j0_0[par] @ SE(R0, p)
+    else:
+        E_pj0 = SE(R0, p)
+    sc.E_pj0[j] = E_pj0
+    if j < len(sc.E_j0_0):
+        E_jp0 = Einv(E_pj0)
+        sc.E_j0_0[j] = E_jp0 if par < 0 else E_jp0 @ sc.E_j0_0[par]

@@ -424,6 +424,81 @@ def capsule_case(T, seed):
                 df_dq0=np.array(br.df_dq0), df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, nu))
 
 
+def randomized_case():
+    """The domain-randomisation calls of the reference's envs before reset() -- update_joint_damping, update_body_size,
+    update_endeffector_position, update_joint_location (R/envs/dclaw_rotate_env.py:173-178) and update_body_density
+    (R/envs/stable_grasp_env.py:122) -- then a short rollout.  The fixture keeps the ORIGINAL scene blobs (+ names);
+    the tests apply the same updates through tactilesimulation_b200.scene.update_* and compare the rollouts."""
+    out = {}
+    # ---- DClaw: cap radius / damping / location
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
+    sim = redmax_py.Simulation(xml)
+    sc = compile_scene(xml)
+    upd = dict(damping=0.0015, size=np.array([0.03, 0.052]), ee=np.array([0.052, 0.0, 0.0]), loc=np.array([0.003, -0.004, 0.075]))
+    sim.update_joint_damping("cap", upd["damping"])
+    sim.update_body_size("cap", upd["size"])
+    sim.update_endeffector_position("cap", upd["ee"])
+    sim.update_joint_location("cap", upd["loc"])
+    q0 = np.zeros(10)
+    q0[[1, 4, 7]] = -0.5
+    q0[[2, 5, 8]] = 0.8
+    rng = np.random.default_rng(7)
+    T = 30
+    u = rng.uniform(-1, 1, (T, 9))
+    u[:, 1::3] = 0.6 + 0.4 * u[:, 1::3]
+    sim.set_state_init(q0, np.zeros(10))
+    sim.reset(False)
+    q, var, tac = [], [], []
+    for t in range(T):
+        sim.set_u(u[t])
+        sim.forward(1)
+        q.append(sim.get_q().copy())
+        var.append(sim.get_variables().copy())
+        if t % 5 == 4:
+            tac.append(sim.get_tactile_force_vector().copy())
+    d = sc.to_npz_dict()
+    out.update(dclaw_ibuf=d["ibuf"], dclaw_dbuf=d["dbuf"], dclaw_joint_names=np.array(sc.joint_names), dclaw_body_names=np.array(sc.body_names),
+               dclaw_ee_names=np.array([e["name"] for e in sc.end_effectors]),
+               dclaw_damping=upd["damping"], dclaw_size=upd["size"], dclaw_ee=upd["ee"], dclaw_loc=upd["loc"], dclaw_q0=q0, dclaw_u=u,
+               dclaw_q=np.array(q), dclaw_var=np.array(var), dclaw_tactile=np.array(tac))
+    # ---- StableGrasp: box densities
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "stable_grasp", "stable_grasp.xml")
+    sim = redmax_py.Simulation(xml)
+    sc = compile_scene(xml)
+    dens = rng.uniform(100.0, 1500.0, 11)
+    for i in range(11):
+        sim.update_body_density("box_%d" % i, float(dens[i]))
+    g = stable_grasp_case.__globals__
+    q0 = np.zeros(12)
+    q0[2] = 0.2029862
+    q0[4] = q0[5] = -0.03
+    gp = 0.01
+    q0[1] = gp
+    stages = [np.array([0.0, gp, 0.2029862, 0.0, -0.03, -0.03]), np.array([0.0, gp, 0.2029862, 0.0, -0.008, -0.008]),
+              np.array([0.0, gp, 0.2029862, 0.0, -0.008, -0.008]), np.array([0.0, gp, 0.2329862, 0.0, -0.008, -0.008])]
+    T = 45
+    steps = [20, 8, T - 28]
+    u = []
+    for st in range(3):
+        for i in range(steps[st]):
+            u.append((stages[st + 1] - stages[st]) / steps[st] * (i + 1) + stages[st])
+    u = np.array(u)
+    u[:, 2] += 0.003
+    sim.set_state_init(q0, np.zeros(12))
+    sim.reset(False)
+    q, tac = [], []
+    for t in range(T):
+        sim.set_u(u[t])
+        sim.forward(1)
+        q.append(sim.get_q().copy())
+        if t % 5 == 4:
+            tac.append(sim.get_tactile_force_vector().copy())
+    d = sc.to_npz_dict()
+    out.update(sg_ibuf=d["ibuf"], sg_dbuf=d["dbuf"], sg_body_names=np.array(sc.body_names), sg_dens=dens, sg_q0=q0, sg_u=u,
+               sg_q=np.array(q), sg_tactile=np.array(tac))
+    return out
+
+
 def rolling_ball_bdf1_case(T, seed):
     """The rolling-ball scene (40x40 markers) under BDF1 with Simulation::backward(): the adjoint through the free3d-exp
     joint, the sphere SDF (ground, pad contact, tactile field) and the 2168-point pad.  Inputs: the script's action
@@ -601,6 +676,7 @@ def main():
         "rollingball_bdf1_adjoint_s0": lambda: rolling_ball_bdf1_case(60, 0),
         "free2d_plate_bdf1_s0": lambda: free2d_case(60, 0),
         "capsule_press_bdf1_s0": lambda: capsule_case(60, 0),
+        "randomized_updates_s0": randomized_case,
         "spherical_exp_bdf2_s0": lambda: spherical_exp_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate
