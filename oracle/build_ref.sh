@@ -35,26 +35,38 @@ X
 SRCS="$(find "$C/projects/redmax" -name '*.cpp' ! -name main.cpp ! -name SimViewer.cpp ! -name Test.cpp | sort) \
  $C/projects/opengl_viewer/src/geometry.cpp $C/projects/opengl_viewer/src/image.cpp $C/projects/opengl_viewer/src/bounding_box.cpp \
  $C/externals/pugixml/src/pugixml.cpp $C/externals/tiny_obj_loader/tiny_obj_loader.cpp $OUT/SimViewerStub.cpp"
-FLAGS="-O2 -std=c++14 -fPIC -w -DGLEW_STATIC -DGLEW_NO_GLU -DGLFW_INCLUDE_NONE -include $OUT/defs.h \
+# Release flags of the reference's own build (core/setup.py:39,49 -> CMAKE_BUILD_TYPE=Release = -O3 -DNDEBUG)
+FLAGS="-O3 -DNDEBUG -std=c++14 -fPIC -w -DGLEW_STATIC -DGLEW_NO_GLU -DGLFW_INCLUDE_NONE -include $OUT/defs.h \
  -I$C/projects/redmax -I$C/projects/opengl_viewer/include -I$C/externals/eigen -I$C/externals/glew/include \
  -I$C/externals/glfw/include/GLFW -I$C/externals/imgui -I$C/externals/stb -I$C/externals/pugixml/src -I$C/externals/tiny_obj_loader \
  -I$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])') -I$($PY -c 'import pybind11;print(pybind11.get_include())')"
 TARGET="$OUT/redmax_py$EXT"
 PROBE="$OUT/redmax_probe$EXT"
-if [ -f "$TARGET" ] && [ -f "$PROBE" ] && [ "$PROBE" -nt "$HERE/ref_probe.cpp" ] && [ -z "${FORCE:-}" ]; then
+FLAGTAG="$OUT/obj/.flags_O3_NDEBUG_v2"
+if [ ! -f "$FLAGTAG" ]; then rm -rf "$OUT/obj"; mkdir -p "$OUT/obj"; fi
+if [ -f "$TARGET" ] && [ -f "$PROBE" ] && [ "$PROBE" -nt "$HERE/ref_probe.cpp" ] && [ "$PROBE" -nt "$HERE/build_ref.sh" ] && [ -z "${FORCE:-}" ]; then
   echo "build_ref: $TARGET and $PROBE already built"
 else
   if [ ! -f "$OUT/obj/.done" ] || [ -n "${FORCE:-}" ]; then
     i=0
     for s in $SRCS; do i=$((i+1)); b="$(basename "$s" .cpp)"; echo "g++ $FLAGS -c $s -o $OUT/obj/${i}_$b.o"; done | xargs -P "$(nproc)" -I{} sh -c "{}"
-    touch "$OUT/obj/.done"
+    touch "$OUT/obj/.done" "$FLAGTAG"
   fi
   g++ -shared -o "$TARGET" "$OUT"/obj/*.o -ldl
   # the probe: our own read-only pybind module, linked with the same reference objects
   # (minus the reference's python_interface.o, which defines the other module)
-  g++ $FLAGS -c "$HERE/ref_probe.cpp" -o "$OUT/obj/probe.o.tmp"
-  g++ -shared -o "$PROBE" $(ls "$OUT"/obj/*.o | grep -v python_interface) "$OUT/obj/probe.o.tmp" -ldl
-  rm -f "$OUT/obj/probe.o.tmp"
+  # The probe module alone links an INSTRUMENTED compile of Simulation.cpp: two counters (Newton iterations = calls of
+  # func_with_derivatives, line-search evaluations = calls of func, DH/Simulation.cpp:1171,1189) inserted by sed into a
+  # scratch copy under the git-ignored _ref directory.  redmax_py itself stays the unmodified reference.
+  mkdir -p "$OUT/probe_src"
+  sed -e 's|^\( *\)(this->\*func_with_derivatives)(x, g, H, false);|\1(this->*func_with_derivatives)(x, g, H, false); ++g_probe_newton_iters;|' \
+      -e 's|^\( *\)(this->\*func)(x + alpha \* dx, g_new);|\1(this->*func)(x + alpha * dx, g_new); ++g_probe_ls_evals;|' \
+      "$C/projects/redmax/Simulation.cpp" > "$OUT/probe_src/Simulation_counted.cpp"
+  [ "$(grep -c 'g_probe_' "$OUT/probe_src/Simulation_counted.cpp")" = "2" ] || { echo "build_ref: instrumentation did not apply" >&2; exit 1; }
+  echo 'extern int g_probe_newton_iters, g_probe_ls_evals;' > "$OUT/probe_src/probe_counters.h"
+  g++ $FLAGS -include "$OUT/probe_src/probe_counters.h" -c "$OUT/probe_src/Simulation_counted.cpp" -o "$OUT/probe_src/Simulation_counted.o"
+  g++ $FLAGS -include "$OUT/probe_src/probe_counters.h" -c "$HERE/ref_probe.cpp" -o "$OUT/probe_src/probe.o"
+  g++ -shared -o "$PROBE" $(ls "$OUT"/obj/*.o | grep -v python_interface | grep -v '_Simulation\.o$') "$OUT/probe_src/Simulation_counted.o" "$OUT/probe_src/probe.o" -ldl
   echo "build_ref: built $TARGET and $PROBE"
 fi
 # Scene assets the reference binary needs at run time (XML + meshes are data, not source;

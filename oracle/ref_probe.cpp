@@ -39,6 +39,18 @@
 namespace py = pybind11;
 using namespace redmax;
 
+// Counters incremented by the instrumented compile of Simulation::newton that build_ref.sh links into THIS module only
+// (one line each, inserted by sed after the func_with_derivatives / func calls of DH/Simulation.cpp:1171,1189).
+int g_probe_newton_iters = 0, g_probe_ls_evals = 0;
+
+// (Newton iterations, line-search evaluations) since the last call; resets the counters.
+static py::tuple newton_counts(Simulation&) {
+    py::tuple t = py::make_tuple(g_probe_newton_iters, g_probe_ls_evals);
+    g_probe_newton_iters = 0;
+    g_probe_ls_evals = 0;
+    return t;
+}
+
 static int body_index(Robot* robot, Body* b) {
     if (b == nullptr) return -1;
     for (size_t i = 0; i < robot->_bodies.size(); ++i)
@@ -145,6 +157,8 @@ PYBIND11_MODULE(redmax_probe, m) {
         .def("get_qdot", &Simulation::get_qdot)
         .def("get_variables", &Simulation::get_variables)
         .def("get_tactile_force_vector", &Simulation::get_tactile_force_vector)
+        .def("set_qdot_init", &Simulation::set_qdot_init)
+        .def("newton_counts", &newton_counts)
         .def("contact_sets", &contact_sets)
         .def("matrices", &matrices)
         .def("tape", &tape)

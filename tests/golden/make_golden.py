@@ -62,12 +62,13 @@ def episodic_case(xml, T, seed, push=True):
         s.set_state_init(q0, np.zeros(n))
         s.reset(True)
     q, qd, var, tac = [], [], [], []
-    ground, gp, mb = [], [], []
+    ground, gp, mb, newton = [], [], [], []
     for t in range(T):
         for s in (sim, probe):
             s.set_u(u[t])
             s.forward(1)
         assert np.array_equal(sim.get_q(), probe.get_q())
+        newton.append(probe.newton_counts())     # (Newton iterations, line-search evaluations) of this step
         q.append(sim.get_q().copy())
         qd.append(sim.get_qdot().copy())
         var.append(sim.get_variables().copy())
@@ -96,7 +97,7 @@ def episodic_case(xml, T, seed, push=True):
                 gp_ids=pad_ids(gp, len(sc.contact_points[sc.gp_contacts[0]["body1"]])),
                 marker_body=np.array(mb, dtype=np.int32), df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac,
                 df_dq0=np.array(br.df_dq0), df_dqdot0=np.array(br.df_dqdot0),
-                df_du=np.array(br.df_du).reshape(T, sim.ndof_u))
+                df_du=np.array(br.df_du).reshape(T, sim.ndof_u), newton=np.array(newton, dtype=np.int32))
 
 
 def stepsim_case(xml, nsteps, frame_skip, seed):
@@ -147,12 +148,13 @@ def multi_case(xml, q0, u, seed):
     for s in (sim, probe):
         s.set_state_init(q0, np.zeros(n))
         s.reset(True)
-    q, qd, var, tac, ground, gp, mb = [], [], [], [], [], [], []
+    q, qd, var, tac, ground, gp, mb, newton = [], [], [], [], [], [], [], []
     for t in range(T):
         for s in (sim, probe):
             s.set_u(u[t])
             s.forward(1)
         assert np.array_equal(sim.get_q(), probe.get_q())
+        newton.append(probe.newton_counts())
         q.append(sim.get_q().copy())
         qd.append(sim.get_qdot().copy())
         var.append(sim.get_variables().copy())
@@ -186,7 +188,8 @@ def multi_case(xml, q0, u, seed):
                 tactile=np.array(tac), ground_ids_f=pad3(ground, len(sc.ground_contacts), gw),
                 gp_ids_f=pad3(gp, len(sc.gp_contacts), pw), marker_body=np.array(mb, dtype=np.int32),
                 df_dq=df_dq, df_dvar=df_dvar, df_dtactile=df_dtac, df_dq0=np.array(br.df_dq0),
-                df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, sim.ndof_u))
+                df_dqdot0=np.array(br.df_dqdot0), df_du=np.array(br.df_du).reshape(T, sim.ndof_u),
+                newton=np.array(newton, dtype=np.int32))
 
 
 def dclaw_case(T, seed):

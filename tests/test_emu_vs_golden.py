@@ -20,6 +20,10 @@ def test_emulated_kernel_math_matches_reference(name):
     T = g["u"].shape[0]
     out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
     assert int((out["status"] >> 16).max()) == 0
+    # Newton iterations | line-search evaluations << 8 equal the counters of the reference's own newton()
+    # (instrumented probe of oracle/build_ref.sh, DH/Simulation.cpp:1171,1189)
+    assert np.array_equal(out["status"][:, 0] & 0xff, g["newton"][:, 0])
+    assert np.array_equal((out["status"][:, 0] >> 8) & 0xff, g["newton"][:, 1])
     for t in range(T):
         assert rel_err(out["q"][t, 0], g["q"][t]) <= 1e-9
         assert rel_err(out["qd"][t, 0], g["qd"][t]) <= 1e-9

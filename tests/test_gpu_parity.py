@@ -54,7 +54,11 @@ def test_forward_and_adjoint_match_reference(name, lanes, variant):
     var, tac = out["var"].cpu().numpy(), out["tactile"].cpu().numpy()
     cm, mb = out["contact_masks"].cpu().numpy(), out["marker_body"].cpu().numpy()
     assert int((out["status"] >> 16).max().item()) == 0
+    st = out["status"].cpu().numpy()
     for e in range(B):
+        # Newton iterations / line-search evaluations per step equal the reference's own counters (status bits 0-15)
+        assert np.array_equal(st[:, e] & 0xff, g["newton"][:, 0]), e
+        assert np.array_equal((st[:, e] >> 8) & 0xff, g["newton"][:, 1]), e
         for t in range(T):
             assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
             assert rel_err(qdt[t, e], g["qd"][t]) <= 1e-9, (t, e)
@@ -179,7 +183,11 @@ def test_dclaw_and_insertion_match_reference(name, lanes):
     cm, mb = out["contact_masks"].cpu().numpy(), out["marker_body"].cpu().numpy()
     assert int((out["status"] >> 16).max().item()) == 0
     assert float(np.abs(g["tactile"]).max()) > 0
+    st = out["status"].cpu().numpy()
     for e in range(B):
+        if "newton" in g.files:       # Newton iterations / line-search evaluations per step as counted in the reference
+            assert np.array_equal(st[:, e] & 0xff, g["newton"][:, 0]), e
+            assert np.array_equal((st[:, e] >> 8) & 0xff, g["newton"][:, 1]), e
         for t in range(T):
             assert rel_err(qt[t, e], g["q"][t]) <= 1e-9, (t, e)
             assert rel_err(qdt[t, e], g["qd"][t]) <= 1e-9, (t, e)
