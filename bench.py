@@ -187,6 +187,8 @@ def run_reference(a):
     if rank != 0:
         return
     import multiprocessing as mp
+    sys.path.insert(0, REF_DIR)
+    import redmax_py  # noqa: F401  (loaded once in the parent: the forked workers inherit it, the driver's hook sees the .so)
     cores = host_cores()
     T = a.horizon
     envs_per_core = a.ref_envs_per_core
@@ -205,7 +207,8 @@ def run_reference(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"TactilePush 32x13 fwd+adjoint horizon {T}, bounded sample of the batch-{a.batch} job",
                        "horizon": T, "markers": N_MARKERS},
-            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "build": "oracle/build_ref.sh: g++ -O3 -DNDEBUG (the reference's CMake Release flags)"},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -296,6 +299,9 @@ def run_b200(a):
     ms_total = float(ms_t.item())
     env_steps = B * T * world * a.steps
     value = env_steps / (ms_total * 1e-3)
+    touched = int((out["tactile"].abs().amax(dim=2) > 0).sum().item())    # env-steps whose pad touches (after timing)
+    from tactilesimulation_b200 import _lib as tsim_lib
+    fp64_peak = tsim_lib.fp64_peak(local_rank) if rank == 0 else None
     del out, bw
     torch.cuda.empty_cache()
 
@@ -359,32 +365,47 @@ def run_b200(a):
     else:
         peak, peak_src = 6650.0, "fallback"
     M = core.n_markers
+    items = B * T
     # algorithmic HBM bytes per env-step of each kernel: the step loop moves u in, q / qd / var and
-    # the H block of the tape out; the tactile field (24 M) is written by tac_kernel, G0 / G1 / gains by tape_kernel
+    # the H block of the tape out; G0 / G1 / gains are written by tape_kernel.  The two passes that stream are credited
+    # with the bytes they MOVE: the tactile pass zeroes the whole field (cudaMemsetAsync, inside its timer) and re-writes
+    # the env-steps whose pad touches; the pull-back pass reads the tactile cotangent of the touched env-steps only.
     per_step = {"fwd_kernel": 8 * nu + 16 * n + 8 * nvar + 8 * n * n,
                 "tape_kernel": 8 * nu + 32 * n + 16 * n * n + 8 * nu,
-                "tac_kernel": 16 * n + 24 * M,
-                "vjp_kernel": 16 * n + 8 * nvar + 24 * M + 16 * n,
                 "bwd_kernel": 8 * n + 16 * n + 8 * (3 * n * n + nu) + 8 * nu}
-    fwd_bytes = per_step["fwd_kernel"] * B * T
+    launch_bytes = {k: v * items for k, v in per_step.items()}
+    launch_bytes["tac_kernel"] = items * (16 * n + 24 * M) + touched * 24 * M
+    launch_bytes["vjp_kernel"] = items * (16 * n + 8 * nvar + 16 * n) + touched * 24 * M
+    fwd_bytes = launch_bytes["fwd_kernel"]
     achieved = fwd_bytes / (fwd_ms * 1e-3) / 1e9
-    kernels = {k: {"ms": kt[k], "algorithmic_bytes_per_launch": per_step[k] * B * T,
-                   "achieved_gbs": per_step[k] * B * T / (kt[k] * 1e-3) / 1e9, "frac": per_step[k] * B * T / (kt[k] * 1e-3) / 1e9 / peak}
-               for k in per_step if kt.get(k)}
-    traffic = None
-    tp = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
-    tp = os.path.join(ROOT, "profiles", tp[-1]) if tp else ""
-    if os.path.exists(tp):
+    kernels = {k: {"ms": kt[k], "algorithmic_bytes_per_launch": launch_bytes[k],
+                   "achieved_gbs": launch_bytes[k] / (kt[k] * 1e-3) / 1e9, "frac": launch_bytes[k] / (kt[k] * 1e-3) / 1e9 / peak}
+               for k in launch_bytes if kt.get(k)}
+    kernels["tac_kernel"]["note"] = "memset of the field + env-steps in touch re-written (%d of %d)" % (touched, items)
+    kernels["vjp_kernel"]["note"] = "tactile cotangent read for the env-steps in touch only (%d of %d)" % (touched, items)
+    # figures captured under ncu (tools/gpu_ncu_r02.sh) are quoted only for the kernel sources they were captured on
+    from tactilesimulation_b200.build import source_sha
+    traffic, flops, cap_note = None, None, "no ncu capture for these kernel sources (profiles/r02_counters.json)"
+    cpath = os.path.join(ROOT, "profiles", "r02_counters.json")
+    if os.path.exists(cpath):
         try:
-            traffic = json.load(open(tp)).get("fwd_kernel_dram_bytes_per_launch")
+            cap = json.load(open(cpath))
+            if cap.get("source_sha") == source_sha() and cap.get("B") == B and cap.get("T") == T:
+                traffic = cap.get("fwd_kernel_dram_bytes_per_launch")
+                flops = cap.get("fwd_kernel_fp64_flops_per_launch")
+                cap_note = "ncu capture of this source (sha %s), B=%d T=%d" % (cap["source_sha"], B, T)
         except Exception:
-            traffic = None
+            pass
+    fp64 = {"peak_gflops": fp64_peak["gflops"], "peak_source": "tsim_debug_fp64_peak (DFMA chains, %d SMs, best of 3)" % fp64_peak["sms"],
+            "flops_per_launch": flops, "achieved_gflops": (flops / (fwd_ms * 1e-3) / 1e9) if flops else None,
+            "frac": (flops / (fwd_ms * 1e-3) / 1e9 / fp64_peak["gflops"]) if flops else None,
+            "flops_source": "smsp__sass_thread_inst_executed_op_{dfma x2, dmul, dadd}_pred_on of fwd_kernel; " + cap_note}
     roofline = {"bound": "hbm", "kernel": "fwd_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": cap_note,
                 "algorithmic_bytes_per_launch": fwd_bytes, "kernel_ms": fwd_ms,
-                "forward_call_ms": fwd_call_ms, "adjoint_call_ms": bwd_call_ms, "kernels": kernels,
-                "note": "fwd_kernel (the step loop) is fp64 latency-bound: its HBM fraction is small by construction; "
-                        "tac_kernel, the tactile read-out pass, is the kernel that streams (DESIGN.md roofline section)"}
+                "forward_call_ms": fwd_call_ms, "adjoint_call_ms": bwd_call_ms, "kernels": kernels, "fp64": fp64,
+                "note": "fwd_kernel (the step loop) is fp64 latency / issue bound: its HBM fraction is small by construction "
+                        "(SURVEY.md 8d), roofline.fp64 is the roofline that binds; the passes that stream are tac_kernel / vjp_kernel"}
 
     # ---- CPU baseline beside it: unmodified reference C++ on the host cores, bounded sample
     cpu = None

@@ -122,6 +122,13 @@ enum { TSIM_K_FWD = 0 /* step loop */, TSIM_K_TAPE /* G0 / G1 pass */, TSIM_K_TA
        TSIM_K_VJP /* readout pull-back pass */, TSIM_K_BWD /* reverse sweep */, TSIM_N_KERNELS };
 int tsim_scene_kernel_times(const tsim_scene* scene, double* ms /* [TSIM_N_KERNELS] */);
 
+/* Measurement aid: fp64 FMA peak of `device`, measured by a kernel of independent DFMA chains at full occupancy
+ * (csrc/microbench.cu).  out[0] = GFLOP/s (FMA = 2 flops), out[1] = kernel ms, out[2] = SM count, out[3] = max SM MHz.
+ * The path is fp64 (DH/Common.h:24) and latency / issue bound, not HBM bound: this is the
+ * denominator of bench.py's `roofline.fp64`.  Error text: tsim_debug_last_error(). */
+int tsim_debug_fp64_peak(int device, double* out /* [4] */);
+const char* tsim_debug_last_error(void);
+
 /* Readouts at a given state (no stepping). Any output may be NULL. */
 int tsim_readout(const tsim_scene* scene, int32_t B, const double* q, const double* qd, double* var_out,
                  double* tac_out, int32_t* marker_body, uint32_t* contact_masks, void* stream);

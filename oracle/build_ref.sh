@@ -82,4 +82,16 @@ cp -rf "$REF/assets/tactile_pad"/* "$OUT/assets/tactile_pad/"
 sed 's/resolution="13 10"/resolution="32 13"/' "$OUT/assets/pusher/pusher.xml" > "$OUT/assets/pusher/pusher_32x13.xml"
 # rolling-ball scene with a 40x40 marker grid (same dynamics, small golden fixture)
 sed 's/resolution="200 200"/resolution="40 40"/' "$OUT/assets/tactile_pad/tactile_pad.xml" > "$OUT/assets/tactile_pad/tactile_pad_40x40.xml"
-echo "build_ref: assets in $OUT/assets"
+# The reference's own python callers of the path (R/envs/*.py, R/utils/*.py, R/algorithms/gd.py, the gd config), staged
+# UNMODIFIED under the git-ignored _ref directory with the scene assets beside them where the env files look for them
+# (envs/assets): tests run these files against the reference module AND against tactilesimulation_b200.redmax
+# (sys.modules['redmax_py']) -- tests/test_reference_callers.py, tests/test_gpu_reference_callers.py.
+PYD="$OUT/py"
+mkdir -p "$PYD/envs" "$PYD/utils" "$PYD/algorithms" "$PYD/cfg"
+cp -f "$REF"/envs/*.py "$PYD/envs/"
+cp -f "$REF"/utils/*.py "$PYD/utils/"
+cp -f "$REF"/algorithms/gd.py "$PYD/algorithms/"
+cp -f "$REF"/examples/TactilePushExp/cfg/gd_tactile.yaml "$PYD/cfg/"
+rm -rf "$PYD/envs/assets"
+cp -r "$OUT/assets" "$PYD/envs/assets"
+echo "build_ref: assets in $OUT/assets, reference callers in $PYD"

@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_b200.so")
 
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
-           "tsim_forward", "tsim_forward_multistep", "tsim_scene_kernel_times", "tsim_readout", "tsim_backward"]
+           "tsim_forward", "tsim_forward_multistep", "tsim_scene_kernel_times", "tsim_readout", "tsim_backward",
+           "tsim_debug_fp64_peak", "tsim_debug_last_error"]
 KERNELS = ("fwd_kernel", "tape_kernel", "tac_kernel", "vjp_kernel", "bwd_kernel")
 (NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, CMASK_WORDS, INTEGRATOR, N_SIZES) = range(11)
 INT_BDF1, INT_BDF2, INT_SDIRK2 = 0, 1, 2
@@ -44,8 +45,20 @@ def load():
     lib.tsim_scene_kernel_times.argtypes = [vp, vp]
     lib.tsim_readout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_backward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsim_debug_fp64_peak.argtypes = [ctypes.c_int, vp]
+    lib.tsim_debug_last_error.restype = ctypes.c_char_p
     _lib = lib
     return lib
+
+
+def fp64_peak(device: int = 0):
+    """Measured fp64 FMA peak of the device: dict(gflops, ms, sms, sm_mhz).  tsim_debug_fp64_peak."""
+    import numpy as np
+    lib = load()
+    out = np.zeros(4, dtype=np.float64)
+    if lib.tsim_debug_fp64_peak(int(device), out.ctypes.data) != 0:
+        raise TactileSimError(lib.tsim_debug_last_error().decode("utf-8", "replace"))
+    return dict(gflops=float(out[0]), ms=float(out[1]), sms=int(out[2]), sm_mhz=float(out[3]))
 
 
 def check(rc, lib):

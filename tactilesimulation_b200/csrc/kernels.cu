@@ -110,6 +110,13 @@ struct DevTile {
     return p;
 #endif
   }
+  HD bool warp_any(bool p) const {
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+  }
   // ---- whole-warp helpers: every lane of the warp must call them together
   static const int TPW = 32 / LPE_;
   HD int tile_in_warp() const { return (threadIdx.x & 31) / LPE_; }
@@ -538,12 +545,10 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     if (!qd_traj) { a.qd_traj = (double*)p; p += nvec * sizeof(double); }
     CK(cudaMemsetAsync(a.work_counter, 0, 16, st));
     a.defer_tac = tac_pass ? 1 : 0;
-    // identity row map: the whole [T,B,3M] field is this call's; a memset runs at the HBM rate and the pass then
-    // only writes where a body can reach a pad (the sign of a zero is not part of the contract)
-    if (tac_pass && !tac_row) {
-      CK(cudaMemsetAsync(tac_out, 0, (size_t)T * B * s->sizes[TSIM_NDOF_TACTILE] * sizeof(double), st));
-      a.tac_prezeroed = 1;
-    }
+    // identity row map: the whole [T,B,3M] field is this call's; a memset (issued with the pass, inside its timer)
+    // runs at the HBM rate and the pass then only writes where a body can reach a pad (the sign of a zero is not
+    // part of the contract)
+    if (tac_pass && !tac_row) a.tac_prezeroed = 1;
     if (tape_pass) {
       double* qs = (double*)p;
       CK(cudaMemcpyAsync(qs, q, nst * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -581,6 +586,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   }
   CK(cudaEventRecord(s->ev[2], st));
   if (tac_pass) {
+    if (a.tac_prezeroed) CK(cudaMemsetAsync(tac_out, 0, (size_t)T * B * s->sizes[TSIM_NDOF_TACTILE] * sizeof(double), st));
 #if TS_MAXN <= 8
     if (s->lanes == 8) { if (prep(tac_kernel<8>, smem, TS_PASS_BPS)) return 1; tac_kernel<8><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
     else

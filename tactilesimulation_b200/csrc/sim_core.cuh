@@ -1302,6 +1302,7 @@ struct HostTile {
   HD void tile_sync() const {}
   HD bool cta_any(bool p) const { return p; }
   HD bool warp_all(bool p) const { return p; }
+  HD bool warp_any(bool p) const { return p; }
   // whole-warp helpers (one tile per "warp" on the host)
   static const int TPW = 1;
   HD int tile_in_warp() const { return 0; }
@@ -2458,7 +2459,7 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   v.cap_newton = a.max_newton;
   v.mode = TS_ST_BDF1;
   v.defer_g0 = a.defer_g0 != 0;
-  int t = 0;                             // warp-uniform
+  int t = 0;                             // step in flight: per tile (TS_TILE_STEPS) or warp-uniform
   bool tile_done = !active;
 #if KT_MULTISTEP
   const int integ = S.ib[KI_INTEGRATOR];
@@ -2476,101 +2477,132 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     tl.tile_sync();
     step_begin(S, v, ts);
   }
+  // Scheduling of the rounds (bit-identical results, only the pacing differs):
+  //  * TS_ROUNDS_PER_VOTE: the warps of a block meet at one block-wide vote per SUPER-round; between two votes a warp
+  //    runs up to that many evaluation rounds, but stops after a round in which one of its tiles had an active
+  //    general-primitive contact point.  A round in contact costs ~3x a contact-free one (the serial loop over the
+  //    active points): with one round per vote every warp of the block paid that price in every round; now the
+  //    contact-free warps run on while the warps in contact are in their point loop (a small loop that stays in the
+  //    instruction cache), and the block still streams through the large residual code together.
+  //  * TS_TILE_STEPS: the tiles of a warp advance through the time steps independently (t is per tile): a tile whose
+  //    step is complete starts its next step in the next round instead of idling until the slowest tile of the warp is done.
+#ifndef TS_ROUNDS_PER_VOTE
+#define TS_ROUNDS_PER_VOTE 3
+#endif
+#ifndef TS_TILE_STEPS
+#define TS_TILE_STEPS 1
+#endif
   for (;;) {
     { TS_TIC(tl); const bool go = tl.cta_any(t < a.T); TS_TOC(tl, 4); if (!go) break; }
-    if (t >= a.T) continue;
-    const long long es = (long long)t * B + env;
-    {
-      TS_TIC2(tl);
-      double cole[TS_NC(Tile::LPE)][TS_MAXN];
-      if (!tile_done) {
-        step_eval(tl, S, v, WD, cole);
-        tile_done = step_post(tl, S, v, a.tape ? a.tape + es * S.ntape : (double*)0, WD, cole);
-      }
-      TS_TOC2(tl, 5);
-    }
-    if (!tl.warp_all(tile_done)) continue;
-    TS_TIC(tl);
-#if KT_MULTISTEP
-    if (v.mode == TS_ST_SDIRK_A) {
-      // first SDIRK2 stage solved: (q_alpha, qd_alpha) become the second state, the second stage starts
-      double qa[TS_MAXN], qda[TS_MAXN];
-      for (int i = 0; i < TS_MAXN; ++i) {
-        qa[i] = (i < n) ? ts.x[i] : 0.0;
-        qda[i] = (i < n) ? (ts.x[i] - ts.q[i]) / (TS_SDIRK_ALPHA * S.h) : 0.0;
-      }
-      tl.tile_sync();
-      for (int i = 0; i < TS_MAXN; ++i) { ts.pq[i] = qa[i]; ts.pqd[i] = qda[i]; }
-      v.mode = TS_ST_SDIRK_B;
-      tl.tile_sync();
-      step_begin(S, v, ts);
-      tile_done = !active;
-      TS_TOC(tl, 6);
-      continue;
-    }
-#endif
-    // ---- the step is complete for every tile of this warp
-    if (active) {
-      int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
-      double qn[TS_MAXN], qdn[TS_MAXN];        // read-modify-write of shared tile state: reads, sync, writes
-#if KT_MULTISTEP
-      double qo[TS_MAXN], qdo[TS_MAXN];
-#endif
-      for (int i = 0; i < TS_MAXN; ++i) {
-        const double q1 = ts.x[i];
-        double xv = 0.0, xl = 0.0;
-        if (i < n) stage_inputs(S, ts, v.mode, i, q1, xv, xl);
-        qdn[i] = xv;
-        qn[i] = (i < n) ? q1 : 0.0;
-        if (i < n && !(q1 == q1)) stat |= TS_STAT_NAN;
-#if KT_MULTISTEP
-        qo[i] = ts.q[i]; qdo[i] = ts.qd[i];
-#endif
-      }
-      tl.tile_sync();
-      for (int i = 0; i < TS_MAXN; ++i) {
-        ts.q[i] = qn[i]; ts.qd[i] = qdn[i];
-#if KT_MULTISTEP
-        ts.pq[i] = qo[i]; ts.pqd[i] = qdo[i];      // state one step back (BDF2)
-#endif
-      }
-      if (tl.lane == 0) {
-#ifdef __CUDA_ARCH__
-        if (a.tape_order) {
-          // contact and contact-free evaluations cost 3:1; the tape pass takes its env-steps grouped by kind so that
-          // the tiles of a warp and the warps of a block run evaluations of the same cost together
-          const long long items = (long long)a.T * B;
-          const unsigned pos = WD.gp_any ? atomicAdd(a.work_counter + 2, 1u)
-                                         : (unsigned)(items - 1) - atomicAdd(a.work_counter + 3, 1u);
-          a.tape_order[pos] = (int)es;
+#pragma unroll 1
+    for (int rep = 0; rep < TS_ROUNDS_PER_VOTE; ++rep) {      // (not unrolled: ONE copy of the residual code)
+      bool heavy = false;
+      if (t < a.T) {                       // per tile with TS_TILE_STEPS, warp-uniform otherwise
+        const long long es = (long long)t * B + env;
+        {
+          TS_TIC2(tl);
+          double cole[TS_NC(Tile::LPE)][TS_MAXN];
+          if (!tile_done) {
+            step_eval(tl, S, v, WD, cole);
+            tile_done = step_post(tl, S, v, a.tape ? a.tape + es * S.ntape : (double*)0, WD, cole);
+            heavy = WD.gp_any != 0;
+          }
+          TS_TOC2(tl, 5);
         }
+#if TS_TILE_STEPS
+        const bool finish = tile_done;
+#else
+        const bool finish = tl.warp_all(tile_done);
 #endif
-        if (a.status) a.status[es] = stat;
-        if (a.q_traj) for (int i = 0; i < n; ++i) st_stream(a.q_traj + es * n + i, qn[i]);
-        if (a.qd_traj) for (int i = 0; i < n; ++i) st_stream(a.qd_traj + es * n + i, qdn[i]);
-      }
-      const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
-      const int tr = (a.tac_out && !a.defer_tac) ? (a.tac_row ? a.tac_row[t] : t) : -1;
-      if (vr >= 0 || tr >= 0 || a.cmask) {
-        // the work space already holds the kinematics of the new state (last residual evaluation)
-        readout_from_work(tl, S, WD,
-                          vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
-                          tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
-                          (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
-                          a.cmask ? a.cmask + es * S.cmw : (unsigned*)0);
-      }
-    }
-    ++t;
+        if (finish) {
+          TS_TIC(tl);
+          bool next_stage = false;
 #if KT_MULTISTEP
-    v.mode = (integ == TS_INT_SDIRK2) ? TS_ST_SDIRK_A : ((integ == TS_INT_BDF2) ? TS_ST_BDF2 : TS_ST_BDF1);
+          if (v.mode == TS_ST_SDIRK_A) {
+            // first SDIRK2 stage solved: (q_alpha, qd_alpha) become the second state, the second stage starts
+            double qa[TS_MAXN], qda[TS_MAXN];
+            for (int i = 0; i < TS_MAXN; ++i) {
+              qa[i] = (i < n) ? ts.x[i] : 0.0;
+              qda[i] = (i < n) ? (ts.x[i] - ts.q[i]) / (TS_SDIRK_ALPHA * S.h) : 0.0;
+            }
+            tl.tile_sync();
+            for (int i = 0; i < TS_MAXN; ++i) { ts.pq[i] = qa[i]; ts.pqd[i] = qda[i]; }
+            v.mode = TS_ST_SDIRK_B;
+            tl.tile_sync();
+            step_begin(S, v, ts);
+            tile_done = !active;
+            next_stage = true;
+          }
 #endif
-    if (t < a.T) {
-      tl.tile_sync();                    // readouts of this step are done in every lane of the tile
-      for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
-      step_begin(S, v, ts);
-      tile_done = !active;
+          if (!next_stage) {
+            // ---- the step is complete (for this tile / for every tile of this warp)
+            if (active) {
+              int stat = (v.iters & 0xff) | ((v.ls & 0xff) << 8) | (v.converged ? 0 : TS_STAT_NOT_CONVERGED);
+              double qn[TS_MAXN], qdn[TS_MAXN];        // read-modify-write of shared tile state: reads, sync, writes
+#if KT_MULTISTEP
+              double qo[TS_MAXN], qdo[TS_MAXN];
+#endif
+              for (int i = 0; i < TS_MAXN; ++i) {
+                const double q1 = ts.x[i];
+                double xv = 0.0, xl = 0.0;
+                if (i < n) stage_inputs(S, ts, v.mode, i, q1, xv, xl);
+                qdn[i] = xv;
+                qn[i] = (i < n) ? q1 : 0.0;
+                if (i < n && !(q1 == q1)) stat |= TS_STAT_NAN;
+#if KT_MULTISTEP
+                qo[i] = ts.q[i]; qdo[i] = ts.qd[i];
+#endif
+              }
+              tl.tile_sync();
+              for (int i = 0; i < TS_MAXN; ++i) {
+                ts.q[i] = qn[i]; ts.qd[i] = qdn[i];
+#if KT_MULTISTEP
+                ts.pq[i] = qo[i]; ts.pqd[i] = qdo[i];      // state one step back (BDF2)
+#endif
+              }
+              if (tl.lane == 0) {
+#ifdef __CUDA_ARCH__
+                if (a.tape_order) {
+                  // contact and contact-free evaluations cost 3:1; the tape pass takes its env-steps grouped by kind so that
+                  // the tiles of a warp and the warps of a block run evaluations of the same cost together
+                  const long long items = (long long)a.T * B;
+                  const unsigned pos = WD.gp_any ? atomicAdd(a.work_counter + 2, 1u)
+                                                 : (unsigned)(items - 1) - atomicAdd(a.work_counter + 3, 1u);
+                  a.tape_order[pos] = (int)es;
+                }
+#endif
+                if (a.status) a.status[es] = stat;
+                if (a.q_traj) for (int i = 0; i < n; ++i) st_stream(a.q_traj + es * n + i, qn[i]);
+                if (a.qd_traj) for (int i = 0; i < n; ++i) st_stream(a.qd_traj + es * n + i, qdn[i]);
+              }
+              const int vr = a.var_out ? (a.var_row ? a.var_row[t] : t) : -1;
+              const int tr = (a.tac_out && !a.defer_tac) ? (a.tac_row ? a.tac_row[t] : t) : -1;
+              if (vr >= 0 || tr >= 0 || a.cmask) {
+                // the work space already holds the kinematics of the new state (last residual evaluation)
+                readout_from_work(tl, S, WD,
+                                  vr >= 0 ? a.var_out + ((long long)vr * B + env) * 3 * S.nee : (double*)0,
+                                  tr >= 0 ? a.tac_out + ((long long)tr * B + env) * 3 * S.nmark : (double*)0,
+                                  (tr >= 0 && a.marker_body) ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0,
+                                  a.cmask ? a.cmask + es * S.cmw : (unsigned*)0);
+              }
+            }
+            ++t;
+#if KT_MULTISTEP
+            v.mode = (integ == TS_INT_SDIRK2) ? TS_ST_SDIRK_A : ((integ == TS_INT_BDF2) ? TS_ST_BDF2 : TS_ST_BDF1);
+#endif
+            if (t < a.T) {
+              tl.tile_sync();                    // readouts of this step are done in every lane of the tile
+              for (int i = 0; i < TS_MAXU; ++i) ts.u[i] = (i < nu) ? a.u[t * a.u_stride + (long long)env * nu + i] : 0.0;
+              step_begin(S, v, ts);
+              tile_done = !active;
+            }
+          }
+          TS_TOC(tl, 6);
+        }
+      }
+      // (whole-warp votes, outside of the per-tile control flow)
+      if (tl.warp_any(heavy) || !tl.warp_any(t < a.T)) break;
     }
-    TS_TOC(tl, 6);
   }
 #if KT_MULTISTEP
   tl.tile_sync();

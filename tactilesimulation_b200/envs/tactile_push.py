@@ -93,15 +93,23 @@ class BatchedTactilePushEnv:
             return torch.cat([state, tac.reshape(self.B, -1)], dim=1)
         return tac.permute(0, 3, 1, 2), state
 
-    def reset(self):
+    def reset(self, q0: Optional[torch.Tensor] = None, goal: Optional[torch.Tensor] = None):
+        """q0 [B,7] / goal [B,3]: given initial states / goals instead of the random draws (replay of recorded
+        episodes, e.g. of the reference's own environment in tests/test_gpu_reference_callers.py)."""
         B = self.B
-        q0 = self.q_init.unsqueeze(0).repeat(B, 1)
-        q0[:, 1] = -0.001
-        q0[:, 4] = self._uniform((B,), -0.02, 0.02)
-        gx = self._uniform((B,), 0.15, 0.25)
-        gy = self._uniform((B,), -0.2, 0.2)
-        gr = gy * math.pi + self._uniform((B,), -math.pi / 16.0, math.pi / 16.0)
-        self.goal = torch.stack([gx, gy, gr], dim=1)
+        if q0 is None:
+            q0 = self.q_init.unsqueeze(0).repeat(B, 1)
+            q0[:, 1] = -0.001
+            q0[:, 4] = self._uniform((B,), -0.02, 0.02)
+        else:
+            q0 = q0.to(device=self.device, dtype=torch.float64).clone()
+        if goal is None:
+            gx = self._uniform((B,), 0.15, 0.25)
+            gy = self._uniform((B,), -0.2, 0.2)
+            gr = gy * math.pi + self._uniform((B,), -math.pi / 16.0, math.pi / 16.0)
+            self.goal = torch.stack([gx, gy, gr], dim=1)
+        else:
+            self.goal = goal.to(device=self.device, dtype=torch.float64).clone()
         self.sim.set_state_init(q0, torch.zeros_like(q0))
         self.sim.reset(backward_flag=self.gradient)
         self.state_q = q0
@@ -110,11 +118,14 @@ class BatchedTactilePushEnv:
         self.current_step = 0
         return self._obs()
 
-    def step(self, u: torch.Tensor) -> Tuple[object, torch.Tensor, bool, dict]:
-        """u [B,3] raw policy output (before tanh).  Returns obs, reward [B], done (time limit), info."""
+    def step(self, u: torch.Tensor, external_force: Optional[torch.Tensor] = None) -> Tuple[object, torch.Tensor, bool, dict]:
+        """u [B,3] raw policy output (before tanh).  Returns obs, reward [B], done (time limit), info.
+        external_force [B,2]: given pushes on the box for this step instead of the random draw."""
         B = self.B
         action = torch.tanh(u.to(torch.float64))
-        if self.current_step % 10 == 0:
+        if external_force is not None:
+            self.external_force = external_force.to(device=self.device, dtype=torch.float64)
+        elif self.current_step % 10 == 0:
             p = self._uniform((B, 1), 0.0, 1.0)
             self.external_force = torch.where(p < 0.5, self._uniform((B, 2), -1.0, 1.0), torch.zeros((B, 2), dtype=torch.float64, device=self.device))
         robot_action = torch.cat([action, self.external_force, torch.zeros((B, 1), dtype=torch.float64, device=self.device)], dim=1)

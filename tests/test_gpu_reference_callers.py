@@ -1,0 +1,109 @@
+"""north_star: "envs/redmax_torch_functions.py ... envs/redmax_torch_env.py and algorithms/gd.py run unchanged".
+
+The reference's OWN files (staged unmodified under oracle/_ref/py by oracle/build_ref.sh; gym / tensorboardX / matplotlib
+from tests/shims) are imported with sys.modules['redmax_py'] = tactilesimulation_b200.redmax and run on the GPU:
+  * the unmodified EpisodicSimFunction / StepSimFunction reproduce the reference's golden gradients;
+  * the unmodified TactilePushEnv (reset / step through StepSimFunction) gives the observations, rewards and action
+    gradients of the SAME files run on the reference's own module (executed live on the box's CPU);
+  * one GD.compute_reward_and_grad epoch of the unmodified gd.py gives the same episode reward and policy gradient;
+  * the batched front-end (tactilesimulation_b200.envs.BatchedTactilePushEnv) replays episodes recorded from the
+    reference's environment: same observations / rewards / action gradients per environment."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import ref_callers as rc
+from tests.conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+XML = os.path.join(rc.PY_DIR, "envs", "assets", "pusher", "pusher.xml")
+
+
+def _need_ref():
+    if not rc.available():
+        pytest.fail("oracle/_ref/py (reference callers + assets) is missing on this box: run oracle/build_ref.sh before gpurun")
+
+
+def _dropin():
+    import tactilesimulation_b200.redmax as redmax
+    return rc.load(redmax)
+
+
+def test_unmodified_functions_reproduce_the_goldens_on_the_dropin():
+    _need_ref()
+    ns = _dropin()
+    rc.check_episodic_function(ns, XML, np.load(os.path.join(GOLDEN, "pusher13x10_episodic_s0.npz")), rel_err)
+    rc.check_stepsim_function(ns, XML, np.load(os.path.join(GOLDEN, "pusher13x10_stepsim_s0.npz")), rel_err)
+
+
+def test_unmodified_push_env_matches_itself_on_the_reference_module():
+    _need_ref()
+    o_ref, r_ref, g_ref = rc.run_push_env(rc.load(rc.reference_module()), steps=12)
+    o_new, r_new, g_new = rc.run_push_env(_dropin(), steps=12)
+    assert o_new.shape == o_ref.shape == (13, 393)
+    assert np.abs(o_new[:, :3] - o_ref[:, :3]).max() <= 1e-9            # goal pose in the gripper frame
+    assert rel_err(o_new[:, 3:], o_ref[:, 3:]) <= 1e-8                   # tactile field
+    assert np.abs(o_ref[:, 3:]).max() > 0
+    assert np.allclose(r_new, r_ref, rtol=1e-9, atol=1e-12)
+    assert rel_err(g_new, g_ref) <= 1e-6
+
+
+def test_unmodified_gd_epoch_matches_itself_on_the_reference_module(tmp_path):
+    _need_ref()
+    rew_ref, len_ref, gd_ref = rc.run_gd_epoch(rc.load(rc.reference_module()), str(tmp_path / "ref"))
+    g_ref = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_ref.actor.parameters()])
+    rew_new, len_new, gd_new = rc.run_gd_epoch(_dropin(), str(tmp_path / "new"))
+    g_new = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_new.actor.parameters()])
+    assert len_new == len_ref == [100]
+    assert np.allclose(rew_new, rew_ref, rtol=1e-8)
+    assert rel_err(g_new, g_ref) <= 1e-6 and np.abs(g_ref).max() > 0
+
+
+def test_batched_frontend_replays_episodes_of_the_reference_env():
+    """B = 4 episodes of the unmodified TactilePushEnv on the reference module (different seeds: initial state, goal,
+    random pushes and actions recorded) replayed through BatchedTactilePushEnv in ONE batch."""
+    _need_ref()
+    from tactilesimulation_b200.envs import BatchedTactilePushEnv
+    from tactilesimulation_b200.redmax import Simulation
+    ns = rc.load(rc.reference_module())
+    B, steps = 4, 12
+    rec = []
+    for e in range(B):
+        env = ns.gym.make("TactilePush-v1", use_torch=True, gradient=True, observation_type="tactile_flatten")
+        env.seed(10 + e)
+        obs = [env.reset().detach().numpy().copy()]
+        q0, goal = env.unwrapped.state_q.numpy().copy(), env.unwrapped.goal.numpy().copy()
+        rng = np.random.RandomState(100 + e)
+        acts, ext, rews, total = [], [], [], 0.0
+        for k in range(steps):
+            a = torch.tensor(rng.normal(size=3), dtype=torch.double, requires_grad=True)
+            o, r, done, info = env.step(a)
+            obs.append(o.detach().numpy().copy())
+            ext.append(env.unwrapped.external_force.copy())
+            rews.append(float(r.detach()))
+            acts.append(a)
+            total = total + r
+        total.backward()
+        rec.append(dict(q0=q0, goal=goal, obs=np.stack(obs), ext=np.stack(ext), rew=np.array(rews),
+                        act=np.stack([a.detach().numpy() for a in acts]), grad=np.stack([a.grad.numpy() for a in acts])))
+    sim = Simulation(XML, batch=B)
+    benv = BatchedTactilePushEnv(sim, observation_type="tactile_flatten", gradient=True)
+    dev = sim.device
+    obs = [benv.reset(q0=torch.tensor(np.stack([r["q0"] for r in rec])), goal=torch.tensor(np.stack([r["goal"] for r in rec])))]
+    acts, total, rews = [], 0.0, []
+    for k in range(steps):
+        a = torch.tensor(np.stack([r["act"][k] for r in rec]), device=dev, requires_grad=True)
+        o, r, done, info = benv.step(a, external_force=torch.tensor(np.stack([rc_["ext"][k] for rc_ in rec])))
+        obs.append(o)
+        rews.append(r.detach().cpu().numpy())
+        acts.append(a)
+        total = total + r.sum()
+    total.backward()
+    for e in range(B):
+        o_new = np.stack([o[e].detach().cpu().numpy() for o in obs])
+        assert np.abs(o_new[:, :3] - rec[e]["obs"][:, :3]).max() <= 1e-9, e
+        assert rel_err(o_new[:, 3:], rec[e]["obs"][:, 3:]) <= 1e-8, e
+        assert np.allclose(np.array([r[e] for r in rews]), rec[e]["rew"], rtol=1e-9, atol=1e-12), e
+        assert rel_err(np.stack([a.grad[e].cpu().numpy() for a in acts]), rec[e]["grad"]) <= 1e-6, e
