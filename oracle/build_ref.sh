@@ -82,6 +82,25 @@ cp -rf "$REF/assets/tactile_pad"/* "$OUT/assets/tactile_pad/"
 sed 's/resolution="13 10"/resolution="32 13"/' "$OUT/assets/pusher/pusher.xml" > "$OUT/assets/pusher/pusher_32x13.xml"
 # rolling-ball scene with a 40x40 marker grid (same dynamics, small golden fixture)
 sed 's/resolution="200 200"/resolution="40 40"/' "$OUT/assets/tactile_pad/tactile_pad.xml" > "$OUT/assets/tactile_pad/tactile_pad_40x40.xml"
+# synthetic variants named by BASELINE.json configs[3] / [4]: TactileInsertion with 2 x (20x20)
+# pads (same scene, denser marker grids), DClaw with 3 x (8x6) = 48-marker pads (every 6th marker of the reference's
+# 302-marker fingertip spec up to 48, laid on an 8x6 image grid)
+sed 's/resolution="13 10"/resolution="20 20"/g' "$OUT/assets/tactile_insertion/tactile_insertion.xml" > "$OUT/assets/tactile_insertion/tactile_insertion_20x20.xml"
+$PY - "$OUT/assets/dclaw_rotate" <<'PYX'
+import sys, os
+d = sys.argv[1]
+lines = open(os.path.join(d, "tactile", "dclaw_fingertip_tactile.txt")).read().strip().splitlines()
+n, rows = int(lines[0]), lines[1:]
+pick = [rows[i] for i in range(0, n, 6)][:48]
+out = ["48"]
+for k, r in enumerate(pick):
+    f = r.split('" "')
+    f[1] = "%d %d" % (k // 6, k % 6)
+    out.append('" "'.join(f))
+open(os.path.join(d, "tactile", "dclaw_fingertip_tactile_8x6.txt"), "w").write("\n".join(out) + "\n")
+x = open(os.path.join(d, "dclaw_torque_control.xml")).read().replace("tactile/dclaw_fingertip_tactile.txt", "tactile/dclaw_fingertip_tactile_8x6.txt")
+open(os.path.join(d, "dclaw_torque_control_8x6.xml"), "w").write(x)
+PYX
 # The reference's own python callers of the path (R/envs/*.py, R/utils/*.py, R/algorithms/gd.py, the gd config), staged
 # UNMODIFIED under the git-ignored _ref directory with the scene assets beside them where the env files look for them
 # (envs/assets): tests run these files against the reference module AND against tactilesimulation_b200.redmax

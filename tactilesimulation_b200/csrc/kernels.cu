@@ -24,6 +24,16 @@
 #define TS_SYNC_EVALS 1
 #endif
 #include "kernel_layout.h"
+// 224 threads = 7 warps = 28 environments per block: 4096 environments make 147 blocks, one per SM
+// (148 SMs), and the block is the lockstep domain of TS_SYNC_EVALS (sim_core.cuh, step_forward).
+#ifndef TS_BLOCK
+#define TS_BLOCK 224
+#endif
+// Block-cooperative evaluation of the active contact points in the step loop (sim_core.cuh, gp_points_coop): variant 8
+// (cuboid contacts only, one lane per reduced coordinate).  -DTS_NO_COOP_GP builds the A/B library without it.
+#if TS_VARIANT == 8 && !defined(TS_NO_COOP_GP)
+#define TS_COOP_GP 1
+#endif
 // this translation unit is one VARIANT of the library (kernel_layout.h): every ABI name gets the variant's
 // suffix; csrc/cabi.cpp owns the public names and dispatches per scene
 #define TS_CAT_(a, b) a##b
@@ -50,16 +60,27 @@ namespace TSV(tsimns) {
 #include "sim_core.cuh"
 
 #ifdef TS_PROFILE
-__device__ long long* g_prof = 0;      // [threads][8] cycle accumulators (development builds only)
+__device__ long long* g_prof = 0;      // [threads][16] cycle accumulators (development builds only)
 #endif
 
-template <int LPE_>
+template <int LPE_, bool COOP_ = false>
 struct DevTile {
   static const int LPE = LPE_;
+  static const bool COOP = COOP_;      // the tiles of the block evaluate the active contact points together (fwd_kernel)
   int lane;
   unsigned mask;
+  void* coop;                          // CoopArea<LPE> of the block (shared memory), COOP only
+  int tile_id;                         // tile index inside the block
+  // block-wide barriers that the lanes of a warp may reach diverged (tiles run independent control flow)
+  __device__ __forceinline__ void cta_sync_unaligned() const { asm volatile("barrier.sync 0;" ::: "memory"); }
+  __device__ __forceinline__ bool cta_or_unaligned(bool p) const {
+    int r;
+    asm volatile("{\n\t.reg .pred pin, pout;\n\tsetp.ne.s32 pin, %1, 0;\n\tbarrier.red.or.pred pout, 0, pin;\n\tselp.s32 %0, 1, 0, pout;\n\t}"
+                 : "=r"(r) : "r"((int)p) : "memory");
+    return r != 0;
+  }
 #ifdef TS_PROFILE
-  mutable long long acc[8];
+  mutable long long acc[16];
 #endif
   HD double bcast(double v, int src) const {
 #ifdef __CUDA_ARCH__
@@ -165,11 +186,6 @@ struct DevTile {
   }
 };
 
-// 224 threads = 7 warps = 28 environments per block: 4096 environments make 147 blocks, one per SM
-// (148 SMs), and the block is the lockstep domain of TS_SYNC_EVALS (sim_core.cuh, step_forward).
-#ifndef TS_BLOCK
-#define TS_BLOCK 224
-#endif
 // resident blocks per SM the launch bounds and the shared-memory carve-out are sized for
 #ifndef TS_BPS
 #define TS_BPS 1
@@ -220,14 +236,24 @@ __device__ __forceinline__ void bind_work(WorkSplit& W, const SceneView& S, int 
   W.beta = 0.0;
 }
 
-template <int LPE>
-__device__ __forceinline__ DevTile<LPE> make_tile() {
-  DevTile<LPE> tl;
+template <int LPE, bool COOP = false>
+__device__ __forceinline__ DevTile<LPE, COOP> make_tile() {
+  DevTile<LPE, COOP> tl;
   tl.lane = threadIdx.x % LPE;
   const int wl = threadIdx.x & 31;
   tl.mask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (wl - tl.lane));
+  tl.coop = 0;
+  tl.tile_id = threadIdx.x / LPE;
   return tl;
 }
+// cooperative step loop: one lane per reduced coordinate (one evaluation per round), 8-lane tiles
+#ifdef TS_COOP_GP
+#define TS_COOP_FOR(LPE) ((LPE) == 8 && TS_MAXN <= 8)
+template <int LPE> __host__ __device__ inline size_t coop_bytes() { return TS_COOP_FOR(LPE) ? sizeof(CoopArea<LPE>) : 0; }
+#else
+#define TS_COOP_FOR(LPE) false
+template <int LPE> __host__ __device__ inline size_t coop_bytes() { return 0; }
+#endif
 
 template <int LPE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
@@ -235,17 +261,19 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
-  DevTile<LPE> tl = make_tile<LPE>();
+  DevTile<LPE, TS_COOP_FOR(LPE)> tl = make_tile<LPE, TS_COOP_FOR(LPE)>();
   WorkSplit WD;
   bind_work<LPE>(WD, S, ni, nd, smem);
+  // the cooperative area follows the tile regions
+  tl.coop = smem + ((scene_bytes(ni, nd) + (size_t)(TS_BLOCK / LPE) * tile_region_doubles(S.nj) * sizeof(double) + 15) & ~(size_t)15);
 #ifdef TS_PROFILE
-  for (int i = 0; i < 8; ++i) tl.acc[i] = 0;
+  for (int i = 0; i < 16; ++i) tl.acc[i] = 0;
   const long long t_begin = clock64();
 #endif
   env_forward(tl, S, a, env, WD);     // tiles past the batch stay in the block-wide votes
 #ifdef TS_PROFILE
   tl.acc[7] = clock64() - t_begin;
-  if (g_prof) for (int i = 0; i < 8; ++i) g_prof[(long long)(blockIdx.x * blockDim.x + threadIdx.x) * 8 + i] = tl.acc[i];
+  if (g_prof) for (int i = 0; i < 16; ++i) g_prof[(long long)(blockIdx.x * blockDim.x + threadIdx.x) * 16 + i] = tl.acc[i];
 #endif
 }
 
@@ -521,6 +549,8 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
   a.defer_tac = 0; a.tac_prezeroed = 0; a.work_counter = 0;
   const size_t smem = scene_smem(s);
+  // the step loop adds the cooperative contact-point area of its block (8-lane tiles of variant 8)
+  const size_t smem_fwd = s->lanes == 8 && coop_bytes<8>() ? ((smem + 15) & ~(size_t)15) + coop_bytes<8>() : smem;
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
@@ -561,7 +591,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   s->ran[TSIM_K_FWD] = 1; s->ran[TSIM_K_TAPE] = tape_pass ? 1 : 0; s->ran[TSIM_K_TAC] = tac_pass ? 1 : 0;
   CK(cudaEventRecord(s->ev[0], st));
 #if TS_MAXN <= 8
-  if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
+  if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem_fwd)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem_fwd, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
   else
 #endif
   if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }

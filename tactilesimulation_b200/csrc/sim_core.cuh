@@ -68,6 +68,16 @@
 #define TS_GPT(tl, slot)
 #define TS_GPT0()
 #endif
+// cooperative contact-point phase (slots 8..15): items, phases with items, batches | cycles: publish, compute, wait, accumulate
+#if defined(TS_PROFILE) && defined(__CUDA_ARCH__)
+#define TS_CPT0() long long ts_cp_ = clock64()
+#define TS_CPT(tl, slot) do { const long long ts_now_ = clock64(); (tl).acc[slot] += ts_now_ - ts_cp_; ts_cp_ = ts_now_; } while (0)
+#define TS_CPN(tl, slot, n) (tl).acc[slot] += (n)
+#else
+#define TS_CPT0()
+#define TS_CPT(tl, slot)
+#define TS_CPN(tl, slot, n)
+#endif
 
 // Output streams (tactile field, tape, trajectory) are written once and never re-read by the forward kernel:
 // evict-first stores keep them from displacing the per-lane tangent work space (local memory) in L2, whose
@@ -857,71 +867,105 @@ template <class T> struct GpPair {
   double R1v[9], p1v[3], R2v[9], p2v[3];    // values of the two body frames (reference evaluation order of the face pick)
 };
 
-// Penalty force of ONE active sampled point (DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
+// Penalty force of NP active sampled points (DH/Force/ForceGeneralPrimitiveContact.cpp:154-229,
 // DH/Body/BodyCuboid.cpp:146-184), accumulated as wrenches on body 1 / body 2, both in box coordinates
 // about the box origin.
-template <class T>
-HD void gp_point_force(const GpPair<T>& P, const double* xi1, const double* hs, double kn, double kt, double mu,
-                       double damp, T* w1, T* w2) {
+// The force of one point is a chain of ~360 dependent fp64 instructions that a warp issues at ~0.1 IPC (7 warps per SM,
+// nothing to switch to): NP points are evaluated side by side, stage by stage, so that the instruction scheduler
+// interleaves NP independent chains.  The arithmetic of each point and the order in which the wrenches are summed are
+// those of the one-point evaluation: results do not depend on NP.
+template <int NP, class T>
+HD void gp_point_terms(const GpPair<T>& P, const double* const* xi1, const double* hs, double kn, double kt, double mu,
+                       double damp, T (*tq2)[3], T (*Fb)[3], T (*tq1)[3]) {
   // face pick on the reference's evaluation order (BodyCuboid.cpp:162-173), values only
-  double xwv[3], yv[3], xv[3];
-  mv3(P.R1v, xi1, xwv);
-  for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
-  mtv3(P.R2v, yv, xv);
-  int ax; double sg;
-  cuboid_face(xv, hs, ax, sg);
-  // the face axis is data: select instead of indexing so that every vector stays in registers
-  const bool a0 = (ax == 0), a1 = (ax == 1), a2 = (ax == 2);
-  const double e[3] = {a0 ? sg : 0.0, a1 ? sg : 0.0, a2 ? sg : 0.0};
-  const double hsa = a0 ? hs[0] : (a1 ? hs[1] : hs[2]);
-  T ap[3], x[3];
-  mv3(P.Q, xi1, ap);                                   // pad point relative to the pad origin, box coordinates
-  for (int i = 0; i < 3; ++i) x[i] = ap[i] + P.rr[i];
-  T d = sg * (a0 ? x[0] : (a1 ? x[1] : x[2])) - hsa;
-  // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
-  T u[3], t3[3];
-  cross3(P.w1b, ap, u);
-  cross3(P.ph2, x, t3);
-  for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
-  T ddot = sg * (a0 ? u[0] : (a1 ? u[1] : u[2]));
-  // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
-  T tb[3];
-  cross3(P.ph2, e, t3);
-  for (int i = 0; i < 3; ++i) tb[i] = u[i] + d * t3[i];
-  {
-    T c0 = tb[0] - sg * (sg * tb[0]), c1 = tb[1] - sg * (sg * tb[1]), c2 = tb[2] - sg * (sg * tb[2]);
-    tb[0] = a0 ? c0 : tb[0]; tb[1] = a1 ? c1 : tb[1]; tb[2] = a2 ? c2 : tb[2];
+  double sg[NP], hsa[NP], e[NP][3];
+  bool a0[NP], a1[NP], a2[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    double xwv[3], yv[3], xv[3];
+    mv3(P.R1v, xi1[q], xwv);
+    for (int i = 0; i < 3; ++i) yv[i] = (xwv[i] + P.p1v[i]) - P.p2v[i];
+    mtv3(P.R2v, yv, xv);
+    int ax;
+    cuboid_face(xv, hs, ax, sg[q]);
+    // the face axis is data: select instead of indexing so that every vector stays in registers
+    a0[q] = (ax == 0); a1[q] = (ax == 1); a2[q] = (ax == 2);
+    e[q][0] = a0[q] ? sg[q] : 0.0; e[q][1] = a1[q] ? sg[q] : 0.0; e[q][2] = a2[q] ? sg[q] : 0.0;
+    hsa[q] = a0[q] ? hs[0] : (a1[q] ? hs[1] : hs[2]);
   }
-  T s = kn * d - damp * ddot * d;
-  T Fb[3];
-  for (int i = 0; i < 3; ++i) Fb[i] = -(s * e[i]);
+  T x[NP][3], d[NP], tb[NP][3], s[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    T ap[3];
+    mv3(P.Q, xi1[q], ap);                                // pad point relative to the pad origin, box coordinates
+    for (int i = 0; i < 3; ++i) x[q][i] = ap[i] + P.rr[i];
+    d[q] = sg[q] * (a0[q] ? x[q][0] : (a1[q] ? x[q][1] : x[q][2])) - hsa[q];
+    // relative velocity in the box frame: u = R2^T xw_dot - w2 x x - v2
+    T u[3], t3[3];
+    cross3(P.w1b, ap, u);
+    cross3(P.ph2, x[q], t3);
+    for (int i = 0; i < 3; ++i) u[i] = ((u[i] + P.v1b[i]) - t3[i]) - P.ph2[3 + i];
+    T ddot = sg[q] * (a0[q] ? u[0] : (a1[q] ? u[1] : u[2]));
+    // tangential velocity in the box frame: (I - e e^T)(u + d w2 x e)
+    cross3(P.ph2, e[q], t3);
+    for (int i = 0; i < 3; ++i) tb[q][i] = u[i] + d[q] * t3[i];
+    {
+      T c0 = tb[q][0] - sg[q] * (sg[q] * tb[q][0]), c1 = tb[q][1] - sg[q] * (sg[q] * tb[q][1]), c2 = tb[q][2] - sg[q] * (sg[q] * tb[q][2]);
+      tb[q][0] = a0[q] ? c0 : tb[q][0]; tb[q][1] = a1[q] ? c1 : tb[q][1]; tb[q][2] = a2[q] ? c2 : tb[q][2];
+    }
+    s[q] = kn * d[q] - damp * ddot * d[q];
+    for (int i = 0; i < 3; ++i) Fb[q][i] = -(s[q] * e[q][i]);
+  }
   if (mu > TS_EPS) {
     // the reference uses the norm of the 6-vector wrench on body 1 (:208): n1 = R1^T R2 e = row `ax` of
     // R21 times sg, m1 = xi1 x n1
-    T n1[3], m1[3];
-    for (int i = 0; i < 3; ++i) n1[i] = sg * (a0 ? P.Q[i] : (a1 ? P.Q[3 + i] : P.Q[6 + i]));
-    cross3(xi1, n1, m1);
-    double n6 = 0.0;
-    for (int i = 0; i < 3; ++i) n6 += val(m1[i]) * val(m1[i]) + val(n1[i]) * val(n1[i]);
-    double fcn = fabs(val(s)) * sqrt(n6);
-    double tn = sqrt(val(tb[0]) * val(tb[0]) + val(tb[1]) * val(tb[1]) + val(tb[2]) * val(tb[2]));
-    if (mu * fcn >= kt * tn - TS_EPS) {
-      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - kt * tb[i];
-    } else {
-      T n6T = m1[0] * m1[0] + m1[1] * m1[1] + m1[2] * m1[2] + n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2];
-      T fcT = dabs(s) * dsqrt(n6T);
-      T tnT = dsqrt(tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2]);
-      T sc = mu * fcT / tnT;
-      for (int i = 0; i < 3; ++i) Fb[i] = Fb[i] - sc * tb[i];
+    T n1[NP][3], m1[NP][3];
+    bool stat[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      for (int i = 0; i < 3; ++i) n1[q][i] = sg[q] * (a0[q] ? P.Q[i] : (a1[q] ? P.Q[3 + i] : P.Q[6 + i]));
+      cross3(xi1[q], n1[q], m1[q]);
+      double n6 = 0.0;
+      for (int i = 0; i < 3; ++i) n6 += val(m1[q][i]) * val(m1[q][i]) + val(n1[q][i]) * val(n1[q][i]);
+      double fcn = fabs(val(s[q])) * sqrt(n6);
+      double tn = sqrt(val(tb[q][0]) * val(tb[q][0]) + val(tb[q][1]) * val(tb[q][1]) + val(tb[q][2]) * val(tb[q][2]));
+      stat[q] = mu * fcn >= kt * tn - TS_EPS;
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      if (stat[q]) {
+        for (int i = 0; i < 3; ++i) Fb[q][i] = Fb[q][i] - kt * tb[q][i];
+      } else {
+        T n6T = m1[q][0] * m1[q][0] + m1[q][1] * m1[q][1] + m1[q][2] * m1[q][2] + n1[q][0] * n1[q][0] + n1[q][1] * n1[q][1] + n1[q][2] * n1[q][2];
+        T fcT = dabs(s[q]) * dsqrt(n6T);
+        T tnT = dsqrt(tb[q][0] * tb[q][0] + tb[q][1] * tb[q][1] + tb[q][2] * tb[q][2]);
+        T sc = mu * fcT / tnT;
+        for (int i = 0; i < 3; ++i) Fb[q][i] = Fb[q][i] - sc * tb[q][i];
+      }
     }
   }
   // body 2 gets -Fb at the surface point xi2 = x - d e, body 1 gets +Fb at the pad point x
-  T xi2[3], tq[3];
-  for (int i = 0; i < 3; ++i) xi2[i] = x[i] - d * e[i];
-  cross3(xi2, Fb, tq);
-  for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
-  cross3(x, Fb, tq);
-  for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    T xi2[3];
+    for (int i = 0; i < 3; ++i) xi2[i] = x[q][i] - d[q] * e[q][i];
+    cross3(xi2, Fb[q], tq2[q]);
+    cross3(x[q], Fb[q], tq1[q]);
+  }
+}
+// the terms of one point added to the wrenches on body 1 / body 2 (the ONE place that defines the summation order)
+template <class T>
+HD void gp_point_accumulate(const T* tq2, const T* Fb, const T* tq1, T* w1, T* w2) {
+  for (int i = 0; i < 3; ++i) { w2[i] = w2[i] - tq2[i]; w2[3 + i] = w2[3 + i] - Fb[i]; }
+  for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq1[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
+}
+template <int NP, class T>
+HD void gp_point_force(const GpPair<T>& P, const double* const* xi1, const double* hs, double kn, double kt, double mu,
+                       double damp, T* w1, T* w2) {
+  T tq2[NP][3], Fb[NP][3], tq1[NP][3];
+  gp_point_terms<NP>(P, xi1, hs, kn, kt, mu, damp, tq2, Fb, tq1);
+#pragma unroll
+  for (int q = 0; q < NP; ++q) gp_point_accumulate(tq2[q], Fb[q], tq1[q], w1, w2);    // point by point, in order
 }
 
 // ---- cylinder SDF (DH/Body/BodyCylinder.cpp:88-139: radial distance only, no contact with the caps)
@@ -1019,6 +1063,131 @@ HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* 
   for (int i = 0; i < 3; ++i) { w1[i] = w1[i] + tq[i]; w1[3 + i] = w1[3 + i] + Fb[i]; }
 }
 
+// ---- block-cooperative evaluation of the active cuboid contact points (fwd_kernel of the variants that enable it)
+// In a lock-step block every round costs what its slowest warp costs, and a tile in contact runs the point force
+// ~9 times in a row while the other 27 tiles of the block wait at the next vote.  Here the tiles in contact PUBLISH
+// their pair kinematics (GpPair: 24 dual numbers + 24 frame values) and their list of active points in shared memory,
+// the active points of the whole block form one item list (tile by tile, points ascending), every tile of the block
+// evaluates the items dealt to it (item i of a batch -> tile i) with the publisher's kinematics and writes the
+// per-point terms (tq2, Fb, tq1) back, and each publisher sums the terms of its own points IN POINT ORDER with the
+// arithmetic of the serial evaluation -- same numbers, bit for bit, whoever computed them.
+// Block-wide barriers inside: every thread of the block calls this the same number of times (idle tiles with mine = false).
+template <bool COOP> struct CoopTag {};
+// TS_GP_ILP: active cuboid points evaluated side by side by one lane (gp_point_terms<NP>).  MEASURED on B200 (forward
+// call, B=4096, T=200): 1 -> 103.0 ms, 2 -> 131.2, 3 -> 142.4, 4 -> 153.0: the second chain does not fit in the 255
+// registers next to the pair kinematics and spills; one point at a time it is.
+#ifndef TS_GP_ILP
+#define TS_GP_ILP 1
+#endif
+#if defined(TS_COOP_GP) && defined(__CUDACC__)
+template <int LPE> struct CoopArea {
+  static const int NT = TS_BLOCK / LPE;           // tiles per block = items per batch
+  int cnt[NT];                                   // active points of each tile for the force in flight
+  int off[NT];                                   // first item of each publishing tile
+  unsigned char owner[NT * KT_MAXPW * 32];       // publishing tile of each item
+  unsigned short pts[NT][KT_MAXPW * 32];         // active point indices of each tile, ascending
+  double Pv[NT][48];                             // values: Q rr w1b v1b ph2 (24), then R1v p1v R2v p2v (24)
+  double Pt[NT][24][LPE];                        // tangents of the first 24, by component and lane
+  double Rv[NT][9];                              // per-item terms tq2, Fb, tq1: values ...
+  double Rt[NT][9][LPE];                         // ... and tangents by lane
+};
+template <class Tile, class T>
+__device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, const SceneView& S, GpPair<T>& P, const unsigned* act,
+                                               bool mine, int po, const double* hs, double kn, double kt, double mu,
+                                               double damp, T* w1, T* w2) {
+  typedef CoopArea<Tile::LPE> CA;
+  CA& C = *(CA*)tl.coop;
+  const int my = tl.tile_id, lane = tl.lane;
+  int cnt = 0;
+  if (mine) for (int w = 0; w < KT_MAXPW; ++w) cnt += __popc(act[w]);
+  TS_CPT0();
+  if (!tl.cta_or_unaligned(cnt > 0)) return false;              // nobody in this block touches: one barrier
+  if (lane == 0) C.cnt[my] = cnt;
+  tl.cta_sync_unaligned();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int t = 0; t < CA::NT; ++t) {
+    const int c = C.cnt[t];
+    if (t == my) off = total;
+    total += c;
+  }
+  if (cnt > 0) {
+    if (lane == 0) {
+      C.off[my] = off;
+      int r = 0;
+      for (int w = 0; w < KT_MAXPW; ++w) {
+        unsigned m = act[w];
+        while (m) { C.owner[off + r] = (unsigned char)my; C.pts[my][r++] = (unsigned short)(32 * w + ts_ffs(m)); m &= m - 1; }
+      }
+    }
+    const T* pt = P.Q;                            // Q rr w1b v1b ph2: 24 contiguous scalars
+    const double* pv = P.R1v;                     // R1v p1v R2v p2v: 24 contiguous doubles
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      C.Pt[my][i][lane] = tan_of(pt[i]);
+      if (lane == (i % Tile::LPE)) { C.Pv[my][i] = val(pt[i]); C.Pv[my][24 + i] = pv[i]; }
+    }
+  }
+  tl.cta_sync_unaligned();
+  TS_CPT(tl, 11);
+  TS_CPN(tl, 8, total); TS_CPN(tl, 9, 1);
+  for (int base = 0; base < total; base += CA::NT) {
+    TS_CPN(tl, 10, 1);
+    const int item = base + my;
+    if (item < total) {
+      const int src = C.owner[item];              // publisher of the item
+      const int k = C.pts[src][item - C.off[src]];
+      GpPair<T> Q;
+      T* qt = Q.Q;
+      double* qv = Q.R1v;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        qt[i] = Lift<T>::mk(C.Pv[src][i], C.Pt[src][i][lane]);
+        qv[i] = C.Pv[src][24 + i];
+      }
+      const double* xi1 = S.db + S.d_points + 3 * (po + k);
+      T tq2[1][3], Fb[1][3], tq1[1][3];
+      gp_point_terms<1>(Q, &xi1, hs, kn, kt, mu, damp, tq2, Fb, tq1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        C.Rt[my][i][lane] = tan_of(tq2[0][i]); C.Rt[my][3 + i][lane] = tan_of(Fb[0][i]); C.Rt[my][6 + i][lane] = tan_of(tq1[0][i]);
+        if (lane == 0) { C.Rv[my][i] = val(tq2[0][i]); C.Rv[my][3 + i] = val(Fb[0][i]); C.Rv[my][6 + i] = val(tq1[0][i]); }
+      }
+    }
+    TS_CPT(tl, 12);
+    tl.cta_sync_unaligned();
+    TS_CPT(tl, 13);
+    if (cnt > 0) {
+      const int lo = off > base ? off : base, hi = (off + cnt < base + CA::NT) ? off + cnt : base + CA::NT;
+      // (two items per pass: the loads of the second overlap the sums of the first; the order of the sums is unchanged)
+      int it = lo;
+      for (; it + 1 < hi; it += 2) {
+        const int r = it - base;
+        T a[9], b2[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { a[i] = Lift<T>::mk(C.Rv[r][i], C.Rt[r][i][lane]); b2[i] = Lift<T>::mk(C.Rv[r + 1][i], C.Rt[r + 1][i][lane]); }
+        gp_point_accumulate(a, a + 3, a + 6, w1, w2);
+        gp_point_accumulate(b2, b2 + 3, b2 + 6, w1, w2);
+      }
+      if (it < hi) {
+        const int r = it - base;
+        T a[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a[i] = Lift<T>::mk(C.Rv[r][i], C.Rt[r][i][lane]);
+        gp_point_accumulate(a, a + 3, a + 6, w1, w2);
+      }
+    }
+    TS_CPT(tl, 14);
+    tl.cta_sync_unaligned();
+    TS_CPT(tl, 13);
+  }
+  return cnt > 0;
+}
+#endif
+template <class Tile, class T>
+HD bool gp_points_coop(const Tile&, CoopTag<false>, const SceneView&, GpPair<T>&, const unsigned*, bool, int, const double*,
+                       double, double, double, double, T*, T*) { return false; }
+
 // sampled points of a general body vs a primitive SDF (cuboid or cylinder):
 // DH/Force/ForceGeneralPrimitiveContact.cpp:154-229, DH/Body/BodyCuboid.cpp:146-184, BodyCylinder.cpp:105-139,
 // detection d < 0: CollisionDetection.cpp:66-83.
@@ -1026,8 +1195,9 @@ HD void gp_point_force_cyl(const GpPair<T>& P, const double* xi1, const double* 
 // active points -- pair kinematics by shuffles, points dealt to the tiles of the warp, xor-tree reduction -- was
 // measured slower on B200 twice: 144 vs 125-140 ms, the pair structs end up in local memory; kept as
 // tools/experiments/warp_cooperative_contacts_v2.patch.)
+// idle: this tile has no evaluation of its own in flight; it only takes part in the cooperative point evaluation of its block
 template <class Tile, class WK>
-HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
+HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W, bool idle = false) {
   typedef typename WK::Scalar T;
   const int L = Tile::LPE;
   const double h2 = W.beta;
@@ -1049,7 +1219,7 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     body_frame_v(S, W, b2, P.R2v, P.p2v, phv);
     unsigned act[KT_MAXPW];
     for (int i = 0; i < KT_MAXPW; ++i) act[i] = 0u;
-    {
+    if (!idle) {
       // exact-safe culls on values: bounding spheres, then (cuboid) the bounding box of the point set against
       // the face planes of the box
       const double rr = c[4] + bd2[KB_RBOUND] + TS_CULL_MARGIN;
@@ -1124,11 +1294,12 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     unsigned any = 0u;
     for (int i = 0; i < KT_MAXPW; ++i) any |= act[i];
     TS_GPT(tl, 0);
-    if (!any) continue;
-    W.gp_any = 1;
+    const bool coop = Tile::COOP && !cyl;          // (block-uniform: a property of the force)
+    if (!any && !coop) continue;
     // the tile's own relative kinematics in the frame of body 2 (dual numbers)
     T R2[9], p2[3];
-    {
+    if (any) {
+      W.gp_any = 1;
       T R1[9], p1[3], ph1[6], dp[3];
       body_frame(S, W, b1, R1, p1, ph1);
       body_frame(S, W, b2, R2, p2, P.ph2);
@@ -1142,15 +1313,30 @@ HDN void gp_contacts(const Tile& tl, const SceneView& S, WK& W) {
     TS_GPT(tl, 1);
     T w1[6], w2[6];          // wrenches on body 1 / body 2, both in body-2 coordinates about its origin
     for (int i = 0; i < 6; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+    if (coop && gp_points_coop(tl, CoopTag<Tile::COOP>(), S, P, act, any != 0u, po, hs, kn, kt, mu, damp, w1, w2)) {
+      push_wrench(W, j1, R2, p2, w1, -h2);
+      push_wrench(W, j2, R2, p2, w2, -h2);
+      continue;
+    }
+    if (!any) continue;
+    const double* pend[TS_GP_ILP];           // active cuboid points waiting to be evaluated side by side
+    int npend = 0;
     for (int wd = 0; wd < KT_MAXPW; ++wd) {
       unsigned m = act[wd];
       while (m) {
         const int k = 32 * wd + ts_ffs(m);
         m &= m - 1;
-        if (cyl) gp_point_force_cyl(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2, sph, cap ? hs[1] : -1.0);
-        else gp_point_force(P, S.db + S.d_points + 3 * (po + k), hs, kn, kt, mu, damp, w1, w2);
+        const double* xi1 = S.db + S.d_points + 3 * (po + k);
+        if (cyl) gp_point_force_cyl(P, xi1, hs, kn, kt, mu, damp, w1, w2, sph, cap ? hs[1] : -1.0);
+        else {
+          pend[npend++] = xi1;
+          if (npend == TS_GP_ILP) { gp_point_force<TS_GP_ILP>(P, pend, hs, kn, kt, mu, damp, w1, w2); npend = 0; }
+        }
       }
     }
+#if TS_GP_ILP > 1
+    for (int i = 0; i < npend; ++i) gp_point_force<1>(P, pend + i, hs, kn, kt, mu, damp, w1, w2);
+#endif
     push_wrench(W, j1, R2, p2, w1, -h2);
     push_wrench(W, j2, R2, p2, w2, -h2);
     TS_GPT(tl, 3);
@@ -1270,28 +1456,33 @@ HDN void inward(const SceneView& S, WK& W, const In& in, const double* u, typena
 // beta = h^2 (DH/Simulation.cpp:1227-1235); the other integrators only change (qd, dl, beta): stage_inputs().
 template <class Tile, class WK, class In>
 HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* u, WK& W, typename WK::Scalar* g,
-                double beta) {
-  W.beta = beta;
-  W.gp_any = 0;
+                double beta, bool idle = false) {
+  // (idle: Tile::COOP only -- nothing of its own to evaluate, the tile helps the block with its contact points; the
+  // general-primitive phase has ONE call site so that the lanes of a warp run their shares of the points together)
+  const bool own = !(Tile::COOP && idle);
+  if (own) {
+    W.beta = beta;
+    W.gp_any = 0;
+  }
 #ifdef TS_PROFILE_GP      // slots 0, 1, 3 are re-used for the phases INSIDE gp_contacts (detect / pair setup / point forces)
-  kinematics(S, in, W, true);
-  ground_contacts(S, W);
-  { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
-  inward(S, W, in, u, g);
+  if (own) { kinematics(S, in, W, true); ground_contacts(S, W); }
+  { TS_TIC(tl); gp_contacts(tl, S, W, !own); TS_TOC(tl, 2); }
+  if (own) inward(S, W, in, u, g);
 #else
-  { TS_TIC(tl); kinematics(S, in, W, true); TS_TOC(tl, 0); }
-  { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
-  { TS_TIC(tl); gp_contacts(tl, S, W); TS_TOC(tl, 2); }
-  { TS_TIC(tl); inward(S, W, in, u, g); TS_TOC(tl, 3); }
+  if (own) { TS_TIC(tl); kinematics(S, in, W, true); TS_TOC(tl, 0); }
+  if (own) { TS_TIC(tl); ground_contacts(S, W); TS_TOC(tl, 1); }
+  { TS_TIC(tl); gp_contacts(tl, S, W, !own); TS_TOC(tl, 2); }
+  if (own) { TS_TIC(tl); inward(S, W, in, u, g); TS_TOC(tl, 3); }
 #endif
 }
 
 // ------------------------------------------------------------------ tile policies
 struct HostTile {
   static const int LPE = 1;
+  static const bool COOP = false;
   int lane;
 #ifdef TS_PROFILE
-  mutable long long acc[8];
+  mutable long long acc[16];
 #endif
   HD HostTile() : lane(0) {}
   HD double bcast(double v, int) const { return v; }
@@ -1480,7 +1671,7 @@ HD double norm_n(const double* v, int n) {
 // machine calls it from exactly ONE place, so the residual code exists once per kernel.
 template <class Tile, class WK>
 HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const double* x, int seed, int mode, WK& W,
-                     double (*col)[TS_MAXN]) {
+                     double (*col)[TS_MAXN], bool idle = false) {
   const int L = Tile::LPE;
   const int n = S.n;
   SeedIn in;
@@ -1495,19 +1686,22 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
   in.tq0 = (seed == 1) ? 1.0 : 0.0;
   in.tqd0 = (seed == 2) ? 1.0 : 0.0;
   tl.tile_sync();          // every lane of the tile is done with the previous evaluation and its bookkeeping
+  if (!(Tile::COOP && idle)) {
 #pragma unroll
-  for (int i = 0; i < TS_MAXN; ++i) {
-    const double xi = (i < n) ? x[i] : 0.0;
-    double xv = 0.0, xl = 0.0;
-    if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
-    ts.xq[i] = xi;
-    ts.xv[i] = xv;
-    ts.xl[i] = xl;
+    for (int i = 0; i < TS_MAXN; ++i) {
+      const double xi = (i < n) ? x[i] : 0.0;
+      double xv = 0.0, xl = 0.0;
+      if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
+      ts.xq[i] = xi;
+      ts.xv[i] = xv;
+      ts.xl[i] = xl;
+    }
   }
   for (int c = 0; c < TS_NC(L); ++c) {
     in.k = tl.lane + c * L;
     Dual gD[TS_MAXN];
-    eval_g(tl, S, in, ts.u, W, gD, sbeta);
+    eval_g(tl, S, in, ts.u, W, gD, sbeta, idle);
+    if (Tile::COOP && idle) continue;
 #pragma unroll
     for (int i = 0; i < TS_MAXN; ++i) {
       ts.g[i] = (i < n) ? gD[i].v : 0.0;
@@ -1686,9 +1880,9 @@ HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
 // step_eval is the evaluation (every tile of a warp runs it together, also tiles whose step is already
 // complete: the residual code votes and shuffles across the warp); step_post is the bookkeeping.
 template <class Tile, class WK>
-HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, WK& WD, double (*cole)[TS_MAXN]) {
+HD void step_eval(const Tile& tl, const SceneView& S, const StepVars& v, WK& WD, double (*cole)[TS_MAXN], bool idle = false) {
   TileState& ts = WD.state();
-  eval_columns(tl, S, ts, (v.phase == 1) ? ts.xn : ts.x, v.phase == 3 ? 1 : 0, v.mode, WD, cole);
+  eval_columns(tl, S, ts, (v.phase == 1) ? ts.xn : ts.x, v.phase == 3 ? 1 : 0, v.mode, WD, cole, idle);
 }
 
 template <class Tile, class WK>
@@ -1760,6 +1954,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         // order, that reduces ||g|| is then evaluated with its Jacobian by the normal path, which also
         // re-checks the acceptance.  Same accepted step length as the sequential search.
         bool found = false;
+        TS_CPT0();
         while (v.trial < S.max_ls) {
           const int left = S.max_ls - v.trial;
           const int nb = left < L ? left : L;
@@ -1781,6 +1976,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
           v.ls += nb;
           for (int i = 0; i < nb; ++i) v.alpha *= 0.5;
         }
+        TS_CPT(tl, 15);
         if (found) {
           for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
           return false;
@@ -2478,16 +2674,16 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
     step_begin(S, v, ts);
   }
   // Scheduling of the rounds (bit-identical results, only the pacing differs):
-  //  * TS_ROUNDS_PER_VOTE: the warps of a block meet at one block-wide vote per SUPER-round; between two votes a warp
-  //    runs up to that many evaluation rounds, but stops after a round in which one of its tiles had an active
-  //    general-primitive contact point.  A round in contact costs ~3x a contact-free one (the serial loop over the
-  //    active points): with one round per vote every warp of the block paid that price in every round; now the
-  //    contact-free warps run on while the warps in contact are in their point loop (a small loop that stays in the
-  //    instruction cache), and the block still streams through the large residual code together.
+  //  * TS_ROUNDS_PER_VOTE (default 1 = strict lock-step: one block-wide vote per evaluation round).  With K > 1 a warp
+  //    runs up to K rounds between two votes and stops after a round in which one of its tiles had an active
+  //    general-primitive contact point (a round in contact costs ~3x a contact-free one), so that contact-free warps
+  //    run on while the warps in contact are in their point loop.  MEASURED SLOWER on B200 (forward call, B=4096,
+  //    T=200: K=1 105.6 ms, K=2 172, K=3 141, K=4 143, K=6 164): as soon as the warps of an SM are at different places
+  //    of the 110 KB residual code, instruction fetch dominates -- the lock-step stays strict.
   //  * TS_TILE_STEPS: the tiles of a warp advance through the time steps independently (t is per tile): a tile whose
   //    step is complete starts its next step in the next round instead of idling until the slowest tile of the warp is done.
 #ifndef TS_ROUNDS_PER_VOTE
-#define TS_ROUNDS_PER_VOTE 3
+#define TS_ROUNDS_PER_VOTE 1
 #endif
 #ifndef TS_TILE_STEPS
 #define TS_TILE_STEPS 1
@@ -2497,18 +2693,23 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
 #pragma unroll 1
     for (int rep = 0; rep < TS_ROUNDS_PER_VOTE; ++rep) {      // (not unrolled: ONE copy of the residual code)
       bool heavy = false;
+      {
+        // ONE call site of the evaluation.  Block-cooperative kernels (Tile::COOP) run it in every tile of the block,
+        // every round: a tile without an evaluation of its own (idle) still joins the barriers of the cooperative
+        // contact-point phase and takes its share of the block's active points.
+        TS_TIC2(tl);
+        const bool run = t < a.T && !tile_done;
+        double cole[TS_NC(Tile::LPE)][TS_MAXN];
+        if (run || Tile::COOP) step_eval(tl, S, v, WD, cole, !run);
+        if (run) {
+          const long long es0 = (long long)t * B + env;
+          tile_done = step_post(tl, S, v, a.tape ? a.tape + es0 * S.ntape : (double*)0, WD, cole);
+          heavy = WD.gp_any != 0;
+        }
+        TS_TOC2(tl, 5);
+      }
       if (t < a.T) {                       // per tile with TS_TILE_STEPS, warp-uniform otherwise
         const long long es = (long long)t * B + env;
-        {
-          TS_TIC2(tl);
-          double cole[TS_NC(Tile::LPE)][TS_MAXN];
-          if (!tile_done) {
-            step_eval(tl, S, v, WD, cole);
-            tile_done = step_post(tl, S, v, a.tape ? a.tape + es * S.ntape : (double*)0, WD, cole);
-            heavy = WD.gp_any != 0;
-          }
-          TS_TOC2(tl, 5);
-        }
 #if TS_TILE_STEPS
         const bool finish = tile_done;
 #else

@@ -116,6 +116,8 @@ class Simulation:
         self._current_backward_step = 0
         self._carry: Optional[torch.Tensor] = None
         self._cache = []
+        self._q_hist: List[torch.Tensor] = []          # q trajectories since reset() (export_replay; Simulation::_q_his)
+        self._virtual = {}                             # poses of the render-only objects
 
     # ------------------------------------------------------------------ helpers
     def _t(self, x, width, name):
@@ -304,7 +306,13 @@ class Simulation:
         return None
 
     def update_virtual_object(self, name, data):
-        """Render-only objects (goal marker) do not enter the dynamics: accepted as a no-op."""
+        """Render-only objects (goal marker) do not enter the dynamics; the pose (pos, quat wxyz) is kept for
+        export_replay (DH/VirtualObject/VirtualObjectCuboid.cpp:13-30)."""
+        d = np.asarray(data, dtype=np.float64).reshape(-1)
+        if d.size >= 7:
+            self._virtual[name] = d[:7].copy()
+        elif d.size >= 3:
+            self._virtual[name] = np.concatenate([d[:3], [1.0, 0.0, 0.0, 0.0]])
         return None
 
     # ------------------------------------------------------------------ reset / caches (Simulation.cpp:999-1055)
@@ -321,6 +329,7 @@ class Simulation:
         self._nsteps = 0
         self._current_backward_step = 0
         self._carry = None
+        self._q_hist = []
         self._reset_done = True
 
     def clearBackwardCache(self):
@@ -355,11 +364,14 @@ class Simulation:
         trows = rows if tac_rows is None else tac_rows
         u = u.contiguous()
         fwd = self.core.forward(self._q, self._qd, u, T, grad=self._grad, var_rows=rows, tac_rows=trows,
-                                want_var=want_outputs, want_tactile=want_outputs, want_traj=want_outputs or self._grad,
+                                want_var=want_outputs, want_tactile=want_outputs,
+                                want_traj=want_outputs or self._grad or self.batch == 1,
                                 q_prev=self._q_prev, qd_prev=self._qd_prev, steps_done=self._nsteps)
         if self._grad:
             self._chunks.append(_Chunk(T, u, fwd, rows, self._nsteps))
             self._current_backward_step += T
+        if fwd.get("q_traj") is not None and (self.batch == 1 or self._grad):
+            self._q_hist.append(fwd["q_traj"])          # the compat face keeps the history like Simulation::_q_his
         self._nsteps += T
         return fwd if want_outputs else None
 
@@ -478,16 +490,18 @@ class Simulation:
     def replay(self):
         return None
 
-    def export_replay(self, path):
-        """Trajectory export for an offline viewer (the role of DH/Simulation.cpp export_replay): one text line
-        per recorded sim-step holding the reduced coordinates q (environment 0), preceded by a header line
-        `ndof_r num_steps h`.  Only grad-mode rollouts keep their q history on the device."""
-        rows = [c.fwd["q_traj"][:, 0].cpu().numpy() for c in self._chunks if c.fwd.get("q_traj") is not None]
-        qs = np.concatenate(rows, axis=0) if rows else np.zeros((0, self.ndof_r))
-        with open(path, "w") as f:
-            f.write(f"{self.ndof_r} {len(qs)} {self.options.h!r}\n")
-            for q in qs:
-                f.write(" ".join(repr(float(x)) for x in q) + "\n")
+    def export_replay(self, folder):
+        """``Simulation::export_replay`` (DH/Simulation.cpp:2037-2120): <folder>/meshes/<k>.obj and one <folder>/<i>.txt per
+        state of the q history since reset() (frame 0 = the initial state) holding the 4 x 4 world transforms of the
+        bodies, render-only objects, sensors and end-effectors -- the reference's text format, written by
+        ``tactilesimulation_b200.replay`` (host-side kinematics).  Environment 0 of a batch is exported."""
+        from . import replay
+        qs = [self._q_init[0:1].detach().cpu().numpy()] if self._reset_done else []
+        qs += [h[:, 0].detach().cpu().numpy() for h in self._q_hist]
+        qh = np.concatenate(qs, axis=0) if qs else np.zeros((0, self.ndof_r))
+        vp = [self._virtual.get(nm, self.scene.virtual_pose[i] if i < len(self.scene.virtual_pose) else np.array([0, 0, 0, 1.0, 0, 0, 0]))
+              for i, nm in enumerate(self.scene.virtual_names)]
+        return replay.export_replay(self.scene, qh, str(folder), virtual_pose=vp)
 
     def print_time_report(self):
         print("[tactilesimulation_b200] timing lives in CUDA events / ncu; see bench.py")

@@ -218,6 +218,7 @@ class Scene:
     end_effectors: List[dict] = field(default_factory=list)    # joint,pos
     sensors: List[TactileSensor] = field(default_factory=list)
     virtual_names: List[str] = field(default_factory=list)
+    virtual_pose: List[np.ndarray] = field(default_factory=list)   # host-only: (pos, quat wxyz) of each render-only object
     # host-only construction parameters (not in the blob): what the update_* calls of the reference need to redo a part
     # of the construction (DH/Robot.cpp:571-650).  Empty for scenes rebuilt from a blob.
     body_density: List[float] = field(default_factory=list)
@@ -695,12 +696,18 @@ def compile_scene(xml_path: str) -> Scene:
             jname = e.get("joint")
             if jname not in joint_map:
                 raise SceneError("Endeffector joint name error: " + str(jname))
+            # radius: rendering only (export_replay lists end-effectors with radius > 0), Simulation_Constructor.cpp:355-360
+            rad = _attr(e, root.find("default"), "endeffector", "radius")
             sc.end_effectors.append({"joint": joint_map[jname], "pos": _vec(e.get("pos")),
-                                     "name": e.get("name", "")})
+                                     "name": e.get("name", ""), "radius": _f32(rad) if rad is not None else _f32("0.1")})
     for vn in root:
         if vn.tag == "virtual":
             for e in vn:
                 sc.virtual_names.append(e.get("name", ""))
+                # render-only objects: pose (pos, quat wxyz) kept for export_replay (Simulation_Constructor.cpp:380-420)
+                pos = _vec(e.get("pos")) if e.get("pos") else np.zeros(3)
+                quat = _vec(e.get("quat")) if (e.tag == "cuboid" and e.get("quat")) else np.array([1.0, 0.0, 0.0, 0.0])
+                sc.virtual_pose.append(np.concatenate([pos, quat]))
     for s in sc.sensors:
         for k in s.candidates:
             if sc.shape[k] not in (SH_CUBOID, SH_CYLINDER, SH_SPHERE, SH_CAPSULE):

@@ -63,6 +63,7 @@ def episodic_case(xml, T, seed, push=True):
         s.reset(True)
     q, qd, var, tac = [], [], [], []
     ground, gp, mb, newton = [], [], [], []
+    probe.newton_counts()                        # (process-wide counters: drop what earlier cases left)
     for t in range(T):
         for s in (sim, probe):
             s.set_u(u[t])
@@ -149,6 +150,7 @@ def multi_case(xml, q0, u, seed):
         s.set_state_init(q0, np.zeros(n))
         s.reset(True)
     q, qd, var, tac, ground, gp, mb, newton = [], [], [], [], [], [], [], []
+    probe.newton_counts()                        # (process-wide counters: drop what earlier cases left)
     for t in range(T):
         for s in (sim, probe):
             s.set_u(u[t])
@@ -192,10 +194,10 @@ def multi_case(xml, q0, u, seed):
                 newton=np.array(newton, dtype=np.int32))
 
 
-def dclaw_case(T, seed):
+def dclaw_case(T, seed, xml_name="dclaw_torque_control.xml"):
     """DClaw rotate-cap (R/envs/assets/dclaw_rotate/dclaw_torque_control.xml, BASELINE configs[3]): initial pose of
     R/envs/dclaw_rotate_env.py:76-77, actions U(-1,1)^9 with the middle joints biased to close on the cap."""
-    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", xml_name)
     q0 = np.zeros(10)
     q0[[1, 4, 7]] = -0.5
     q0[[2, 5, 8]] = 0.8
@@ -205,12 +207,12 @@ def dclaw_case(T, seed):
     return multi_case(xml, q0, u, seed)
 
 
-def insertion_case(T, seed):
+def insertion_case(T, seed, xml_name="tactile_insertion.xml"):
     """TactileInsertion (R/envs/assets/tactile_insertion/tactile_insertion.xml, BASELINE configs[4]): position-controlled
     gripper base (translational + revolute), force-controlled fingers, free3d-euler box in a hole of four cuboids,
     two 13x10 pads.  Grasp as in R/envs/tactile_insertion_env.py:126-164 (fingers ramped closed), then the base is
     driven sideways / rotated / down so that the box meets the hole walls."""
-    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_insertion", "tactile_insertion.xml")
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_insertion", xml_name)
     q0 = np.zeros(12)
     q0[2] = 0.2
     q0[4] = q0[5] = -0.03
@@ -434,7 +436,7 @@ def randomized_case():
     the tests apply the same updates through tactilesimulation_b200.scene.update_* and compare the rollouts."""
     out = {}
     # ---- DClaw: cap radius / damping / location
-    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", xml_name)
     sim = redmax_py.Simulation(xml)
     sc = compile_scene(xml)
     upd = dict(damping=0.0015, size=np.array([0.03, 0.052]), ee=np.array([0.052, 0.0, 0.0]), loc=np.array([0.003, -0.004, 0.075]))
@@ -673,6 +675,9 @@ def main():
         "dclaw_episodic_s0": lambda: dclaw_case(40, 0),
         "insertion_episodic_s0": lambda: insertion_case(60, 0),
         "stable_grasp_episodic_s0": lambda: stable_grasp_case(50, 0),
+        # synthetic sensor variants named by BASELINE.json configs[3] / [4] (oracle/build_ref.sh writes the XML files)
+        "dclaw8x6_episodic_s0": lambda: dclaw_case(40, 0, "dclaw_torque_control_8x6.xml"),
+        "insertion20x20_episodic_s0": lambda: insertion_case(60, 0, "tactile_insertion_20x20.xml"),
         "rollingball_bdf2_s0": rolling_ball_case,
         "pusher13x10_integrators_s0": lambda: integrators_case(40, 0),
         "spherical_euler_bdf1_s0": lambda: spherical_euler_case(60, 0),

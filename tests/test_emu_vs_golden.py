@@ -101,12 +101,14 @@ def test_emulated_matches_oracle_on_fresh_seed():
     assert rel_err(bw["df_dqdot0"][0], ref["df_dqdot0"]) <= 1e-6
 
 
-def test_emulated_dclaw_matches_reference():
+@pytest.mark.parametrize("name", ["dclaw_episodic_s0", "dclaw8x6_episodic_s0"])
+def test_emulated_dclaw_matches_reference(name):
     """DClaw rotate-cap (BASELINE configs[3], the reference's own asset): 10 reduced dofs (16-dof kernel variant),
-    abstract bodies with sampled contact points, cylinder SDF (cap), three abstract 302-marker sensors."""
+    abstract bodies with sampled contact points, cylinder SDF (cap), three abstract 302-marker sensors; and the
+    synthetic 3 x (8x6) marker variant BASELINE.json names (oracle/build_ref.sh)."""
     from tests.blob_scene import scene_from_blob
     from tests.multi_force import expected_words
-    g = np.load(os.path.join(GOLDEN, "dclaw_episodic_s0.npz"))
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
     sc = scene_from_blob(g["ibuf"], g["dbuf"])
     T = g["u"].shape[0]
     out = emu_lib.forward(g["ibuf"], g["dbuf"], g["q0"], g["qd0"], g["u"][:, None, :], grad=True)
@@ -126,7 +128,7 @@ def test_emulated_dclaw_matches_reference():
     assert rel_err(bw["df_dqdot0"][0], g["df_dqdot0"]) <= 1e-6
 
 
-@pytest.mark.parametrize("name", ["insertion_episodic_s0", "stable_grasp_episodic_s0"])
+@pytest.mark.parametrize("name", ["insertion_episodic_s0", "stable_grasp_episodic_s0", "insertion20x20_episodic_s0"])
 def test_emulated_insertion_and_stable_grasp_match_reference(name):
     """TactileInsertion (BASELINE configs[4], the reference's own asset): 12 reduced dofs, position-controlled base
     (PD on the previous state: extra adjoint terms), free3d-euler box, prismatic fingers, ten general-primitive

@@ -150,6 +150,8 @@ def test_batched_line_search_equals_sequential_search():
 
 
 MULTI = {"dclaw_episodic_s0": (10, 90, 9, 12, 2718), "insertion_episodic_s0": (12, 78, 6, 0, 780),
+         "dclaw8x6_episodic_s0": (10, 90, 9, 12, 432),         # synthetic 3 x (8x6) pads of BASELINE configs[3]
+         "insertion20x20_episodic_s0": (12, 78, 6, 0, 2400),   # synthetic 2 x (20x20) pads of BASELINE configs[4]
          "stable_grasp_episodic_s0": (12, 126, 6, 0, 780),
          "spherical_euler_bdf1_s0": (6, 12, 6, 3, 48),        # our own two-link arm on spherical-euler joints
          "free2d_plate_bdf1_s0": (4, 12, 4, 3, 36)}           # our own plate on a free2d joint carrying a revolute arm

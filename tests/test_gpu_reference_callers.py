@@ -53,9 +53,9 @@ def test_unmodified_push_env_matches_itself_on_the_reference_module():
 def test_unmodified_gd_epoch_matches_itself_on_the_reference_module(tmp_path):
     _need_ref()
     rew_ref, len_ref, gd_ref = rc.run_gd_epoch(rc.load(rc.reference_module()), str(tmp_path / "ref"))
-    g_ref = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_ref.actor.parameters()])
+    g_ref = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_ref.actor.parameters() if p.grad is not None])
     rew_new, len_new, gd_new = rc.run_gd_epoch(_dropin(), str(tmp_path / "new"))
-    g_new = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_new.actor.parameters()])
+    g_new = np.concatenate([p.grad.reshape(-1).numpy() for p in gd_new.actor.parameters() if p.grad is not None])
     assert len_new == len_ref == [100]
     assert np.allclose(rew_new, rew_ref, rtol=1e-8)
     assert rel_err(g_new, g_ref) <= 1e-6 and np.abs(g_ref).max() > 0

@@ -11,7 +11,7 @@ sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=8)
 dev = sim.device
 B, T = int(os.environ.get('PB', 4096)), int(os.environ.get('PT', 50))
 nthreads = ((B * 8 + 223) // 224) * 224
-prof = torch.zeros((nthreads, 8), dtype=torch.int64, device=dev)
+prof = torch.zeros((nthreads, 16), dtype=torch.int64, device=dev)
 sim.lib.tsim_debug_set_prof_v8(ctypes.c_void_p(prof.data_ptr()))
 q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
 ut = torch.tensor(u, device=dev)
@@ -19,7 +19,7 @@ for rep in range(3):
     q, qd = torch.tensor(q0, device=dev), torch.tensor(qd0, device=dev)
     out = sim.forward(q, qd, ut, T, grad=True)
     torch.cuda.synchronize()
-p = prof.cpu().numpy().reshape(-1, 28, 8, 8)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
+p = prof.cpu().numpy().reshape(-1, 28, 8, 16)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
 names = ["kinematics+dyn", "ground", "gp", "inward", "vote wait", "step_round total", "epilogue", "kernel total"]
 tot = p[:, :, 7].astype(float)
 bt = tot.max(axis=1)
@@ -31,3 +31,12 @@ for i, nm in enumerate(names):
 # slowest block
 b = int(tot.mean(axis=1).argmax())
 print("slowest block", b, {nm: float(p[b, :, i].mean()) for i, nm in enumerate(names)})
+
+# cooperative contact-point phase (slots 8..14)
+if p[:, :, 9].sum() > 0:
+    ph = p[:, 0, 9].astype(float)          # phases with items, per block (tile 0)
+    print("coop: phases with items per block mean %.0f, items per phase %.1f, batches per phase %.2f" % (
+        ph.mean(), p[:, 0, 8].sum() / ph.sum(), p[:, 0, 10].sum() / ph.sum()))
+    for i, nm in ((11, "coop publish"), (12, "coop compute"), (13, "coop barrier wait"), (14, "coop accumulate"), (15, "batched line search")):
+        v = p[:, :, i].astype(float)
+        print(f"{nm:18s} mean {v.mean():.4g} ({100 * v.mean() / tot.mean():5.1f}% of kernel)  per phase {v.mean() / ph.mean():.0f} cycles")
