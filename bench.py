@@ -267,8 +267,11 @@ def _ref_stepsim_worker(args):
     """One process: E episodes of the UNMODIFIED TactilePushEnv + StepSimFunction (the gd.py shape: 100 gym steps x
     frame_skip 5, loss = -sum reward, loss.backward()) on the reference module.  Returns (gym-steps, seconds)."""
     seeds, steps = args
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     from tests import ref_callers as rc
     import torch
+    torch.set_num_threads(1)
     ns = rc.load(rc.reference_module())
     env = ns.gym.make("TactilePush-v1", use_torch=True, gradient=True, observation_type="tactile_flatten")
     t0 = time.perf_counter()
@@ -696,7 +699,9 @@ def run_stepsim(a):
     if world == 1 and ref_available() and not a.no_cpu_baseline:
         import multiprocessing as mp
         cores = host_cores()
-        with mp.get_context("fork").Pool(cores) as pool:
+        # (spawn: the workers run torch autograd, which cannot be used in a fork of a process that already has)
+        with mp.get_context("spawn").Pool(cores) as pool:
+            pool.map(_ref_stepsim_worker, [([900 + c], 2) for c in range(cores)])      # imports + first call
             t0 = time.perf_counter()
             res = pool.map(_ref_stepsim_worker, [([c], G) for c in range(cores)])
             w = time.perf_counter() - t0

@@ -1932,20 +1932,36 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     return true;
   }
   bool finished = false, fresh = (v.phase == 2);   // fresh: (ge, cole) belong to the final x
+  // eager: the Newton iteration below has just set up a search and this step is struggling (TS_LS_EAGER iterations or
+  // more): the search starts with the batched evaluation of the step lengths instead of two sequential trials -- the
+  // same accepted step length and evaluation counts, one or two rounds fewer per iteration of the steps that run into
+  // hundreds of iterations (and decide the duration of a kernel whose blocks end with their slowest environment).
+#ifndef TS_LS_EAGER
+#define TS_LS_EAGER 6
+#endif
+  bool eager = false;
+  for (;;) {
   if (v.phase == 1) {
-    ++v.ls;
-    double gnn = norm_n(ge, n);
-    if (gnn < v.gnorm) {                           // trial accepted: it is the next iterate
+    double gnn = 0.0;
+    bool accepted = false;
+    if (!eager) {
+      ++v.ls;
+      gnn = norm_n(ge, n);
+      accepted = gnn < v.gnorm;
+    }
+    if (accepted) {                                // trial accepted: it is the next iterate
       for (int i = 0; i < n; ++i) ts.x[i] = ts.xn[i];
       v.fail_strike = 0;
       fresh = true;
       if (gnn < S.tol) { v.converged = true; finished = true; }
     } else {
-      ++v.trial;
-      v.alpha *= 0.5;
-      if (v.trial < S.max_ls && !(L >= TS_MAXN && v.batch_ls && v.trial >= 2)) {
-        for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
-        return false;
+      if (!eager) {
+        ++v.trial;
+        v.alpha *= 0.5;
+        if (v.trial < S.max_ls && !(L >= TS_MAXN && v.batch_ls && v.trial >= 2)) {
+          for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
+          return false;
+        }
       }
       if (v.trial < S.max_ls) {
         // Two trials already failed: a struggling line search (up to max_ls = 20 trials per iteration,
@@ -1978,6 +1994,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         }
         TS_CPT(tl, 15);
         if (found) {
+          tl.tile_sync();
           for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
           return false;
         }
@@ -1990,6 +2007,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         for (int i = 0; i < TS_MAXN; ++i) xs[i] = (i < n) ? ts.x[i] + v.alpha * ts.dx[i] : 0.0;
         tl.tile_sync();
         for (int i = 0; i < TS_MAXN; ++i) ts.x[i] = xs[i];
+        fresh = false;                         // x moved: (ge, cole) are no longer those of x
         if (gnn < S.tol) { v.converged = true; finished = true; }
         else if (v.iters >= max_newton) finished = true;
         else { v.phase = 0; return false; }
@@ -2035,8 +2053,12 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   v.trial = 0;
   for (int i = 0; i < TS_MAXN; ++i) { ts.dx[i] = dx[i]; ts.xn[i] = (i < n) ? ts.x[i] + dx[i] : 0.0; }
   v.phase = 1;
-  return false;
+  if (!(TS_LS_EAGER > 0 && L >= TS_MAXN && v.batch_ls && v.iters >= TS_LS_EAGER)) return false;
+  tl.tile_sync();                      // dx is in place for the value-only trials of every lane
+  eager = true;
+  }   // for (;;): second pass = the search of a struggling step, batched from its first trial
 }
+
 
 // ------------------------------------------------------------------ readouts at a state
 // end-effector positions (DH/EndEffector/EndEffector.cpp:31-36)
