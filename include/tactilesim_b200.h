@@ -79,6 +79,18 @@ enum { TSIM_OPT_LS_BATCH = 0, TSIM_OPT_MAX_NEWTON = 1, TSIM_OPT_VJP_PASS = 2, TS
        TSIM_N_OPTS };
 int tsim_scene_set_option(tsim_scene* scene, int key, int value);
 
+/* Per-environment parameters (domain randomisation: what the reference does by calling update_joint_damping /
+ * update_body_size / update_endeffector_position / update_joint_location / update_body_density / update_contact_parameters /
+ * update_tactile_parameters on each environment's own Simulation before reset(): DH/python_interface.cpp:181-211,
+ * DH/Robot.cpp:571-650; R/envs/dclaw_rotate_env.py:173-178, stable_grasp_env.py:122-128, tactile_insertion_env.py:254-275).
+ *   ibufs [B][n_int], dbufs [B][n_dbl]  (HOST) B packed scenes of the handle's topology, one per environment of the batch
+ * The scenes are lowered one by one; counts and connectivity must equal the handle's (values may differ).  Afterwards
+ * tsim_forward / tsim_readout / tsim_backward calls with this B read every environment's own parameters (joint damping,
+ * contact and tactile coefficients, body sizes / inertias, joint locations, end-effector positions ...); other batch
+ * sizes are refused.  B = 0 returns to one parameter set for all environments. */
+int tsim_scene_set_env_scenes(tsim_scene* scene, int32_t B, const int32_t* ibufs, int64_t n_int, const double* dbufs,
+                              int64_t n_dbl);
+
 /* Advances B environments by T implicit (BDF1/Newton) steps.
  *   q, qd        [B,n]        state, in/out
  *   u            u[t*u_step_stride + env*nu + i]; u_step_stride = 0 holds one action for all T steps

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_b200.so")
 
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
+           "tsim_scene_set_env_scenes",
            "tsim_forward", "tsim_forward_multistep", "tsim_scene_kernel_times", "tsim_readout", "tsim_backward",
            "tsim_debug_fp64_peak", "tsim_debug_last_error"]
 KERNELS = ("fwd_kernel", "tape_kernel", "tac_kernel", "vjp_kernel", "bwd_kernel")
@@ -40,6 +41,7 @@ def load():
     lib.tsim_scene_sizes.argtypes = [vp, vp]
     lib.tsim_scene_set_lanes.argtypes = [vp, ctypes.c_int]
     lib.tsim_scene_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.tsim_scene_set_env_scenes.argtypes = [vp, i32, vp, i64, vp, i64]
     lib.tsim_forward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_forward_multistep.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_scene_kernel_times.argtypes = [vp, vp]

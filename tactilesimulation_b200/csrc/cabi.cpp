@@ -19,6 +19,7 @@
   int tsim_scene_sizes_v##V(const void*, int32_t*);                                                                   \
   int tsim_scene_set_lanes_v##V(void*, int);                                                                          \
   int tsim_scene_set_option_v##V(void*, int, int);                                                                    \
+  int tsim_scene_set_env_scenes_v##V(void*, int32_t, const int32_t*, int64_t, const double*, int64_t);                \
   int tsim_forward_multistep_v##V(const void*, int32_t, int32_t, double*, double*, double*, double*, int32_t,        \
                                   const double*, int64_t, double*, double*, double*, const int32_t*, double*,        \
                                   const int32_t*, double*, int32_t*, uint32_t*, int32_t*, void*);                     \
@@ -104,6 +105,13 @@ int tsim_scene_set_option(tsim_scene* s, int key, int value) {
   if (!s) return own_fail("tsim_scene_set_option: null scene");
   return DISPATCH(s, tsim_scene_set_option_v8(s->inner, key, value), tsim_scene_set_option_v16(s->inner, key, value),
                   tsim_scene_set_option_v17(s->inner, key, value));
+}
+
+int tsim_scene_set_env_scenes(tsim_scene* s, int32_t B, const int32_t* ibufs, int64_t n_int, const double* dbufs, int64_t n_dbl) {
+  if (!s) return own_fail("tsim_scene_set_env_scenes: null scene");
+  return DISPATCH(s, tsim_scene_set_env_scenes_v8(s->inner, B, ibufs, n_int, dbufs, n_dbl),
+                  tsim_scene_set_env_scenes_v16(s->inner, B, ibufs, n_int, dbufs, n_dbl),
+                  tsim_scene_set_env_scenes_v17(s->inner, B, ibufs, n_int, dbufs, n_dbl));
 }
 
 int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q, double* qd, double* q_prev, double* qd_prev,

@@ -46,6 +46,7 @@
 #define tsim_scene_sizes TSV(tsim_scene_sizes)
 #define tsim_scene_set_lanes TSV(tsim_scene_set_lanes)
 #define tsim_scene_set_option TSV(tsim_scene_set_option)
+#define tsim_scene_set_env_scenes TSV(tsim_scene_set_env_scenes)
 #define tsim_forward TSV(tsim_forward)
 #define tsim_forward_multistep TSV(tsim_forward_multistep)
 #define tsim_readout TSV(tsim_readout)
@@ -255,13 +256,23 @@ template <int LPE> __host__ __device__ inline size_t coop_bytes() { return TS_CO
 template <int LPE> __host__ __device__ inline size_t coop_bytes() { return 0; }
 #endif
 
-template <int LPE>
+// PE (per-environment parameters, tsim_scene_set_env_scenes): every environment has its own lowered double table in
+// global memory (read through L1); the tile works on a private copy of the scene view whose table pointer is its
+// environment's.  The integer tables (topology) and the marker table are the batch's.  Separate instantiations: the
+// broadcast kernels keep the table in shared memory and pay nothing.
+#define TS_PE_VIEW(ENV)                                                                   \
+  SceneView Sl;                                                                          \
+  const SceneView* Sp = &S;                                                              \
+  if (PE) { Sl = S; Sl.db = a.env_db + (long long)(ENV) * a.env_stride; Sp = &Sl; }
+
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
-  DevTile<LPE, TS_COOP_FOR(LPE)> tl = make_tile<LPE, TS_COOP_FOR(LPE)>();
+  TS_PE_VIEW(env < a.B ? env : a.B - 1)
+  DevTile<LPE, TS_COOP_FOR(LPE) && !PE> tl = make_tile<LPE, TS_COOP_FOR(LPE) && !PE>();
   WorkSplit WD;
   bind_work<LPE>(WD, S, ni, nd, smem);
   // the cooperative area follows the tile regions
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
   for (int i = 0; i < 16; ++i) tl.acc[i] = 0;
   const long long t_begin = clock64();
 #endif
-  env_forward(tl, S, a, env, WD);     // tiles past the batch stay in the block-wide votes
+  env_forward(tl, *Sp, a, env, WD);   // tiles past the batch stay in the block-wide votes
 #ifdef TS_PROFILE
   tl.acc[7] = clock64() - t_begin;
   if (g_prof) for (int i = 0; i < 16; ++i) g_prof[(long long)(blockIdx.x * blockDim.x + threadIdx.x) * 16 + i] = tl.acc[i];
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
 
 // Tactile fields of all T x B env-steps of a forward call (env_tactile), one tile per env-step, env-steps drawn from a
 // counter like in vjp_kernel.
-template <int LPE>
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) tac_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
@@ -295,14 +306,17 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) tac_kernel(const int* i
     base = __shfl_sync(0xffffffffu, base, 0);
     if ((long long)base >= items) break;
     const long long item = (long long)base + (threadIdx.x & 31) / LPE;
-    if (item < items) env_tactile(tl, S, a, item, WD);
+    if (item < items) {
+      TS_PE_VIEW(item % a.B)
+      env_tactile(tl, *Sp, a, item, WD);
+    }
     __syncwarp();
   }
 }
 
 // (the adjoint exists for BDF1 scenes; tsim_forward / tsim_backward refuse a tape for the other integrators)
 // G0 / G1 / gain blocks of the tape for all T x B env-steps of a forward call (env_tape), env-steps drawn from a counter.
-template <int LPE>
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tape_kernel(const int* ib, int ni, const double* db, int nd, FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
@@ -322,21 +336,26 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) tape_kernel(const int* ib, i
     const unsigned base = sbase;
     if ((long long)base >= items) break;
     const long long slot = (long long)base + threadIdx.x / LPE;
-    if (slot < items) env_tape(tl, S, a, a.tape_order ? (long long)a.tape_order[slot] : slot, WD);
+    if (slot < items) {
+      const long long item = a.tape_order ? (long long)a.tape_order[slot] : slot;
+      TS_PE_VIEW(item % a.B)
+      env_tape(tl, *Sp, a, item, WD);
+    }
   }
 }
 
-template <int LPE>
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= a.B) return;
+  TS_PE_VIEW(env)
   DevTile<LPE> tl = make_tile<LPE>();
   WorkSplit WD;
   bind_work<LPE>(WD, S, ni, nd, smem);
-  env_backward(tl, S, a, env, WD);
+  env_backward(tl, *Sp, a, env, WD);
 }
 
 // Readout pull-backs of all T x B env-steps (vjp_terms), one tile per env-step.  The work per env-step depends on
@@ -344,7 +363,7 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) bwd_kernel(const int* ib, in
 // consecutive environments of one step, whose loads coalesce) instead of owning a fixed share.
 // Two launches: phase 0 takes every env-step, finishes those whose pads nothing can reach (kinematics + variables
 // only) and lists the others; phase 1 takes the listed ones -- so the tiles of a warp run work of the same kind.
-template <int LPE>
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) vjp_kernel(const int* ib, int ni, const double* db, int nd, BwdArgs a,
                                                                int phase) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -363,22 +382,25 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_PASS_BPS) vjp_kernel(const int* i
     const long long slot = (long long)base + (threadIdx.x & 31) / LPE;
     if (slot < items) {
       const long long item = phase ? (long long)a.vjp_list[slot] : slot;
-      const bool deferred = env_vjp(tl, S, a, item, WD, phase == 0);
+      TS_PE_VIEW(item % a.B)
+      const bool deferred = env_vjp(tl, *Sp, a, item, WD, phase == 0);
       if (deferred && tl.lane == 0) a.vjp_list[atomicAdd(a.work_counter + 2, 1u)] = (int)item;
     }
     __syncwarp();
   }
 }
 
-template <int LPE>
+struct EnvTables { const double* env_db; long long env_stride; };
+template <int LPE, bool PE>
 __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni, const double* db, int nd, int B,
                                                           const double* q, const double* qd, double* var_out,
-                                                          double* tac_out, int* marker_body, unsigned* cmask) {
+                                                          double* tac_out, int* marker_body, unsigned* cmask, EnvTables a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SceneView S;
   stage_scene(S, ib, ni, db, nd, smem);
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
   if (env >= B) return;
+  TS_PE_VIEW(env)
   DevTile<LPE> tl = make_tile<LPE>();
   Work<double> wb;
   wb.beta = 0.0;
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(TS_BLOCK) readout_kernel(const int* ib, int ni
     ql[i] = (i < S.n) ? q[(long long)env * S.n + i] : 0.0;
     qdl[i] = (i < S.n) ? qd[(long long)env * S.n + i] : 0.0;
   }
-  env_readout(tl, S, ql, qdl, var_out ? var_out + (long long)env * 3 * S.nee : (double*)0,
+  env_readout(tl, *Sp, ql, qdl, var_out ? var_out + (long long)env * 3 * S.nee : (double*)0,
               tac_out ? tac_out + (long long)env * 3 * S.nmark : (double*)0,
               marker_body ? marker_body + (long long)env * S.nmark : (int*)0,
               cmask ? cmask + (long long)env * S.cmw : (unsigned*)0, wb);
@@ -403,6 +425,10 @@ struct tsim_scene {
   int nmj;                 // moving joints of the lowered scene
   int opts[TSIM_N_OPTS];
   int sizes[TSIM_N_SIZES];
+  // per-environment parameters (tsim_scene_set_env_scenes): lowered double tables [env_B][nd] on the device, or null
+  double* d_env_db;
+  int env_B;
+  std::vector<int> base_ib;          // lowered integer tables of the handle: every environment must lower to the same
   // events around the kernels of the last tsim_forward / tsim_backward call (tsim_scene_kernel_times)
   cudaEvent_t ev[7];
   mutable int ran[TSIM_N_KERNELS];
@@ -434,6 +460,28 @@ static int prep(K kern, size_t smem, int bps = TS_BPS) {
   return 0;
 }
 
+// Launch KERN<lanes, PE> with the handle's lanes per environment; the per-environment-parameter instantiation exists for
+// the variant's own lane count only (TS_MAXN lanes: one per reduced coordinate).
+#if TS_MAXN <= 8
+#define TS_LAUNCH_LANES8(KERN, GRID, SMEM8, BPS, ...)                                                        \
+  if (s->lanes == 8) { if (prep(KERN<8, false>, SMEM8, BPS)) return 1; KERN<8, false><<<GRID, TS_BLOCK, SMEM8, st>>>(__VA_ARGS__); } else
+#else
+#define TS_LAUNCH_LANES8(KERN, GRID, SMEM8, BPS, ...)
+#endif
+#define TS_LAUNCH(KERN, GRID, SMEM, SMEM8, BPS, ...)                                                         \
+  do {                                                                                                       \
+    if (pe) { if (prep(KERN<TS_MAXN, true>, SMEM, BPS)) return 1; KERN<TS_MAXN, true><<<GRID, TS_BLOCK, SMEM, st>>>(__VA_ARGS__); } \
+    else TS_LAUNCH_LANES8(KERN, GRID, SMEM8, BPS, __VA_ARGS__)                                               \
+    if (s->lanes == 16) { if (prep(KERN<16, false>, SMEM, BPS)) return 1; KERN<16, false><<<GRID, TS_BLOCK, SMEM, st>>>(__VA_ARGS__); } \
+    else { if (prep(KERN<32, false>, SMEM, BPS)) return 1; KERN<32, false><<<GRID, TS_BLOCK, SMEM, st>>>(__VA_ARGS__); } \
+    CK(cudaGetLastError());                                                                                  \
+  } while (0)
+// per-environment tables in use for a call of batch B?  (they must have been set for exactly this batch)
+#define TS_PE_CHECK(NAME)                                                                                    \
+  const bool pe = s->d_env_db != 0;                                                                          \
+  if (pe && B != s->env_B) return fail(NAME ": the handle holds per-environment parameters for another batch size"); \
+  if (pe && s->lanes != TS_MAXN) return fail(NAME ": per-environment parameters need the default lanes per environment");
+
 extern "C" {
 
 #ifdef TS_PROFILE
@@ -459,6 +507,9 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->nd = kt.ib[KI_D_MARKERS];       // doubles staged in shared memory: everything before the marker table
   s->lanes = TS_MAXN;        // one lane per reduced coordinate
   s->nmj = kt.ib[KI_NMJ];
+  s->d_env_db = 0;
+  s->env_B = 0;
+  s->base_ib = kt.ib;
   for (int i = 0; i < 7; ++i) CK(cudaEventCreate(&s->ev[i]));
   for (int i = 0; i < TSIM_N_KERNELS; ++i) s->ran[i] = 0;
   s->opts[TSIM_OPT_LS_BATCH] = 1;
@@ -498,6 +549,7 @@ void tsim_scene_destroy(tsim_scene* s) {
   cudaSetDevice(s->device);
   cudaFree(s->d_ib);
   cudaFree(s->d_db);
+  if (s->d_env_db) cudaFree(s->d_env_db);
   for (int i = 0; i < 7; ++i) cudaEventDestroy(s->ev[i]);
   delete s;
 }
@@ -521,6 +573,31 @@ int tsim_scene_set_option(tsim_scene* s, int key, int value) {
   if (!s) return fail("tsim_scene_set_option: null scene");
   if (key < 0 || key >= TSIM_N_OPTS) return fail("tsim_scene_set_option: unknown option");
   s->opts[key] = value;
+  return 0;
+}
+
+// Per-environment parameters: B packed scenes of the handle's topology (the host edits a copy of the scene per
+// environment: tactilesimulation_b200.scene.update_*), lowered here one by one; the integer tables must come out
+// identical to the handle's, the double tables before the marker table are uploaded as [B][nd].  B = 0 drops them.
+int tsim_scene_set_env_scenes(tsim_scene* s, int32_t B, const int32_t* ibufs, int64_t n_int, const double* dbufs, int64_t n_dbl) {
+  if (!s) return fail("tsim_scene_set_env_scenes: null scene");
+  CK(cudaSetDevice(s->device));
+  if (s->d_env_db) { CK(cudaDeviceSynchronize()); CK(cudaFree(s->d_env_db)); s->d_env_db = 0; s->env_B = 0; }
+  if (B <= 0) return 0;
+  if (!ibufs || !dbufs) return fail("tsim_scene_set_env_scenes: null argument");
+  std::vector<double> tables((size_t)B * s->nd);
+  for (int e = 0; e < B; ++e) {
+    KernelTables kt;
+    const std::string err = lower_scene(ibufs + (size_t)e * n_int, n_int, dbufs + (size_t)e * n_dbl, n_dbl, kt);
+    if (!err.empty()) return fail("tsim_scene_set_env_scenes: environment " + std::to_string(e) + ": " + err);
+    if (kt.ib != s->base_ib || (int)kt.db.size() != s->nd_all)
+      return fail("tsim_scene_set_env_scenes: environment " + std::to_string(e) +
+                  " does not have the topology of the handle (per-environment parameters may change values, not counts)");
+    memcpy(tables.data() + (size_t)e * s->nd, kt.db.data(), sizeof(double) * s->nd);
+  }
+  CK(cudaMalloc(&s->d_env_db, sizeof(double) * tables.size()));
+  CK(cudaMemcpy(s->d_env_db, tables.data(), sizeof(double) * tables.size(), cudaMemcpyHostToDevice));
+  s->env_B = B;
   return 0;
 }
 
@@ -548,6 +625,8 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   a.max_newton = s->opts[TSIM_OPT_MAX_NEWTON];
   a.q_prev = q_prev; a.qd_prev = qd_prev; a.steps_done = steps_done;
   a.defer_tac = 0; a.tac_prezeroed = 0; a.work_counter = 0;
+  TS_PE_CHECK("tsim_forward")
+  a.env_db = s->d_env_db; a.env_stride = s->nd;
   const size_t smem = scene_smem(s);
   // the step loop adds the cooperative contact-point area of its block (8-lane tiles of variant 8)
   const size_t smem_fwd = s->lanes == 8 && coop_bytes<8>() ? ((smem + 15) & ~(size_t)15) + coop_bytes<8>() : smem;
@@ -590,13 +669,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   }
   s->ran[TSIM_K_FWD] = 1; s->ran[TSIM_K_TAPE] = tape_pass ? 1 : 0; s->ran[TSIM_K_TAC] = tac_pass ? 1 : 0;
   CK(cudaEventRecord(s->ev[0], st));
-#if TS_MAXN <= 8
-  if (s->lanes == 8) { if (prep(fwd_kernel<8>, smem_fwd)) return 1; fwd_kernel<8><<<grid, TS_BLOCK, smem_fwd, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else
-#endif
-  if (s->lanes == 16) { if (prep(fwd_kernel<16>, smem)) return 1; fwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else { if (prep(fwd_kernel<32>, smem)) return 1; fwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  CK(cudaGetLastError());
+  TS_LAUNCH(fwd_kernel, grid, smem, smem_fwd, TS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   CK(cudaEventRecord(s->ev[1], st));
   int tgrid = 1;
   if (tac_pass || tape_pass) {
@@ -606,24 +679,12 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     tgrid = (int)(want < (long long)nsm * TS_BPS ? want : (long long)nsm * TS_BPS);
   }
   if (tape_pass) {
-#if TS_MAXN <= 8
-    if (s->lanes == 8) { if (prep(tape_kernel<8>, smem)) return 1; tape_kernel<8><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else
-#endif
-    if (s->lanes == 16) { if (prep(tape_kernel<16>, smem)) return 1; tape_kernel<16><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else { if (prep(tape_kernel<32>, smem)) return 1; tape_kernel<32><<<tgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    CK(cudaGetLastError());
+    TS_LAUNCH(tape_kernel, tgrid, smem, smem, TS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   }
   CK(cudaEventRecord(s->ev[2], st));
   if (tac_pass) {
     if (a.tac_prezeroed) CK(cudaMemsetAsync(tac_out, 0, (size_t)T * B * s->sizes[TSIM_NDOF_TACTILE] * sizeof(double), st));
-#if TS_MAXN <= 8
-    if (s->lanes == 8) { if (prep(tac_kernel<8>, smem, TS_PASS_BPS)) return 1; tac_kernel<8><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else
-#endif
-    if (s->lanes == 16) { if (prep(tac_kernel<16>, smem, TS_PASS_BPS)) return 1; tac_kernel<16><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    else { if (prep(tac_kernel<32>, smem, TS_PASS_BPS)) return 1; tac_kernel<32><<<tgrid * TS_PASS_BPS / TS_BPS, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-    CK(cudaGetLastError());
+    TS_LAUNCH(tac_kernel, tgrid * TS_PASS_BPS / TS_BPS, smem, smem, TS_PASS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   }
   CK(cudaEventRecord(s->ev[3], st));
   if (scratch) CK(cudaFreeAsync(scratch, st));
@@ -635,17 +696,14 @@ int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* 
   if (!s) return fail("tsim_readout: null scene");
   if (B <= 0 || !q || !qd) return fail("tsim_readout: bad arguments");
   CK(cudaSetDevice(s->device));
+  TS_PE_CHECK("tsim_readout")
+  EnvTables et;
+  et.env_db = s->d_env_db; et.env_stride = s->nd;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
-#if TS_MAXN <= 8
-  if (s->lanes == 8) { if (prep(readout_kernel<8>, smem)) return 1; readout_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
-  else
-#endif
-  if (s->lanes == 16) { if (prep(readout_kernel<16>, smem)) return 1; readout_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
-  else { if (prep(readout_kernel<32>, smem)) return 1; readout_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks); }
-  CK(cudaGetLastError());
+  TS_LAUNCH(readout_kernel, grid, smem, smem, TS_BPS, s->d_ib, s->ni, s->d_db, s->nd, B, q, qd, var_out, tac_out, marker_body, contact_masks, et);
   return 0;
 }
 
@@ -666,6 +724,8 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   a.df_dq = df_dq; a.dq_row = dq_row; a.df_dvar = df_dvar; a.dvar_row = dvar_row; a.df_dtac = df_dtac;
   a.dtac_row = dtac_row; a.carry = carry; a.df_du = df_du; a.df_dq0 = df_dq0; a.df_dqdot0 = df_dqdot0;
   a.vjp_y = 0; a.vjp_c = 0; a.work_counter = 0; a.vjp_list = 0;
+  TS_PE_CHECK("tsim_backward")
+  a.env_db = s->d_env_db; a.env_stride = s->nd;
   const size_t smem = scene_smem(s);
   const long long threads = (long long)B * s->lanes;
   const int grid = (int)((threads + TS_BLOCK - 1) / TS_BLOCK);
@@ -688,24 +748,12 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
     const long long want = ((long long)T * B * s->lanes + TS_BLOCK - 1) / TS_BLOCK;
     const int vgrid = (int)(want < (long long)nsm * TS_PASS_BPS ? want : (long long)nsm * TS_PASS_BPS);
     for (int phase = 0; phase < 2; ++phase) {
-#if TS_MAXN <= 8
-      if (s->lanes == 8) { if (prep(vjp_kernel<8>, smem, TS_PASS_BPS)) return 1; vjp_kernel<8><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
-      else
-#endif
-      if (s->lanes == 16) { if (prep(vjp_kernel<16>, smem, TS_PASS_BPS)) return 1; vjp_kernel<16><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
-      else { if (prep(vjp_kernel<32>, smem, TS_PASS_BPS)) return 1; vjp_kernel<32><<<vgrid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a, phase); }
-      CK(cudaGetLastError());
+      TS_LAUNCH(vjp_kernel, vgrid, smem, smem, TS_PASS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a, phase);
     }
   }
   s->ran[TSIM_K_VJP] = split ? 1 : 0; s->ran[TSIM_K_BWD] = 1;
   CK(cudaEventRecord(s->ev[5], st));
-#if TS_MAXN <= 8
-  if (s->lanes == 8) { if (prep(bwd_kernel<8>, smem)) return 1; bwd_kernel<8><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else
-#endif
-  if (s->lanes == 16) { if (prep(bwd_kernel<16>, smem)) return 1; bwd_kernel<16><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  else { if (prep(bwd_kernel<32>, smem)) return 1; bwd_kernel<32><<<grid, TS_BLOCK, smem, st>>>(s->d_ib, s->ni, s->d_db, s->nd, a); }
-  CK(cudaGetLastError());
+  TS_LAUNCH(bwd_kernel, grid, smem, smem, TS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   CK(cudaEventRecord(s->ev[6], st));
   if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;

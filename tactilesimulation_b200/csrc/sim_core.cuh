@@ -2633,6 +2633,7 @@ struct FwdArgs {
   int defer_tac;                      // the tactile field is read out by the pass of its own (env_tactile), not by the step loop
   int tac_prezeroed;                  // ... into a buffer that tsim_forward has already set to zero
   unsigned* work_counter;             // dynamic distribution of the env-steps of that pass
+  const double* env_db; long long env_stride;   // per-environment lowered double tables [B][env_stride], or null
 };
 
 // readouts from a work space that holds the kinematics of the state: variables, tactile field, contact sets
@@ -2851,6 +2852,7 @@ struct BwdArgs {
   double* vjp_y; double* vjp_c;                  // [T,B,n] readout pull-backs (vjp_terms): written by env_vjp, read by the sweep; or null
   unsigned* work_counter;                        // [4] dynamic distribution of the env-steps of the vjp passes
   int* vjp_list;                                 // [T*B] env-steps deferred by the first vjp pass (count: work_counter[2])
+  const double* env_db; long long env_stride;    // per-environment lowered double tables [B][env_stride], or null
 };
 
 template <class Tile, class WK>

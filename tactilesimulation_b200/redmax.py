@@ -116,6 +116,8 @@ class Simulation:
         self._current_backward_step = 0
         self._carry: Optional[torch.Tensor] = None
         self._cache = []
+        self._env_updates = []                         # per-environment parameter updates: (fn, names, values [B, ...])
+        self._dirty = False                            # host scene edited since the device handle was built
         self._q_hist: List[torch.Tensor] = []          # q trajectories since reset() (export_replay; Simulation::_q_his)
         self._virtual = {}                             # poses of the render-only objects
 
@@ -175,12 +177,14 @@ class Simulation:
         return self._np(self.get_variables_t())
 
     def get_variables_t(self):
+        self._ensure_core()
         return self.core.readout(self._q, self._qd)["var"]
 
     def get_tactile_force_vector(self):
         return self._np(self.get_tactile_force_vector_t())
 
     def get_tactile_force_vector_t(self):
+        self._ensure_core()
         return self.core.readout(self._q, self._qd)["tactile"]
 
     def get_tactile_sensor_pos(self, name):
@@ -239,67 +243,120 @@ class Simulation:
         return out
 
     # ------------------------------------------------------------------ parameter updates (domain randomisation)
-    # The scene tables are batch-invariant and live once per handle: an update edits the host scene and
-    # uploads a new handle (python_interface.cpp:181-211; DH/Robot.cpp update_* walk the pointer graph).
+    # python_interface.cpp:181-211; DH/Robot.cpp update_* walk the pointer graph of ONE environment.  Here a value may be
+    # a scalar / vector (all environments, as in the reference) or carry a leading batch dimension [B, ...]: then every
+    # environment gets its own value -- the reference's per-environment randomisation (dclaw_rotate_env.py:173-178,
+    # stable_grasp_env.py:122-128, tactile_insertion_env.py:254-275) in one batch.  Updates edit the host scene(s); the
+    # device handle is rebuilt lazily, once, at the next reset() / forward() / read-out (options are carried over).
+    def _per_env(self, value, tail_ndim):
+        a = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value, dtype=np.float64)
+        return self.batch > 1 and a.ndim == tail_ndim + 1 and a.shape[0] == self.batch, a
+
+    def _update(self, fn, names, values, tail_ndims):
+        """fn(scene, *names, *values) edits a Scene; values with a leading [B] dimension are logged per environment."""
+        conv = [self._per_env(v, nd) for v, nd in zip(values, tail_ndims)]
+        if any(pe for pe, _ in conv):
+            self._env_updates.append((fn, names, [a if pe else np.broadcast_to(a, (self.batch,) + a.shape) for pe, a in conv]))
+        else:
+            fn(self.scene, *names, *[a for _, a in conv])
+            # a broadcast update after per-environment ones applies to every environment as well
+            if self._env_updates:
+                self._env_updates.append((fn, names, [np.broadcast_to(a, (self.batch,) + a.shape) for _, a in conv]))
+        self._dirty = True
+
+    def clear_env_parameters(self):
+        """Back to one parameter set for all environments (drops the per-environment updates)."""
+        self._env_updates = []
+        self._dirty = True
+
     def _rebuild(self):
+        import copy
+        old = getattr(self, "core", None)
         self.core = BatchedSim(self.scene, device=self.device, lanes=self._lanes)
+        if old is not None:
+            for k, v in getattr(old, "options", {}).items():
+                self.core.set_option(k, v)
+        if self._env_updates:
+            ibs, dbs = [], []
+            for e in range(self.batch):
+                sc = copy.deepcopy(self.scene)
+                for fn, names, vals in self._env_updates:
+                    fn(sc, *names, *[v[e] for v in vals])
+                ib, db = sc.pack()
+                ibs.append(ib)
+                dbs.append(db)
+            self.core.set_env_scenes(np.stack(ibs), np.stack(dbs))
+        self._dirty = False
+
+    def _ensure_core(self):
+        if self._dirty:
+            self._rebuild()
+
+    @staticmethod
+    def _set_contact(sc, body1, body2, kn, kt, mu, damping):
+        names = sc.body_names
+        for f in sc.gp_contacts:
+            if names[f["body1"]] == body1 and names[f["body2"]] == body2:
+                f.update(kn=float(kn), kt=float(kt), mu=float(mu), damping=float(damping))
+
+    @staticmethod
+    def _set_tactile(sc, name, kn, kt, mu, damping):
+        for s_ in sc.sensors:
+            if s_.name == name:
+                s_.kn, s_.kt, s_.mu, s_.damping = float(kn), float(kt), float(mu), float(damping)
+
+    @staticmethod
+    def _set_damping(sc, joint_name, damping):
+        if joint_name in sc.joint_names:
+            sc.damping[sc.joint_names.index(joint_name)] = float(damping)
+
+    @staticmethod
+    def _set_ee(sc, name, position):
+        for e in sc.end_effectors:
+            if e["name"] == name:
+                e["pos"] = np.asarray(position, dtype=np.float64).copy()
 
     def update_contact_parameters(self, body1, body2, kn, kt, mu, damping):
         names = self.scene.body_names
-        hit = False
-        for f in self.scene.gp_contacts:
-            if names[f["body1"]] == body1 and names[f["body2"]] == body2:
-                f.update(kn=float(kn), kt=float(kt), mu=float(mu), damping=float(damping))
-                hit = True
-        if not hit:
+        if not any(names[f["body1"]] == body1 and names[f["body2"]] == body2 for f in self.scene.gp_contacts):
             raise TactileSimError(f"contact {body1} - {body2} not found")
-        self._rebuild()
+        self._update(self._set_contact, (body1, body2), (kn, kt, mu, damping), (0, 0, 0, 0))
 
     def update_tactile_parameters(self, name, kn, kt, mu, damping):
-        _, s = self._sensor(name)
-        s.kn, s.kt, s.mu, s.damping = float(kn), float(kt), float(mu), float(damping)
-        self._rebuild()
+        self._sensor(name)
+        self._update(self._set_tactile, (name,), (kn, kt, mu, damping), (0, 0, 0, 0))
 
     def update_joint_damping(self, joint_name, damping):
         if joint_name not in self.scene.joint_names:
             raise TactileSimError(f"joint {joint_name} not found")
-        self.scene.damping[self.scene.joint_names.index(joint_name)] = float(damping)
-        self._rebuild()
+        self._update(self._set_damping, (joint_name,), (damping,), (0,))
 
     def update_endeffector_position(self, endeffector_name, position):
-        for e in self.scene.end_effectors:
-            if e["name"] == endeffector_name:
-                e["pos"] = np.asarray(position, dtype=np.float64).copy()
-                self._rebuild()
-                return
-        raise TactileSimError(f"endeffector {endeffector_name} not found")
+        if not any(e["name"] == endeffector_name for e in self.scene.end_effectors):
+            raise TactileSimError(f"endeffector {endeffector_name} not found")
+        self._update(self._set_ee, (endeffector_name,), (position,), (1,))
+
+    def _scene_update(self, fn, name, value, tail_ndim):
+        from . import scene as _scene
+        try:
+            self._update(fn, (name,), (value,), (tail_ndim,))
+        except _scene.SceneError as e:
+            raise TactileSimError(str(e))
 
     def update_body_density(self, body_name, density):
         """DH/python_interface.cpp:181-211, DH/Robot.cpp:596-610 (R/envs/stable_grasp_env.py:122)."""
         from . import scene as _scene
-        try:
-            _scene.update_body_density(self.scene, body_name, density)
-        except _scene.SceneError as e:
-            raise TactileSimError(str(e))
-        self._rebuild()
+        self._scene_update(_scene.update_body_density, body_name, density, 0)
 
     def update_body_size(self, body_name, body_size):
         """DH/Robot.cpp:612-626 (R/envs/dclaw_rotate_env.py:175: the cap's (length, radius))."""
         from . import scene as _scene
-        try:
-            _scene.update_body_size(self.scene, body_name, body_size)
-        except _scene.SceneError as e:
-            raise TactileSimError(str(e))
-        self._rebuild()
+        self._scene_update(_scene.update_body_size, body_name, body_size, 1)
 
     def update_joint_location(self, joint_name, joint_location):
         """DH/Robot.cpp:636-650, DH/Joint/Joint.cpp:98-117 (R/envs/dclaw_rotate_env.py:178)."""
         from . import scene as _scene
-        try:
-            _scene.update_joint_location(self.scene, joint_name, joint_location)
-        except _scene.SceneError as e:
-            raise TactileSimError(str(e))
-        self._rebuild()
+        self._scene_update(_scene.update_joint_location, joint_name, joint_location, 1)
 
     def update_body_color(self, body_name, color):
         """Render-only."""
@@ -319,6 +376,7 @@ class Simulation:
     def reset(self, backward_flag: bool = False, backward_design_params_flag: bool = False):
         if backward_design_params_flag:
             raise TactileSimError("design-parameter gradients are out of scope of the B200 path")
+        self._ensure_core()
         if backward_flag and self.core.integrator != 0:
             raise TactileSimError("gradients exist for integrator BDF1 only on the B200 path (options.integrator is "
                                   + str(self.options.integrator) + ")")
@@ -360,6 +418,7 @@ class Simulation:
         T = int(num_steps)
         if T <= 0:
             return None
+        self._ensure_core()
         rows = ([-1] * (T - 1) + [0]) if save_last_frame_var_only else None
         trows = rows if tac_rows is None else tac_rows
         u = u.contiguous()

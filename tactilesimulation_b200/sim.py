@@ -54,12 +54,30 @@ class BatchedSim:
         self.integrator = int(sizes[_lib.INTEGRATOR])      # _lib.INT_BDF1 / INT_BDF2 / INT_SDIRK2
         self.h = float(self.dbuf[0])
         self.lanes = None
+        self.options = {}
+        self.env_batch = 0
         if lanes is not None:
             self.set_lanes(lanes)
 
     def set_option(self, key: int, value: int):
         """tsim_scene_set_option (include/tactilesim_b200.h): 0 = TSIM_OPT_LS_BATCH."""
         _lib.check(self.lib.tsim_scene_set_option(self.handle, key, value), self.lib)
+        self.options[int(key)] = int(value)
+
+    def set_env_scenes(self, ibufs, dbufs):
+        """Per-environment parameters (tsim_scene_set_env_scenes): ibufs [B, n_int] int32, dbufs [B, n_dbl] float64 -- one
+        packed scene of this handle's topology per environment; None / empty returns to one parameter set."""
+        if ibufs is None or len(ibufs) == 0:
+            _lib.check(self.lib.tsim_scene_set_env_scenes(self.handle, 0, None, 0, None, 0), self.lib)
+            self.env_batch = 0
+            return
+        ib = np.ascontiguousarray(ibufs, dtype=np.int32)
+        db = np.ascontiguousarray(dbufs, dtype=np.float64)
+        if ib.ndim != 2 or db.ndim != 2 or ib.shape[0] != db.shape[0]:
+            raise _lib.TactileSimError("set_env_scenes: expected ibufs [B, n_int] and dbufs [B, n_dbl]")
+        _lib.check(self.lib.tsim_scene_set_env_scenes(self.handle, ib.shape[0], ib.ctypes.data, ib.shape[1],
+                                                      db.ctypes.data, db.shape[1]), self.lib)
+        self.env_batch = ib.shape[0]
 
     def kernel_times(self):
         """Device time (ms) of each kernel of the last forward / backward call on this handle (None: did not run);

@@ -436,7 +436,7 @@ def randomized_case():
     the tests apply the same updates through tactilesimulation_b200.scene.update_* and compare the rollouts."""
     out = {}
     # ---- DClaw: cap radius / damping / location
-    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", xml_name)
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
     sim = redmax_py.Simulation(xml)
     sc = compile_scene(xml)
     upd = dict(damping=0.0015, size=np.array([0.03, 0.052]), ee=np.array([0.052, 0.0, 0.0]), loc=np.array([0.003, -0.004, 0.075]))
@@ -501,6 +501,79 @@ def randomized_case():
     d = sc.to_npz_dict()
     out.update(sg_ibuf=d["ibuf"], sg_dbuf=d["dbuf"], sg_body_names=np.array(sc.body_names), sg_dens=dens, sg_q0=q0, sg_u=u,
                sg_q=np.array(q), sg_tactile=np.array(tac))
+    return out
+
+
+def perenv_case():
+    """Per-ENVIRONMENT domain randomisation: K environments, each with its own parameters drawn like the reference's envs
+    draw them per reset -- DClaw: cap joint damping, cap radius, end-effector position, cap joint location and initial
+    finger pose (R/envs/dclaw_rotate_env.py:162-178); TactileInsertion: contact and tactile coefficients of both pads
+    (R/envs/tactile_insertion_env.py:232-275) -- one reference Simulation per environment, short rollouts.  The fixture
+    keeps the ORIGINAL scene blobs; the GPU test applies all K parameter sets to ONE batched Simulation."""
+    out = {}
+    rng = np.random.default_rng(11)
+    # ---- DClaw
+    K, T = 4, 30
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "dclaw_rotate", "dclaw_torque_control.xml")
+    sc = compile_scene(xml)
+    damping, radius = rng.uniform(0.01, 0.7, K), rng.uniform(0.02, 0.08, K)
+    dxy = rng.uniform(-0.02, 0.02, (K, 2))
+    q0 = np.zeros((K, 10))
+    q0[:, [1, 4, 7]] = -0.5
+    q0[:, [2, 5, 8]] = 0.8
+    q0[:, :9] += 0.05 * rng.normal(size=(K, 9))
+    u = rng.uniform(-1, 1, (T, K, 9))
+    u[:, :, 1::3] = 0.6 + 0.4 * u[:, :, 1::3]
+    q, var, tac = np.zeros((K, T, 10)), np.zeros((K, T, 12)), np.zeros((K, T // 5, 2718))
+    for e in range(K):
+        sim = redmax_py.Simulation(xml)
+        sim.update_joint_damping("cap", damping[e])
+        sim.update_body_size("cap", np.array([0.03, radius[e]]))
+        sim.update_endeffector_position("cap", np.array([radius[e], 0.0, 0.0]))
+        sim.update_joint_location("cap", np.array([dxy[e, 0], dxy[e, 1], 0.075]))
+        sim.set_state_init(q0[e], np.zeros(10))
+        sim.reset(False)
+        for t in range(T):
+            sim.set_u(u[t, e])
+            sim.forward(1)
+            q[e, t], var[e, t] = sim.get_q(), sim.get_variables()
+            if t % 5 == 4:
+                tac[e, t // 5] = sim.get_tactile_force_vector()
+    d = sc.to_npz_dict()
+    out.update(dclaw_ibuf=d["ibuf"], dclaw_dbuf=d["dbuf"], dclaw_joint_names=np.array(sc.joint_names), dclaw_body_names=np.array(sc.body_names),
+               dclaw_ee_names=np.array([e_["name"] for e_ in sc.end_effectors]), dclaw_damping=damping, dclaw_radius=radius, dclaw_dxy=dxy,
+               dclaw_q0=q0, dclaw_u=u, dclaw_q=q, dclaw_var=var, dclaw_tactile=tac)
+    # ---- TactileInsertion
+    K, T = 3, 45
+    xml = os.path.join(ROOT, "oracle", "_ref", "assets", "tactile_insertion", "tactile_insertion.xml")
+    sc = compile_scene(xml)
+    cpar = np.stack([rng.uniform(2e3, 14e3, K), rng.uniform(20., 140., K), rng.uniform(0.5, 2.5, K), rng.uniform(0., 100., K)], axis=1)
+    tpar = np.stack([rng.uniform(50, 450, K), rng.uniform(0.2, 2.3, K), rng.uniform(0.5, 2.5, K), rng.uniform(0., 100., K)], axis=1)
+    q0 = np.zeros(12)
+    q0[2] = 0.2
+    q0[4] = q0[5] = -0.03
+    u = np.zeros((T, 6))
+    for t in range(T):
+        g_ = min(1.0, (t + 1) / 15.0)
+        m = max(0.0, (t - 25) / float(max(T - 25, 1)))
+        u[t] = [0.004 * m, -0.003 * m, 0.2 - 0.002 * m, 0.15 * m, g_, g_]
+    q, tac = np.zeros((K, T, 12)), np.zeros((K, T // 5, 780))
+    for e in range(K):
+        sim = redmax_py.Simulation(xml)
+        for pad in ("tactile_pad_left", "tactile_pad_right"):
+            sim.update_contact_parameters(pad, "box", *[float(x) for x in cpar[e]])
+            sim.update_tactile_parameters(pad, *[float(x) for x in tpar[e]])
+        sim.set_state_init(q0, np.zeros(12))
+        sim.reset(False)
+        for t in range(T):
+            sim.set_u(u[t])
+            sim.forward(1)
+            q[e, t] = sim.get_q()
+            if t % 5 == 4:
+                tac[e, t // 5] = sim.get_tactile_force_vector()
+    d = sc.to_npz_dict()
+    out.update(ins_ibuf=d["ibuf"], ins_dbuf=d["dbuf"], ins_body_names=np.array(sc.body_names), ins_sensor_names=np.array([s_.name for s_ in sc.sensors]),
+               ins_cpar=cpar, ins_tpar=tpar, ins_q0=q0, ins_u=u, ins_q=q, ins_tactile=tac)
     return out
 
 
@@ -685,6 +758,7 @@ def main():
         "free2d_plate_bdf1_s0": lambda: free2d_case(60, 0),
         "capsule_press_bdf1_s0": lambda: capsule_case(60, 0),
         "randomized_updates_s0": randomized_case,
+        "perenv_updates_s0": perenv_case,
         "spherical_exp_bdf2_s0": lambda: spherical_exp_case(60, 0),
     }
     only = sys.argv[1:]          # optional: names of the fixtures to (re)generate

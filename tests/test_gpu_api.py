@@ -166,6 +166,6 @@ def test_compat_simulation_dclaw_surface():
     sim.forward(3)
     import tempfile
     with tempfile.TemporaryDirectory() as d:
-        sim.export_replay(os.path.join(d, "replay.txt"))
-        lines = open(os.path.join(d, "replay.txt")).read().strip().split("\n")
-        assert lines[0].split()[:2] == ["10", "3"] and len(lines) == 4
+        n_mesh = sim.export_replay(os.path.join(d, "replay"))          # the reference's folder format (tests/test_replay_export.py)
+        assert sorted(f for f in os.listdir(os.path.join(d, "replay")) if f.endswith(".txt")) == ["0.txt", "1.txt", "2.txt", "3.txt"]
+        assert open(os.path.join(d, "replay", "3.txt")).readline().strip() == str(n_mesh)
