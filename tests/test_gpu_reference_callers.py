@@ -107,3 +107,47 @@ def test_batched_frontend_replays_episodes_of_the_reference_env():
         assert rel_err(o_new[:, 3:], rec[e]["obs"][:, 3:]) <= 1e-8, e
         assert np.allclose(np.array([r[e] for r in rews]), rec[e]["rew"], rtol=1e-9, atol=1e-12), e
         assert rel_err(np.stack([a.grad[e].cpu().numpy() for a in acts]), rec[e]["grad"]) <= 1e-6, e
+
+
+def test_batched_insertion_frontend_matches_the_reference_env():
+    """BatchedTactileInsertionEnv (BASELINE configs[4] is defined through this env) against the UNMODIFIED
+    R/envs/tactile_insertion_env.py run on the reference module: grasp pose of generate_initial_pose, then B = 3 episodes
+    (reset with given noises, two steps with given actions): observations, rewards, success flags."""
+    _need_ref()
+    from tactilesimulation_b200.envs import BatchedTactileInsertionEnv
+    from tactilesimulation_b200.redmax import Simulation
+    ns = rc.load(rc.reference_module())
+    kw = dict(observation_type="tactile_flatten", observation_noise=False, normalize_tactile_obs=True, allow_translation=True,
+              allow_rotation=True, action_type="relative", reward_type="delta", domain_randomization=False)
+    env = ns.gym.make("Insertion-v3", use_torch=True, verbose=False, render_tactile=False, **kw)
+    B = 3
+    rng = np.random.RandomState(4)
+    pos = np.stack([rng.uniform(-0.006, 0.006, B), rng.uniform(-0.006, 0.006, B), rng.uniform(-0.0002, 0.0002, B)], axis=1)
+    rot = rng.uniform(-np.pi / 18, np.pi / 18, B)
+    gh = rng.uniform(-0.01, 0.005, B)
+    acts = rng.uniform(-1, 1, (2, B, 3))
+    rec = []
+    for e in range(B):
+        o = [env.reset(position_noise=pos[e], rotation_noise=rot[e], grasp_height_noise=gh[e]).detach().numpy().copy()]
+        rs, ds = [], []
+        for k in range(2):
+            ob, r, d, info = env.step(torch.tensor(acts[k, e]))
+            o.append(ob.detach().numpy().copy())
+            rs.append(float(r))
+            ds.append(bool(info["success"]))
+        rec.append((o, rs, ds))
+    xml = os.path.join(rc.PY_DIR, "envs", "assets", "tactile_insertion", "tactile_insertion.xml")
+    benv = BatchedTactileInsertionEnv(Simulation(xml, batch=B), **kw)
+    assert rel_err(benv.q_init_reference[0].cpu().numpy(), env.unwrapped.q_init_reference) <= 1e-8
+    obs = [benv.reset(position_noise=torch.tensor(pos), rotation_noise=torch.tensor(rot), grasp_height_noise=torch.tensor(gh))]
+    rews, dones = [], []
+    for k in range(2):
+        ob, r, d, info = benv.step(torch.tensor(acts[k]))
+        obs.append(ob)
+        rews.append(r.cpu().numpy())
+        dones.append(d.cpu().numpy())
+    for e in range(B):
+        for k in range(3):
+            assert rel_err(obs[k][e].cpu().numpy(), rec[e][0][k]) <= 1e-6, (e, k)
+        assert np.allclose([r[e] for r in rews], rec[e][1], rtol=1e-7, atol=1e-9), e
+        assert [bool(d[e]) for d in dones] == rec[e][2], e
