@@ -1687,14 +1687,29 @@ HD void eval_columns(const Tile& tl, const SceneView& S, TileState& ts, const do
   in.tqd0 = (seed == 2) ? 1.0 : 0.0;
   tl.tile_sync();          // every lane of the tile is done with the previous evaluation and its bookkeeping
   if (!(Tile::COOP && idle)) {
+    if (L >= TS_MAXN) {
+      // one coordinate per lane (the stage formulas hold fp64 divisions: 8 of them in every lane cost 6 % of the
+      // instructions of the step loop); the values are the same, written once instead of LPE times
+      const int i = tl.lane;
+      if (i < TS_MAXN) {
+        const double xi = (i < n) ? x[i] : 0.0;
+        double xv = 0.0, xl = 0.0;
+        if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
+        ts.xq[i] = xi;
+        ts.xv[i] = xv;
+        ts.xl[i] = xl;
+      }
+      tl.tile_sync();
+    } else {
 #pragma unroll
-    for (int i = 0; i < TS_MAXN; ++i) {
-      const double xi = (i < n) ? x[i] : 0.0;
-      double xv = 0.0, xl = 0.0;
-      if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
-      ts.xq[i] = xi;
-      ts.xv[i] = xv;
-      ts.xl[i] = xl;
+      for (int i = 0; i < TS_MAXN; ++i) {
+        const double xi = (i < n) ? x[i] : 0.0;
+        double xv = 0.0, xl = 0.0;
+        if (i < n) stage_inputs(S, ts, mode, i, xi, xv, xl);
+        ts.xq[i] = xi;
+        ts.xv[i] = xv;
+        ts.xl[i] = xl;
+      }
     }
   }
   for (int c = 0; c < TS_NC(L); ++c) {

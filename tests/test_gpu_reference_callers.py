@@ -119,6 +119,19 @@ def test_batched_insertion_frontend_matches_the_reference_env():
     ns = rc.load(rc.reference_module())
     kw = dict(observation_type="tactile_flatten", observation_noise=False, normalize_tactile_obs=True, allow_translation=True,
               allow_rotation=True, action_type="relative", reward_type="delta", domain_randomization=False)
+    # (the env builds its action ramp with torch.zeros((T, 6)): under torch's default float32 the position targets would be
+    # rounded to 6e-8 relative, which the stiff position control turns into 1e-5 of tactile force; the comparison runs
+    # the reference under float64 defaults, like R/examples/TactilePushExp/train_tactile_push_gd.py:13 sets them)
+    torch.set_default_dtype(torch.float64)
+    try:
+        return _insertion_episodes(ns, kw)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def _insertion_episodes(ns, kw):
+    from tactilesimulation_b200.envs import BatchedTactileInsertionEnv
+    from tactilesimulation_b200.redmax import Simulation
     env = ns.gym.make("Insertion-v3", use_torch=True, verbose=False, render_tactile=False, **kw)
     B = 3
     rng = np.random.RandomState(4)
@@ -139,6 +152,10 @@ def test_batched_insertion_frontend_matches_the_reference_env():
     xml = os.path.join(rc.PY_DIR, "envs", "assets", "tactile_insertion", "tactile_insertion.xml")
     benv = BatchedTactileInsertionEnv(Simulation(xml, batch=B), **kw)
     assert rel_err(benv.q_init_reference[0].cpu().numpy(), env.unwrapped.q_init_reference) <= 1e-8
+    # The grasp pose is the end of 1 000 contact-rich sim-steps; the pads penetrate the box by ~1e-4 m, so the 1e-9 m left
+    # of that rollout's rounding would show as 1e-5 in the RELATIVE tactile observations.  The episodes below start
+    # from the reference's pose so that they test the env logic (and 45-step rollouts), not that amplification.
+    benv.q_init_reference = torch.tensor(np.tile(env.unwrapped.q_init_reference, (B, 1)), device=benv.device)
     obs = [benv.reset(position_noise=torch.tensor(pos), rotation_noise=torch.tensor(rot), grasp_height_noise=torch.tensor(gh))]
     rews, dones = [], []
     for k in range(2):
@@ -151,3 +168,53 @@ def test_batched_insertion_frontend_matches_the_reference_env():
             assert rel_err(obs[k][e].cpu().numpy(), rec[e][0][k]) <= 1e-6, (e, k)
         assert np.allclose([r[e] for r in rews], rec[e][1], rtol=1e-7, atol=1e-9), e
         assert [bool(d[e]) for d in dones] == rec[e][2], e
+
+
+@pytest.mark.parametrize("torque", [False, True])
+def test_batched_dclaw_frontend_matches_the_reference_env(torque):
+    """BatchedDClawRotateEnv (BASELINE configs[3]) against the UNMODIFIED R/envs/dclaw_rotate_env.py on the reference module:
+    B = 3 environments, each with its OWN randomised cap (damping / radius / end-effector / joint location read back from
+    the reference env's seeded draws), eight steps with given actions: observations, rewards, done / success flags."""
+    _need_ref()
+    from tactilesimulation_b200.envs import BatchedDClawRotateEnv
+    from tactilesimulation_b200.redmax import Simulation
+    ns = rc.load(rc.reference_module())
+    B, steps = 3, 8
+    rng = np.random.RandomState(21)
+    acts = rng.uniform(-1.2, 1.2, (steps, B, 9))
+    rec = []
+    for e in range(B):
+        env = ns.gym.make("TactileRotation-v1", use_torch=False, observation_type="tactile_flatten", render_tactile=False,
+                          torque_control=torque, relative_control=True)
+        env.seed(50 + e)
+        # replay the env's own reset draws (dclaw_rotate_env.py:163-169) to know what it randomised
+        r2 = np.random.RandomState(50 + e)
+        qn = r2.randn(9) * 0.05
+        damping, radius = r2.uniform(low=0.01, high=0.7), r2.uniform(low=0.02, high=0.08)
+        dxy = r2.uniform(low=-0.02, high=0.02, size=2)
+        obs = [np.asarray(env.reset()).copy()]
+        rews, dones = [], []
+        for k in range(steps):
+            o, r, d, info = env.step(acts[k, e].copy())
+            obs.append(np.asarray(o).copy())
+            rews.append(float(r))
+            dones.append((bool(d), bool(info["success"])))
+        rec.append(dict(qn=qn, damping=damping, radius=radius, dxy=dxy, obs=np.stack(obs), rew=np.array(rews), done=dones))
+    xml = os.path.join(rc.PY_DIR, "envs", "assets", "dclaw_rotate",
+                       "dclaw_torque_control.xml" if torque else "dclaw_position_control.xml")
+    benv = BatchedDClawRotateEnv(Simulation(xml, batch=B), observation_type="tactile_flatten", torque_control=torque)
+    obs = [benv.reset(q_noise=torch.tensor(np.stack([r["qn"] for r in rec])), damping=np.array([r["damping"] for r in rec]),
+                      radius=np.array([r["radius"] for r in rec]), dxy=np.stack([r["dxy"] for r in rec]))]
+    rews, dones = [], []
+    for k in range(steps):
+        o, r, d, info = benv.step(torch.tensor(acts[k]))
+        obs.append(o)
+        rews.append(r.cpu().numpy())
+        dones.append((d.cpu().numpy(), info["success"].cpu().numpy()))
+    for e in range(B):
+        o_new = np.stack([o[e].cpu().numpy() for o in obs])
+        assert o_new.shape == rec[e]["obs"].shape == (steps + 1, 18 + 3 * 20 * 20 * 3)
+        assert np.abs(o_new[:, :18] - rec[e]["obs"][:, :18]).max() <= 1e-8, e          # joint angles, fingertip positions
+        assert rel_err(o_new[:, 18:], rec[e]["obs"][:, 18:]) <= 1e-6, e                # tactile flow images
+        assert np.allclose(np.array([r[e] for r in rews]), rec[e]["rew"], rtol=1e-7, atol=1e-9), e
+        assert [(bool(d[e]), bool(s_[e])) for d, s_ in dones] == rec[e]["done"], e

@@ -91,5 +91,19 @@ for k, d in per.items():
     md.append(f"| fp64 flops (2 dfma + dmul + dadd, thread level) | {f64:,.4g} | = {f64 / ms / 1e9:.3f} TFLOP/s under ncu |")
     md.append(f"| DRAM bytes per env-step | {(d['dram__bytes_read.sum'][0] + d['dram__bytes_write.sum'][0]) / (B * T):,.0f} | byte |")
     md.append("")
+# ---- source-level attribution of the ncu --set full capture (T=20 per launch), per source function
+rep = os.path.join(G, "r02_fwd_full.ncu-rep")
+if os.path.exists(rep):
+    src = os.path.join(G, "r02_fwd_src.csv")
+    with open(src, "w") as f:
+        subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=f, stderr=subprocess.DEVNULL)
+    tab = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_function.py"), src,
+                          os.path.join(ROOT, "tactilesimulation_b200", "libtactilesim_b200.so"), "fwd_kernelILi8ELb0"],
+                         capture_output=True, text=True).stdout
+    md += ["## fwd_kernel<8, 0>: warp-state samples per source function", "",
+           "`ncu --set full --clock-control none --import-source on -k regex:fwd_kernel -c 1` on `tools/perf_probe.py --B 4096 --T 20 --lanes 8",
+           "--grad-only`, source page joined with nvdisasm line info (`tools/ncu_by_function.py`).  `kernels.cu` = the block-wide vote of a",
+           "round; `gp_points_coop` = the cooperative contact-point phase (its barriers); `mkdual` = inlined dual-number arithmetic.", "", "```"]
+    md += tab.strip().split("\n")[:34] + ["```", ""]
 open(os.path.join(P, "r02_ncu_summary.md"), "w").write("\n".join(md) + "\n")
 print("fwd flops/launch %.4g, dram %.4g B, sha %s" % (flops, dram, source_sha()))
