@@ -12,7 +12,8 @@ Semantics kept from the reference (line numbers of ``R/envs/dclaw_rotate_env.py`
   * observation (:92-122): the nine joint angles, the three fingertip positions (variables) and the three 20 x 20
     tactile flow images (``get_tactile_flow_images``, DH/Robot.cpp:372-387), flattened ("tactile_flatten") or as
     [9, 20, 20] maps ("tactile"); "no_tactile": joint angles + fingertip positions;
-  * reward (:124-160): -0.5 per finger whose summed tactile force norm is below 1, -(min(cap angle - pi/4, 0))^2,
+  * reward (:124-160): -0.5 per finger whose summed tactile force norm (of the PREVIOUS observation: the reference
+    refreshes its tactile buffer after the reward) is below 1, -(min(cap angle - pi/4, 0))^2,
     -0.005 |action|^2, -50 and done when a fingertip rises above the cap's top surface, +50, success and done at pi/4.
 """
 import math
@@ -50,12 +51,17 @@ class BatchedDClawRotateEnv:
         q_init[[2, 5, 8]] = 0.8
         self.q_init = q_init
         # marker -> pixel of each 20 x 20 flow image (get_tactile_image_pos)
-        idx, off = [], 0
+        # (several markers of the fingertip spec share a pixel -- 302 markers on 182 pixels: the reference writes them in
+        # marker order, the last one stays, DH/Robot.cpp:383-384)
+        self._pix, self._nmark = [], []
         for s_ in sim.scene.sensors:
             ip = np.asarray(s_.image_pos, dtype=np.int64).reshape(-1, 2)
-            idx.append(torch.as_tensor(ip[:, 0] * self.tactile_cols + ip[:, 1], device=dev))
-            off += len(ip)
-        self._pix = idx
+            last = {}
+            for j, (r, c) in enumerate(ip):
+                last[int(r) * self.tactile_cols + int(c)] = j
+            pix = np.array(sorted(last), dtype=np.int64)
+            self._pix.append((torch.as_tensor(pix, device=dev), torch.as_tensor(np.array([last[p_] for p_ in pix], dtype=np.int64), device=dev)))
+            self._nmark.append(len(ip))
         self.tactile_force_buf = torch.zeros((self.B, 3, self.tactile_rows, self.tactile_cols, 3), dtype=f64, device=dev)
         self.energy_usage = torch.zeros(self.B, dtype=f64, device=dev)
 
@@ -67,9 +73,9 @@ class BatchedDClawRotateEnv:
         B = tactile.shape[0]
         out = torch.zeros((B, len(self._pix), self.tactile_rows * self.tactile_cols, 3), dtype=tactile.dtype, device=tactile.device)
         off = 0
-        for k, pix in enumerate(self._pix):
-            M = pix.numel()
-            out[:, k, pix] = tactile[:, off:off + 3 * M].reshape(B, M, 3)
+        for k, (pix, marker) in enumerate(self._pix):
+            M = self._nmark[k]
+            out[:, k, pix] = tactile[:, off:off + 3 * M].reshape(B, M, 3)[:, marker]
             off += 3 * M
         return out.reshape(B, len(self._pix), self.tactile_rows, self.tactile_cols, 3)
 
@@ -117,8 +123,10 @@ class BatchedDClawRotateEnv:
             else:
                 action = 0.5 * (action + 1.0) * (hi - lo) + lo
         self.sim.forward_t(self.frame_skip, action.contiguous())
-        obs = self._get_obs()
+        # (as in the reference, :208-221: the reward is computed BEFORE the observation refreshes the tactile buffer, so its
+        # contact term looks at the tactile images of the previous observation)
         reward, done, success = self._get_reward(u)
+        obs = self._get_obs()
         return obs, reward, done, dict(success=success)
 
     def _get_reward(self, action):
