@@ -64,6 +64,7 @@ namespace TSV(tsimns) {
 __device__ long long* g_prof = 0;      // [threads][16] cycle accumulators (development builds only)
 #endif
 
+template <int SUBL> struct SubTileOf;       // (defined after DevTile)
 template <int LPE_, bool COOP_ = false>
 struct DevTile {
   static const int LPE = LPE_;
@@ -139,6 +140,9 @@ struct DevTile {
     return p;
 #endif
   }
+  // sub-tile of SUBL consecutive lanes of this tile (SUBL = 1: one lane alone = the host policy): the value-only trial
+  // evaluations of the batched line search (sim_core.cuh, trial_norm)
+  template <int SUBL> __device__ __forceinline__ typename SubTileOf<SUBL>::type sub() const { return SubTileOf<SUBL>::make(); }
   // ---- whole-warp helpers: every lane of the warp must call them together
   static const int TPW = 32 / LPE_;
   HD int tile_in_warp() const { return (threadIdx.x & 31) / LPE_; }
@@ -236,6 +240,23 @@ __device__ __forceinline__ void bind_work(WorkSplit& W, const SceneView& S, int 
   W.fr = (Frames*)(base + S.nj * WK_REC + sizeof(TileState) / 8);
   W.beta = 0.0;
 }
+
+template <int SUBL> struct SubTileOf {
+  typedef DevTile<SUBL, false> type;
+  static __device__ __forceinline__ type make() {
+    type t;
+    const int wl = threadIdx.x & 31;
+    t.lane = wl % SUBL;
+    t.mask = (SUBL == 32) ? 0xffffffffu : (((1u << SUBL) - 1u) << (wl - t.lane));
+    t.coop = 0;
+    t.tile_id = 0;
+    return t;
+  }
+};
+template <> struct SubTileOf<1> {            // one lane alone: the host policy (no cross-lane operations at all)
+  typedef HostTile type;
+  static __device__ __forceinline__ type make() { return HostTile(); }
+};
 
 template <int LPE, bool COOP = false>
 __device__ __forceinline__ DevTile<LPE, COOP> make_tile() {

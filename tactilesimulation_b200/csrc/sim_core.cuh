@@ -1494,6 +1494,7 @@ struct HostTile {
   HD bool cta_any(bool p) const { return p; }
   HD bool warp_all(bool p) const { return p; }
   HD bool warp_any(bool p) const { return p; }
+  template <int SUBL> HD HostTile sub() const { return *this; }
   // whole-warp helpers (one tile per "warp" on the host)
   static const int TPW = 1;
   HD int tile_in_warp() const { return 0; }
@@ -1832,10 +1833,14 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
   }
 }
 
-// ||g(x + alpha dx)|| by a value-only evaluation that this lane runs ALONE (one-lane tile policy, plain
-// per-lane work space): the lanes of a tile evaluate different step lengths of a struggling line
-// search at the same time.
-HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha, int mode) {
+// ||g(x + alpha dx)|| by a value-only evaluation (plain per-lane work space) that a SUB-TILE of the tile's lanes runs
+// for itself: the sub-tiles of a tile evaluate different step lengths of a struggling line search at the same time.
+// TS_LS_SUB = 1: every lane alone (one-lane policy).  TS_LS_SUB = 4 (the 16-lane variants): four lanes per step length
+// repeat the same value arithmetic and share the contact DETECTION of the evaluation (dealt to the lanes, gathered by
+// ballot, as in the full evaluation): the scenes of those variants test hundreds of sampled points per force
+// (DClaw: 3 x 217), which one lane alone took longer than a whole round of the block.
+template <class SubTile>
+HDN double trial_norm(const SubTile& solo, const SceneView& S, const TileState& ts, double alpha, int mode) {
   const int n = S.n;
   double xq[TS_MAXN], xv[TS_MAXN], xl[TS_MAXN], g[TS_MAXN];
   for (int i = 0; i < TS_MAXN; ++i) {
@@ -1849,7 +1854,6 @@ HDN double trial_norm(const SceneView& S, const TileState& ts, double alpha, int
   ArrIn<double> in;
   in.q_ = xq; in.qd_ = xv; in.dl_ = xl; in.q0_ = ts.q; in.qd0_ = ts.qd;
   WorkRec<double> Wv;
-  HostTile solo;
   double stv, sbeta;
   stage_coef(S, mode, stv, sbeta);
   eval_g(solo, S, in, ts.u, Wv, g, sbeta);
@@ -1986,23 +1990,28 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         // re-checks the acceptance.  Same accepted step length as the sequential search.
         bool found = false;
         TS_CPT0();
+#ifndef TS_LS_SUB
+#define TS_LS_SUB (TS_MAXN > 8 ? 4 : 1)
+#endif
+        const int NBMAX = L / TS_LS_SUB > 0 ? L / TS_LS_SUB : 1;     // step lengths evaluated at once
         while (v.trial < S.max_ls) {
           const int left = S.max_ls - v.trial;
-          const int nb = left < L ? left : L;
+          const int nb = left < NBMAX ? left : NBMAX;
+          const int mine = tl.lane / TS_LS_SUB;      // the step length this lane works on
           double my_alpha = v.alpha;
-          for (int i = 0; i < tl.lane; ++i) my_alpha *= 0.5;
+          for (int i = 0; i < mine; ++i) my_alpha *= 0.5;
           double my_norm = 0.0;
-          if (tl.lane < nb) my_norm = trial_norm(S, ts, my_alpha, v.mode);
-          const unsigned okbits = tl.ballot(tl.lane < nb && my_norm < v.gnorm);
+          if (mine < nb) my_norm = trial_norm(tl.template sub<TS_LS_SUB>(), S, ts, my_alpha, v.mode);
+          const unsigned okbits = tl.ballot(mine < nb && my_norm < v.gnorm);
           if (okbits) {
-            const int k = ts_ffs(okbits);
+            const int k = ts_ffs(okbits) / TS_LS_SUB;
             v.trial += k;
             v.ls += k;                           // the rejected trials the sequential search would have evaluated
             for (int i = 0; i < k; ++i) v.alpha *= 0.5;
             found = true;
             break;
           }
-          gnn = tl.bcast(my_norm, nb - 1);       // ||g|| of the last trial evaluated (used by the exhausted path)
+          gnn = tl.bcast(my_norm, (nb - 1) * TS_LS_SUB);   // ||g|| of the last trial evaluated (used by the exhausted path)
           v.trial += nb;
           v.ls += nb;
           for (int i = 0; i < nb; ++i) v.alpha *= 0.5;
