@@ -457,6 +457,36 @@ struct tsim_scene {
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
+
+// Stream-ordered scratch of a call, returned to the pool on EVERY exit path of the call.
+struct Scratch {
+  void* p;
+  cudaStream_t st;
+  Scratch(cudaStream_t s) : p(0), st(s) {}
+  ~Scratch() { if (p) cudaFreeAsync(p, st); }
+};
+// The scratch comes from a memory pool of the library's own (one per device, kept between calls: release threshold
+// = max), not from the device's default pool, whose settings belong to the application (torch's allocator does not see
+// memory cached there).
+static cudaError_t scratch_alloc(void** p, size_t bytes, int device, cudaStream_t st) {
+  static cudaMemPool_t pools[64] = {0};
+  if (device < 0 || device >= 64) return cudaMallocAsync(p, bytes, st);
+  if (!pools[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[device] = pool;
+  }
+  return cudaMallocFromPoolAsync(p, bytes, pools[device], st);
+}
 #define CK(x)                                                                                          \
   do {                                                                                                 \
     cudaError_t e_ = (x);                                                                              \
@@ -522,7 +552,13 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   if (!err.empty()) return fail("tsim_scene_create: " + err);
   CK(cudaSetDevice(device));
   tsim_scene* s = new tsim_scene();
+  struct Guard {                       // a failure below destroys what was built so far
+    tsim_scene* s;
+    ~Guard() { if (s) tsim_scene_destroy(s); }
+  } guard = {s};
   s->device = device;
+  s->d_ib = 0; s->d_db = 0;
+  for (int i = 0; i < 7; ++i) s->ev[i] = 0;
   s->ni = (int)kt.ib.size();
   s->nd_all = (int)kt.db.size();
   s->nd = kt.ib[KI_D_MARKERS];       // doubles staged in shared memory: everything before the marker table
@@ -538,14 +574,6 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->opts[TSIM_OPT_VJP_PASS] = 1;
   s->opts[TSIM_OPT_TAC_PASS] = 1;
   s->opts[TSIM_OPT_TAPE_PASS] = 1;
-  {
-    // keep the stream-ordered scratch of tsim_backward in the pool between calls
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
   CK(cudaMalloc(&s->d_ib, sizeof(int) * s->ni));
   CK(cudaMalloc(&s->d_db, sizeof(double) * s->nd_all));
   CK(cudaMemcpy(s->d_ib, kt.ib.data(), sizeof(int) * s->ni, cudaMemcpyHostToDevice));
@@ -561,6 +589,7 @@ int tsim_scene_create(const int32_t* ibuf, int64_t n_int, const double* dbuf, in
   s->sizes[TSIM_TAPE_DOUBLES] = 3 * n * n + ibuf[TS_I_NDOF_U];
   s->sizes[TSIM_CMASK_WORDS] = kt.ib[KI_CMW];
   s->sizes[TSIM_INTEGRATOR] = kt.ib[KI_INTEGRATOR];
+  guard.s = 0;
   *out = s;
   return 0;
 }
@@ -571,7 +600,7 @@ void tsim_scene_destroy(tsim_scene* s) {
   cudaFree(s->d_ib);
   cudaFree(s->d_db);
   if (s->d_env_db) cudaFree(s->d_env_db);
-  for (int i = 0; i < 7; ++i) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < 7; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   delete s;
 }
 
@@ -656,7 +685,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
   cudaStream_t st = (cudaStream_t)stream;
   // The tactile field is read out by a pass of its own over the recorded trajectory (tac_kernel) when the call covers
   // more than a few steps; scratch (trajectory if the caller keeps none, work counter) is stream-ordered.
-  void* scratch = 0;
+  Scratch scratch(st);
   const bool big = T >= 4 && (long long)T * B < (1ll << 31) - 64;
   const bool tac_pass = tac_out && s->opts[TSIM_OPT_TAC_PASS] != 0 && big;
   // ... and so are the G0 / G1 / gain blocks of the tape (tape_kernel), which need the state at the start of the call
@@ -667,8 +696,8 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     const int own_traj = (q_traj ? 0 : 1) + (qd_traj ? 0 : 1);    // trajectories the caller does not keep: scratch
     const size_t norder = (((size_t)T * B * sizeof(int)) + 15) & ~(size_t)15;
     const size_t need = 16 + own_traj * nvec * sizeof(double) + (tape_pass ? 2 * nst * sizeof(double) + norder : 0);
-    CK(cudaMallocAsync(&scratch, need, st));
-    unsigned char* p = (unsigned char*)scratch;
+    CK(scratch_alloc(&scratch.p, need, s->device, st));
+    unsigned char* p = (unsigned char*)scratch.p;
     a.work_counter = (unsigned*)p;
     p += 16;
     if (!q_traj) { a.q_traj = (double*)p; p += nvec * sizeof(double); }
@@ -708,8 +737,7 @@ int tsim_forward_multistep(const tsim_scene* s, int32_t B, int32_t T, double* q,
     TS_LAUNCH(tac_kernel, tgrid * TS_PASS_BPS / TS_BPS, smem, smem, TS_PASS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   }
   CK(cudaEventRecord(s->ev[3], st));
-  if (scratch) CK(cudaFreeAsync(scratch, st));
-  return 0;
+  return 0;                                  // (~Scratch returns the scratch to the pool, stream-ordered)
 }
 
 int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* qd, double* var_out, double* tac_out,
@@ -754,12 +782,12 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   // Pass 1: readout pull-backs of all env-steps (balanced over the whole GPU); pass 2: the reverse sweep reads them.
   // Scratch: 2 x [T,B,n] doubles + the work counter, stream-ordered allocation (retained by the device's pool).
   CK(cudaEventRecord(s->ev[4], st));
-  void* scratch = 0;
+  Scratch scratch(st);
   const bool split = (df_dvar || df_dtac) && s->opts[TSIM_OPT_VJP_PASS] != 0 && (long long)T * B < (1ll << 31) - 64;
   if (split) {
     const size_t nvec = (size_t)T * B * s->sizes[TSIM_NDOF_R];
-    CK(cudaMallocAsync(&scratch, 2 * nvec * sizeof(double) + 16 + (size_t)T * B * sizeof(int), st));
-    a.vjp_y = (double*)scratch;
+    CK(scratch_alloc(&scratch.p, 2 * nvec * sizeof(double) + 16 + (size_t)T * B * sizeof(int), s->device, st));
+    a.vjp_y = (double*)scratch.p;
     a.vjp_c = a.vjp_y + nvec;
     a.work_counter = (unsigned*)(a.vjp_c + nvec);
     a.vjp_list = (int*)(a.work_counter + 4);
@@ -776,7 +804,6 @@ int tsim_backward(const tsim_scene* s, int32_t B, int32_t T, const double* q_tra
   CK(cudaEventRecord(s->ev[5], st));
   TS_LAUNCH(bwd_kernel, grid, smem, smem, TS_BPS, s->d_ib, s->ni, s->d_db, s->nd, a);
   CK(cudaEventRecord(s->ev[6], st));
-  if (scratch) CK(cudaFreeAsync(scratch, st));
   return 0;
 }
 

@@ -53,6 +53,30 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   const int npoints = ib[TS_I_NPOINTS];
   const int integrator = ib[TS_I_INTEGRATOR];
   if (integrator < TS_INT_BDF1 || integrator > TS_INT_SDIRK2) return "unknown integrator";
+  // The blob comes through the public C ABI: every count and every section [offset, offset + count * stride) is checked
+  // against the two buffers before anything is indexed (a truncated or stale blob must fail here, not read out of bounds).
+  {
+    if (nj < 0 || n < 0 || nu < 0 || nee < 0 || nmark < 0 || nground < 0 || ngp < 0 || nact < 0 || nsens < 0 || npoints < 0)
+      return "malformed scene blob (negative count)";
+    struct Sec { int off_slot; long long count, stride; bool dbl; const char* what; };
+    const Sec secs[] = {
+      {TS_I_OFF_JOINT, nj, TS_JI_STRIDE, false, "joint records"}, {TS_I_OFF_GROUND, nground, TS_GI_STRIDE, false, "ground contact records"},
+      {TS_I_OFF_GP, ngp, TS_PI_STRIDE, false, "general-primitive contact records"}, {TS_I_OFF_ACT, nact, TS_AI_STRIDE, false, "actuator records"},
+      {TS_I_OFF_EE, nee, TS_EI_STRIDE, false, "end-effector records"}, {TS_I_OFF_SENSOR, nsens, si_stride, false, "sensor records"},
+      {TS_I_DOFF_JOINT, nj, TS_JD_STRIDE, true, "joint data"}, {TS_I_DOFF_GROUND, nground, TS_CD_STRIDE, true, "ground contact data"},
+      {TS_I_DOFF_GP, ngp, TS_CD_STRIDE, true, "general-primitive contact data"}, {TS_I_DOFF_ACT, nact, TS_AD_STRIDE, true, "actuator data"},
+      {TS_I_DOFF_EE, nee, TS_ED_STRIDE, true, "end-effector data"}, {TS_I_DOFF_SENSOR, nsens, TS_SD_STRIDE, true, "sensor data"},
+      {TS_I_DOFF_POINTS, npoints, 3, true, "contact points"}, {TS_I_DOFF_MARKERS, nmark, 3, true, "marker positions"}};
+    for (const Sec& c : secs) {
+      const long long off = ib[c.off_slot], lim = c.dbl ? nd : ni;
+      if (c.count == 0) continue;
+      if (off < (c.dbl ? (long long)TS_D_HEADER : (long long)TS_I_HEADER) || off + c.count * c.stride > lim)
+        return std::string("malformed scene blob (") + c.what + " out of range)";
+    }
+    if (ib[TS_I_DOFF_MARKER_AXES] != 0 && (ib[TS_I_DOFF_MARKER_AXES] < TS_D_HEADER || (long long)ib[TS_I_DOFF_MARKER_AXES] + 9ll * nmark > nd))
+      return "malformed scene blob (marker axes out of range)";
+    if (nd < TS_D_HEADER) return "malformed scene blob (double header)";
+  }
   if (integrator != TS_INT_BDF1 && !KT_MULTISTEP) return "scene exceeds the compiled capacity (BDF2 / SDIRK2 integrators)";
   if (nj > KT_MAXB) return "scene exceeds the compiled capacity (bodies)";
   if (n > KT_MAXN || nu > KT_MAXU) return "scene exceeds the compiled capacities (dofs/controls)";
@@ -64,7 +88,7 @@ inline std::string lower_scene(const int* ib, long long ni, const double* db, lo
   int nmj = 0;
   for (int j = 0; j < nj; ++j) {
     const int jt = J[j * TS_JI_STRIDE], par = J[j * TS_JI_STRIDE + 1];
-    if (par >= j) return "joints are not in parent-first order";
+    if (par >= j || par < -1) return "joints are not in parent-first order";
     if ((jt == TS_JT_FREE3D_EULER || jt == TS_JT_SPHERICAL_EULER) && !KT_FREE3D) return "scene exceeds the compiled capacity (free3d-euler / spherical-euler joints)";
     if ((jt == TS_JT_FREE3D_EXP || jt == TS_JT_SPHERICAL_EXP) && !KT_EXP3D) return "scene exceeds the compiled capacity (free3d-exp / spherical-exp joints)";
     if (jt == TS_JT_FREE2D && !KT_FREE3D) return "scene exceeds the compiled capacity (free2d joints)";

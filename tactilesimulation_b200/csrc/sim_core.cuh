@@ -1835,10 +1835,12 @@ HDN void mass_column(const SceneView& S, const WK& W, const double* qv, int k, d
 
 // ||g(x + alpha dx)|| by a value-only evaluation (plain per-lane work space) that a SUB-TILE of the tile's lanes runs
 // for itself: the sub-tiles of a tile evaluate different step lengths of a struggling line search at the same time.
-// TS_LS_SUB = 1: every lane alone (one-lane policy).  TS_LS_SUB = 4 (the 16-lane variants): four lanes per step length
-// repeat the same value arithmetic and share the contact DETECTION of the evaluation (dealt to the lanes, gathered by
-// ballot, as in the full evaluation): the scenes of those variants test hundreds of sampled points per force
-// (DClaw: 3 x 217), which one lane alone took longer than a whole round of the block.
+// TS_LS_SUB = 1 (default): every lane alone (one-lane policy).  TS_LS_SUB = 4: four lanes per step length repeat the same
+// value arithmetic and share the contact DETECTION of the evaluation (dealt to the lanes, gathered by ballot) -- the
+// scenes of the 16-lane variants test hundreds of sampled points per force (DClaw: 3 x 217).  MEASURED SLOWER on B200
+// (forward call: DClaw B=2048 T=200 691 -> 798 ms, TactileInsertion B=1024 T=45 675 -> 904 ms, StableGrasp 719 -> 981 ms):
+// a struggling search accepts a step length many halvings down, and four step lengths per pass instead of sixteen
+// means more passes.
 template <class SubTile>
 HDN double trial_norm(const SubTile& solo, const SceneView& S, const TileState& ts, double alpha, int mode) {
   const int n = S.n;
@@ -1991,7 +1993,7 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
         bool found = false;
         TS_CPT0();
 #ifndef TS_LS_SUB
-#define TS_LS_SUB (TS_MAXN > 8 ? 4 : 1)
+#define TS_LS_SUB 1
 #endif
         const int NBMAX = L / TS_LS_SUB > 0 ? L / TS_LS_SUB : 1;     // step lengths evaluated at once
         while (v.trial < S.max_ls) {

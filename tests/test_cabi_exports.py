@@ -63,3 +63,29 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "redmax_oracle" not in text, f
                 assert "tests.emu" not in text and "libtsim_emu" not in text, f
+
+
+def test_scene_create_rejects_truncated_and_corrupted_blobs():
+    """lower_scene validates every count and section of the blob against the buffer sizes before indexing it."""
+    import numpy as np
+    from tactilesimulation_b200 import _lib
+    lib = _lib.load()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pusher13x10_stepsim_s0.npz"))
+    ib0, db0 = g["ibuf"].astype(np.int32), g["dbuf"].astype(np.float64)
+
+    def create(ib, db):
+        h = ctypes.c_void_p()
+        rc = lib.tsim_scene_create(ib.ctypes.data, ib.size, db.ctypes.data, db.size, 0, ctypes.byref(h))
+        return rc, lib.tsim_last_error()
+    rc, msg = create(ib0, np.ascontiguousarray(db0[: db0.size // 2]))            # truncated double buffer
+    assert rc != 0 and b"malformed scene blob" in msg
+    rc, msg = create(np.ascontiguousarray(ib0[:40]), db0)                          # truncated int buffer
+    assert rc != 0 and b"malformed scene blob" in msg
+    ib = ib0.copy()
+    ib[2] = -3                                                                    # negative joint count
+    rc, msg = create(ib, db0)
+    assert rc != 0 and b"malformed scene blob" in msg
+    ib = ib0.copy()
+    ib[24] = 10 ** 8                                                              # joint data offset past the buffer
+    rc, msg = create(ib, db0)
+    assert rc != 0 and b"malformed scene blob" in msg
