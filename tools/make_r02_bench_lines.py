@@ -4,7 +4,8 @@ import os
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-FILES = [("i_bench.json", "headline, 1 GPU: `python bench.py --steps 5 --warmup 3`"),
+FILES = [("i_bench.json", "headline, 1 GPU: `python bench.py --gpus 1 --steps 20 --warmup 5` (the driver's flags)"),
+         ("fin_ref.json", "reference arm: `python bench.py --impl reference --gpus 1 --steps 20 --warmup 5`"),
          ("h_bench_push_fwd.json", "configs[1]: `python bench.py --workload push_fwd --steps 5 --warmup 3`"),
          ("h_bench_dclaw.json", "configs[3]: `python bench.py --workload dclaw --steps 5 --warmup 3`"),
          ("h_bench_insertion.json", "configs[4] on 1 GPU (B=1024): `python bench.py --workload insertion --steps 5 --warmup 3`"),
