@@ -218,3 +218,51 @@ def test_batched_dclaw_frontend_matches_the_reference_env(torque):
         assert rel_err(o_new[:, 18:], rec[e]["obs"][:, 18:]) <= 1e-6, e                # tactile flow images
         assert np.allclose(np.array([r[e] for r in rews]), rec[e]["rew"], rtol=1e-7, atol=1e-9), e
         assert [(bool(d[e]), bool(s_[e])) for d, s_ in dones] == rec[e]["done"], e
+
+
+def test_batched_stable_grasp_frontend_matches_the_reference_env():
+    """BatchedStableGraspEnv against the UNMODIFIED R/envs/stable_grasp_env.py on the reference module: B = 3 bars with
+    their own box densities (read back from the reference env's seeded reset), the first grasp and two more with given
+    actions: observations, rewards, success."""
+    _need_ref()
+    torch.set_default_dtype(torch.float64)          # (the env builds its targets with default-dtype tensors, see the insertion test)
+    try:
+        from tactilesimulation_b200.envs import BatchedStableGraspEnv
+        from tactilesimulation_b200.redmax import Simulation
+        ns = rc.load(rc.reference_module())
+        B = 3
+        rng = np.random.RandomState(9)
+        acts = rng.uniform(-1, 1, (2, B, 1))
+        rec = []
+        for e in range(B):
+            env = ns.gym.make("StableGrasp-v1", use_torch=True, observation_type="tactile_flatten", render_tactile=False)
+            env.seed(70 + e)
+            env.unwrapped.render = lambda *a, **k: None          # (the env opens the viewer when an episode succeeds)
+            obs = [env.reset().detach().numpy().copy()]
+            dens = env.unwrapped.block_densitys.copy()
+            rews, succ = [float(env.unwrapped.reward_buf)], [bool(env.unwrapped.is_success)]
+            for k in range(2):
+                o, r, d, info = env.step(torch.tensor(acts[k, e]))
+                obs.append(o.detach().numpy().copy())
+                rews.append(float(r))
+                succ.append(bool(info["success"]))
+            rec.append(dict(dens=dens, obs=np.stack(obs), rew=np.array(rews), succ=succ, q0=env.unwrapped.qpos_init_reference.numpy().copy()))
+        xml = os.path.join(rc.PY_DIR, "envs", "assets", "stable_grasp", "stable_grasp.xml")
+        benv = BatchedStableGraspEnv(Simulation(xml, batch=B), observation_type="tactile_flatten")
+        assert rel_err(benv.qpos_init_reference[0].cpu().numpy(), rec[0]["q0"]) <= 1e-8
+        benv.qpos_init_reference = torch.tensor(np.stack([r["q0"] for r in rec]), device=benv.device)      # same start (see the insertion test)
+        obs = [benv.reset(block_densitys=np.stack([r["dens"] for r in rec]))]
+        rews, succ = [benv.reward_buf.cpu().numpy()], [benv.is_success.cpu().numpy()]
+        for k in range(2):
+            o, r, d, info = benv.step(torch.tensor(acts[k]))
+            obs.append(o)
+            rews.append(r.cpu().numpy())
+            succ.append(info["success"].cpu().numpy())
+        for e in range(B):
+            o_new = np.stack([o[e].cpu().numpy() for o in obs])
+            assert o_new.shape == rec[e]["obs"].shape == (3, 520)
+            assert rel_err(o_new, rec[e]["obs"]) <= 1e-6, e
+            assert np.allclose(np.array([r[e] for r in rews]), rec[e]["rew"], rtol=1e-6, atol=1e-9), e
+            assert [bool(s_[e]) for s_ in succ] == rec[e]["succ"], e
+    finally:
+        torch.set_default_dtype(torch.float32)
