@@ -1,10 +1,10 @@
 // sm_100a kernels + C ABI (include/tactilesim_b200.h) of the B200 tactile simulator.
 //
 // Execution model: one environment per TILE of LPE lanes (8/16/32) of a warp, one persistent
-// tile per environment for all T steps of a call (state stays in registers across steps, the
-// scene blob is staged once per CTA in shared memory).  Lane k of a tile owns reduced
+// tile per environment for all T steps of a call (the tile-uniform state lives in shared memory, the
+// scene tables are staged once per CTA in shared memory).  Lane k of a tile owns reduced
 // coordinate k: it carries the Dual tangent along q_k through the matrix-free residual, holds
-// column k of the Newton matrix for the shuffle-based pivoted LU, and strides over tactile
+// column k / row k of the Newton matrix for the shuffle-based LU, and strides over tactile
 // markers / contact points in the readout and adjoint passes.  See sim_core.cuh.
 //
 // A forward call is three kernels and a backward call three launches: only what is sequential per environment (the
@@ -12,6 +12,13 @@
 // what depends on the recorded trajectory only -- tactile read-out (tac_kernel), the G0 / G1 blocks of the tape
 // (tape_kernel), the pull-back of the readout cotangents (vjp_kernel, two phases) -- runs over all T x B env-steps in
 // persistent kernels that draw env-steps from a work counter.
+//
+// fwd_kernel: the warps of a block advance evaluation round by evaluation round together (one block-wide vote per
+// round: the residual code is ~110 KB, an SM cannot fetch it for seven warps at seven places), the tiles advance
+// through their time steps independently, and (variant 8) the active contact points of the whole block are evaluated
+// by all its tiles together (gp_points_coop: DevTile<LPE, COOP = true>, CoopArea in shared memory).
+// Every kernel exists once more per variant with per-environment parameter tables (template parameter PE,
+// tsim_scene_set_env_scenes).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
