@@ -10,5 +10,4 @@ for w in push_fwd dclaw insertion stepsim; do
   timeout 900 python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/h_bench_$w.json 2> gpurun_out/h_bench_$w.err
 done
 python tools/make_r02_bench_lines.py | sed -n 3,12p | cut -c1-330
-( bash tools/gpu_variants.sh 200 3 tactilesimulation_b200/libtactilesim_b200.so tactilesimulation_b200/_variants/blk256.so ) > gpurun_out/fin_variants.txt 2>&1; cat gpurun_out/fin_variants.txt
 bash tools/gpu_ncu_r02.sh
