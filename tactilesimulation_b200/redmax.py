@@ -479,6 +479,39 @@ class Simulation:
         self._carry = None
         return out
 
+    def backward_last_frame_t(self, num_backward_steps: int, df_dq, df_dvar, df_dtactile):
+        """``backward_steps`` for the StepSimFunction shape (R/envs/redmax_torch_functions.py:147-174): cotangents [batch, *]
+        on the LAST of the ``num_backward_steps`` sub-steps only.  The reference pads them with zeros to
+        ``num_steps`` frames; here the kernel's row maps say which step has a cotangent, so no [T, B, 3M] zero tensor is
+        built per gym step.  Same result as ``backward_steps_t`` with the padded tensors."""
+        ns = int(num_backward_steps)
+        hi = self._current_backward_step
+        lo = hi - ns
+        ch = self._chunks[-1] if self._chunks else None
+        for c in reversed(self._chunks):
+            if c.start <= lo and hi <= c.start + c.T:
+                ch = c
+                break
+        if hi <= 0 or lo < 0 or ch is None or not (ch.start == lo and ch.start + ch.T == hi):
+            # general case (the sweep crosses forward() calls): pad like the reference and take the general path
+            def pad(c, width):
+                if c is None or width == 0:
+                    return None
+                full = torch.zeros((ns, self.batch, width), dtype=torch.float64, device=self.device)
+                full[-1] = c.reshape(self.batch, width)
+                return full
+            return self.backward_steps_t(ns, pad(df_dq, self.ndof_r), pad(df_dvar, self.ndof_var), pad(df_dtactile, self.ndof_tactile))
+        if self._carry is None:
+            self._carry = torch.zeros((self.batch, 2, self.ndof_r), dtype=torch.float64, device=self.device)
+        last = [-1] * (ns - 1) + [0]
+        one = lambda c, width: None if (c is None or width == 0) else c.reshape(1, self.batch, width).contiguous()
+        f = ch.fwd
+        res = self.core.backward(dict(q_traj=f["q_traj"], qd_traj=f["qd_traj"], tape=f["tape"]), ch.u, ns,
+                                 one(df_dq, self.ndof_r), one(df_dvar, self.ndof_var), one(df_dtactile, self.ndof_tactile),
+                                 dq_rows=last, dvar_rows=last, dtac_rows=last, carry=self._carry, want_q0=False)
+        self._current_backward_step = lo
+        return res["df_du"]
+
     def backward_steps_t(self, num_backward_steps: int, df_dq, df_dvar, df_dtactile):
         """The last ``num_backward_steps`` not yet swept steps (Simulation::backward_steps)."""
         if self._current_backward_step <= 0:

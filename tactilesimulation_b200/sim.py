@@ -56,6 +56,7 @@ class BatchedSim:
         self.lanes = None
         self.options = {}
         self.env_batch = 0
+        self._row_cache = {}
         if lanes is not None:
             self.set_lanes(lanes)
 
@@ -118,8 +119,15 @@ class BatchedSim:
             r = torch.as_tensor(np.asarray(rows, dtype=np.int32))
         if r.numel() != T:
             raise _lib.TactileSimError("row map must have one entry per step")
-        mx = int(r.max().item()) if r.numel() else -1
-        return r.to(self.device), max(mx + 1, 0)
+        # (the same few maps come back every gym step of a StepSimFunction loop: keep their device copies)
+        key = tuple(r.tolist())
+        hit = self._row_cache.get(key)
+        if hit is None:
+            if len(self._row_cache) > 64:
+                self._row_cache.clear()
+            hit = (r.to(self.device), max((max(key) if key else -1) + 1, 0))
+            self._row_cache[key] = hit
+        return hit
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -50,14 +50,12 @@ class StepSimFunction(autograd.Function):
         sim, ns = ctx.sim, ctx.num_steps
         dev = sim.device
 
-        def last_only(c, width):
+        def cot(c, width):
             if width == 0 or c is None:
                 return None
-            full = torch.zeros((ns, sim.batch, width), dtype=torch.float64, device=dev)
-            full[-1] = c.detach().to(device=dev, dtype=torch.float64).reshape(sim.batch, width)
-            return full
-        df_du = sim.backward_steps_t(ns, last_only(df_dq, sim.ndof_r), last_only(df_dvar, sim.ndof_var),
-                                     last_only(df_dtactile, sim.ndof_tactile))
+            return c.detach().to(device=dev, dtype=torch.float64).reshape(sim.batch, width)
+        # cotangents live on the last sub-step only: the row maps of the kernel say so (no zero-padded [ns, B, 3M] tensors)
+        df_du = sim.backward_last_frame_t(ns, cot(df_dq, sim.ndof_r), cot(df_dvar, sim.ndof_var), cot(df_dtactile, sim.ndof_tactile))
         if not ctx.grad_actions:
             return None, None, None, None
         return df_du.sum(dim=0).to(ctx.in_dtype), None, None, None
