@@ -319,6 +319,21 @@ struct WorkSplit {
   HD void put(int j, int o, const Dual& x) { sv[j * WK_REC + o] = x.v; dt[j][o] = x.d; }
   HD Frames& frames() { return *fr; }
 };
+// ... or values only, kept once per tile in the same shared region (the tactile read-out pass: kinematics of a recorded
+// state without derivatives -- a third of the arithmetic of the dual-number work space and no local-memory tangents)
+struct WorkSharedV {
+  typedef double Scalar;
+  double* sv;
+  Frames* fr;
+  TileState* ts;
+  double beta;
+  int gp_any;
+  HD TileState& state() { return *ts; }
+  HD double get(int j, int o) const { return sv[j * WK_REC + o]; }
+  HD double getv(int j, int o) const { return sv[j * WK_REC + o]; }
+  HD void put(int j, int o, double x) { sv[j * WK_REC + o] = x; }
+  HD Frames& frames() { return *fr; }
+};
 template <class WK, class T> HD void wk_ld(const WK& W, int j, int o, int n, T* out) {
   for (int i = 0; i < n; ++i) out[i] = W.get(j, o + i);
 }
@@ -2942,6 +2957,28 @@ HDN bool env_vjp(const Tile& tl, const SceneView& S, const BwdArgs& a, long long
   return false;
 }
 
+// kinematics of the state held in (ts.xq, ts.xv) + tactile field.  Generic work space: the evaluation's own scalar type
+// with zero tangents (host harness); the GPU's split work space: VALUES ONLY in the tile's shared region (WorkSharedV).
+template <class Tile, class WK>
+HD void tactile_of_state(const Tile& tl, const SceneView& S, TileState& ts, WK& WD, double* tac_o, int* mb_o, bool prezeroed) {
+  SeedIn in;
+  in.xq = ts.xq; in.xv = ts.xv; in.xl = ts.xv;     // dl is not read by the kinematics-only pass
+  in.k = -1; in.tq = 0.0; in.tv = 0.0; in.tl = 0.0;
+  in.q0v = ts.xq; in.qd0v = ts.xv; in.tq0 = 0.0; in.tqd0 = 0.0;
+  kinematics(S, in, WD, false);
+  tactile_values(tl, S, WD, tac_o, mb_o, prezeroed);
+}
+template <class Tile>
+HD void tactile_of_state(const Tile& tl, const SceneView& S, TileState& ts, WorkSplit& WD, double* tac_o, int* mb_o, bool prezeroed) {
+  WorkSharedV WV;
+  WV.sv = WD.sv; WV.fr = WD.fr; WV.ts = WD.ts; WV.beta = 0.0; WV.gp_any = 0;
+  ArrIn<double> in;
+  in.q_ = ts.xq; in.qd_ = ts.xv; in.dl_ = ts.xv;
+  in.q0_ = ts.xq; in.qd0_ = ts.xv;
+  kinematics(S, in, WV, false);
+  tactile_values(tl, S, WV, tac_o, mb_o, prezeroed);
+}
+
 // Tactile field of ONE env-step (item = t * B + env) from the recorded trajectory: the readout pass of tsim_forward.
 // Same code and work space as the readout at the end of a step (kinematics of the state, then tactile_values), so the
 // field is the same value for value; it only runs where the whole GPU can share it instead of inside the step loop,
@@ -2956,14 +2993,9 @@ HDN void env_tactile(const Tile& tl, const SceneView& S, const FwdArgs& a, long 
   TileState& ts = WD.state();
   tl.tile_sync();
   for (int i = 0; i < TS_MAXN; ++i) { ts.xq[i] = (i < n) ? a.q_traj[item * n + i] : 0.0; ts.xv[i] = (i < n) ? a.qd_traj[item * n + i] : 0.0; }
-  SeedIn in;
-  in.xq = ts.xq; in.xv = ts.xv; in.xl = ts.xv;     // dl is not read by the kinematics-only pass
-  in.k = -1; in.tq = 0.0; in.tv = 0.0; in.tl = 0.0;
-  in.q0v = ts.xq; in.qd0v = ts.xv; in.tq0 = 0.0; in.tqd0 = 0.0;
   tl.tile_sync();
-  kinematics(S, in, WD, false);
-  tactile_values(tl, S, WD, a.tac_out + ((long long)tr * B + env) * 3 * S.nmark,
-                 a.marker_body ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0, a.tac_prezeroed != 0);
+  tactile_of_state(tl, S, ts, WD, a.tac_out + ((long long)tr * B + env) * 3 * S.nmark,
+                   a.marker_body ? a.marker_body + ((long long)tr * B + env) * S.nmark : (int*)0, a.tac_prezeroed != 0);
 }
 
 // Adjoint blocks G0 = dg/dq0, G1 = dg/dqdot0 and the control gains of ONE env-step (item = t * B + env) from the recorded
