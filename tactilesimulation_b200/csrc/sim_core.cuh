@@ -1116,9 +1116,10 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
   int cnt = 0;
   if (mine) for (int w = 0; w < KT_MAXPW; ++w) cnt += __popc(act[w]);
   TS_CPT0();
-  if (!tl.cta_or_unaligned(cnt > 0)) return false;              // nobody in this block touches: one barrier
+  // (the counts are published before the vote: its barrier orders them; nobody reads cnt[] of a phase after that
+  // phase's publish barrier, so the next phase may overwrite it)
   if (lane == 0) C.cnt[my] = cnt;
-  tl.cta_sync_unaligned();
+  if (!tl.cta_or_unaligned(cnt > 0)) return false;              // nobody in this block touches: one barrier
   int off = 0, total = 0;
 #pragma unroll
   for (int t = 0; t < CA::NT; ++t) {
@@ -1676,6 +1677,49 @@ HD bool lu_rows_solve(const Tile& tl, double* a, double b, double* x) {
   return tl.ballot(exch) != 0u;
 }
 
+// The same elimination with the pivot rows travelling through the tile's shared scratch instead of shuffles (a double
+// shuffle is two 32-bit shuffles plus packing: ~5 instructions against one shared-memory load): scr holds two pivot-row
+// buffers of TS_MAXN + 1 doubles (row + right-hand side, alternating between steps) and TS_MAXN solution slots.
+// Same operations on the same numbers as lu_rows_solve: bit-identical results.
+template <class Tile>
+HD bool lu_rows_solve_smem(const Tile& tl, double* a, double b, double* x, double* scr) {
+  bool exch = false;
+  double* xs = scr + 2 * (TS_MAXN + 1);
+#pragma unroll
+  for (int j = 0; j < TS_MAXN; ++j) {
+    double* pr = scr + (j & 1) * (TS_MAXN + 1);
+    if (tl.lane == j) {
+#pragma unroll
+      for (int c = j; c < TS_MAXN; ++c) pr[c] = a[c];
+      pr[TS_MAXN] = b;
+    }
+    tl.tile_sync();
+    const double pjj = pr[j];
+    const bool below = tl.lane > j;
+    exch = exch || (below && fabs(a[j]) > fabs(pjj));
+    const double l = a[j] / pjj;
+#pragma unroll
+    for (int c = j + 1; c < TS_MAXN; ++c) {
+      const double pjc = pr[c];
+      if (below) a[c] -= l * pjc;
+    }
+    const double bj = pr[TS_MAXN];
+    if (below) b -= l * bj;
+  }
+#pragma unroll
+  for (int k = TS_MAXN - 1; k >= 0; --k) {
+    if (tl.lane == k) xs[k] = b / a[k];
+    tl.tile_sync();
+    const double xk = xs[k];
+    x[k] = xk;
+    if (tl.lane < k) b -= a[k] * xk;
+  }
+  return tl.ballot(exch) != 0u;
+}
+#ifndef TS_LU_SMEM
+#define TS_LU_SMEM 1
+#endif
+
 HD double norm_n(const double* v, int n) {
   double s = 0.0;
   for (int i = 0; i < n; ++i) s += v[i] * v[i];
@@ -2083,7 +2127,12 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     for (int c = 0; c < TS_MAXN; ++c) a[c] = (tl.lane < TS_MAXN) ? Hs[tl.lane * TS_MAXN + c] : 0.0;
     double bsel = 0.0;
     for (int i = 0; i < TS_MAXN; ++i) if (i == tl.lane && i < n) bsel = -ge[i];
+#if TS_LU_SMEM
+    tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
+    solved = !lu_rows_solve_smem(tl, a, bsel, dx, Hs);
+#else
     solved = !lu_rows_solve(tl, a, bsel, dx);
+#endif
     tl.tile_sync();
   }
   if (!solved) {
@@ -2547,7 +2596,13 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
     double a[TS_MAXN];
     for (int c = 0; c < TS_MAXN; ++c)
       a[c] = (tl.lane < n && c < n) ? tape[c * n + tl.lane] : ((c == tl.lane) ? 1.0 : 0.0);
+#if TS_LU_SMEM
+    tl.tile_sync();
+    solved = !lu_rows_solve_smem(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
+    tl.tile_sync();
+#else
     solved = !lu_rows_solve(tl, a, (tl.lane < n) ? y[0] : 0.0, z);
+#endif
   }
   if (!solved) {
     // replicated pivoting solve: gather y; the lane owning dof k loads row k of H = column k of H^T
