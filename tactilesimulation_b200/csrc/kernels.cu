@@ -513,6 +513,9 @@ static int prep(K kern, size_t smem, int bps = TS_BPS) {
 #ifndef TS_NO_CARVEOUT
   int pct = (int)((smem + 1024) * bps * 100 / (228 * 1024)) + 1;
   if (pct > 100) pct = 100;
+#ifdef TS_FORCE_CARVEOUT
+  pct = TS_FORCE_CARVEOUT;               // A/B builds: how much the L1 left beside the shared memory matters
+#endif
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
 #endif
   return 0;

@@ -1095,14 +1095,24 @@ template <bool COOP> struct CoopTag {};
 #define TS_GP_ILP 1
 #endif
 #if defined(TS_COOP_GP) && defined(__CUDACC__)
+// Shared-memory budget: the step loop's block holds the scene tables, 28 tile regions (96 KB) and this area; with at
+// most TS_COOP_SLOTS = 22 publishers per phase (of 28 tiles; on average 8 are in contact) and byte-sized point lists the
+// block stays below the 164 KB shared-memory configuration, which leaves 92 KB of L1 for the per-lane tangents in local
+// memory instead of 60 KB (forcing the L1 down to 28 KB cost 7 %, profiles/r02_experiments.md).  A tile beyond the
+// slots (never seen in the bench workload) takes part in the barriers and in the work and sums its own points serially.
+#ifndef TS_COOP_SLOTS
+#define TS_COOP_SLOTS 22
+#endif
 template <int LPE> struct CoopArea {
   static const int NT = TS_BLOCK / LPE;           // tiles per block = items per batch
+  static const int NS = TS_COOP_SLOTS < NT ? TS_COOP_SLOTS : NT;   // publishers per phase
+  static const int MAXP = KT_MAXPW * 32;          // sampled points of a general body (fits a byte: static_assert below)
   int cnt[NT];                                   // active points of each tile for the force in flight
-  int off[NT];                                   // first item of each publishing tile
-  unsigned char owner[NT * KT_MAXPW * 32];       // publishing tile of each item
-  unsigned short pts[NT][KT_MAXPW * 32];         // active point indices of each tile, ascending
-  double Pv[NT][48];                             // values: Q rr w1b v1b ph2 (24), then R1v p1v R2v p2v (24)
-  double Pt[NT][24][LPE];                        // tangents of the first 24, by component and lane
+  int soff[NS];                                  // first item of each publisher (slot)
+  unsigned char owner[NS * MAXP];                // slot of each item
+  unsigned char pts[NS][MAXP];                   // active point indices of each slot, ascending
+  double Pv[NS][48];                             // values: Q rr w1b v1b ph2 (24), then R1v p1v R2v p2v (24)
+  double Pt[NS][24][LPE];                        // tangents of the first 24, by component and lane
   double Rv[NT][9];                              // per-item terms tq2, Fb, tq1: values ...
   double Rt[NT][9][LPE];                         // ... and tangents by lane
 };
@@ -1111,6 +1121,7 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
                                                bool mine, int po, const double* hs, double kn, double kt, double mu,
                                                double damp, T* w1, T* w2) {
   typedef CoopArea<Tile::LPE> CA;
+  static_assert(CA::MAXP <= 256, "point indices of the cooperative lists are bytes");
   CA& C = *(CA*)tl.coop;
   const int my = tl.tile_id, lane = tl.lane;
   int cnt = 0;
@@ -1120,28 +1131,30 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
   // phase's publish barrier, so the next phase may overwrite it)
   if (lane == 0) C.cnt[my] = cnt;
   if (!tl.cta_or_unaligned(cnt > 0)) return false;              // nobody in this block touches: one barrier
-  int off = 0, total = 0;
+  // publishers in tile order take the slots; off / total count the items of the publishers only
+  int off = 0, total = 0, slot = -1, nsl = 0;
 #pragma unroll
   for (int t = 0; t < CA::NT; ++t) {
     const int c = C.cnt[t];
-    if (t == my) off = total;
-    total += c;
+    const bool pub = c > 0 && nsl < CA::NS;
+    if (t == my) { off = total; slot = pub ? nsl : -1; }
+    if (pub) { total += c; ++nsl; }
   }
-  if (cnt > 0) {
+  if (slot >= 0) {
     if (lane == 0) {
-      C.off[my] = off;
+      C.soff[slot] = off;
       int r = 0;
       for (int w = 0; w < KT_MAXPW; ++w) {
         unsigned m = act[w];
-        while (m) { C.owner[off + r] = (unsigned char)my; C.pts[my][r++] = (unsigned short)(32 * w + ts_ffs(m)); m &= m - 1; }
+        while (m) { C.owner[off + r] = (unsigned char)slot; C.pts[slot][r++] = (unsigned char)(32 * w + ts_ffs(m)); m &= m - 1; }
       }
     }
     const T* pt = P.Q;                            // Q rr w1b v1b ph2: 24 contiguous scalars
     const double* pv = P.R1v;                     // R1v p1v R2v p2v: 24 contiguous doubles
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
-      C.Pt[my][i][lane] = tan_of(pt[i]);
-      if (lane == (i % Tile::LPE)) { C.Pv[my][i] = val(pt[i]); C.Pv[my][24 + i] = pv[i]; }
+      C.Pt[slot][i][lane] = tan_of(pt[i]);
+      if (lane == (i % Tile::LPE)) { C.Pv[slot][i] = val(pt[i]); C.Pv[slot][24 + i] = pv[i]; }
     }
   }
   tl.cta_sync_unaligned();
@@ -1151,8 +1164,8 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
     TS_CPN(tl, 10, 1);
     const int item = base + my;
     if (item < total) {
-      const int src = C.owner[item];              // publisher of the item
-      const int k = C.pts[src][item - C.off[src]];
+      const int src = C.owner[item];              // publisher (slot) of the item
+      const int k = C.pts[src][item - C.soff[src]];
       GpPair<T> Q;
       T* qt = Q.Q;
       double* qv = Q.R1v;
@@ -1173,7 +1186,7 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
     TS_CPT(tl, 12);
     tl.cta_sync_unaligned();
     TS_CPT(tl, 13);
-    if (cnt > 0) {
+    if (slot >= 0) {
       const int lo = off > base ? off : base, hi = (off + cnt < base + CA::NT) ? off + cnt : base + CA::NT;
       // (two items per pass: the loads of the second overlap the sums of the first; the order of the sums is unchanged)
       int it = lo;
@@ -1197,7 +1210,7 @@ __device__ __forceinline__ bool gp_points_coop(const Tile& tl, CoopTag<true>, co
     tl.cta_sync_unaligned();
     TS_CPT(tl, 13);
   }
-  return cnt > 0;
+  return slot >= 0;                               // false: no points, or no slot left -> the caller's serial loop
 }
 #endif
 template <class Tile, class T>
