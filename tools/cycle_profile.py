@@ -6,20 +6,29 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 from bench import make_inputs
 from tactilesimulation_b200.sim import BatchedSim
-g = np.load(os.path.join(ROOT, "tests", "golden", "pusher32x13_episodic_s0.npz"))
-sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=8)
+CASE = os.environ.get("PCASE", "pusher32x13_episodic_s0")       # PCASE / PLANES: another scene (16-lane variants)
+LANES = int(os.environ.get("PLANES", 8))
+g = np.load(os.path.join(ROOT, "tests", "golden", CASE + ".npz"))
+sim = BatchedSim((g["ibuf"], g["dbuf"]), "cuda:0", lanes=LANES)
 dev = sim.device
 B, T = int(os.environ.get('PB', 4096)), int(os.environ.get('PT', 50))
-nthreads = ((B * 8 + 223) // 224) * 224
+NT = 224 // LANES
+nthreads = ((B * LANES + 223) // 224) * 224
 prof = torch.zeros((nthreads, 16), dtype=torch.int64, device=dev)
-sim.lib.tsim_debug_set_prof_v8(ctypes.c_void_p(prof.data_ptr()))
-q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
-ut = torch.tensor(u, device=dev)
+getattr(sim.lib, "tsim_debug_set_prof_v%d" % (8 if LANES == 8 else 16))(ctypes.c_void_p(prof.data_ptr()))
+if LANES == 8:
+    q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
+    ut = torch.tensor(u, device=dev)
+else:
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from perf_probe import inputs
+    q0, qd0, ut = inputs(g, B, T, dev)
+    q0, qd0 = q0.cpu().numpy(), qd0.cpu().numpy()
 for rep in range(3):
     q, qd = torch.tensor(q0, device=dev), torch.tensor(qd0, device=dev)
     out = sim.forward(q, qd, ut, T, grad=True)
     torch.cuda.synchronize()
-p = prof.cpu().numpy().reshape(-1, 28, 8, 16)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
+p = prof.cpu().numpy().reshape(-1, NT, LANES, 16)[:, :, 0, :]      # [block, tile, slot] lane 0 of each tile
 names = ["kinematics+dyn", "ground", "gp", "inward", "vote wait", "step_round total", "epilogue", "kernel total"]
 tot = p[:, :, 7].astype(float)
 bt = tot.max(axis=1)
@@ -32,6 +41,9 @@ for i, nm in enumerate(names):
 b = int(tot.mean(axis=1).argmax())
 print("slowest block", b, {nm: float(p[b, :, i].mean()) for i, nm in enumerate(names)})
 
+v = p[:, :, 15].astype(float)
+print("batched line search mean %.4g (%5.1f%% of kernel) max-tile %.4g; in the slowest block: mean %.4g max-tile %.4g of %.4g" % (
+    v.mean(), 100 * v.mean() / tot.mean(), v.max(), v[b].mean(), v[b].max(), tot[b].max()))
 # cooperative contact-point phase (slots 8..14)
 if p[:, :, 9].sum() > 0:
     ph = p[:, 0, 9].astype(float)          # phases with items, per block (tile 0)
