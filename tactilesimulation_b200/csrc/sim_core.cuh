@@ -1729,6 +1729,64 @@ HD bool lu_rows_solve_smem(const Tile& tl, double* a, double b, double* x, doubl
   }
   return tl.ballot(exch) != 0u;
 }
+
+#if TS_MAXN > 8
+// Row-owner elimination WITH partial pivoting (16-dof variants): the rows stay in their lanes and carry their current
+// position; step j takes the row of maximal |a_j| among the positions >= j (first position on ties: Eigen partialPivLu,
+// DH/Simulation.cpp:1178, and lu_factor_solve<true>), exchanges the two positions and eliminates as above.  Same
+// operations on the same numbers as the replicated pivoting solve.  The exchange-free elimination above hands every
+// system that needs a row exchange to the replicated solve -- 16 x 16 in local memory, ~50 K cycles -- and the Newton
+// matrices of the struggling steps (hundreds of iterations at the cap, the environments a kernel waits for) need one
+// in every iteration: 38 % of the time of the slowest tile of TactileInsertion, 22 % of DClaw (profiles/r02_experiments.md).
+// scr: two pivot-row buffers of TS_MAXN + 1, TS_MAXN solution slots, two magnitude buffers of TS_MAXN.
+template <class Tile>
+HD void lu_rows_solve_pivot(const Tile& tl, double* a, double b, double* x, double* scr) {
+  double* xs = scr + 2 * (TS_MAXN + 1);
+  double* mag = xs + TS_MAXN;
+  const bool row = tl.lane < TS_MAXN;
+  int pos = tl.lane;
+#pragma unroll
+  for (int j = 0; j < TS_MAXN; ++j) {
+    double* pr = scr + (j & 1) * (TS_MAXN + 1);
+    double* mg = mag + (j & 1) * TS_MAXN;
+    if (row && pos >= j) mg[pos] = fabs(a[j]);
+    tl.tile_sync();
+    int p = j;
+    double best = mg[j];
+#pragma unroll
+    for (int i = j + 1; i < TS_MAXN; ++i) {
+      const double v = mg[i];
+      if (v > best) { best = v; p = i; }
+    }
+    if (pos == p) pos = j;
+    else if (pos == j) pos = p;
+    if (row && pos == j) {
+#pragma unroll
+      for (int c = j; c < TS_MAXN; ++c) pr[c] = a[c];
+      pr[TS_MAXN] = b;
+    }
+    tl.tile_sync();
+    const double pjj = pr[j];
+    const bool below = pos > j;
+    const double l = a[j] / pjj;
+#pragma unroll
+    for (int c = j + 1; c < TS_MAXN; ++c) {
+      const double pjc = pr[c];
+      if (below) a[c] -= l * pjc;
+    }
+    const double bj = pr[TS_MAXN];
+    if (below) b -= l * bj;
+  }
+#pragma unroll
+  for (int k = TS_MAXN - 1; k >= 0; --k) {
+    if (row && pos == k) xs[k] = b / a[k];
+    tl.tile_sync();
+    const double xk = xs[k];
+    x[k] = xk;
+    if (pos < k) b -= a[k] * xk;
+  }
+}
+#endif
 #ifndef TS_LU_SMEM
 #define TS_LU_SMEM 1
 #endif
@@ -2140,7 +2198,11 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     for (int c = 0; c < TS_MAXN; ++c) a[c] = (tl.lane < TS_MAXN) ? Hs[tl.lane * TS_MAXN + c] : 0.0;
     double bsel = 0.0;
     for (int i = 0; i < TS_MAXN; ++i) if (i == tl.lane && i < n) bsel = -ge[i];
-#if TS_LU_SMEM
+#if TS_LU_SMEM && TS_MAXN > 8 && !defined(TS_NO_LU_PIVOT)
+    tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
+    lu_rows_solve_pivot(tl, a, bsel, dx, Hs);
+    solved = true;
+#elif TS_LU_SMEM
     tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
     solved = !lu_rows_solve_smem(tl, a, bsel, dx, Hs);
 #else
@@ -2609,7 +2671,12 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
     double a[TS_MAXN];
     for (int c = 0; c < TS_MAXN; ++c)
       a[c] = (tl.lane < n && c < n) ? tape[c * n + tl.lane] : ((c == tl.lane) ? 1.0 : 0.0);
-#if TS_LU_SMEM
+#if TS_LU_SMEM && TS_MAXN > 8 && !defined(TS_NO_LU_PIVOT)
+    tl.tile_sync();
+    lu_rows_solve_pivot(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
+    solved = true;
+    tl.tile_sync();
+#elif TS_LU_SMEM
     tl.tile_sync();
     solved = !lu_rows_solve_smem(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
     tl.tile_sync();
