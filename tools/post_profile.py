@@ -18,7 +18,11 @@ NT = 224 // LANES
 nthreads = ((B * LANES + 223) // 224) * 224
 prof = torch.zeros((nthreads, 16), dtype=torch.int64, device=dev)
 getattr(sim.lib, "tsim_debug_set_prof_v%d" % (8 if LANES == 8 else 16))(ctypes.c_void_p(prof.data_ptr()))
-if LANES == 8:
+if os.environ.get("PWORK"):          # the inputs of a bench workload (bench.workload_inputs)
+    import bench
+    q0, qd0, u, goal = bench.workload_inputs(os.environ["PWORK"], g, B, T, 1234)
+    ut = torch.tensor(u, device=dev)
+elif LANES == 8:
     q0, qd0, u, goal = make_inputs(g["q0"], B, T, 1234)
     ut = torch.tensor(u, device=dev)
 else:
