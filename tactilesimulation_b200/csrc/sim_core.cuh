@@ -1730,16 +1730,16 @@ HD bool lu_rows_solve_smem(const Tile& tl, double* a, double b, double* x, doubl
   return tl.ballot(exch) != 0u;
 }
 
-// Row-owner elimination WITH partial pivoting (16-dof variants: every solve; variant 8: the solves whose exchange-free
-// elimination above reports that a row exchange is needed): the rows stay in their lanes and carry their current
+// Row-owner elimination WITH partial pivoting (what the kernels run): the rows stay in their lanes and carry their current
 // position; step j takes the row of maximal |a_j| among the positions >= j (first position on ties: Eigen partialPivLu,
 // DH/Simulation.cpp:1178, and lu_factor_solve<true>), exchanges the two positions and eliminates as above.  Same
 // operations on the same numbers as the replicated pivoting solve.  The exchange-free elimination above hands every
 // system that needs a row exchange to the replicated solve -- 16 x 16 in local memory, ~50 K cycles -- and the Newton
 // matrices of the struggling steps (hundreds of iterations at the cap, the environments a kernel waits for) need one
 // in every iteration: 38 % of the time of the slowest tile of TactileInsertion, 22 % of DClaw (profiles/r02_experiments.md).
-// TactilePush needs an exchange in few solves, but in a lock-step block one tile in the replicated 8 x 8 solve holds up
-// the round of all 28: forward call 75.6 -> 69.2 ms, adjoint call 11.6 -> 9.6 ms at B = 4096, T = 200.
+// TactilePush needs an exchange in fewer solves, but in a lock-step block one tile in the replicated 8 x 8 solve holds up
+// the round of all 28: forward call 75.6 -> 68.0 ms, adjoint call 11.6 -> 8.7 ms at B = 4096, T = 200 (exchange-free
+// attempt first, pivoting on demand: 69.2 / 9.6 ms).
 // scr: two pivot-row buffers of TS_MAXN + 1, TS_MAXN solution slots, two magnitude buffers of TS_MAXN.
 template <class Tile>
 HD void lu_rows_solve_pivot(const Tile& tl, double* a, double b, double* x, double* scr) {
@@ -2199,25 +2199,10 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
     for (int c = 0; c < TS_MAXN; ++c) a[c] = (tl.lane < TS_MAXN) ? Hs[tl.lane * TS_MAXN + c] : 0.0;
     double bsel = 0.0;
     for (int i = 0; i < TS_MAXN; ++i) if (i == tl.lane && i < n) bsel = -ge[i];
-#if TS_LU_SMEM && TS_MAXN > 8 && !defined(TS_NO_LU_PIVOT)
+#if TS_LU_SMEM && !defined(TS_NO_LU_PIVOT)
     tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
     lu_rows_solve_pivot(tl, a, bsel, dx, Hs);
     solved = true;
-#elif TS_LU_SMEM && !defined(TS_NO_LU_PIVOT)
-    // variant 8: the exchange-free elimination first (TactilePush's matrices rarely need an exchange); when one is
-    // needed, the rows are fetched again and the pivoting row-owner elimination runs, not the replicated solve
-    tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
-    solved = !lu_rows_solve_smem(tl, a, bsel, dx, Hs);
-    if (!solved) {
-      tl.tile_sync();
-      if (tl.lane < TS_MAXN)
-        for (int i = 0; i < TS_MAXN; ++i) Hs[i * TS_MAXN + tl.lane] = (i < n && tl.lane < n) ? cole[0][i] : ((i == tl.lane) ? 1.0 : 0.0);
-      tl.tile_sync();
-      for (int c = 0; c < TS_MAXN; ++c) a[c] = (tl.lane < TS_MAXN) ? Hs[tl.lane * TS_MAXN + c] : 0.0;
-      tl.tile_sync();
-      lu_rows_solve_pivot(tl, a, bsel, dx, Hs);
-      solved = true;
-    }
 #elif TS_LU_SMEM
     tl.tile_sync();                      // every lane has its row: the scratch is free for the pivot rows
     solved = !lu_rows_solve_smem(tl, a, bsel, dx, Hs);
@@ -2687,22 +2672,11 @@ HDN void step_backward(const Tile& tl, const SceneView& S, const double* uk, con
     double a[TS_MAXN];
     for (int c = 0; c < TS_MAXN; ++c)
       a[c] = (tl.lane < n && c < n) ? tape[c * n + tl.lane] : ((c == tl.lane) ? 1.0 : 0.0);
-#if TS_LU_SMEM && TS_MAXN > 8 && !defined(TS_NO_LU_PIVOT)
+#if TS_LU_SMEM && !defined(TS_NO_LU_PIVOT)
     tl.tile_sync();
     lu_rows_solve_pivot(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
     solved = true;
     tl.tile_sync();
-#elif TS_LU_SMEM && !defined(TS_NO_LU_PIVOT)
-    tl.tile_sync();
-    solved = !lu_rows_solve_smem(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
-    tl.tile_sync();
-    if (!solved) {
-      for (int c = 0; c < TS_MAXN; ++c)
-        a[c] = (tl.lane < n && c < n) ? tape[c * n + tl.lane] : ((c == tl.lane) ? 1.0 : 0.0);
-      lu_rows_solve_pivot(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
-      solved = true;
-      tl.tile_sync();
-    }
 #elif TS_LU_SMEM
     tl.tile_sync();
     solved = !lu_rows_solve_smem(tl, a, (tl.lane < n) ? y[0] : 0.0, z, WD.scratch());
