@@ -141,6 +141,12 @@ int tsim_scene_kernel_times(const tsim_scene* scene, double* ms /* [TSIM_N_KERNE
 int tsim_debug_fp64_peak(int device, double* out /* [4] */);
 const char* tsim_debug_last_error(void);
 
+/* Test aid: the n x n solves of the Newton iteration and of the adjoint sweep (row-owner elimination with partial
+ * pivoting, csrc/sim_core.cuh lu_rows_solve_pivot; the reference: Eigen partialPivLu, DH/Simulation.cpp:1178, :1640) on
+ * `nsys` given systems.  n = 8 or 16 (the dof capacities of the kernel variants; smaller systems are padded with the
+ * identity by the caller, as the kernels do).  HOST buffers: A [nsys][n][n] row-major, b [nsys][n], x [nsys][n] out. */
+int tsim_debug_lu_solve(int n, int device, int nsys, const double* A, const double* b, double* x);
+
 /* Readouts at a given state (no stepping). Any output may be NULL. */
 int tsim_readout(const tsim_scene* scene, int32_t B, const double* q, const double* qd, double* var_out,
                  double* tac_out, int32_t* marker_body, uint32_t* contact_masks, void* stream);

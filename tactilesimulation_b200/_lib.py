@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(HERE, "libtactilesim_
 SYMBOLS = ["tsim_last_error", "tsim_scene_create", "tsim_scene_destroy", "tsim_scene_sizes", "tsim_scene_set_lanes", "tsim_scene_set_option",
            "tsim_scene_set_env_scenes",
            "tsim_forward", "tsim_forward_multistep", "tsim_scene_kernel_times", "tsim_readout", "tsim_backward",
-           "tsim_debug_fp64_peak", "tsim_debug_last_error"]
+           "tsim_debug_fp64_peak", "tsim_debug_last_error", "tsim_debug_lu_solve"]
 KERNELS = ("fwd_kernel", "tape_kernel", "tac_kernel", "vjp_kernel", "bwd_kernel")
 (NJ, NDOF_R, NDOF_M, NDOF_U, NDOF_VAR, NDOF_TACTILE, N_MARKERS, TAPE_DOUBLES, CMASK_WORDS, INTEGRATOR, N_SIZES) = range(11)
 INT_BDF1, INT_BDF2, INT_SDIRK2 = 0, 1, 2
@@ -49,6 +49,7 @@ def load():
     lib.tsim_backward.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tsim_debug_fp64_peak.argtypes = [ctypes.c_int, vp]
     lib.tsim_debug_last_error.restype = ctypes.c_char_p
+    lib.tsim_debug_lu_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -61,6 +62,21 @@ def fp64_peak(device: int = 0):
     if lib.tsim_debug_fp64_peak(int(device), out.ctypes.data) != 0:
         raise TactileSimError(lib.tsim_debug_last_error().decode("utf-8", "replace"))
     return dict(gflops=float(out[0]), ms=float(out[1]), sms=int(out[2]), sm_mhz=float(out[3]))
+
+
+def lu_solve(A, b, device: int = 0):
+    """The kernels' n x n solve (row-owner elimination with partial pivoting) on a batch of systems: A [nsys, n, n],
+    b [nsys, n] with n = 8 or 16 -> x [nsys, n].  Test aid, tsim_debug_lu_solve."""
+    import numpy as np
+    lib = load()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    nsys, n = b.shape
+    if A.shape != (nsys, n, n):
+        raise ValueError("A must be [nsys, n, n] for b [nsys, n]")
+    x = np.zeros_like(b)
+    check(lib.tsim_debug_lu_solve(int(n), int(device), int(nsys), A.ctypes.data, b.ctypes.data, x.ctypes.data), lib)
+    return x
 
 
 def check(rc, lib):

@@ -24,6 +24,7 @@
                                   const double*, int64_t, double*, double*, double*, const int32_t*, double*,        \
                                   const int32_t*, double*, int32_t*, uint32_t*, int32_t*, void*);                     \
   int tsim_scene_kernel_times_v##V(const void*, double*);                                                             \
+  int tsim_variant_lu_solve_v##V(int, int, const double*, const double*, double*);                                    \
   int tsim_readout_v##V(const void*, int32_t, const double*, const double*, double*, double*, int32_t*, uint32_t*,    \
                         void*);                                                                                       \
   int tsim_backward_v##V(const void*, int32_t, int32_t, const double*, const double*, const double*, int64_t,        \
@@ -138,6 +139,12 @@ int tsim_scene_kernel_times(const tsim_scene* s, double* ms) {
   if (!s) return own_fail("tsim_scene_kernel_times: null scene");
   return DISPATCH(s, tsim_scene_kernel_times_v8(s->inner, ms), tsim_scene_kernel_times_v16(s->inner, ms),
                   tsim_scene_kernel_times_v17(s->inner, ms));
+}
+
+int tsim_debug_lu_solve(int n, int device, int nsys, const double* A, const double* b, double* x) {
+  if (n == 8) return fwd_rc(tsim_variant_lu_solve_v8(device, nsys, A, b, x), 8);
+  if (n == 16) return fwd_rc(tsim_variant_lu_solve_v16(device, nsys, A, b, x), 16);
+  return own_fail("tsim_debug_lu_solve: n must be 8 or 16 (the dof capacities of the kernel variants)");
 }
 
 int tsim_readout(const tsim_scene* s, int32_t B, const double* q, const double* qd, double* var_out, double* tac_out,

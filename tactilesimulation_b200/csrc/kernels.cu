@@ -59,6 +59,7 @@
 #define tsim_readout TSV(tsim_readout)
 #define tsim_backward TSV(tsim_backward)
 #define tsim_debug_set_prof TSV(tsim_debug_set_prof)
+#define tsim_variant_lu_solve TSV(tsim_variant_lu_solve)
 #define tsim_scene_kernel_times TSV(tsim_scene_kernel_times)
 // Everything below lives in a per-variant namespace: the two variants instantiate templates and kernels
 // with identical signatures but different capacities, and must not share symbols.
@@ -543,7 +544,43 @@ static int prep(K kern, size_t smem, int bps = TS_BPS) {
   if (pe && B != s->env_B) return fail(NAME ": the handle holds per-environment parameters for another batch size"); \
   if (pe && s->lanes != TS_MAXN) return fail(NAME ": per-environment parameters need the default lanes per environment");
 
+// Test aid (tsim_debug_lu_solve): the row-owner elimination with partial pivoting of the Newton / adjoint solves on
+// given systems of the variant's capacity, one tile per system.
+template <int LPE>
+__global__ void lu_debug_kernel(const double* A, const double* b, double* x, int nsys) {
+  __shared__ double scr[32 / LPE][TS_MAXN * TS_MAXN];
+  DevTile<LPE> tl = make_tile<LPE>();
+  const int sys = blockIdx.x * (32 / LPE) + threadIdx.x / LPE;
+  const int s = sys < nsys ? sys : nsys - 1;
+  double a[TS_MAXN], xs[TS_MAXN];
+  for (int c = 0; c < TS_MAXN; ++c) a[c] = tl.lane < TS_MAXN ? A[((long long)s * TS_MAXN + tl.lane) * TS_MAXN + c] : 0.0;
+  const double bb = tl.lane < TS_MAXN ? b[(long long)s * TS_MAXN + tl.lane] : 0.0;
+  lu_rows_solve_pivot(tl, a, bb, xs, scr[threadIdx.x / LPE]);
+  if (sys < nsys && tl.lane == 0) for (int i = 0; i < TS_MAXN; ++i) x[(long long)s * TS_MAXN + i] = xs[i];
+}
+
 extern "C" {
+
+int tsim_variant_lu_solve(int device, int nsys, const double* A, const double* b, double* x) {
+  if (!A || !b || !x || nsys < 1) return fail("tsim_debug_lu_solve: bad argument");
+  const size_t na = (size_t)nsys * TS_MAXN * TS_MAXN * sizeof(double), nb = (size_t)nsys * TS_MAXN * sizeof(double);
+  double *dA = 0, *db = 0, *dx = 0;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&dA, na);
+  if (e == cudaSuccess) e = cudaMalloc(&db, nb);
+  if (e == cudaSuccess) e = cudaMalloc(&dx, nb);
+  if (e == cudaSuccess) e = cudaMemcpy(dA, A, na, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int per = 32 / TS_MAXN;
+    lu_debug_kernel<TS_MAXN><<<(nsys + per - 1) / per, 32>>>(dA, db, dx, nsys);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(x, dx, nb, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(db); cudaFree(dx);
+  if (e != cudaSuccess) return fail(std::string("tsim_debug_lu_solve: ") + cudaGetErrorString(e));
+  return 0;
+}
 
 #ifdef TS_PROFILE
 int tsim_debug_set_prof(void* p) { return cudaMemcpyToSymbol(g_prof, &p, sizeof(p)) != cudaSuccess; }
