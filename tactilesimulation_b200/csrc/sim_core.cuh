@@ -2088,8 +2088,12 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   // more): the search starts with the batched evaluation of the step lengths instead of two sequential trials -- the
   // same accepted step length and evaluation counts, one or two rounds fewer per iteration of the steps that run into
   // hundreds of iterations (and decide the duration of a kernel whose blocks end with their slowest environment).
+  // Threshold, measured on B200 with the pivoting row-owner LU in place (forward call): TactilePush (variant 8) 3 / 4 / 6 /
+  // 8 / 12 / 16 / 24 / 40 iterations: 78.8 / 73.0 / 67.9 / 65.7 / 65.5 / 65.9 / 65.9 / 65.5 ms; the 16-dof scenes are
+  // best at 6 (3 / 4 / 6 / 10: DClaw 557 / 543 / 535 / 548 ms, TactileInsertion 385 / 389 / 394 / 400 ms, StableGrasp 859 /
+  // 856 / 862 / 875 ms).
 #ifndef TS_LS_EAGER
-#define TS_LS_EAGER 6
+#define TS_LS_EAGER (TS_MAXN > 8 ? 6 : 12)
 #endif
   bool eager = false;
   for (;;) {
@@ -2110,13 +2114,20 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
       if (!eager) {
         ++v.trial;
         v.alpha *= 0.5;
-        if (v.trial < S.max_ls && !(L >= TS_MAXN && v.batch_ls && v.trial >= 2)) {
+        // (sequential trials before the batch, measured on B200 with the pivoting row-owner LU in place, forward call:
+        // TactilePush 1 / 2 / 3 / 4 / 5 / 8 / 20 trials: 70.2 / 65.1 / 63.0 / 62.4 / 62.3 / 62.6 / 62.3 ms -- a value-only
+        // pass in one tile holds up the round of its lock-step block; the 16-dof scenes stay at 2: DClaw 542 / 536 / 536 ms,
+        // TactileInsertion 387 / 392 / 394 ms, StableGrasp 861 / 863 / 868 ms for 1 / 2 / 3)
+#ifndef TS_LS_BATCH_AFTER
+#define TS_LS_BATCH_AFTER (TS_MAXN > 8 ? 2 : 4)
+#endif
+        if (v.trial < S.max_ls && !(L >= TS_MAXN && v.batch_ls && v.trial >= TS_LS_BATCH_AFTER)) {
           for (int i = 0; i < n; ++i) ts.xn[i] = ts.x[i] + v.alpha * ts.dx[i];
           return false;
         }
       }
       if (v.trial < S.max_ls) {
-        // Two trials already failed: a struggling line search (up to max_ls = 20 trials per iteration,
+        // TS_LS_BATCH_AFTER trials already failed: a struggling line search (up to max_ls = 20 trials per iteration,
         // DH/Simulation.cpp:1186-1200) would serialise the whole block behind this tile.  The lanes of the
         // tile evaluate the next LPE step lengths at once (value only); the first one, in the reference's
         // order, that reduces ||g|| is then evaluated with its Jacobian by the normal path, which also
