@@ -4,7 +4,7 @@
 // tile per environment for all T steps of a call (the tile-uniform state lives in shared memory, the
 // scene tables are staged once per CTA in shared memory).  Lane k of a tile owns reduced
 // coordinate k: it carries the Dual tangent along q_k through the matrix-free residual, holds
-// column k / row k of the Newton matrix for the shuffle-based LU, and strides over tactile
+// column k / row k of the Newton matrix for the row-owner LU with partial pivoting, and strides over tactile
 // markers / contact points in the readout and adjoint passes.  See sim_core.cuh.
 //
 // A forward call is three kernels and a backward call three launches: only what is sequential per environment (the

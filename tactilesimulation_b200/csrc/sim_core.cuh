@@ -1542,11 +1542,11 @@ struct HostTile {
 // in registers with compile-time indices: no cross-lane traffic inside the elimination, and the
 // solution comes out replicated, which is how the Newton update needs it.
 // PIVOT=false is the same elimination without row exchanges; it reports whether partial pivoting
-// would have exchanged any row (then the caller redoes the solve with PIVOT=true).  Newton matrices
-// H = M - h^2 K - h D are mass dominated, so the exchange-free pass almost always stands.
+// would have exchanged any row (then the caller redoes the solve with PIVOT=true).
+// The GPU kernels do NOT run this any more (tiles with one lane per row: lu_rows_solve_pivot below); it serves tiles
+// with fewer lanes than dofs -- the host harness of the CPU tests -- and the A/B builds with -DTS_NO_LU_PIVOT.
 #if TS_MAXN > 8
-// 16-dof variant: the replicated solve is only the rare fallback of lu_rows_solve (and the host harness):
-// plain loops, the matrix lives in local memory
+// 16-dof variant: plain loops, the matrix lives in local memory
 template <bool PIVOT>
 HDN bool lu_factor_solve(double (*A)[TS_MAXN], double* b) {
   bool exchanged = false;
@@ -1663,7 +1663,8 @@ HDN void lu_solve(const Tile& tl, double (*col)[TS_MAXN], double* rhs, int n) {
 // b_i; pivot rows travel by shuffles, the solution comes out replicated in x.  Same operations on the
 // same numbers as lu_factor_solve<false> (no row exchanges), at 1/8 of the per-lane work and without
 // the 8x8 register copy.  Returns true (tile-wide) when partial pivoting would have exchanged a row:
-// the caller then runs the replicated pivoting solve instead.
+// the caller then runs the replicated pivoting solve instead.  (Round-1 / early round-2 path, kept for the A/B builds
+// -DTS_NO_LU_PIVOT [-DTS_LU_SMEM=0]: the kernels run lu_rows_solve_pivot.)
 template <class Tile>
 HD bool lu_rows_solve(const Tile& tl, double* a, double b, double* x) {
   bool exch = false;
