@@ -81,6 +81,13 @@ struct DevTile {
   unsigned mask;
   void* coop;                          // CoopArea<LPE> of the block (shared memory), COOP only
   int tile_id;                         // tile index inside the block
+  // block-wide line-search service (sim_core.cuh, ls_service_round): tiles with one lane per row, outside the
+  // cooperative step loop; the tile states of the block's tiles (shared memory) are ts_stride doubles apart from ts0
+  static const int NTILES = TS_BLOCK / LPE_;
+  static const bool LS_SERVICE = TS_LS_SERVICE && LPE_ >= TS_MAXN && !COOP_;
+  double* ts0;
+  int ts_stride;
+  __device__ __forceinline__ TileState* peer_state(int r) const { return (TileState*)(ts0 + (size_t)r * ts_stride); }
   // block-wide barriers that the lanes of a warp may reach diverged (tiles run independent control flow)
   __device__ __forceinline__ void cta_sync_unaligned() const { asm volatile("barrier.sync 0;" ::: "memory"); }
   __device__ __forceinline__ bool cta_or_unaligned(bool p) const {
@@ -258,6 +265,8 @@ template <int SUBL> struct SubTileOf {
     t.mask = (SUBL == 32) ? 0xffffffffu : (((1u << SUBL) - 1u) << (wl - t.lane));
     t.coop = 0;
     t.tile_id = 0;
+    t.ts0 = 0;
+    t.ts_stride = 0;
     return t;
   }
 };
@@ -274,6 +283,8 @@ __device__ __forceinline__ DevTile<LPE, COOP> make_tile() {
   tl.mask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (wl - tl.lane));
   tl.coop = 0;
   tl.tile_id = threadIdx.x / LPE;
+  tl.ts0 = 0;
+  tl.ts_stride = 0;
   return tl;
 }
 // cooperative step loop: one lane per reduced coordinate (one evaluation per round), 8-lane tiles
@@ -306,6 +317,8 @@ __global__ void __launch_bounds__(TS_BLOCK, TS_BPS) fwd_kernel(const int* ib, in
   bind_work<LPE>(WD, S, ni, nd, smem);
   // the cooperative area follows the tile regions
   tl.coop = smem + ((scene_bytes(ni, nd) + (size_t)(TS_BLOCK / LPE) * tile_region_doubles(S.nj) * sizeof(double) + 15) & ~(size_t)15);
+  tl.ts0 = (double*)(smem + scene_bytes(ni, nd)) + S.nj * WK_REC;       // tile states of the block (bind_work)
+  tl.ts_stride = tile_region_doubles(S.nj);
 #ifdef TS_PROFILE
   for (int i = 0; i < 16; ++i) tl.acc[i] = 0;
   const long long t_begin = clock64();

@@ -98,6 +98,13 @@ HD void st_stream(int* p, int v) {
 }
 
 #define TS_MAXJ KT_MAXJ
+// Block-wide line-search service (ls_service_round below): 1 = the batched step lengths of a struggling line search are
+// evaluated by lanes spread over all warps of the block instead of by the sixteen neighbouring lanes of the searching
+// tile (16-dof variants; TactilePush hardly batches any more, and its step loop has its own block-wide phase).
+#ifndef TS_LS_SERVICE
+#define TS_LS_SERVICE (KT_MAXN > 8)
+#endif
+#define TS_LS_CAP 24          // step lengths per request (the reference's default line-search cap is 20)
 #define TS_MAXN KT_MAXN
 #define TS_MAXU KT_MAXU
 #define TS_MAXCAND KT_MAXCAND
@@ -215,6 +222,13 @@ struct TileState {
 #if KT_MULTISTEP
   double pq[TS_MAXN], pqd[TS_MAXN];                // second state of the two-state formulas: BDF2 (q, qd) one step back,
                                                    // SDIRK2 second stage (q_alpha, qd_alpha)
+#endif
+#if TS_LS_SERVICE
+  // request of this tile to the block's line-search service (ls_service_round): ||g(x + 2^-i alpha0 dx)||, i < ls_n
+  double lsn[TS_LS_CAP];                           // answers (HUGE_VAL = not evaluated)
+  double ls_alpha0, ls_gnorm;                      // first step length, the norm a trial has to beat
+  const double* ls_db;                             // double table of the requester's scene view (per-environment parameters)
+  int ls_req, ls_n, ls_mode, ls_found;             // request pending, step lengths asked for, implicit stage, one accepted
 #endif
 };
 
@@ -1509,6 +1523,7 @@ HDN void eval_g(const Tile& tl, const SceneView& S, const In& in, const double* 
 struct HostTile {
   static const int LPE = 1;
   static const bool COOP = false;
+  static const bool LS_SERVICE = false;
   int lane;
 #ifdef TS_PROFILE
   mutable long long acc[16];
@@ -2007,6 +2022,7 @@ struct StepVars {
   int cap_newton;
   int mode;                 // TS_ST_*: implicit stage in flight
   bool defer_g0;            // the G0 / G1 blocks of the tape are written by the pass of their own (env_tape), not by phase 3
+  bool ls_pending, ls_fresh; // a request to the line-search service is out (step_post resumes behind it); `fresh` across it
 };
 
 HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
@@ -2022,6 +2038,7 @@ HD void step_begin(const SceneView& S, StepVars& v, TileState& ts) {
   }
   v.phase = 0; v.fail_strike = 0; v.iters = 0; v.ls = 0; v.trial = 0;
   v.alpha = 1.0; v.gnorm = 0.0; v.converged = false;
+  v.ls_pending = false; v.ls_fresh = false;
 }
 
 // One round = ONE residual evaluation (with Jacobian columns) plus the bookkeeping that follows it.
@@ -2097,6 +2114,12 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
 #define TS_LS_EAGER (TS_MAXN > 8 ? 6 : 12)
 #endif
   bool eager = false;
+#if TS_LS_SERVICE
+  // second call of a round: the answers of the line-search service are in the tile state, the search resumes at its
+  // batched evaluation ((ge, cole) are still those of the first call: same round, same scope)
+  const bool resume = Tile::LS_SERVICE && v.ls_pending;
+  if (resume) { eager = true; fresh = v.ls_fresh; v.ls_pending = false; }
+#endif
   for (;;) {
   if (v.phase == 1) {
     double gnn = 0.0;
@@ -2139,6 +2162,31 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
 #define TS_LS_SUB 1
 #endif
         const int NBMAX = L / TS_LS_SUB > 0 ? L / TS_LS_SUB : 1;     // step lengths evaluated at once
+#if TS_LS_SERVICE
+        if (Tile::LS_SERVICE && (resume || S.max_ls - v.trial <= TS_LS_CAP)) {
+          const int nal = S.max_ls - v.trial;
+          if (!resume) {
+            // hand the step lengths to the block (env_forward runs ls_service behind this call, then calls again)
+            for (int i = tl.lane; i < nal; i += L) ts.lsn[i] = HUGE_VAL;
+            if (tl.lane == 0) {
+              ts.ls_alpha0 = v.alpha; ts.ls_gnorm = v.gnorm; ts.ls_db = S.db;
+              ts.ls_n = nal; ts.ls_mode = v.mode; ts.ls_found = 0; ts.ls_req = 1;
+            }
+            v.ls_pending = true; v.ls_fresh = fresh;
+            return false;
+          }
+          int k = -1;
+          for (int i = nal - 1; i >= 0; --i) if (ts.lsn[i] < v.gnorm) k = i;      // first accepted, in the reference's order
+          const int adv = k >= 0 ? k : nal;
+          v.trial += adv;
+          v.ls += adv;
+          for (int i = 0; i < adv; ++i) v.alpha *= 0.5;
+          found = k >= 0;
+          if (!found) gnn = ts.lsn[nal - 1];
+          tl.tile_sync();
+          if (tl.lane == 0) ts.ls_req = 0;
+        } else
+#endif
         while (v.trial < S.max_ls) {
           const int left = S.max_ls - v.trial;
           const int nb = left < NBMAX ? left : NBMAX;
@@ -2235,6 +2283,66 @@ HD bool step_post(const Tile& tl, const SceneView& S, StepVars& v, double* tape,
   tl.tile_sync();                      // dx is in place for the value-only trials of every lane
   eager = true;
   }   // for (;;): second pass = the search of a struggling step, batched from its first trial
+}
+
+
+// ---- block-wide line-search service (TS_LS_SERVICE, the kernels whose tile policy sets LS_SERVICE)
+// A struggling line search asks for ||g|| at up to max_ls = 20 step lengths per Newton iteration, hundreds of iterations
+// per step, and the kernels of the 16-dof scenes end with ONE such environment (profiles/r02_experiments.md).  The
+// in-tile batch (step_post) gives every step length to one lane of the searching tile: sixteen neighbouring lanes of one
+// warp, each with its own contact set, walking through the value-only evaluation under divergence.  Here the requests
+// of a round are served by the block instead: item (step length i, request j) = number k = i R + j (R requests, lower
+// step-length indices first) goes to lane k / NW of warp k % NW (NW warps) -- still one lane per step length, with its
+// joint records in local memory (16 to 20 evaluating lanes: the footprint that fits L1), but two or three of them per
+// warp instead of sixteen.  The norms come back through the requester's tile state; step_post picks the first
+// accepted one in the reference's order, so the accepted step length and the evaluation counts are those of the
+// sequential search (DH/Simulation.cpp:1186-1200).  Forward call, B200: DClaw 534 -> 500 ms, TactileInsertion 406 ->
+// 371 ms, StableGrasp 866 -> 805 ms.  (Sub-tiles of 8 lanes sharing the contact detection of a step length, with
+// their joint records in local or in shared memory, lost: tools/experiments/line_search_service.patch.)
+template <bool ON> struct LsTag {};
+template <class Tile>
+HD bool ls_service_round(const Tile&, const SceneView&, bool, LsTag<false>) { return false; }
+template <class Tile>
+HDN bool ls_service_round(const Tile& tl, const SceneView& S, bool pending, LsTag<true>) {
+#if TS_LS_SERVICE && defined(__CUDACC__)          // (device tiles only: the host harness never instantiates it)
+  if (!tl.cta_or_unaligned(pending)) return false;
+  const int NT = Tile::NTILES, NW = TS_BLOCK / 32;
+  unsigned reqmask = 0, found = 0;
+  int R = 0, maxn = 0;
+  for (int r = 0; r < NT; ++r) {
+    const TileState* rts = tl.peer_state(r);
+    if (rts->ls_req) { reqmask |= 1u << r; ++R; maxn = rts->ls_n > maxn ? rts->ls_n : maxn; }
+  }
+  const int items = maxn * R;
+  // item k goes to lane k / NW of warp k % NW: the step lengths of a search are evaluated by ONE lane each, as in the
+  // in-tile batch, but spread over the warps of the block instead of sixteen neighbouring lanes of one warp
+  const int mine = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
+  for (int base = 0; base < items; base += TS_BLOCK) {
+    const int k = base + mine;
+    if (k < items) {
+      const int i = k / R;
+      int j = k % R, r = 0;
+      for (unsigned m = reqmask;; m &= m - 1, --j) if (j == 0) { r = ts_ffs(m); break; }
+      TileState* rts = tl.peer_state(r);
+      if (i < rts->ls_n && !((found >> r) & 1u)) {
+        double al = rts->ls_alpha0;
+        for (int q = 0; q < i; ++q) al *= 0.5;
+        SceneView Sl = S;
+        Sl.db = rts->ls_db;
+        const double nrm = trial_norm(HostTile(), Sl, *rts, al, rts->ls_mode);
+        rts->lsn[i] = nrm;
+        if (nrm < rts->ls_gnorm) rts->ls_found = 1;
+      }
+    }
+    tl.cta_sync_unaligned();           // the answers of this pass are in place
+    for (int r = 0; r < NT; ++r) if (((reqmask >> r) & 1u) && tl.peer_state(r)->ls_found) found |= 1u << r;
+    if (found == reqmask) break;       // (block-uniform) every search has its step length
+    if (base + TS_BLOCK < items) tl.cta_sync_unaligned();   // flags read before the next pass writes them
+  }
+  return true;
+#else
+  return false;
+#endif
 }
 
 
@@ -2863,6 +2971,10 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
   TileState& ts = WD.state();            // tile-uniform step state (shared memory on the GPU)
   for (int i = 0; i < TS_MAXN; ++i) { ts.q[i] = (i < n) ? a.q[(long long)env * n + i] : 0.0; ts.qd[i] = (i < n) ? a.qd[(long long)env * n + i] : 0.0; }
   StepVars v;
+#if TS_LS_SERVICE
+  if (tl.lane == 0) { ts.ls_req = 0; ts.ls_found = 0; }      // (the first vote of the round loop orders it for the block)
+#endif
+  v.ls_pending = false; v.ls_fresh = false;
   v.batch_ls = a.ls_batch != 0;
   v.cap_newton = a.max_newton;
   v.mode = TS_ST_BDF1;
@@ -2917,6 +3029,16 @@ HDN void env_forward(const Tile& tl, const SceneView& S, const FwdArgs& a, int e
           const long long es0 = (long long)t * B + env;
           tile_done = step_post(tl, S, v, a.tape ? a.tape + es0 * S.ntape : (double*)0, WD, cole);
           heavy = WD.gp_any != 0;
+        }
+        if (Tile::LS_SERVICE) {
+          // requests of this round to the line-search service: the whole block serves them, the requesters resume
+          TS_CPT0();
+          const bool pending = run && v.ls_pending;
+          if (ls_service_round(tl, S, pending, LsTag<Tile::LS_SERVICE>()) && pending) {
+            const long long es0 = (long long)t * B + env;
+            tile_done = step_post(tl, S, v, a.tape ? a.tape + es0 * S.ntape : (double*)0, WD, cole);
+          }
+          TS_CPT(tl, 14);
         }
         TS_TOC2(tl, 5);
       }
